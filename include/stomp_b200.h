@@ -1,0 +1,255 @@
+/*
+ * stomp_b200.h — C ABI of the B200-native STOMP rollout engine.
+ *
+ * This is the drop-in boundary for the per-iteration rollout loop of
+ * kalakris/stomp_motion_planner_icra2011.  Every entry point names the
+ * reference interface it replaces (paths relative to
+ * stomp_motion_planner/ in the reference tree).  Plain pointers and sizes
+ * only; the caller owns every host buffer, the engine owns device memory.
+ *
+ * Conventions
+ *   D  = joints in the planning group   (num_dimensions)
+ *   N  = free trajectory points         (num_time_steps; params == timesteps)
+ *   R  = rollouts per iteration         (num_rollouts)
+ *   K  = collision spheres of the group
+ *   B  = independent planning problems held by one engine (reference: 1)
+ *   All host arrays are C-contiguous fp64 with the LAST index fastest:
+ *   theta[B][D][N], rollouts[B][R][D][N], costs[B][R][N].
+ *   Every function returns 0 on success, non-zero on failure; the message is
+ *   available from stomp_engine_last_error().  (Reference convention: every
+ *   method returns bool and logs with ROS_ERROR, include/.../assert.h:43-56.)
+ *   A handle is not thread-safe: one handle = one device = one CUDA stream.
+ */
+#ifndef STOMP_B200_H_
+#define STOMP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STOMP_DIFF_RULE_LENGTH 7 /* include/stomp_motion_planner/stomp_utils.h:49 */
+#define STOMP_NUM_DIFF_RULES 3   /* include/stomp_motion_planner/stomp_utils.h:50 */
+
+enum stomp_dtype { STOMP_F64 = 0, STOMP_F32 = 1 };
+enum stomp_sdf_mode { STOMP_SDF_NEAREST = 0, STOMP_SDF_TRILINEAR = 1 };
+enum stomp_voxel_dtype {
+  STOMP_VOXEL_F32 = 0,   /* distance in metres */
+  STOMP_VOXEL_U8_SQ = 1, /* squared cell distance, distance = sqrt(v)*resolution */
+  STOMP_VOXEL_U16_SQ = 2
+};
+enum stomp_joint_type { STOMP_JOINT_FIXED = 0, STOMP_JOINT_REVOLUTE = 1, STOMP_JOINT_PRISMATIC = 2 };
+enum stomp_noise_mode {
+  STOMP_NOISE_PHILOX = 0,  /* engine RNG: eps = sigma * chol(R^-1) * z, z ~ Philox4x32-10 + Box-Muller */
+  STOMP_NOISE_INJECTED = 1 /* host-injection mode: eps supplied by stomp_engine_inject_noise */
+};
+
+/* Scalar configuration.  Replaces the ROS parameters read by
+ * PolicyImprovementLoop::readParameters (src/policy_improvement_loop.cpp:112-123),
+ * StompParameters::initFromNodeHandle (src/stomp_parameters.cpp:50-76) and the
+ * arguments of CovariantTrajectoryPolicy::initialize
+ * (src/covariant_trajectory_policy.cpp:70-90). */
+typedef struct stomp_engine_desc {
+  int32_t num_dimensions;
+  int32_t num_time_steps;
+  int32_t num_rollouts;
+  int32_t num_reused_rollouts;
+  int32_t num_problems;
+  int32_t dtype;                /* stomp_dtype: arithmetic type of the device path */
+  int32_t use_cumulative_costs; /* src/policy_improvement_loop.cpp:121 */
+  int32_t sdf_mode;             /* stomp_sdf_mode; NEAREST is the parity mode */
+  int32_t device;               /* CUDA device ordinal */
+  int32_t rollout_shard_rank;   /* rollout sharding of ONE problem over GPUs (config C3) */
+  int32_t rollout_shard_world;  /* 1 = no sharding */
+  int32_t keep_intermediates;  /* 1: also store the per-rollout parity taps (noise_projected, cumulative
+                                  costs, probabilities) that the fused update never needs in HBM */
+  double movement_duration;     /* policy dt = duration/(N+1), covariant_trajectory_policy.cpp:152 */
+  double discretization;        /* trajectory discretization: FD velocity (stomp_optimizer.cpp:620), StompCost */
+  double derivative_costs[STOMP_NUM_DIFF_RULES]; /* vel, acc, jerk */
+  double ridge_factor;
+  double smoothness_cost_weight; /* == control cost weight, stomp_optimizer.cpp:1178-1182 */
+  double obstacle_cost_weight;
+} stomp_engine_desc;
+
+/* One KDL-tree segment in DFS pre-order (parent index < own index).
+ * Replaces the kdl_parser/KDL::Tree consumed by
+ * KDL::TreeFkSolverJointPosAxisPartial (src/treefksolverjointposaxis_partial.cpp:76-178).
+ * segment.pose(q) = Frame(Rot(axis, q) * rot, pos)          (revolute)
+ *                   Frame(rot, pos + q * axis)              (prismatic)
+ *                   Frame(rot, pos)                         (fixed) */
+typedef struct stomp_segment {
+  int32_t parent;      /* -1 for the root */
+  int32_t joint_type;  /* stomp_joint_type */
+  int32_t group_index; /* [0,D) if the joint belongs to the planning group, else -1 */
+  int32_t reserved0;
+  double rot[9];       /* parent->joint rotation, row-major */
+  double pos[3];       /* parent->joint translation (== KDL JointOrigin) */
+  double axis[3];      /* joint axis in the parent segment frame (== KDL JointAxis) */
+  double fixed_value;  /* joint value when the joint is not in the group (robot start state) */
+} stomp_segment;
+
+/* Replaces StompCollisionPoint (include/stomp_motion_planner/stomp_collision_point.h:76-82). */
+typedef struct stomp_sphere {
+  int32_t segment;
+  int32_t reserved0;
+  double radius;
+  double clearance;
+  double pos[3]; /* centre in the segment frame */
+} stomp_sphere;
+
+/* Replaces StompJoint limits (include/stomp_motion_planner/stomp_robot_model.h:78-90). */
+typedef struct stomp_joint_limit {
+  int32_t has_limits;
+  int32_t reserved0;
+  double min;
+  double max;
+} stomp_joint_limit;
+
+/* Per-iteration result; mirrors what StompOptimizer::optimize reads after
+ * runSingleIteration (src/stomp_optimizer.cpp:301-339): last_trajectory_cost_,
+ * last_trajectory_collision_free_.  Arrays are [B], caller-allocated, may be NULL. */
+typedef struct stomp_iter_stats {
+  double* noiseless_cost;          /* sum_t costs of the noise-less rollout */
+  int32_t* noiseless_collision_free;
+  int32_t num_generated_rollouts;  /* R on the first iteration, R - R_reuse afterwards */
+  int32_t reserved0;
+} stomp_iter_stats;
+
+/* Parity taps / state getters, selector for stomp_engine_get. */
+enum stomp_field {
+  STOMP_FIELD_THETA = 0,          /* [B][D][N]     policy parameters (free block of parameters_all_) */
+  STOMP_FIELD_NOISE = 1,          /* [B][R][D][N]  Rollout::noise_ */
+  STOMP_FIELD_PARAMETERS = 2,     /* [B][R][D][N]  Rollout::parameters_ */
+  STOMP_FIELD_NOISE_PROJECTED = 3,/* [B][R][D][N]  Rollout::noise_projected_ */
+  STOMP_FIELD_STATE_COSTS = 4,    /* [B][R][N]     Rollout::state_costs_ */
+  STOMP_FIELD_CONTROL_COSTS = 5,  /* [B][R][D][N]  Rollout::control_costs_ */
+  STOMP_FIELD_CUMULATIVE_COSTS = 6,/*[B][R][D][N]  Rollout::cumulative_costs_ */
+  STOMP_FIELD_PROBABILITIES = 7,  /* [B][R][D][N]  Rollout::probabilities_ */
+  STOMP_FIELD_UPDATES = 8,        /* [B][D][N]     row 0 of parameter_updates_ */
+  STOMP_FIELD_NOISELESS_COSTS = 9,/* [B][N]        tmp_rollout_cost_ of the noise-less rollout */
+  STOMP_FIELD_COLLISION_FREE = 10,/* [B][R+1] int32 (slot R = noise-less rollout) */
+  STOMP_FIELD_ROLLOUT_TOTAL_COSTS = 11, /* [B][R+1] Rollout::getCost() (slot R = extra rollout) */
+  STOMP_FIELD_INV_CONTROL_COST = 12, /* [N][N] R^-1 */
+  STOMP_FIELD_NOISE_CHOLESKY = 13,   /* [N][N] lower chol(R^-1) */
+  STOMP_FIELD_PROJECTION = 14,       /* [N][N] M */
+  STOMP_FIELD_QUAD_COST_INV = 15,    /* [N][N] StompCost::quad_cost_inv_ (scaled) */
+  STOMP_FIELD_CONTROL_COST = 16,     /* [N][N] R */
+  STOMP_FIELD_CLIPPED_PARAMETERS = 17 /* [B][R][D][N] trajectory after handleJointLimits (what FK sees) */
+};
+
+/* Per-sphere debug record of one rollout (parity tap for the integer work). */
+typedef struct stomp_sphere_debug {
+  int32_t voxel[3];     /* grid cell, PropagationDistanceField::worldToGrid */
+  int32_t in_collision; /* point_is_in_collision_ */
+  double position[3];   /* collision_point_pos_ */
+  double potential;     /* collision_point_potential_ */
+  double vel_mag;       /* collision_point_vel_mag_ */
+} stomp_sphere_debug;
+
+/* ---- lifetime ------------------------------------------------------------------ */
+int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine);
+int stomp_engine_destroy(void* engine);
+const char* stomp_engine_last_error(void);
+/* ABI version and a constant that proves the CUDA build is the one loaded. */
+int stomp_engine_abi_version(void);
+const char* stomp_engine_build_info(void);
+
+/* ---- scene / robot (outputs of StompRobotModel and StompCollisionSpace) ---------- */
+/* Replaces StompRobotModel::StompPlanningGroup {fk_solver_, collision_points_, stomp_joints_}
+ * (include/stomp_motion_planner/stomp_robot_model.h:95-119). */
+int stomp_engine_set_robot(void* engine, const stomp_segment* segments, int32_t num_segments,
+                           int32_t reference_segment, const stomp_sphere* spheres, int32_t num_spheres,
+                           const stomp_joint_limit* limits /* [D] */);
+/* Replaces the distance_field::PropagationDistanceField owned by StompCollisionSpace
+ * (src/stomp_collision_space.cpp:83).  voxels is x-major [nx][ny][nz].  For the *_SQ voxel
+ * types distance = sqrt(v) * resolution. */
+int stomp_engine_set_sdf(void* engine, const void* voxels, int32_t nx, int32_t ny, int32_t nz,
+                         const double origin[3], double resolution, int32_t voxel_dtype);
+/* noise_stddev / noise_decay of PolicyImprovementLoop (src/policy_improvement_loop.cpp:118-119,155-160). */
+int stomp_engine_set_noise(void* engine, const double* noise_stddev /* [D] */, const double* noise_decay /* [D] */);
+
+/* ---- policy (CovariantTrajectoryPolicy) --------------------------------------- */
+/* setToMinControlCost(start, goal) for every problem (src/covariant_trajectory_policy.cpp:102-148);
+ * also resets the rollout-reuse state like PolicyImprovement::initialize (src/policy_improvement.cpp:64-94). */
+int stomp_engine_set_problems(void* engine, const double* start /* [B][D] */, const double* goal /* [B][D] */);
+/* Policy::setParameters / getParameters (include/.../covariant_trajectory_policy.h:200-227). */
+int stomp_engine_set_parameters(void* engine, const double* theta /* [B][D][N] */);
+int stomp_engine_get_parameters(void* engine, double* theta /* [B][D][N] */);
+/* Policy::updateParameters with row 0 of the updates (src/covariant_trajectory_policy.cpp:306-323). */
+int stomp_engine_update_parameters(void* engine, const double* updates /* [B][D][N] */);
+/* Policy::computeControlCosts(noise variant) for caller-supplied vectors
+ * (src/covariant_trajectory_policy.cpp:228-255).  n = vectors per problem. */
+int stomp_engine_compute_control_costs(void* engine, const double* parameters /* [B][n][D][N] */,
+                                       const double* noise /* [B][n][D][N] */, int32_t n, double weight,
+                                       double* control_costs /* [B][n][D][N] */);
+
+/* ---- noise ---------------------------------------------------------------------- */
+int stomp_engine_seed(void* engine, uint64_t seed);
+/* Host-injection mode: eps[B][R_gen][D][N] used by the NEXT get_rollouts / iterate instead of the
+ * engine RNG (already scaled by the noise stddev, i.e. Rollout::noise_).  n = rollouts per problem
+ * supplied (>= the number generated that iteration). */
+int stomp_engine_inject_noise(void* engine, const double* eps, int32_t n);
+/* Draw the engine's own standard normals z[B][n][D][N] (iteration, global rollout id keyed Philox)
+ * without touching engine state: statistical validation of the RNG against N(0, R^-1). */
+int stomp_engine_sample_noise(void* engine, int32_t iteration, int32_t n, double* eps_out /* [B][n][D][N], unit stddev */);
+
+/* ---- cost plugin: batched Task::execute ---------------------------------------- */
+/* StompOptimizer::execute for n rollouts per problem (src/stomp_optimizer.cpp:1063-1165):
+ * joint-limit projection, FK, collision spheres, SDF potential, FD velocity, cumulative obstacle cost.
+ * collision_free may be NULL.  iteration_number == 1 reproduces the reference's first outer iteration
+ * (iteration_ == 0), where the fixed start/goal padding points also count towards collision_free
+ * (src/stomp_optimizer.cpp:624-630). */
+int stomp_engine_execute(void* engine, const double* parameters /* [B][n][D][N] */, int32_t n,
+                         int32_t iteration_number, double* costs /* [B][n][N] */,
+                         int32_t* collision_free /* [B][n] */);
+/* Same, plus the per-sphere records of performForwardKinematics (src/stomp_optimizer.cpp:618-709)
+ * for rollout 0 of problem 0: debug[N][K]. */
+int stomp_engine_execute_debug(void* engine, const double* parameters /* [D][N] */,
+                               stomp_sphere_debug* debug /* [N+3][K]: trajectory points -1 .. N+1 */);
+
+/* ---- PolicyImprovement, step by step (keeps the caller's own Task) ---------------- */
+/* PolicyImprovement::getRollouts (src/policy_improvement.cpp:241-260).  Writes the newly generated
+ * rollouts [B][R_gen][D][N] and R_gen. */
+int stomp_engine_get_rollouts(void* engine, const double* noise_stddev /* [D] */, double* rollouts,
+                              int32_t* num_generated);
+/* PolicyImprovement::setRolloutCosts (src/policy_improvement.cpp:262-281).  costs[B][R_gen][N];
+ * rollout_costs_total[B][R] may be NULL. */
+int stomp_engine_set_rollout_costs(void* engine, const double* costs, double control_cost_weight,
+                                   double* rollout_costs_total);
+/* PolicyImprovement::improvePolicy (src/policy_improvement.cpp:385-401): updates[B][D][N] = row 0. */
+int stomp_engine_improve_policy(void* engine, double* updates);
+/* PolicyImprovement::addExtraRollouts with the current policy parameters as the single extra
+ * rollout (src/policy_improvement.cpp:443-462; src/policy_improvement_loop.cpp:186-192). costs[B][N]. */
+int stomp_engine_add_extra_rollouts(void* engine, const double* costs);
+
+/* ---- the hot path --------------------------------------------------------------- */
+/* PolicyImprovementLoop::runSingleIteration(iteration_number) with the built-in GPU Task
+ * (src/policy_improvement_loop.cpp:143-202).  stats may be NULL (no host sync then). */
+int stomp_engine_iterate(void* engine, int32_t iteration_number, stomp_iter_stats* stats);
+/* iterations first..first+count-1 back to back on the device, no host round trip in between. */
+int stomp_engine_run(void* engine, int32_t first_iteration, int32_t count, stomp_iter_stats* last_stats);
+int stomp_engine_synchronize(void* engine);
+
+/* ---- getters -------------------------------------------------------------------- */
+/* Copies a field (see stomp_field) to a host buffer of `bytes` bytes (fp64 unless noted). */
+int stomp_engine_get(void* engine, int32_t field, void* out, size_t bytes);
+/* Number of CUDA kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t stomp_engine_launch_count(void* engine);
+/* CUDA stream of the handle as an opaque pointer (for event timing on the launching stream). */
+void* stomp_engine_stream(void* engine);
+/* Device timing helpers on the handle's stream: record/elapsed of two internal events. */
+int stomp_engine_timer_start(void* engine);
+int stomp_engine_timer_stop(void* engine, float* elapsed_ms);
+
+/* ---- rollout sharding over GPUs (config C3) ----------------------------------------- */
+/* Device buffers the host plumbing (torch.distributed / NCCL) all-reduces between the phases of
+ * a sharded iteration: minmax = [2][D][N] (MAX of {c, -c}), sums = [2][D][N] (SUM of {e, e*eps}). */
+int stomp_engine_shard_buffers(void* engine, void** minmax_dev, void** sums_dev, size_t* bytes_each);
+int stomp_engine_iterate_sharded_phase(void* engine, int32_t iteration_number, int32_t phase /* 0,1,2 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STOMP_B200_H_ */
