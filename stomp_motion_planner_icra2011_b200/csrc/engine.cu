@@ -1,0 +1,880 @@
+// engine.cu — host side of the B200 STOMP rollout engine and its C ABI (include/stomp_b200.h).
+//
+// One handle = one device = one CUDA stream.  The handle owns every device buffer; the host only
+// orchestrates kernel launches (kernels.cuh) and the once-per-request fp64 setup (host_math.hpp).
+// There is no CPU fallback: every entry point that computes launches CUDA kernels, and a missing
+// device is an error.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "host_math.hpp"
+#include "kernels.cuh"
+
+using namespace stomp_dev;
+namespace sh = stomp_host;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(const std::string& msg) {
+  g_error = msg;
+  return 1;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      (void)cudaGetLastError();                                                                 \
+      return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));                          \
+    }                                                                                           \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(p, 0, count * sizeof(T));
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+struct Engine {
+  stomp_engine_desc desc;
+  int B = 0, D = 0, N = 0, R = 0, Rre = 0, K = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t launches = 0;
+  bool f32 = false;
+
+  sh::PolicyMatrices pm;
+  sh::FoldedRobot robot;
+  bool have_robot = false, have_sdf = false, have_problems = false;
+  std::vector<double> noise_stddev, noise_decay;
+  uint64_t seed = 0x57012011ull;
+
+  // PolicyImprovement state
+  int cur = 0;  // ping-pong index of params / state costs
+  bool reused_next = false, extra_added = false;
+  int num_gen = 0;
+  bool injected_pending = false;
+  double control_cost_weight = 0.0;
+
+  // device buffers
+  DevBuf<double> theta, pad_start, pad_goal;
+  DevBuf<double> params[2], state[2];
+  DevBuf<double> noise, control, cumulative, totals;
+  DevBuf<double> noise_projected, probabilities, clipped;      // taps (keep_intermediates)
+  DevBuf<double> extra_state, extra_control, updates, noiseless_sum;
+  DevBuf<double> eps_in;
+  DevBuf<int> reuse_src, collision_free;
+  DevBuf<double> band, inv_diag, proj_scale, qinv_t, noise_scale;
+  DevBuf<double> limit_min, limit_max;
+  DevBuf<int> has_limits;
+  DevBuf<unsigned char> nodes, spheres, sqrt_table, vox;
+  DevBuf<double> scratch_params, scratch_noise, scratch_costs;  // execute / compute_control_costs staging
+  DevBuf<int> scratch_flags;
+  DevBuf<stomp_sphere_debug> debug;
+  DevBuf<double> part, minmax, sums;  // sharded / huge-R statistics
+  int num_nodes = 0;
+  Sdf sdf;
+  size_t scratch_n = 0;
+
+  Band band_view() const { return Band{band.p, inv_diag.p, proj_scale.p, pm.chol.hb}; }
+  Stencil stencil() const {
+    Stencil st;
+    for (int k = 0; k < 3; ++k) {
+      st.weight[k] = desc.derivative_costs[k];
+      for (int j = 0; j < 7; ++j) st.coef[k][j] = pm.stencil_scale[k] * sh::kDiffRules[k][j];
+    }
+    return st;
+  }
+  bool huge_path() const { return desc.rollout_shard_world > 1 || R > 4096; }
+};
+
+int check_launch(Engine& e, const char* what) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(std::string(what) + ": " + cudaGetErrorString(err));
+  e.launches++;
+  return 0;
+}
+
+template <typename T>
+int upload(Engine& e, DevBuf<T>& buf, const T* host, size_t count) {
+  if (buf.n != count) CUDA_TRY(buf.alloc(count));
+  if (count) CUDA_TRY(cudaMemcpyAsync(buf.p, host, count * sizeof(T), cudaMemcpyHostToDevice, e.stream));
+  return 0;
+}
+
+template <typename Real>
+int upload_robot_tables(Engine& e) {
+  std::vector<DevNode<Real>> nodes(e.robot.nodes.size());
+  for (size_t i = 0; i < nodes.size(); ++i) {
+    const sh::HostNode& h = e.robot.nodes[i];
+    DevNode<Real>& n = nodes[i];
+    std::memset(&n, 0, sizeof(n));
+    for (int k = 0; k < 9; ++k) n.A0[k] = Real(h.A0[k]), n.A1[k] = Real(h.A1[k]), n.A2[k] = Real(h.A2[k]);
+    for (int k = 0; k < 3; ++k) n.p[k] = Real(h.p[k]), n.ax[k] = Real(h.ax[k]);
+    n.parent = h.parent; n.type = h.type; n.q_index = h.q_index; n.save_slot = h.save_slot; n.load_slot = h.load_slot;
+    n.sphere_begin = h.sphere_begin; n.sphere_end = h.sphere_end;
+  }
+  std::vector<DevSphere<Real>> sph(e.robot.spheres.size());
+  for (size_t i = 0; i < sph.size(); ++i) {
+    const sh::HostSphere& h = e.robot.spheres[i];
+    std::memset(&sph[i], 0, sizeof(sph[i]));
+    for (int k = 0; k < 3; ++k) sph[i].pos[k] = Real(h.pos[k]);
+    sph[i].radius = Real(h.radius); sph[i].clearance = Real(h.clearance); sph[i].inv_clearance = Real(h.inv_clearance);
+    sph[i].weight = Real(h.weight); sph[i].original_index = h.original_index;
+  }
+  if (upload(e, e.nodes, reinterpret_cast<const unsigned char*>(nodes.data()), nodes.size() * sizeof(DevNode<Real>))) return 1;
+  if (upload(e, e.spheres, reinterpret_cast<const unsigned char*>(sph.data()), sph.size() * sizeof(DevSphere<Real>))) return 1;
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+template <typename Real>
+int upload_sqrt_table(Engine& e) {
+  std::vector<Real> tab(256);
+  for (int i = 0; i < 256; ++i) tab[i] = Real(std::sqrt(double(i)) * e.sdf.res);  // PropagationDistanceField sqrt_table_
+  if (upload(e, e.sqrt_table, reinterpret_cast<const unsigned char*>(tab.data()), tab.size() * sizeof(Real))) return 1;
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+// ---- kernel launch helpers ----------------------------------------------------------------------
+
+int launch_generate(Engine& e, GenArgs a) {
+  const int N = e.N, hb = e.pm.chol.hb;
+  const size_t fixed = size_t(N) * (hb + 1) * 8 + size_t(N) * 16;
+  const size_t per_thread = size_t(N | 1) * 8 + 16;
+  int tpb = int((200 * 1024 - fixed) / per_thread);
+  tpb = std::min(128, (tpb / 32) * 32);
+  if (tpb < 32) return fail("num_time_steps too large for the shared-memory row buffers of k_generate");
+  long long nvec = (long long)a.B * (a.extra ? 1 : a.R) * a.D;
+  // prefer >= 2 CTAs per SM worth of parallelism for small problems
+  while (tpb > 32 && (nvec + tpb - 1) / tpb < 296) tpb -= 32;
+  size_t smem = fixed + per_thread * tpb;
+  CUDA_TRY(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  unsigned grid = unsigned((nvec + tpb - 1) / tpb);
+  k_generate<<<grid, tpb, smem, e.stream>>>(a);
+  return check_launch(e, "k_generate");
+}
+
+GenArgs base_gen_args(Engine& e) {
+  GenArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.B = e.B; a.R = e.R; a.D = e.D; a.N = e.N;
+  a.R_gen = e.num_gen;
+  a.seed = e.seed;
+  a.rollout_id_offset = int64_t(e.desc.rollout_shard_rank) * e.R;
+  a.rollouts_global = int64_t(e.desc.rollout_shard_world) * e.R;
+  a.theta = e.theta.p; a.pad_start = e.pad_start.p; a.pad_goal = e.pad_goal.p;
+  a.noise_scale = e.noise_scale.p;
+  a.eps_in = e.eps_in.p;
+  a.params_prev = e.params[1 - e.cur].p;
+  a.reuse_src = e.reuse_src.p;
+  a.noise = e.noise.p;
+  a.params = e.params[e.cur].p;
+  a.noise_projected = e.noise_projected.p;
+  a.control = e.control.p;
+  a.band = e.band_view();
+  a.st = e.stencil();
+  return a;
+}
+
+template <typename Real, bool kDebug>
+int launch_cost_t(Engine& e, CostArgs<Real>& a, int num_problems) {
+  const int ntiles = (e.N + kTileSteps - 1) / kTileSteps;
+  int warps = std::min(ntiles, 8);
+  warps = std::max(warps, std::min(e.D, 4));  // joint-limit pass likes a few warps
+  size_t smem = size_t(e.D) * e.N * 8 + size_t(e.num_nodes) * sizeof(DevNode<Real>) + size_t(e.K) * sizeof(DevSphere<Real>) +
+                256 * sizeof(Real);
+  auto kern = k_cost<Real, kDebug>;
+  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  if (smem > 220 * 1024) return fail("trajectory + robot tables exceed shared memory");
+  kern<<<unsigned(num_problems) * a.n_rollouts, warps * 32, smem, e.stream>>>(a);
+  return check_launch(e, "k_cost");
+}
+
+template <typename Real>
+CostArgs<Real> base_cost_args(Engine& e) {
+  CostArgs<Real> a;
+  std::memset(&a, 0, sizeof(a));
+  a.D = e.D; a.N = e.N; a.K = e.K; a.num_nodes = e.num_nodes;
+  a.pad_start = e.pad_start.p; a.pad_goal = e.pad_goal.p;
+  a.qinv_t = e.qinv_t.p;
+  a.has_limits = e.has_limits.p; a.limit_min = e.limit_min.p; a.limit_max = e.limit_max.p;
+  a.nodes = reinterpret_cast<const DevNode<Real>*>(e.nodes.p);
+  a.spheres = reinterpret_cast<const DevSphere<Real>*>(e.spheres.p);
+  a.sqrt_table = reinterpret_cast<const Real*>(e.sqrt_table.p);
+  a.sdf = e.sdf;
+  a.inv_time = 1.0 / e.desc.discretization;
+  a.obstacle_weight = e.desc.obstacle_cost_weight;
+  return a;
+}
+
+// cost plugin over rollouts stored as params[b*pstride + r*D*N], writing costs[b*cstride + r*N]
+int launch_cost(Engine& e, const double* params, size_t pstride, int n_rollouts, int num_problems, int include_pads,
+                double* costs, size_t cstride, int* flags, int flag_stride, int flag_offset, double* clipped,
+                stomp_sphere_debug* debug) {
+  if (!e.have_robot || !e.have_sdf) return fail("set_robot and set_sdf must be called before the cost plugin runs");
+  if (!e.have_problems) return fail("set_problems must be called before the cost plugin runs");
+  if (e.f32) {
+    CostArgs<float> a = base_cost_args<float>(e);
+    a.n_rollouts = n_rollouts; a.include_pads = include_pads;
+    a.params = params; a.params_problem_stride = pstride; a.params_rollout_stride = size_t(e.D) * e.N;
+    a.costs = costs; a.cost_problem_stride = cstride;
+    a.collision_free = flags; a.flag_problem_stride = flag_stride; a.flag_offset = flag_offset;
+    a.clipped = clipped; a.debug = debug;
+    return debug ? launch_cost_t<float, true>(e, a, num_problems) : launch_cost_t<float, false>(e, a, num_problems);
+  }
+  CostArgs<double> a = base_cost_args<double>(e);
+  a.n_rollouts = n_rollouts; a.include_pads = include_pads;
+  a.params = params; a.params_problem_stride = pstride; a.params_rollout_stride = size_t(e.D) * e.N;
+  a.costs = costs; a.cost_problem_stride = cstride;
+  a.collision_free = flags; a.flag_problem_stride = flag_stride; a.flag_offset = flag_offset;
+  a.clipped = clipped; a.debug = debug;
+  return debug ? launch_cost_t<double, true>(e, a, num_problems) : launch_cost_t<double, false>(e, a, num_problems);
+}
+
+int block_for(int N) { return std::min(1024, ((N + 31) / 32) * 32); }
+
+int launch_cumulative(Engine& e) {
+  k_cumulative<<<unsigned(e.B) * e.R, block_for(e.N), 0, e.stream>>>(e.R, e.D, e.N, e.desc.use_cumulative_costs,
+                                                                    e.state[e.cur].p, e.control.p, e.cumulative.p, e.totals.p);
+  return check_launch(e, "k_cumulative");
+}
+
+size_t band_smem(const Engine& e) { return (size_t(e.N) * (e.pm.chol.hb + 2) + e.N) * 8; }
+
+int launch_update(Engine& e, int apply) {
+  UpdateArgs a;
+  a.R = e.R; a.D = e.D; a.N = e.N; a.apply = apply;
+  a.cumulative = e.cumulative.p; a.noise = e.noise.p; a.probabilities = e.probabilities.p;
+  a.updates = e.updates.p; a.theta = e.theta.p; a.band = e.band_view();
+  k_update<<<unsigned(e.B) * e.D, block_for(e.N), band_smem(e), e.stream>>>(a);
+  return check_launch(e, "k_update");
+}
+
+// huge-R / sharded statistics, phase by phase (B == 1)
+constexpr int kChunks = 128;
+int launch_minmax(Engine& e) {
+  const int DN = e.D * e.N, rpc = (e.R + kChunks - 1) / kChunks, nch = (e.R + rpc - 1) / rpc;
+  dim3 grid((DN + 127) / 128, nch);
+  k_minmax_partial<<<grid, 128, 0, e.stream>>>(e.R, DN, rpc, e.cumulative.p, e.part.p);
+  if (check_launch(e, "k_minmax_partial")) return 1;
+  k_pair_reduce<<<(2 * DN + 127) / 128, 128, 0, e.stream>>>(DN, nch, 1, e.part.p, e.minmax.p);
+  return check_launch(e, "k_pair_reduce");
+}
+int launch_sums(Engine& e) {
+  const int DN = e.D * e.N, rpc = (e.R + kChunks - 1) / kChunks, nch = (e.R + rpc - 1) / rpc;
+  dim3 grid((DN + 127) / 128, nch);
+  k_sums_partial<<<grid, 128, 0, e.stream>>>(e.R, DN, rpc, e.cumulative.p, e.noise.p, e.minmax.p, e.part.p);
+  if (check_launch(e, "k_sums_partial")) return 1;
+  k_pair_reduce<<<(2 * DN + 127) / 128, 128, 0, e.stream>>>(DN, nch, 0, e.part.p, e.sums.p);
+  return check_launch(e, "k_pair_reduce");
+}
+int launch_finalize(Engine& e, int apply) {
+  if (e.probabilities.p) {
+    k_probabilities<<<1184, 256, 0, e.stream>>>(e.R, e.D * e.N, e.cumulative.p, e.minmax.p, e.sums.p, e.probabilities.p);
+    if (check_launch(e, "k_probabilities")) return 1;
+  }
+  k_finalize<<<e.D, block_for(e.N), band_smem(e), e.stream>>>(e.D, e.N, apply, e.sums.p, e.updates.p, e.theta.p, e.band_view());
+  return check_launch(e, "k_finalize");
+}
+
+// ---- PolicyImprovement steps ----------------------------------------------------------------------
+
+int set_noise_scale(Engine& e, const double* scale) {
+  return upload(e, e.noise_scale, scale, size_t(e.D));
+}
+
+// generateRollouts bookkeeping (src/policy_improvement.cpp:166-176) + reuse selection + k_generate
+int step_get_rollouts(Engine& e, int iteration_number, bool with_control) {
+  e.cur = 1 - e.cur;
+  e.num_gen = e.R - e.Rre;
+  bool reuse = false;
+  if (!e.reused_next) {
+    e.num_gen = e.R;
+    if (e.Rre > 0) e.reused_next = true;
+  } else {
+    reuse = true;
+  }
+  if (reuse) {
+    k_select_reuse<<<e.B, 128, 0, e.stream>>>(e.totals.p, e.R, e.Rre, e.extra_added ? 1 : 0, e.reuse_src.p);
+    if (check_launch(e, "k_select_reuse")) return 1;
+    e.extra_added = false;
+    // reused rollouts keep their (stale) state costs: gather them into the current buffer with the parameters.
+    // Done by k_gather_state below (tiny).
+  }
+  GenArgs a = base_gen_args(e);
+  a.mode_generate = 1;
+  a.mode_project = 1;
+  a.mode_control = with_control ? 1 : 0;
+  a.injected = e.injected_pending ? 1 : 0;
+  a.iteration = uint32_t(iteration_number);
+  a.control_weight = 0.5 * e.control_cost_weight;
+  e.injected_pending = false;
+  return launch_generate(e, a);
+}
+
+__global__ void k_gather_state(int R, int R_gen, int N, const int* __restrict__ reuse_src, const double* __restrict__ prev,
+                               const double* __restrict__ extra, double* __restrict__ cur) {
+  const int b = blockIdx.x / (R - R_gen), j = blockIdx.x - b * (R - R_gen);
+  const int src = reuse_src[size_t(b) * (R - R_gen) + j];
+  const double* s = src >= 0 ? prev + (size_t(b) * R + src) * N : extra + size_t(b) * N;
+  double* d = cur + (size_t(b) * R + R_gen + j) * N;
+  for (int t = threadIdx.x; t < N; t += blockDim.x) d[t] = s[t];
+}
+
+int gather_reused_state(Engine& e) {
+  if (e.num_gen == e.R) return 0;
+  k_gather_state<<<unsigned(e.B) * (e.R - e.num_gen), 128, 0, e.stream>>>(e.R, e.num_gen, e.N, e.reuse_src.p,
+                                                                          e.state[1 - e.cur].p, e.extra_state.p, e.state[e.cur].p);
+  return check_launch(e, "k_gather_state");
+}
+
+int step_control_costs(Engine& e) {  // computeRolloutControlCosts for all R rollouts with the current weight
+  GenArgs a = base_gen_args(e);
+  a.mode_generate = 0; a.mode_project = 1; a.mode_control = 1;
+  a.control_weight = 0.5 * e.control_cost_weight;
+  return launch_generate(e, a);
+}
+
+int step_improve(Engine& e, int apply) {
+  if (launch_cumulative(e)) return 1;
+  if (e.huge_path()) {
+    if (e.B != 1) return fail("the sharded / huge-rollout statistics path supports num_problems == 1 only");
+    if (launch_minmax(e) || launch_sums(e)) return 1;
+    return launch_finalize(e, apply);
+  }
+  return launch_update(e, apply);
+}
+
+int step_extra(Engine& e, bool run_cost, int iteration_number) {
+  if (run_cost) {
+    if (launch_cost(e, e.theta.p, size_t(e.D) * e.N, 1, e.B, iteration_number == 1, e.extra_state.p, size_t(e.N),
+                    e.collision_free.p, e.R + 1, e.R, nullptr, nullptr))
+      return 1;
+  }
+  GenArgs a = base_gen_args(e);
+  a.extra = 1; a.mode_generate = 0; a.mode_project = 0; a.mode_control = 1;
+  a.control = e.extra_control.p;
+  a.control_weight = 0.5 * e.control_cost_weight;
+  if (launch_generate(e, a)) return 1;
+  k_extra_total<<<e.B, 128, 0, e.stream>>>(e.R, e.D, e.N, e.extra_state.p, e.extra_control.p, e.totals.p, e.noiseless_sum.p);
+  if (check_launch(e, "k_extra_total")) return 1;
+  e.extra_added = true;
+  return 0;
+}
+
+int iterate_front(Engine& e, int iteration_number) {  // up to and including k_cumulative
+  std::vector<double> scale(e.D);
+  for (int d = 0; d < e.D; ++d) scale[d] = e.noise_stddev[d] * std::pow(e.noise_decay[d], iteration_number - 1);
+  if (set_noise_scale(e, scale.data())) return 1;
+  e.control_cost_weight = e.desc.smoothness_cost_weight;
+  if (step_get_rollouts(e, iteration_number, true)) return 1;
+  if (gather_reused_state(e)) return 1;
+  if (launch_cost(e, e.params[e.cur].p, size_t(e.R) * e.D * e.N, e.num_gen, e.B, iteration_number == 1, e.state[e.cur].p,
+                  size_t(e.R) * e.N, e.collision_free.p, e.R + 1, 0, e.clipped.p, nullptr))
+    return 1;
+  return launch_cumulative(e);
+}
+
+int iterate_once(Engine& e, int iteration_number) {
+  if (iterate_front(e, iteration_number)) return 1;
+  if (e.huge_path()) {
+    if (e.B != 1) return fail("the sharded / huge-rollout statistics path supports num_problems == 1 only");
+    if (e.desc.rollout_shard_world > 1)
+      return fail("rollout-sharded engines iterate through stomp_engine_iterate_sharded_phase");
+    if (launch_minmax(e) || launch_sums(e) || launch_finalize(e, 1)) return 1;
+  } else if (launch_update(e, 1)) {
+    return 1;
+  }
+  return step_extra(e, true, iteration_number);
+}
+
+int fill_stats(Engine& e, stomp_iter_stats* stats) {
+  if (!stats) return 0;
+  stats->num_generated_rollouts = e.num_gen;
+  if (stats->noiseless_cost)
+    CUDA_TRY(cudaMemcpyAsync(stats->noiseless_cost, e.noiseless_sum.p, size_t(e.B) * 8, cudaMemcpyDeviceToHost, e.stream));
+  if (stats->noiseless_collision_free) {
+    CUDA_TRY(cudaMemcpy2DAsync(stats->noiseless_collision_free, 4, e.collision_free.p + e.R, size_t(e.R + 1) * 4, 4, e.B,
+                               cudaMemcpyDeviceToHost, e.stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+int ensure_scratch(Engine& e, size_t n_rollouts_total) {
+  if (e.scratch_n >= n_rollouts_total) return 0;
+  CUDA_TRY(e.scratch_params.alloc(n_rollouts_total * e.D * e.N));
+  CUDA_TRY(e.scratch_noise.alloc(n_rollouts_total * e.D * e.N));
+  CUDA_TRY(e.scratch_costs.alloc(n_rollouts_total * e.D * e.N));
+  CUDA_TRY(e.scratch_flags.alloc(n_rollouts_total));
+  e.scratch_n = n_rollouts_total;
+  return 0;
+}
+
+Engine* E(void* h) { return static_cast<Engine*>(h); }
+
+#define ENGINE_OR_FAIL(h)                          \
+  if (!(h)) return fail("null engine handle");     \
+  Engine& e = *E(h);                               \
+  CUDA_TRY(cudaSetDevice(e.device));
+
+}  // namespace
+
+extern "C" {
+
+const char* stomp_engine_last_error(void) { return g_error.c_str(); }
+int stomp_engine_abi_version(void) { return 1; }
+const char* stomp_engine_build_info(void) { return "stomp_b200 CUDA engine, sm_100a, " __DATE__ " " __TIME__; }
+
+int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
+  if (!desc || !out_engine) return fail("null argument");
+  *out_engine = nullptr;
+  if (desc->num_dimensions < 1 || desc->num_time_steps < 2 || desc->num_rollouts < 1 || desc->num_problems < 1)
+    return fail("num_dimensions, num_rollouts, num_problems must be >= 1 and num_time_steps >= 2");
+  if (desc->num_reused_rollouts < 0 || desc->num_reused_rollouts >= desc->num_rollouts)
+    return fail("Number of reused rollouts must be strictly less than number of rollouts.");  // policy_improvement.cpp:102-106
+  if (desc->dtype != STOMP_F64 && desc->dtype != STOMP_F32) return fail("unknown dtype");
+  if (desc->sdf_mode != STOMP_SDF_NEAREST) return fail("only the nearest-cell distance-field lookup (the reference's) is implemented");
+  if (desc->rollout_shard_world < 1 || desc->rollout_shard_rank < 0 || desc->rollout_shard_rank >= desc->rollout_shard_world)
+    return fail("bad rollout shard rank / world");
+  if (desc->rollout_shard_world > 1 && (desc->num_reused_rollouts != 0 || desc->num_problems != 1))
+    return fail("rollout sharding requires num_reused_rollouts == 0 and num_problems == 1");
+  if (desc->discretization <= 0.0 || desc->movement_duration <= 0.0) return fail("durations must be positive");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    (void)cudaGetLastError();
+    return fail("no CUDA device available: the STOMP B200 engine has no CPU fallback");
+  }
+  if (desc->device < 0 || desc->device >= ndev) return fail("CUDA device ordinal out of range");
+  Engine* ep = new Engine();
+  Engine& e = *ep;
+  e.desc = *desc;
+  e.B = desc->num_problems; e.D = desc->num_dimensions; e.N = desc->num_time_steps; e.R = desc->num_rollouts;
+  e.Rre = desc->num_reused_rollouts;
+  e.device = desc->device;
+  e.f32 = desc->dtype == STOMP_F32;
+  std::string err;
+  if (!sh::build_policy_matrices(*desc, e.pm, err)) { delete ep; return fail(err); }
+  if (e.pm.chol.hb > kMaxHb) { delete ep; return fail("control cost bandwidth too large"); }
+  auto bail = [&](cudaError_t c, const char* what) {
+    std::string m = std::string(what) + ": " + cudaGetErrorString(c);
+    (void)cudaGetLastError();
+    delete ep;
+    return fail(m);
+  };
+  cudaError_t c;
+  if ((c = cudaSetDevice(e.device)) != cudaSuccess) return bail(c, "cudaSetDevice");
+  if ((c = cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
+  if ((c = cudaEventCreate(&e.ev0)) != cudaSuccess || (c = cudaEventCreate(&e.ev1)) != cudaSuccess) return bail(c, "cudaEventCreate");
+  const size_t BDN = size_t(e.B) * e.D * e.N, BRDN = BDN * e.R, BRN = size_t(e.B) * e.R * e.N;
+#define ALLOC(buf, n) if ((c = (buf).alloc(n)) != cudaSuccess) return bail(c, "cudaMalloc " #buf)
+  ALLOC(e.theta, BDN); ALLOC(e.pad_start, size_t(e.B) * e.D); ALLOC(e.pad_goal, size_t(e.B) * e.D);
+  ALLOC(e.params[0], BRDN); ALLOC(e.params[1], BRDN); ALLOC(e.state[0], BRN); ALLOC(e.state[1], BRN);
+  ALLOC(e.noise, BRDN); ALLOC(e.control, BRDN); ALLOC(e.cumulative, BRDN); ALLOC(e.totals, size_t(e.B) * (e.R + 1));
+  if (desc->keep_intermediates) { ALLOC(e.noise_projected, BRDN); ALLOC(e.probabilities, BRDN); ALLOC(e.clipped, BRDN); }
+  ALLOC(e.extra_state, size_t(e.B) * e.N); ALLOC(e.extra_control, BDN); ALLOC(e.updates, BDN); ALLOC(e.noiseless_sum, size_t(e.B));
+  ALLOC(e.reuse_src, size_t(e.B) * std::max(1, e.Rre)); ALLOC(e.collision_free, size_t(e.B) * (e.R + 1));
+  ALLOC(e.noise_scale, size_t(e.D));
+  ALLOC(e.part, size_t(kChunks) * 2 * e.D * e.N); ALLOC(e.minmax, size_t(2) * e.D * e.N); ALLOC(e.sums, size_t(2) * e.D * e.N);
+#undef ALLOC
+  // matrices
+  std::vector<double> qt(size_t(e.N) * e.N);
+  for (int i = 0; i < e.N; ++i)
+    for (int j = 0; j < e.N; ++j) qt[size_t(j) * e.N + i] = e.pm.Qinv(i, j);
+  if (upload(e, e.band, e.pm.chol.band.data(), e.pm.chol.band.size()) || upload(e, e.inv_diag, e.pm.chol.inv_diag.data(), size_t(e.N)) ||
+      upload(e, e.proj_scale, e.pm.proj_scale.data(), size_t(e.N)) || upload(e, e.qinv_t, qt.data(), qt.size())) {
+    delete ep;
+    return 1;
+  }
+  e.noise_stddev.assign(e.D, 1.0);
+  e.noise_decay.assign(e.D, 1.0);
+  std::vector<int> hl(e.D, 0);
+  std::vector<double> zeros(e.D, 0.0);
+  if (upload(e, e.has_limits, hl.data(), size_t(e.D)) || upload(e, e.limit_min, zeros.data(), size_t(e.D)) ||
+      upload(e, e.limit_max, zeros.data(), size_t(e.D))) {
+    delete ep;
+    return 1;
+  }
+  if ((c = cudaStreamSynchronize(e.stream)) != cudaSuccess) return bail(c, "cudaStreamSynchronize");
+  e.control_cost_weight = desc->smoothness_cost_weight;
+  *out_engine = ep;
+  return 0;
+}
+
+int stomp_engine_destroy(void* h) {
+  if (!h) return 0;
+  Engine* e = E(h);
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return 0;
+}
+
+int stomp_engine_set_robot(void* h, const stomp_segment* segments, int32_t num_segments, int32_t reference_segment,
+                           const stomp_sphere* spheres, int32_t num_spheres, const stomp_joint_limit* limits) {
+  ENGINE_OR_FAIL(h);
+  if (!segments || num_segments < 1 || (!spheres && num_spheres > 0)) return fail("null robot tables");
+  std::string err;
+  if (!sh::fold_robot(segments, num_segments, reference_segment, spheres, num_spheres, e.D, e.robot, err)) return fail(err);
+  if (e.robot.num_slots > kMaxSlots) return fail("kinematic tree branches too deeply for the FK kernel (frame slots)");
+  e.K = num_spheres;
+  e.num_nodes = int(e.robot.nodes.size());
+  if (e.f32 ? upload_robot_tables<float>(e) : upload_robot_tables<double>(e)) return 1;
+  std::vector<int> hl(e.D, 0);
+  std::vector<double> lo(e.D, 0.0), hi(e.D, 0.0);
+  if (limits)
+    for (int d = 0; d < e.D; ++d) hl[d] = limits[d].has_limits, lo[d] = limits[d].min, hi[d] = limits[d].max;
+  if (upload(e, e.has_limits, hl.data(), size_t(e.D)) || upload(e, e.limit_min, lo.data(), size_t(e.D)) ||
+      upload(e, e.limit_max, hi.data(), size_t(e.D)))
+    return 1;
+  CUDA_TRY(e.debug.alloc(size_t(e.N + 3) * std::max(1, e.K)));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  e.have_robot = true;
+  return 0;
+}
+
+int stomp_engine_set_sdf(void* h, const void* voxels, int32_t nx, int32_t ny, int32_t nz, const double origin[3],
+                         double resolution, int32_t voxel_dtype) {
+  ENGINE_OR_FAIL(h);
+  if (!voxels || nx < 3 || ny < 3 || nz < 3 || resolution <= 0.0) return fail("bad distance field");
+  size_t esz = voxel_dtype == STOMP_VOXEL_U8_SQ ? 1 : voxel_dtype == STOMP_VOXEL_U16_SQ ? 2 : voxel_dtype == STOMP_VOXEL_F32 ? 4 : 0;
+  if (!esz) return fail("unknown voxel dtype");
+  size_t bytes = size_t(nx) * ny * nz * esz;
+  if (upload(e, e.vox, static_cast<const unsigned char*>(voxels), bytes)) return 1;
+  e.sdf.vox = e.vox.p;
+  e.sdf.nx = nx; e.sdf.ny = ny; e.sdf.nz = nz; e.sdf.dtype = voxel_dtype;
+  for (int i = 0; i < 3; ++i) e.sdf.origin[i] = origin[i];
+  e.sdf.res = resolution;
+  e.sdf.inv_res = 1.0 / resolution;
+  if (e.f32 ? upload_sqrt_table<float>(e) : upload_sqrt_table<double>(e)) return 1;
+  e.have_sdf = true;
+  return 0;
+}
+
+int stomp_engine_set_noise(void* h, const double* noise_stddev, const double* noise_decay) {
+  ENGINE_OR_FAIL(h);
+  if (!noise_stddev || !noise_decay) return fail("null argument");
+  e.noise_stddev.assign(noise_stddev, noise_stddev + e.D);
+  e.noise_decay.assign(noise_decay, noise_decay + e.D);
+  return 0;
+}
+
+int stomp_engine_set_problems(void* h, const double* start, const double* goal) {
+  ENGINE_OR_FAIL(h);
+  if (!start || !goal) return fail("null argument");
+  std::vector<double> th(size_t(e.B) * e.D * e.N);
+  for (int b = 0; b < e.B; ++b)
+    for (int d = 0; d < e.D; ++d)
+      sh::min_control_cost(e.pm, start[size_t(b) * e.D + d], goal[size_t(b) * e.D + d], &th[(size_t(b) * e.D + d) * e.N]);
+  if (upload(e, e.theta, th.data(), th.size()) || upload(e, e.pad_start, start, size_t(e.B) * e.D) ||
+      upload(e, e.pad_goal, goal, size_t(e.B) * e.D))
+    return 1;
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  // PolicyImprovement::initialize / setNumRollouts state (src/policy_improvement.cpp:64-147)
+  e.reused_next = false;
+  e.extra_added = false;
+  e.num_gen = 0;
+  e.cur = 0;
+  e.injected_pending = false;
+  e.have_problems = true;
+  return 0;
+}
+
+int stomp_engine_set_parameters(void* h, const double* theta) {
+  ENGINE_OR_FAIL(h);
+  if (!theta) return fail("null argument");
+  if (upload(e, e.theta, theta, size_t(e.B) * e.D * e.N)) return 1;
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+int stomp_engine_get_parameters(void* h, double* theta) {
+  ENGINE_OR_FAIL(h);
+  if (!theta) return fail("null argument");
+  CUDA_TRY(cudaMemcpyAsync(theta, e.theta.p, size_t(e.B) * e.D * e.N * 8, cudaMemcpyDeviceToHost, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+int stomp_engine_update_parameters(void* h, const double* updates) {
+  ENGINE_OR_FAIL(h);
+  if (!updates) return fail("null argument");
+  size_t n = size_t(e.B) * e.D * e.N;
+  if (upload(e, e.updates, updates, n)) return 1;
+  k_axpy<<<unsigned((n + 255) / 256), 256, 0, e.stream>>>(n, e.updates.p, e.theta.p);
+  if (check_launch(e, "k_axpy")) return 1;
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+int stomp_engine_compute_control_costs(void* h, const double* parameters, const double* noise, int32_t n, double weight,
+                                       double* control_costs) {
+  ENGINE_OR_FAIL(h);
+  if (!parameters || !noise || !control_costs || n < 1) return fail("bad argument");
+  if (!e.have_problems) return fail("set_problems must be called first (the padding values come from the policy)");
+  size_t total = size_t(e.B) * n;
+  if (ensure_scratch(e, total)) return 1;
+  size_t cnt = total * e.D * e.N;
+  CUDA_TRY(cudaMemcpyAsync(e.scratch_params.p, parameters, cnt * 8, cudaMemcpyHostToDevice, e.stream));
+  CUDA_TRY(cudaMemcpyAsync(e.scratch_noise.p, noise, cnt * 8, cudaMemcpyHostToDevice, e.stream));
+  GenArgs a = base_gen_args(e);
+  a.R = n; a.R_gen = n;
+  a.mode_generate = 0; a.mode_project = 0; a.mode_control = 1;
+  a.eps_in = e.scratch_noise.p; a.params = e.scratch_params.p; a.control = e.scratch_costs.p; a.noise_projected = nullptr;
+  a.control_weight = weight;
+  if (launch_generate(e, a)) return 1;
+  CUDA_TRY(cudaMemcpyAsync(control_costs, e.scratch_costs.p, cnt * 8, cudaMemcpyDeviceToHost, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+int stomp_engine_seed(void* h, uint64_t seed) {
+  ENGINE_OR_FAIL(h);
+  e.seed = seed;
+  return 0;
+}
+
+int stomp_engine_inject_noise(void* h, const double* eps, int32_t n) {
+  ENGINE_OR_FAIL(h);
+  if (!eps || n < 1 || n > e.R) return fail("bad argument");
+  if (e.eps_in.n != size_t(e.B) * e.R * e.D * e.N) CUDA_TRY(e.eps_in.alloc(size_t(e.B) * e.R * e.D * e.N));
+  size_t row = size_t(n) * e.D * e.N * 8;
+  CUDA_TRY(cudaMemcpy2DAsync(e.eps_in.p, size_t(e.R) * e.D * e.N * 8, eps, row, row, e.B, cudaMemcpyHostToDevice, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  e.injected_pending = true;
+  return 0;
+}
+
+int stomp_engine_sample_noise(void* h, int32_t iteration, int32_t n, double* eps_out) {
+  ENGINE_OR_FAIL(h);
+  if (!eps_out || n < 1) return fail("bad argument");
+  size_t total = size_t(e.B) * n;
+  if (ensure_scratch(e, total)) return 1;
+  std::vector<double> ones(e.D, 1.0);
+  if (set_noise_scale(e, ones.data())) return 1;
+  GenArgs a = base_gen_args(e);
+  a.R = n; a.R_gen = n;
+  a.mode_generate = 1; a.mode_project = 0; a.mode_control = 0; a.injected = 0;
+  a.iteration = uint32_t(iteration);
+  a.noise = e.scratch_noise.p; a.params = e.scratch_params.p; a.noise_projected = nullptr;
+  a.rollouts_global = std::max<int64_t>(a.rollouts_global, n);
+  if (launch_generate(e, a)) return 1;
+  CUDA_TRY(cudaMemcpyAsync(eps_out, e.scratch_noise.p, total * e.D * e.N * 8, cudaMemcpyDeviceToHost, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+int stomp_engine_execute(void* h, const double* parameters, int32_t n, int32_t iteration_number, double* costs,
+                         int32_t* collision_free) {
+  ENGINE_OR_FAIL(h);
+  if (!parameters || !costs || n < 1) return fail("bad argument");
+  size_t total = size_t(e.B) * n;
+  if (ensure_scratch(e, total)) return 1;
+  CUDA_TRY(cudaMemcpyAsync(e.scratch_params.p, parameters, total * e.D * e.N * 8, cudaMemcpyHostToDevice, e.stream));
+  if (launch_cost(e, e.scratch_params.p, size_t(n) * e.D * e.N, n, e.B, iteration_number == 1, e.scratch_costs.p, size_t(n) * e.N,
+                  e.scratch_flags.p, n, 0, nullptr, nullptr))
+    return 1;
+  CUDA_TRY(cudaMemcpyAsync(costs, e.scratch_costs.p, total * e.N * 8, cudaMemcpyDeviceToHost, e.stream));
+  if (collision_free) CUDA_TRY(cudaMemcpyAsync(collision_free, e.scratch_flags.p, total * 4, cudaMemcpyDeviceToHost, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+int stomp_engine_execute_debug(void* h, const double* parameters, stomp_sphere_debug* debug) {
+  ENGINE_OR_FAIL(h);
+  if (!parameters || !debug) return fail("bad argument");
+  if (ensure_scratch(e, size_t(e.B))) return 1;
+  CUDA_TRY(cudaMemcpyAsync(e.scratch_params.p, parameters, size_t(e.D) * e.N * 8, cudaMemcpyHostToDevice, e.stream));
+  CUDA_TRY(cudaMemsetAsync(e.debug.p, 0, e.debug.n * sizeof(stomp_sphere_debug), e.stream));
+  if (launch_cost(e, e.scratch_params.p, size_t(e.D) * e.N, 1, 1, 1, e.scratch_costs.p, size_t(e.N), e.scratch_flags.p, 1, 0,
+                  e.scratch_noise.p, e.debug.p))
+    return 1;
+  CUDA_TRY(cudaMemcpyAsync(debug, e.debug.p, size_t(e.N + 3) * e.K * sizeof(stomp_sphere_debug), cudaMemcpyDeviceToHost, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+int stomp_engine_get_rollouts(void* h, const double* noise_stddev, double* rollouts, int32_t* num_generated) {
+  ENGINE_OR_FAIL(h);
+  if (!noise_stddev) return fail("null argument");
+  if (!e.have_problems) return fail("set_problems must be called first");
+  if (set_noise_scale(e, noise_stddev)) return 1;
+  if (step_get_rollouts(e, 0, false)) return 1;
+  if (gather_reused_state(e)) return 1;
+  if (rollouts) {
+    size_t row = size_t(e.num_gen) * e.D * e.N * 8;
+    CUDA_TRY(cudaMemcpy2DAsync(rollouts, row, e.params[e.cur].p, size_t(e.R) * e.D * e.N * 8, row, e.B, cudaMemcpyDeviceToHost, e.stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  if (num_generated) *num_generated = e.num_gen;
+  return 0;
+}
+
+int stomp_engine_set_rollout_costs(void* h, const double* costs, double control_cost_weight, double* rollout_costs_total) {
+  ENGINE_OR_FAIL(h);
+  if (!costs) return fail("null argument");
+  if (e.num_gen < 1) return fail("get_rollouts must be called first");
+  e.control_cost_weight = control_cost_weight;
+  size_t row = size_t(e.num_gen) * e.N * 8;
+  CUDA_TRY(cudaMemcpy2DAsync(e.state[e.cur].p, size_t(e.R) * e.N * 8, costs, row, row, e.B, cudaMemcpyHostToDevice, e.stream));
+  if (step_control_costs(e)) return 1;
+  if (launch_cumulative(e)) return 1;
+  if (rollout_costs_total)
+    CUDA_TRY(cudaMemcpy2DAsync(rollout_costs_total, size_t(e.R) * 8, e.totals.p, size_t(e.R + 1) * 8, size_t(e.R) * 8, e.B,
+                               cudaMemcpyDeviceToHost, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+int stomp_engine_improve_policy(void* h, double* updates) {
+  ENGINE_OR_FAIL(h);
+  if (e.desc.rollout_shard_world > 1) return fail("use stomp_engine_iterate_sharded_phase on a rollout-sharded engine");
+  if (step_improve(e, 0)) return 1;
+  if (updates) CUDA_TRY(cudaMemcpyAsync(updates, e.updates.p, size_t(e.B) * e.D * e.N * 8, cudaMemcpyDeviceToHost, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+int stomp_engine_add_extra_rollouts(void* h, const double* costs) {
+  ENGINE_OR_FAIL(h);
+  if (!costs) return fail("null argument");
+  CUDA_TRY(cudaMemcpyAsync(e.extra_state.p, costs, size_t(e.B) * e.N * 8, cudaMemcpyHostToDevice, e.stream));
+  if (step_extra(e, false, 0)) return 1;
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+int stomp_engine_iterate(void* h, int32_t iteration_number, stomp_iter_stats* stats) {
+  ENGINE_OR_FAIL(h);
+  if (!e.have_problems) return fail("set_problems must be called first");
+  if (iterate_once(e, iteration_number)) return 1;
+  return fill_stats(e, stats);
+}
+
+int stomp_engine_run(void* h, int32_t first_iteration, int32_t count, stomp_iter_stats* last_stats) {
+  ENGINE_OR_FAIL(h);
+  if (!e.have_problems) return fail("set_problems must be called first");
+  for (int i = 0; i < count; ++i)
+    if (iterate_once(e, first_iteration + i)) return 1;
+  return fill_stats(e, last_stats);
+}
+
+int stomp_engine_synchronize(void* h) {
+  ENGINE_OR_FAIL(h);
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+int stomp_engine_get(void* h, int32_t field, void* out, size_t bytes) {
+  ENGINE_OR_FAIL(h);
+  if (!out) return fail("null argument");
+  const size_t BDN = size_t(e.B) * e.D * e.N, BRDN = BDN * e.R, NN = size_t(e.N) * e.N;
+  const void* src = nullptr;
+  size_t need = 0;
+  std::vector<double> host;
+  switch (field) {
+    case STOMP_FIELD_THETA: src = e.theta.p; need = BDN * 8; break;
+    case STOMP_FIELD_NOISE: src = e.noise.p; need = BRDN * 8; break;
+    case STOMP_FIELD_PARAMETERS: src = e.params[e.cur].p; need = BRDN * 8; break;
+    case STOMP_FIELD_NOISE_PROJECTED: src = e.noise_projected.p; need = BRDN * 8; break;
+    case STOMP_FIELD_STATE_COSTS: src = e.state[e.cur].p; need = size_t(e.B) * e.R * e.N * 8; break;
+    case STOMP_FIELD_CONTROL_COSTS: src = e.control.p; need = BRDN * 8; break;
+    case STOMP_FIELD_CUMULATIVE_COSTS: src = e.cumulative.p; need = BRDN * 8; break;
+    case STOMP_FIELD_PROBABILITIES: src = e.probabilities.p; need = BRDN * 8; break;
+    case STOMP_FIELD_UPDATES: src = e.updates.p; need = BDN * 8; break;
+    case STOMP_FIELD_NOISELESS_COSTS: src = e.extra_state.p; need = size_t(e.B) * e.N * 8; break;
+    case STOMP_FIELD_COLLISION_FREE: src = e.collision_free.p; need = size_t(e.B) * (e.R + 1) * 4; break;
+    case STOMP_FIELD_ROLLOUT_TOTAL_COSTS: src = e.totals.p; need = size_t(e.B) * (e.R + 1) * 8; break;
+    case STOMP_FIELD_CLIPPED_PARAMETERS: src = e.clipped.p; need = BRDN * 8; break;
+    case STOMP_FIELD_INV_CONTROL_COST: host = e.pm.Rinv.a; need = NN * 8; break;
+    case STOMP_FIELD_CONTROL_COST: host = e.pm.R.a; need = NN * 8; break;
+    case STOMP_FIELD_QUAD_COST_INV: host = e.pm.Qinv.a; need = NN * 8; break;
+    case STOMP_FIELD_NOISE_CHOLESKY: {
+      sh::Dense L;
+      if (!sh::cholesky_lower(e.pm.Rinv, L)) return fail("R^-1 is not positive definite");
+      host = L.a; need = NN * 8; break;
+    }
+    case STOMP_FIELD_PROJECTION: {
+      host = e.pm.Rinv.a;
+      for (int i = 0; i < e.N; ++i)
+        for (int p = 0; p < e.N; ++p) host[size_t(i) * e.N + p] *= e.pm.proj_scale[p];
+      need = NN * 8; break;
+    }
+    default: return fail("unknown field");
+  }
+  if (bytes < need) return fail("output buffer too small");
+  if (!host.empty()) { std::memcpy(out, host.data(), need); return 0; }
+  if (!src) return fail("this field is only stored when keep_intermediates is set");
+  CUDA_TRY(cudaMemcpyAsync(out, src, need, cudaMemcpyDeviceToHost, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+int64_t stomp_engine_launch_count(void* h) { return h ? E(h)->launches : -1; }
+void* stomp_engine_stream(void* h) { return h ? static_cast<void*>(E(h)->stream) : nullptr; }
+
+int stomp_engine_timer_start(void* h) {
+  ENGINE_OR_FAIL(h);
+  CUDA_TRY(cudaEventRecord(e.ev0, e.stream));
+  return 0;
+}
+int stomp_engine_timer_stop(void* h, float* elapsed_ms) {
+  ENGINE_OR_FAIL(h);
+  CUDA_TRY(cudaEventRecord(e.ev1, e.stream));
+  CUDA_TRY(cudaEventSynchronize(e.ev1));
+  if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, e.ev0, e.ev1));
+  return 0;
+}
+
+int stomp_engine_shard_buffers(void* h, void** minmax_dev, void** sums_dev, size_t* bytes_each) {
+  ENGINE_OR_FAIL(h);
+  if (minmax_dev) *minmax_dev = e.minmax.p;
+  if (sums_dev) *sums_dev = e.sums.p;
+  if (bytes_each) *bytes_each = size_t(2) * e.D * e.N * 8;
+  return 0;
+}
+
+/* phase 0: rollouts, costs, local {max c, max -c}  -> caller all-reduces minmax with MAX
+ * phase 1: local {sum e, sum e*eps}                -> caller all-reduces sums with SUM
+ * phase 2: update + noise-less rollout (replicated on every rank) */
+int stomp_engine_iterate_sharded_phase(void* h, int32_t iteration_number, int32_t phase) {
+  ENGINE_OR_FAIL(h);
+  if (!e.have_problems) return fail("set_problems must be called first");
+  if (e.B != 1) return fail("rollout sharding requires num_problems == 1");
+  switch (phase) {
+    case 0: if (iterate_front(e, iteration_number)) return 1; return launch_minmax(e);
+    case 1: return launch_sums(e);
+    case 2: if (launch_finalize(e, 1)) return 1; return step_extra(e, true, iteration_number);
+    default: return fail("phase must be 0, 1 or 2");
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,807 @@
+// kernels.cuh — sm_100a device code of the STOMP rollout engine.
+//
+// Data layout in HBM (all fp64 unless noted; the LAST index is time and is contiguous):
+//   theta[B][D][N]   pad_start[B][D]   pad_goal[B][D]
+//   noise / params / control_costs / cumulative [B][R][D][N]      state_costs[B][R][N]
+//   voxels[nx][ny][nz] (u8 / u16 squared cell distance, or f32 metres)
+//
+// Kernel <-> reference map (paths relative to stomp_motion_planner/ in the reference):
+//   k_select_reuse   PolicyImprovement::generateRollouts, reuse part   src/policy_improvement.cpp:178-225
+//   k_generate       generateRollouts (new part) + computeProjectedNoise + computeControlCosts
+//                    src/policy_improvement.cpp:228-236,473-489; src/covariant_trajectory_policy.cpp:228-255;
+//                    include/stomp_motion_planner/multivariate_gaussian.h:88-94
+//   k_cost           StompOptimizer::execute / handleJointLimits / performForwardKinematics
+//                    src/stomp_optimizer.cpp:562-709,1063-1165; stomp_collision_space.h:193-228
+//   k_cumulative     computeRolloutCumulativeCosts + Rollout::getCost   src/policy_improvement.cpp:149-156,301-320
+//   k_update         computeRolloutProbabilities + computeParameterUpdates + updateParameters
+//                    src/policy_improvement.cpp:322-383; src/covariant_trajectory_policy.cpp:306-323
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/stomp_b200.h"
+
+namespace stomp_dev {
+
+constexpr int kPad = STOMP_DIFF_RULE_LENGTH - 1;  // 6 fixed points each side
+constexpr int kMaxHb = 6;                         // half bandwidth of R (jerk stencil: 5, +1 spare)
+constexpr int kMaxSlots = 4;
+constexpr int kTileSteps = 29;                    // productive timesteps per warp (lanes 1..29; halo -1, +1, +2)
+
+// ---------------------------------------------------------------------------------------------
+// device tables
+// ---------------------------------------------------------------------------------------------
+template <typename Real>
+struct DevNode {
+  Real A0[9], A1[9], A2[9], p[3], ax[3];
+  int parent, type, q_index, save_slot, load_slot, sphere_begin, sphere_end, pad_;
+};
+
+template <typename Real>
+struct DevSphere {
+  Real pos[3], radius, clearance, inv_clearance, weight;
+  int original_index;
+};
+
+struct Band {           // banded Cholesky factor of R and the projection scaling
+  const double* band;   // [N][hb+1], band[i][k] = C(i, i-k)
+  const double* inv_diag;   // [N]
+  const double* proj_scale; // [N]
+  int hb;
+};
+
+struct Stencil {        // control-cost stencils of CovariantTrajectoryPolicy
+  double coef[3][7];    // rule_k[j] / dt^(k+1)
+  double weight[3];     // derivative_costs
+};
+
+struct Sdf {
+  const void* vox;
+  int nx, ny, nz, dtype;
+  double origin[3], res, inv_res;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller: one stream per (problem, global rollout, dimension), counter = sample pair
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+__device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t stream, uint32_t iteration, uint32_t pair,
+                                            double& z0, double& z1) {
+  uint32_t c[4] = {pair, iteration, uint32_t(stream), uint32_t(stream >> 32)};
+  philox4x32_10(c, uint32_t(seed), uint32_t(seed >> 32));
+  // 53-bit uniforms in (0,1]
+  double u1 = (double((uint64_t(c[0]) << 21) ^ (uint64_t(c[1]) >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
+  double u2 = (double((uint64_t(c[2]) << 21) ^ (uint64_t(c[3]) >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
+  double r = sqrt(-2.0 * log(u1));
+  double s, co;
+  sincospi(2.0 * u2, &s, &co);
+  z0 = r * co;
+  z1 = r * s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_select_reuse: per problem, rank (cost, index) pairs ascending like std::sort on std::pair<double,int>;
+// the extra (noise-less) rollout has index -1 and therefore wins ties.  out: src[b][j] for j < R_reuse
+// (>=0: rollout slot of the previous iteration, -1: the extra rollout).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_select_reuse(const double* __restrict__ totals, int R, int R_reuse, int use_extra,
+                               int* __restrict__ reuse_src) {
+  int b = blockIdx.x;
+  const double* tot = totals + size_t(b) * (R + 1);
+  int n = R + (use_extra ? 1 : 0);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double ci = tot[i];
+    int ii = (i == R) ? -1 : i;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      double cj = tot[j];
+      int jj = (j == R) ? -1 : j;
+      rank += (cj < ci) || (cj == ci && jj < ii);
+    }
+    if (rank < R_reuse) reuse_src[size_t(b) * R_reuse + rank] = ii;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_generate: one thread per vector v = (b, r, d); the time series lives in one padded shared-memory row.
+// ---------------------------------------------------------------------------------------------
+struct GenArgs {
+  int B, R, D, N;
+  int R_gen;                 // slots < R_gen are new, slots >= R_gen are reused (gathered)
+  int mode_generate;         // 1: produce noise/params (new: sample or injected; reused: gather)
+  int mode_project;          // 1: y = M * noise is added before the stencil; 0: stencil on params + eps_in
+  int mode_control;          // 1: compute control costs
+  int injected;              // 1: noise for new rollouts comes from eps_in
+  int extra;                 // 1: vectors are (b, d) of the extra rollout: params = theta, noise = 0
+  double control_weight;     // 0.5 * control_cost_weight
+  uint64_t seed;
+  uint32_t iteration;
+  int64_t rollout_id_offset; // global rollout id of local slot 0 (rollout sharding)
+  int64_t rollouts_global;   // global number of rollouts per problem (stream id stride)
+  const double* theta;       // [B][D][N]
+  const double* pad_start;   // [B][D]
+  const double* pad_goal;    // [B][D]
+  const double* noise_scale; // [D] sigma_d * decay_d^(it-1)
+  const double* eps_in;      // [B][R][D][N] injected noise (or caller noise when !mode_project)
+  const double* params_prev; // [B][R][D][N] previous-iteration parameters (reuse gather)
+  const int* reuse_src;      // [B][R_reuse]
+  double* noise;             // [B][R][D][N]
+  double* params;            // [B][R][D][N]  (extra: unused)
+  double* noise_projected;   // optional tap
+  double* control;           // [B][R][D][N]  (extra: [B][D][N])
+  Band band;
+  Stencil st;
+};
+
+__device__ __forceinline__ void band_forward(double* x, const double* sb, const double* sinv, int N, int hb) {
+  for (int i = 0; i < N; ++i) {
+    double s = x[i];
+    int kmax = min(hb, i);
+    for (int k = 1; k <= kmax; ++k) s -= sb[i * (hb + 1) + k] * x[i - k];
+    x[i] = s * sinv[i];
+  }
+}
+
+__device__ __forceinline__ void band_backward(double* x, const double* sb, const double* sinv, int N, int hb) {
+  for (int i = N - 1; i >= 0; --i) {
+    double s = x[i];
+    int kmax = min(hb, N - 1 - i);
+    for (int k = 1; k <= kmax; ++k) s -= sb[(i + k) * (hb + 1) + k] * x[i + k];
+    x[i] = s * sinv[i];
+  }
+}
+
+// One thread owns one vector v = (b, r, d) (or (b, d) for the extra rollout); its time series lives in one
+// shared-memory row with an odd stride, so the sequential band solves and stencils are bank-conflict free.
+// All global traffic is done by the whole CTA on the contiguous [blockDim][N] tile (coalesced).
+__global__ void k_generate(GenArgs a) {
+  extern __shared__ double smem[];
+  const int N = a.N, hb = a.band.hb, TPB = blockDim.x;
+  const int stride = N | 1;
+  double* sband = smem;                      // [N][hb+1]
+  double* sinv = sband + N * (hb + 1);       // [N]
+  double* sscale = sinv + N;                 // [N]
+  double* rows = sscale + N;                 // [TPB][stride]
+  const double** s_theta = reinterpret_cast<const double**>(rows + size_t(TPB) * stride);  // [TPB]
+  const double** s_prev = s_theta + TPB;     // [TPB] reused-rollout source row (NULL for new rollouts)
+  for (int i = threadIdx.x; i < N * (hb + 1); i += TPB) sband[i] = a.band.band[i];
+  for (int i = threadIdx.x; i < N; i += TPB) sinv[i] = a.band.inv_diag[i], sscale[i] = a.band.proj_scale[i];
+
+  const int per_problem = (a.extra ? 1 : a.R) * a.D;
+  const long long nvec = (long long)a.B * per_problem;
+  const long long v0 = (long long)blockIdx.x * TPB;
+  const long long v = v0 + threadIdx.x;
+  const int nrows = int(min((long long)TPB, nvec - v0));   // rows of this CTA that exist
+  const bool active = v < nvec;
+  int b = 0, r = 0, d = 0;
+  if (active) {
+    b = int(v / per_problem);
+    int rem = int(v - (long long)b * per_problem);
+    r = rem / a.D;
+    d = rem - r * a.D;
+  }
+  const bool is_new = a.extra ? true : (r < a.R_gen);
+  const size_t tile_off = size_t(v0) * N;
+  const size_t tile_len = size_t(nrows) * N;
+  double* x = rows + size_t(threadIdx.x) * stride;
+  {
+    const double* th = a.theta + (size_t(b) * a.D + d) * N;
+    const double* pv = nullptr;
+    if (active && !a.extra && !is_new) {
+      int src = a.reuse_src[size_t(b) * (a.R - a.R_gen) + (r - a.R_gen)];
+      pv = src >= 0 ? a.params_prev + ((size_t(b) * a.R + src) * a.D + d) * N : th;
+    }
+    s_theta[threadIdx.x] = th;
+    s_prev[threadIdx.x] = pv;
+  }
+  __syncthreads();
+
+  // ---- 1. noise into the rows --------------------------------------------------------------
+  if (a.extra) {
+    for (size_t k = threadIdx.x; k < tile_len; k += TPB) rows[(k / N) * stride + (k % N)] = 0.0;
+  } else if (!a.mode_generate) {
+    const double* src = (a.mode_project ? a.noise : a.eps_in) + tile_off;
+    for (size_t k = threadIdx.x; k < tile_len; k += TPB) rows[(k / N) * stride + (k % N)] = src[k];
+  } else {
+    for (size_t k = threadIdx.x; k < tile_len; k += TPB) {
+      int row = int(k / N), col = int(k % N);
+      const double* pv = s_prev[row];
+      double val = 0.0;
+      if (pv) val = pv[col] - s_theta[row][col];          // noise = parameters - theta, policy_improvement.cpp:222
+      else if (a.injected) val = a.eps_in[tile_off + k];
+      rows[row * stride + col] = val;
+    }
+    __syncthreads();
+    if (active && is_new && !a.injected) {
+      uint64_t stream = (uint64_t(b) * uint64_t(a.rollouts_global) + uint64_t(a.rollout_id_offset + r)) * uint64_t(a.D) + d;
+      for (int i = 0; i < N; i += 2) {
+        double z0, z1;
+        normal_pair(a.seed, stream, a.iteration, uint32_t(i >> 1), z0, z1);
+        x[i] = z0;
+        if (i + 1 < N) x[i + 1] = z1;
+      }
+      // eps = sigma * C^-T z  ~ N(0, sigma^2 R^-1)  with R = C C^T
+      band_backward(x, sband, sinv, N, hb);
+      double sg = a.noise_scale[d];
+      for (int i = 0; i < N; ++i) x[i] *= sg;
+    }
+    __syncthreads();
+    for (size_t k = threadIdx.x; k < tile_len; k += TPB) {
+      int row = int(k / N), col = int(k % N);
+      double e = rows[row * stride + col];
+      const double* pv = s_prev[row];
+      a.noise[tile_off + k] = e;
+      a.params[tile_off + k] = pv ? pv[col] : s_theta[row][col] + e;
+    }
+  }
+  if (!a.mode_control) return;
+  __syncthreads();
+
+  // ---- 2. projected noise y = R^-1 (s .* eps) --------------------------------------------------
+  if (a.mode_project && !a.extra) {
+    if (active) {
+      for (int i = 0; i < N; ++i) x[i] *= sscale[i];
+      band_forward(x, sband, sinv, N, hb);
+      band_backward(x, sband, sinv, N, hb);
+    }
+    __syncthreads();
+    if (a.noise_projected)
+      for (size_t k = threadIdx.x; k < tile_len; k += TPB) a.noise_projected[tile_off + k] = rows[(k / N) * stride + (k % N)];
+  }
+  // ---- 3. x = parameters + y -------------------------------------------------------------------
+  {
+    const double* pp = a.extra ? a.theta + tile_off : a.params + tile_off;
+    for (size_t k = threadIdx.x; k < tile_len; k += TPB) rows[(k / N) * stride + (k % N)] += pp[k];
+  }
+  __syncthreads();
+  // ---- 4. control-cost stencils over the padded series, in place (sliding register window) -----
+  if (active) {
+    const double xs = a.pad_start[size_t(b) * a.D + d], xg = a.pad_goal[size_t(b) * a.D + d];
+    const int Nall = N + 2 * kPad;
+    auto xall = [&](int idx) -> double {
+      if (idx < 0 || idx >= Nall) return 0.0;   // dropped taps of the differentiation matrices
+      return idx < kPad ? xs : (idx >= kPad + N ? xg : x[idx - kPad]);
+    };
+    double w[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) w[j] = xall(j - 3);
+    double hc[kPad], tc[kPad];
+    for (int i = 0; i < Nall; ++i) {
+      double cost = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (a.st.weight[k] == 0.0) continue;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) acc += a.st.coef[k][j] * w[j];
+        cost += a.control_weight * a.st.weight[k] * (acc * acc);
+      }
+      double next = xall(i + 4);   // read before x[i - kPad] is overwritten (it is x[i + 4 - kPad])
+      if (i < kPad) {
+#pragma unroll
+        for (int q = 0; q < kPad; ++q) if (q == i) hc[q] = cost;
+      } else if (i >= kPad + N) {
+#pragma unroll
+        for (int q = 0; q < kPad; ++q) if (q == i - kPad - N) tc[q] = cost;
+      } else {
+        x[i - kPad] = cost;
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) w[j] = w[j + 1];
+      w[6] = next;
+    }
+    // fold the padded entries: covariant_trajectory_policy.cpp:245-250
+#pragma unroll
+    for (int i = 0; i < kPad; ++i) {
+      x[0] += hc[i];
+      x[N - 1] += tc[kPad - 1 - i];
+    }
+  }
+  __syncthreads();
+  for (size_t k = threadIdx.x; k < tile_len; k += TPB) a.control[tile_off + k] = rows[(k / N) * stride + (k % N)];
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_cost: the cost plugin.  One CTA per rollout; each warp owns a tile of 29 free timesteps
+// (lane l <-> timestep tile*29 - 1 + l), so the finite-difference velocity taps (-1, 0, +1, +2) of the
+// productive lanes 1..29 come from neighbouring lanes by warp shuffle and no sphere position ever leaves
+// the register file.
+// ---------------------------------------------------------------------------------------------
+template <typename Real>
+struct CostArgs {
+  int n_rollouts;            // rollouts per problem processed by this launch
+  int D, N, K, num_nodes;
+  int include_pads;          // 1: start/goal padding points count towards collision_free (iteration_ == 0)
+  size_t params_problem_stride, params_rollout_stride;  // in doubles
+  size_t cost_problem_stride;                           // in doubles
+  int flag_problem_stride, flag_offset;
+  const double* params;      // rollout parameters
+  const double* pad_start;   // [B][D]
+  const double* pad_goal;    // [B][D]
+  const double* qinv_t;      // [N][N] transposed scaled quad_cost_inv_ (row fv = column fv)
+  const int* has_limits;     // [D]
+  const double* limit_min;   // [D]
+  const double* limit_max;   // [D]
+  const DevNode<Real>* nodes;
+  const DevSphere<Real>* spheres;
+  const Real* sqrt_table;    // [256] distance of a squared cell distance (u8 grids)
+  Sdf sdf;
+  double inv_time;           // 1/discretization
+  double obstacle_weight;
+  double* costs;             // [..][N]
+  int* collision_free;       // [..]
+  double* clipped;           // optional tap [same layout as params]
+  stomp_sphere_debug* debug; // optional tap [N+3][K] (rollout 0 of problem 0)
+};
+
+template <typename Real> struct Math;
+template <> struct Math<double> {
+  static __device__ __forceinline__ void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
+  static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+  static __device__ __forceinline__ double round_(double x) { return round(x); }
+  static __device__ __forceinline__ double fabs_(double x) { return fabs(x); }
+};
+template <> struct Math<float> {
+  static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
+  static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+  static __device__ __forceinline__ float round_(float x) { return roundf(x); }
+  static __device__ __forceinline__ float fabs_(float x) { return fabsf(x); }
+};
+
+__device__ __forceinline__ double shfl_rel(double v, int delta) {
+  // value of lane (lane + delta), clamped at the warp edges (edge lanes are halo lanes, never productive)
+  return delta < 0 ? __shfl_up_sync(0xffffffffu, v, unsigned(-delta)) : __shfl_down_sync(0xffffffffu, v, unsigned(delta));
+}
+__device__ __forceinline__ float shfl_rel(float v, int delta) {
+  return delta < 0 ? __shfl_up_sync(0xffffffffu, v, unsigned(-delta)) : __shfl_down_sync(0xffffffffu, v, unsigned(delta));
+}
+
+template <typename Real>
+__device__ __forceinline__ int voxel_cell(Real pos, Real origin, Real res, Real inv_res) {
+  // distance_field VoxelGrid::getCellFromLocation: int(round((loc - origin) / resolution)).
+  // Fast path multiplies by 1/res; whenever that product is within 1e-6 of a rounding boundary the exact
+  // division decides, so the index is bit-identical to the division form.
+  Real t = (pos - origin) * inv_res;
+  Real r = Math<Real>::round_(t);
+  if (Math<Real>::fabs_(Math<Real>::fabs_(t - r) - Real(0.5)) < Real(1e-6)) r = Math<Real>::round_((pos - origin) / res);
+  return int(r);
+}
+
+template <typename Real, bool kDebug>
+__global__ void __launch_bounds__(256) k_cost(CostArgs<Real> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int D = a.D, N = a.N, K = a.K;
+  double* q = reinterpret_cast<double*>(smem_raw);                        // [D][N] clipped trajectory
+  DevNode<Real>* nodes = reinterpret_cast<DevNode<Real>*>(q + size_t(D) * N);
+  DevSphere<Real>* spheres = reinterpret_cast<DevSphere<Real>*>(nodes + a.num_nodes);
+  Real* sqrt_tab = reinterpret_cast<Real*>(spheres + K);                  // [256]
+  __shared__ int s_collision;
+
+  const int b = blockIdx.x / a.n_rollouts, r = blockIdx.x - b * a.n_rollouts;
+  const double* src = a.params + size_t(b) * a.params_problem_stride + size_t(r) * a.params_rollout_stride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+
+  for (int i = threadIdx.x; i < D * N; i += blockDim.x) q[i] = src[i];
+  {
+    const int* s32 = reinterpret_cast<const int*>(a.nodes);
+    int* d32 = reinterpret_cast<int*>(nodes);
+    for (int i = threadIdx.x; i < int(sizeof(DevNode<Real>) / 4) * a.num_nodes; i += blockDim.x) d32[i] = s32[i];
+    s32 = reinterpret_cast<const int*>(a.spheres);
+    d32 = reinterpret_cast<int*>(spheres);
+    for (int i = threadIdx.x; i < int(sizeof(DevSphere<Real>) / 4) * K; i += blockDim.x) d32[i] = s32[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sqrt_tab[i] = a.sqrt_table[i];
+  }
+  if (threadIdx.x == 0) s_collision = 0;
+  __syncthreads();
+
+  // ---- handleJointLimits: warp per joint, <= 11 passes of (arg max violation, rank-1 correction) ----------
+  for (int d = warp; d < D; d += nwarps) {
+    if (!a.has_limits[d]) continue;
+    const double jmax = a.limit_max[d], jmin = a.limit_min[d];
+    double* qd = q + size_t(d) * N;
+    for (int count = 0; count < 11; ++count) {
+      double best_abs = 1e-6, best_amount = 0.0;
+      int best_idx = -1;
+      for (int i = lane; i < N; i += 32) {
+        double v = qd[i], amount = 0.0;
+        if (v > jmax) amount = jmax - v;
+        else if (v < jmin) amount = jmin - v;
+        double aa = fabs(amount);
+        if (aa > best_abs) { best_abs = aa; best_amount = amount; best_idx = i; }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        double oa = __shfl_xor_sync(0xffffffffu, best_abs, off);
+        double om = __shfl_xor_sync(0xffffffffu, best_amount, off);
+        int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
+        // strict '>' in index order keeps the first maximum: larger violation wins, ties -> smaller index
+        bool take = (oi >= 0) && (best_idx < 0 || oa > best_abs || (oa == best_abs && oi < best_idx));
+        if (take) { best_abs = oa; best_amount = om; best_idx = oi; }
+      }
+      if (best_idx < 0) break;
+      const double* col = a.qinv_t + size_t(best_idx) * N;
+      double multiplier = best_amount / col[best_idx];
+      for (int i = lane; i < N; i += 32) qd[i] += multiplier * col[i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (a.clipped) {
+    double* dst = a.clipped + size_t(b) * a.params_problem_stride + size_t(r) * a.params_rollout_stride;
+    for (int i = threadIdx.x; i < D * N; i += blockDim.x) dst[i] = q[i];
+  }
+
+  // ---- FK + spheres + SDF + velocity + cost -------------------------------------------------------
+  const double* ps = a.pad_start + size_t(b) * D;
+  const double* pg = a.pad_goal + size_t(b) * D;
+  const Real ox = Real(a.sdf.origin[0]), oy = Real(a.sdf.origin[1]), oz = Real(a.sdf.origin[2]);
+  const Real res = Real(a.sdf.res), inv_res = Real(a.sdf.inv_res);
+  const Real c_m1 = Real(a.inv_time * (-2.0 / 6.0)), c_0 = Real(a.inv_time * (-3.0 / 6.0)), c_p1 = Real(a.inv_time * (6.0 / 6.0)),
+             c_p2 = Real(a.inv_time * (-1.0 / 6.0));
+  const int ntiles = (N + kTileSteps - 1) / kTileSteps;
+  double* out = a.costs + size_t(b) * a.cost_problem_stride + size_t(r) * N;
+  int collided = 0;
+
+  for (int tile = warp; tile < ntiles; tile += nwarps) {
+    const int t = tile * kTileSteps - 1 + lane;      // trajectory point of this lane (-1 .. N+1 are meaningful)
+    const bool productive = lane >= 1 && lane <= kTileSteps && t < N;
+    const bool counts = productive || (a.include_pads && (t == -1 || t == N));
+    Real cost = Real(0);
+    Real F[12], saved[kMaxSlots][12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) F[i] = Real(0);
+
+    for (int n = 0; n < a.num_nodes; ++n) {
+      const DevNode<Real>& nd = nodes[n];
+      Real Pm[12];
+      {
+        Real qv = Real(0);
+        if (nd.q_index >= 0) qv = Real(t < 0 ? ps[nd.q_index] : (t >= N ? pg[nd.q_index] : q[size_t(nd.q_index) * N + t]));
+        if (nd.type == STOMP_JOINT_REVOLUTE) {
+          Real s, c;
+          Math<Real>::sincos_(qv, &s, &c);
+#pragma unroll
+          for (int i = 0; i < 9; ++i) Pm[i] = nd.A0[i] + c * nd.A1[i] + s * nd.A2[i];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) Pm[9 + i] = nd.p[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) Pm[i] = nd.A0[i];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) Pm[9 + i] = nd.p[i] + qv * nd.ax[i];
+        }
+      }
+      if (nd.parent < 0) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) F[i] = Pm[i];
+      } else {
+        Real Pf[12];
+        if (nd.load_slot >= 0) {
+#pragma unroll
+          for (int i = 0; i < 12; ++i) Pf[i] = saved[nd.load_slot][i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 12; ++i) Pf[i] = F[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) F[i * 3 + j] = Pf[i * 3] * Pm[j] + Pf[i * 3 + 1] * Pm[3 + j] + Pf[i * 3 + 2] * Pm[6 + j];
+          F[9 + i] = Pf[i * 3] * Pm[9] + Pf[i * 3 + 1] * Pm[10] + Pf[i * 3 + 2] * Pm[11] + Pf[9 + i];
+        }
+      }
+      if (nd.save_slot >= 0) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) saved[nd.save_slot][i] = F[i];
+      }
+      if (nd.sphere_end > nd.sphere_begin) {
+        // velocity frame: V = sum_k rule_k/dt * F(t+k); vel(sphere) = V.R * p + V.p  (linear in the frame)
+        Real V[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+          V[i] = c_m1 * shfl_rel(F[i], -1) + c_0 * F[i] + c_p1 * shfl_rel(F[i], 1) + c_p2 * shfl_rel(F[i], 2);
+        for (int j = nd.sphere_begin; j < nd.sphere_end; ++j) {
+          const DevSphere<Real>& sp = spheres[j];
+          Real px = F[0] * sp.pos[0] + F[1] * sp.pos[1] + F[2] * sp.pos[2] + F[9];
+          Real py = F[3] * sp.pos[0] + F[4] * sp.pos[1] + F[5] * sp.pos[2] + F[10];
+          Real pz = F[6] * sp.pos[0] + F[7] * sp.pos[1] + F[8] * sp.pos[2] + F[11];
+          Real vx = V[0] * sp.pos[0] + V[1] * sp.pos[1] + V[2] * sp.pos[2] + V[9];
+          Real vy = V[3] * sp.pos[0] + V[4] * sp.pos[1] + V[5] * sp.pos[2] + V[10];
+          Real vz = V[6] * sp.pos[0] + V[7] * sp.pos[1] + V[8] * sp.pos[2] + V[11];
+          int cx = voxel_cell<Real>(px, ox, res, inv_res);
+          int cy = voxel_cell<Real>(py, oy, res, inv_res);
+          int cz = voxel_cell<Real>(pz, oz, res, inv_res);
+          Real dist = Real(0);
+          if (cx >= 1 && cy >= 1 && cz >= 1 && cx < a.sdf.nx - 1 && cy < a.sdf.ny - 1 && cz < a.sdf.nz - 1) {
+            size_t idx = (size_t(cx) * a.sdf.ny + cy) * a.sdf.nz + cz;
+            if (a.sdf.dtype == STOMP_VOXEL_U8_SQ) dist = sqrt_tab[__ldg(static_cast<const uint8_t*>(a.sdf.vox) + idx)];
+            else if (a.sdf.dtype == STOMP_VOXEL_U16_SQ)
+              dist = Math<Real>::sqrt_(Real(__ldg(static_cast<const uint16_t*>(a.sdf.vox) + idx))) * res;
+            else dist = Real(__ldg(static_cast<const float*>(a.sdf.vox) + idx));
+          }
+          Real dd = dist - sp.radius, pot;
+          if (dd >= sp.clearance) pot = Real(0);
+          else if (dd >= Real(0)) { Real diff = dd - sp.clearance; pot = Real(0.5) * (diff * sp.inv_clearance) * diff; }
+          else pot = -dd + Real(0.5) * sp.clearance;
+          Real vm = Math<Real>::sqrt_(vx * vx + vy * vy + vz * vz);
+          bool hit = dist <= sp.radius;
+          cost += sp.weight * (pot * vm);
+          if (hit && counts) collided = 1;
+          if (kDebug) {
+            if (t >= -1 && t <= N + 1 && (lane >= 1 && lane <= kTileSteps || (tile == 0 && lane == 0) ||
+                                           (tile == ntiles - 1 && lane > kTileSteps))) {
+              stomp_sphere_debug& rec = a.debug[size_t(t + 1) * K + sp.original_index];
+              rec.voxel[0] = cx; rec.voxel[1] = cy; rec.voxel[2] = cz;
+              rec.in_collision = hit;
+              rec.position[0] = px; rec.position[1] = py; rec.position[2] = pz;
+              rec.potential = pot;
+              rec.vel_mag = (t >= 0 && t < N && lane >= 1 && lane <= kTileSteps) ? double(vm) : 0.0;
+            }
+          }
+        }
+      }
+    }
+    if (productive) out[t] = a.obstacle_weight * double(cost);
+  }
+  if (collided) s_collision = 1;
+  __syncthreads();
+  if (threadIdx.x == 0 && a.collision_free)
+    a.collision_free[size_t(b) * a.flag_problem_stride + a.flag_offset + r] = s_collision ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-wide reverse inclusive scan over threads (warp shuffles + one shared array)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_suffix_scan(double v, double* swarp /* [32] */, double carry_in, double* carry_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    double o = __shfl_down_sync(0xffffffffu, v, off);
+    if (lane + off < 32) v += o;
+  }
+  if (lane == 0) swarp[warp] = v;  // total of the warp
+  __syncthreads();
+  double add = carry_in;
+  for (int w = warp + 1; w < nwarps; ++w) add += swarp[w];
+  double total = carry_in;
+  for (int w = 0; w < nwarps; ++w) total += swarp[w];
+  __syncthreads();
+  *carry_out = total;
+  return v + add;
+}
+
+// k_cumulative: CTA per (b, r).  cumulative[b][r][d][t] = S + C[d] (suffix-summed over t when enabled) and
+// totals[b][r] = sum_t S + sum_d sum_t C[d]  (Rollout::getCost).
+__global__ void k_cumulative(int R, int D, int N, int use_cumulative, const double* __restrict__ state,
+                             const double* __restrict__ control, double* __restrict__ cumulative,
+                             double* __restrict__ totals) {
+  __shared__ double swarp[32];
+  __shared__ double sred[32];
+  const int b = blockIdx.x / R, r = blockIdx.x - b * R;
+  const double* S = state + (size_t(b) * R + r) * N;
+  const double* C = control + (size_t(b) * R + r) * D * N;
+  double* out = cumulative + (size_t(b) * R + r) * D * N;
+  double acc = 0.0;
+  for (int t = threadIdx.x; t < N; t += blockDim.x) acc += S[t];
+  const int nchunks = (N + blockDim.x - 1) / blockDim.x;
+  for (int d = 0; d < D; ++d) {
+    double carry = 0.0;
+    for (int chunk = nchunks - 1; chunk >= 0; --chunk) {
+      int t = chunk * blockDim.x + threadIdx.x;
+      double c = 0.0, s = 0.0;
+      if (t < N) { c = C[size_t(d) * N + t]; s = S[t]; acc += c; }
+      double v = s + c;
+      if (use_cumulative) {
+        double next;
+        v = block_suffix_scan(t < N ? v : 0.0, swarp, carry, &next);
+        carry = next;
+      }
+      if (t < N) out[size_t(d) * N + t] = v;
+    }
+  }
+  // block reduce acc
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) sred[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += sred[w];
+    totals[size_t(b) * (R + 1) + r] = s;
+  }
+}
+
+// k_extra_total: totals[b][R] of the extra rollout = sum S_extra + sum control_extra
+__global__ void k_extra_total(int R, int D, int N, const double* __restrict__ state_extra,
+                              const double* __restrict__ control_extra, double* __restrict__ totals,
+                              double* __restrict__ noiseless_cost) {
+  __shared__ double sred[32];
+  const int b = blockIdx.x;
+  double acc = 0.0, accs = 0.0;
+  for (int t = threadIdx.x; t < N; t += blockDim.x) accs += state_extra[size_t(b) * N + t];
+  for (int i = threadIdx.x; i < D * N; i += blockDim.x) acc += control_extra[size_t(b) * D * N + i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    accs += __shfl_xor_sync(0xffffffffu, accs, off);
+  }
+  __shared__ double sred2[32];
+  if (lane == 0) { sred[warp] = acc; sred2[warp] = accs; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0, s2 = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += sred[w], s2 += sred2[w];
+    totals[size_t(b) * (R + 1) + R] = s2 + s;
+    if (noiseless_cost) noiseless_cost[b] = s2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_update: CTA per (b, d), thread per timestep.  min / max / exp-normalise over rollouts, probability
+// weighted noise, projection through M (banded solve), theta += update.
+// ---------------------------------------------------------------------------------------------
+struct UpdateArgs {
+  int R, D, N, apply;
+  const double* cumulative;  // [B][R][D][N]
+  const double* noise;       // [B][R][D][N]
+  double* probabilities;     // optional tap
+  double* updates;           // [B][D][N]
+  double* theta;             // [B][D][N]
+  Band band;
+};
+
+__global__ void k_update(UpdateArgs a) {
+  extern __shared__ double smem[];
+  const int N = a.N, R = a.R, D = a.D, hb = a.band.hb;
+  double* u = smem;                 // [N]
+  double* sband = u + N;            // [N][hb+1]
+  double* sinv = sband + N * (hb + 1);
+  const int b = blockIdx.x / D, d = blockIdx.x - b * D;
+  for (int i = threadIdx.x; i < N * (hb + 1); i += blockDim.x) sband[i] = a.band.band[i];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sinv[i] = a.band.inv_diag[i];
+  const size_t rstride = size_t(D) * N;
+  const size_t base = (size_t(b) * R * D + d) * N;
+  for (int t = threadIdx.x; t < N; t += blockDim.x) {
+    const double* c = a.cumulative + base + t;
+    const double* e = a.noise + base + t;
+    double mn = c[0], mx = c[0];
+    for (int r = 1; r < R; ++r) {
+      double v = c[r * rstride];
+      if (v < mn) mn = v;
+      if (v > mx) mx = v;
+    }
+    double denom = mx - mn;
+    if (denom < 1e-8) denom = 1e-8;
+    double p_sum = 0.0;
+    for (int r = 0; r < R; ++r) p_sum += exp(-10.0 * (c[r * rstride] - mn) / denom);
+    double acc = 0.0;
+    for (int r = 0; r < R; ++r) {
+      double p = exp(-10.0 * (c[r * rstride] - mn) / denom) / p_sum;
+      if (a.probabilities) a.probabilities[base + r * rstride + t] = p;
+      acc += e[r * rstride] * p;
+    }
+    u[t] = acc * a.band.proj_scale[t];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    band_forward(u, sband, sinv, N, hb);
+    band_backward(u, sband, sinv, N, hb);
+  }
+  __syncthreads();
+  const size_t off = (size_t(b) * D + d) * N;
+  for (int t = threadIdx.x; t < N; t += blockDim.x) {
+    a.updates[off + t] = u[t];
+    if (a.apply) a.theta[off + t] += u[t];
+  }
+}
+
+// theta += updates  (Policy::updateParameters for caller-supplied updates)
+__global__ void k_axpy(size_t n, const double* __restrict__ x, double* __restrict__ y) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += x[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rollout-sharded / huge-R statistics (config C3): partial reductions over rollout chunks.
+//   k_minmax_partial : part[chunk][2][D*N] = {max c, max -c}
+//   k_minmax_reduce  : minmax[2][D*N]
+//   k_sums_partial   : part[chunk][2][D*N] = {sum e, sum e*eps}
+//   k_sums_reduce    : sums[2][D*N]
+//   k_finalize       : u = (sum e*eps / sum e) -> projection -> theta
+// ---------------------------------------------------------------------------------------------
+__global__ void k_minmax_partial(int R, int DN, int rollouts_per_chunk, const double* __restrict__ cumulative,
+                                 double* __restrict__ part) {
+  const int chunk = blockIdx.y;
+  const int r0 = chunk * rollouts_per_chunk, r1 = min(R, r0 + rollouts_per_chunk);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < DN; i += gridDim.x * blockDim.x) {
+    double mx = -1.0e300, mn = 1.0e300;
+    for (int r = r0; r < r1; ++r) {
+      double v = cumulative[size_t(r) * DN + i];
+      mx = fmax(mx, v);
+      mn = fmin(mn, v);
+    }
+    part[(size_t(chunk) * 2 + 0) * DN + i] = mx;
+    part[(size_t(chunk) * 2 + 1) * DN + i] = -mn;
+  }
+}
+
+__global__ void k_pair_reduce(int DN, int nchunks, int is_max, const double* __restrict__ part, double* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * DN) return;
+  int which = i / DN, j = i - which * DN;
+  double acc = is_max ? -1.0e300 : 0.0;
+  for (int c = 0; c < nchunks; ++c) {
+    double v = part[(size_t(c) * 2 + which) * DN + j];
+    acc = is_max ? fmax(acc, v) : acc + v;
+  }
+  out[i] = acc;
+}
+
+__global__ void k_sums_partial(int R, int DN, int rollouts_per_chunk, const double* __restrict__ cumulative,
+                               const double* __restrict__ noise, const double* __restrict__ minmax,
+                               double* __restrict__ part) {
+  const int chunk = blockIdx.y;
+  const int r0 = chunk * rollouts_per_chunk, r1 = min(R, r0 + rollouts_per_chunk);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < DN; i += gridDim.x * blockDim.x) {
+    double mx = minmax[i], mn = -minmax[DN + i];
+    double denom = mx - mn;
+    if (denom < 1e-8) denom = 1e-8;
+    double se = 0.0, see = 0.0;
+    for (int r = r0; r < r1; ++r) {
+      double e = exp(-10.0 * (cumulative[size_t(r) * DN + i] - mn) / denom);
+      se += e;
+      see += e * noise[size_t(r) * DN + i];
+    }
+    part[(size_t(chunk) * 2 + 0) * DN + i] = se;
+    part[(size_t(chunk) * 2 + 1) * DN + i] = see;
+  }
+}
+
+__global__ void k_probabilities(int R, int DN, const double* __restrict__ cumulative, const double* __restrict__ minmax,
+                                const double* __restrict__ sums, double* __restrict__ prob) {
+  size_t n = size_t(R) * DN;
+  for (size_t k = size_t(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += size_t(gridDim.x) * blockDim.x) {
+    int i = int(k % DN);
+    double mx = minmax[i], mn = -minmax[DN + i];
+    double denom = mx - mn;
+    if (denom < 1e-8) denom = 1e-8;
+    prob[k] = exp(-10.0 * (cumulative[k] - mn) / denom) / sums[i];
+  }
+}
+
+__global__ void k_finalize(int D, int N, int apply, const double* __restrict__ sums, double* __restrict__ updates,
+                           double* __restrict__ theta, Band band) {
+  extern __shared__ double smem[];
+  const int hb = band.hb, d = blockIdx.x, DN = D * N;
+  double* u = smem;
+  double* sband = u + N;
+  double* sinv = sband + N * (hb + 1);
+  for (int i = threadIdx.x; i < N * (hb + 1); i += blockDim.x) sband[i] = band.band[i];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sinv[i] = band.inv_diag[i];
+  for (int t = threadIdx.x; t < N; t += blockDim.x)
+    u[t] = (sums[DN + d * N + t] / sums[d * N + t]) * band.proj_scale[t];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    band_forward(u, sband, sinv, N, hb);
+    band_backward(u, sband, sinv, N, hb);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < N; t += blockDim.x) {
+    updates[d * N + t] = u[t];
+    if (apply) theta[d * N + t] += u[t];
+  }
+}
+
+}  // namespace stomp_dev

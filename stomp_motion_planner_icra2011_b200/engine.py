@@ -1,0 +1,239 @@
+"""ctypes binding of the CUDA engine's C ABI (include/stomp_b200.h).
+
+The shared library is built in-tree by `__graft_entry__.build()` (nvcc, sm_100a).  There is no
+fallback of any kind: if the library is missing or no CUDA device is present, construction
+raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstomp_b200.so")
+_lib = None
+
+EXPORTS = [
+    "stomp_engine_create", "stomp_engine_destroy", "stomp_engine_last_error", "stomp_engine_abi_version",
+    "stomp_engine_build_info", "stomp_engine_set_robot", "stomp_engine_set_sdf", "stomp_engine_set_noise",
+    "stomp_engine_set_problems", "stomp_engine_set_parameters", "stomp_engine_get_parameters",
+    "stomp_engine_update_parameters", "stomp_engine_compute_control_costs", "stomp_engine_seed",
+    "stomp_engine_inject_noise", "stomp_engine_sample_noise", "stomp_engine_execute", "stomp_engine_execute_debug",
+    "stomp_engine_get_rollouts", "stomp_engine_set_rollout_costs", "stomp_engine_improve_policy",
+    "stomp_engine_add_extra_rollouts", "stomp_engine_iterate", "stomp_engine_run", "stomp_engine_synchronize",
+    "stomp_engine_get", "stomp_engine_launch_count", "stomp_engine_stream", "stomp_engine_timer_start",
+    "stomp_engine_timer_stop", "stomp_engine_shard_buffers", "stomp_engine_iterate_sharded_phase",
+]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("CUDA engine library %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`"
+                               % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.stomp_engine_last_error.restype = C.c_char_p
+        _lib.stomp_engine_build_info.restype = C.c_char_p
+        _lib.stomp_engine_launch_count.restype = C.c_int64
+        _lib.stomp_engine_stream.restype = C.c_void_p
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Engine:
+    """B planning problems on one GPU.  Mirrors the reference's PolicyImprovementLoop /
+    PolicyImprovement / Task surface for the per-iteration rollout loop."""
+
+    def __init__(self, scenario, dtype=_abi.F64, device=0, keep_intermediates=0, problems=None,
+                 shard_rank=0, shard_world=1):
+        self.sc = scenario
+        self.L = lib()
+        sel = slice(None) if problems is None else problems
+        self.start = _f64(scenario.start[sel])
+        self.goal = _f64(scenario.goal[sel])
+        self.B = self.start.shape[0]
+        self.D, self.N, self.R = scenario.robot.num_dimensions, scenario.num_time_steps, scenario.num_rollouts
+        self.K = len(scenario.robot.spheres)
+        self.desc = scenario.desc(dtype=dtype, device=device, keep_intermediates=keep_intermediates,
+                                  num_problems=self.B, shard_rank=shard_rank, shard_world=shard_world)
+        self.h = C.c_void_p()
+        self._ck(self.L.stomp_engine_create(C.byref(self.desc), C.byref(self.h)))
+        rb = scenario.robot
+        self._ck(self.L.stomp_engine_set_robot(self.h, rb.c_segments(), len(rb.segments), rb.reference_segment,
+                                               rb.c_spheres(), len(rb.spheres), rb.c_limits()))
+        sdf = scenario.sdf
+        nx, ny, nz = sdf.dims
+        self._ck(self.L.stomp_engine_set_sdf(self.h, sdf.voxels.ctypes.data_as(C.c_void_p), nx, ny, nz,
+                                             (C.c_double * 3)(*sdf.origin), C.c_double(sdf.resolution), sdf.voxel_dtype))
+        self._ck(self.L.stomp_engine_set_noise(self.h, _dp(_f64(scenario.noise_stddev)), _dp(_f64(scenario.noise_decay))))
+        self.set_problems(self.start, self.goal)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError("stomp_b200: " + self.L.stomp_engine_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.stomp_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- policy -------------------------------------------------------------------------
+    def set_problems(self, start, goal):
+        s, g = _f64(start), _f64(goal)
+        self._ck(self.L.stomp_engine_set_problems(self.h, _dp(s), _dp(g)))
+
+    def set_parameters(self, theta):
+        self._ck(self.L.stomp_engine_set_parameters(self.h, _dp(_f64(theta))))
+
+    def get_parameters(self):
+        out = np.empty((self.B, self.D, self.N))
+        self._ck(self.L.stomp_engine_get_parameters(self.h, _dp(out)))
+        return out
+
+    def update_parameters(self, updates):
+        self._ck(self.L.stomp_engine_update_parameters(self.h, _dp(_f64(updates))))
+
+    def compute_control_costs(self, parameters, noise, weight):
+        p, e = _f64(parameters), _f64(noise)
+        n = p.shape[1]
+        out = np.empty((self.B, n, self.D, self.N))
+        self._ck(self.L.stomp_engine_compute_control_costs(self.h, _dp(p), _dp(e), n, C.c_double(weight), _dp(out)))
+        return out
+
+    # ---- noise --------------------------------------------------------------------------
+    def seed(self, seed):
+        self._ck(self.L.stomp_engine_seed(self.h, C.c_uint64(seed)))
+
+    def inject_noise(self, eps):
+        e = _f64(eps)
+        assert e.shape[0] == self.B and e.shape[2:] == (self.D, self.N)
+        self._ck(self.L.stomp_engine_inject_noise(self.h, _dp(e), e.shape[1]))
+
+    def sample_noise(self, iteration, n):
+        out = np.empty((self.B, n, self.D, self.N))
+        self._ck(self.L.stomp_engine_sample_noise(self.h, iteration, n, _dp(out)))
+        return out
+
+    # ---- cost plugin ----------------------------------------------------------------------
+    def execute(self, parameters, iteration_number=2):
+        p = _f64(parameters)
+        n = p.shape[1]
+        costs = np.empty((self.B, n, self.N))
+        cf = np.empty((self.B, n), dtype=np.int32)
+        self._ck(self.L.stomp_engine_execute(self.h, _dp(p), n, iteration_number, _dp(costs), _ip(cf)))
+        return costs, cf
+
+    def execute_debug(self, parameters):
+        from numpy import frombuffer
+        p = _f64(parameters).reshape(self.D, self.N)
+        dbg = (_abi.SphereDebug * ((self.N + 3) * self.K))()
+        self._ck(self.L.stomp_engine_execute_debug(self.h, _dp(p), dbg))
+        a = frombuffer(dbg, dtype=np.dtype([("voxel", np.int32, 3), ("in_collision", np.int32), ("position", np.float64, 3),
+                                            ("potential", np.float64), ("vel_mag", np.float64)])).reshape(self.N + 3, self.K)
+        return {k: a[k].copy() for k in a.dtype.names}
+
+    # ---- PolicyImprovement step by step -----------------------------------------------------
+    def get_rollouts(self, noise_stddev):
+        out = np.empty((self.B, self.R, self.D, self.N))
+        ngen = C.c_int32()
+        tmp = np.empty((self.B * self.R * self.D * self.N))
+        self._ck(self.L.stomp_engine_get_rollouts(self.h, _dp(_f64(noise_stddev)), _dp(tmp), C.byref(ngen)))
+        g = ngen.value
+        return tmp[: self.B * g * self.D * self.N].reshape(self.B, g, self.D, self.N).copy()
+
+    def set_rollout_costs(self, costs, control_cost_weight):
+        c = _f64(costs)
+        totals = np.empty((self.B, self.R))
+        self._ck(self.L.stomp_engine_set_rollout_costs(self.h, _dp(c), C.c_double(control_cost_weight), _dp(totals)))
+        return totals
+
+    def improve_policy(self):
+        out = np.empty((self.B, self.D, self.N))
+        self._ck(self.L.stomp_engine_improve_policy(self.h, _dp(out)))
+        return out
+
+    def add_extra_rollouts(self, costs):
+        self._ck(self.L.stomp_engine_add_extra_rollouts(self.h, _dp(_f64(costs))))
+
+    # ---- the hot path ---------------------------------------------------------------------
+    def iterate(self, iteration_number, stats=True):
+        if not stats:
+            self._ck(self.L.stomp_engine_iterate(self.h, iteration_number, None))
+            return None
+        cost = np.empty(self.B)
+        cf = np.empty(self.B, dtype=np.int32)
+        st = _abi.IterStats(_dp(cost), _ip(cf), 0, 0)
+        self._ck(self.L.stomp_engine_iterate(self.h, iteration_number, C.byref(st)))
+        return cost, cf, st.num_generated_rollouts
+
+    def run(self, first_iteration, count, stats=False):
+        if not stats:
+            self._ck(self.L.stomp_engine_run(self.h, first_iteration, count, None))
+            return None
+        cost = np.empty(self.B)
+        cf = np.empty(self.B, dtype=np.int32)
+        st = _abi.IterStats(_dp(cost), _ip(cf), 0, 0)
+        self._ck(self.L.stomp_engine_run(self.h, first_iteration, count, C.byref(st)))
+        return cost, cf, st.num_generated_rollouts
+
+    def synchronize(self):
+        self._ck(self.L.stomp_engine_synchronize(self.h))
+
+    def timer_start(self):
+        self._ck(self.L.stomp_engine_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self.L.stomp_engine_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(self.L.stomp_engine_launch_count(self.h))
+
+    def shard_buffers(self):
+        mm, sm, nb = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        self._ck(self.L.stomp_engine_shard_buffers(self.h, C.byref(mm), C.byref(sm), C.byref(nb)))
+        return mm.value, sm.value, nb.value
+
+    def iterate_sharded_phase(self, iteration_number, phase):
+        self._ck(self.L.stomp_engine_iterate_sharded_phase(self.h, iteration_number, phase))
+
+    def get(self, field):
+        B, R, D, N = self.B, self.R, self.D, self.N
+        shapes = {
+            _abi.FIELD_THETA: (B, D, N), _abi.FIELD_NOISE: (B, R, D, N), _abi.FIELD_PARAMETERS: (B, R, D, N),
+            _abi.FIELD_NOISE_PROJECTED: (B, R, D, N), _abi.FIELD_STATE_COSTS: (B, R, N),
+            _abi.FIELD_CONTROL_COSTS: (B, R, D, N), _abi.FIELD_CUMULATIVE_COSTS: (B, R, D, N),
+            _abi.FIELD_PROBABILITIES: (B, R, D, N), _abi.FIELD_UPDATES: (B, D, N), _abi.FIELD_NOISELESS_COSTS: (B, N),
+            _abi.FIELD_ROLLOUT_TOTAL_COSTS: (B, R + 1), _abi.FIELD_INV_CONTROL_COST: (N, N),
+            _abi.FIELD_NOISE_CHOLESKY: (N, N), _abi.FIELD_PROJECTION: (N, N), _abi.FIELD_QUAD_COST_INV: (N, N),
+            _abi.FIELD_CONTROL_COST: (N, N), _abi.FIELD_CLIPPED_PARAMETERS: (B, R, D, N),
+        }
+        if field == _abi.FIELD_COLLISION_FREE:
+            out = np.empty((B, R + 1), dtype=np.int32)
+        else:
+            out = np.empty(shapes[field])
+        self._ck(self.L.stomp_engine_get(self.h, field, out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes)))
+        return out

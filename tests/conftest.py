@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def tiny():
+    from stomp_motion_planner_icra2011_b200 import scenes
+    return scenes.make_scenario("tiny")
+
+
+@pytest.fixture(scope="session")
+def c1():
+    from stomp_motion_planner_icra2011_b200 import scenes
+    return scenes.make_scenario("C1", num_problems=3)

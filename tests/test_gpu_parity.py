@@ -1,0 +1,246 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): voxel indices / collision flags / reuse order bit-exact; floating point
+within 1e-5 relative in fp64 mode and 1e-3 in fp32 mode.
+"""
+import numpy as np
+import pytest
+
+from stomp_motion_planner_icra2011_b200 import _abi, scenes
+from tests.helpers import RTOL_F64, RTOL_F32, assert_close, correlated_noise, oracle_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(sc, **kw):
+    from stomp_motion_planner_icra2011_b200.engine import Engine
+    return Engine(sc, **kw)
+
+
+def _oracles(sc):
+    from oracle import oracle
+    return oracle_batch(oracle, sc)
+
+
+def _noisy_rollouts(sc, ors, rng, n, sigma=2.0):
+    L = ors[0].get(_abi.FIELD_NOISE_CHOLESKY)
+    B, D = sc.start.shape
+    eps = correlated_noise(L, rng, (B, n), np.full(D, sigma))
+    theta = np.stack([o.get_parameters() for o in ors])
+    return theta[:, None] + eps
+
+
+@pytest.mark.parametrize("name", ["tiny", "C1"])
+def test_setup_matrices_match(name):
+    sc = scenes.make_scenario(name, num_problems=2)
+    eng, ors = _engine(sc), _oracles(sc)
+    for f in (_abi.FIELD_CONTROL_COST, _abi.FIELD_INV_CONTROL_COST, _abi.FIELD_PROJECTION, _abi.FIELD_QUAD_COST_INV,
+              _abi.FIELD_NOISE_CHOLESKY):
+        assert_close(eng.get(f), ors[0].get(f), 1e-9, "field %d" % f)
+    theta = eng.get_parameters()
+    for b, o in enumerate(ors):
+        assert_close(theta[b], o.get_parameters(), 1e-12, "min control cost trajectory")
+
+
+@pytest.mark.parametrize("name,n", [("tiny", 5), ("C1", 6)])
+def test_cost_plugin_parity_f64(name, n):
+    sc = scenes.make_scenario(name, num_problems=3)
+    eng, ors = _engine(sc), _oracles(sc)
+    rng = np.random.default_rng(3)
+    params = _noisy_rollouts(sc, ors, rng, n)
+    for it in (1, 2):
+        costs, cf = eng.execute(params, iteration_number=it)
+        for b, o in enumerate(ors):
+            oc, ocf = o.execute(params[b], iteration_number=it)
+            assert_close(costs[b], oc, RTOL_F64, "state costs")
+            np.testing.assert_array_equal(cf[b], ocf)
+    assert costs.max() > 0.0  # the scene actually produces obstacle cost
+
+
+def test_cost_plugin_integer_work_bit_exact():
+    sc = scenes.make_scenario("C1", num_problems=1)
+    eng, ors = _engine(sc), _oracles(sc)
+    rng = np.random.default_rng(5)
+    params = _noisy_rollouts(sc, ors, rng, 4)
+    near_boundary = 0
+    for r in range(4):
+        dbg = eng.execute_debug(params[0, r])
+        odbg, clipped = ors[0].execute_debug(params[0, r])
+        # voxel indices must be exactly int(round((x - origin) / res)) of the engine's own positions ...
+        org, res = np.asarray(sc.sdf.origin), sc.sdf.resolution
+        own = np.round((dbg["position"] - org) / res).astype(np.int32)
+        np.testing.assert_array_equal(dbg["voxel"], own)
+        # ... and equal to the oracle's wherever the oracle's position is not within 1e-9 cells of a boundary
+        frac = (odbg["position"] - org) / res
+        safe = np.all(np.abs(np.abs(frac - np.round(frac)) - 0.5) > 1e-9, axis=-1)
+        near_boundary += int((~safe).sum())
+        np.testing.assert_array_equal(dbg["voxel"][safe], odbg["voxel"][safe])
+        np.testing.assert_array_equal(dbg["in_collision"][safe], odbg["in_collision"][safe])
+        assert_close(dbg["position"], odbg["position"], 1e-12, "sphere positions", atol_scale=1e-12)
+        assert_close(dbg["potential"][safe], odbg["potential"][safe], RTOL_F64, "potential")
+        assert_close(dbg["vel_mag"], odbg["vel_mag"], RTOL_F64, "velocity magnitude")
+    assert near_boundary < 5
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_forward_kinematics_random_trees(seed):
+    rng = np.random.default_rng(100 + seed)
+    sc = scenes.make_scenario("tiny", num_problems=2)
+    rb = scenes.random_tree(rng)
+    sc.robot = rb
+    sc.start = rng.uniform(-1, 1, (2, rb.num_dimensions))
+    sc.goal = rng.uniform(-1, 1, (2, rb.num_dimensions))
+    sc.noise_stddev = np.full(rb.num_dimensions, 1.0)
+    sc.noise_decay = np.full(rb.num_dimensions, 1.0)
+    eng, ors = _engine(sc), _oracles(sc)
+    params = _noisy_rollouts(sc, ors, rng, 1, sigma=1.0)
+    dbg = eng.execute_debug(params[0, 0])
+    odbg, _ = ors[0].execute_debug(params[0, 0])
+    assert_close(dbg["position"], odbg["position"], 1e-11, "sphere positions", atol_scale=1e-11)
+    assert_close(dbg["vel_mag"], odbg["vel_mag"], RTOL_F64, "velocity magnitude")
+
+
+def _run_iterations(sc, iterations, dtype=_abi.F64, check=True, rtol=RTOL_F64):
+    eng, ors = _engine(sc, dtype=dtype, keep_intermediates=1), _oracles(sc)
+    rng = np.random.default_rng(11)
+    L = ors[0].get(_abi.FIELD_NOISE_CHOLESKY)
+    B, D = sc.start.shape
+    fields = [(_abi.FIELD_NOISE, "noise"), (_abi.FIELD_PARAMETERS, "parameters"), (_abi.FIELD_NOISE_PROJECTED, "noise_projected"),
+              (_abi.FIELD_CONTROL_COSTS, "control_costs"), (_abi.FIELD_STATE_COSTS, "state_costs"),
+              (_abi.FIELD_CUMULATIVE_COSTS, "cumulative_costs"), (_abi.FIELD_PROBABILITIES, "probabilities"),
+              (_abi.FIELD_UPDATES, "updates"), (_abi.FIELD_THETA, "theta"), (_abi.FIELD_NOISELESS_COSTS, "noiseless costs"),
+              (_abi.FIELD_ROLLOUT_TOTAL_COSTS, "rollout total costs")]
+    for it in range(1, iterations + 1):
+        sigma = sc.noise_stddev * sc.noise_decay ** (it - 1)
+        ngen = sc.num_rollouts if it == 1 else sc.num_rollouts - sc.num_reused_rollouts
+        eps = correlated_noise(L, rng, (B, ngen), sigma)
+        eng.inject_noise(eps)
+        cost, cf, g = eng.iterate(it)
+        assert g == ngen
+        for b, o in enumerate(ors):
+            oc, ocf, og = o.iterate(it, eps[b])
+            assert og == ngen
+            if not check:
+                continue
+            for f, nm in fields:
+                assert_close(eng.get(f)[b], o.get(f), rtol, "%s, iteration %d, problem %d" % (nm, it, b))
+            assert_close(cost[b], oc, rtol, "noiseless cost")
+            assert cf[b] == ocf
+            ecf, orcf = eng.get(_abi.FIELD_COLLISION_FREE)[b], o.get(_abi.FIELD_COLLISION_FREE)
+            np.testing.assert_array_equal(ecf[:ngen], orcf[:ngen])
+    return eng, ors
+
+
+@pytest.mark.parametrize("name,cumulative", [("tiny", 0), ("tiny", 1), ("C1", 0), ("C1", 1)])
+def test_full_iteration_parity_f64(name, cumulative):
+    sc = scenes.make_scenario(name, num_problems=2, use_cumulative_costs=cumulative)
+    _run_iterations(sc, 6)
+
+
+def test_full_iteration_parity_n99_yaml_exact():
+    sc = scenes.make_scenario("C1", num_problems=1, num_time_steps=99)
+    _run_iterations(sc, 4)
+
+
+def test_stepwise_policy_improvement_api():
+    """getRollouts / setRolloutCosts / improvePolicy / updateParameters / addExtraRollouts with a host Task."""
+    sc = scenes.make_scenario("tiny", num_problems=2)
+    eng, ors = _engine(sc, keep_intermediates=1), _oracles(sc)
+    rng = np.random.default_rng(4)
+    L = ors[0].get(_abi.FIELD_NOISE_CHOLESKY)
+    B, D = sc.start.shape
+    for it in range(1, 5):
+        sigma = sc.noise_stddev * sc.noise_decay ** (it - 1)
+        ngen = sc.num_rollouts if it == 1 else sc.num_rollouts - sc.num_reused_rollouts
+        eps = correlated_noise(L, rng, (B, ngen), sigma)
+        eng.inject_noise(eps)
+        ro = eng.get_rollouts(sigma)
+        assert ro.shape[1] == ngen
+        host_costs = np.abs(np.sin(ro)).sum(axis=2)            # an arbitrary host-side Task::execute
+        totals = eng.set_rollout_costs(host_costs, 0.3)
+        upd = eng.improve_policy()
+        eng.update_parameters(upd)
+        th = eng.get_parameters()
+        extra_costs = np.abs(np.sin(th)).sum(axis=1)
+        eng.add_extra_rollouts(extra_costs)
+        for b, o in enumerate(ors):
+            oro = o.get_rollouts(sigma, eps[b])
+            assert_close(ro[b], oro, RTOL_F64, "rollouts")
+            ot = o.set_rollout_costs(np.abs(np.sin(oro)).sum(axis=1), 0.3)
+            assert_close(totals[b], ot, RTOL_F64, "rollout totals")
+            ou = o.improve_policy()
+            assert_close(upd[b], ou, RTOL_F64, "updates")
+            o.update_parameters(ou)
+            oth = o.get_parameters()
+            assert_close(th[b], oth, RTOL_F64, "theta")
+            o.add_extra_rollouts(np.abs(np.sin(oth)).sum(axis=0))
+
+
+def test_compute_control_costs_matches_policy():
+    sc = scenes.make_scenario("tiny", num_problems=2)
+    eng, ors = _engine(sc), _oracles(sc)
+    rng = np.random.default_rng(9)
+    p = rng.normal(size=(2, 3, sc.robot.num_dimensions, sc.num_time_steps))
+    e = 0.1 * rng.normal(size=p.shape)
+    got = eng.compute_control_costs(p, e, 0.7)
+    for b, o in enumerate(ors):
+        assert_close(got[b], o.compute_control_costs(p[b], e[b], 0.7), RTOL_F64, "control costs")
+
+
+def test_fp32_mode_within_1e3():
+    """fp32 instantiation of the cost plugin: costs within 1e-3 relative wherever no voxel index flipped
+    (a position that differs by 1e-7 m can land in the neighbouring 15 mm cell; such rollouts are counted)."""
+    sc = scenes.make_scenario("C1", num_problems=2)
+    eng, ors = _engine(sc, dtype=_abi.F32), _oracles(sc)
+    rng = np.random.default_rng(3)
+    params = _noisy_rollouts(sc, ors, rng, 8)
+    costs, cf = eng.execute(params, iteration_number=2)
+    bad = 0
+    for b, o in enumerate(ors):
+        oc, ocf = o.execute(params[b], iteration_number=2)
+        scale = np.abs(oc).max()
+        err = np.abs(costs[b] - oc).max(axis=-1) / scale
+        bad += int((err > RTOL_F32).sum())
+    assert bad <= 2, "more than 2 of 16 rollouts differ by > 1e-3 (voxel flips expected to be rare)"
+
+
+def test_philox_noise_statistics():
+    """The engine's own RNG: sample covariance of eps against R^-1 and stream independence."""
+    sc = scenes.make_scenario("tiny", num_problems=1, num_time_steps=24)
+    eng, ors = _engine(sc), _oracles(sc)
+    n = 20000
+    x = eng.sample_noise(1, n)[0]                  # [n][D][N], unit sigma
+    D, N = x.shape[1:]
+    Rinv = ors[0].get(_abi.FIELD_INV_CONTROL_COST)
+    flat = x.reshape(n * D, N)
+    cov = flat.T @ flat / flat.shape[0]
+    assert np.abs(flat.mean(axis=0)).max() < 4 * np.sqrt(Rinv.diagonal().max() / flat.shape[0])
+    rel = np.linalg.norm(cov - Rinv) / np.linalg.norm(Rinv)
+    assert rel < 0.02, rel
+    # whitened samples are i.i.d. N(0,1): kurtosis ~ 3, and different (rollout, dimension) streams are uncorrelated
+    C = np.linalg.cholesky(ors[0].get(_abi.FIELD_CONTROL_COST))
+    z = flat @ C                                   # cov = C^T R^-1 C = I
+    assert abs(np.mean(z ** 4) - 3.0) < 0.1
+    assert abs(np.mean(z[:-1] * z[1:])) < 0.01
+    # a different iteration gives a different draw; the same iteration is reproducible
+    assert np.array_equal(eng.sample_noise(1, 4), eng.sample_noise(1, 4))
+    assert not np.array_equal(eng.sample_noise(1, 4), eng.sample_noise(2, 4))
+
+
+def test_philox_iterations_reduce_cost():
+    sc = scenes.make_scenario("C1", num_problems=4)
+    eng = _engine(sc)
+    first = eng.iterate(1)[0]
+    for it in range(2, 41):
+        last = eng.iterate(it)[0]
+    assert np.all(np.isfinite(last))
+    assert last.mean() < first.mean()
+    assert eng.launch_count() > 0
+
+
+def test_errors_are_reported():
+    from stomp_motion_planner_icra2011_b200.engine import Engine
+    sc = scenes.make_scenario("tiny")
+    sc.num_reused_rollouts = sc.num_rollouts
+    with pytest.raises(RuntimeError, match="reused rollouts"):
+        Engine(sc)
