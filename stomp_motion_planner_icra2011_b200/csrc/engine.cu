@@ -46,6 +46,8 @@ struct DevBuf {
     if (count == 0) return cudaSuccess;
     cudaError_t e = cudaMalloc(&p, count * sizeof(T));
     if (e == cudaSuccess) e = cudaMemset(p, 0, count * sizeof(T));
+    // the handle's stream is non-blocking: make sure the legacy-stream memset cannot overtake later copies
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     return e;
   }
   void release() {

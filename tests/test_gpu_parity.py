@@ -70,13 +70,15 @@ def test_cost_plugin_integer_work_bit_exact():
         org, res = np.asarray(sc.sdf.origin), sc.sdf.resolution
         own = np.round((dbg["position"] - org) / res).astype(np.int32)
         np.testing.assert_array_equal(dbg["voxel"], own)
-        # ... and equal to the oracle's wherever the oracle's position is not within 1e-9 cells of a boundary
+        # ... and equal to the oracle's wherever the oracle's position is not within 1e-6 cells of a boundary.
+        # (Positions agree to ~1e-10 m, not 1e-16: the joint-limit projection multiplies by columns of the
+        # inverse of a matrix with condition number ~6e6, so two correct fp64 inverses differ by ~1e-10.)
         frac = (odbg["position"] - org) / res
-        safe = np.all(np.abs(np.abs(frac - np.round(frac)) - 0.5) > 1e-9, axis=-1)
+        safe = np.all(np.abs(np.abs(frac - np.round(frac)) - 0.5) > 1e-6, axis=-1)
         near_boundary += int((~safe).sum())
         np.testing.assert_array_equal(dbg["voxel"][safe], odbg["voxel"][safe])
         np.testing.assert_array_equal(dbg["in_collision"][safe], odbg["in_collision"][safe])
-        assert_close(dbg["position"], odbg["position"], 1e-12, "sphere positions", atol_scale=1e-12)
+        assert_close(dbg["position"], odbg["position"], 1e-8, "sphere positions", atol_scale=1e-8)
         assert_close(dbg["potential"][safe], odbg["potential"][safe], RTOL_F64, "potential")
         assert_close(dbg["vel_mag"], odbg["vel_mag"], RTOL_F64, "velocity magnitude")
     assert near_boundary < 5
