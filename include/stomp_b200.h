@@ -243,6 +243,13 @@ void* stomp_engine_stream(void* engine);
 int stomp_engine_timer_start(void* engine);
 int stomp_engine_timer_stop(void* engine, float* elapsed_ms);
 
+/* Per-kernel device timing (CUDA events on the handle's stream around every launch): enable, run, then sum
+ * the durations of the launches whose kernel name contains kernel_substr ("" = all).  Used by bench.py for
+ * the roofline of the dominant kernel; replaces the reference's commented-out ros::WallTime phase timers
+ * (src/policy_improvement.cpp:255-257,389-397). */
+int stomp_engine_set_profiling(void* engine, int32_t enabled);
+int stomp_engine_get_profile(void* engine, const char* kernel_substr, double* total_ms, int64_t* num_launches);
+
 /* ---- rollout sharding over GPUs (config C3) ----------------------------------------- */
 /* Device buffers the host plumbing (torch.distributed / NCCL) all-reduces between the phases of
  * a sharded iteration: minmax = [2][D][N] (MAX of {c, -c}), sums = [2][D][N] (SUM of {e, e*eps}). */

@@ -100,6 +100,12 @@ struct Engine {
   Sdf sdf;
   size_t scratch_n = 0;
 
+  // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_a, prof_b;
+  std::vector<std::string> prof_name;
+  size_t prof_used = 0;
+
   Band band_view() const { return Band{band.p, inv_diag.p, proj_scale.p, pm.chol.hb}; }
   Stencil stencil() const {
     Stencil st;
@@ -112,10 +118,28 @@ struct Engine {
   bool huge_path() const { return desc.rollout_shard_world > 1 || R > 4096; }
 };
 
+void begin_launch(Engine& e) {
+  if (!e.prof_on) return;
+  if (e.prof_used == e.prof_a.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    e.prof_a.push_back(a);
+    e.prof_b.push_back(b);
+    e.prof_name.push_back("");
+  }
+  cudaEventRecord(e.prof_a[e.prof_used], e.stream);
+}
+
 int check_launch(Engine& e, const char* what) {
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(std::string(what) + ": " + cudaGetErrorString(err));
   e.launches++;
+  if (e.prof_on) {
+    cudaEventRecord(e.prof_b[e.prof_used], e.stream);
+    e.prof_name[e.prof_used] = what;
+    e.prof_used++;
+  }
   return 0;
 }
 
@@ -176,6 +200,7 @@ int launch_generate(Engine& e, GenArgs a) {
   size_t smem = fixed + per_thread * tpb;
   CUDA_TRY(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   unsigned grid = unsigned((nvec + tpb - 1) / tpb);
+  begin_launch(e);
   k_generate<<<grid, tpb, smem, e.stream>>>(a);
   return check_launch(e, "k_generate");
 }
@@ -212,6 +237,7 @@ int launch_cost_t(Engine& e, CostArgs<Real>& a, int num_problems) {
   auto kern = k_cost<Real, kDebug>;
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   if (smem > 220 * 1024) return fail("trajectory + robot tables exceed shared memory");
+  begin_launch(e);
   kern<<<unsigned(num_problems) * a.n_rollouts, warps * 32, smem, e.stream>>>(a);
   return check_launch(e, "k_cost");
 }
@@ -260,6 +286,7 @@ int launch_cost(Engine& e, const double* params, size_t pstride, int n_rollouts,
 int block_for(int N) { return std::min(1024, ((N + 31) / 32) * 32); }
 
 int launch_cumulative(Engine& e) {
+  begin_launch(e);
   k_cumulative<<<unsigned(e.B) * e.R, block_for(e.N), 0, e.stream>>>(e.R, e.D, e.N, e.desc.use_cumulative_costs,
                                                                     e.state[e.cur].p, e.control.p, e.cumulative.p, e.totals.p);
   return check_launch(e, "k_cumulative");
@@ -272,6 +299,7 @@ int launch_update(Engine& e, int apply) {
   a.R = e.R; a.D = e.D; a.N = e.N; a.apply = apply;
   a.cumulative = e.cumulative.p; a.noise = e.noise.p; a.probabilities = e.probabilities.p;
   a.updates = e.updates.p; a.theta = e.theta.p; a.band = e.band_view();
+  begin_launch(e);
   k_update<<<unsigned(e.B) * e.D, block_for(e.N), band_smem(e), e.stream>>>(a);
   return check_launch(e, "k_update");
 }
@@ -281,24 +309,30 @@ constexpr int kChunks = 128;
 int launch_minmax(Engine& e) {
   const int DN = e.D * e.N, rpc = (e.R + kChunks - 1) / kChunks, nch = (e.R + rpc - 1) / rpc;
   dim3 grid((DN + 127) / 128, nch);
+  begin_launch(e);
   k_minmax_partial<<<grid, 128, 0, e.stream>>>(e.R, DN, rpc, e.cumulative.p, e.part.p);
   if (check_launch(e, "k_minmax_partial")) return 1;
+  begin_launch(e);
   k_pair_reduce<<<(2 * DN + 127) / 128, 128, 0, e.stream>>>(DN, nch, 1, e.part.p, e.minmax.p);
   return check_launch(e, "k_pair_reduce");
 }
 int launch_sums(Engine& e) {
   const int DN = e.D * e.N, rpc = (e.R + kChunks - 1) / kChunks, nch = (e.R + rpc - 1) / rpc;
   dim3 grid((DN + 127) / 128, nch);
+  begin_launch(e);
   k_sums_partial<<<grid, 128, 0, e.stream>>>(e.R, DN, rpc, e.cumulative.p, e.noise.p, e.minmax.p, e.part.p);
   if (check_launch(e, "k_sums_partial")) return 1;
+  begin_launch(e);
   k_pair_reduce<<<(2 * DN + 127) / 128, 128, 0, e.stream>>>(DN, nch, 0, e.part.p, e.sums.p);
   return check_launch(e, "k_pair_reduce");
 }
 int launch_finalize(Engine& e, int apply) {
   if (e.probabilities.p) {
+    begin_launch(e);
     k_probabilities<<<1184, 256, 0, e.stream>>>(e.R, e.D * e.N, e.cumulative.p, e.minmax.p, e.sums.p, e.probabilities.p);
     if (check_launch(e, "k_probabilities")) return 1;
   }
+  begin_launch(e);
   k_finalize<<<e.D, block_for(e.N), band_smem(e), e.stream>>>(e.D, e.N, apply, e.sums.p, e.updates.p, e.theta.p, e.band_view());
   return check_launch(e, "k_finalize");
 }
@@ -321,6 +355,7 @@ int step_get_rollouts(Engine& e, int iteration_number, bool with_control) {
     reuse = true;
   }
   if (reuse) {
+    begin_launch(e);
     k_select_reuse<<<e.B, 128, 0, e.stream>>>(e.totals.p, e.R, e.Rre, e.extra_added ? 1 : 0, e.reuse_src.p);
     if (check_launch(e, "k_select_reuse")) return 1;
     e.extra_added = false;
@@ -349,6 +384,7 @@ __global__ void k_gather_state(int R, int R_gen, int N, const int* __restrict__ 
 
 int gather_reused_state(Engine& e) {
   if (e.num_gen == e.R) return 0;
+  begin_launch(e);
   k_gather_state<<<unsigned(e.B) * (e.R - e.num_gen), 128, 0, e.stream>>>(e.R, e.num_gen, e.N, e.reuse_src.p,
                                                                           e.state[1 - e.cur].p, e.extra_state.p, e.state[e.cur].p);
   return check_launch(e, "k_gather_state");
@@ -382,6 +418,7 @@ int step_extra(Engine& e, bool run_cost, int iteration_number) {
   a.control = e.extra_control.p;
   a.control_weight = 0.5 * e.control_cost_weight;
   if (launch_generate(e, a)) return 1;
+  begin_launch(e);
   k_extra_total<<<e.B, 128, 0, e.stream>>>(e.R, e.D, e.N, e.extra_state.p, e.extra_control.p, e.totals.p, e.noiseless_sum.p);
   if (check_launch(e, "k_extra_total")) return 1;
   e.extra_added = true;
@@ -535,6 +572,8 @@ int stomp_engine_destroy(void* h) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  for (cudaEvent_t ev : e->prof_a) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : e->prof_b) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return 0;
@@ -631,6 +670,7 @@ int stomp_engine_update_parameters(void* h, const double* updates) {
   if (!updates) return fail("null argument");
   size_t n = size_t(e.B) * e.D * e.N;
   if (upload(e, e.updates, updates, n)) return 1;
+  begin_launch(e);
   k_axpy<<<unsigned((n + 255) / 256), 256, 0, e.stream>>>(n, e.updates.p, e.theta.p);
   if (check_launch(e, "k_axpy")) return 1;
   CUDA_TRY(cudaStreamSynchronize(e.stream));
@@ -853,6 +893,33 @@ int stomp_engine_timer_stop(void* h, float* elapsed_ms) {
   CUDA_TRY(cudaEventRecord(e.ev1, e.stream));
   CUDA_TRY(cudaEventSynchronize(e.ev1));
   if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, e.ev0, e.ev1));
+  return 0;
+}
+
+int stomp_engine_set_profiling(void* h, int32_t enabled) {
+  ENGINE_OR_FAIL(h);
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  e.prof_on = enabled != 0;
+  e.prof_used = 0;
+  return 0;
+}
+
+/* Sums the event-timed durations of the launches recorded since profiling was enabled whose kernel name
+ * contains `kernel_substr` ("" = all).  Resets nothing. */
+int stomp_engine_get_profile(void* h, const char* kernel_substr, double* total_ms, int64_t* num_launches) {
+  ENGINE_OR_FAIL(h);
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  double ms = 0.0;
+  int64_t n = 0;
+  for (size_t i = 0; i < e.prof_used; ++i) {
+    if (kernel_substr && kernel_substr[0] && e.prof_name[i].find(kernel_substr) == std::string::npos) continue;
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, e.prof_a[i], e.prof_b[i]));
+    ms += t;
+    ++n;
+  }
+  if (total_ms) *total_ms = ms;
+  if (num_launches) *num_launches = n;
   return 0;
 }
 

@@ -27,6 +27,7 @@ EXPORTS = [
     "stomp_engine_add_extra_rollouts", "stomp_engine_iterate", "stomp_engine_run", "stomp_engine_synchronize",
     "stomp_engine_get", "stomp_engine_launch_count", "stomp_engine_stream", "stomp_engine_timer_start",
     "stomp_engine_timer_stop", "stomp_engine_shard_buffers", "stomp_engine_iterate_sharded_phase",
+    "stomp_engine_set_profiling", "stomp_engine_get_profile",
 ]
 
 
@@ -107,8 +108,9 @@ class Engine:
     def set_parameters(self, theta):
         self._ck(self.L.stomp_engine_set_parameters(self.h, _dp(_f64(theta))))
 
-    def get_parameters(self):
-        out = np.empty((self.B, self.D, self.N))
+    def get_parameters(self, out=None):
+        if out is None:
+            out = np.empty((self.B, self.D, self.N))
         self._ck(self.L.stomp_engine_get_parameters(self.h, _dp(out)))
         return out
 
@@ -127,7 +129,7 @@ class Engine:
         self._ck(self.L.stomp_engine_seed(self.h, C.c_uint64(seed)))
 
     def inject_noise(self, eps):
-        e = _f64(eps)
+        e = eps if (isinstance(eps, np.ndarray) and eps.dtype == np.float64 and eps.flags.c_contiguous) else _f64(eps)
         assert e.shape[0] == self.B and e.shape[2:] == (self.D, self.N)
         self._ck(self.L.stomp_engine_inject_noise(self.h, _dp(e), e.shape[1]))
 
@@ -208,6 +210,14 @@ class Engine:
         ms = C.c_float()
         self._ck(self.L.stomp_engine_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+    def set_profiling(self, enabled):
+        self._ck(self.L.stomp_engine_set_profiling(self.h, int(enabled)))
+
+    def get_profile(self, kernel_substr=""):
+        ms, n = C.c_double(), C.c_int64()
+        self._ck(self.L.stomp_engine_get_profile(self.h, kernel_substr.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def launch_count(self):
         return int(self.L.stomp_engine_launch_count(self.h))
