@@ -88,7 +88,7 @@ struct Engine {
   DevBuf<double> extra_state, extra_control, updates, noiseless_sum;
   DevBuf<double> eps_in;
   DevBuf<int> reuse_src, collision_free;
-  DevBuf<double> band, inv_diag, proj_scale, qinv_t, noise_scale;
+  DevBuf<double> band_fw, band_bw, proj_scale, qinv_t, noise_scale;
   DevBuf<double> limit_min, limit_max;
   DevBuf<int> has_limits;
   DevBuf<unsigned char> nodes, spheres, sqrt_table, vox;
@@ -106,7 +106,7 @@ struct Engine {
   std::vector<std::string> prof_name;
   size_t prof_used = 0;
 
-  Band band_view() const { return Band{band.p, inv_diag.p, proj_scale.p, pm.chol.hb}; }
+  Band band_view() const { return Band{band_fw.p, band_bw.p, proj_scale.p}; }
   Stencil stencil() const {
     Stencil st;
     for (int k = 0; k < 3; ++k) {
@@ -188,14 +188,20 @@ int upload_sqrt_table(Engine& e) {
 // ---- kernel launch helpers ----------------------------------------------------------------------
 
 int launch_generate(Engine& e, GenArgs a) {
-  const int N = e.N, hb = e.pm.chol.hb;
-  const size_t fixed = size_t(N) * (hb + 1) * 8 + size_t(N) * 16;
+  const int N = e.N;
+  const size_t fixed = size_t(N) * 17 * 8;
   const size_t per_thread = size_t(N | 1) * 8 + 16;
-  int tpb = int((200 * 1024 - fixed) / per_thread);
-  tpb = std::min(128, (tpb / 32) * 32);
+  // pick the CTA size that keeps the most row-owning threads resident per SM (shared memory is the limiter)
+  int tpb = 0, best = 0;
+  for (int cand = 128; cand >= 32; cand -= 32) {
+    size_t need = fixed + per_thread * cand + 1024;
+    if (need > 227 * 1024) continue;
+    int resident = int((227 * 1024) / need) * cand;
+    if (resident > best) best = resident, tpb = cand;
+  }
   if (tpb < 32) return fail("num_time_steps too large for the shared-memory row buffers of k_generate");
   long long nvec = (long long)a.B * (a.extra ? 1 : a.R) * a.D;
-  // prefer >= 2 CTAs per SM worth of parallelism for small problems
+  // small batches: spread over more CTAs
   while (tpb > 32 && (nvec + tpb - 1) / tpb < 296) tpb -= 32;
   size_t smem = fixed + per_thread * tpb;
   CUDA_TRY(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -230,7 +236,7 @@ GenArgs base_gen_args(Engine& e) {
 template <typename Real, bool kDebug>
 int launch_cost_t(Engine& e, CostArgs<Real>& a, int num_problems) {
   const int ntiles = (e.N + kTileSteps - 1) / kTileSteps;
-  int warps = std::min(ntiles, 8);
+  int warps = std::min(ntiles, 4);
   warps = std::max(warps, std::min(e.D, 4));  // joint-limit pass likes a few warps
   size_t smem = size_t(e.D) * e.N * 8 + size_t(e.num_nodes) * sizeof(DevNode<Real>) + size_t(e.K) * sizeof(DevSphere<Real>) +
                 256 * sizeof(Real);
@@ -292,15 +298,22 @@ int launch_cumulative(Engine& e) {
   return check_launch(e, "k_cumulative");
 }
 
-size_t band_smem(const Engine& e) { return (size_t(e.N) * (e.pm.chol.hb + 2) + e.N) * 8; }
+size_t band_smem(const Engine& e, int rows) { return (size_t(e.N) * 16 + size_t(rows) * (e.N | 1)) * 8; }
 
 int launch_update(Engine& e, int apply) {
   UpdateArgs a;
   a.R = e.R; a.D = e.D; a.N = e.N; a.apply = apply;
   a.cumulative = e.cumulative.p; a.noise = e.noise.p; a.probabilities = e.probabilities.p;
   a.updates = e.updates.p; a.theta = e.theta.p; a.band = e.band_view();
+  // enough CTAs to fill the machine twice when the batch allows it; otherwise one dimension per CTA
+  int dpc = int(std::min<long long>(std::min(e.D, 32), std::max<long long>(1, (long long)e.B * e.D / 296)));
+  size_t smem = band_smem(e, dpc);
+  while (smem > 200 * 1024 && dpc > 1) smem = band_smem(e, --dpc);
+  a.dims_per_cta = dpc;
+  const int groups = (e.D + dpc - 1) / dpc;
+  CUDA_TRY(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   begin_launch(e);
-  k_update<<<unsigned(e.B) * e.D, block_for(e.N), band_smem(e), e.stream>>>(a);
+  k_update<<<unsigned(e.B) * groups, std::min(256, ((dpc * e.N + 31) / 32) * 32), smem, e.stream>>>(a);
   return check_launch(e, "k_update");
 }
 
@@ -333,7 +346,7 @@ int launch_finalize(Engine& e, int apply) {
     if (check_launch(e, "k_probabilities")) return 1;
   }
   begin_launch(e);
-  k_finalize<<<e.D, block_for(e.N), band_smem(e), e.stream>>>(e.D, e.N, apply, e.sums.p, e.updates.p, e.theta.p, e.band_view());
+  k_finalize<<<e.D, block_for(e.N), band_smem(e, 1), e.stream>>>(e.D, e.N, apply, e.sums.p, e.updates.p, e.theta.p, e.band_view());
   return check_launch(e, "k_finalize");
 }
 
@@ -545,7 +558,19 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   std::vector<double> qt(size_t(e.N) * e.N);
   for (int i = 0; i < e.N; ++i)
     for (int j = 0; j < e.N; ++j) qt[size_t(j) * e.N + i] = e.pm.Qinv(i, j);
-  if (upload(e, e.band, e.pm.chol.band.data(), e.pm.chol.band.size()) || upload(e, e.inv_diag, e.pm.chol.inv_diag.data(), size_t(e.N)) ||
+  std::vector<double> fw(size_t(e.N) * 8, 0.0), bw(size_t(e.N) * 8, 0.0);
+  {
+    const int hb = e.pm.chol.hb;
+    for (int i = 0; i < e.N; ++i) {
+      const double inv = e.pm.chol.inv_diag[i];
+      fw[size_t(i) * 8] = bw[size_t(i) * 8] = inv;
+      for (int j = 1; j <= hb; ++j) {
+        if (i - j >= 0) fw[size_t(i) * 8 + j] = e.pm.chol.band[size_t(i) * (hb + 1) + j] * inv;
+        if (i + j < e.N) bw[size_t(i) * 8 + j] = e.pm.chol.band[size_t(i + j) * (hb + 1) + j] * inv;
+      }
+    }
+  }
+  if (upload(e, e.band_fw, fw.data(), fw.size()) || upload(e, e.band_bw, bw.data(), bw.size()) ||
       upload(e, e.proj_scale, e.pm.proj_scale.data(), size_t(e.N)) || upload(e, e.qinv_t, qt.data(), qt.size())) {
     delete ep;
     return 1;
@@ -608,6 +633,7 @@ int stomp_engine_set_sdf(void* h, const void* voxels, int32_t nx, int32_t ny, in
   if (!voxels || nx < 3 || ny < 3 || nz < 3 || resolution <= 0.0) return fail("bad distance field");
   size_t esz = voxel_dtype == STOMP_VOXEL_U8_SQ ? 1 : voxel_dtype == STOMP_VOXEL_U16_SQ ? 2 : voxel_dtype == STOMP_VOXEL_F32 ? 4 : 0;
   if (!esz) return fail("unknown voxel dtype");
+  if (size_t(nx) * ny * nz >= (size_t(1) << 31)) return fail("distance field too large (cells must fit a 32-bit index)");
   size_t bytes = size_t(nx) * ny * nz * esz;
   if (upload(e, e.vox, static_cast<const unsigned char*>(voxels), bytes)) return 1;
   e.sdf.vox = e.vox.p;

@@ -43,11 +43,10 @@ struct DevSphere {
   int original_index;
 };
 
-struct Band {           // banded Cholesky factor of R and the projection scaling
-  const double* band;   // [N][hb+1], band[i][k] = C(i, i-k)
-  const double* inv_diag;   // [N]
-  const double* proj_scale; // [N]
-  int hb;
+struct Band {           // banded Cholesky factor of R = C C^T and the projection scaling
+  const double* fw;         // [N][8]  {1/C(i,i), C(i,i-1)/C(i,i), ..., C(i,i-6)/C(i,i), 0}
+  const double* bw;         // [N][8]  {1/C(i,i), C(i+1,i)/C(i,i), ..., C(i+6,i)/C(i,i), 0}
+  const double* proj_scale; // [N]     s_p = 1/(N * max column p of R^-1)
 };
 
 struct Stencil {        // control-cost stencils of CovariantTrajectoryPolicy
@@ -143,39 +142,70 @@ struct GenArgs {
   Stencil st;
 };
 
-__device__ __forceinline__ void band_forward(double* x, const double* sb, const double* sinv, int N, int hb) {
+// Banded triangular solves with R = C C^T.  The tables hold, per row, the inverse diagonal and the six
+// sub-diagonal coefficients already multiplied by it (zero beyond the bandwidth), so one step is
+//   x_i = fma(-c1, x_{i-1}, fma(-c2, x_{i-2}, ... inv_i * b_i))
+// with the last outputs kept in registers: the dependent chain is ONE DFMA per step.
+//   fw[i] = {1/C(i,i), C(i,i-1)/C(i,i), ..., C(i,i-6)/C(i,i), 0}      (forward:  C   x = b)
+//   bw[i] = {1/C(i,i), C(i+1,i)/C(i,i), ..., C(i+6,i)/C(i,i), 0}      (backward: C^T x = b)
+// (built once per request on the host, engine.cu)
+__device__ __forceinline__ void band_forward(double* x, const double* fw, int N) {
+  double w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0, w6 = 0;
+#pragma unroll 4
   for (int i = 0; i < N; ++i) {
-    double s = x[i];
-    int kmax = min(hb, i);
-    for (int k = 1; k <= kmax; ++k) s -= sb[i * (hb + 1) + k] * x[i - k];
-    x[i] = s * sinv[i];
+    const double2* c = reinterpret_cast<const double2*>(fw + i * 8);
+    double2 c01 = c[0], c23 = c[1], c45 = c[2], c67 = c[3];
+    double s = c01.x * x[i];
+    s = fma(-c67.x, w6, s);
+    s = fma(-c45.y, w5, s);
+    s = fma(-c45.x, w4, s);
+    s = fma(-c23.y, w3, s);
+    s = fma(-c23.x, w2, s);
+    s = fma(-c01.y, w1, s);
+    x[i] = s;
+    w6 = w5; w5 = w4; w4 = w3; w3 = w2; w2 = w1; w1 = s;
   }
 }
 
-__device__ __forceinline__ void band_backward(double* x, const double* sb, const double* sinv, int N, int hb) {
+__device__ __forceinline__ void band_backward(double* x, const double* bw, int N) {
+  double w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0, w6 = 0;
+#pragma unroll 4
   for (int i = N - 1; i >= 0; --i) {
-    double s = x[i];
-    int kmax = min(hb, N - 1 - i);
-    for (int k = 1; k <= kmax; ++k) s -= sb[(i + k) * (hb + 1) + k] * x[i + k];
-    x[i] = s * sinv[i];
+    const double2* c = reinterpret_cast<const double2*>(bw + i * 8);
+    double2 c01 = c[0], c23 = c[1], c45 = c[2], c67 = c[3];
+    double s = c01.x * x[i];
+    s = fma(-c67.x, w6, s);
+    s = fma(-c45.y, w5, s);
+    s = fma(-c45.x, w4, s);
+    s = fma(-c23.y, w3, s);
+    s = fma(-c23.x, w2, s);
+    s = fma(-c01.y, w1, s);
+    x[i] = s;
+    w6 = w5; w5 = w4; w4 = w3; w3 = w2; w2 = w1; w1 = s;
   }
 }
 
 // One thread owns one vector v = (b, r, d) (or (b, d) for the extra rollout); its time series lives in one
 // shared-memory row with an odd stride, so the sequential band solves and stencils are bank-conflict free.
-// All global traffic is done by the whole CTA on the contiguous [blockDim][N] tile (coalesced).
+// All global traffic is done warp-wide on the contiguous [blockDim][N] tile: a warp copies one row at a time,
+// 32 consecutive doubles per instruction (coalesced, no index division).
+#define STOMP_TILE_LOOP(row, col, body)                                   \
+  for (int row = warp; row < nrows; row += nwarps)                        \
+    for (int col = lane; col < N; col += 32) { body }
+
 __global__ void k_generate(GenArgs a) {
   extern __shared__ double smem[];
-  const int N = a.N, hb = a.band.hb, TPB = blockDim.x;
+  const int N = a.N, TPB = blockDim.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = TPB >> 5;
   const int stride = N | 1;
-  double* sband = smem;                      // [N][hb+1]
-  double* sinv = sband + N * (hb + 1);       // [N]
-  double* sscale = sinv + N;                 // [N]
+  double* sfw = smem;                        // [N][8]
+  double* sbw = sfw + N * 8;                 // [N][8]
+  double* sscale = sbw + N * 8;              // [N]
   double* rows = sscale + N;                 // [TPB][stride]
   const double** s_theta = reinterpret_cast<const double**>(rows + size_t(TPB) * stride);  // [TPB]
   const double** s_prev = s_theta + TPB;     // [TPB] reused-rollout source row (NULL for new rollouts)
-  for (int i = threadIdx.x; i < N * (hb + 1); i += TPB) sband[i] = a.band.band[i];
-  for (int i = threadIdx.x; i < N; i += TPB) sinv[i] = a.band.inv_diag[i], sscale[i] = a.band.proj_scale[i];
+  for (int k = threadIdx.x; k < N * 8; k += TPB) sfw[k] = a.band.fw[k], sbw[k] = a.band.bw[k];
+  for (int i = threadIdx.x; i < N; i += TPB) sscale[i] = a.band.proj_scale[i];
 
   const int per_problem = (a.extra ? 1 : a.R) * a.D;
   const long long nvec = (long long)a.B * per_problem;
@@ -192,7 +222,6 @@ __global__ void k_generate(GenArgs a) {
   }
   const bool is_new = a.extra ? true : (r < a.R_gen);
   const size_t tile_off = size_t(v0) * N;
-  const size_t tile_len = size_t(nrows) * N;
   double* x = rows + size_t(threadIdx.x) * stride;
   {
     const double* th = a.theta + (size_t(b) * a.D + d) * N;
@@ -208,19 +237,17 @@ __global__ void k_generate(GenArgs a) {
 
   // ---- 1. noise into the rows --------------------------------------------------------------
   if (a.extra) {
-    for (size_t k = threadIdx.x; k < tile_len; k += TPB) rows[(k / N) * stride + (k % N)] = 0.0;
+    STOMP_TILE_LOOP(row, col, rows[row * stride + col] = 0.0;)
   } else if (!a.mode_generate) {
     const double* src = (a.mode_project ? a.noise : a.eps_in) + tile_off;
-    for (size_t k = threadIdx.x; k < tile_len; k += TPB) rows[(k / N) * stride + (k % N)] = src[k];
+    STOMP_TILE_LOOP(row, col, rows[row * stride + col] = src[row * N + col];)
   } else {
-    for (size_t k = threadIdx.x; k < tile_len; k += TPB) {
-      int row = int(k / N), col = int(k % N);
+    STOMP_TILE_LOOP(row, col,
       const double* pv = s_prev[row];
       double val = 0.0;
       if (pv) val = pv[col] - s_theta[row][col];          // noise = parameters - theta, policy_improvement.cpp:222
-      else if (a.injected) val = a.eps_in[tile_off + k];
-      rows[row * stride + col] = val;
-    }
+      else if (a.injected) val = a.eps_in[tile_off + row * N + col];
+      rows[row * stride + col] = val;)
     __syncthreads();
     if (active && is_new && !a.injected) {
       uint64_t stream = (uint64_t(b) * uint64_t(a.rollouts_global) + uint64_t(a.rollout_id_offset + r)) * uint64_t(a.D) + d;
@@ -231,18 +258,16 @@ __global__ void k_generate(GenArgs a) {
         if (i + 1 < N) x[i + 1] = z1;
       }
       // eps = sigma * C^-T z  ~ N(0, sigma^2 R^-1)  with R = C C^T
-      band_backward(x, sband, sinv, N, hb);
+      band_backward(x, sbw, N);
       double sg = a.noise_scale[d];
       for (int i = 0; i < N; ++i) x[i] *= sg;
     }
     __syncthreads();
-    for (size_t k = threadIdx.x; k < tile_len; k += TPB) {
-      int row = int(k / N), col = int(k % N);
+    STOMP_TILE_LOOP(row, col,
       double e = rows[row * stride + col];
       const double* pv = s_prev[row];
-      a.noise[tile_off + k] = e;
-      a.params[tile_off + k] = pv ? pv[col] : s_theta[row][col] + e;
-    }
+      a.noise[tile_off + row * N + col] = e;
+      a.params[tile_off + row * N + col] = pv ? pv[col] : s_theta[row][col] + e;)
   }
   if (!a.mode_control) return;
   __syncthreads();
@@ -251,17 +276,18 @@ __global__ void k_generate(GenArgs a) {
   if (a.mode_project && !a.extra) {
     if (active) {
       for (int i = 0; i < N; ++i) x[i] *= sscale[i];
-      band_forward(x, sband, sinv, N, hb);
-      band_backward(x, sband, sinv, N, hb);
+      band_forward(x, sfw, N);
+      band_backward(x, sbw, N);
     }
     __syncthreads();
-    if (a.noise_projected)
-      for (size_t k = threadIdx.x; k < tile_len; k += TPB) a.noise_projected[tile_off + k] = rows[(k / N) * stride + (k % N)];
+    if (a.noise_projected) {
+      STOMP_TILE_LOOP(row, col, a.noise_projected[tile_off + row * N + col] = rows[row * stride + col];)
+    }
   }
   // ---- 3. x = parameters + y -------------------------------------------------------------------
   {
     const double* pp = a.extra ? a.theta + tile_off : a.params + tile_off;
-    for (size_t k = threadIdx.x; k < tile_len; k += TPB) rows[(k / N) * stride + (k % N)] += pp[k];
+    STOMP_TILE_LOOP(row, col, rows[row * stride + col] += pp[row * N + col];)
   }
   __syncthreads();
   // ---- 4. control-cost stencils over the padded series, in place (sliding register window) -----
@@ -308,8 +334,9 @@ __global__ void k_generate(GenArgs a) {
     }
   }
   __syncthreads();
-  for (size_t k = threadIdx.x; k < tile_len; k += TPB) a.control[tile_off + k] = rows[(k / N) * stride + (k % N)];
+  STOMP_TILE_LOOP(row, col, a.control[tile_off + row * N + col] = rows[row * stride + col];)
 }
+#undef STOMP_TILE_LOOP
 
 // ---------------------------------------------------------------------------------------------
 // k_cost: the cost plugin.  One CTA per rollout; each warp owns a tile of 29 free timesteps
@@ -366,19 +393,25 @@ __device__ __forceinline__ float shfl_rel(float v, int delta) {
   return delta < 0 ? __shfl_up_sync(0xffffffffu, v, unsigned(-delta)) : __shfl_down_sync(0xffffffffu, v, unsigned(delta));
 }
 
-template <typename Real>
-__device__ __forceinline__ int voxel_cell(Real pos, Real origin, Real res, Real inv_res) {
-  // distance_field VoxelGrid::getCellFromLocation: int(round((loc - origin) / resolution)).
-  // Fast path multiplies by 1/res; whenever that product is within 1e-6 of a rounding boundary the exact
-  // division decides, so the index is bit-identical to the division form.
-  Real t = (pos - origin) * inv_res;
-  Real r = Math<Real>::round_(t);
-  if (Math<Real>::fabs_(Math<Real>::fabs_(t - r) - Real(0.5)) < Real(1e-6)) r = Math<Real>::round_((pos - origin) / res);
-  return int(r);
+// distance_field VoxelGrid::getCellFromLocation: int(round((loc - origin) / resolution)).
+// Fast path: multiply by 1/res and round to nearest-even in one conversion; whenever the product is within
+// 1e-6 of a rounding boundary the exact division + round-half-away form decides, so the index is identical
+// to the division form for every input.
+__device__ __forceinline__ int voxel_cell(double pos, double origin, double res, double inv_res) {
+  double t = (pos - origin) * inv_res;
+  int r = __double2int_rn(t);
+  if (fabs(t - double(r)) > 0.5 - 1e-6) r = int(round((pos - origin) / res));
+  return r;
+}
+__device__ __forceinline__ int voxel_cell(float pos, float origin, float res, float inv_res) {
+  float t = (pos - origin) * inv_res;
+  int r = __float2int_rn(t);
+  if (fabsf(t - float(r)) > 0.5f - 1e-3f) r = int(roundf((pos - origin) / res));
+  return r;
 }
 
 template <typename Real, bool kDebug>
-__global__ void __launch_bounds__(256) k_cost(CostArgs<Real> a) {
+__global__ void __launch_bounds__(128, 6) k_cost(CostArgs<Real> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = a.D, N = a.N, K = a.K;
   double* q = reinterpret_cast<double*>(smem_raw);                        // [D][N] clipped trajectory
@@ -449,6 +482,8 @@ __global__ void __launch_bounds__(256) k_cost(CostArgs<Real> a) {
   const Real c_m1 = Real(a.inv_time * (-2.0 / 6.0)), c_0 = Real(a.inv_time * (-3.0 / 6.0)), c_p1 = Real(a.inv_time * (6.0 / 6.0)),
              c_p2 = Real(a.inv_time * (-1.0 / 6.0));
   const int ntiles = (N + kTileSteps - 1) / kTileSteps;
+  const int nx1 = a.sdf.nx - 1, ny1 = a.sdf.ny - 1, nz1 = a.sdf.nz - 1, sny = a.sdf.ny, snz = a.sdf.nz, vdtype = a.sdf.dtype;
+  const void* vox = a.sdf.vox;
   double* out = a.costs + size_t(b) * a.cost_problem_stride + size_t(r) * N;
   int collided = 0;
 
@@ -505,38 +540,48 @@ __global__ void __launch_bounds__(256) k_cost(CostArgs<Real> a) {
         for (int i = 0; i < 12; ++i) saved[nd.save_slot][i] = F[i];
       }
       if (nd.sphere_end > nd.sphere_begin) {
-        // velocity frame: V = sum_k rule_k/dt * F(t+k); vel(sphere) = V.R * p + V.p  (linear in the frame)
+        // velocity frame V = sum_k rule_k/dt * F(t+k), vel(sphere) = V.R * p + V.p (linear in the frame); built
+        // lazily, only when some lane of the warp has a sphere of this link inside its clearance band
         Real V[12];
-#pragma unroll
-        for (int i = 0; i < 12; ++i)
-          V[i] = c_m1 * shfl_rel(F[i], -1) + c_0 * F[i] + c_p1 * shfl_rel(F[i], 1) + c_p2 * shfl_rel(F[i], 2);
+        bool haveV = false;
         for (int j = nd.sphere_begin; j < nd.sphere_end; ++j) {
           const DevSphere<Real>& sp = spheres[j];
-          Real px = F[0] * sp.pos[0] + F[1] * sp.pos[1] + F[2] * sp.pos[2] + F[9];
-          Real py = F[3] * sp.pos[0] + F[4] * sp.pos[1] + F[5] * sp.pos[2] + F[10];
-          Real pz = F[6] * sp.pos[0] + F[7] * sp.pos[1] + F[8] * sp.pos[2] + F[11];
-          Real vx = V[0] * sp.pos[0] + V[1] * sp.pos[1] + V[2] * sp.pos[2] + V[9];
-          Real vy = V[3] * sp.pos[0] + V[4] * sp.pos[1] + V[5] * sp.pos[2] + V[10];
-          Real vz = V[6] * sp.pos[0] + V[7] * sp.pos[1] + V[8] * sp.pos[2] + V[11];
-          int cx = voxel_cell<Real>(px, ox, res, inv_res);
-          int cy = voxel_cell<Real>(py, oy, res, inv_res);
-          int cz = voxel_cell<Real>(pz, oz, res, inv_res);
+          const Real s0 = sp.pos[0], s1 = sp.pos[1], s2 = sp.pos[2];
+          Real px = F[0] * s0 + F[1] * s1 + F[2] * s2 + F[9];
+          Real py = F[3] * s0 + F[4] * s1 + F[5] * s2 + F[10];
+          Real pz = F[6] * s0 + F[7] * s1 + F[8] * s2 + F[11];
+          int cx = voxel_cell(px, ox, res, inv_res);
+          int cy = voxel_cell(py, oy, res, inv_res);
+          int cz = voxel_cell(pz, oz, res, inv_res);
           Real dist = Real(0);
-          if (cx >= 1 && cy >= 1 && cz >= 1 && cx < a.sdf.nx - 1 && cy < a.sdf.ny - 1 && cz < a.sdf.nz - 1) {
-            size_t idx = (size_t(cx) * a.sdf.ny + cy) * a.sdf.nz + cz;
-            if (a.sdf.dtype == STOMP_VOXEL_U8_SQ) dist = sqrt_tab[__ldg(static_cast<const uint8_t*>(a.sdf.vox) + idx)];
-            else if (a.sdf.dtype == STOMP_VOXEL_U16_SQ)
-              dist = Math<Real>::sqrt_(Real(__ldg(static_cast<const uint16_t*>(a.sdf.vox) + idx))) * res;
-            else dist = Real(__ldg(static_cast<const float*>(a.sdf.vox) + idx));
+          if (cx >= 1 && cy >= 1 && cz >= 1 && cx < nx1 && cy < ny1 && cz < nz1) {
+            int idx = (cx * sny + cy) * snz + cz;
+            if (vdtype == STOMP_VOXEL_U8_SQ) dist = sqrt_tab[__ldg(static_cast<const uint8_t*>(vox) + idx)];
+            else if (vdtype == STOMP_VOXEL_U16_SQ)
+              dist = Math<Real>::sqrt_(Real(__ldg(static_cast<const uint16_t*>(vox) + idx))) * res;
+            else dist = Real(__ldg(static_cast<const float*>(vox) + idx));
           }
-          Real dd = dist - sp.radius, pot;
-          if (dd >= sp.clearance) pot = Real(0);
-          else if (dd >= Real(0)) { Real diff = dd - sp.clearance; pot = Real(0.5) * (diff * sp.inv_clearance) * diff; }
-          else pot = -dd + Real(0.5) * sp.clearance;
-          Real vm = Math<Real>::sqrt_(vx * vx + vy * vy + vz * vz);
-          bool hit = dist <= sp.radius;
-          cost += sp.weight * (pot * vm);
+          const Real radius = sp.radius, clearance = sp.clearance;
+          Real dd = dist - radius, pot;
+          if (dd >= clearance) pot = Real(0);
+          else if (dd >= Real(0)) { Real diff = dd - clearance; pot = Real(0.5) * (diff * sp.inv_clearance) * diff; }
+          else pot = -dd + Real(0.5) * clearance;
+          bool hit = dist <= radius;
           if (hit && counts) collided = 1;
+          Real vm = Real(0);
+          if (__any_sync(0xffffffffu, kDebug || pot != Real(0))) {
+            if (!haveV) {
+#pragma unroll
+              for (int i = 0; i < 12; ++i)
+                V[i] = c_m1 * shfl_rel(F[i], -1) + c_0 * F[i] + c_p1 * shfl_rel(F[i], 1) + c_p2 * shfl_rel(F[i], 2);
+              haveV = true;
+            }
+            Real vx = V[0] * s0 + V[1] * s1 + V[2] * s2 + V[9];
+            Real vy = V[3] * s0 + V[4] * s1 + V[5] * s2 + V[10];
+            Real vz = V[6] * s0 + V[7] * s1 + V[8] * s2 + V[11];
+            vm = Math<Real>::sqrt_(vx * vx + vy * vy + vz * vz);
+            cost += sp.weight * (pot * vm);
+          }
           if (kDebug) {
             if (t >= -1 && t <= N + 1 && (lane >= 1 && lane <= kTileSteps || (tile == 0 && lane == 0) ||
                                            (tile == ntiles - 1 && lane > kTileSteps))) {
@@ -654,6 +699,7 @@ __global__ void k_extra_total(int R, int D, int N, const double* __restrict__ st
 // ---------------------------------------------------------------------------------------------
 struct UpdateArgs {
   int R, D, N, apply;
+  int dims_per_cta;          // a CTA handles dims [g*dims_per_cta, ...) of one problem
   const double* cumulative;  // [B][R][D][N]
   const double* noise;       // [B][R][D][N]
   double* probabilities;     // optional tap
@@ -662,20 +708,26 @@ struct UpdateArgs {
   Band band;
 };
 
+// CTA per (problem, group of dimensions).  Phase 1 (all threads, thread per timestep): min / max over
+// rollouts, exp-normalised weights, probability-weighted noise.  Phase 2 (one lane per dimension): the
+// projection through M = R^-1 diag(s) as two banded triangular solves.  Phase 3: theta += update.
 __global__ void k_update(UpdateArgs a) {
   extern __shared__ double smem[];
-  const int N = a.N, R = a.R, D = a.D, hb = a.band.hb;
-  double* u = smem;                 // [N]
-  double* sband = u + N;            // [N][hb+1]
-  double* sinv = sband + N * (hb + 1);
-  const int b = blockIdx.x / D, d = blockIdx.x - b * D;
-  for (int i = threadIdx.x; i < N * (hb + 1); i += blockDim.x) sband[i] = a.band.band[i];
-  for (int i = threadIdx.x; i < N; i += blockDim.x) sinv[i] = a.band.inv_diag[i];
+  const int N = a.N, R = a.R, D = a.D, G = a.dims_per_cta;
+  const int stride = N | 1;
+  double* sfw = smem;               // [N][8]
+  double* sbw = sfw + N * 8;        // [N][8]
+  double* u = sbw + N * 8;          // [G][stride]
+  const int groups = (D + G - 1) / G;
+  const int b = blockIdx.x / groups, d0 = (blockIdx.x - b * groups) * G;
+  const int nd = min(G, D - d0);
+  for (int k = threadIdx.x; k < N * 8; k += blockDim.x) sfw[k] = a.band.fw[k], sbw[k] = a.band.bw[k];
   const size_t rstride = size_t(D) * N;
-  const size_t base = (size_t(b) * R * D + d) * N;
-  for (int t = threadIdx.x; t < N; t += blockDim.x) {
-    const double* c = a.cumulative + base + t;
-    const double* e = a.noise + base + t;
+  for (int k = threadIdx.x; k < nd * N; k += blockDim.x) {
+    const int dl = k / N, t = k - dl * N, d = d0 + dl;
+    const size_t base = (size_t(b) * R * D + d) * N + t;
+    const double* c = a.cumulative + base;
+    const double* e = a.noise + base;
     double mn = c[0], mx = c[0];
     for (int r = 1; r < R; ++r) {
       double v = c[r * rstride];
@@ -684,26 +736,31 @@ __global__ void k_update(UpdateArgs a) {
     }
     double denom = mx - mn;
     if (denom < 1e-8) denom = 1e-8;
-    double p_sum = 0.0;
-    for (int r = 0; r < R; ++r) p_sum += exp(-10.0 * (c[r * rstride] - mn) / denom);
-    double acc = 0.0;
+    const double h = -10.0 / denom;
+    double p_sum = 0.0, acc = 0.0;
     for (int r = 0; r < R; ++r) {
-      double p = exp(-10.0 * (c[r * rstride] - mn) / denom) / p_sum;
-      if (a.probabilities) a.probabilities[base + r * rstride + t] = p;
-      acc += e[r * rstride] * p;
+      double w = exp(h * (c[r * rstride] - mn));
+      p_sum += w;
+      acc += e[r * rstride] * w;
     }
-    u[t] = acc * a.band.proj_scale[t];
+    const double inv = 1.0 / p_sum;
+    if (a.probabilities)
+      for (int r = 0; r < R; ++r) a.probabilities[base + r * rstride] = exp(h * (c[r * rstride] - mn)) * inv;
+    u[dl * stride + t] = acc * inv * a.band.proj_scale[t];
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    band_forward(u, sband, sinv, N, hb);
-    band_backward(u, sband, sinv, N, hb);
+  if (threadIdx.x < nd) {
+    double* x = u + threadIdx.x * stride;
+    band_forward(x, sfw, N);
+    band_backward(x, sbw, N);
   }
   __syncthreads();
-  const size_t off = (size_t(b) * D + d) * N;
-  for (int t = threadIdx.x; t < N; t += blockDim.x) {
-    a.updates[off + t] = u[t];
-    if (a.apply) a.theta[off + t] += u[t];
+  const size_t off = (size_t(b) * D + d0) * N;
+  for (int k = threadIdx.x; k < nd * N; k += blockDim.x) {
+    const int dl = k / N, t = k - dl * N;
+    double v = u[dl * stride + t];
+    a.updates[off + k] = v;
+    if (a.apply) a.theta[off + k] += v;
   }
 }
 
@@ -784,18 +841,17 @@ __global__ void k_probabilities(int R, int DN, const double* __restrict__ cumula
 __global__ void k_finalize(int D, int N, int apply, const double* __restrict__ sums, double* __restrict__ updates,
                            double* __restrict__ theta, Band band) {
   extern __shared__ double smem[];
-  const int hb = band.hb, d = blockIdx.x, DN = D * N;
-  double* u = smem;
-  double* sband = u + N;
-  double* sinv = sband + N * (hb + 1);
-  for (int i = threadIdx.x; i < N * (hb + 1); i += blockDim.x) sband[i] = band.band[i];
-  for (int i = threadIdx.x; i < N; i += blockDim.x) sinv[i] = band.inv_diag[i];
+  const int d = blockIdx.x, DN = D * N;
+  double* sfw = smem;
+  double* sbw = sfw + N * 8;
+  double* u = sbw + N * 8;
+  for (int k = threadIdx.x; k < N * 8; k += blockDim.x) sfw[k] = band.fw[k], sbw[k] = band.bw[k];
   for (int t = threadIdx.x; t < N; t += blockDim.x)
     u[t] = (sums[DN + d * N + t] / sums[d * N + t]) * band.proj_scale[t];
   __syncthreads();
   if (threadIdx.x == 0) {
-    band_forward(u, sband, sinv, N, hb);
-    band_backward(u, sband, sinv, N, hb);
+    band_forward(u, sfw, N);
+    band_backward(u, sbw, N);
   }
   __syncthreads();
   for (int t = threadIdx.x; t < N; t += blockDim.x) {

@@ -246,3 +246,22 @@ def test_errors_are_reported():
     sc.num_reused_rollouts = sc.num_rollouts
     with pytest.raises(RuntimeError, match="reused rollouts"):
         Engine(sc)
+
+
+def test_engine_matches_committed_golden_vectors():
+    """the committed fixtures (tests/golden/make_golden.py) need no oracle at run time."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_iterations.npz"))
+    for cumulative in (0, 1):
+        sc = scenes.make_scenario("tiny", num_problems=2, use_cumulative_costs=cumulative)
+        eng = _engine(sc, keep_intermediates=1)
+        for it in range(1, 5):
+            key = "c%d_it%d_" % (cumulative, it)
+            eng.inject_noise(g[key + "eps"])
+            cost, cf, _ = eng.iterate(it)
+            assert_close(cost, g[key + "noiseless_cost"], RTOL_F64, "noiseless cost")
+            np.testing.assert_array_equal(cf, g[key + "collision_free"])
+            for f, nm in ((_abi.FIELD_THETA, "theta"), (_abi.FIELD_STATE_COSTS, "state_costs"),
+                          (_abi.FIELD_PROBABILITIES, "probabilities"), (_abi.FIELD_UPDATES, "updates"),
+                          (_abi.FIELD_ROLLOUT_TOTAL_COSTS, "totals")):
+                assert_close(eng.get(f), g[key + nm], RTOL_F64, nm + " it %d" % it)
