@@ -1,0 +1,440 @@
+// stomp_b200_facade.hpp — host C++ classes with the reference's names and call signatures for the
+// per-iteration rollout loop, implemented on top of the C ABI (include/stomp_b200.h).
+//
+// What maps to what (reference paths relative to stomp_motion_planner/):
+//   Policy, Task                         include/stomp_motion_planner/policy.h:47-134, task.h:49-93
+//   CovariantTrajectoryPolicy            include/stomp_motion_planner/covariant_trajectory_policy.h:48-283
+//     (alias CovariantMovementPrimitive: the name BASELINE.json uses, from the later `stomp` package)
+//   PolicyImprovement                    include/stomp_motion_planner/policy_improvement.h:65-126
+//   PolicyImprovementLoop                include/stomp_motion_planner/policy_improvement_loop.h:53-62
+//   StompOptimizer                       include/stomp_motion_planner/stomp_optimizer.h:63-114
+//
+// Differences that are forced by the missing dependencies (no ROS / Eigen 2 / Boost / KDL here):
+//   Eigen::VectorXd -> std::vector<double>; Eigen::MatrixXd -> stomp_motion_planner::MatrixXd (row-major);
+//   boost::shared_ptr -> std::shared_ptr; ros::NodeHandle parameters -> StompParameters (plain struct with the
+//   reference's parameter names and defaults).  Every method returns bool like the reference; the C ABI's error
+//   string is available from lastError().
+//
+// The cost-function plugin surface is Task::execute.  PolicyImprovementLoop::runSingleIteration runs the whole
+// iteration on the GPU (one stomp_engine_iterate call) when the task is the built-in StompOptimizer, and falls
+// back to the reference's exact call sequence (getRollouts -> task->execute per rollout -> setRolloutCosts ->
+// improvePolicy -> updateParameters -> execute(noise-less) -> addExtraRollouts) for any other Task, with the
+// PI^2 arithmetic still on the GPU.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "stomp_b200.h"
+
+namespace stomp_motion_planner {
+
+typedef std::vector<double> VectorXd;
+
+struct MatrixXd {
+  int rows_ = 0, cols_ = 0;
+  std::vector<double> data;
+  MatrixXd() {}
+  MatrixXd(int r, int c) : rows_(r), cols_(c), data(size_t(r) * c, 0.0) {}
+  static MatrixXd Zero(int r, int c) { return MatrixXd(r, c); }
+  int rows() const { return rows_; }
+  int cols() const { return cols_; }
+  double& operator()(int i, int j) { return data[size_t(i) * cols_ + j]; }
+  double operator()(int i, int j) const { return data[size_t(i) * cols_ + j]; }
+};
+
+inline const char* lastError() { return stomp_engine_last_error(); }
+
+// ---- parameters: config/params.yaml + StompParameters defaults (src/stomp_parameters.cpp:53-75) ---------
+struct StompParameters {
+  double trajectory_duration = 5.0, trajectory_discretization = 0.05;
+  int max_iterations = 500, max_iterations_after_collision_free = 500;
+  double smoothness_cost_velocity = 0.0, smoothness_cost_acceleration = 1.0, smoothness_cost_jerk = 0.0;
+  double smoothness_cost_weight = 0.1, obstacle_cost_weight = 1.0, ridge_factor = 0.0;
+  // PolicyImprovementLoop::readParameters (src/policy_improvement_loop.cpp:112-123)
+  int num_rollouts = 10, num_reused_rollouts = 5, num_time_steps = 99;
+  std::vector<double> noise_stddev, noise_decay;
+  bool use_cumulative_costs = true;
+  // engine-only knobs
+  int dtype = STOMP_F64, device = 0;
+  uint64_t seed = 0x57012011ull;
+};
+
+// ---- outputs of StompRobotModel / StompCollisionSpace that the path consumes ------------------------------
+struct StompRobotModel {
+  std::vector<stomp_segment> segments;  // KDL tree in DFS pre-order
+  int reference_segment = 0;
+  std::vector<stomp_sphere> collision_points;
+  std::vector<stomp_joint_limit> joint_limits;  // one per planning-group joint
+  int getNumJoints() const { return int(joint_limits.size()); }
+};
+
+struct StompCollisionSpace {
+  std::vector<uint8_t> voxels;  // squared cell distances, x-major
+  int nx = 0, ny = 0, nz = 0, voxel_dtype = STOMP_VOXEL_U8_SQ;
+  double origin[3] = {0, 0, 0}, resolution = 0.015;
+};
+
+// shared RAII owner of one engine handle
+class Engine {
+ public:
+  explicit Engine(void* h) : h_(h) {}
+  ~Engine() { if (h_) stomp_engine_destroy(h_); }
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+  void* get() const { return h_; }
+  int D = 0, N = 0, R = 0, R_reused = 0;
+ private:
+  void* h_;
+};
+
+// ---- Policy / Task: the plugin interfaces ------------------------------------------------------------------
+class Policy {
+ public:
+  virtual ~Policy() {}
+  virtual bool setNumTimeSteps(const int num_time_steps) = 0;
+  virtual bool getNumTimeSteps(int& num_time_steps) = 0;
+  virtual bool getNumDimensions(int& num_dimensions) = 0;
+  virtual bool getNumParameters(std::vector<int>& num_params) = 0;
+  virtual bool getBasisFunctions(std::vector<MatrixXd>& basis_functions) = 0;
+  virtual bool getControlCosts(std::vector<MatrixXd>& control_costs) = 0;
+  virtual bool updateParameters(const std::vector<MatrixXd>& updates) = 0;
+  virtual bool getParameters(std::vector<VectorXd>& parameters) = 0;
+  virtual bool setParameters(const std::vector<VectorXd>& parameters) = 0;
+  virtual bool computeControlCosts(const std::vector<MatrixXd>& control_cost_matrices, const std::vector<VectorXd>& parameters,
+                                   const std::vector<VectorXd>& noise, const double weight,
+                                   std::vector<VectorXd>& control_costs) = 0;
+};
+
+class Task {
+ public:
+  virtual ~Task() {}
+  virtual bool initialize(const StompParameters& params, int num_time_steps) = 0;
+  // executes one rollout: parameters[d][t] -> costs[t]   (include/stomp_motion_planner/task.h:70)
+  virtual bool execute(std::vector<VectorXd>& parameters, VectorXd& costs, const int iteration_number) = 0;
+  virtual bool getPolicy(std::shared_ptr<Policy>& policy) = 0;
+  virtual bool setPolicy(const std::shared_ptr<Policy> policy) = 0;
+  virtual bool getControlCostWeight(double& control_cost_weight) = 0;
+  // engine the task's policy lives on (the PI^2 state is kept there)
+  virtual std::shared_ptr<Engine> getEngine() = 0;
+};
+
+// ---- CovariantTrajectoryPolicy ---------------------------------------------------------------------------------
+class CovariantTrajectoryPolicy : public Policy {
+ public:
+  explicit CovariantTrajectoryPolicy(std::shared_ptr<Engine> engine) : e_(engine) {}
+  // setToMinControlCost (src/covariant_trajectory_policy.cpp:102-112): also resets the rollout-reuse state
+  bool setToMinControlCost(const VectorXd& start, const VectorXd& goal) {
+    return stomp_engine_set_problems(e_->get(), start.data(), goal.data()) == 0;
+  }
+  bool setNumTimeSteps(const int n) override { return n == e_->N; }
+  bool getNumTimeSteps(int& n) override { n = e_->N; return true; }
+  bool getNumDimensions(int& d) override { d = e_->D; return true; }
+  bool getNumParameters(std::vector<int>& n) override { n.assign(e_->D, e_->N); return true; }
+  bool getBasisFunctions(std::vector<MatrixXd>& basis) override {  // identity (params == time steps)
+    MatrixXd I(e_->N, e_->N);
+    for (int i = 0; i < e_->N; ++i) I(i, i) = 1.0;
+    basis.assign(e_->D, I);
+    return true;
+  }
+  bool getControlCosts(std::vector<MatrixXd>& control_costs) override { return getMatrix(STOMP_FIELD_CONTROL_COST, control_costs); }
+  bool getInvControlCosts(std::vector<MatrixXd>& inv) { return getMatrix(STOMP_FIELD_INV_CONTROL_COST, inv); }
+  bool updateParameters(const std::vector<MatrixXd>& updates) override {  // row 0 only, like the reference
+    std::vector<double> u(size_t(e_->D) * e_->N);
+    if (int(updates.size()) != e_->D) return false;
+    for (int d = 0; d < e_->D; ++d)
+      for (int t = 0; t < e_->N; ++t) u[size_t(d) * e_->N + t] = updates[d](0, t);
+    return stomp_engine_update_parameters(e_->get(), u.data()) == 0;
+  }
+  bool getParameters(std::vector<VectorXd>& parameters) override {
+    std::vector<double> th(size_t(e_->D) * e_->N);
+    if (stomp_engine_get_parameters(e_->get(), th.data())) return false;
+    parameters.resize(e_->D);
+    for (int d = 0; d < e_->D; ++d) parameters[d].assign(th.begin() + size_t(d) * e_->N, th.begin() + size_t(d + 1) * e_->N);
+    return true;
+  }
+  bool setParameters(const std::vector<VectorXd>& parameters) override {
+    std::vector<double> th;
+    for (const VectorXd& p : parameters) th.insert(th.end(), p.begin(), p.end());
+    return th.size() == size_t(e_->D) * e_->N && stomp_engine_set_parameters(e_->get(), th.data()) == 0;
+  }
+  bool computeControlCosts(const std::vector<MatrixXd>&, const std::vector<VectorXd>& parameters, const std::vector<VectorXd>& noise,
+                           const double weight, std::vector<VectorXd>& control_costs) override {
+    std::vector<double> p, n, c(size_t(e_->D) * e_->N);
+    for (int d = 0; d < e_->D; ++d) p.insert(p.end(), parameters[d].begin(), parameters[d].end()), n.insert(n.end(), noise[d].begin(), noise[d].end());
+    if (stomp_engine_compute_control_costs(e_->get(), p.data(), n.data(), 1, weight, c.data())) return false;
+    control_costs.resize(e_->D);
+    for (int d = 0; d < e_->D; ++d) control_costs[d].assign(c.begin() + size_t(d) * e_->N, c.begin() + size_t(d + 1) * e_->N);
+    return true;
+  }
+  std::shared_ptr<Engine> engine() const { return e_; }
+
+ private:
+  bool getMatrix(int field, std::vector<MatrixXd>& out) {
+    MatrixXd m(e_->N, e_->N);
+    if (stomp_engine_get(e_->get(), field, m.data.data(), m.data.size() * sizeof(double))) return false;
+    out.assign(e_->D, m);
+    return true;
+  }
+  std::shared_ptr<Engine> e_;
+};
+typedef CovariantTrajectoryPolicy CovariantMovementPrimitive;
+
+// ---- PolicyImprovement ---------------------------------------------------------------------------------------
+class PolicyImprovement {
+ public:
+  bool initialize(const int num_rollouts, const int num_time_steps, const int num_reused_rollouts, const int num_extra_rollouts,
+                  std::shared_ptr<Policy> policy, bool use_cumulative_costs = true) {
+    (void)use_cumulative_costs;
+    auto ctp = std::dynamic_pointer_cast<CovariantTrajectoryPolicy>(policy);
+    if (!ctp) return false;  // the PI^2 state lives on the policy's engine
+    e_ = ctp->engine();
+    if (num_extra_rollouts != 1) return false;  // hard-coded 1 in the reference loop (policy_improvement_loop.cpp:103)
+    return (initialized_ = (num_rollouts == e_->R && num_time_steps == e_->N && num_reused_rollouts == e_->R_reused));
+  }
+  bool getRollouts(std::vector<std::vector<VectorXd> >& rollouts, const std::vector<double>& noise_stddev) {
+    if (!initialized_) return false;
+    std::vector<double> buf(size_t(e_->R) * e_->D * e_->N);
+    int32_t gen = 0;
+    if (stomp_engine_get_rollouts(e_->get(), noise_stddev.data(), buf.data(), &gen)) return false;
+    rollouts.assign(gen, std::vector<VectorXd>(e_->D));
+    for (int r = 0; r < gen; ++r)
+      for (int d = 0; d < e_->D; ++d) {
+        const double* p = &buf[(size_t(r) * e_->D + d) * e_->N];
+        rollouts[r][d].assign(p, p + e_->N);
+      }
+    num_gen_ = gen;
+    return true;
+  }
+  // costs: [num generated rollouts][num_time_steps]
+  bool setRolloutCosts(const MatrixXd& costs, const double control_cost_weight, std::vector<double>& rollout_costs_total) {
+    if (!initialized_ || costs.rows() < num_gen_ || costs.cols() != e_->N) return false;
+    rollout_costs_total.resize(e_->R);
+    return stomp_engine_set_rollout_costs(e_->get(), costs.data.data(), control_cost_weight, rollout_costs_total.data()) == 0;
+  }
+  bool improvePolicy(std::vector<MatrixXd>& parameter_updates) {
+    if (!initialized_) return false;
+    std::vector<double> u(size_t(e_->D) * e_->N);
+    if (stomp_engine_improve_policy(e_->get(), u.data())) return false;
+    parameter_updates.assign(e_->D, MatrixXd(e_->N, e_->N));  // only row 0 is ever filled (policy_improvement.cpp:370-383)
+    for (int d = 0; d < e_->D; ++d)
+      for (int t = 0; t < e_->N; ++t) parameter_updates[d](0, t) = u[size_t(d) * e_->N + t];
+    return true;
+  }
+  // the single extra rollout must be the policy's current parameters (as in policy_improvement_loop.cpp:186-192)
+  bool addExtraRollouts(std::vector<std::vector<VectorXd> >& rollouts, std::vector<VectorXd>& rollout_costs) {
+    if (!initialized_ || rollouts.size() != 1 || rollout_costs.size() != 1) return false;
+    return stomp_engine_add_extra_rollouts(e_->get(), rollout_costs[0].data()) == 0;
+  }
+
+ private:
+  std::shared_ptr<Engine> e_;
+  bool initialized_ = false;
+  int num_gen_ = 0;
+};
+
+class StompOptimizer;
+
+// ---- PolicyImprovementLoop -------------------------------------------------------------------------------------
+class PolicyImprovementLoop {
+ public:
+  bool initialize(const StompParameters& params, std::shared_ptr<Task> task);
+  bool runSingleIteration(const int iteration_number);
+  // results of the noise-less rollout of the last iteration
+  double lastNoiselessCost() const { return last_cost_; }
+  bool lastNoiselessCollisionFree() const { return last_collision_free_; }
+
+ private:
+  StompParameters params_;
+  std::shared_ptr<Task> task_;
+  std::shared_ptr<Policy> policy_;
+  std::shared_ptr<Engine> e_;
+  PolicyImprovement policy_improvement_;
+  double control_cost_weight_ = 0.0, last_cost_ = 0.0;
+  bool last_collision_free_ = false, fused_ = false, initialized_ = false;
+};
+
+// ---- StompOptimizer: the built-in GPU Task + the outer optimisation loop ------------------------------------------
+struct STOMPStatistics {  // msg/STOMPStatistics.msg
+  bool success = false;
+  int success_iteration = -1, collision_success_iteration = -1;
+  double best_cost = 0.0;
+  std::vector<double> costs;
+};
+
+class StompOptimizer : public Task, public std::enable_shared_from_this<StompOptimizer> {
+ public:
+  // start / goal: the fixed trajectory end points of the planning group (free_vars_start_-1, free_vars_end_+1)
+  StompOptimizer(const VectorXd& start, const VectorXd& goal, const StompRobotModel* robot_model,
+                 const StompParameters* parameters, const StompCollisionSpace* collision_space)
+      : start_(start), goal_(goal), robot_model_(robot_model), parameters_(parameters), collision_space_(collision_space) {
+    ok_ = initializeEngine();
+  }
+  bool ok() const { return ok_; }
+
+  bool initialize(const StompParameters&, int num_time_steps) override { return ok_ && num_time_steps == engine_->N; }
+  bool execute(std::vector<VectorXd>& parameters, VectorXd& costs, const int iteration_number) override {
+    std::vector<double> p;
+    for (const VectorXd& v : parameters) p.insert(p.end(), v.begin(), v.end());
+    if (p.size() != size_t(engine_->D) * engine_->N) return false;
+    costs.assign(engine_->N, 0.0);
+    int32_t cf = 0;
+    if (stomp_engine_execute(engine_->get(), p.data(), 1, iteration_number, costs.data(), &cf)) return false;
+    last_trajectory_collision_free_ = cf != 0;
+    last_trajectory_cost_ = 0.0;
+    for (double c : costs) last_trajectory_cost_ += c;
+    return true;
+  }
+  bool getPolicy(std::shared_ptr<Policy>& policy) override { policy = policy_; return true; }
+  bool setPolicy(const std::shared_ptr<Policy>) override { return true; }
+  bool getControlCostWeight(double& w) override { w = parameters_->smoothness_cost_weight; return true; }
+  std::shared_ptr<Engine> getEngine() override { return engine_; }
+
+  // StompOptimizer::optimize (src/stomp_optimizer.cpp:249-401), STOMP branch
+  bool optimize(STOMPStatistics* stats = nullptr) {
+    if (!ok_) return false;
+    PolicyImprovementLoop pi_loop;
+    if (!pi_loop.initialize(*parameters_, shared_from_this())) return false;
+    STOMPStatistics st;
+    int collision_free_iteration = 0;
+    std::vector<VectorXd> best;
+    double best_cost = 0.0;
+    last_improvement_iteration_ = -1;
+    for (iteration_ = 0; iteration_ < parameters_->max_iterations; iteration_++) {
+      if (!pi_loop.runSingleIteration(iteration_ + 1)) return false;
+      last_trajectory_cost_ = pi_loop.lastNoiselessCost();
+      last_trajectory_collision_free_ = pi_loop.lastNoiselessCollisionFree();
+      collision_free_iteration = last_trajectory_collision_free_ ? collision_free_iteration + 1 : 0;
+      if (last_trajectory_collision_free_ && st.collision_success_iteration == -1) st.collision_success_iteration = iteration_;
+      if (last_trajectory_collision_free_ && st.success_iteration == -1) { st.success_iteration = iteration_; st.success = true; }
+      double cost = last_trajectory_cost_;
+      st.costs.push_back(cost);
+      if (iteration_ == 0 || (cost < best_cost && last_trajectory_collision_free_)) {
+        if (iteration_ > 0) last_improvement_iteration_ = iteration_;
+        policy_->getParameters(best);
+        best_cost = cost;
+      }
+      if (collision_free_iteration >= parameters_->max_iterations_after_collision_free) { iteration_++; break; }
+    }
+    policy_->setParameters(best);  // group_trajectory_ = best_group_trajectory_
+    st.best_cost = best_cost;
+    if (stats) *stats = st;
+    return true;
+  }
+
+  double getLastTrajectoryCost() const { return last_trajectory_cost_; }
+  bool isLastTrajectoryCollisionFree() const { return last_trajectory_collision_free_; }
+  int getLastImprovementIteration() const { return last_improvement_iteration_; }
+
+ private:
+  bool initializeEngine() {
+    stomp_engine_desc d = {};
+    d.num_dimensions = robot_model_->getNumJoints();
+    d.num_time_steps = parameters_->num_time_steps;
+    d.num_rollouts = parameters_->num_rollouts;
+    d.num_reused_rollouts = parameters_->num_reused_rollouts;
+    d.num_problems = 1;
+    d.dtype = parameters_->dtype;
+    d.use_cumulative_costs = parameters_->use_cumulative_costs ? 1 : 0;
+    d.sdf_mode = STOMP_SDF_NEAREST;
+    d.device = parameters_->device;
+    d.rollout_shard_rank = 0;
+    d.rollout_shard_world = 1;
+    // group trajectory: N free + 2*6 padded points; StompTrajectory::getDuration() returns int and seeds the
+    // policy's movement duration (stomp_trajectory.h:141, stomp_optimizer.cpp:187): keep the truncation
+    d.movement_duration = double(int((parameters_->num_time_steps + 2 * (STOMP_DIFF_RULE_LENGTH - 1) - 1) *
+                                     parameters_->trajectory_discretization));
+    d.discretization = parameters_->trajectory_discretization;
+    d.derivative_costs[0] = parameters_->smoothness_cost_velocity;
+    d.derivative_costs[1] = parameters_->smoothness_cost_acceleration;
+    d.derivative_costs[2] = parameters_->smoothness_cost_jerk;
+    d.ridge_factor = parameters_->ridge_factor;
+    d.smoothness_cost_weight = parameters_->smoothness_cost_weight;
+    d.obstacle_cost_weight = parameters_->obstacle_cost_weight;
+    void* h = nullptr;
+    if (stomp_engine_create(&d, &h)) return false;
+    engine_ = std::make_shared<Engine>(h);
+    engine_->D = d.num_dimensions; engine_->N = d.num_time_steps; engine_->R = d.num_rollouts; engine_->R_reused = d.num_reused_rollouts;
+    if (stomp_engine_set_robot(h, robot_model_->segments.data(), int(robot_model_->segments.size()), robot_model_->reference_segment,
+                               robot_model_->collision_points.data(), int(robot_model_->collision_points.size()),
+                               robot_model_->joint_limits.data()))
+      return false;
+    if (stomp_engine_set_sdf(h, collision_space_->voxels.data(), collision_space_->nx, collision_space_->ny, collision_space_->nz,
+                             collision_space_->origin, collision_space_->resolution, collision_space_->voxel_dtype))
+      return false;
+    std::vector<double> sd = parameters_->noise_stddev, dc = parameters_->noise_decay;
+    sd.resize(d.num_dimensions, 2.0);
+    dc.resize(d.num_dimensions, 0.999);
+    if (stomp_engine_set_noise(h, sd.data(), dc.data()) || stomp_engine_seed(h, parameters_->seed)) return false;
+    policy_ = std::make_shared<CovariantTrajectoryPolicy>(engine_);
+    return policy_->setToMinControlCost(start_, goal_);
+  }
+
+  VectorXd start_, goal_;
+  const StompRobotModel* robot_model_;
+  const StompParameters* parameters_;
+  const StompCollisionSpace* collision_space_;
+  std::shared_ptr<Engine> engine_;
+  std::shared_ptr<CovariantTrajectoryPolicy> policy_;
+  bool ok_ = false, last_trajectory_collision_free_ = false;
+  double last_trajectory_cost_ = 0.0;
+  int iteration_ = 0, last_improvement_iteration_ = -1;
+};
+
+// ---- PolicyImprovementLoop implementation -----------------------------------------------------------------------
+inline bool PolicyImprovementLoop::initialize(const StompParameters& params, std::shared_ptr<Task> task) {
+  params_ = params;
+  task_ = task;
+  if (!task_->initialize(params_, params_.num_time_steps)) return false;
+  if (!task_->getPolicy(policy_) || !task_->getControlCostWeight(control_cost_weight_)) return false;
+  e_ = task_->getEngine();
+  if (!e_) return false;
+  params_.noise_stddev.resize(e_->D, 2.0);
+  params_.noise_decay.resize(e_->D, 0.999);
+  if (!policy_improvement_.initialize(params_.num_rollouts, params_.num_time_steps, params_.num_reused_rollouts, 1, policy_,
+                                      params_.use_cumulative_costs))
+    return false;
+  fused_ = dynamic_cast<StompOptimizer*>(task_.get()) != nullptr;
+  return (initialized_ = true);
+}
+
+inline bool PolicyImprovementLoop::runSingleIteration(const int iteration_number) {
+  if (!initialized_) return false;
+  if (fused_) {  // the built-in GPU task: the whole iteration stays on the device
+    double cost = 0.0;
+    int32_t cf = 0;
+    stomp_iter_stats st = {&cost, &cf, 0, 0};
+    if (stomp_engine_iterate(e_->get(), iteration_number, &st)) return false;
+    last_cost_ = cost;
+    last_collision_free_ = cf != 0;
+    return true;
+  }
+  // any other Task: the reference's call sequence (src/policy_improvement_loop.cpp:143-202)
+  std::vector<double> noise(e_->D);
+  for (int i = 0; i < e_->D; ++i) noise[i] = params_.noise_stddev[i] * std::pow(params_.noise_decay[i], iteration_number - 1);
+  std::vector<std::vector<VectorXd> > rollouts;
+  if (!policy_improvement_.getRollouts(rollouts, noise)) return false;
+  MatrixXd rollout_costs(int(rollouts.size()), e_->N);
+  VectorXd tmp;
+  for (size_t r = 0; r < rollouts.size(); ++r) {
+    if (!task_->execute(rollouts[r], tmp, iteration_number)) return false;
+    for (int t = 0; t < e_->N; ++t) rollout_costs(int(r), t) = tmp[t];
+  }
+  std::vector<double> all_costs;
+  if (!policy_improvement_.setRolloutCosts(rollout_costs, control_cost_weight_, all_costs)) return false;
+  std::vector<MatrixXd> parameter_updates;
+  if (!policy_improvement_.improvePolicy(parameter_updates)) return false;
+  if (!policy_->updateParameters(parameter_updates)) return false;
+  std::vector<VectorXd> parameters;
+  if (!policy_->getParameters(parameters)) return false;
+  if (!task_->execute(parameters, tmp, iteration_number)) return false;
+  last_cost_ = 0.0;
+  for (double c : tmp) last_cost_ += c;
+  std::vector<std::vector<VectorXd> > extra_rollout(1, parameters);
+  std::vector<VectorXd> extra_rollout_cost(1, tmp);
+  return policy_improvement_.addExtraRollouts(extra_rollout, extra_rollout_cost);
+}
+
+}  // namespace stomp_motion_planner

@@ -77,6 +77,7 @@ struct Engine {
   int cur = 0;  // ping-pong index of params / state costs
   bool reused_next = false, extra_added = false;
   int num_gen = 0;
+  uint32_t generation = 0;  // rollout generations since set_problems: the Philox "iteration" counter
   bool injected_pending = false;
   double control_cost_weight = 0.0;
 
@@ -380,7 +381,8 @@ int step_get_rollouts(Engine& e, int iteration_number, bool with_control) {
   a.mode_project = 1;
   a.mode_control = with_control ? 1 : 0;
   a.injected = e.injected_pending ? 1 : 0;
-  a.iteration = uint32_t(iteration_number);
+  (void)iteration_number;
+  a.iteration = ++e.generation;
   a.control_weight = 0.5 * e.control_cost_weight;
   e.injected_pending = false;
   return launch_generate(e, a);
@@ -669,6 +671,7 @@ int stomp_engine_set_problems(void* h, const double* start, const double* goal) 
   e.reused_next = false;
   e.extra_added = false;
   e.num_gen = 0;
+  e.generation = 0;
   e.cur = 0;
   e.injected_pending = false;
   e.have_problems = true;
