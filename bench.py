@@ -221,10 +221,27 @@ def run_engine(args):
         return float(t.item())
 
     name = args.workload
-    B = args.problems
-    sc = workload(name, rank, B)
     dtype = _abi.F32 if args.dtype == "f32" else _abi.F64
-    eng = Engine(sc, dtype=dtype, device=local)
+    sharded = name == "C3"
+    if sharded:
+        # one planning problem, rollouts sharded over the ranks (strong scaling), two NCCL all-reduces per iteration
+        from stomp_motion_planner_icra2011_b200 import scenes
+        from stomp_motion_planner_icra2011_b200.distributed import ShardedIteration, device_views
+        B = 1
+        total_rollouts = args.rollouts
+        sc = scenes.make_scenario("C3", num_problems=1, num_rollouts=total_rollouts // world, seed=7)
+        eng = Engine(sc, dtype=dtype, device=local, shard_rank=rank, shard_world=world)
+        if world > 1:
+            mm, sm = device_views(eng)
+            driver = ShardedIteration(eng, mm, sm, dist=dist)
+            eng_iterate = lambda i, stats=False: driver.iterate(i)
+        else:
+            eng_iterate = lambda i, stats=False: eng.iterate(i, stats=stats)
+    else:
+        B = args.problems
+        sc = workload(name, rank, B)
+        eng = Engine(sc, dtype=dtype, device=local)
+        eng_iterate = lambda i, stats=False: eng.iterate(i, stats=stats)
     D, N, R = eng.D, eng.N, eng.R
     rgen = R - sc.num_reused_rollouts
     K, W = args.steps, max(args.warmup, 3)
@@ -232,7 +249,7 @@ def run_engine(args):
     # ---- device-resident throughput ("value") -----------------------------------------------------
     it = 1
     for _ in range(W):
-        eng.iterate(it, stats=False)
+        eng_iterate(it)
         it += 1
     eng.synchronize()
     sampler = ClockSampler(local)
@@ -242,53 +259,69 @@ def run_engine(args):
     l0 = eng.launch_count()
     eng.timer_start()
     for _ in range(K):
-        eng.iterate(it, stats=False)
+        eng_iterate(it)
         it += 1
     ms = eng.timer_stop()
     barrier()
     launches = eng.launch_count() - l0
     ms = max_over_ranks(ms)
     clocks = sampler.stop() if rank == 0 else None
-    evals_step = evals_per_iteration(sc, B, False)
-    value = world * evals_step * K / (ms * 1e-3)
+    evals_step = evals_per_iteration(sc, B, False)        # per rank
+    if sharded:   # the noise-less rollout is replicated on every rank: count it once
+        total_evals_step = world * B * rgen * N + N
+    else:
+        total_evals_step = world * evals_step
+    value = total_evals_step * K / (ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ("e2e") ----------------------------------------
     # host-injection mode: every step copies that step's noise from pinned host memory, runs the iteration,
     # and reads the per-problem noise-less cost / collision flag and the updated trajectories back.
-    L = np.linalg.cholesky(eng.get(_abi.FIELD_INV_CONTROL_COST))
-    rng = np.random.default_rng(1234 + rank)
-    eps_pinned = torch.empty((B, rgen, D, N), dtype=torch.float64).pin_memory()
     theta_pinned = torch.empty((B, D, N), dtype=torch.float64).pin_memory()
-    eps_np, theta_np = eps_pinned.numpy(), theta_pinned.numpy()
-    z = rng.standard_normal((min(B, 16), rgen, D, N))
-    base = np.einsum("ij,...j->...i", L, z) * 2.0
-    eps_np[...] = np.resize(base, eps_np.shape)
+    theta_np = theta_pinned.numpy()
     Ke = max(3, min(K, 20))
+    if not sharded:
+        L = np.linalg.cholesky(eng.get(_abi.FIELD_INV_CONTROL_COST))
+        rng = np.random.default_rng(1234 + rank)
+        eps_pinned = torch.empty((B, rgen, D, N), dtype=torch.float64).pin_memory()
+        eps_np = eps_pinned.numpy()
+        z = rng.standard_normal((min(B, 16), rgen, D, N))
+        base = np.einsum("ij,...j->...i", L, z) * 2.0
+        eps_np[...] = np.resize(base, eps_np.shape)
+
+        def e2e_step(i):
+            eng.inject_noise(eps_np)
+            eng.iterate(i)
+            eng.get_parameters(theta_np)
+        h2d, api = int(eps_np.nbytes + 8 * D), ("stomp_engine_inject_noise(pinned eps) + stomp_engine_iterate(stats) + "
+                                                "stomp_engine_get_parameters(pinned)")
+    else:
+        def e2e_step(i):
+            eng_iterate(i)
+            eng.get_parameters(theta_np)
+        h2d, api = 8 * D, "sharded iterate (3 phases + 2 all-reduces) + stomp_engine_get_parameters(pinned); noise is engine Philox"
     for _ in range(2):
-        eng.inject_noise(eps_np); eng.iterate(it); eng.get_parameters(theta_np); it += 1
+        e2e_step(it); it += 1
     barrier()
     t0 = time.perf_counter()
     for _ in range(Ke):
-        eng.inject_noise(eps_np)
-        eng.iterate(it)
-        eng.get_parameters(theta_np)
+        e2e_step(it)
         it += 1
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e = {"value": world * evals_step * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(eps_np.nbytes + 8 * D),
-           "d2h_bytes_per_step": int(theta_np.nbytes + B * 12), "ms_per_step": 1e3 * e2e_s / Ke, "steps": Ke,
-           "api": "stomp_engine_inject_noise(pinned eps) + stomp_engine_iterate(stats) + stomp_engine_get_parameters(pinned)"}
+    e2e = {"value": total_evals_step * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": int(theta_np.nbytes + B * 12), "ms_per_step": 1e3 * e2e_s / Ke, "steps": Ke, "api": api}
 
     # ---- per-kernel event timing for the roofline (separate pass: events around every launch) ---------
     eng.set_profiling(1)
     Kp = max(3, min(K, 20))
     for _ in range(Kp):
-        eng.iterate(it, stats=False)
+        eng_iterate(it)
         it += 1
     cost_ms, cost_n = eng.get_profile("k_cost")
     all_ms, all_n = eng.get_profile("")
     shares = {}
-    for kn in ("k_select_reuse", "k_generate", "k_gather_state", "k_cost", "k_cumulative", "k_update", "k_extra_total"):
+    for kn in ("k_select_reuse", "k_generate", "k_gather_state", "k_cost", "k_cumulative", "k_update", "k_extra_total",
+               "k_minmax_partial", "k_sums_partial", "k_pair_reduce", "k_finalize"):
         m, n = eng.get_profile(kn)
         shares[kn] = {"ms_per_iteration": m / Kp, "launches_per_iteration": n / Kp}
     eng.set_profiling(0)
@@ -310,15 +343,19 @@ def run_engine(args):
                 "kernels": shares}
 
     if rank == 0:
-        cpu = cpu_baseline(name) if world == 1 and not args.no_cpu_baseline else None
+        cpu = cpu_baseline(name) if world == 1 and not args.no_cpu_baseline and not sharded else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": _workload_desc(name, sc, B), "parallelism": "problems sharded over %d GPU(s), no collective" % world,
+                "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": args.dtype,
+                "data": "synthetic",
+                "config": {"workload": _workload_desc(name, sc, B),
+                           "parallelism": ("rollouts sharded over %d GPU(s), 2 NCCL all-reduces of 2*D*N doubles per iteration" % world)
+                           if sharded else ("problems sharded over %d GPU(s), no collective" % world),
                            "l2": "per-iteration working set %.2f GB of rollout arrays >> 126 MB L2 (no flush needed)"
                                  % (6 * B * R * D * N * 8 / 1e9),
                            "noise": "engine Philox RNG", "evals_per_step_per_gpu": evals_step,
-                           "iterations_per_sec": world * 1e3 * K / ms, "problem_iterations_per_sec": world * B * 1e3 * K / ms,
-                           "rollouts_per_sec": world * B * (rgen + 1) * 1e3 * K / ms},
+                           "iterations_per_sec": 1e3 * K / ms,
+                           "problem_iterations_per_sec": (1 if sharded else world * B) * 1e3 * K / ms,
+                           "rollouts_per_sec": total_evals_step / N * 1e3 * K / ms},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -337,6 +374,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--problems", type=int, default=1024, help="planning problems per GPU")
+    ap.add_argument("--rollouts", type=int, default=65536, help="total rollouts of the C3 workload")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
