@@ -97,6 +97,7 @@ struct Engine {
   DevBuf<int> scratch_flags;
   DevBuf<stomp_sphere_debug> debug;
   DevBuf<double> part, minmax, sums;  // sharded / huge-R statistics
+  DevBuf<double> gen_scratch;         // time-major work buffer of k_generate
   int num_nodes = 0;
   Sdf sdf;
   size_t scratch_n = 0;
@@ -189,24 +190,16 @@ int upload_sqrt_table(Engine& e) {
 // ---- kernel launch helpers ----------------------------------------------------------------------
 
 int launch_generate(Engine& e, GenArgs a) {
-  const int N = e.N;
-  const size_t fixed = size_t(N) * 17 * 8;
-  const size_t per_thread = size_t(N | 1) * 8 + 16;
-  // pick the CTA size that keeps the most row-owning threads resident per SM (shared memory is the limiter)
-  int tpb = 0, best = 0;
-  for (int cand = 128; cand >= 32; cand -= 32) {
-    size_t need = fixed + per_thread * cand + 1024;
-    if (need > 227 * 1024) continue;
-    int resident = int((227 * 1024) / need) * cand;
-    if (resident > best) best = resident, tpb = cand;
-  }
-  if (tpb < 32) return fail("num_time_steps too large for the shared-memory row buffers of k_generate");
-  long long nvec = (long long)a.B * (a.extra ? 1 : a.R) * a.D;
-  // small batches: spread over more CTAs
-  while (tpb > 32 && (nvec + tpb - 1) / tpb < 296) tpb -= 32;
-  size_t smem = fixed + per_thread * tpb;
-  CUDA_TRY(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  unsigned grid = unsigned((nvec + tpb - 1) / tpb);
+  const int N = e.N, tpb = 128;
+  const long long nvec = (long long)a.B * (a.extra ? 1 : a.R) * a.D;
+  const unsigned grid = unsigned((nvec + tpb - 1) / tpb);
+  const size_t stride = size_t(grid) * tpb;
+  if (e.gen_scratch.n < stride * N) CUDA_TRY(e.gen_scratch.alloc(stride * N));
+  a.scratch = e.gen_scratch.p;
+  a.scratch_stride = stride;
+  const size_t smem = (size_t(N) * 17 + size_t(tpb / 32) * 2 * 32 * kTileLd) * 8;
+  if (smem > 220 * 1024) return fail("num_time_steps too large for the band tables of k_generate");
+  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   begin_launch(e);
   k_generate<<<grid, tpb, smem, e.stream>>>(a);
   return check_launch(e, "k_generate");

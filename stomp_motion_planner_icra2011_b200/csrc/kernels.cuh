@@ -111,9 +111,6 @@ __global__ void k_select_reuse(const double* __restrict__ totals, int R, int R_r
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// k_generate: one thread per vector v = (b, r, d); the time series lives in one padded shared-memory row.
-// ---------------------------------------------------------------------------------------------
 struct GenArgs {
   int B, R, D, N;
   int R_gen;                 // slots < R_gen are new, slots >= R_gen are reused (gathered)
@@ -138,6 +135,8 @@ struct GenArgs {
   double* params;            // [B][R][D][N]  (extra: unused)
   double* noise_projected;   // optional tap
   double* control;           // [B][R][D][N]  (extra: [B][D][N])
+  double* scratch;           // time-major [N][scratch_stride] work buffer
+  size_t scratch_stride;     // >= number of vectors, multiple of the CTA size
   Band band;
   Stencil st;
 };
@@ -185,33 +184,89 @@ __device__ __forceinline__ void band_backward(double* x, const double* bw, int N
   }
 }
 
-// One thread owns one vector v = (b, r, d) (or (b, d) for the extra rollout); its time series lives in one
-// shared-memory row with an odd stride, so the sequential band solves and stencils are bank-conflict free.
-// All global traffic is done warp-wide on the contiguous [blockDim][N] tile: a warp copies one row at a time,
-// 32 consecutive doubles per instruction (coalesced, no index division).
-#define STOMP_TILE_LOOP(row, col, body)                                   \
-  for (int row = warp; row < nrows; row += nwarps)                        \
-    for (int col = lane; col < N; col += 32) { body }
+// ---------------------------------------------------------------------------------------------
+// k_generate: streaming, one thread per vector v = (b, r, d) (or (b, d) for the extra rollout).
+//
+// Every step of the band solves / stencils is sequential in time, so a thread walks its own series.  To keep
+// all global traffic coalesced without parking the whole series in shared memory (which capped occupancy at
+// ~8 warps/SM), the kernel works in sweeps:
+//   A (backward in t)  noise: eps = sigma C^-T z from the Philox stream | injected | parameters - theta (reused);
+//                      writes noise and parameters
+//   B (forward)        w = C^-1 (s .* eps)                         -> scratch, TIME-MAJOR [t][vector]
+//   C (backward)       y = C^-T w = M eps ; x = parameters + y     -> scratch (in place)
+//   D (forward)        7-tap control-cost stencils over [pads, x, pads] with a sliding register window; writes
+//                      control costs
+// Row-major arrays ([vector][t]) are read / written through per-warp 32 x 16 transposition tiles in shared
+// memory (128-byte row segments); the time-major scratch is accessed directly (lane = vector -> coalesced).
+// ---------------------------------------------------------------------------------------------
+constexpr int kChunk = 16;
+constexpr int kTileLd = kChunk + 1;
 
-__global__ void k_generate(GenArgs a) {
+__device__ __forceinline__ const double* shfl_ptr(const double* p, int src_lane) {
+  unsigned long long v = reinterpret_cast<unsigned long long>(p);
+  v = __shfl_sync(0xffffffffu, v, src_lane);
+  return reinterpret_cast<const double*>(v);
+}
+
+// tile[row][col] = row_ptr(row)[c0 + col] for the 32 rows whose base pointers the lanes hold (nullptr -> 0)
+__device__ __forceinline__ void warp_tile_load(double* tile, const double* my_row, int c0, int len, int lane) {
+  __syncwarp();
+#pragma unroll 4
+  for (int e = lane; e < 32 * kChunk; e += 32) {
+    const int row = e >> 4, col = e & 15;
+    const double* rp = shfl_ptr(my_row, row);
+    double v = 0.0;
+    if (rp != nullptr && col < len) v = rp[c0 + col];
+    tile[row * kTileLd + col] = v;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void warp_tile_store(const double* tile, double* my_row, int c0, int len, int lane) {
+  __syncwarp();
+#pragma unroll 4
+  for (int e = lane; e < 32 * kChunk; e += 32) {
+    const int row = e >> 4, col = e & 15;
+    double* rp = const_cast<double*>(shfl_ptr(my_row, row));
+    if (rp != nullptr && col < len) rp[c0 + col] = tile[row * kTileLd + col];
+  }
+  __syncwarp();
+}
+
+struct BandWindow {
+  double w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0, w6 = 0;
+  // one step of a banded triangular solve: row = {1/diag, c1/diag, ..., c6/diag, 0}; returns x_i
+  __device__ __forceinline__ double step(const double* row, double rhs) {
+    const double2* c = reinterpret_cast<const double2*>(row);
+    const double2 c01 = c[0], c23 = c[1], c45 = c[2], c67 = c[3];
+    double s = c01.x * rhs;
+    s = fma(-c67.x, w6, s);
+    s = fma(-c45.y, w5, s);
+    s = fma(-c45.x, w4, s);
+    s = fma(-c23.y, w3, s);
+    s = fma(-c23.x, w2, s);
+    s = fma(-c01.y, w1, s);
+    w6 = w5; w5 = w4; w4 = w3; w3 = w2; w2 = w1; w1 = s;
+    return s;
+  }
+};
+
+__global__ void __launch_bounds__(128) k_generate(GenArgs a) {
   extern __shared__ double smem[];
-  const int N = a.N, TPB = blockDim.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = TPB >> 5;
-  const int stride = N | 1;
+  const int N = a.N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* sfw = smem;                        // [N][8]
   double* sbw = sfw + N * 8;                 // [N][8]
   double* sscale = sbw + N * 8;              // [N]
-  double* rows = sscale + N;                 // [TPB][stride]
-  const double** s_theta = reinterpret_cast<const double**>(rows + size_t(TPB) * stride);  // [TPB]
-  const double** s_prev = s_theta + TPB;     // [TPB] reused-rollout source row (NULL for new rollouts)
-  for (int k = threadIdx.x; k < N * 8; k += TPB) sfw[k] = a.band.fw[k], sbw[k] = a.band.bw[k];
-  for (int i = threadIdx.x; i < N; i += TPB) sscale[i] = a.band.proj_scale[i];
+  double* tE = sscale + N + size_t(warp) * 2 * 32 * kTileLd;   // per-warp tiles
+  double* tT = tE + 32 * kTileLd;
+  for (int k = threadIdx.x; k < N * 8; k += blockDim.x) sfw[k] = a.band.fw[k], sbw[k] = a.band.bw[k];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sscale[i] = a.band.proj_scale[i];
+  __syncthreads();
 
   const int per_problem = (a.extra ? 1 : a.R) * a.D;
   const long long nvec = (long long)a.B * per_problem;
-  const long long v0 = (long long)blockIdx.x * TPB;
-  const long long v = v0 + threadIdx.x;
-  const int nrows = int(min((long long)TPB, nvec - v0));   // rows of this CTA that exist
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = v < nvec;
   int b = 0, r = 0, d = 0;
   if (active) {
@@ -220,89 +275,124 @@ __global__ void k_generate(GenArgs a) {
     r = rem / a.D;
     d = rem - r * a.D;
   }
-  const bool is_new = a.extra ? true : (r < a.R_gen);
-  const size_t tile_off = size_t(v0) * N;
-  double* x = rows + size_t(threadIdx.x) * stride;
-  {
-    const double* th = a.theta + (size_t(b) * a.D + d) * N;
-    const double* pv = nullptr;
-    if (active && !a.extra && !is_new) {
-      int src = a.reuse_src[size_t(b) * (a.R - a.R_gen) + (r - a.R_gen)];
-      pv = src >= 0 ? a.params_prev + ((size_t(b) * a.R + src) * a.D + d) * N : th;
-    }
-    s_theta[threadIdx.x] = th;
-    s_prev[threadIdx.x] = pv;
-  }
-  __syncthreads();
+  const size_t row_off = size_t(v) * N;
+  const double* th_row = active ? a.theta + (size_t(b) * a.D + d) * N : nullptr;
+  double* wb = a.scratch + v;                 // time-major scratch: element i at wb[i * sstride]
+  const size_t sstride = a.scratch_stride;
+  const int last_c0 = ((N - 1) / kChunk) * kChunk;
+  double* my_tE = tE + lane * kTileLd;
+  double* my_tT = tT + lane * kTileLd;
 
-  // ---- 1. noise into the rows --------------------------------------------------------------
-  if (a.extra) {
-    STOMP_TILE_LOOP(row, col, rows[row * stride + col] = 0.0;)
-  } else if (!a.mode_generate) {
-    const double* src = (a.mode_project ? a.noise : a.eps_in) + tile_off;
-    STOMP_TILE_LOOP(row, col, rows[row * stride + col] = src[row * N + col];)
-  } else {
-    STOMP_TILE_LOOP(row, col,
-      const double* pv = s_prev[row];
-      double val = 0.0;
-      if (pv) val = pv[col] - s_theta[row][col];          // noise = parameters - theta, policy_improvement.cpp:222
-      else if (a.injected) val = a.eps_in[tile_off + row * N + col];
-      rows[row * stride + col] = val;)
-    __syncthreads();
-    if (active && is_new && !a.injected) {
-      uint64_t stream = (uint64_t(b) * uint64_t(a.rollouts_global) + uint64_t(a.rollout_id_offset + r)) * uint64_t(a.D) + d;
-      for (int i = 0; i < N; i += 2) {
-        double z0, z1;
-        normal_pair(a.seed, stream, a.iteration, uint32_t(i >> 1), z0, z1);
-        x[i] = z0;
-        if (i + 1 < N) x[i + 1] = z1;
+  // ---- sweep A: noise and parameters --------------------------------------------------------------------
+  if (a.mode_generate && !a.extra) {
+    const bool is_new = r < a.R_gen;
+    const bool philox = active && is_new && !a.injected;
+    const double* src = nullptr;
+    if (active) {
+      if (!is_new) {
+        int sidx = a.reuse_src[size_t(b) * (a.R - a.R_gen) + (r - a.R_gen)];
+        src = sidx >= 0 ? a.params_prev + ((size_t(b) * a.R + sidx) * a.D + d) * N : th_row;
+      } else if (a.injected) {
+        src = a.eps_in + row_off;
       }
-      // eps = sigma * C^-T z  ~ N(0, sigma^2 R^-1)  with R = C C^T
-      band_backward(x, sbw, N);
-      double sg = a.noise_scale[d];
-      for (int i = 0; i < N; ++i) x[i] *= sg;
     }
-    __syncthreads();
-    STOMP_TILE_LOOP(row, col,
-      double e = rows[row * stride + col];
-      const double* pv = s_prev[row];
-      a.noise[tile_off + row * N + col] = e;
-      a.params[tile_off + row * N + col] = pv ? pv[col] : s_theta[row][col] + e;)
+    double* out_noise = active ? a.noise + row_off : nullptr;
+    double* out_params = active ? a.params + row_off : nullptr;
+    const double sg = active ? a.noise_scale[d] : 0.0;
+    const uint64_t stream = (uint64_t(b) * uint64_t(a.rollouts_global) + uint64_t(a.rollout_id_offset + r)) * uint64_t(a.D) + d;
+    BandWindow bw;
+    double zkeep = 0.0;
+    for (int c0 = last_c0; c0 >= 0; c0 -= kChunk) {
+      const int len = min(kChunk, N - c0);
+      warp_tile_load(tE, src, c0, len, lane);
+      warp_tile_load(tT, th_row, c0, len, lane);
+      if (philox) {
+        // eps = sigma * C^-T z  ~ N(0, sigma^2 R^-1)  with R = C C^T (z drawn for descending i)
+        for (int k = len - 1; k >= 0; --k) {
+          const int i = c0 + k;
+          double z;
+          if ((i & 1) || i == N - 1) {
+            double z0, z1;
+            normal_pair(a.seed, stream, a.iteration, uint32_t(i >> 1), z0, z1);
+            z = (i & 1) ? z1 : z0;
+            zkeep = z0;
+          } else {
+            z = zkeep;
+          }
+          const double e = sg * bw.step(sbw + i * 8, z);
+          my_tT[k] += e;          // parameters = theta + noise
+          my_tE[k] = e;
+        }
+      } else if (active && is_new) {   // injected noise
+        for (int k = 0; k < len; ++k) my_tT[k] += my_tE[k];
+      } else if (active) {             // reused rollout: noise = parameters - theta (policy_improvement.cpp:222)
+        for (int k = 0; k < len; ++k) {
+          const double pv = my_tE[k];
+          my_tE[k] = pv - my_tT[k];
+          my_tT[k] = pv;
+        }
+      }
+      warp_tile_store(tE, out_noise, c0, len, lane);
+      warp_tile_store(tT, out_params, c0, len, lane);
+    }
   }
   if (!a.mode_control) return;
-  __syncthreads();
 
-  // ---- 2. projected noise y = R^-1 (s .* eps) --------------------------------------------------
+  // ---- sweeps B + C: x = parameters + M * noise into the time-major scratch -----------------------------------
   if (a.mode_project && !a.extra) {
-    if (active) {
-      for (int i = 0; i < N; ++i) x[i] *= sscale[i];
-      band_forward(x, sfw, N);
-      band_backward(x, sbw, N);
+    const double* nrow = active ? a.noise + row_off : nullptr;
+    {
+      BandWindow fwd;
+      for (int c0 = 0; c0 < N; c0 += kChunk) {
+        const int len = min(kChunk, N - c0);
+        warp_tile_load(tE, nrow, c0, len, lane);
+        if (active)
+          for (int k = 0; k < len; ++k) {
+            const int i = c0 + k;
+            wb[size_t(i) * sstride] = fwd.step(sfw + i * 8, sscale[i] * my_tE[k]);
+          }
+      }
     }
-    __syncthreads();
-    if (a.noise_projected) {
-      STOMP_TILE_LOOP(row, col, a.noise_projected[tile_off + row * N + col] = rows[row * stride + col];)
+    {
+      const double* prow = active ? a.params + row_off : nullptr;
+      double* ytap = (active && a.noise_projected) ? a.noise_projected + row_off : nullptr;
+      BandWindow bwd;
+      for (int c0 = last_c0; c0 >= 0; c0 -= kChunk) {
+        const int len = min(kChunk, N - c0);
+        warp_tile_load(tT, prow, c0, len, lane);
+        if (active)
+          for (int k = len - 1; k >= 0; --k) {
+            const int i = c0 + k;
+            const double y = bwd.step(sbw + i * 8, wb[size_t(i) * sstride]);
+            my_tE[k] = y;
+            wb[size_t(i) * sstride] = my_tT[k] + y;
+          }
+        if (a.noise_projected) warp_tile_store(tE, ytap, c0, len, lane);
+      }
+    }
+  } else {
+    // no projection: x = theta (extra rollout) or x = parameters + caller noise (Policy::computeControlCosts)
+    const double* prow = active ? (a.extra ? th_row : a.params + row_off) : nullptr;
+    const double* erow = (active && !a.extra) ? a.eps_in + row_off : nullptr;
+    for (int c0 = 0; c0 < N; c0 += kChunk) {
+      const int len = min(kChunk, N - c0);
+      warp_tile_load(tT, prow, c0, len, lane);
+      warp_tile_load(tE, erow, c0, len, lane);
+      if (active)
+        for (int k = 0; k < len; ++k) wb[size_t(c0 + k) * sstride] = my_tT[k] + my_tE[k];
     }
   }
-  // ---- 3. x = parameters + y -------------------------------------------------------------------
+
+  // ---- sweep D: control-cost stencils over the padded series (covariant_trajectory_policy.cpp:228-255) -------
   {
-    const double* pp = a.extra ? a.theta + tile_off : a.params + tile_off;
-    STOMP_TILE_LOOP(row, col, rows[row * stride + col] += pp[row * N + col];)
-  }
-  __syncthreads();
-  // ---- 4. control-cost stencils over the padded series, in place (sliding register window) -----
-  if (active) {
-    const double xs = a.pad_start[size_t(b) * a.D + d], xg = a.pad_goal[size_t(b) * a.D + d];
     const int Nall = N + 2 * kPad;
+    double xs = 0.0, xg = 0.0;
+    if (active) { xs = a.pad_start[size_t(b) * a.D + d]; xg = a.pad_goal[size_t(b) * a.D + d]; }
     auto xall = [&](int idx) -> double {
       if (idx < 0 || idx >= Nall) return 0.0;   // dropped taps of the differentiation matrices
-      return idx < kPad ? xs : (idx >= kPad + N ? xg : x[idx - kPad]);
+      return idx < kPad ? xs : (idx >= kPad + N ? xg : wb[size_t(idx - kPad) * sstride]);
     };
-    double w[7];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) w[j] = xall(j - 3);
-    double hc[kPad], tc[kPad];
-    for (int i = 0; i < Nall; ++i) {
+    auto stencil_cost = [&](const double* w) -> double {
       double cost = 0.0;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -312,31 +402,56 @@ __global__ void k_generate(GenArgs a) {
         for (int j = 0; j < 7; ++j) acc += a.st.coef[k][j] * w[j];
         cost += a.control_weight * a.st.weight[k] * (acc * acc);
       }
-      double next = xall(i + 4);   // read before x[i - kPad] is overwritten (it is x[i + 4 - kPad])
-      if (i < kPad) {
+      return cost;
+    };
+    double hc[kPad], tc[kPad], w[7];
+    if (active) {
+      // the six trailing padded rows only see the last three free values and the goal padding
 #pragma unroll
-        for (int q = 0; q < kPad; ++q) if (q == i) hc[q] = cost;
-      } else if (i >= kPad + N) {
+      for (int q = 0; q < kPad; ++q) {
+        const int p = kPad + N + q;
+        double ww[7];
 #pragma unroll
-        for (int q = 0; q < kPad; ++q) if (q == i - kPad - N) tc[q] = cost;
-      } else {
-        x[i - kPad] = cost;
+        for (int j = 0; j < 7; ++j) ww[j] = xall(p + j - 3);
+        tc[q] = stencil_cost(ww);
       }
 #pragma unroll
-      for (int j = 0; j < 6; ++j) w[j] = w[j + 1];
-      w[6] = next;
-    }
-    // fold the padded entries: covariant_trajectory_policy.cpp:245-250
+      for (int j = 0; j < 7; ++j) w[j] = xall(j - 3);
 #pragma unroll
-    for (int i = 0; i < kPad; ++i) {
-      x[0] += hc[i];
-      x[N - 1] += tc[kPad - 1 - i];
+      for (int p = 0; p < kPad; ++p) {   // leading padded rows
+        hc[p] = stencil_cost(w);
+        const double next = xall(p + 4);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) w[j] = w[j + 1];
+        w[6] = next;
+      }
+    }
+    double* crow = active ? a.control + row_off : nullptr;
+    for (int c0 = 0; c0 < N; c0 += kChunk) {
+      const int len = min(kChunk, N - c0);
+      __syncwarp();
+      if (active)
+        for (int k = 0; k < len; ++k) {
+          const int t = c0 + k, p = t + kPad;
+          double cost = stencil_cost(w);
+          if (t == 0) {
+#pragma unroll
+            for (int q = 0; q < kPad; ++q) cost += hc[q];
+          }
+          if (t == N - 1) {
+#pragma unroll
+            for (int q = 0; q < kPad; ++q) cost += tc[kPad - 1 - q];
+          }
+          my_tE[k] = cost;
+          const double next = xall(p + 4);
+#pragma unroll
+          for (int j = 0; j < 6; ++j) w[j] = w[j + 1];
+          w[6] = next;
+        }
+      warp_tile_store(tE, crow, c0, len, lane);
     }
   }
-  __syncthreads();
-  STOMP_TILE_LOOP(row, col, a.control[tile_off + row * N + col] = rows[row * stride + col];)
 }
-#undef STOMP_TILE_LOOP
 
 // ---------------------------------------------------------------------------------------------
 // k_cost: the cost plugin.  One CTA per rollout; each warp owns a tile of 29 free timesteps
