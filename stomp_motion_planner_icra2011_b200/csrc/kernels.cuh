@@ -208,23 +208,44 @@ __device__ __forceinline__ const double* shfl_ptr(const double* p, int src_lane)
   return reinterpret_cast<const double*>(v);
 }
 
-// tile[row][col] = row_ptr(row)[c0 + col] for the 32 rows whose base pointers the lanes hold (nullptr -> 0)
-__device__ __forceinline__ void warp_tile_load(double* tile, const double* my_row, int c0, int len, int lane) {
-  __syncwarp();
-#pragma unroll 4
+// tile[row][col] = row_ptr(row)[c0 + col] for the 32 rows whose base pointers the lanes hold (nullptr -> 0).
+// The copies are asynchronous (cp.async, LDGSTS): all 16 row segments of a tile - and of a second tile issued
+// right after - are in flight together, so a chunk pays one memory latency instead of one per row pair.
+__device__ __forceinline__ void warp_tile_load_async(double* tile, const double* my_row, int c0, int len, int lane) {
+#pragma unroll
   for (int e = lane; e < 32 * kChunk; e += 32) {
     const int row = e >> 4, col = e & 15;
     const double* rp = shfl_ptr(my_row, row);
-    double v = 0.0;
-    if (rp != nullptr && col < len) v = rp[c0 + col];
-    tile[row * kTileLd + col] = v;
+    double* dst = tile + row * kTileLd + col;
+    if (rp != nullptr && col < len) {
+      const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(dst));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(rp + c0 + col) : "memory");
+    } else {
+      *dst = 0.0;
+    }
   }
+}
+__device__ __forceinline__ void warp_tile_wait(void) {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncwarp();
+}
+__device__ __forceinline__ void warp_tile_load(double* tile, const double* my_row, int c0, int len, int lane) {
+  __syncwarp();
+  warp_tile_load_async(tile, my_row, c0, len, lane);
+  warp_tile_wait();
+}
+__device__ __forceinline__ void warp_tile_load2(double* t0, const double* row0, double* t1, const double* row1, int c0, int len,
+                                                int lane) {
+  __syncwarp();
+  warp_tile_load_async(t0, row0, c0, len, lane);
+  warp_tile_load_async(t1, row1, c0, len, lane);
+  warp_tile_wait();
 }
 
 __device__ __forceinline__ void warp_tile_store(const double* tile, double* my_row, int c0, int len, int lane) {
   __syncwarp();
-#pragma unroll 4
+#pragma unroll
   for (int e = lane; e < 32 * kChunk; e += 32) {
     const int row = e >> 4, col = e & 15;
     double* rp = const_cast<double*>(shfl_ptr(my_row, row));
@@ -301,27 +322,31 @@ __global__ void __launch_bounds__(128) k_generate(GenArgs a) {
     const double sg = active ? a.noise_scale[d] : 0.0;
     const uint64_t stream = (uint64_t(b) * uint64_t(a.rollouts_global) + uint64_t(a.rollout_id_offset + r)) * uint64_t(a.D) + d;
     BandWindow bw;
-    double zkeep = 0.0;
     for (int c0 = last_c0; c0 >= 0; c0 -= kChunk) {
       const int len = min(kChunk, N - c0);
-      warp_tile_load(tE, src, c0, len, lane);
-      warp_tile_load(tT, th_row, c0, len, lane);
+      warp_tile_load2(tE, src, tT, th_row, c0, len, lane);
       if (philox) {
-        // eps = sigma * C^-T z  ~ N(0, sigma^2 R^-1)  with R = C C^T (z drawn for descending i)
-        for (int k = len - 1; k >= 0; --k) {
-          const int i = c0 + k;
-          double z;
-          if ((i & 1) || i == N - 1) {
+        // eps = sigma * C^-T z  ~ N(0, sigma^2 R^-1)  with R = C C^T.
+        // 1. the chunk's standard normals: independent Philox / Box-Muller evaluations (ILP), parked in the tile row
+        {
+          const int p_lo = c0 >> 1, p_hi = (c0 + len - 1) >> 1;
+          for (int pr = p_lo; pr <= p_hi; ++pr) {
             double z0, z1;
-            normal_pair(a.seed, stream, a.iteration, uint32_t(i >> 1), z0, z1);
-            z = (i & 1) ? z1 : z0;
-            zkeep = z0;
-          } else {
-            z = zkeep;
+            normal_pair(a.seed, stream, a.iteration, uint32_t(pr), z0, z1);
+            const int i0 = 2 * pr - c0, i1 = i0 + 1;
+            if (i0 >= 0 && i0 < len) my_tE[i0] = z0;
+            if (i1 >= 0 && i1 < len) my_tE[i1] = z1;
           }
-          const double e = sg * bw.step(sbw + i * 8, z);
-          my_tT[k] += e;          // parameters = theta + noise
-          my_tE[k] = e;
+        }
+        // 2. the sequential back-substitution (one DFMA on the critical path per step)
+#pragma unroll
+        for (int kk = 0; kk < kChunk; ++kk) {
+          const int k = len - 1 - kk;
+          if (k >= 0) {
+            const double e = sg * bw.step(sbw + (c0 + k) * 8, my_tE[k]);
+            my_tT[k] += e;          // parameters = theta + noise
+            my_tE[k] = e;
+          }
         }
       } else if (active && is_new) {   // injected noise
         for (int k = 0; k < len; ++k) my_tT[k] += my_tE[k];
@@ -343,14 +368,18 @@ __global__ void __launch_bounds__(128) k_generate(GenArgs a) {
     const double* nrow = active ? a.noise + row_off : nullptr;
     {
       BandWindow fwd;
+      double* wp = wb;
       for (int c0 = 0; c0 < N; c0 += kChunk) {
         const int len = min(kChunk, N - c0);
         warp_tile_load(tE, nrow, c0, len, lane);
-        if (active)
-          for (int k = 0; k < len; ++k) {
-            const int i = c0 + k;
-            wb[size_t(i) * sstride] = fwd.step(sfw + i * 8, sscale[i] * my_tE[k]);
-          }
+        if (active) {
+#pragma unroll
+          for (int k = 0; k < kChunk; ++k)
+            if (k < len) {
+              *wp = fwd.step(sfw + (c0 + k) * 8, sscale[c0 + k] * my_tE[k]);
+              wp += sstride;
+            }
+        }
       }
     }
     {
@@ -360,13 +389,25 @@ __global__ void __launch_bounds__(128) k_generate(GenArgs a) {
       for (int c0 = last_c0; c0 >= 0; c0 -= kChunk) {
         const int len = min(kChunk, N - c0);
         warp_tile_load(tT, prow, c0, len, lane);
-        if (active)
-          for (int k = len - 1; k >= 0; --k) {
-            const int i = c0 + k;
-            const double y = bwd.step(sbw + i * 8, wb[size_t(i) * sstride]);
-            my_tE[k] = y;
-            wb[size_t(i) * sstride] = my_tT[k] + y;
+        if (active) {
+          double* wp = wb + size_t(c0) * sstride;
+          double wv[kChunk];
+#pragma unroll
+          for (int k = 0; k < kChunk; ++k)       // independent loads first: one memory latency per chunk
+            if (k < len) wv[k] = wp[size_t(k) * sstride];
+#pragma unroll
+          for (int kk = 0; kk < kChunk; ++kk) {
+            const int k = kChunk - 1 - kk;
+            if (k < len) {
+              const double y = bwd.step(sbw + (c0 + k) * 8, wv[k]);
+              my_tE[k] = y;
+              wv[k] = my_tT[k] + y;
+            }
           }
+#pragma unroll
+          for (int k = 0; k < kChunk; ++k)
+            if (k < len) wp[size_t(k) * sstride] = wv[k];
+        }
         if (a.noise_projected) warp_tile_store(tE, ytap, c0, len, lane);
       }
     }
@@ -376,10 +417,13 @@ __global__ void __launch_bounds__(128) k_generate(GenArgs a) {
     const double* erow = (active && !a.extra) ? a.eps_in + row_off : nullptr;
     for (int c0 = 0; c0 < N; c0 += kChunk) {
       const int len = min(kChunk, N - c0);
-      warp_tile_load(tT, prow, c0, len, lane);
-      warp_tile_load(tE, erow, c0, len, lane);
-      if (active)
-        for (int k = 0; k < len; ++k) wb[size_t(c0 + k) * sstride] = my_tT[k] + my_tE[k];
+      warp_tile_load2(tT, prow, tE, erow, c0, len, lane);
+      if (active) {
+        double* wp = wb + size_t(c0) * sstride;
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k)
+          if (k < len) wp[size_t(k) * sstride] = my_tT[k] + my_tE[k];
+      }
     }
   }
 
@@ -430,24 +474,34 @@ __global__ void __launch_bounds__(128) k_generate(GenArgs a) {
     for (int c0 = 0; c0 < N; c0 += kChunk) {
       const int len = min(kChunk, N - c0);
       __syncwarp();
-      if (active)
-        for (int k = 0; k < len; ++k) {
-          const int t = c0 + k, p = t + kPad;
-          double cost = stencil_cost(w);
-          if (t == 0) {
+      if (active) {
+        // look-ahead values x_all[t + kPad + 4] of the chunk: independent loads, one memory latency per chunk
+        double nx[kChunk];
 #pragma unroll
-            for (int q = 0; q < kPad; ++q) cost += hc[q];
-          }
-          if (t == N - 1) {
-#pragma unroll
-            for (int q = 0; q < kPad; ++q) cost += tc[kPad - 1 - q];
-          }
-          my_tE[k] = cost;
-          const double next = xall(p + 4);
-#pragma unroll
-          for (int j = 0; j < 6; ++j) w[j] = w[j + 1];
-          w[6] = next;
+        for (int k = 0; k < kChunk; ++k) {
+          const int f = c0 + k + 4;           // free index of the look-ahead element
+          nx[k] = 0.0;
+          if (k < len) nx[k] = f < N ? wb[size_t(f) * sstride] : (f < N + kPad ? xg : 0.0);
         }
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k)
+          if (k < len) {
+            const int t = c0 + k;
+            double cost = stencil_cost(w);
+            if (t == 0) {
+#pragma unroll
+              for (int q = 0; q < kPad; ++q) cost += hc[q];
+            }
+            if (t == N - 1) {
+#pragma unroll
+              for (int q = 0; q < kPad; ++q) cost += tc[kPad - 1 - q];
+            }
+            my_tE[k] = cost;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) w[j] = w[j + 1];
+            w[6] = nx[k];
+          }
+      }
       warp_tile_store(tE, crow, c0, len, lane);
     }
   }
