@@ -8,6 +8,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -61,7 +62,7 @@ struct DevBuf {
 struct Engine {
   stomp_engine_desc desc;
   int B = 0, D = 0, N = 0, R = 0, Rre = 0, K = 0;
-  int device = 0;
+  int device = 0, num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
@@ -233,12 +234,19 @@ int launch_cost_t(Engine& e, CostArgs<Real>& a, int num_problems) {
   int warps = std::min(ntiles, 4);
   warps = std::max(warps, std::min(e.D, 4));  // joint-limit pass likes a few warps
   size_t smem = size_t(e.D) * e.N * 8 + size_t(e.num_nodes) * sizeof(DevNode<Real>) + size_t(e.K) * sizeof(DevSphere<Real>) +
-                256 * sizeof(Real);
+                256 * sizeof(Real) + size_t(warps) * 12 * 32 * sizeof(Real);
   auto kern = k_cost<Real, kDebug>;
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   if (smem > 220 * 1024) return fail("trajectory + robot tables exceed shared memory");
   begin_launch(e);
-  kern<<<unsigned(num_problems) * a.n_rollouts, warps * 32, smem, e.stream>>>(a);
+  a.total_rollouts = num_problems * a.n_rollouts;
+  int per_sm = 1;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+  // STOMP_PERSISTENT=1: one CTA per resident slot walking rollouts with a grid stride; default: one CTA per
+  // rollout (the hardware block scheduler balances rollouts whose joint-limit projection takes longer)
+  static const bool persistent = getenv("STOMP_PERSISTENT") && atoi(getenv("STOMP_PERSISTENT")) != 0;
+  const int grid = persistent ? std::min(a.total_rollouts, std::max(1, per_sm) * e.num_sms) : a.total_rollouts;
+  kern<<<grid, warps * 32, smem, e.stream>>>(a);
   return check_launch(e, "k_cost");
 }
 
@@ -537,6 +545,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   cudaError_t c;
   if ((c = cudaSetDevice(e.device)) != cudaSuccess) return bail(c, "cudaSetDevice");
   if ((c = cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
+  if ((c = cudaDeviceGetAttribute(&e.num_sms, cudaDevAttrMultiProcessorCount, e.device)) != cudaSuccess) return bail(c, "cudaDeviceGetAttribute");
   if ((c = cudaEventCreate(&e.ev0)) != cudaSuccess || (c = cudaEventCreate(&e.ev1)) != cudaSuccess) return bail(c, "cudaEventCreate");
   const size_t BDN = size_t(e.B) * e.D * e.N, BRDN = BDN * e.R, BRN = size_t(e.B) * e.R * e.N;
 #define ALLOC(buf, n) if ((c = (buf).alloc(n)) != cudaSuccess) return bail(c, "cudaMalloc " #buf)

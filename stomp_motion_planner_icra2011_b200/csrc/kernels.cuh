@@ -516,6 +516,7 @@ __global__ void __launch_bounds__(128) k_generate(GenArgs a) {
 template <typename Real>
 struct CostArgs {
   int n_rollouts;            // rollouts per problem processed by this launch
+  int total_rollouts;        // problems * n_rollouts
   int D, N, K, num_nodes;
   int include_pads;          // 1: start/goal padding points count towards collision_free (iteration_ == 0)
   size_t params_problem_stride, params_rollout_stride;  // in doubles
@@ -563,24 +564,48 @@ __device__ __forceinline__ float shfl_rel(float v, int delta) {
 }
 
 // distance_field VoxelGrid::getCellFromLocation: int(round((loc - origin) / resolution)).
-// Fast path: multiply by 1/res and round to nearest-even in one conversion; whenever the product is within
-// 1e-6 of a rounding boundary the exact division + round-half-away form decides, so the index is identical
-// to the division form for every input.
+// Fast path: multiply by 1/res and round to nearest with the 2^52+2^51 trick (the integer is the low word of
+// the sum, no F2I/I2F conversions); whenever the product is within 1e-6 of a rounding boundary the exact
+// division + round-half-away form decides, so the index is identical to the division form for every input.
+// Coordinates too large for a 32-bit cell index return -1 (outside the grid).
 __device__ __forceinline__ int voxel_cell(double pos, double origin, double res, double inv_res) {
+#if STOMP_MAGIC_ROUND
+  const double magic = 6755399441055744.0;
+  const double t = (pos - origin) * inv_res;
+  const double m = t + magic;
+  int r = __double2loint(m);
+  if (fabs(t - (m - magic)) > 0.5 - 1e-6 || !(fabs(t) < 1.0e9))
+    r = fabs(t) < 1.0e9 ? int(round((pos - origin) / res)) : -1;
+  return r;
+#else
   double t = (pos - origin) * inv_res;
   int r = __double2int_rn(t);
   if (fabs(t - double(r)) > 0.5 - 1e-6) r = int(round((pos - origin) / res));
   return r;
+#endif
 }
 __device__ __forceinline__ int voxel_cell(float pos, float origin, float res, float inv_res) {
   float t = (pos - origin) * inv_res;
   int r = __float2int_rn(t);
-  if (fabsf(t - float(r)) > 0.5f - 1e-3f) r = int(roundf((pos - origin) / res));
+  if (fabsf(t - float(r)) > 0.5f - 1e-3f || !(fabsf(t) < 1.0e9f)) r = fabsf(t) < 1.0e9f ? int(roundf((pos - origin) / res)) : -1;
   return r;
 }
 
+#ifndef STOMP_KCOST_MIN_BLOCKS
+#define STOMP_KCOST_MIN_BLOCKS 7
+#endif
+#ifndef STOMP_SPHERE_BATCH
+#define STOMP_SPHERE_BATCH 1
+#endif
+#ifndef STOMP_MAGIC_ROUND
+#define STOMP_MAGIC_ROUND 1
+#endif
+constexpr int kSphereBatch = STOMP_SPHERE_BATCH;   // SDF gathers kept in flight per lane
+
+// Persistent CTAs: the grid is sized to the machine (SMs x resident CTAs) and every CTA walks rollouts with a
+// grid stride, so the robot tables are staged in shared memory once per CTA instead of once per rollout.
 template <typename Real, bool kDebug>
-__global__ void __launch_bounds__(128, 6) k_cost(CostArgs<Real> a) {
+__global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<Real> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = a.D, N = a.N, K = a.K;
   double* q = reinterpret_cast<double*>(smem_raw);                        // [D][N] clipped trajectory
@@ -589,11 +614,9 @@ __global__ void __launch_bounds__(128, 6) k_cost(CostArgs<Real> a) {
   Real* sqrt_tab = reinterpret_cast<Real*>(spheres + K);                  // [256]
   __shared__ int s_collision;
 
-  const int b = blockIdx.x / a.n_rollouts, r = blockIdx.x - b * a.n_rollouts;
-  const double* src = a.params + size_t(b) * a.params_problem_stride + size_t(r) * a.params_rollout_stride;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-
-  for (int i = threadIdx.x; i < D * N; i += blockDim.x) q[i] = src[i];
+  // per-warp velocity frame [12][32]: kept in shared memory so that the register file holds only one frame
+  Real* Vs = sqrt_tab + 256 + size_t(warp) * 12 * 32 + lane;
   {
     const int* s32 = reinterpret_cast<const int*>(a.nodes);
     int* d32 = reinterpret_cast<int*>(nodes);
@@ -603,49 +626,6 @@ __global__ void __launch_bounds__(128, 6) k_cost(CostArgs<Real> a) {
     for (int i = threadIdx.x; i < int(sizeof(DevSphere<Real>) / 4) * K; i += blockDim.x) d32[i] = s32[i];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sqrt_tab[i] = a.sqrt_table[i];
   }
-  if (threadIdx.x == 0) s_collision = 0;
-  __syncthreads();
-
-  // ---- handleJointLimits: warp per joint, <= 11 passes of (arg max violation, rank-1 correction) ----------
-  for (int d = warp; d < D; d += nwarps) {
-    if (!a.has_limits[d]) continue;
-    const double jmax = a.limit_max[d], jmin = a.limit_min[d];
-    double* qd = q + size_t(d) * N;
-    for (int count = 0; count < 11; ++count) {
-      double best_abs = 1e-6, best_amount = 0.0;
-      int best_idx = -1;
-      for (int i = lane; i < N; i += 32) {
-        double v = qd[i], amount = 0.0;
-        if (v > jmax) amount = jmax - v;
-        else if (v < jmin) amount = jmin - v;
-        double aa = fabs(amount);
-        if (aa > best_abs) { best_abs = aa; best_amount = amount; best_idx = i; }
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        double oa = __shfl_xor_sync(0xffffffffu, best_abs, off);
-        double om = __shfl_xor_sync(0xffffffffu, best_amount, off);
-        int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
-        // strict '>' in index order keeps the first maximum: larger violation wins, ties -> smaller index
-        bool take = (oi >= 0) && (best_idx < 0 || oa > best_abs || (oa == best_abs && oi < best_idx));
-        if (take) { best_abs = oa; best_amount = om; best_idx = oi; }
-      }
-      if (best_idx < 0) break;
-      const double* col = a.qinv_t + size_t(best_idx) * N;
-      double multiplier = best_amount / col[best_idx];
-      for (int i = lane; i < N; i += 32) qd[i] += multiplier * col[i];
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  if (a.clipped) {
-    double* dst = a.clipped + size_t(b) * a.params_problem_stride + size_t(r) * a.params_rollout_stride;
-    for (int i = threadIdx.x; i < D * N; i += blockDim.x) dst[i] = q[i];
-  }
-
-  // ---- FK + spheres + SDF + velocity + cost -------------------------------------------------------
-  const double* ps = a.pad_start + size_t(b) * D;
-  const double* pg = a.pad_goal + size_t(b) * D;
   const Real ox = Real(a.sdf.origin[0]), oy = Real(a.sdf.origin[1]), oz = Real(a.sdf.origin[2]);
   const Real res = Real(a.sdf.res), inv_res = Real(a.sdf.inv_res);
   const Real c_m1 = Real(a.inv_time * (-2.0 / 6.0)), c_0 = Real(a.inv_time * (-3.0 / 6.0)), c_p1 = Real(a.inv_time * (6.0 / 6.0)),
@@ -653,124 +633,201 @@ __global__ void __launch_bounds__(128, 6) k_cost(CostArgs<Real> a) {
   const int ntiles = (N + kTileSteps - 1) / kTileSteps;
   const int nx1 = a.sdf.nx - 1, ny1 = a.sdf.ny - 1, nz1 = a.sdf.nz - 1, sny = a.sdf.ny, snz = a.sdf.nz, vdtype = a.sdf.dtype;
   const void* vox = a.sdf.vox;
-  double* out = a.costs + size_t(b) * a.cost_problem_stride + size_t(r) * N;
-  int collided = 0;
 
-  for (int tile = warp; tile < ntiles; tile += nwarps) {
-    const int t = tile * kTileSteps - 1 + lane;      // trajectory point of this lane (-1 .. N+1 are meaningful)
-    const bool productive = lane >= 1 && lane <= kTileSteps && t < N;
-    const bool counts = productive || (a.include_pads && (t == -1 || t == N));
-    Real cost = Real(0);
-    Real F[12], saved[kMaxSlots][12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) F[i] = Real(0);
+  for (int job = blockIdx.x; job < a.total_rollouts; job += gridDim.x) {
+    const int b = job / a.n_rollouts, r = job - b * a.n_rollouts;
+    const double* src = a.params + size_t(b) * a.params_problem_stride + size_t(r) * a.params_rollout_stride;
+    __syncthreads();   // previous rollout fully consumed (and the tables are in place on the first pass)
+    for (int i = threadIdx.x; i < D * N; i += blockDim.x) q[i] = src[i];
+    if (threadIdx.x == 0) s_collision = 0;
+    __syncthreads();
 
-    for (int n = 0; n < a.num_nodes; ++n) {
-      const DevNode<Real>& nd = nodes[n];
-      Real Pm[12];
-      {
-        Real qv = Real(0);
-        if (nd.q_index >= 0) qv = Real(t < 0 ? ps[nd.q_index] : (t >= N ? pg[nd.q_index] : q[size_t(nd.q_index) * N + t]));
-        if (nd.type == STOMP_JOINT_REVOLUTE) {
-          Real s, c;
-          Math<Real>::sincos_(qv, &s, &c);
-#pragma unroll
-          for (int i = 0; i < 9; ++i) Pm[i] = nd.A0[i] + c * nd.A1[i] + s * nd.A2[i];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) Pm[9 + i] = nd.p[i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < 9; ++i) Pm[i] = nd.A0[i];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) Pm[9 + i] = nd.p[i] + qv * nd.ax[i];
-        }
-      }
-      if (nd.parent < 0) {
-#pragma unroll
-        for (int i = 0; i < 12; ++i) F[i] = Pm[i];
-      } else {
-        Real Pf[12];
-        if (nd.load_slot >= 0) {
-#pragma unroll
-          for (int i = 0; i < 12; ++i) Pf[i] = saved[nd.load_slot][i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < 12; ++i) Pf[i] = F[i];
+    // ---- handleJointLimits: warp per joint, <= 11 passes of (arg max violation, rank-1 correction) ----------
+    for (int d = warp; d < D; d += nwarps) {
+      if (!a.has_limits[d]) continue;
+      const double jmax = a.limit_max[d], jmin = a.limit_min[d];
+      double* qd = q + size_t(d) * N;
+      for (int count = 0; count < 11; ++count) {
+        double best_abs = 1e-6, best_amount = 0.0;
+        int best_idx = -1;
+        for (int i = lane; i < N; i += 32) {
+          double v = qd[i], amount = 0.0;
+          if (v > jmax) amount = jmax - v;
+          else if (v < jmin) amount = jmin - v;
+          double aa = fabs(amount);
+          if (aa > best_abs) { best_abs = aa; best_amount = amount; best_idx = i; }
         }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-#pragma unroll
-          for (int j = 0; j < 3; ++j) F[i * 3 + j] = Pf[i * 3] * Pm[j] + Pf[i * 3 + 1] * Pm[3 + j] + Pf[i * 3 + 2] * Pm[6 + j];
-          F[9 + i] = Pf[i * 3] * Pm[9] + Pf[i * 3 + 1] * Pm[10] + Pf[i * 3 + 2] * Pm[11] + Pf[9 + i];
+        for (int off = 16; off > 0; off >>= 1) {
+          double oa = __shfl_xor_sync(0xffffffffu, best_abs, off);
+          double om = __shfl_xor_sync(0xffffffffu, best_amount, off);
+          int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
+          // strict '>' in index order keeps the first maximum: larger violation wins, ties -> smaller index
+          bool take = (oi >= 0) && (best_idx < 0 || oa > best_abs || (oa == best_abs && oi < best_idx));
+          if (take) { best_abs = oa; best_amount = om; best_idx = oi; }
         }
-      }
-      if (nd.save_slot >= 0) {
-#pragma unroll
-        for (int i = 0; i < 12; ++i) saved[nd.save_slot][i] = F[i];
-      }
-      if (nd.sphere_end > nd.sphere_begin) {
-        // velocity frame V = sum_k rule_k/dt * F(t+k), vel(sphere) = V.R * p + V.p (linear in the frame); built
-        // lazily, only when some lane of the warp has a sphere of this link inside its clearance band
-        Real V[12];
-        bool haveV = false;
-        for (int j = nd.sphere_begin; j < nd.sphere_end; ++j) {
-          const DevSphere<Real>& sp = spheres[j];
-          const Real s0 = sp.pos[0], s1 = sp.pos[1], s2 = sp.pos[2];
-          Real px = F[0] * s0 + F[1] * s1 + F[2] * s2 + F[9];
-          Real py = F[3] * s0 + F[4] * s1 + F[5] * s2 + F[10];
-          Real pz = F[6] * s0 + F[7] * s1 + F[8] * s2 + F[11];
-          int cx = voxel_cell(px, ox, res, inv_res);
-          int cy = voxel_cell(py, oy, res, inv_res);
-          int cz = voxel_cell(pz, oz, res, inv_res);
-          Real dist = Real(0);
-          if (cx >= 1 && cy >= 1 && cz >= 1 && cx < nx1 && cy < ny1 && cz < nz1) {
-            int idx = (cx * sny + cy) * snz + cz;
-            if (vdtype == STOMP_VOXEL_U8_SQ) dist = sqrt_tab[__ldg(static_cast<const uint8_t*>(vox) + idx)];
-            else if (vdtype == STOMP_VOXEL_U16_SQ)
-              dist = Math<Real>::sqrt_(Real(__ldg(static_cast<const uint16_t*>(vox) + idx))) * res;
-            else dist = Real(__ldg(static_cast<const float*>(vox) + idx));
-          }
-          const Real radius = sp.radius, clearance = sp.clearance;
-          Real dd = dist - radius, pot;
-          if (dd >= clearance) pot = Real(0);
-          else if (dd >= Real(0)) { Real diff = dd - clearance; pot = Real(0.5) * (diff * sp.inv_clearance) * diff; }
-          else pot = -dd + Real(0.5) * clearance;
-          bool hit = dist <= radius;
-          if (hit && counts) collided = 1;
-          Real vm = Real(0);
-          if (__any_sync(0xffffffffu, kDebug || pot != Real(0))) {
-            if (!haveV) {
-#pragma unroll
-              for (int i = 0; i < 12; ++i)
-                V[i] = c_m1 * shfl_rel(F[i], -1) + c_0 * F[i] + c_p1 * shfl_rel(F[i], 1) + c_p2 * shfl_rel(F[i], 2);
-              haveV = true;
-            }
-            Real vx = V[0] * s0 + V[1] * s1 + V[2] * s2 + V[9];
-            Real vy = V[3] * s0 + V[4] * s1 + V[5] * s2 + V[10];
-            Real vz = V[6] * s0 + V[7] * s1 + V[8] * s2 + V[11];
-            vm = Math<Real>::sqrt_(vx * vx + vy * vy + vz * vz);
-            cost += sp.weight * (pot * vm);
-          }
-          if (kDebug) {
-            if (t >= -1 && t <= N + 1 && (lane >= 1 && lane <= kTileSteps || (tile == 0 && lane == 0) ||
-                                           (tile == ntiles - 1 && lane > kTileSteps))) {
-              stomp_sphere_debug& rec = a.debug[size_t(t + 1) * K + sp.original_index];
-              rec.voxel[0] = cx; rec.voxel[1] = cy; rec.voxel[2] = cz;
-              rec.in_collision = hit;
-              rec.position[0] = px; rec.position[1] = py; rec.position[2] = pz;
-              rec.potential = pot;
-              rec.vel_mag = (t >= 0 && t < N && lane >= 1 && lane <= kTileSteps) ? double(vm) : 0.0;
-            }
-          }
-        }
+        if (best_idx < 0) break;
+        const double* col = a.qinv_t + size_t(best_idx) * N;
+        double multiplier = best_amount / col[best_idx];
+        for (int i = lane; i < N; i += 32) qd[i] += multiplier * col[i];
+        __syncwarp();
       }
     }
-    if (productive) out[t] = a.obstacle_weight * double(cost);
+    __syncthreads();
+    if (a.clipped) {
+      double* dst = a.clipped + size_t(b) * a.params_problem_stride + size_t(r) * a.params_rollout_stride;
+      for (int i = threadIdx.x; i < D * N; i += blockDim.x) dst[i] = q[i];
+    }
+
+    // ---- FK + spheres + SDF + velocity + cost -------------------------------------------------------
+    const double* ps = a.pad_start + size_t(b) * D;
+    const double* pg = a.pad_goal + size_t(b) * D;
+    double* out = a.costs + size_t(b) * a.cost_problem_stride + size_t(r) * N;
+    int collided = 0;
+
+    for (int tile = warp; tile < ntiles; tile += nwarps) {
+      const int t = tile * kTileSteps - 1 + lane;      // trajectory point of this lane (-1 .. N+1 are meaningful)
+      const bool productive = lane >= 1 && lane <= kTileSteps && t < N;
+      const bool counts = productive || (a.include_pads && (t == -1 || t == N));
+      Real cost = Real(0);
+      Real F[12], saved[kMaxSlots][12];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) F[i] = Real(0);
+
+      for (int n = 0; n < a.num_nodes; ++n) {
+        const DevNode<Real>& nd = nodes[n];
+        Real Pm[12];
+        {
+          Real qv = Real(0);
+          if (nd.q_index >= 0) qv = Real(t < 0 ? ps[nd.q_index] : (t >= N ? pg[nd.q_index] : q[size_t(nd.q_index) * N + t]));
+          if (nd.type == STOMP_JOINT_REVOLUTE) {
+            Real sn, cs;
+            Math<Real>::sincos_(qv, &sn, &cs);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Pm[i] = nd.A0[i] + cs * nd.A1[i] + sn * nd.A2[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) Pm[9 + i] = nd.p[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Pm[i] = nd.A0[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) Pm[9 + i] = nd.p[i] + qv * nd.ax[i];
+          }
+        }
+        if (nd.parent < 0) {
+#pragma unroll
+          for (int i = 0; i < 12; ++i) F[i] = Pm[i];
+        } else {
+          Real Pf[12];
+          if (nd.load_slot >= 0) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) Pf[i] = saved[nd.load_slot][i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) Pf[i] = F[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) F[i * 3 + j] = Pf[i * 3] * Pm[j] + Pf[i * 3 + 1] * Pm[3 + j] + Pf[i * 3 + 2] * Pm[6 + j];
+            F[9 + i] = Pf[i * 3] * Pm[9] + Pf[i * 3 + 1] * Pm[10] + Pf[i * 3 + 2] * Pm[11] + Pf[9 + i];
+          }
+        }
+        if (nd.save_slot >= 0) {
+#pragma unroll
+          for (int i = 0; i < 12; ++i) saved[nd.save_slot][i] = F[i];
+        }
+        const int sph_begin = nd.sphere_begin, sph_end = nd.sphere_end;
+        if (sph_end > sph_begin) {
+          // velocity frame V = sum_k rule_k/dt * F(t+k), vel(sphere) = V.R * p + V.p (linear in the frame); built
+          // lazily, only when some lane of the warp has a sphere of this link inside its clearance band
+          bool haveV = false;
+          for (int j0 = sph_begin; j0 < sph_end; j0 += kSphereBatch) {
+            // 1. positions, voxel indices and the gathers of up to kSphereBatch spheres (loads stay in flight)
+            unsigned raw[kSphereBatch];
+            bool inside[kSphereBatch];
+            int cell[kSphereBatch][3];
+            Real pos[kSphereBatch][3];
+#pragma unroll
+            for (int u = 0; u < kSphereBatch; ++u) {
+              raw[u] = 0u;
+              inside[u] = false;
+              if (j0 + u < sph_end) {
+                const DevSphere<Real>& sp = spheres[j0 + u];
+                const Real s0 = sp.pos[0], s1 = sp.pos[1], s2 = sp.pos[2];
+                const Real px = F[0] * s0 + F[1] * s1 + F[2] * s2 + F[9];
+                const Real py = F[3] * s0 + F[4] * s1 + F[5] * s2 + F[10];
+                const Real pz = F[6] * s0 + F[7] * s1 + F[8] * s2 + F[11];
+                const int cx = voxel_cell(px, ox, res, inv_res);
+                const int cy = voxel_cell(py, oy, res, inv_res);
+                const int cz = voxel_cell(pz, oz, res, inv_res);
+                inside[u] = cx >= 1 && cy >= 1 && cz >= 1 && cx < nx1 && cy < ny1 && cz < nz1;
+                if (inside[u]) {
+                  const int idx = (cx * sny + cy) * snz + cz;
+                  if (vdtype == STOMP_VOXEL_U8_SQ) raw[u] = __ldg(static_cast<const uint8_t*>(vox) + idx);
+                  else if (vdtype == STOMP_VOXEL_U16_SQ) raw[u] = __ldg(static_cast<const uint16_t*>(vox) + idx);
+                  else raw[u] = __float_as_uint(__ldg(static_cast<const float*>(vox) + idx));
+                }
+                if (kDebug) { cell[u][0] = cx; cell[u][1] = cy; cell[u][2] = cz; pos[u][0] = px; pos[u][1] = py; pos[u][2] = pz; }
+              }
+            }
+            // 2. distance -> three-piece potential -> (lazy) velocity -> cost
+#pragma unroll
+            for (int u = 0; u < kSphereBatch; ++u) {
+              if (j0 + u < sph_end) {
+                const DevSphere<Real>& sp = spheres[j0 + u];
+                Real dist = Real(0);
+                if (inside[u]) {
+                  if (vdtype == STOMP_VOXEL_U8_SQ) dist = sqrt_tab[raw[u]];
+                  else if (vdtype == STOMP_VOXEL_U16_SQ) dist = Math<Real>::sqrt_(Real(raw[u])) * res;
+                  else dist = Real(__uint_as_float(raw[u]));
+                }
+                const Real radius = sp.radius, clearance = sp.clearance;
+                const Real dd = dist - radius;
+                Real pot;
+                if (dd >= clearance) pot = Real(0);
+                else if (dd >= Real(0)) { const Real diff = dd - clearance; pot = Real(0.5) * (diff * sp.inv_clearance) * diff; }
+                else pot = -dd + Real(0.5) * clearance;
+                const bool hit = dist <= radius;
+                if (hit && counts) collided = 1;
+                Real vm = Real(0);
+                if (__any_sync(0xffffffffu, kDebug || pot != Real(0))) {
+                  if (!haveV) {
+#pragma unroll
+                    for (int i = 0; i < 12; ++i)
+                      Vs[i * 32] = c_m1 * shfl_rel(F[i], -1) + c_0 * F[i] + c_p1 * shfl_rel(F[i], 1) + c_p2 * shfl_rel(F[i], 2);
+                    haveV = true;
+                  }
+                  const Real s0 = sp.pos[0], s1 = sp.pos[1], s2 = sp.pos[2];
+                  const Real vx = Vs[0 * 32] * s0 + Vs[1 * 32] * s1 + Vs[2 * 32] * s2 + Vs[9 * 32];
+                  const Real vy = Vs[3 * 32] * s0 + Vs[4 * 32] * s1 + Vs[5 * 32] * s2 + Vs[10 * 32];
+                  const Real vz = Vs[6 * 32] * s0 + Vs[7 * 32] * s1 + Vs[8 * 32] * s2 + Vs[11 * 32];
+                  vm = Math<Real>::sqrt_(vx * vx + vy * vy + vz * vz);
+                  cost += sp.weight * (pot * vm);
+                }
+                if (kDebug) {
+                  if (t >= -1 && t <= N + 1 && (lane >= 1 && lane <= kTileSteps || (tile == 0 && lane == 0) ||
+                                                 (tile == ntiles - 1 && lane > kTileSteps))) {
+                    stomp_sphere_debug& rec = a.debug[size_t(t + 1) * K + sp.original_index];
+                    rec.voxel[0] = cell[u][0]; rec.voxel[1] = cell[u][1]; rec.voxel[2] = cell[u][2];
+                    rec.in_collision = hit;
+                    rec.position[0] = pos[u][0]; rec.position[1] = pos[u][1]; rec.position[2] = pos[u][2];
+                    rec.potential = pot;
+                    rec.vel_mag = (t >= 0 && t < N && lane >= 1 && lane <= kTileSteps) ? double(vm) : 0.0;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      if (productive) out[t] = a.obstacle_weight * double(cost);
+    }
+    if (collided) s_collision = 1;
+    __syncthreads();
+    if (threadIdx.x == 0 && a.collision_free)
+      a.collision_free[size_t(b) * a.flag_problem_stride + a.flag_offset + r] = s_collision ? 0 : 1;
   }
-  if (collided) s_collision = 1;
-  __syncthreads();
-  if (threadIdx.x == 0 && a.collision_free)
-    a.collision_free[size_t(b) * a.flag_problem_stride + a.flag_offset + r] = s_collision ? 0 : 1;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -14,7 +14,7 @@ import numpy as np
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstomp_b200.so")
+LIB_PATH = os.environ.get("STOMP_B200_LIB", os.path.join(_HERE, "libstomp_b200.so"))  # env override: A/B builds
 _lib = None
 
 EXPORTS = [
