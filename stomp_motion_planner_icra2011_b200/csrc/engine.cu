@@ -233,7 +233,7 @@ int launch_cost_t(Engine& e, CostArgs<Real>& a, int num_problems) {
   const int ntiles = (e.N + kTileSteps - 1) / kTileSteps;
   int warps = std::min(ntiles, 4);
   warps = std::max(warps, std::min(e.D, 4));  // joint-limit pass likes a few warps
-  size_t smem = size_t(e.D) * e.N * 8 + size_t(e.num_nodes) * sizeof(DevNode<Real>) + size_t(e.K) * sizeof(DevSphere<Real>) +
+  size_t smem = ((size_t(e.D) * e.N * 8 + 15) & ~size_t(15)) + size_t(e.num_nodes) * sizeof(DevNode<Real>) + size_t(e.K) * sizeof(DevSphere<Real>) +
                 256 * sizeof(Real) + size_t(warps) * 12 * 32 * sizeof(Real);
   auto kern = k_cost<Real, kDebug>;
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -302,9 +302,16 @@ int launch_cumulative(Engine& e) {
 
 size_t band_smem(const Engine& e, int rows) { return (size_t(e.N) * 16 + size_t(rows) * (e.N | 1)) * 8; }
 
-int launch_update(Engine& e, int apply) {
+int launch_update(Engine& e, int apply, bool fuse_extra_control) {
   UpdateArgs a;
+  std::memset(&a, 0, sizeof(a));
   a.R = e.R; a.D = e.D; a.N = e.N; a.apply = apply;
+  if (fuse_extra_control) {
+    a.extra_control = e.extra_control.p;
+    a.pad_start = e.pad_start.p; a.pad_goal = e.pad_goal.p;
+    a.control_weight = 0.5 * e.control_cost_weight;
+    a.st = e.stencil();
+  }
   a.cumulative = e.cumulative.p; a.noise = e.noise.p; a.probabilities = e.probabilities.p;
   a.updates = e.updates.p; a.theta = e.theta.p; a.band = e.band_view();
   // enough CTAs to fill the machine twice when the batch allows it; otherwise one dimension per CTA
@@ -420,20 +427,22 @@ int step_improve(Engine& e, int apply) {
     if (launch_minmax(e) || launch_sums(e)) return 1;
     return launch_finalize(e, apply);
   }
-  return launch_update(e, apply);
+  return launch_update(e, apply, false);
 }
 
-int step_extra(Engine& e, bool run_cost, int iteration_number) {
+int step_extra(Engine& e, bool run_cost, int iteration_number, bool have_control = false) {
   if (run_cost) {
     if (launch_cost(e, e.theta.p, size_t(e.D) * e.N, 1, e.B, iteration_number == 1, e.extra_state.p, size_t(e.N),
                     e.collision_free.p, e.R + 1, e.R, nullptr, nullptr))
       return 1;
   }
-  GenArgs a = base_gen_args(e);
-  a.extra = 1; a.mode_generate = 0; a.mode_project = 0; a.mode_control = 1;
-  a.control = e.extra_control.p;
-  a.control_weight = 0.5 * e.control_cost_weight;
-  if (launch_generate(e, a)) return 1;
+  if (!have_control) {
+    GenArgs a = base_gen_args(e);
+    a.extra = 1; a.mode_generate = 0; a.mode_project = 0; a.mode_control = 1;
+    a.control = e.extra_control.p;
+    a.control_weight = 0.5 * e.control_cost_weight;
+    if (launch_generate(e, a)) return 1;
+  }
   begin_launch(e);
   k_extra_total<<<e.B, 128, 0, e.stream>>>(e.R, e.D, e.N, e.extra_state.p, e.extra_control.p, e.totals.p, e.noiseless_sum.p);
   if (check_launch(e, "k_extra_total")) return 1;
@@ -461,8 +470,9 @@ int iterate_once(Engine& e, int iteration_number) {
     if (e.desc.rollout_shard_world > 1)
       return fail("rollout-sharded engines iterate through stomp_engine_iterate_sharded_phase");
     if (launch_minmax(e) || launch_sums(e) || launch_finalize(e, 1)) return 1;
-  } else if (launch_update(e, 1)) {
-    return 1;
+  } else {
+    if (launch_update(e, 1, true)) return 1;
+    return step_extra(e, true, iteration_number, true);
   }
   return step_extra(e, true, iteration_number);
 }

@@ -21,6 +21,14 @@
 
 #include "../../include/stomp_b200.h"
 
+// build-time tuning knobs of k_cost (A/B tested on B200, see profiles/)
+#ifndef STOMP_KCOST_MIN_BLOCKS
+#define STOMP_KCOST_MIN_BLOCKS 7   // resident CTAs per SM the register allocation targets
+#endif
+#ifndef STOMP_SPHERE_BATCH
+#define STOMP_SPHERE_BATCH 1       // SDF gathers kept in flight per lane
+#endif
+
 namespace stomp_dev {
 
 constexpr int kPad = STOMP_DIFF_RULE_LENGTH - 1;  // 6 fixed points each side
@@ -32,13 +40,13 @@ constexpr int kTileSteps = 29;                    // productive timesteps per wa
 // device tables
 // ---------------------------------------------------------------------------------------------
 template <typename Real>
-struct DevNode {
+struct alignas(16) DevNode {
   Real A0[9], A1[9], A2[9], p[3], ax[3];
   int parent, type, q_index, save_slot, load_slot, sphere_begin, sphere_end, pad_;
 };
 
 template <typename Real>
-struct DevSphere {
+struct alignas(16) DevSphere {
   Real pos[3], radius, clearance, inv_clearance, weight;
   int original_index;
 };
@@ -563,43 +571,43 @@ __device__ __forceinline__ float shfl_rel(float v, int delta) {
   return delta < 0 ? __shfl_up_sync(0xffffffffu, v, unsigned(-delta)) : __shfl_down_sync(0xffffffffu, v, unsigned(delta));
 }
 
-// distance_field VoxelGrid::getCellFromLocation: int(round((loc - origin) / resolution)).
-// Fast path: multiply by 1/res and round to nearest with the 2^52+2^51 trick (the integer is the low word of
-// the sum, no F2I/I2F conversions); whenever the product is within 1e-6 of a rounding boundary the exact
-// division + round-half-away form decides, so the index is identical to the division form for every input.
-// Coordinates too large for a 32-bit cell index return -1 (outside the grid).
-__device__ __forceinline__ int voxel_cell(double pos, double origin, double res, double inv_res) {
-#if STOMP_MAGIC_ROUND
-  const double magic = 6755399441055744.0;
-  const double t = (pos - origin) * inv_res;
-  const double m = t + magic;
-  int r = __double2loint(m);
-  if (fabs(t - (m - magic)) > 0.5 - 1e-6 || !(fabs(t) < 1.0e9))
-    r = fabs(t) < 1.0e9 ? int(round((pos - origin) / res)) : -1;
-  return r;
-#else
-  double t = (pos - origin) * inv_res;
-  int r = __double2int_rn(t);
-  if (fabs(t - double(r)) > 0.5 - 1e-6) r = int(round((pos - origin) / res));
-  return r;
-#endif
+// distance_field VoxelGrid::getCellFromLocation: int(round((loc - origin) / resolution)), and the 1-cell margin
+// test of getDistanceGradient.  Fast path (fp64): t = pos/res - origin/res as one DFMA, then t + 1.5*2^36 puts
+// t as Q16.16 fixed point into the low mantissa word: cell = (lo + 0x8000) >> 16 and the distance to the
+// rounding boundary are integer-pipe work, and the high word tells whether 0 <= t < 65536.  Whenever t is
+// within 2^-15 cell of a rounding boundary (or out of that range) the exact division + round-half-away form
+// decides, so the index is identical to the reference form for every input.
+// Returns true when the cell is inside the grid with the 1-cell margin (1 <= cell <= n-2).
+__device__ __forceinline__ bool voxel_cell(double pos, double origin, double res, double inv_res, double neg_origin_cells,
+                                           int n_minus_1, int& cell) {
+  const double magic = 103079215104.0;                    // 1.5 * 2^36
+  const double m = fma(pos, inv_res, neg_origin_cells) + magic;
+  const unsigned lo = unsigned(__double2loint(m));
+  const unsigned f = lo + 0x8000u;
+  cell = int(f >> 16);
+  const unsigned frac = f & 0xffffu;
+  if (__double2hiint(m) != 0x42380000 || frac < 2u || frac > 0xfffdu || f < lo) {
+    const double tq = (pos - origin) / res;               // exact reference form (rare)
+    cell = fabs(tq) < 2.0e9 ? int(round(tq)) : -1;
+  }
+  return unsigned(cell - 1) < unsigned(n_minus_1 - 1);
 }
-__device__ __forceinline__ int voxel_cell(float pos, float origin, float res, float inv_res) {
-  float t = (pos - origin) * inv_res;
-  int r = __float2int_rn(t);
-  if (fabsf(t - float(r)) > 0.5f - 1e-3f || !(fabsf(t) < 1.0e9f)) r = fabsf(t) < 1.0e9f ? int(roundf((pos - origin) / res)) : -1;
-  return r;
+__device__ __forceinline__ bool voxel_cell(float pos, float origin, float res, float inv_res, float neg_origin_cells,
+                                           int n_minus_1, int& cell) {
+  (void)neg_origin_cells;
+  const float t = (pos - origin) * inv_res;
+  cell = __float2int_rn(t);
+  if (fabsf(t - float(cell)) > 0.5f - 1e-3f || !(fabsf(t) < 1.0e9f)) cell = fabsf(t) < 1.0e9f ? int(roundf((pos - origin) / res)) : -1;
+  return unsigned(cell - 1) < unsigned(n_minus_1 - 1);
 }
 
-#ifndef STOMP_KCOST_MIN_BLOCKS
-#define STOMP_KCOST_MIN_BLOCKS 7
-#endif
-#ifndef STOMP_SPHERE_BATCH
-#define STOMP_SPHERE_BATCH 1
-#endif
-#ifndef STOMP_MAGIC_ROUND
-#define STOMP_MAGIC_ROUND 1
-#endif
+__device__ __forceinline__ void cta_copy_async16(void* dst_smem, const void* src, int bytes) {
+  for (int off = threadIdx.x * 16; off < bytes; off += blockDim.x * 16) {
+    const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(static_cast<char*>(dst_smem) + off));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(static_cast<const char*>(src) + off) : "memory");
+  }
+}
+
 constexpr int kSphereBatch = STOMP_SPHERE_BATCH;   // SDF gathers kept in flight per lane
 
 // Persistent CTAs: the grid is sized to the machine (SMs x resident CTAs) and every CTA walks rollouts with a
@@ -609,25 +617,21 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = a.D, N = a.N, K = a.K;
   double* q = reinterpret_cast<double*>(smem_raw);                        // [D][N] clipped trajectory
-  DevNode<Real>* nodes = reinterpret_cast<DevNode<Real>*>(q + size_t(D) * N);
+  DevNode<Real>* nodes = reinterpret_cast<DevNode<Real>*>(smem_raw + ((size_t(D) * N * 8 + 15) & ~size_t(15)));
   DevSphere<Real>* spheres = reinterpret_cast<DevSphere<Real>*>(nodes + a.num_nodes);
   Real* sqrt_tab = reinterpret_cast<Real*>(spheres + K);                  // [256]
-  __shared__ int s_collision;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   // per-warp velocity frame [12][32]: kept in shared memory so that the register file holds only one frame
   Real* Vs = sqrt_tab + 256 + size_t(warp) * 12 * 32 + lane;
-  {
-    const int* s32 = reinterpret_cast<const int*>(a.nodes);
-    int* d32 = reinterpret_cast<int*>(nodes);
-    for (int i = threadIdx.x; i < int(sizeof(DevNode<Real>) / 4) * a.num_nodes; i += blockDim.x) d32[i] = s32[i];
-    s32 = reinterpret_cast<const int*>(a.spheres);
-    d32 = reinterpret_cast<int*>(spheres);
-    for (int i = threadIdx.x; i < int(sizeof(DevSphere<Real>) / 4) * K; i += blockDim.x) d32[i] = s32[i];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) sqrt_tab[i] = a.sqrt_table[i];
-  }
+  // robot tables: asynchronous 16-byte copies, all in flight together (waited for with the first trajectory)
+  cta_copy_async16(nodes, a.nodes, int(sizeof(DevNode<Real>)) * a.num_nodes);
+  cta_copy_async16(spheres, a.spheres, int(sizeof(DevSphere<Real>)) * K);
+  cta_copy_async16(sqrt_tab, a.sqrt_table, 256 * int(sizeof(Real)));
   const Real ox = Real(a.sdf.origin[0]), oy = Real(a.sdf.origin[1]), oz = Real(a.sdf.origin[2]);
   const Real res = Real(a.sdf.res), inv_res = Real(a.sdf.inv_res);
+  const Real nox = Real(-a.sdf.origin[0] * a.sdf.inv_res), noy = Real(-a.sdf.origin[1] * a.sdf.inv_res),
+             noz = Real(-a.sdf.origin[2] * a.sdf.inv_res);
   const Real c_m1 = Real(a.inv_time * (-2.0 / 6.0)), c_0 = Real(a.inv_time * (-3.0 / 6.0)), c_p1 = Real(a.inv_time * (6.0 / 6.0)),
              c_p2 = Real(a.inv_time * (-1.0 / 6.0));
   const int ntiles = (N + kTileSteps - 1) / kTileSteps;
@@ -637,9 +641,15 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
   for (int job = blockIdx.x; job < a.total_rollouts; job += gridDim.x) {
     const int b = job / a.n_rollouts, r = job - b * a.n_rollouts;
     const double* src = a.params + size_t(b) * a.params_problem_stride + size_t(r) * a.params_rollout_stride;
-    __syncthreads();   // previous rollout fully consumed (and the tables are in place on the first pass)
-    for (int i = threadIdx.x; i < D * N; i += blockDim.x) q[i] = src[i];
-    if (threadIdx.x == 0) s_collision = 0;
+    __syncthreads();   // previous rollout fully consumed
+    for (int i = threadIdx.x; i < D * N; i += blockDim.x) {
+      const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(q + i));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(src + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    int* flag = a.collision_free ? a.collision_free + size_t(b) * a.flag_problem_stride + a.flag_offset + r : nullptr;
+    if (threadIdx.x == 0 && flag) *flag = 1;   // ordered before the warps' "= 0" stores by the barriers below
     __syncthreads();
 
     // ---- handleJointLimits: warp per joint, <= 11 passes of (arg max violation, rank-1 correction) ----------
@@ -758,10 +768,11 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
                 const Real px = F[0] * s0 + F[1] * s1 + F[2] * s2 + F[9];
                 const Real py = F[3] * s0 + F[4] * s1 + F[5] * s2 + F[10];
                 const Real pz = F[6] * s0 + F[7] * s1 + F[8] * s2 + F[11];
-                const int cx = voxel_cell(px, ox, res, inv_res);
-                const int cy = voxel_cell(py, oy, res, inv_res);
-                const int cz = voxel_cell(pz, oz, res, inv_res);
-                inside[u] = cx >= 1 && cy >= 1 && cz >= 1 && cx < nx1 && cy < ny1 && cz < nz1;
+                int cx, cy, cz;
+                const bool inx = voxel_cell(px, ox, res, inv_res, nox, nx1, cx);
+                const bool iny = voxel_cell(py, oy, res, inv_res, noy, ny1, cy);
+                const bool inz = voxel_cell(pz, oz, res, inv_res, noz, nz1, cz);
+                inside[u] = inx && iny && inz;
                 if (inside[u]) {
                   const int idx = (cx * sny + cy) * snz + cz;
                   if (vdtype == STOMP_VOXEL_U8_SQ) raw[u] = __ldg(static_cast<const uint8_t*>(vox) + idx);
@@ -823,10 +834,7 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
       }
       if (productive) out[t] = a.obstacle_weight * double(cost);
     }
-    if (collided) s_collision = 1;
-    __syncthreads();
-    if (threadIdx.x == 0 && a.collision_free)
-      a.collision_free[size_t(b) * a.flag_problem_stride + a.flag_offset + r] = s_collision ? 0 : 1;
+    if (collided && flag) *flag = 0;
   }
 }
 
@@ -932,6 +940,12 @@ struct UpdateArgs {
   double* updates;           // [B][D][N]
   double* theta;             // [B][D][N]
   Band band;
+  // optional fusion of addExtraRollouts' control cost: control cost of the UPDATED theta with zero noise
+  double* extra_control;     // [B][D][N] or nullptr
+  const double* pad_start;   // [B][D]
+  const double* pad_goal;    // [B][D]
+  double control_weight;     // 0.5 * control_cost_weight
+  Stencil st;
 };
 
 // CTA per (problem, group of dimensions).  Phase 1 (all threads, thread per timestep): min / max over
@@ -986,7 +1000,44 @@ __global__ void k_update(UpdateArgs a) {
     const int dl = k / N, t = k - dl * N;
     double v = u[dl * stride + t];
     a.updates[off + k] = v;
-    if (a.apply) a.theta[off + k] += v;
+    if (a.apply) {
+      const double th = a.theta[off + k] + v;
+      a.theta[off + k] = th;
+      u[dl * stride + t] = th;   // keep the updated trajectory for the control-cost stencil below
+    }
+  }
+  if (!(a.apply && a.extra_control)) return;
+  __syncthreads();
+  // control cost of the noise-less (updated) trajectory: fully parallel 7-tap stencils over [pads, theta, pads]
+  // (covariant_trajectory_policy.cpp:228-255 with zero noise; what addExtraRollouts computes for the extra rollout)
+  const int Nall = N + 2 * kPad;
+  for (int k = threadIdx.x; k < nd * N; k += blockDim.x) {
+    const int dl = k / N, t = k - dl * N, d = d0 + dl;
+    const double xs = a.pad_start[size_t(b) * D + d], xg = a.pad_goal[size_t(b) * D + d];
+    const double* row = u + dl * stride;
+    auto cost_at = [&](int p) -> double {
+      double cost = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 3; ++kk) {
+        if (a.st.weight[kk] == 0.0) continue;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          const int idx = p + j - 3;
+          if (idx < 0 || idx >= Nall) continue;
+          const double xv = idx < kPad ? xs : (idx >= kPad + N ? xg : row[idx - kPad]);
+          acc += a.st.coef[kk][j] * xv;
+        }
+        cost += a.control_weight * a.st.weight[kk] * (acc * acc);
+      }
+      return cost;
+    };
+    double c = cost_at(t + kPad);
+    if (t == 0)
+      for (int i = 0; i < kPad; ++i) c += cost_at(i);
+    if (t == N - 1)
+      for (int i = 0; i < kPad; ++i) c += cost_at(Nall - 1 - i);
+    a.extra_control[off + k] = c;
   }
 }
 
