@@ -198,7 +198,7 @@ int launch_generate(Engine& e, GenArgs a) {
   if (e.gen_scratch.n < stride * N) CUDA_TRY(e.gen_scratch.alloc(stride * N));
   a.scratch = e.gen_scratch.p;
   a.scratch_stride = stride;
-  const size_t smem = (size_t(N) * 17 + size_t(tpb / 32) * 2 * 32 * kTileLd) * 8;
+  const size_t smem = ((STOMP_GEN_LDG_BAND ? 0 : size_t(N) * 17) + size_t(tpb / 32) * 2 * 32 * kTileLd) * 8;
   if (smem > 220 * 1024) return fail("num_time_steps too large for the band tables of k_generate");
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   begin_launch(e);

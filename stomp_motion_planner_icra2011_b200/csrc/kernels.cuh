@@ -25,6 +25,12 @@
 #ifndef STOMP_KCOST_MIN_BLOCKS
 #define STOMP_KCOST_MIN_BLOCKS 7   // resident CTAs per SM the register allocation targets
 #endif
+#ifndef STOMP_GEN_MIN_BLOCKS
+#define STOMP_GEN_MIN_BLOCKS 4     // k_generate: resident CTAs per SM targeted by the register allocation
+#endif
+#ifndef STOMP_GEN_LDG_BAND
+#define STOMP_GEN_LDG_BAND 0       // k_generate: 1 = read the band tables through L1 instead of shared memory
+#endif
 #ifndef STOMP_SPHERE_BATCH
 #define STOMP_SPHERE_BATCH 1       // SDF gathers kept in flight per lane
 #endif
@@ -280,10 +286,17 @@ struct BandWindow {
   }
 };
 
-__global__ void __launch_bounds__(128) k_generate(GenArgs a) {
+__global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs a) {
   extern __shared__ double smem[];
   const int N = a.N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#if STOMP_GEN_LDG_BAND
+  const double* sfw = a.band.fw;             // [N][8]  warp-uniform addresses: one L1 transaction per row
+  const double* sbw = a.band.bw;
+  const double* sscale = a.band.proj_scale;
+  double* tE = smem + size_t(warp) * 2 * 32 * kTileLd;   // per-warp tiles
+  double* tT = tE + 32 * kTileLd;
+#else
   double* sfw = smem;                        // [N][8]
   double* sbw = sfw + N * 8;                 // [N][8]
   double* sscale = sbw + N * 8;              // [N]
@@ -292,6 +305,7 @@ __global__ void __launch_bounds__(128) k_generate(GenArgs a) {
   for (int k = threadIdx.x; k < N * 8; k += blockDim.x) sfw[k] = a.band.fw[k], sbw[k] = a.band.bw[k];
   for (int i = threadIdx.x; i < N; i += blockDim.x) sscale[i] = a.band.proj_scale[i];
   __syncthreads();
+#endif
 
   const int per_problem = (a.extra ? 1 : a.R) * a.D;
   const long long nvec = (long long)a.B * per_problem;
