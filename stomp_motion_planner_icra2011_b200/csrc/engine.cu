@@ -228,26 +228,38 @@ GenArgs base_gen_args(Engine& e) {
   return a;
 }
 
-template <typename Real, bool kDebug>
-int launch_cost_t(Engine& e, CostArgs<Real>& a, int num_problems) {
+template <typename Real, bool kDebug, int kVox>
+int launch_cost_v(Engine& e, CostArgs<Real>& a, int num_problems) {
   const int ntiles = (e.N + kTileSteps - 1) / kTileSteps;
   int warps = std::min(ntiles, 4);
   warps = std::max(warps, std::min(e.D, 4));  // joint-limit pass likes a few warps
   size_t smem = ((size_t(e.D) * e.N * 8 + 15) & ~size_t(15)) + size_t(e.num_nodes) * sizeof(DevNode<Real>) + size_t(e.K) * sizeof(DevSphere<Real>) +
                 256 * sizeof(Real) + size_t(warps) * 12 * 32 * sizeof(Real);
-  auto kern = k_cost<Real, kDebug>;
+  auto kern = k_cost<Real, kDebug, kVox>;
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   if (smem > 220 * 1024) return fail("trajectory + robot tables exceed shared memory");
-  begin_launch(e);
   a.total_rollouts = num_problems * a.n_rollouts;
-  int per_sm = 1;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
   // STOMP_PERSISTENT=1: one CTA per resident slot walking rollouts with a grid stride; default: one CTA per
   // rollout (the hardware block scheduler balances rollouts whose joint-limit projection takes longer)
   static const bool persistent = getenv("STOMP_PERSISTENT") && atoi(getenv("STOMP_PERSISTENT")) != 0;
-  const int grid = persistent ? std::min(a.total_rollouts, std::max(1, per_sm) * e.num_sms) : a.total_rollouts;
+  int grid = a.total_rollouts;
+  if (persistent) {
+    int per_sm = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    grid = std::min(a.total_rollouts, std::max(1, per_sm) * e.num_sms);
+  }
+  begin_launch(e);
   kern<<<grid, warps * 32, smem, e.stream>>>(a);
   return check_launch(e, "k_cost");
+}
+
+template <typename Real, bool kDebug>
+int launch_cost_t(Engine& e, CostArgs<Real>& a, int num_problems) {
+  switch (e.sdf.dtype) {
+    case STOMP_VOXEL_U8_SQ: return launch_cost_v<Real, kDebug, STOMP_VOXEL_U8_SQ>(e, a, num_problems);
+    case STOMP_VOXEL_U16_SQ: return launch_cost_v<Real, kDebug, STOMP_VOXEL_U16_SQ>(e, a, num_problems);
+    default: return launch_cost_v<Real, kDebug, STOMP_VOXEL_F32>(e, a, num_problems);
+  }
 }
 
 template <typename Real>

@@ -588,31 +588,71 @@ __device__ __forceinline__ float shfl_rel(float v, int delta) {
 // distance_field VoxelGrid::getCellFromLocation: int(round((loc - origin) / resolution)), and the 1-cell margin
 // test of getDistanceGradient.  Fast path (fp64): t = pos/res - origin/res as one DFMA, then t + 1.5*2^36 puts
 // t as Q16.16 fixed point into the low mantissa word: cell = (lo + 0x8000) >> 16 and the distance to the
-// rounding boundary are integer-pipe work, and the high word tells whether 0 <= t < 65536.  Whenever t is
-// within 2^-15 cell of a rounding boundary (or out of that range) the exact division + round-half-away form
-// decides, so the index is identical to the reference form for every input.
-// Returns true when the cell is inside the grid with the 1-cell margin (1 <= cell <= n-2).
-__device__ __forceinline__ bool voxel_cell(double pos, double origin, double res, double inv_res, double neg_origin_cells,
-                                           int n_minus_1, int& cell) {
-  const double magic = 103079215104.0;                    // 1.5 * 2^36
-  const double m = fma(pos, inv_res, neg_origin_cells) + magic;
-  const unsigned lo = unsigned(__double2loint(m));
-  const unsigned f = lo + 0x8000u;
-  cell = int(f >> 16);
-  const unsigned frac = f & 0xffffu;
-  if (__double2hiint(m) != 0x42380000 || frac < 2u || frac > 0xfffdu || f < lo) {
-    const double tq = (pos - origin) / res;               // exact reference form (rare)
-    cell = fabs(tq) < 2.0e9 ? int(round(tq)) : -1;
-  }
-  return unsigned(cell - 1) < unsigned(n_minus_1 - 1);
+// rounding boundary are integer-pipe work, and the high word tells whether 0 <= t < 65536.  Whenever any of the
+// three coordinates is within 2^-15 cell of a rounding boundary (or out of that range) the exact division +
+// round-half-away form decides (one rarely taken branch per sphere), so the indices are identical to the
+// reference form for every input.
+struct GridD {   // per-kernel constants of the lookup
+  double ox, oy, oz, res, inv_res, nox, noy, noz;   // no* = -origin/res
+  int nx1, ny1, nz1, sny, snz;
+};
+struct GridF {
+  float ox, oy, oz, res, inv_res, nox, noy, noz;
+  int nx1, ny1, nz1, sny, snz;
+};
+template <typename Real> struct GridOf;
+template <> struct GridOf<double> { typedef GridD type; };
+template <> struct GridOf<float> { typedef GridF type; };
+
+__device__ __forceinline__ int exact_cell(double pos, double origin, double res) {
+  const double tq = (pos - origin) / res;
+  return fabs(tq) < 2.0e9 ? int(round(tq)) : -1;
 }
-__device__ __forceinline__ bool voxel_cell(float pos, float origin, float res, float inv_res, float neg_origin_cells,
-                                           int n_minus_1, int& cell) {
-  (void)neg_origin_cells;
-  const float t = (pos - origin) * inv_res;
-  cell = __float2int_rn(t);
-  if (fabsf(t - float(cell)) > 0.5f - 1e-3f || !(fabsf(t) < 1.0e9f)) cell = fabsf(t) < 1.0e9f ? int(roundf((pos - origin) / res)) : -1;
-  return unsigned(cell - 1) < unsigned(n_minus_1 - 1);
+__device__ __forceinline__ int exact_cell(float pos, float origin, float res) {
+  const float tq = (pos - origin) / res;
+  return fabsf(tq) < 2.0e9f ? int(roundf(tq)) : -1;
+}
+
+// returns true when (cx,cy,cz) is inside the grid with the 1-cell margin (1 <= cell <= n-2 on every axis)
+__device__ __forceinline__ bool voxel_cells(const GridD& g, double px, double py, double pz, int& cx, int& cy, int& cz) {
+  const double magic = 103079215104.0;                    // 1.5 * 2^36
+  const double mx = fma(px, g.inv_res, g.nox) + magic;
+  const double my = fma(py, g.inv_res, g.noy) + magic;
+  const double mz = fma(pz, g.inv_res, g.noz) + magic;
+  const unsigned lx = unsigned(__double2loint(mx)), ly = unsigned(__double2loint(my)), lz = unsigned(__double2loint(mz));
+  const unsigned fx = lx + 0x8000u, fy = ly + 0x8000u, fz = lz + 0x8000u;
+  cx = int(fx >> 16); cy = int(fy >> 16); cz = int(fz >> 16);
+  // near a rounding boundary (fraction within 2 units of 0 or 65536), wrapped, or outside [0, 65536)
+  const unsigned bad = unsigned(((fx & 0xffffu) - 2u) > 0xfffbu) | unsigned(((fy & 0xffffu) - 2u) > 0xfffbu) |
+                       unsigned(((fz & 0xffffu) - 2u) > 0xfffbu) | unsigned(fx < lx) | unsigned(fy < ly) | unsigned(fz < lz) |
+                       unsigned(__double2hiint(mx) != 0x42380000) | unsigned(__double2hiint(my) != 0x42380000) |
+                       unsigned(__double2hiint(mz) != 0x42380000);
+  if (bad) {
+    cx = exact_cell(px, g.ox, g.res);
+    cy = exact_cell(py, g.oy, g.res);
+    cz = exact_cell(pz, g.oz, g.res);
+  }
+  return (unsigned(cx - 1) < unsigned(g.nx1 - 1)) & (unsigned(cy - 1) < unsigned(g.ny1 - 1)) & (unsigned(cz - 1) < unsigned(g.nz1 - 1));
+}
+__device__ __forceinline__ bool voxel_cells(const GridF& g, float px, float py, float pz, int& cx, int& cy, int& cz) {
+  const float tx = fmaf(px, g.inv_res, g.nox), ty = fmaf(py, g.inv_res, g.noy), tz = fmaf(pz, g.inv_res, g.noz);
+  cx = __float2int_rn(tx); cy = __float2int_rn(ty); cz = __float2int_rn(tz);
+  const bool bad = (fabsf(tx - float(cx)) > 0.5f - 1e-3f) | (fabsf(ty - float(cy)) > 0.5f - 1e-3f) |
+                   (fabsf(tz - float(cz)) > 0.5f - 1e-3f) | !(fabsf(tx) < 1.0e9f) | !(fabsf(ty) < 1.0e9f) | !(fabsf(tz) < 1.0e9f);
+  if (bad) {
+    cx = exact_cell(px, g.ox, g.res);
+    cy = exact_cell(py, g.oy, g.res);
+    cz = exact_cell(pz, g.oz, g.res);
+  }
+  return (unsigned(cx - 1) < unsigned(g.nx1 - 1)) & (unsigned(cy - 1) < unsigned(g.ny1 - 1)) & (unsigned(cz - 1) < unsigned(g.nz1 - 1));
+}
+
+// distance of one voxel: PropagationDistanceField::getDistance = sqrt_table[d^2] (u8 / u16 grids) or metres (f32)
+template <typename Real, int kVox>
+__device__ __forceinline__ Real voxel_distance(const void* vox, int idx, const Real* sqrt_tab, Real res) {
+  if (kVox == STOMP_VOXEL_U8_SQ) return sqrt_tab[__ldg(static_cast<const uint8_t*>(vox) + idx)];
+  if (kVox == STOMP_VOXEL_U16_SQ) return Math<Real>::sqrt_(Real(__ldg(static_cast<const uint16_t*>(vox) + idx))) * res;
+  return Real(__ldg(static_cast<const float*>(vox) + idx));
 }
 
 __device__ __forceinline__ void cta_copy_async16(void* dst_smem, const void* src, int bytes) {
@@ -622,11 +662,10 @@ __device__ __forceinline__ void cta_copy_async16(void* dst_smem, const void* src
   }
 }
 
-constexpr int kSphereBatch = STOMP_SPHERE_BATCH;   // SDF gathers kept in flight per lane
 
 // Persistent CTAs: the grid is sized to the machine (SMs x resident CTAs) and every CTA walks rollouts with a
 // grid stride, so the robot tables are staged in shared memory once per CTA instead of once per rollout.
-template <typename Real, bool kDebug>
+template <typename Real, bool kDebug, int kVox>
 __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<Real> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = a.D, N = a.N, K = a.K;
@@ -642,14 +681,15 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
   cta_copy_async16(nodes, a.nodes, int(sizeof(DevNode<Real>)) * a.num_nodes);
   cta_copy_async16(spheres, a.spheres, int(sizeof(DevSphere<Real>)) * K);
   cta_copy_async16(sqrt_tab, a.sqrt_table, 256 * int(sizeof(Real)));
-  const Real ox = Real(a.sdf.origin[0]), oy = Real(a.sdf.origin[1]), oz = Real(a.sdf.origin[2]);
-  const Real res = Real(a.sdf.res), inv_res = Real(a.sdf.inv_res);
-  const Real nox = Real(-a.sdf.origin[0] * a.sdf.inv_res), noy = Real(-a.sdf.origin[1] * a.sdf.inv_res),
-             noz = Real(-a.sdf.origin[2] * a.sdf.inv_res);
+  typename GridOf<Real>::type g;
+  g.ox = Real(a.sdf.origin[0]); g.oy = Real(a.sdf.origin[1]); g.oz = Real(a.sdf.origin[2]);
+  g.res = Real(a.sdf.res); g.inv_res = Real(a.sdf.inv_res);
+  g.nox = Real(-a.sdf.origin[0] * a.sdf.inv_res); g.noy = Real(-a.sdf.origin[1] * a.sdf.inv_res);
+  g.noz = Real(-a.sdf.origin[2] * a.sdf.inv_res);
+  g.nx1 = a.sdf.nx - 1; g.ny1 = a.sdf.ny - 1; g.nz1 = a.sdf.nz - 1; g.sny = a.sdf.ny; g.snz = a.sdf.nz;
   const Real c_m1 = Real(a.inv_time * (-2.0 / 6.0)), c_0 = Real(a.inv_time * (-3.0 / 6.0)), c_p1 = Real(a.inv_time * (6.0 / 6.0)),
              c_p2 = Real(a.inv_time * (-1.0 / 6.0));
   const int ntiles = (N + kTileSteps - 1) / kTileSteps;
-  const int nx1 = a.sdf.nx - 1, ny1 = a.sdf.ny - 1, nz1 = a.sdf.nz - 1, sny = a.sdf.ny, snz = a.sdf.nz, vdtype = a.sdf.dtype;
   const void* vox = a.sdf.vox;
 
   for (int job = blockIdx.x; job < a.total_rollouts; job += gridDim.x) {
@@ -766,81 +806,47 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
           // velocity frame V = sum_k rule_k/dt * F(t+k), vel(sphere) = V.R * p + V.p (linear in the frame); built
           // lazily, only when some lane of the warp has a sphere of this link inside its clearance band
           bool haveV = false;
-          for (int j0 = sph_begin; j0 < sph_end; j0 += kSphereBatch) {
-            // 1. positions, voxel indices and the gathers of up to kSphereBatch spheres (loads stay in flight)
-            unsigned raw[kSphereBatch];
-            bool inside[kSphereBatch];
-            int cell[kSphereBatch][3];
-            Real pos[kSphereBatch][3];
+          for (int j = sph_begin; j < sph_end; ++j) {
+            const DevSphere<Real>& sp = spheres[j];
+            const Real s0 = sp.pos[0], s1 = sp.pos[1], s2 = sp.pos[2];
+            const Real px = F[0] * s0 + F[1] * s1 + F[2] * s2 + F[9];
+            const Real py = F[3] * s0 + F[4] * s1 + F[5] * s2 + F[10];
+            const Real pz = F[6] * s0 + F[7] * s1 + F[8] * s2 + F[11];
+            int cx, cy, cz;
+            const bool inside = voxel_cells(g, px, py, pz, cx, cy, cz);
+            // outside the grid (or within one cell of its faces) the reference returns distance 0
+            const Real dist = inside ? voxel_distance<Real, kVox>(vox, (cx * g.sny + cy) * g.snz + cz, sqrt_tab, g.res) : Real(0);
+            // three-piece potential (stomp_collision_space.h:209-226), branch-free
+            const Real radius = sp.radius, clearance = sp.clearance;
+            const Real dd = dist - radius, diff = dd - clearance;
+            const Real pot_mid = Real(0.5) * (diff * sp.inv_clearance) * diff;
+            const Real pot_neg = -dd + Real(0.5) * clearance;
+            const Real pot = dd >= clearance ? Real(0) : (dd >= Real(0) ? pot_mid : pot_neg);
+            const bool hit = dist <= radius;
+            collided |= int(hit & counts);
+            Real vm = Real(0);
+            if (__any_sync(0xffffffffu, kDebug || pot != Real(0))) {
+              if (!haveV) {
 #pragma unroll
-            for (int u = 0; u < kSphereBatch; ++u) {
-              raw[u] = 0u;
-              inside[u] = false;
-              if (j0 + u < sph_end) {
-                const DevSphere<Real>& sp = spheres[j0 + u];
-                const Real s0 = sp.pos[0], s1 = sp.pos[1], s2 = sp.pos[2];
-                const Real px = F[0] * s0 + F[1] * s1 + F[2] * s2 + F[9];
-                const Real py = F[3] * s0 + F[4] * s1 + F[5] * s2 + F[10];
-                const Real pz = F[6] * s0 + F[7] * s1 + F[8] * s2 + F[11];
-                int cx, cy, cz;
-                const bool inx = voxel_cell(px, ox, res, inv_res, nox, nx1, cx);
-                const bool iny = voxel_cell(py, oy, res, inv_res, noy, ny1, cy);
-                const bool inz = voxel_cell(pz, oz, res, inv_res, noz, nz1, cz);
-                inside[u] = inx && iny && inz;
-                if (inside[u]) {
-                  const int idx = (cx * sny + cy) * snz + cz;
-                  if (vdtype == STOMP_VOXEL_U8_SQ) raw[u] = __ldg(static_cast<const uint8_t*>(vox) + idx);
-                  else if (vdtype == STOMP_VOXEL_U16_SQ) raw[u] = __ldg(static_cast<const uint16_t*>(vox) + idx);
-                  else raw[u] = __float_as_uint(__ldg(static_cast<const float*>(vox) + idx));
-                }
-                if (kDebug) { cell[u][0] = cx; cell[u][1] = cy; cell[u][2] = cz; pos[u][0] = px; pos[u][1] = py; pos[u][2] = pz; }
+                for (int i = 0; i < 12; ++i)
+                  Vs[i * 32] = c_m1 * shfl_rel(F[i], -1) + c_0 * F[i] + c_p1 * shfl_rel(F[i], 1) + c_p2 * shfl_rel(F[i], 2);
+                haveV = true;
               }
+              const Real vx = Vs[0 * 32] * s0 + Vs[1 * 32] * s1 + Vs[2 * 32] * s2 + Vs[9 * 32];
+              const Real vy = Vs[3 * 32] * s0 + Vs[4 * 32] * s1 + Vs[5 * 32] * s2 + Vs[10 * 32];
+              const Real vz = Vs[6 * 32] * s0 + Vs[7 * 32] * s1 + Vs[8 * 32] * s2 + Vs[11 * 32];
+              vm = Math<Real>::sqrt_(vx * vx + vy * vy + vz * vz);
+              cost += sp.weight * (pot * vm);
             }
-            // 2. distance -> three-piece potential -> (lazy) velocity -> cost
-#pragma unroll
-            for (int u = 0; u < kSphereBatch; ++u) {
-              if (j0 + u < sph_end) {
-                const DevSphere<Real>& sp = spheres[j0 + u];
-                Real dist = Real(0);
-                if (inside[u]) {
-                  if (vdtype == STOMP_VOXEL_U8_SQ) dist = sqrt_tab[raw[u]];
-                  else if (vdtype == STOMP_VOXEL_U16_SQ) dist = Math<Real>::sqrt_(Real(raw[u])) * res;
-                  else dist = Real(__uint_as_float(raw[u]));
-                }
-                const Real radius = sp.radius, clearance = sp.clearance;
-                const Real dd = dist - radius;
-                Real pot;
-                if (dd >= clearance) pot = Real(0);
-                else if (dd >= Real(0)) { const Real diff = dd - clearance; pot = Real(0.5) * (diff * sp.inv_clearance) * diff; }
-                else pot = -dd + Real(0.5) * clearance;
-                const bool hit = dist <= radius;
-                if (hit && counts) collided = 1;
-                Real vm = Real(0);
-                if (__any_sync(0xffffffffu, kDebug || pot != Real(0))) {
-                  if (!haveV) {
-#pragma unroll
-                    for (int i = 0; i < 12; ++i)
-                      Vs[i * 32] = c_m1 * shfl_rel(F[i], -1) + c_0 * F[i] + c_p1 * shfl_rel(F[i], 1) + c_p2 * shfl_rel(F[i], 2);
-                    haveV = true;
-                  }
-                  const Real s0 = sp.pos[0], s1 = sp.pos[1], s2 = sp.pos[2];
-                  const Real vx = Vs[0 * 32] * s0 + Vs[1 * 32] * s1 + Vs[2 * 32] * s2 + Vs[9 * 32];
-                  const Real vy = Vs[3 * 32] * s0 + Vs[4 * 32] * s1 + Vs[5 * 32] * s2 + Vs[10 * 32];
-                  const Real vz = Vs[6 * 32] * s0 + Vs[7 * 32] * s1 + Vs[8 * 32] * s2 + Vs[11 * 32];
-                  vm = Math<Real>::sqrt_(vx * vx + vy * vy + vz * vz);
-                  cost += sp.weight * (pot * vm);
-                }
-                if (kDebug) {
-                  if (t >= -1 && t <= N + 1 && (lane >= 1 && lane <= kTileSteps || (tile == 0 && lane == 0) ||
-                                                 (tile == ntiles - 1 && lane > kTileSteps))) {
-                    stomp_sphere_debug& rec = a.debug[size_t(t + 1) * K + sp.original_index];
-                    rec.voxel[0] = cell[u][0]; rec.voxel[1] = cell[u][1]; rec.voxel[2] = cell[u][2];
-                    rec.in_collision = hit;
-                    rec.position[0] = pos[u][0]; rec.position[1] = pos[u][1]; rec.position[2] = pos[u][2];
-                    rec.potential = pot;
-                    rec.vel_mag = (t >= 0 && t < N && lane >= 1 && lane <= kTileSteps) ? double(vm) : 0.0;
-                  }
-                }
+            if (kDebug) {
+              if (t >= -1 && t <= N + 1 && (lane >= 1 && lane <= kTileSteps || (tile == 0 && lane == 0) ||
+                                             (tile == ntiles - 1 && lane > kTileSteps))) {
+                stomp_sphere_debug& rec = a.debug[size_t(t + 1) * K + sp.original_index];
+                rec.voxel[0] = cx; rec.voxel[1] = cy; rec.voxel[2] = cz;
+                rec.in_collision = hit;
+                rec.position[0] = px; rec.position[1] = py; rec.position[2] = pz;
+                rec.potential = pot;
+                rec.vel_mag = (t >= 0 && t < N && lane >= 1 && lane <= kTileSteps) ? double(vm) : 0.0;
               }
             }
           }
