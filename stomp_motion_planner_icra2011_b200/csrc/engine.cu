@@ -118,7 +118,9 @@ struct Engine {
     }
     return st;
   }
-  bool huge_path() const { return desc.rollout_shard_world > 1 || R > 4096; }
+  // statistics over rollouts: one CTA per (problem, dims) looping over R (small R, many problems), or the
+  // two-stage partial reductions over rollout chunks (rollout sharding, or one problem with many rollouts)
+  bool huge_path() const { return desc.rollout_shard_world > 1 || R > 4096 || (B == 1 && R >= 128); }
 };
 
 void begin_launch(Engine& e) {

@@ -265,3 +265,79 @@ def test_engine_matches_committed_golden_vectors():
                           (_abi.FIELD_PROBABILITIES, "probabilities"), (_abi.FIELD_UPDATES, "updates"),
                           (_abi.FIELD_ROLLOUT_TOTAL_COSTS, "totals")):
                 assert_close(eng.get(f), g[key + nm], RTOL_F64, nm + " it %d" % it)
+
+
+def test_many_rollouts_single_problem_uses_chunked_statistics():
+    """B == 1 with R >= 128 takes the two-stage (rollout-chunk) reduction path that rollout sharding also uses."""
+    sc = scenes.make_scenario("tiny", num_problems=1, num_rollouts=160)
+    sc.num_reused_rollouts = 40
+    _run_iterations(sc, 3)
+
+
+@pytest.mark.parametrize("voxel_dtype", [_abi.VOXEL_U16_SQ, _abi.VOXEL_F32])
+def test_other_voxel_types(voxel_dtype):
+    sc = scenes.make_scenario("tiny", num_problems=2)
+    sc.sdf = scenes.bake_distance_field(size=(1.6, 1.6, 1.6), origin=(-0.3, -1.0, 0.0), resolution=0.04,
+                                        boxes=[((0.7, -0.3, 0.7), (0.3, 0.5, 0.06))], cylinders=[((0.5, -0.6, 0.8), 0.06, 1.0)],
+                                        max_distance=0.17, voxel_dtype=voxel_dtype)
+    eng, ors = _engine(sc), _oracles(sc)
+    params = _noisy_rollouts(sc, ors, np.random.default_rng(8), 4)
+    costs, cf = eng.execute(params)
+    for b, o in enumerate(ors):
+        oc, ocf = o.execute(params[b])
+        # f32 voxels hold the same distances rounded to float: 6e-8 relative on the distance
+        assert_close(costs[b], oc, 1e-5 if voxel_dtype == _abi.VOXEL_F32 else RTOL_F64, "state costs")
+        np.testing.assert_array_equal(cf[b], ocf)
+
+
+def test_c4_dense_clutter_shape():
+    """BASELINE configs[3] at reduced batch: 256^3 grid @ 1 cm, 60 spheres per link (K = 420), 200 timesteps."""
+    sc = scenes.make_scenario("C4", num_problems=2)
+    assert len(sc.robot.spheres) == 420 and sc.sdf.dims == (256, 256, 256) and sc.num_time_steps == 200
+    _run_iterations(sc, 2)
+
+
+def test_c5_thirty_dof_chain_shape():
+    """BASELINE configs[4] at reduced rollout count: 30-DOF serial chain, 300 timesteps."""
+    sc = scenes.make_scenario("C5", num_problems=1, num_rollouts=12)
+    sc.num_reused_rollouts = 4
+    assert sc.robot.num_dimensions == 30 and sc.num_time_steps == 300
+    _run_iterations(sc, 2)
+
+
+def test_full_size_batch_properties():
+    """BASELINE configs[1] at full size (1024 problems): size-independent properties.
+    (a) every problem of the batch evolves exactly as it does when planned alone (problems are independent);
+    (b) probabilities sum to one over rollouts; (c) reused rollouts keep their state costs and parameters."""
+    sc = scenes.make_scenario("C2")
+    assert sc.start.shape[0] == 1024
+    big = _engine(sc, keep_intermediates=1)
+    picks = [0, 511, 1023]
+    small = _engine(sc, keep_intermediates=1, problems=picks)
+    rng = np.random.default_rng(21)
+    L = np.linalg.cholesky(big.get(_abi.FIELD_INV_CONTROL_COST))
+    D = sc.robot.num_dimensions
+    prev_state = prev_params = None
+    for it in (1, 2, 3):
+        ngen = sc.num_rollouts if it == 1 else sc.num_rollouts - sc.num_reused_rollouts
+        base = correlated_noise(L, rng, (8, ngen), np.full(D, 2.0))
+        eps = np.resize(base, (1024, ngen, D, sc.num_time_steps))
+        big.inject_noise(eps)
+        small.inject_noise(eps[picks])
+        cb, fb, _ = big.iterate(it)
+        cs, fs, _ = small.iterate(it)
+        np.testing.assert_array_equal(cb[picks], cs)
+        np.testing.assert_array_equal(fb[picks], fs)
+        np.testing.assert_array_equal(big.get(_abi.FIELD_THETA)[picks], small.get(_abi.FIELD_THETA))
+        P = big.get(_abi.FIELD_PROBABILITIES)
+        np.testing.assert_allclose(P.sum(axis=1), 1.0, rtol=1e-12)
+        state, params = big.get(_abi.FIELD_STATE_COSTS), big.get(_abi.FIELD_PARAMETERS)
+        if prev_state is not None:
+            # every reused slot holds one of the previous iteration's rollouts (or the noise-less one) unchanged
+            for b in picks:
+                for r in range(ngen, sc.num_rollouts):
+                    match = [np.array_equal(state[b, r], prev_state[b, q]) and np.array_equal(params[b, r], prev_params[b, q])
+                             for q in range(sc.num_rollouts)]
+                    assert any(match) or np.array_equal(state[b, r], prev_extra[b])
+        prev_state, prev_params, prev_extra = state, params, big.get(_abi.FIELD_NOISELESS_COSTS)
+    assert np.all(np.isfinite(cb))
