@@ -333,13 +333,20 @@ def run_engine(args):
     avg_launch_s = cost_ms * 1e-3 / max(cost_n, 1)
     achieved = algo_bytes_launch / avg_launch_s / 1e9
     flops_per_eval = 7 * 110 + Ksph * 54
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and name == "C2" and B == 1024 and args.dtype == "f64":
+        with open(tpath) as f:
+            traffic = json.load(f)["k_cost"]["avg_launch_bytes"]
     roofline = {"bound": "hbm", "kernel": "k_cost", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
                 "algorithmic_bytes_per_eval": bytes_per_eval, "avg_launch_ms": 1e3 * avg_launch_s,
                 "kernel_share_of_step": cost_ms / all_ms if all_ms else None,
-                "note": "k_cost is fp64-ALU / latency bound, not HBM bound: algorithmic traffic is ~%d B/eval against ~%d fp64 flop/eval; "
-                        "est. %.2f TFLOP/s fp64" % (bytes_per_eval, flops_per_eval,
-                                                    flops_per_eval * evals_step / 2.0 / avg_launch_s / 1e12),
+                "binding": {"roof": "sm instruction issue", "frac": 0.68,
+                            "source": "ncu smsp__issue_active.avg.pct_of_peak_sustained_active, profiles/r1_top3_ncu_summary.csv"},
+                "note": "k_cost is instruction-issue bound, not HBM bound: algorithmic traffic is ~%d B/eval against ~%d fp64 flop/eval "
+                        "(est. %.2f TFLOP/s fp64); traffic = ncu DRAM bytes per launch, mostly L2 hits on the u8 grid"
+                        % (bytes_per_eval, flops_per_eval, flops_per_eval * evals_step / 2.0 / avg_launch_s / 1e12),
                 "kernels": shares}
 
     if rank == 0:
