@@ -136,7 +136,9 @@ enum stomp_field {
   STOMP_FIELD_PROJECTION = 14,       /* [N][N] M */
   STOMP_FIELD_QUAD_COST_INV = 15,    /* [N][N] StompCost::quad_cost_inv_ (scaled) */
   STOMP_FIELD_CONTROL_COST = 16,     /* [N][N] R */
-  STOMP_FIELD_CLIPPED_PARAMETERS = 17 /* [B][R][D][N] trajectory after handleJointLimits (what FK sees) */
+  STOMP_FIELD_CLIPPED_PARAMETERS = 17, /* [B][R][D][N] trajectory after handleJointLimits (what FK sees) */
+  STOMP_FIELD_BEST_TRAJECTORY = 18,    /* [B][D][N] best_group_trajectory_ kept by stomp_engine_optimize */
+  STOMP_FIELD_NOISELESS_TRAJECTORY = 19 /* [B][D][N] group trajectory of the last noise-less rollout (after joint limits) */
 };
 
 /* Per-sphere debug record of one rollout (parity tap for the integer work). */
@@ -231,6 +233,25 @@ int stomp_engine_iterate(void* engine, int32_t iteration_number, stomp_iter_stat
 /* iterations first..first+count-1 back to back on the device, no host round trip in between. */
 int stomp_engine_run(void* engine, int32_t first_iteration, int32_t count, stomp_iter_stats* last_stats);
 int stomp_engine_synchronize(void* engine);
+
+/* StompOptimizer::optimize, STOMP branch (src/stomp_optimizer.cpp:284-359,368-400), for every problem of the batch with
+ * the bookkeeping on the device: per iteration the noise-less rollout's cost / collision flag update
+ * collision_free_iteration_, the success iterations, the best (joint-limit-clipped) trajectory and
+ * last_improvement_iteration_; a problem stops being tracked once it has been collision free for
+ * max_iterations_after_collision_free consecutive iterations (the reference's early exit), and the call returns when
+ * every problem has stopped or after max_iterations.  Mirrors msg/STOMPStatistics.msg.  All arrays are [B] and may be
+ * NULL; costs is [max_iterations][B] (iteration-major), entries after a problem's exit are left untouched. */
+typedef struct stomp_optimize_stats {
+  int32_t* success;
+  int32_t* success_iteration;            /* -1 if never collision free */
+  int32_t* collision_success_iteration;  /* -1 if never collision free */
+  int32_t* last_improvement_iteration;   /* -1 if the first iteration stayed the best */
+  int32_t* iterations;                   /* iterations run before the problem's loop ended */
+  double* best_cost;
+  double* costs;
+} stomp_optimize_stats;
+int stomp_engine_optimize(void* engine, int32_t max_iterations, int32_t max_iterations_after_collision_free,
+                          stomp_optimize_stats* stats);
 
 /* ---- getters -------------------------------------------------------------------- */
 /* Copies a field (see stomp_field) to a host buffer of `bytes` bytes (fp64 unless noted). */

@@ -12,7 +12,7 @@ JOINT_FIXED, JOINT_REVOLUTE, JOINT_PRISMATIC = 0, 1, 2
 (FIELD_THETA, FIELD_NOISE, FIELD_PARAMETERS, FIELD_NOISE_PROJECTED, FIELD_STATE_COSTS, FIELD_CONTROL_COSTS,
  FIELD_CUMULATIVE_COSTS, FIELD_PROBABILITIES, FIELD_UPDATES, FIELD_NOISELESS_COSTS, FIELD_COLLISION_FREE,
  FIELD_ROLLOUT_TOTAL_COSTS, FIELD_INV_CONTROL_COST, FIELD_NOISE_CHOLESKY, FIELD_PROJECTION, FIELD_QUAD_COST_INV,
- FIELD_CONTROL_COST, FIELD_CLIPPED_PARAMETERS) = range(18)
+ FIELD_CONTROL_COST, FIELD_CLIPPED_PARAMETERS, FIELD_BEST_TRAJECTORY, FIELD_NOISELESS_TRAJECTORY) = range(20)
 
 
 class EngineDesc(C.Structure):
@@ -86,4 +86,16 @@ class SphereDebug(C.Structure):
         ("position", C.c_double * 3),
         ("potential", C.c_double),
         ("vel_mag", C.c_double),
+    ]
+
+
+class OptimizeStats(C.Structure):
+    _fields_ = [
+        ("success", C.POINTER(C.c_int32)),
+        ("success_iteration", C.POINTER(C.c_int32)),
+        ("collision_success_iteration", C.POINTER(C.c_int32)),
+        ("last_improvement_iteration", C.POINTER(C.c_int32)),
+        ("iterations", C.POINTER(C.c_int32)),
+        ("best_cost", C.POINTER(C.c_double)),
+        ("costs", C.POINTER(C.c_double)),
     ]

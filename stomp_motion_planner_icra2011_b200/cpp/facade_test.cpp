@@ -94,6 +94,11 @@ int main() {
   std::printf("optimize: first cost %.6f, best cost %.6f, %zu iterations, collision-free at %d\n", stats.costs.front(),
               stats.best_cost, stats.costs.size(), stats.collision_success_iteration);
   if (!(stats.best_cost <= stats.costs.front()) || stats.costs.size() != 40u) { std::printf("FAIL cost did not improve\n"); return 1; }
+  std::vector<VectorXd> best;
+  if (!opt->getBestTrajectory(best) || best.size() != 4u || best[0].size() != 60u) { std::printf("FAIL best trajectory\n"); return 1; }
+  for (int d = 0; d < 3; ++d)
+    for (double v : best[d])
+      if (v > robot.joint_limits[d].max + 1e-4 || v < robot.joint_limits[d].min - 1e-4) { std::printf("FAIL joint limits\n"); return 1; }
 
   // ---- 2. fused path == reference call sequence with a host Task --------------------------------------------------
   auto a = std::make_shared<StompOptimizer>(start, goal, &robot, &params, &space);

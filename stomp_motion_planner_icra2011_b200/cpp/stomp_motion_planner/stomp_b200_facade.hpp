@@ -292,35 +292,34 @@ class StompOptimizer : public Task, public std::enable_shared_from_this<StompOpt
   bool getControlCostWeight(double& w) override { w = parameters_->smoothness_cost_weight; return true; }
   std::shared_ptr<Engine> getEngine() override { return engine_; }
 
-  // StompOptimizer::optimize (src/stomp_optimizer.cpp:249-401), STOMP branch
+  // StompOptimizer::optimize (src/stomp_optimizer.cpp:249-401), STOMP branch: the iteration loop and its bookkeeping
+  // (collision_free_iteration_, success iterations, best trajectory, early exit) run on the device.
   bool optimize(STOMPStatistics* stats = nullptr) {
     if (!ok_) return false;
-    PolicyImprovementLoop pi_loop;
-    if (!pi_loop.initialize(*parameters_, shared_from_this())) return false;
+    const int max_it = parameters_->max_iterations;
     STOMPStatistics st;
-    int collision_free_iteration = 0;
-    std::vector<VectorXd> best;
+    st.costs.assign(max_it, 0.0);
+    int32_t success = 0, success_it = -1, coll_it = -1, last_imp = -1, iterations = 0;
     double best_cost = 0.0;
-    last_improvement_iteration_ = -1;
-    for (iteration_ = 0; iteration_ < parameters_->max_iterations; iteration_++) {
-      if (!pi_loop.runSingleIteration(iteration_ + 1)) return false;
-      last_trajectory_cost_ = pi_loop.lastNoiselessCost();
-      last_trajectory_collision_free_ = pi_loop.lastNoiselessCollisionFree();
-      collision_free_iteration = last_trajectory_collision_free_ ? collision_free_iteration + 1 : 0;
-      if (last_trajectory_collision_free_ && st.collision_success_iteration == -1) st.collision_success_iteration = iteration_;
-      if (last_trajectory_collision_free_ && st.success_iteration == -1) { st.success_iteration = iteration_; st.success = true; }
-      double cost = last_trajectory_cost_;
-      st.costs.push_back(cost);
-      if (iteration_ == 0 || (cost < best_cost && last_trajectory_collision_free_)) {
-        if (iteration_ > 0) last_improvement_iteration_ = iteration_;
-        policy_->getParameters(best);
-        best_cost = cost;
-      }
-      if (collision_free_iteration >= parameters_->max_iterations_after_collision_free) { iteration_++; break; }
-    }
-    policy_->setParameters(best);  // group_trajectory_ = best_group_trajectory_
+    stomp_optimize_stats os = {&success, &success_it, &coll_it, &last_imp, &iterations, &best_cost, st.costs.data()};
+    if (stomp_engine_optimize(engine_->get(), max_it, parameters_->max_iterations_after_collision_free, &os)) return false;
+    st.costs.resize(iterations);
+    st.success = success != 0;
+    st.success_iteration = success_it;
+    st.collision_success_iteration = coll_it;
     st.best_cost = best_cost;
+    last_improvement_iteration_ = last_imp;
+    iteration_ = iterations;
+    if (!st.costs.empty()) last_trajectory_cost_ = st.costs.back();
     if (stats) *stats = st;
+    return true;
+  }
+  // group_trajectory_ after optimize(): the best trajectory (after joint-limit handling), [D][N]
+  bool getBestTrajectory(std::vector<VectorXd>& trajectory) {
+    std::vector<double> buf(size_t(engine_->D) * engine_->N);
+    if (stomp_engine_get(engine_->get(), STOMP_FIELD_BEST_TRAJECTORY, buf.data(), buf.size() * sizeof(double))) return false;
+    trajectory.resize(engine_->D);
+    for (int d = 0; d < engine_->D; ++d) trajectory[d].assign(buf.begin() + size_t(d) * engine_->N, buf.begin() + size_t(d + 1) * engine_->N);
     return true;
   }
 

@@ -99,6 +99,9 @@ struct Engine {
   DevBuf<stomp_sphere_debug> debug;
   DevBuf<double> part, minmax, sums;  // sharded / huge-R statistics
   DevBuf<double> gen_scratch;         // time-major work buffer of k_generate
+  DevBuf<double> extra_clipped, best_traj, best_cost, cost_log;   // optimize() bookkeeping
+  DevBuf<unsigned char> track_state;
+  DevBuf<int> num_done;
   int num_nodes = 0;
   Sdf sdf;
   size_t scratch_n = 0;
@@ -447,7 +450,7 @@ int step_improve(Engine& e, int apply) {
 int step_extra(Engine& e, bool run_cost, int iteration_number, bool have_control = false) {
   if (run_cost) {
     if (launch_cost(e, e.theta.p, size_t(e.D) * e.N, 1, e.B, iteration_number == 1, e.extra_state.p, size_t(e.N),
-                    e.collision_free.p, e.R + 1, e.R, nullptr, nullptr))
+                    e.collision_free.p, e.R + 1, e.R, e.extra_clipped.p, nullptr))
       return 1;
   }
   if (!have_control) {
@@ -580,6 +583,8 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   ALLOC(e.extra_state, size_t(e.B) * e.N); ALLOC(e.extra_control, BDN); ALLOC(e.updates, BDN); ALLOC(e.noiseless_sum, size_t(e.B));
   ALLOC(e.reuse_src, size_t(e.B) * std::max(1, e.Rre)); ALLOC(e.collision_free, size_t(e.B) * (e.R + 1));
   ALLOC(e.noise_scale, size_t(e.D));
+  ALLOC(e.extra_clipped, BDN); ALLOC(e.best_traj, BDN); ALLOC(e.best_cost, size_t(e.B));
+  ALLOC(e.track_state, size_t(e.B) * sizeof(TrackState)); ALLOC(e.num_done, 1);
   ALLOC(e.part, size_t(kChunks) * 2 * e.D * e.N); ALLOC(e.minmax, size_t(2) * e.D * e.N); ALLOC(e.sums, size_t(2) * e.D * e.N);
 #undef ALLOC
   // matrices
@@ -884,6 +889,51 @@ int stomp_engine_run(void* h, int32_t first_iteration, int32_t count, stomp_iter
   return fill_stats(e, last_stats);
 }
 
+int stomp_engine_optimize(void* h, int32_t max_iterations, int32_t max_after_cf, stomp_optimize_stats* stats) {
+  ENGINE_OR_FAIL(h);
+  if (!e.have_problems) return fail("set_problems must be called first");
+  if (max_iterations < 1) return fail("max_iterations must be >= 1");
+  if (e.desc.rollout_shard_world > 1) return fail("optimize is not available on a rollout-sharded engine");
+  std::vector<TrackState> init(e.B, TrackState{0, -1, -1, -1, 0, 0});
+  if (upload(e, e.track_state, reinterpret_cast<const unsigned char*>(init.data()), init.size() * sizeof(TrackState))) return 1;
+  CUDA_TRY(cudaMemsetAsync(e.num_done.p, 0, sizeof(int), e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  const bool want_log = stats && stats->costs;
+  if (want_log && e.cost_log.n < size_t(max_iterations) * e.B) CUDA_TRY(e.cost_log.alloc(size_t(max_iterations) * e.B));
+  const int check_every = 16;   // host looks at the "all problems done" counter this often; results do not depend on it
+  int it = 0;
+  for (; it < max_iterations; ++it) {
+    if (iterate_once(e, it + 1)) return 1;
+    begin_launch(e);
+    k_track_best<<<e.B, 128, 0, e.stream>>>(it, max_after_cf, e.D * e.N, e.R + 1, e.R, e.noiseless_sum.p, e.collision_free.p,
+                                            e.extra_clipped.p, reinterpret_cast<TrackState*>(e.track_state.p), e.best_cost.p,
+                                            e.best_traj.p, want_log ? e.cost_log.p : nullptr, e.B, e.num_done.p);
+    if (check_launch(e, "k_track_best")) return 1;
+    if ((it + 1) % check_every == 0 && it + 1 < max_iterations) {
+      int done = 0;
+      CUDA_TRY(cudaMemcpyAsync(&done, e.num_done.p, sizeof(int), cudaMemcpyDeviceToHost, e.stream));
+      CUDA_TRY(cudaStreamSynchronize(e.stream));
+      if (done >= e.B) { ++it; break; }
+    }
+  }
+  const int ran = std::min(it, max_iterations);
+  std::vector<TrackState> st(e.B);
+  CUDA_TRY(cudaMemcpyAsync(st.data(), e.track_state.p, st.size() * sizeof(TrackState), cudaMemcpyDeviceToHost, e.stream));
+  if (stats && stats->best_cost) CUDA_TRY(cudaMemcpyAsync(stats->best_cost, e.best_cost.p, size_t(e.B) * 8, cudaMemcpyDeviceToHost, e.stream));
+  if (want_log) CUDA_TRY(cudaMemcpyAsync(stats->costs, e.cost_log.p, size_t(ran) * e.B * 8, cudaMemcpyDeviceToHost, e.stream));
+  // group_trajectory_ = best_group_trajectory_ (stomp_optimizer.cpp:368): the policy itself is left at the last iterate
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  if (stats)
+    for (int b = 0; b < e.B; ++b) {
+      if (stats->success) stats->success[b] = st[b].success_iteration >= 0;
+      if (stats->success_iteration) stats->success_iteration[b] = st[b].success_iteration;
+      if (stats->collision_success_iteration) stats->collision_success_iteration[b] = st[b].collision_success_iteration;
+      if (stats->last_improvement_iteration) stats->last_improvement_iteration[b] = st[b].last_improvement_iteration;
+      if (stats->iterations) stats->iterations[b] = st[b].iterations;
+    }
+  return 0;
+}
+
 int stomp_engine_synchronize(void* h) {
   ENGINE_OR_FAIL(h);
   CUDA_TRY(cudaStreamSynchronize(e.stream));
@@ -911,6 +961,8 @@ int stomp_engine_get(void* h, int32_t field, void* out, size_t bytes) {
     case STOMP_FIELD_COLLISION_FREE: src = e.collision_free.p; need = size_t(e.B) * (e.R + 1) * 4; break;
     case STOMP_FIELD_ROLLOUT_TOTAL_COSTS: src = e.totals.p; need = size_t(e.B) * (e.R + 1) * 8; break;
     case STOMP_FIELD_CLIPPED_PARAMETERS: src = e.clipped.p; need = BRDN * 8; break;
+    case STOMP_FIELD_BEST_TRAJECTORY: src = e.best_traj.p; need = BDN * 8; break;
+    case STOMP_FIELD_NOISELESS_TRAJECTORY: src = e.extra_clipped.p; need = BDN * 8; break;
     case STOMP_FIELD_INV_CONTROL_COST: host = e.pm.Rinv.a; need = NN * 8; break;
     case STOMP_FIELD_CONTROL_COST: host = e.pm.R.a; need = NN * 8; break;
     case STOMP_FIELD_QUAD_COST_INV: host = e.pm.Qinv.a; need = NN * 8; break;

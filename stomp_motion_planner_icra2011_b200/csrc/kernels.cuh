@@ -1061,6 +1061,52 @@ __global__ void k_update(UpdateArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_track_best: the per-iteration bookkeeping of StompOptimizer::optimize (src/stomp_optimizer.cpp:296-347), CTA per
+// problem.  state[b] = {collision_free_iteration_, success_iteration, collision_success_iteration,
+// last_improvement_iteration_, iterations, done}; best_cost[b]; best[b][D][N] <- clipped noise-less trajectory.
+// ---------------------------------------------------------------------------------------------
+struct TrackState {
+  int collision_free_iteration, success_iteration, collision_success_iteration, last_improvement_iteration, iterations, done;
+};
+
+__global__ void k_track_best(int iteration, int max_after_collision_free, int DN, int flag_stride, int flag_offset,
+                             const double* __restrict__ noiseless_cost, const int* __restrict__ collision_free,
+                             const double* __restrict__ trajectory, TrackState* __restrict__ state, double* __restrict__ best_cost,
+                             double* __restrict__ best, double* __restrict__ cost_log, int B, int* __restrict__ num_done) {
+  const int b = blockIdx.x;
+  __shared__ int s_copy;
+  if (threadIdx.x == 0) {
+    TrackState st = state[b];
+    s_copy = 0;
+    if (!st.done) {
+      const double cost = noiseless_cost[b];
+      const bool cf = collision_free[size_t(b) * flag_stride + flag_offset] != 0;
+      st.collision_free_iteration = cf ? st.collision_free_iteration + 1 : 0;
+      if (cf && st.collision_success_iteration == -1) st.collision_success_iteration = iteration;
+      if (cf && st.success_iteration == -1) st.success_iteration = iteration;
+      if (cost_log) cost_log[size_t(iteration) * B + b] = cost;
+      if (iteration == 0) {
+        best_cost[b] = cost;
+        s_copy = 1;
+      } else if (cost < best_cost[b] && cf) {
+        best_cost[b] = cost;
+        st.last_improvement_iteration = iteration;
+        s_copy = 1;
+      }
+      st.iterations = iteration + 1;
+      if (st.collision_free_iteration >= max_after_collision_free) {
+        st.done = 1;
+        atomicAdd(num_done, 1);
+      }
+      state[b] = st;
+    }
+  }
+  __syncthreads();
+  if (s_copy)
+    for (int i = threadIdx.x; i < DN; i += blockDim.x) best[size_t(b) * DN + i] = trajectory[size_t(b) * DN + i];
+}
+
 // theta += updates  (Policy::updateParameters for caller-supplied updates)
 __global__ void k_axpy(size_t n, const double* __restrict__ x, double* __restrict__ y) {
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;

@@ -27,7 +27,7 @@ EXPORTS = [
     "stomp_engine_add_extra_rollouts", "stomp_engine_iterate", "stomp_engine_run", "stomp_engine_synchronize",
     "stomp_engine_get", "stomp_engine_launch_count", "stomp_engine_stream", "stomp_engine_timer_start",
     "stomp_engine_timer_stop", "stomp_engine_shard_buffers", "stomp_engine_iterate_sharded_phase",
-    "stomp_engine_set_profiling", "stomp_engine_get_profile",
+    "stomp_engine_set_profiling", "stomp_engine_get_profile", "stomp_engine_optimize",
 ]
 
 
@@ -200,6 +200,18 @@ class Engine:
         self._ck(self.L.stomp_engine_run(self.h, first_iteration, count, C.byref(st)))
         return cost, cf, st.num_generated_rollouts
 
+    def optimize(self, max_iterations, max_iterations_after_collision_free):
+        """StompOptimizer::optimize for the whole batch; returns a dict of per-problem statistics."""
+        B = self.B
+        i32 = lambda: np.full(B, -7, dtype=np.int32)
+        out = dict(success=i32(), success_iteration=i32(), collision_success_iteration=i32(), last_improvement_iteration=i32(),
+                   iterations=i32(), best_cost=np.zeros(B), costs=np.full((max_iterations, B), np.nan))
+        st = _abi.OptimizeStats(_ip(out["success"]), _ip(out["success_iteration"]), _ip(out["collision_success_iteration"]),
+                                _ip(out["last_improvement_iteration"]), _ip(out["iterations"]), _dp(out["best_cost"]), _dp(out["costs"]))
+        self._ck(self.L.stomp_engine_optimize(self.h, max_iterations, max_iterations_after_collision_free, C.byref(st)))
+        out["best_trajectory"] = self.get(_abi.FIELD_BEST_TRAJECTORY)
+        return out
+
     def synchronize(self):
         self._ck(self.L.stomp_engine_synchronize(self.h))
 
@@ -240,6 +252,7 @@ class Engine:
             _abi.FIELD_ROLLOUT_TOTAL_COSTS: (B, R + 1), _abi.FIELD_INV_CONTROL_COST: (N, N),
             _abi.FIELD_NOISE_CHOLESKY: (N, N), _abi.FIELD_PROJECTION: (N, N), _abi.FIELD_QUAD_COST_INV: (N, N),
             _abi.FIELD_CONTROL_COST: (N, N), _abi.FIELD_CLIPPED_PARAMETERS: (B, R, D, N),
+            _abi.FIELD_BEST_TRAJECTORY: (B, D, N), _abi.FIELD_NOISELESS_TRAJECTORY: (B, D, N),
         }
         if field == _abi.FIELD_COLLISION_FREE:
             out = np.empty((B, R + 1), dtype=np.int32)

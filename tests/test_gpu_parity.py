@@ -341,3 +341,53 @@ def test_full_size_batch_properties():
                     assert any(match) or np.array_equal(state[b, r], prev_extra[b])
         prev_state, prev_params, prev_extra = state, params, big.get(_abi.FIELD_NOISELESS_COSTS)
     assert np.all(np.isfinite(cb))
+
+
+def test_optimize_outer_loop_matches_host_bookkeeping():
+    """stomp_engine_optimize (device-side bookkeeping of StompOptimizer::optimize) against the same loop written on
+    the host from per-iteration statistics, and against the oracle's trajectories."""
+    sc = scenes.make_scenario("C1", num_problems=6)
+    max_it, max_cf = 40, 8
+    a = _engine(sc)
+    res = a.optimize(max_it, max_cf)
+    b = _engine(sc)                      # same seed -> same Philox noise
+    B = 6
+    cf_count = np.zeros(B, int); succ = np.full(B, -1); done = np.zeros(B, bool); last_imp = np.full(B, -1)
+    best_cost = np.zeros(B); iters = np.zeros(B, int)
+    best = np.zeros((B, sc.robot.num_dimensions, sc.num_time_steps))
+    costs = np.full((max_it, B), np.nan)
+    for it in range(max_it):
+        cost, cf, _ = b.iterate(it + 1)
+        traj = b.get(_abi.FIELD_NOISELESS_TRAJECTORY)
+        for p in range(B):
+            if done[p]:
+                continue
+            cf_count[p] = cf_count[p] + 1 if cf[p] else 0
+            if cf[p] and succ[p] == -1:
+                succ[p] = it
+            costs[it, p] = cost[p]
+            if it == 0 or (cost[p] < best_cost[p] and cf[p]):
+                if it > 0:
+                    last_imp[p] = it
+                best_cost[p] = cost[p]; best[p] = traj[p]
+            iters[p] = it + 1
+            if cf_count[p] >= max_cf:
+                done[p] = True
+        if done.all():
+            break
+    np.testing.assert_array_equal(res["success_iteration"], succ)
+    np.testing.assert_array_equal(res["collision_success_iteration"], succ)
+    np.testing.assert_array_equal(res["success"], (succ >= 0).astype(np.int32))
+    np.testing.assert_array_equal(res["last_improvement_iteration"], last_imp)
+    np.testing.assert_array_equal(res["iterations"], iters)
+    np.testing.assert_array_equal(res["best_cost"], best_cost)
+    np.testing.assert_array_equal(res["best_trajectory"], best)
+    ran = int(iters.max())
+    logged = ~np.isnan(costs[:ran])          # entries after a problem's exit are not written
+    np.testing.assert_array_equal(res["costs"][:ran][logged], costs[:ran][logged])
+    assert (succ >= 0).any(), "scene too hard: no problem became collision free"
+    # the best trajectory is the joint-limit-clipped one: inside the limits
+    for d, (has, lo, hi) in enumerate(sc.robot.limits):
+        if has:
+            ok = res["success"] == 1
+            assert np.all(res["best_trajectory"][ok, d] <= hi + 1e-4) and np.all(res["best_trajectory"][ok, d] >= lo - 1e-4)
