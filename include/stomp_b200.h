@@ -169,6 +169,29 @@ int stomp_engine_set_robot(void* engine, const stomp_segment* segments, int32_t 
  * types distance = sqrt(v) * resolution. */
 int stomp_engine_set_sdf(void* engine, const void* voxels, int32_t nx, int32_t ny, int32_t nz,
                          const double origin[3], double resolution, int32_t voxel_dtype);
+/* Rebuilds the distance field on the device from collision objects, like StompCollisionSpace::setStartState does per
+ * planning request (src/stomp_collision_space.cpp:154-197): every box / cylinder is sampled on a `resolution` lattice
+ * exactly as addCollisionObjectsToPoints does (src/stomp_collision_space.cpp:238-293: lattice from the low corner up to
+ * dimension + resolution, point = pose * (position - lattice point)), the points are binned with the field's
+ * worldToGrid rule, and the squared cell distance to the nearest occupied cell, capped at ceil(max_distance /
+ * resolution)^2, is computed for every voxel (exact Euclidean distance transform; the un-vendored ROS
+ * PropagationDistanceField propagates the same quantity).  num_cells = int(size / resolution).  The result replaces the
+ * field set by stomp_engine_set_sdf (u8 voxels when the cap fits, else u16). */
+typedef struct stomp_box {
+  double position[3];
+  double orientation[4]; /* quaternion x, y, z, w */
+  double dimensions[3];
+} stomp_box;
+typedef struct stomp_cylinder {
+  double position[3];
+  double orientation[4];
+  double radius;
+  double height;
+} stomp_cylinder;
+int stomp_engine_build_sdf(void* engine, const double size[3], const double origin[3], double resolution, double max_distance,
+                           const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders);
+/* Copies the current voxel grid out (parity tap): dims[3], voxel dtype, and up to `bytes` of voxels (may be NULL). */
+int stomp_engine_get_sdf(void* engine, int32_t dims[3], int32_t* voxel_dtype, void* voxels, size_t bytes);
 /* noise_stddev / noise_decay of PolicyImprovementLoop (src/policy_improvement_loop.cpp:118-119,155-160). */
 int stomp_engine_set_noise(void* engine, const double* noise_stddev /* [D] */, const double* noise_decay /* [D] */);
 

@@ -1,0 +1,64 @@
+"""CPU restatement of the reference's distance-field construction for boxes and cylinders (TEST INFRASTRUCTURE ONLY).
+
+Follows StompCollisionSpace::addCollisionObjectsToPoints (src/stomp_collision_space.cpp:238-293): lattice loops with
+accumulated `x += resolution_`, point = pose * (position - lattice point), then distance_field's worldToGrid
+(int(round((p - origin)/res)), points outside the grid dropped) and an exact squared Euclidean distance transform capped at
+ceil(max_distance/res)^2 (scipy.ndimage; PropagationDistanceField is not vendored)."""
+import math
+
+import numpy as np
+
+
+def _lattice(low, extent, res):
+    out = []
+    x = low
+    while x <= low + extent + res:
+        out.append(x)
+        x += res
+    return np.array(out)
+
+
+def _rotation(q):
+    x, y, z, w = q
+    x2, y2, z2, w2 = x * x, y * y, z * z, w * w
+    return np.array([[w2 + x2 - y2 - z2, 2 * x * y - 2 * w * z, 2 * x * z + 2 * w * y],
+                     [2 * x * y + 2 * w * z, w2 - x2 + y2 - z2, 2 * y * z - 2 * w * x],
+                     [2 * x * z - 2 * w * y, 2 * y * z + 2 * w * x, w2 - x2 - y2 + z2]])
+
+
+def _round_half_away(t):
+    return np.where(t >= 0, np.floor(t + 0.5), np.ceil(t - 0.5))
+
+
+def build(size, origin, resolution, max_distance, boxes=(), cylinders=()):
+    from scipy import ndimage
+    n = [int(size[i] / resolution) for i in range(3)]
+    occ = np.zeros(n, dtype=bool)
+    origin = np.asarray(origin, float)
+
+    def mark(pos, quat, xs, ys, zs, radius):
+        pos = np.asarray(pos, float)
+        X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij")
+        keep = np.ones(X.shape, bool)
+        if radius > 0:
+            keep = np.sqrt(np.abs(pos[0] - X) ** 2 + np.abs(pos[1] - Y) ** 2) <= radius
+        P = np.stack([pos[0] - X[keep], pos[1] - Y[keep], pos[2] - Z[keep]], axis=-1)
+        W = P @ _rotation(quat).T + pos
+        c = _round_half_away((W - origin) / resolution).astype(np.int64)
+        ok = np.all((c >= 0) & (c < np.array(n)), axis=1)
+        c = c[ok]
+        occ[c[:, 0], c[:, 1], c[:, 2]] = True
+
+    for (p, q, d) in boxes:
+        mark(p, q, _lattice(p[0] - d[0] / 2.0, d[0], resolution), _lattice(p[1] - d[1] / 2.0, d[1], resolution),
+             _lattice(p[2] - d[2] / 2.0, d[2], resolution), 0.0)
+    for (p, q, r, h) in cylinders:
+        mark(p, q, _lattice(p[0] - r, r * 2.0, resolution), _lattice(p[1] - r, r * 2.0, resolution),
+             _lattice(p[2] - h / 2.0, h, resolution), r)
+    cap = int(math.ceil(max_distance / resolution))
+    if occ.any():
+        d = ndimage.distance_transform_edt(~occ)
+        d2 = np.minimum(np.rint(d * d), cap * cap).astype(np.int64)
+    else:
+        d2 = np.full(n, cap * cap, dtype=np.int64)
+    return d2.astype(np.uint8 if cap * cap < 256 else np.uint16), occ

@@ -99,3 +99,11 @@ class OptimizeStats(C.Structure):
         ("best_cost", C.POINTER(C.c_double)),
         ("costs", C.POINTER(C.c_double)),
     ]
+
+
+class Box(C.Structure):
+    _fields_ = [("position", C.c_double * 3), ("orientation", C.c_double * 4), ("dimensions", C.c_double * 3)]
+
+
+class Cylinder(C.Structure):
+    _fields_ = [("position", C.c_double * 3), ("orientation", C.c_double * 4), ("radius", C.c_double), ("height", C.c_double)]

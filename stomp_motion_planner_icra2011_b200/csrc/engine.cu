@@ -679,6 +679,115 @@ int stomp_engine_set_sdf(void* h, const void* voxels, int32_t nx, int32_t ny, in
   return 0;
 }
 
+namespace {
+// lattice of one axis exactly like the reference's `for (double x = low; x <= low + extent + res; x += res)`
+void append_lattice(std::vector<double>& lat, double low, double extent, double res, int& offset, int& count) {
+  offset = int(lat.size());
+  for (double x = low; x <= low + extent + res; x += res) lat.push_back(x);
+  count = int(lat.size()) - offset;
+}
+void quaternion_to_rotation(const double q[4], double R[9]) {   // KDL::Rotation::Quaternion(x, y, z, w)
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  const double x2 = x * x, y2 = y * y, z2 = z * z, w2 = w * w;
+  R[0] = w2 + x2 - y2 - z2; R[1] = 2 * x * y - 2 * w * z; R[2] = 2 * x * z + 2 * w * y;
+  R[3] = 2 * x * y + 2 * w * z; R[4] = w2 - x2 + y2 - z2; R[5] = 2 * y * z - 2 * w * x;
+  R[6] = 2 * x * z - 2 * w * y; R[7] = 2 * y * z + 2 * w * x; R[8] = w2 - x2 - y2 + z2;
+}
+}  // namespace
+
+int stomp_engine_build_sdf(void* h, const double size[3], const double origin[3], double resolution, double max_distance,
+                           const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders) {
+  ENGINE_OR_FAIL(h);
+  if (!size || !origin || resolution <= 0.0 || max_distance <= 0.0) return fail("bad distance field specification");
+  if ((num_boxes > 0 && !boxes) || (num_cylinders > 0 && !cylinders) || num_boxes < 0 || num_cylinders < 0) return fail("bad collision objects");
+  const int nx = int(size[0] / resolution), ny = int(size[1] / resolution), nz = int(size[2] / resolution);
+  if (nx < 3 || ny < 3 || nz < 3) return fail("distance field too small");
+  const size_t cells = size_t(nx) * ny * nz;
+  if (cells >= (size_t(1) << 31)) return fail("distance field too large (cells must fit a 32-bit index)");
+  const int cap = int(std::ceil(max_distance / resolution));
+  if (cap < 1 || cap > 255) return fail("max_distance / resolution out of range");
+  std::vector<SdfShape> shapes;
+  std::vector<double> lattice;
+  long long total = 0;
+  auto add = [&](const double pos[3], const double quat[4], double ex, double ey, double ez, double lowx, double lowy, double lowz,
+                 double radius) {
+    SdfShape s;
+    std::memset(&s, 0, sizeof(s));
+    for (int i = 0; i < 3; ++i) s.position[i] = pos[i];
+    quaternion_to_rotation(quat, s.R);
+    s.radius = radius;
+    append_lattice(lattice, lowx, ex, resolution, s.x_off, s.nx);
+    append_lattice(lattice, lowy, ey, resolution, s.y_off, s.ny);
+    append_lattice(lattice, lowz, ez, resolution, s.z_off, s.nz);
+    s.first = total;
+    total += (long long)s.nx * s.ny * s.nz;
+    shapes.push_back(s);
+  };
+  for (int i = 0; i < num_boxes; ++i) {   // src/stomp_collision_space.cpp:275-291
+    const stomp_box& b = boxes[i];
+    add(b.position, b.orientation, b.dimensions[0], b.dimensions[1], b.dimensions[2], b.position[0] - b.dimensions[0] / 2.0,
+        b.position[1] - b.dimensions[1] / 2.0, b.position[2] - b.dimensions[2] / 2.0, 0.0);
+  }
+  for (int i = 0; i < num_cylinders; ++i) {   // src/stomp_collision_space.cpp:238-269
+    const stomp_cylinder& c = cylinders[i];
+    if (!(c.radius > 0.0)) return fail("cylinder radius must be positive");
+    add(c.position, c.orientation, c.radius * 2.0, c.radius * 2.0, c.height, c.position[0] - c.radius, c.position[1] - c.radius,
+        c.position[2] - c.height / 2.0, c.radius);
+  }
+  DevBuf<unsigned char> occ, dshapes;
+  DevBuf<double> dlat;
+  DevBuf<uint16_t> g1, g2;
+  CUDA_TRY(occ.alloc(cells));
+  CUDA_TRY(g1.alloc(cells));
+  CUDA_TRY(g2.alloc(cells));
+  if (!shapes.empty()) {
+    if (upload(e, dshapes, reinterpret_cast<const unsigned char*>(shapes.data()), shapes.size() * sizeof(SdfShape)) ||
+        upload(e, dlat, lattice.data(), lattice.size()))
+      return 1;
+    const unsigned grid = unsigned(std::min<long long>((total + 255) / 256, 148 * 32));
+    begin_launch(e);
+    k_sdf_mark<<<std::max(1u, grid), 256, 0, e.stream>>>(int(shapes.size()), total, reinterpret_cast<const SdfShape*>(dshapes.p), dlat.p,
+                                                        origin[0], origin[1], origin[2], resolution, nx, ny, nz, occ.p);
+    if (check_launch(e, "k_sdf_mark")) return 1;
+  }
+  const bool u8 = cap * cap < 256;
+  CUDA_TRY(e.vox.alloc(cells * (u8 ? 1 : 2)));
+  const unsigned egrid = unsigned(std::min<size_t>((cells + 255) / 256, size_t(148) * 64));
+  begin_launch(e);
+  k_edt_pass<0, uint16_t><<<egrid, 256, 0, e.stream>>>(nx, ny, nz, cap, occ.p, g1.p);
+  if (check_launch(e, "k_edt_pass")) return 1;
+  begin_launch(e);
+  k_edt_pass<1, uint16_t><<<egrid, 256, 0, e.stream>>>(nx, ny, nz, cap, g1.p, g2.p);
+  if (check_launch(e, "k_edt_pass")) return 1;
+  begin_launch(e);
+  if (u8) k_edt_pass<2, uint8_t><<<egrid, 256, 0, e.stream>>>(nx, ny, nz, cap, g2.p, reinterpret_cast<uint8_t*>(e.vox.p));
+  else k_edt_pass<2, uint16_t><<<egrid, 256, 0, e.stream>>>(nx, ny, nz, cap, g2.p, reinterpret_cast<uint16_t*>(e.vox.p));
+  if (check_launch(e, "k_edt_pass")) return 1;
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  e.sdf.vox = e.vox.p;
+  e.sdf.nx = nx; e.sdf.ny = ny; e.sdf.nz = nz;
+  e.sdf.dtype = u8 ? STOMP_VOXEL_U8_SQ : STOMP_VOXEL_U16_SQ;
+  for (int i = 0; i < 3; ++i) e.sdf.origin[i] = origin[i];
+  e.sdf.res = resolution;
+  e.sdf.inv_res = 1.0 / resolution;
+  if (e.f32 ? upload_sqrt_table<float>(e) : upload_sqrt_table<double>(e)) return 1;
+  e.have_sdf = true;
+  return 0;
+}
+
+int stomp_engine_get_sdf(void* h, int32_t dims[3], int32_t* voxel_dtype, void* voxels, size_t bytes) {
+  ENGINE_OR_FAIL(h);
+  if (!e.have_sdf) return fail("no distance field has been set");
+  if (dims) { dims[0] = e.sdf.nx; dims[1] = e.sdf.ny; dims[2] = e.sdf.nz; }
+  if (voxel_dtype) *voxel_dtype = e.sdf.dtype;
+  if (voxels) {
+    if (bytes < e.vox.n) return fail("output buffer too small");
+    CUDA_TRY(cudaMemcpyAsync(voxels, e.vox.p, e.vox.n, cudaMemcpyDeviceToHost, e.stream));
+    CUDA_TRY(cudaStreamSynchronize(e.stream));
+  }
+  return 0;
+}
+
 int stomp_engine_set_noise(void* h, const double* noise_stddev, const double* noise_decay) {
   ENGINE_OR_FAIL(h);
   if (!noise_stddev || !noise_decay) return fail("null argument");

@@ -1107,6 +1107,76 @@ __global__ void k_track_best(int iteration, int max_after_collision_free, int DN
     for (int i = threadIdx.x; i < DN; i += blockDim.x) best[size_t(b) * DN + i] = trajectory[size_t(b) * DN + i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Distance-field construction (StompCollisionSpace::setStartState, src/stomp_collision_space.cpp:154-297).
+//   k_sdf_mark  : one thread per lattice point of a collision object -> world point -> cell -> occupancy
+//   k_edt_pass  : separable exact squared Euclidean distance transform with the reference's cap, one axis per pass
+// ---------------------------------------------------------------------------------------------
+struct SdfShape {      // one box or cylinder, lattice coordinates pre-accumulated on the host like the reference's loops
+  double position[3];
+  double R[9];         // KDL::Rotation::Quaternion(x, y, z, w)
+  double radius;       // > 0: cylinder test sqrt(xdist^2 + ydist^2) <= radius
+  int nx, ny, nz;      // lattice counts
+  int x_off, y_off, z_off;  // offsets into the lattice coordinate array
+  long long first;     // index of the shape's first lattice point
+};
+
+__global__ void k_sdf_mark(int num_shapes, long long total, const SdfShape* __restrict__ shapes, const double* __restrict__ lattice,
+                           double ox, double oy, double oz, double res, int nx, int ny, int nz, uint8_t* __restrict__ occ) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = num_shapes - 1;
+    while (lo < hi) {   // last shape whose first point is <= i
+      int mid = (lo + hi + 1) >> 1;
+      if (shapes[mid].first <= i) lo = mid; else hi = mid - 1;
+    }
+    const SdfShape& s = shapes[lo];
+    long long k = i - s.first;
+    const int iz = int(k % s.nz); k /= s.nz;
+    const int iy = int(k % s.ny);
+    const int ix = int(k / s.ny);
+    const double x = lattice[s.x_off + ix], y = lattice[s.y_off + iy], z = lattice[s.z_off + iz];
+    if (s.radius > 0.0) {
+      const double xdist = fabs(s.position[0] - x), ydist = fabs(s.position[1] - y);
+      if (!(sqrt(xdist * xdist + ydist * ydist) <= s.radius)) continue;
+    }
+    const double px = s.position[0] - x, py = s.position[1] - y, pz = s.position[2] - z;
+    const double wx = s.R[0] * px + s.R[1] * py + s.R[2] * pz + s.position[0];
+    const double wy = s.R[3] * px + s.R[4] * py + s.R[5] * pz + s.position[1];
+    const double wz = s.R[6] * px + s.R[7] * py + s.R[8] * pz + s.position[2];
+    const double tx = (wx - ox) / res, ty = (wy - oy) / res, tz = (wz - oz) / res;
+    if (!(fabs(tx) < 1e9 && fabs(ty) < 1e9 && fabs(tz) < 1e9)) continue;
+    const int cx = int(round(tx)), cy = int(round(ty)), cz = int(round(tz));
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= nx || cy >= ny || cz >= nz) continue;
+    occ[(size_t(cx) * ny + cy) * nz + cz] = 1;
+  }
+}
+
+// axis: 0 = x (input: occupancy u8 -> d^2 along x), 1 = y, 2 = z (inputs: u16 partial squared distances).
+// out[v] = min over |k| <= cap of in[v + k along axis] + k^2, saturated at cap^2 (kInf marks "nothing within cap").
+template <int kAxis, typename Out>
+__global__ void k_edt_pass(int nx, int ny, int nz, int cap, const void* __restrict__ in_, Out* __restrict__ out) {
+  const unsigned kInf = 0xffffu;
+  const size_t cells = size_t(nx) * ny * nz;
+  const unsigned cap2 = unsigned(cap) * unsigned(cap);
+  for (size_t v = size_t(blockIdx.x) * blockDim.x + threadIdx.x; v < cells; v += size_t(gridDim.x) * blockDim.x) {
+    const int z = int(v % nz), y = int((v / nz) % ny), x = int(v / (size_t(nz) * ny));
+    const int c = kAxis == 0 ? x : (kAxis == 1 ? y : z);
+    const int n = kAxis == 0 ? nx : (kAxis == 1 ? ny : nz);
+    const size_t stride = kAxis == 0 ? size_t(ny) * nz : (kAxis == 1 ? size_t(nz) : 1);
+    unsigned best = kInf;
+    const int k0 = max(-cap, -c), k1 = min(cap, n - 1 - c);
+    for (int k = k0; k <= k1; ++k) {
+      const size_t u = v + (long long)k * (long long)stride;
+      unsigned val;
+      if (kAxis == 0) val = static_cast<const uint8_t*>(in_)[u] ? 0u : kInf;
+      else val = static_cast<const uint16_t*>(in_)[u];
+      if (val != kInf) best = min(best, val + unsigned(k * k));
+    }
+    if (kAxis == 2) out[v] = Out(min(best, cap2));
+    else out[v] = Out(best > cap2 ? kInf : best);
+  }
+}
+
 // theta += updates  (Policy::updateParameters for caller-supplied updates)
 __global__ void k_axpy(size_t n, const double* __restrict__ x, double* __restrict__ y) {
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;

@@ -28,6 +28,7 @@ EXPORTS = [
     "stomp_engine_get", "stomp_engine_launch_count", "stomp_engine_stream", "stomp_engine_timer_start",
     "stomp_engine_timer_stop", "stomp_engine_shard_buffers", "stomp_engine_iterate_sharded_phase",
     "stomp_engine_set_profiling", "stomp_engine_get_profile", "stomp_engine_optimize",
+    "stomp_engine_build_sdf", "stomp_engine_get_sdf",
 ]
 
 
@@ -99,6 +100,27 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    # ---- distance field construction -----------------------------------------------------
+    def build_sdf(self, size, origin, resolution, max_distance, boxes=(), cylinders=()):
+        """boxes: (position, quaternion xyzw, dimensions); cylinders: (position, quaternion, radius, height)."""
+        cb = (_abi.Box * max(1, len(boxes)))()
+        for i, (p, q, d) in enumerate(boxes):
+            cb[i].position[:], cb[i].orientation[:], cb[i].dimensions[:] = p, q, d
+        cc = (_abi.Cylinder * max(1, len(cylinders)))()
+        for i, (p, q, r, hgt) in enumerate(cylinders):
+            cc[i].position[:], cc[i].orientation[:] = p, q
+            cc[i].radius, cc[i].height = r, hgt
+        self._ck(self.L.stomp_engine_build_sdf(self.h, (C.c_double * 3)(*size), (C.c_double * 3)(*origin), C.c_double(resolution),
+                                               C.c_double(max_distance), cb, len(boxes), cc, len(cylinders)))
+
+    def get_sdf(self):
+        dims = (C.c_int32 * 3)()
+        dt = C.c_int32()
+        self._ck(self.L.stomp_engine_get_sdf(self.h, dims, C.byref(dt), None, 0))
+        out = np.empty(tuple(dims), dtype={_abi.VOXEL_U8_SQ: np.uint8, _abi.VOXEL_U16_SQ: np.uint16, _abi.VOXEL_F32: np.float32}[dt.value])
+        self._ck(self.L.stomp_engine_get_sdf(self.h, dims, C.byref(dt), out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes)))
+        return out, dt.value
 
     # ---- policy -------------------------------------------------------------------------
     def set_problems(self, start, goal):

@@ -391,3 +391,44 @@ def test_optimize_outer_loop_matches_host_bookkeeping():
         if has:
             ok = res["success"] == 1
             assert np.all(res["best_trajectory"][ok, d] <= hi + 1e-4) and np.all(res["best_trajectory"][ok, d] >= lo - 1e-4)
+
+
+def test_distance_field_construction_bit_exact():
+    """stomp_engine_build_sdf (lattice rasterisation + exact EDT on the GPU) against the NumPy/SciPy restatement of
+    StompCollisionSpace::addCollisionObjectsToPoints + the capped squared distance transform: integer work, bit-exact."""
+    from oracle import sdf_builder
+    sc = scenes.make_scenario("tiny", num_problems=2)
+    eng = _engine(sc)
+    ident = (0.0, 0.0, 0.0, 1.0)
+    yaw = (0.0, 0.0, np.sin(0.35), np.cos(0.35))
+    tilt = (np.sin(0.2) * 0.6, np.sin(0.2) * 0.8, 0.0, np.cos(0.2))
+    boxes = [((0.8, -0.1, 0.015), ident, (0.4, 1.2, 0.03)), ((0.8, -0.685, 0.8), ident, (0.4, 0.03, 1.6)),
+             ((0.3, 0.6, 0.9), yaw, (0.25, 0.1, 0.3)), ((-0.45, -1.45, 1.0), tilt, (0.3, 0.3, 0.3))]   # last one pokes out of the grid
+    cyls = [((0.62, -0.62, 0.6), ident, 0.1, 1.2), ((0.2, 0.2, 0.4), tilt, 0.07, 0.5)]
+    spec = dict(size=(2.0, 3.0, 2.2), origin=(-0.5, -1.5, -0.3), resolution=0.015, max_distance=0.17)
+    eng.build_sdf(boxes=boxes, cylinders=cyls, **spec)
+    got, dtype = eng.get_sdf()
+    want, occ = sdf_builder.build(boxes=boxes, cylinders=cyls, **spec)
+    assert dtype == _abi.VOXEL_U8_SQ and got.shape == want.shape == (133, 200, 146)
+    assert occ.sum() > 10000
+    np.testing.assert_array_equal(got, want)
+    # the rebuilt field is the one the cost plugin now uses
+    sc2 = scenes.make_scenario("tiny", num_problems=2)
+    sc2.sdf = scenes.DistanceField(want, spec["origin"], spec["resolution"], _abi.VOXEL_U8_SQ)
+    ors = _oracles(sc2)
+    params = _noisy_rollouts(sc2, ors, np.random.default_rng(2), 3)
+    costs, cf = eng.execute(params)
+    for b, o in enumerate(ors):
+        oc, ocf = o.execute(params[b])
+        assert_close(costs[b], oc, RTOL_F64, "state costs on the rebuilt field")
+        np.testing.assert_array_equal(cf[b], ocf)
+    # a coarse cap that needs u16 voxels, and an empty scene
+    eng.build_sdf(size=(1.0, 1.0, 1.0), origin=(0, 0, 0), resolution=0.02, max_distance=0.5, boxes=[((0.5, 0.5, 0.5), ident, (0.1, 0.1, 0.1))])
+    got, dtype = eng.get_sdf()
+    want, _ = sdf_builder.build(size=(1.0, 1.0, 1.0), origin=(0, 0, 0), resolution=0.02, max_distance=0.5,
+                                boxes=[((0.5, 0.5, 0.5), ident, (0.1, 0.1, 0.1))])
+    assert dtype == _abi.VOXEL_U16_SQ
+    np.testing.assert_array_equal(got, want)
+    eng.build_sdf(size=(0.5, 0.5, 0.5), origin=(0, 0, 0), resolution=0.02, max_distance=0.17)
+    got, _ = eng.get_sdf()
+    assert np.all(got == 81)
