@@ -288,12 +288,16 @@ def run_engine(args):
         base = np.einsum("ij,...j->...i", L, z) * 2.0
         eps_np[...] = np.resize(base, eps_np.shape)
 
+        cost_np, cf_np = np.empty(B), np.empty(B, dtype=np.int32)
+        eng.inject_noise_async(eps_np)              # noise of the first timed step
+
         def e2e_step(i):
-            eng.inject_noise(eps_np)
-            eng.iterate(i)
-            eng.get_parameters(theta_np)
-        h2d, api = int(eps_np.nbytes + 8 * D), ("stomp_engine_inject_noise(pinned eps) + stomp_engine_iterate(stats) + "
-                                                "stomp_engine_get_parameters(pinned)")
+            eng.iterate(i, stats=False)             # consumes the pending injection (device-side wait on the copy)
+            eng.inject_noise_async(eps_np)          # next step's noise: H2D on the copy stream, overlaps this iteration
+            eng.last_stats(cost_np, cf_np)          # D2H of the noise-less cost / collision flag of every problem
+            eng.get_parameters(theta_np)            # D2H of the updated trajectories
+        h2d, api = int(eps_np.nbytes + 8 * D), ("stomp_engine_iterate + stomp_engine_inject_noise_async(pinned eps of the next "
+                                                "step) + stomp_engine_last_stats + stomp_engine_get_parameters(pinned)")
     else:
         def e2e_step(i):
             eng_iterate(i)

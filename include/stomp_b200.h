@@ -216,6 +216,11 @@ int stomp_engine_seed(void* engine, uint64_t seed);
  * engine RNG (already scaled by the noise stddev, i.e. Rollout::noise_).  n = rollouts per problem
  * supplied (>= the number generated that iteration). */
 int stomp_engine_inject_noise(void* engine, const double* eps, int32_t n);
+/* Same, but the host->device copy runs on the handle's copy stream and the call returns at once: the next get_rollouts /
+ * iterate waits for it on the device.  Two device buffers alternate, so the noise of iteration i+1 can be uploaded
+ * while iteration i computes.  eps must stay valid (and should be pinned) until the copy has been consumed or
+ * stomp_engine_synchronize returns.  At most one injection can be pending. */
+int stomp_engine_inject_noise_async(void* engine, const double* eps, int32_t n);
 /* Draw the engine's own standard normals z[B][n][D][N] (iteration, global rollout id keyed Philox)
  * without touching engine state: statistical validation of the RNG against N(0, R^-1). */
 int stomp_engine_sample_noise(void* engine, int32_t iteration, int32_t n, double* eps_out /* [B][n][D][N], unit stddev */);
@@ -256,6 +261,9 @@ int stomp_engine_iterate(void* engine, int32_t iteration_number, stomp_iter_stat
 /* iterations first..first+count-1 back to back on the device, no host round trip in between. */
 int stomp_engine_run(void* engine, int32_t first_iteration, int32_t count, stomp_iter_stats* last_stats);
 int stomp_engine_synchronize(void* engine);
+/* Results of the last iteration's noise-less rollout (what stomp_engine_iterate returns through `stats`), for callers
+ * that launched the iteration with stats == NULL; waits for the iteration to finish. */
+int stomp_engine_last_stats(void* engine, stomp_iter_stats* stats);
 
 /* StompOptimizer::optimize, STOMP branch (src/stomp_optimizer.cpp:284-359,368-400), for every problem of the batch with
  * the bookkeeping on the device: per iteration the noise-less rollout's cost / collision flag update

@@ -63,8 +63,10 @@ struct Engine {
   stomp_engine_desc desc;
   int B = 0, D = 0, N = 0, R = 0, Rre = 0, K = 0;
   int device = 0, num_sms = 148;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_copy_done[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  int inject_write = 0, inject_pending_buf = 0;
   int64_t launches = 0;
   bool f32 = false;
 
@@ -88,7 +90,7 @@ struct Engine {
   DevBuf<double> noise, control, cumulative, totals;
   DevBuf<double> noise_projected, probabilities, clipped;      // taps (keep_intermediates)
   DevBuf<double> extra_state, extra_control, updates, noiseless_sum;
-  DevBuf<double> eps_in;
+  DevBuf<double> eps_in2[2];   // injected noise, double buffered (async uploads overlap the previous iteration)
   DevBuf<int> reuse_src, collision_free;
   DevBuf<double> band_fw, band_bw, proj_scale, qinv_t, noise_scale;
   DevBuf<double> limit_min, limit_max;
@@ -221,7 +223,7 @@ GenArgs base_gen_args(Engine& e) {
   a.rollouts_global = int64_t(e.desc.rollout_shard_world) * e.R;
   a.theta = e.theta.p; a.pad_start = e.pad_start.p; a.pad_goal = e.pad_goal.p;
   a.noise_scale = e.noise_scale.p;
-  a.eps_in = e.eps_in.p;
+  a.eps_in = e.eps_in2[e.inject_pending_buf].p;
   a.params_prev = e.params[1 - e.cur].p;
   a.reuse_src = e.reuse_src.p;
   a.noise = e.noise.p;
@@ -409,8 +411,12 @@ int step_get_rollouts(Engine& e, int iteration_number, bool with_control) {
   (void)iteration_number;
   a.iteration = ++e.generation;
   a.control_weight = 0.5 * e.control_cost_weight;
+  const bool injected = e.injected_pending;
   e.injected_pending = false;
-  return launch_generate(e, a);
+  if (injected) CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_copy_done[e.inject_pending_buf], 0));
+  if (launch_generate(e, a)) return 1;
+  if (injected) CUDA_TRY(cudaEventRecord(e.ev_consumed[e.inject_pending_buf], e.stream));
+  return 0;
 }
 
 __global__ void k_gather_state(int R, int R_gen, int N, const int* __restrict__ reuse_src, const double* __restrict__ prev,
@@ -574,6 +580,11 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   if ((c = cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
   if ((c = cudaDeviceGetAttribute(&e.num_sms, cudaDevAttrMultiProcessorCount, e.device)) != cudaSuccess) return bail(c, "cudaDeviceGetAttribute");
   if ((c = cudaEventCreate(&e.ev0)) != cudaSuccess || (c = cudaEventCreate(&e.ev1)) != cudaSuccess) return bail(c, "cudaEventCreate");
+  if ((c = cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
+  for (int i = 0; i < 2; ++i)
+    if ((c = cudaEventCreateWithFlags(&e.ev_copy_done[i], cudaEventDisableTiming)) != cudaSuccess ||
+        (c = cudaEventCreateWithFlags(&e.ev_consumed[i], cudaEventDisableTiming)) != cudaSuccess)
+      return bail(c, "cudaEventCreate");
   const size_t BDN = size_t(e.B) * e.D * e.N, BRDN = BDN * e.R, BRN = size_t(e.B) * e.R * e.N;
 #define ALLOC(buf, n) if ((c = (buf).alloc(n)) != cudaSuccess) return bail(c, "cudaMalloc " #buf)
   ALLOC(e.theta, BDN); ALLOC(e.pad_start, size_t(e.B) * e.D); ALLOC(e.pad_goal, size_t(e.B) * e.D);
@@ -628,6 +639,11 @@ int stomp_engine_destroy(void* h) {
   Engine* e = E(h);
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+  for (int i = 0; i < 2; ++i) {
+    if (e->ev_copy_done[i]) cudaEventDestroy(e->ev_copy_done[i]);
+    if (e->ev_consumed[i]) cudaEventDestroy(e->ev_consumed[i]);
+  }
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   for (cudaEvent_t ev : e->prof_a) cudaEventDestroy(ev);
@@ -873,14 +889,27 @@ int stomp_engine_seed(void* h, uint64_t seed) {
   return 0;
 }
 
-int stomp_engine_inject_noise(void* h, const double* eps, int32_t n) {
+int stomp_engine_inject_noise_async(void* h, const double* eps, int32_t n) {
   ENGINE_OR_FAIL(h);
   if (!eps || n < 1 || n > e.R) return fail("bad argument");
-  if (e.eps_in.n != size_t(e.B) * e.R * e.D * e.N) CUDA_TRY(e.eps_in.alloc(size_t(e.B) * e.R * e.D * e.N));
+  const int buf = e.inject_write;
+  e.inject_write ^= 1;
+  const size_t count = size_t(e.B) * e.R * e.D * e.N;
+  if (e.eps_in2[buf].n != count) CUDA_TRY(e.eps_in2[buf].alloc(count));
+  // the buffer was last read by the k_generate two injections ago: do not overwrite it before that launch is done
+  CUDA_TRY(cudaStreamWaitEvent(e.copy_stream, e.ev_consumed[buf], 0));
   size_t row = size_t(n) * e.D * e.N * 8;
-  CUDA_TRY(cudaMemcpy2DAsync(e.eps_in.p, size_t(e.R) * e.D * e.N * 8, eps, row, row, e.B, cudaMemcpyHostToDevice, e.stream));
-  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  CUDA_TRY(cudaMemcpy2DAsync(e.eps_in2[buf].p, size_t(e.R) * e.D * e.N * 8, eps, row, row, e.B, cudaMemcpyHostToDevice, e.copy_stream));
+  CUDA_TRY(cudaEventRecord(e.ev_copy_done[buf], e.copy_stream));
+  e.inject_pending_buf = buf;
   e.injected_pending = true;
+  return 0;
+}
+
+int stomp_engine_inject_noise(void* h, const double* eps, int32_t n) {
+  if (stomp_engine_inject_noise_async(h, eps, n)) return 1;
+  Engine& e = *E(h);
+  CUDA_TRY(cudaStreamSynchronize(e.copy_stream));
   return 0;
 }
 
@@ -1045,8 +1074,14 @@ int stomp_engine_optimize(void* h, int32_t max_iterations, int32_t max_after_cf,
 
 int stomp_engine_synchronize(void* h) {
   ENGINE_OR_FAIL(h);
+  CUDA_TRY(cudaStreamSynchronize(e.copy_stream));
   CUDA_TRY(cudaStreamSynchronize(e.stream));
   return 0;
+}
+
+int stomp_engine_last_stats(void* h, stomp_iter_stats* stats) {
+  ENGINE_OR_FAIL(h);
+  return fill_stats(e, stats);
 }
 
 int stomp_engine_get(void* h, int32_t field, void* out, size_t bytes) {

@@ -28,7 +28,7 @@ EXPORTS = [
     "stomp_engine_get", "stomp_engine_launch_count", "stomp_engine_stream", "stomp_engine_timer_start",
     "stomp_engine_timer_stop", "stomp_engine_shard_buffers", "stomp_engine_iterate_sharded_phase",
     "stomp_engine_set_profiling", "stomp_engine_get_profile", "stomp_engine_optimize",
-    "stomp_engine_build_sdf", "stomp_engine_get_sdf",
+    "stomp_engine_build_sdf", "stomp_engine_get_sdf", "stomp_engine_inject_noise_async", "stomp_engine_last_stats",
 ]
 
 
@@ -154,6 +154,19 @@ class Engine:
         e = eps if (isinstance(eps, np.ndarray) and eps.dtype == np.float64 and eps.flags.c_contiguous) else _f64(eps)
         assert e.shape[0] == self.B and e.shape[2:] == (self.D, self.N)
         self._ck(self.L.stomp_engine_inject_noise(self.h, _dp(e), e.shape[1]))
+
+    def inject_noise_async(self, eps):
+        """eps must be a C-contiguous float64 array that stays alive (ideally pinned) until it has been consumed."""
+        assert isinstance(eps, np.ndarray) and eps.dtype == np.float64 and eps.flags.c_contiguous
+        assert eps.shape[0] == self.B and eps.shape[2:] == (self.D, self.N)
+        self._ck(self.L.stomp_engine_inject_noise_async(self.h, _dp(eps), eps.shape[1]))
+
+    def last_stats(self, cost=None, cf=None):
+        cost = np.empty(self.B) if cost is None else cost
+        cf = np.empty(self.B, dtype=np.int32) if cf is None else cf
+        st = _abi.IterStats(_dp(cost), _ip(cf), 0, 0)
+        self._ck(self.L.stomp_engine_last_stats(self.h, C.byref(st)))
+        return cost, cf
 
     def sample_noise(self, iteration, n):
         out = np.empty((self.B, n, self.D, self.N))

@@ -432,3 +432,28 @@ def test_distance_field_construction_bit_exact():
     eng.build_sdf(size=(0.5, 0.5, 0.5), origin=(0, 0, 0), resolution=0.02, max_distance=0.17)
     got, _ = eng.get_sdf()
     assert np.all(got == 81)
+
+
+def test_async_injection_pipeline_equals_synchronous():
+    """inject_noise_async of step i+1 issued while step i computes (two alternating device buffers) gives exactly the
+    results of the synchronous injection."""
+    sc = scenes.make_scenario("tiny", num_problems=3)
+    a, b = _engine(sc), _engine(sc)
+    rng = np.random.default_rng(17)
+    L = np.linalg.cholesky(a.get(_abi.FIELD_INV_CONTROL_COST))
+    D = sc.robot.num_dimensions
+    its = 6
+    eps = [np.ascontiguousarray(correlated_noise(L, rng, (3, sc.num_rollouts if it == 0 else sc.num_rollouts - sc.num_reused_rollouts),
+                                                 np.full(D, 2.0))) for it in range(its)]
+    for it in range(its):
+        a.inject_noise(eps[it])
+        ca, fa, _ = a.iterate(it + 1)
+    b.inject_noise_async(eps[0])
+    for it in range(its):
+        b.iterate(it + 1, stats=False)
+        if it + 1 < its:
+            b.inject_noise_async(eps[it + 1])
+        cb, fb = b.last_stats()
+    np.testing.assert_array_equal(ca, cb)
+    np.testing.assert_array_equal(fa, fb)
+    np.testing.assert_array_equal(a.get_parameters(), b.get_parameters())
