@@ -205,6 +205,9 @@ def run_engine(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION/INFO; stdout must carry the JSON line only
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
