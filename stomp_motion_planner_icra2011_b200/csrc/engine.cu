@@ -341,7 +341,8 @@ int launch_update(Engine& e, int apply, bool fuse_extra_control) {
   const int groups = (e.D + dpc - 1) / dpc;
   CUDA_TRY(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   begin_launch(e);
-  k_update<<<unsigned(e.B) * groups, std::min(256, ((dpc * e.N + 31) / 32) * 32), smem, e.stream>>>(a);
+  static const int tpb_max = getenv("STOMP_UPDATE_TPB") ? atoi(getenv("STOMP_UPDATE_TPB")) : 128;  // A/B on B200: 64:0.163 128:0.097 256:0.150 512:0.244 ms
+  k_update<<<unsigned(e.B) * groups, std::min(tpb_max, ((dpc * e.N + 31) / 32) * 32), smem, e.stream>>>(a);
   return check_launch(e, "k_update");
 }
 
