@@ -588,6 +588,42 @@ __device__ __forceinline__ float shfl_rel(float v, int delta) {
   return delta < 0 ? __shfl_up_sync(0xffffffffu, v, unsigned(-delta)) : __shfl_down_sync(0xffffffffu, v, unsigned(delta));
 }
 
+// Explicit 32-bit shared-memory addressing for the per-sphere hot loop: the tables live at run-time offsets of the
+// dynamic shared segment, and with generic pointers ptxas re-derived the shared window base (S2UR/ULEA) at almost every
+// access (14 % of k_cost's issued instructions, ncu source page); a 32-bit .shared address needs none of that.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void lds2(unsigned addr, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+}
+__device__ __forceinline__ double lds1(unsigned addr, double) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds1(unsigned addr, float) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts1(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts1(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
+// one collision sphere from the shared table (layout of DevSphere<Real>)
+struct SphereRegsD { double s0, s1, s2, radius, clearance, inv_clearance; };
+struct SphereRegsF { float s0, s1, s2, radius, clearance, inv_clearance; };
+__device__ __forceinline__ void load_sphere(unsigned addr, SphereRegsD& r) {
+  lds2(addr, r.s0, r.s1);
+  lds2(addr + 16, r.s2, r.radius);
+  lds2(addr + 32, r.clearance, r.inv_clearance);
+}
+__device__ __forceinline__ void load_sphere(unsigned addr, SphereRegsF& r) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.s0), "=f"(r.s1), "=f"(r.s2), "=f"(r.radius) : "r"(addr));
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.clearance), "=f"(r.inv_clearance) : "r"(addr + 16));
+}
+template <typename Real> struct SphereRegsOf;
+template <> struct SphereRegsOf<double> { typedef SphereRegsD type; };
+template <> struct SphereRegsOf<float> { typedef SphereRegsF type; };
+
 // distance_field VoxelGrid::getCellFromLocation: int(round((loc - origin) / resolution)), and the 1-cell margin
 // test of getDistanceGradient.  Fast path (fp64): t = pos/res - origin/res as one DFMA, then t + 1.5*2^36 puts
 // t as Q16.16 fixed point into the low mantissa word: cell = (lo + 0x8000) >> 16 and the distance to the
@@ -652,8 +688,9 @@ __device__ __forceinline__ bool voxel_cells(const GridF& g, float px, float py, 
 
 // distance of one voxel: PropagationDistanceField::getDistance = sqrt_table[d^2] (u8 / u16 grids) or metres (f32)
 template <typename Real, int kVox>
-__device__ __forceinline__ Real voxel_distance(const void* vox, int idx, const Real* sqrt_tab, Real res) {
-  if (kVox == STOMP_VOXEL_U8_SQ) return sqrt_tab[__ldg(static_cast<const uint8_t*>(vox) + idx)];
+__device__ __forceinline__ Real voxel_distance(const void* vox, int idx, unsigned sqrt_tab_addr, Real res) {
+  if (kVox == STOMP_VOXEL_U8_SQ)
+    return lds1(sqrt_tab_addr + unsigned(__ldg(static_cast<const uint8_t*>(vox) + idx)) * unsigned(sizeof(Real)), Real(0));
   if (kVox == STOMP_VOXEL_U16_SQ) return Math<Real>::sqrt_(Real(__ldg(static_cast<const uint16_t*>(vox) + idx))) * res;
   return Real(__ldg(static_cast<const float*>(vox) + idx));
 }
@@ -679,7 +716,9 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   // per-warp velocity frame [12][32]: kept in shared memory so that the register file holds only one frame
-  Real* Vs = sqrt_tab + 256 + size_t(warp) * 12 * 32 + lane;
+  const unsigned vs_addr = smem_u32(sqrt_tab + 256 + size_t(warp) * 12 * 32 + lane);
+  const unsigned sph_addr = smem_u32(spheres), tab_addr = smem_u32(sqrt_tab);
+  constexpr unsigned kVsStride = 32 * sizeof(Real);
   // robot tables: asynchronous 16-byte copies, all in flight together (waited for with the first trajectory)
   cta_copy_async16(nodes, a.nodes, int(sizeof(DevNode<Real>)) * a.num_nodes);
   cta_copy_async16(spheres, a.spheres, int(sizeof(DevSphere<Real>)) * K);
@@ -810,15 +849,17 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
           // lazily, only when some lane of the warp has a sphere of this link inside its clearance band
           bool haveV = false;
           for (int j = sph_begin; j < sph_end; ++j) {
-            const DevSphere<Real>& sp = spheres[j];
-            const Real s0 = sp.pos[0], s1 = sp.pos[1], s2 = sp.pos[2];
+            const unsigned sa = sph_addr + unsigned(j) * unsigned(sizeof(DevSphere<Real>));
+            typename SphereRegsOf<Real>::type sp;
+            load_sphere(sa, sp);
+            const Real s0 = sp.s0, s1 = sp.s1, s2 = sp.s2;
             const Real px = F[0] * s0 + F[1] * s1 + F[2] * s2 + F[9];
             const Real py = F[3] * s0 + F[4] * s1 + F[5] * s2 + F[10];
             const Real pz = F[6] * s0 + F[7] * s1 + F[8] * s2 + F[11];
             int cx, cy, cz;
             const bool inside = voxel_cells(g, px, py, pz, cx, cy, cz);
             // outside the grid (or within one cell of its faces) the reference returns distance 0
-            const Real dist = inside ? voxel_distance<Real, kVox>(vox, (cx * g.sny + cy) * g.snz + cz, sqrt_tab, g.res) : Real(0);
+            const Real dist = inside ? voxel_distance<Real, kVox>(vox, (cx * g.sny + cy) * g.snz + cz, tab_addr, g.res) : Real(0);
             // three-piece potential (stomp_collision_space.h:209-226), branch-free
             const Real radius = sp.radius, clearance = sp.clearance;
             const Real dd = dist - radius, diff = dd - clearance;
@@ -832,19 +873,22 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
               if (!haveV) {
 #pragma unroll
                 for (int i = 0; i < 12; ++i)
-                  Vs[i * 32] = c_m1 * shfl_rel(F[i], -1) + c_0 * F[i] + c_p1 * shfl_rel(F[i], 1) + c_p2 * shfl_rel(F[i], 2);
+                  sts1(vs_addr + i * kVsStride, c_m1 * shfl_rel(F[i], -1) + c_0 * F[i] + c_p1 * shfl_rel(F[i], 1) + c_p2 * shfl_rel(F[i], 2));
                 haveV = true;
               }
-              const Real vx = Vs[0 * 32] * s0 + Vs[1 * 32] * s1 + Vs[2 * 32] * s2 + Vs[9 * 32];
-              const Real vy = Vs[3 * 32] * s0 + Vs[4 * 32] * s1 + Vs[5 * 32] * s2 + Vs[10 * 32];
-              const Real vz = Vs[6 * 32] * s0 + Vs[7 * 32] * s1 + Vs[8 * 32] * s2 + Vs[11 * 32];
+              Real V[12];
+#pragma unroll
+              for (int i = 0; i < 12; ++i) V[i] = lds1(vs_addr + i * kVsStride, Real(0));
+              const Real vx = V[0] * s0 + V[1] * s1 + V[2] * s2 + V[9];
+              const Real vy = V[3] * s0 + V[4] * s1 + V[5] * s2 + V[10];
+              const Real vz = V[6] * s0 + V[7] * s1 + V[8] * s2 + V[11];
               vm = Math<Real>::sqrt_(vx * vx + vy * vy + vz * vz);
-              cost += sp.weight * (pot * vm);
+              cost += lds1(sa + 6 * unsigned(sizeof(Real)), Real(0)) * (pot * vm);   // DevSphere::weight
             }
             if (kDebug) {
               if (t >= -1 && t <= N + 1 && (lane >= 1 && lane <= kTileSteps || (tile == 0 && lane == 0) ||
                                              (tile == ntiles - 1 && lane > kTileSteps))) {
-                stomp_sphere_debug& rec = a.debug[size_t(t + 1) * K + sp.original_index];
+                stomp_sphere_debug& rec = a.debug[size_t(t + 1) * K + spheres[j].original_index];
                 rec.voxel[0] = cx; rec.voxel[1] = cy; rec.voxel[2] = cz;
                 rec.in_collision = hit;
                 rec.position[0] = px; rec.position[1] = py; rec.position[2] = pz;
