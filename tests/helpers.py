@@ -23,7 +23,7 @@ def assert_close(actual, desired, rtol, what, atol_scale=1e-9):
     actual, desired = np.asarray(actual), np.asarray(desired)
     assert actual.shape == desired.shape, (what, actual.shape, desired.shape)
     scale = float(np.max(np.abs(desired))) if desired.size else 0.0
-    np.testing.assert_allclose(actual, desired, rtol=rtol, atol=atol_scale * max(scale, 1e-300) + 1e-300, err_msg=what)
+    np.testing.assert_allclose(actual, desired, rtol=rtol, atol=atol_scale * scale + 1e-20, err_msg=what)   # 1e-20: rounding dust of exactly-zero quantities
 
 
 def oracle_batch(oracle_mod, sc):

@@ -457,3 +457,84 @@ def test_async_injection_pipeline_equals_synchronous():
     np.testing.assert_array_equal(ca, cb)
     np.testing.assert_array_equal(fa, fb)
     np.testing.assert_array_equal(a.get_parameters(), b.get_parameters())
+
+
+@pytest.mark.parametrize("N,R,reuse", [(2, 2, 0), (5, 3, 1), (7, 1, 0), (33, 4, 3), (29, 5, 0), (30, 16, 15), (58, 17, 2)])
+def test_edge_sizes(N, R, reuse):
+    """shortest trajectories (fewer points than the 7-tap stencil), single rollout, tile-boundary lengths (29/30/58),
+    R on both sides of the register-array sizes; all against the oracle."""
+    sc = scenes.make_scenario("tiny", num_problems=2, num_time_steps=N, num_rollouts=R)
+    sc.num_reused_rollouts = reuse
+    _run_iterations(sc, 3)
+
+
+def test_single_joint_no_spheres_and_static_spheres():
+    """D = 1; a robot without collision spheres (state cost 0); spheres attached to a link no group joint moves."""
+    rng = np.random.default_rng(0)
+    rb = scenes.Robot()
+    base = rb.add_segment("base", -1, _abi.JOINT_FIXED, (0, 0, 0))
+    fixed_link = rb.add_segment("post", base, _abi.JOINT_FIXED, (0.4, -0.3, 0.6))
+    j = rb.add_segment("j0", base, _abi.JOINT_REVOLUTE, (0.2, -0.4, 0.7), (0, 1, 0), group=0)
+    rb.add_segment("tip", j, _abi.JOINT_FIXED, (0.5, 0.0, 0.0))
+    rb.limits = [(1, -1.0, 1.0)]
+    for variant in ("none", "static", "both"):
+        rb.spheres = []
+        if variant in ("static", "both"):
+            rb.spheres.append(dict(segment=fixed_link, radius=0.05, clearance=0.07, pos=(0.0, 0.0, 0.1)))
+        if variant == "both":
+            rb.add_even_spheres(j, 4, 0.04, 0.07)
+        sc = scenes.make_scenario("tiny", num_problems=2)
+        sc.robot = rb
+        sc.start = rng.uniform(-0.9, 0.9, (2, 1)); sc.goal = rng.uniform(-0.9, 0.9, (2, 1))
+        sc.noise_stddev = np.full(1, 2.0); sc.noise_decay = np.full(1, 0.99)
+        eng, ors = _run_iterations(sc, 3)
+        if variant == "none":
+            assert np.all(eng.get(_abi.FIELD_STATE_COSTS) == 0.0)
+
+
+def test_start_state_in_collision_counts_only_in_first_iteration():
+    """the padding points take part in collision_free only while iteration_ == 0 (stomp_optimizer.cpp:624-630)."""
+    sc = scenes.make_scenario("tiny", num_problems=1)
+    eng, ors = _engine(sc), _oracles(sc)
+    # put the start configuration inside the box obstacle: find a colliding configuration by sampling
+    rng = np.random.default_rng(1)
+    theta = ors[0].get_parameters()
+    found = None
+    for _ in range(200):
+        q = sc.robot.sample_configurations(rng, 1)[0]
+        sc2 = scenes.make_scenario("tiny", num_problems=1)
+        sc2.start = q[None]; sc2.goal = sc.goal
+        o = _oracles(sc2)[0]
+        dbg, _ = o.execute_debug(o.get_parameters())
+        if dbg["in_collision"][0].any() and not dbg["in_collision"][6:].any():
+            found = sc2
+            break
+    if found is None:
+        pytest.skip("no start-only collision found")
+    eng, o = _engine(found), _oracles(found)[0]
+    p = o.get_parameters()[None, None]
+    for it in (1, 2):
+        c, cf = eng.execute(p, iteration_number=it)
+        oc, ocf = o.execute(p[0], iteration_number=it)
+        np.testing.assert_array_equal(cf[0], ocf)
+
+
+def test_bad_arguments_are_rejected():
+    import ctypes as C
+    sc = scenes.make_scenario("tiny", num_problems=1)
+    eng = _engine(sc)
+    L = eng.L
+    assert L.stomp_engine_iterate(None, 1, None) != 0 and b"null" in L.stomp_engine_last_error()
+    assert L.stomp_engine_get(eng.h, 999, C.c_void_p(1), C.c_size_t(8)) != 0
+    buf = np.empty(4)
+    assert L.stomp_engine_get(eng.h, _abi.FIELD_THETA, buf.ctypes.data_as(C.c_void_p), C.c_size_t(buf.nbytes)) != 0
+    assert b"too small" in L.stomp_engine_last_error()
+    assert L.stomp_engine_get(eng.h, _abi.FIELD_PROBABILITIES, buf.ctypes.data_as(C.c_void_p), C.c_size_t(1 << 30)) != 0   # tap not kept
+    assert L.stomp_engine_set_sdf(eng.h, None, 10, 10, 10, (C.c_double * 3)(), C.c_double(0.1), 1) != 0
+    bad = scenes.make_scenario("tiny", num_problems=1)
+    bad.robot.segments[3]["parent"] = 7            # not DFS pre-order
+    with pytest.raises(RuntimeError, match="pre-order"):
+        _engine(bad)
+    shard = scenes.make_scenario("tiny", num_problems=2)
+    with pytest.raises(RuntimeError, match="sharding"):
+        _engine(shard, shard_rank=0, shard_world=2)
