@@ -1,0 +1,93 @@
+"""URDF ingestion (StompRobotModel's job) reproduces the hand-written PR2-like joint table and sphere list."""
+import numpy as np
+import pytest
+
+from stomp_motion_planner_icra2011_b200 import _abi, scenes
+from stomp_motion_planner_icra2011_b200.urdf import robot_from_urdf
+
+URDF = """<?xml version="1.0"?>
+<robot name="pr2_like_right_arm">
+  <link name="base_link"/><link name="torso_lift_link"/><link name="r_shoulder_pan_link"/><link name="r_shoulder_lift_link"/>
+  <link name="r_upper_arm_roll_link"/><link name="r_upper_arm_link"/><link name="r_elbow_flex_link"/><link name="r_forearm_roll_link"/>
+  <link name="r_forearm_link"/><link name="r_wrist_flex_link"/><link name="r_wrist_roll_link"/><link name="r_gripper_palm_link"/>
+  <link name="r_gripper_l_finger_link"/><link name="r_gripper_l_finger_tip_link"/><link name="r_gripper_l_finger_tip_frame"/>
+  <link name="r_gripper_r_finger_link"/><link name="r_gripper_r_finger_tip_link"/><link name="r_gripper_r_finger_tip_frame"/>
+  <joint name="torso_lift_joint" type="prismatic"><parent link="base_link"/><child link="torso_lift_link"/>
+    <origin xyz="-0.05 0 0.739675"/><axis xyz="0 0 1"/><limit lower="0" upper="0.31"/></joint>
+  <joint name="r_shoulder_pan_joint" type="revolute"><parent link="torso_lift_link"/><child link="r_shoulder_pan_link"/>
+    <origin xyz="0 -0.188 0"/><axis xyz="0 0 1"/><limit lower="-2.1353981634" upper="0.564601836603"/></joint>
+  <joint name="r_shoulder_lift_joint" type="revolute"><parent link="r_shoulder_pan_link"/><child link="r_shoulder_lift_link"/>
+    <origin xyz="0.1 0 0"/><axis xyz="0 1 0"/><limit lower="-0.3536" upper="1.2963"/></joint>
+  <joint name="r_upper_arm_roll_joint" type="revolute"><parent link="r_shoulder_lift_link"/><child link="r_upper_arm_roll_link"/>
+    <origin xyz="0 0 0"/><axis xyz="1 0 0"/><limit lower="-3.75" upper="0.65"/></joint>
+  <joint name="r_upper_arm_joint" type="fixed"><parent link="r_upper_arm_roll_link"/><child link="r_upper_arm_link"/></joint>
+  <joint name="r_elbow_flex_joint" type="revolute"><parent link="r_upper_arm_link"/><child link="r_elbow_flex_link"/>
+    <origin xyz="0.4 0 0"/><axis xyz="0 1 0"/><limit lower="-2.1213" upper="-0.15"/></joint>
+  <joint name="r_forearm_roll_joint" type="continuous"><parent link="r_elbow_flex_link"/><child link="r_forearm_roll_link"/>
+    <axis xyz="1 0 0"/></joint>
+  <joint name="r_forearm_joint" type="fixed"><parent link="r_forearm_roll_link"/><child link="r_forearm_link"/></joint>
+  <joint name="r_wrist_flex_joint" type="revolute"><parent link="r_forearm_link"/><child link="r_wrist_flex_link"/>
+    <origin xyz="0.321 0 0"/><axis xyz="0 1 0"/><limit lower="-2.0" upper="-0.1"/></joint>
+  <joint name="r_wrist_roll_joint" type="continuous"><parent link="r_wrist_flex_link"/><child link="r_wrist_roll_link"/>
+    <axis xyz="1 0 0"/></joint>
+  <joint name="r_gripper_palm_joint" type="fixed"><parent link="r_wrist_roll_link"/><child link="r_gripper_palm_link"/></joint>
+  <joint name="r_gripper_l_finger_joint" type="revolute"><parent link="r_gripper_palm_link"/><child link="r_gripper_l_finger_link"/>
+    <origin xyz="0.07691 0.01 0"/><axis xyz="0 0 1"/><limit lower="0" upper="0.548"/></joint>
+  <joint name="r_gripper_l_finger_tip_joint" type="revolute"><parent link="r_gripper_l_finger_link"/><child link="r_gripper_l_finger_tip_link"/>
+    <origin xyz="0.09137 0.00495 0"/><axis xyz="0 0 -1"/><limit lower="0" upper="0.548"/></joint>
+  <joint name="r_gripper_l_finger_tip_frame_joint" type="fixed"><parent link="r_gripper_l_finger_tip_link"/><child link="r_gripper_l_finger_tip_frame"/>
+    <origin xyz="0.03 0 0" rpy="0 0 0.1"/></joint>
+  <joint name="r_gripper_r_finger_joint" type="revolute"><parent link="r_gripper_palm_link"/><child link="r_gripper_r_finger_link"/>
+    <origin xyz="0.07691 -0.01 0"/><axis xyz="0 0 -1"/><limit lower="0" upper="0.548"/></joint>
+  <joint name="r_gripper_r_finger_tip_joint" type="revolute"><parent link="r_gripper_r_finger_link"/><child link="r_gripper_r_finger_tip_link"/>
+    <origin xyz="0.09137 -0.00495 0"/><axis xyz="0 0 1"/><limit lower="0" upper="0.548"/></joint>
+  <joint name="r_gripper_r_finger_tip_frame_joint" type="fixed"><parent link="r_gripper_r_finger_tip_link"/><child link="r_gripper_r_finger_tip_frame"/>
+    <origin xyz="0.03 0 0" rpy="0 0 -0.1"/></joint>
+</robot>
+"""
+GROUP = ["r_shoulder_pan_joint", "r_shoulder_lift_joint", "r_upper_arm_roll_joint", "r_elbow_flex_joint", "r_forearm_roll_joint",
+         "r_wrist_flex_joint", "r_wrist_roll_joint"]
+COLLISION_LINKS = {   # config/pr2_both_arms_stomp_config.yaml:3-19 (right arm), in kinematic order
+    "r_upper_arm_link": {"link_radius": 0.10}, "r_forearm_link": {"link_radius": 0.065}, "r_gripper_palm_link": {"link_radius": 0.06},
+    "r_gripper_l_finger_link": {"link_radius": 0.03, "link_extension": 0.01},
+    "r_gripper_l_finger_tip_link": {"link_radius": 0.03, "link_extension": 0.01},
+    "r_gripper_r_finger_link": {"link_radius": 0.03, "link_extension": 0.01},
+    "r_gripper_r_finger_tip_link": {"link_radius": 0.03, "link_extension": 0.01},
+}
+STATE = {"torso_lift_joint": 0.1, "r_gripper_l_finger_joint": 0.25, "r_gripper_l_finger_tip_joint": 0.25,
+         "r_gripper_r_finger_joint": 0.25, "r_gripper_r_finger_tip_joint": 0.25}
+
+
+def test_urdf_reproduces_the_synthetic_arm():
+    got = robot_from_urdf(URDF, GROUP, "base_link", COLLISION_LINKS, 0.07, STATE)
+    want = scenes.pr2_right_arm()
+    assert [g["name"] for g in got.segments] == [g["name"] for g in want.segments]      # DFS pre-order numbering
+    for a, b in zip(got.segments, want.segments):
+        assert (a["parent"], a["type"], a["group"]) == (b["parent"], b["type"], b["group"]), a["name"]
+        np.testing.assert_allclose(a["rot"], b["rot"], atol=1e-15)
+        np.testing.assert_allclose(a["pos"], b["pos"], atol=0)
+        if a["type"] != _abi.JOINT_FIXED:
+            np.testing.assert_allclose(a["axis"], b["axis"], atol=1e-15)
+        assert a["fixed"] == b["fixed"]
+    assert got.limits == want.limits and got.reference_segment == want.reference_segment
+    assert len(got.spheres) == len(want.spheres) == 51
+    for a, b in zip(got.spheres, want.spheres):
+        assert a["segment"] == b["segment"] and a["radius"] == b["radius"] and a["clearance"] == b["clearance"]
+        np.testing.assert_allclose(a["pos"], b["pos"], atol=0)
+
+
+def test_urdf_errors():
+    with pytest.raises(ValueError, match="not in the URDF"):
+        robot_from_urdf(URDF, ["nope"], "base_link")
+    with pytest.raises(ValueError, match="reference frame"):
+        robot_from_urdf(URDF, GROUP, "nope")
+    with pytest.raises(ValueError, match="one root"):
+        robot_from_urdf("<robot><link name='a'/><link name='b'/></robot>", [], "a")
+
+
+def test_urdf_rotated_axis_is_expressed_in_the_parent_frame():
+    urdf = """<robot name="r"><link name="a"/><link name="b"/>
+      <joint name="j" type="revolute"><parent link="a"/><child link="b"/><origin xyz="0 0 1" rpy="0 0 1.5707963267948966"/>
+      <axis xyz="1 0 0"/><limit lower="-1" upper="1"/></joint></robot>"""
+    rb = robot_from_urdf(urdf, ["j"], "a")
+    np.testing.assert_allclose(rb.segments[1]["axis"], (0.0, 1.0, 0.0), atol=1e-15)   # R_pj * (1,0,0)
