@@ -107,6 +107,20 @@ typedef struct stomp_joint_limit {
   double max;
 } stomp_joint_limit;
 
+/* Replaces OrientationConstraintEvaluator (src/constraint_evaluator.cpp:50-114): per free trajectory point
+ *   cost = weight * (rw*|roll| + pw*|pitch| + yw*|yaw|)   of   R_segment * R_nominal^-1  (header frame)
+ *                                                         or   R_nominal^-1 * R_segment  (body fixed),
+ * roll/pitch/yaw as bullet's btMatrix3x3::getRPY returns them, rw/pw/yw = 0 when the matching tolerance is >= pi, and
+ * the point "satisfies" the constraint when every angle is within its tolerance.  The per-timestep state cost gets
+ * constraint_cost_weight * sum of the constraint costs added (src/stomp_optimizer.cpp:1107-1151). */
+typedef struct stomp_orientation_constraint {
+  int32_t segment;     /* segment whose frame is constrained (frame_number_) */
+  int32_t body_fixed;  /* 0: HEADER_FRAME, 1: body-fixed */
+  double orientation[4]; /* nominal orientation, quaternion x, y, z, w */
+  double absolute_roll_tolerance, absolute_pitch_tolerance, absolute_yaw_tolerance;
+  double weight;
+} stomp_orientation_constraint;
+
 /* Per-iteration result; mirrors what StompOptimizer::optimize reads after
  * runSingleIteration (src/stomp_optimizer.cpp:301-339): last_trajectory_cost_,
  * last_trajectory_collision_free_.  Arrays are [B], caller-allocated, may be NULL. */
@@ -115,6 +129,7 @@ typedef struct stomp_iter_stats {
   int32_t* noiseless_collision_free;
   int32_t num_generated_rollouts;  /* R on the first iteration, R - R_reuse afterwards */
   int32_t reserved0;
+  int32_t* noiseless_constraints_satisfied; /* last_trajectory_constraints_satisfied_, [B], may be NULL */
 } stomp_iter_stats;
 
 /* Parity taps / state getters, selector for stomp_engine_get. */
@@ -138,7 +153,8 @@ enum stomp_field {
   STOMP_FIELD_CONTROL_COST = 16,     /* [N][N] R */
   STOMP_FIELD_CLIPPED_PARAMETERS = 17, /* [B][R][D][N] trajectory after handleJointLimits (what FK sees) */
   STOMP_FIELD_BEST_TRAJECTORY = 18,    /* [B][D][N] best_group_trajectory_ kept by stomp_engine_optimize */
-  STOMP_FIELD_NOISELESS_TRAJECTORY = 19 /* [B][D][N] group trajectory of the last noise-less rollout (after joint limits) */
+  STOMP_FIELD_NOISELESS_TRAJECTORY = 19, /* [B][D][N] group trajectory of the last noise-less rollout (after joint limits) */
+  STOMP_FIELD_CONSTRAINTS_SATISFIED = 20 /* [B][R+1] int32 last_trajectory_constraints_satisfied_ (slot R = noise-less rollout) */
 };
 
 /* Per-sphere debug record of one rollout (parity tap for the integer work). */
@@ -192,6 +208,10 @@ int stomp_engine_build_sdf(void* engine, const double size[3], const double orig
                            const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders);
 /* Copies the current voxel grid out (parity tap): dims[3], voxel dtype, and up to `bytes` of voxels (may be NULL). */
 int stomp_engine_get_sdf(void* engine, int32_t dims[3], int32_t* voxel_dtype, void* voxels, size_t bytes);
+/* Orientation path constraints of the planning request (StompOptimizer::initialize, src/stomp_optimizer.cpp:196-201) and
+ * constraint_cost_weight (config/params.yaml:12).  n == 0 removes them.  Must be called after stomp_engine_set_robot. */
+int stomp_engine_set_constraints(void* engine, const stomp_orientation_constraint* constraints, int32_t n,
+                                 double constraint_cost_weight);
 /* noise_stddev / noise_decay of PolicyImprovementLoop (src/policy_improvement_loop.cpp:118-119,155-160). */
 int stomp_engine_set_noise(void* engine, const double* noise_stddev /* [D] */, const double* noise_decay /* [D] */);
 
@@ -234,6 +254,8 @@ int stomp_engine_sample_noise(void* engine, int32_t iteration, int32_t n, double
 int stomp_engine_execute(void* engine, const double* parameters /* [B][n][D][N] */, int32_t n,
                          int32_t iteration_number, double* costs /* [B][n][N] */,
                          int32_t* collision_free /* [B][n] */);
+/* last_trajectory_constraints_satisfied_ of the rollouts of the last stomp_engine_execute call: [B][n]. */
+int stomp_engine_execute_constraints_satisfied(void* engine, int32_t* satisfied, size_t count);
 /* Same, plus the per-sphere records of performForwardKinematics (src/stomp_optimizer.cpp:618-709)
  * for rollout 0 of problem 0: debug[N][K]. */
 int stomp_engine_execute_debug(void* engine, const double* parameters /* [D][N] */,

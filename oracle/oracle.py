@@ -86,6 +86,20 @@ class Oracle:
         g = np.ascontiguousarray(goal, dtype=np.float64)
         self._ck(self.L.stomp_oracle_set_problem(self.h, _dp(s), _dp(g)))
 
+    def set_constraints(self, constraints, weight):
+        arr = (_abi.OrientationConstraint * max(1, len(constraints)))()
+        for i, c in enumerate(constraints):
+            arr[i].segment, arr[i].body_fixed = c["segment"], int(c.get("body_fixed", 0))
+            arr[i].orientation[:] = c["orientation"]
+            arr[i].absolute_roll_tolerance, arr[i].absolute_pitch_tolerance, arr[i].absolute_yaw_tolerance = c["tolerances"]
+            arr[i].weight = c.get("weight", 1.0)
+        self._ck(self.L.stomp_oracle_set_constraints(self.h, arr, len(constraints), C.c_double(weight)))
+
+    def execute_constraints_satisfied(self, n):
+        out = np.empty(n, dtype=np.int32)
+        self._ck(self.L.stomp_oracle_execute_constraints_satisfied(self.h, _ip(out), C.c_size_t(n)))
+        return out
+
     def seed(self, seed):
         self._ck(self.L.stomp_oracle_seed(self.h, C.c_uint64(seed)))
 
@@ -164,7 +178,7 @@ class Oracle:
             _abi.FIELD_INV_CONTROL_COST: (N, N), _abi.FIELD_NOISE_CHOLESKY: (N, N), _abi.FIELD_PROJECTION: (N, N),
             _abi.FIELD_QUAD_COST_INV: (N, N), _abi.FIELD_CONTROL_COST: (N, N),
         }
-        if field == _abi.FIELD_COLLISION_FREE:
+        if field in (_abi.FIELD_COLLISION_FREE, _abi.FIELD_CONSTRAINTS_SATISFIED):
             out = np.empty(R + 1, dtype=np.int32)
         else:
             out = np.empty(shapes[field])

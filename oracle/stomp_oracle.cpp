@@ -261,6 +261,12 @@ struct Oracle {
   double last_cost = 0.0;
   Vec noiseless_costs;
   std::vector<int> collision_free_slots; /* [R+1] */
+  /* constraint evaluators (src/constraint_evaluator.cpp) */
+  std::vector<stomp_orientation_constraint> constraints;
+  double constraint_cost_weight = 0.0;
+  std::vector<Frame> cp_frames;  /* [Nall][segments] */
+  bool last_constraints_satisfied = true;
+  std::vector<int> constraints_satisfied_slots; /* [R+1] */
 };
 
 /* ---- CovariantTrajectoryPolicy ------------------------------------------------------ */
@@ -406,6 +412,49 @@ bool collision_potential(const Oracle& o, const stomp_sphere& s, const double po
   return field_distance <= s.radius;
 }
 
+/* ---- OrientationConstraintEvaluator: src/constraint_evaluator.cpp:50-114 (bullet's btMatrix3x3 restated) ---- */
+void bt_set_rotation(const double q[4], double m[9]) { /* btMatrix3x3::setRotation(btQuaternion(x,y,z,w)) */
+  double d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  double s = 2.0 / d;
+  double xs = q[0] * s, ys = q[1] * s, zs = q[2] * s;
+  double wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
+  double xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs;
+  double yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
+  m[0] = 1.0 - (yy + zz); m[1] = xy - wz; m[2] = xz + wy;
+  m[3] = xy + wz; m[4] = 1.0 - (xx + zz); m[5] = yz - wx;
+  m[6] = xz - wy; m[7] = yz + wx; m[8] = 1.0 - (xx + yy);
+}
+void bt_get_rpy(const double m[9], double& roll, double& pitch, double& yaw) { /* btMatrix3x3::getEulerYPR, solution 1 */
+  if (std::fabs(m[6]) >= 1.0) {
+    yaw = 0.0;
+    double delta = std::atan2(m[7], m[8]);
+    if (m[6] < 0.0) { pitch = M_PI / 2.0; roll = delta; }
+    else { pitch = -M_PI / 2.0; roll = delta; }
+  } else {
+    pitch = -std::asin(m[6]);
+    double cp = std::cos(pitch);
+    roll = std::atan2(m[7] / cp, m[8] / cp);
+    yaw = std::atan2(m[3] / cp, m[0] / cp);
+  }
+}
+bool constraint_cost(const stomp_orientation_constraint& c, const Frame& f, double& cost) {
+  double nom[9], inv[9], res[9];
+  bt_set_rotation(c.orientation, nom);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) inv[i * 3 + j] = nom[j * 3 + i]; /* inverse of a rotation */
+  const double* a = c.body_fixed ? inv : f.R;
+  const double* b = c.body_fixed ? f.R : inv;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) res[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
+  double roll, pitch, yaw;
+  bt_get_rpy(res, roll, pitch, yaw);
+  roll = std::fabs(roll); pitch = std::fabs(pitch); yaw = std::fabs(yaw);
+  double rw = c.absolute_roll_tolerance >= M_PI ? 0.0 : 1.0, pw = c.absolute_pitch_tolerance >= M_PI ? 0.0 : 1.0,
+         yw = c.absolute_yaw_tolerance >= M_PI ? 0.0 : 1.0;
+  cost = c.weight * (rw * roll + pw * pitch + yw * yaw);
+  return !(roll > c.absolute_roll_tolerance || pitch > c.absolute_pitch_tolerance || yaw > c.absolute_yaw_tolerance);
+}
+
 /* ---- forward kinematics: src/treefksolverjointposaxis_partial.cpp:76-178 -------------- */
 void forward_kinematics(const Oracle& o, const double* q_group, std::vector<Frame>& frames) {
   int S = int(o.segs.size());
@@ -464,6 +513,7 @@ bool perform_forward_kinematics(Oracle& o) {
   for (int i = start; i <= end; ++i) {
     for (int d = 0; d < o.D; ++d) q[d] = o.group_traj[d][i];
     forward_kinematics(o, q.data(), frames);
+    if (!o.constraints.empty()) std::copy(frames.begin(), frames.end(), o.cp_frames.begin() + size_t(i) * o.segs.size());
     o.state_coll[i] = 0;
     for (int j = 0; j < o.K; ++j) {
       double* pos = &o.cp_pos[(size_t(i) * o.K + j) * 3];
@@ -494,7 +544,9 @@ void task_execute(Oracle& o, const std::vector<Vec>& parameters, Vec& costs, int
   for (int d = 0; d < o.D; ++d)
     for (int i = 0; i < o.N; ++i) o.group_traj[d][o.fs + i] = parameters[d][i];
   handle_joint_limits(o);
+  if (!o.constraints.empty()) o.cp_frames.resize(size_t(o.Nall) * o.segs.size());
   o.last_collision_free = perform_forward_kinematics(o);
+  o.last_constraints_satisfied = true;
   costs.assign(o.N, 0.0);
   for (int i = o.fs; i <= o.fe; ++i) {
     double state_collision_cost = 0.0, cumulative = 0.0;
@@ -502,7 +554,13 @@ void task_execute(Oracle& o, const std::vector<Vec>& parameters, Vec& costs, int
       cumulative += o.cp_pot[size_t(i) * o.K + j] * o.cp_vel_mag[size_t(i) * o.K + j];
       state_collision_cost += cumulative;
     }
-    costs[i - o.fs] = o.desc.obstacle_cost_weight * state_collision_cost;
+    double state_constraint_cost = 0.0;
+    for (const stomp_orientation_constraint& c : o.constraints) {
+      double cost;
+      if (!constraint_cost(c, o.cp_frames[size_t(i) * o.segs.size() + c.segment], cost)) o.last_constraints_satisfied = false;
+      state_constraint_cost += cost;
+    }
+    costs[i - o.fs] = o.desc.obstacle_cost_weight * state_collision_cost + o.constraint_cost_weight * state_constraint_cost;
   }
   double s = 0.0;
   for (double c : costs) s += c;
@@ -667,6 +725,7 @@ void run_single_iteration(Oracle& o, int iteration_number, const double* eps_inj
     task_execute(o, o.rollouts[r].parameters, tmp, iteration_number);
     std::copy(tmp.begin(), tmp.end(), rollout_costs.begin() + size_t(r) * o.N);
     o.collision_free_slots[r] = o.last_collision_free;
+    o.constraints_satisfied_slots[r] = o.last_constraints_satisfied;
   }
   pi_set_rollout_costs(o, rollout_costs.data(), o.desc.smoothness_cost_weight, nullptr);
   pi_improve_policy(o);
@@ -675,6 +734,7 @@ void run_single_iteration(Oracle& o, int iteration_number, const double* eps_inj
   policy_get_parameters(o, theta);
   task_execute(o, theta, o.noiseless_costs, iteration_number);
   o.collision_free_slots[o.R] = o.last_collision_free;
+  o.constraints_satisfied_slots[o.R] = o.last_constraints_satisfied;
   pi_add_extra_rollout(o, theta, o.noiseless_costs);
 }
 
@@ -711,6 +771,7 @@ int stomp_oracle_create(const stomp_engine_desc* desc, void** out) {
   o->limits.assign(o->D, stomp_joint_limit{0, 0, 0.0, 0.0});
   o->noiseless_costs.assign(o->N, 0.0);
   o->collision_free_slots.assign(o->R + 1, 0);
+  o->constraints_satisfied_slots.assign(o->R + 1, 1);
   *out = o;
   return 0;
 }
@@ -750,6 +811,17 @@ int stomp_oracle_set_sdf(void* h, const void* voxels, int32_t nx, int32_t ny, in
   for (int i = 0; i < 65536; ++i) o.sqrt_table[i] = std::sqrt(double(i)) * resolution; /* PropagationDistanceField sqrt_table_ */
   return 0;
 }
+
+int stomp_oracle_set_constraints(void* h, const stomp_orientation_constraint* c, int32_t n, double weight) {
+  Oracle& o = *static_cast<Oracle*>(h);
+  for (int i = 0; i < n; ++i)
+    if (c[i].segment < 0 || c[i].segment >= int(o.segs.size())) return fail("constraint segment out of range");
+  o.constraints.assign(c, c + n);
+  o.constraint_cost_weight = weight;
+  return 0;
+}
+
+int stomp_oracle_last_constraints_satisfied(void* h) { return static_cast<Oracle*>(h)->last_constraints_satisfied ? 1 : 0; }
 
 int stomp_oracle_set_noise(void* h, const double* noise_stddev, const double* noise_decay) {
   Oracle& o = *static_cast<Oracle*>(h);
@@ -822,6 +894,12 @@ int stomp_oracle_compute_control_costs(void* h, const double* parameters, const 
   return 0;
 }
 
+static std::vector<int> g_exec_satisfied;
+int stomp_oracle_execute_constraints_satisfied(void*, int32_t* out, size_t count) {
+  for (size_t i = 0; i < count && i < g_exec_satisfied.size(); ++i) out[i] = g_exec_satisfied[i];
+  return 0;
+}
+
 int stomp_oracle_execute(void* h, const double* parameters, int32_t n, int32_t iteration_number, double* costs,
                          int32_t* collision_free) {
   Oracle& o = *static_cast<Oracle*>(h);
@@ -835,6 +913,8 @@ int stomp_oracle_execute(void* h, const double* parameters, int32_t n, int32_t i
     task_execute(o, p, c, iteration_number);
     std::copy(c.begin(), c.end(), costs + size_t(r) * o.N);
     if (collision_free) collision_free[r] = o.last_collision_free;
+    if (r == 0) g_exec_satisfied.clear();
+    g_exec_satisfied.push_back(o.last_constraints_satisfied ? 1 : 0);
   }
   return 0;
 }
@@ -931,6 +1011,10 @@ int stomp_oracle_get(void* h, int32_t field, void* out_, size_t bytes) {
     case STOMP_FIELD_COLLISION_FREE:
       if (!need(size_t(o.R + 1) * 4)) return fail("buffer too small");
       std::copy(o.collision_free_slots.begin(), o.collision_free_slots.end(), static_cast<int32_t*>(out_));
+      return 0;
+    case STOMP_FIELD_CONSTRAINTS_SATISFIED:
+      if (!need(size_t(o.R + 1) * 4)) return fail("buffer too small");
+      std::copy(o.constraints_satisfied_slots.begin(), o.constraints_satisfied_slots.end(), static_cast<int32_t*>(out_));
       return 0;
     case STOMP_FIELD_ROLLOUT_TOTAL_COSTS:
       if (!need(size_t(o.R + 1) * 8)) return fail("buffer too small");

@@ -12,7 +12,8 @@ JOINT_FIXED, JOINT_REVOLUTE, JOINT_PRISMATIC = 0, 1, 2
 (FIELD_THETA, FIELD_NOISE, FIELD_PARAMETERS, FIELD_NOISE_PROJECTED, FIELD_STATE_COSTS, FIELD_CONTROL_COSTS,
  FIELD_CUMULATIVE_COSTS, FIELD_PROBABILITIES, FIELD_UPDATES, FIELD_NOISELESS_COSTS, FIELD_COLLISION_FREE,
  FIELD_ROLLOUT_TOTAL_COSTS, FIELD_INV_CONTROL_COST, FIELD_NOISE_CHOLESKY, FIELD_PROJECTION, FIELD_QUAD_COST_INV,
- FIELD_CONTROL_COST, FIELD_CLIPPED_PARAMETERS, FIELD_BEST_TRAJECTORY, FIELD_NOISELESS_TRAJECTORY) = range(20)
+ FIELD_CONTROL_COST, FIELD_CLIPPED_PARAMETERS, FIELD_BEST_TRAJECTORY, FIELD_NOISELESS_TRAJECTORY,
+ FIELD_CONSTRAINTS_SATISFIED) = range(21)
 
 
 class EngineDesc(C.Structure):
@@ -76,6 +77,19 @@ class IterStats(C.Structure):
         ("noiseless_collision_free", C.POINTER(C.c_int32)),
         ("num_generated_rollouts", C.c_int32),
         ("reserved0", C.c_int32),
+        ("noiseless_constraints_satisfied", C.POINTER(C.c_int32)),
+    ]
+
+
+class OrientationConstraint(C.Structure):
+    _fields_ = [
+        ("segment", C.c_int32),
+        ("body_fixed", C.c_int32),
+        ("orientation", C.c_double * 4),
+        ("absolute_roll_tolerance", C.c_double),
+        ("absolute_pitch_tolerance", C.c_double),
+        ("absolute_yaw_tolerance", C.c_double),
+        ("weight", C.c_double),
     ]
 
 

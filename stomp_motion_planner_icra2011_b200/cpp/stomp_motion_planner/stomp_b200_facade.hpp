@@ -404,7 +404,7 @@ inline bool PolicyImprovementLoop::runSingleIteration(const int iteration_number
   if (fused_) {  // the built-in GPU task: the whole iteration stays on the device
     double cost = 0.0;
     int32_t cf = 0;
-    stomp_iter_stats st = {&cost, &cf, 0, 0};
+    stomp_iter_stats st = {&cost, &cf, 0, 0, nullptr};
     if (stomp_engine_iterate(e_->get(), iteration_number, &st)) return false;
     last_cost_ = cost;
     last_collision_free_ = cf != 0;

@@ -91,7 +91,10 @@ struct Engine {
   DevBuf<double> noise_projected, probabilities, clipped;      // taps (keep_intermediates)
   DevBuf<double> extra_state, extra_control, updates, noiseless_sum;
   DevBuf<double> eps_in2[2];   // injected noise, double buffered (async uploads overlap the previous iteration)
-  DevBuf<int> reuse_src, collision_free;
+  DevBuf<int> reuse_src, collision_free, constraints_ok, scratch_cflags;
+  DevBuf<unsigned char> dconstraints;
+  std::vector<stomp_orientation_constraint> constraints;
+  double constraint_cost_weight = 0.0;
   DevBuf<double> band_fw, band_bw, proj_scale, qinv_t, noise_scale;
   DevBuf<double> limit_min, limit_max;
   DevBuf<int> has_limits;
@@ -235,14 +238,14 @@ GenArgs base_gen_args(Engine& e) {
   return a;
 }
 
-template <typename Real, bool kDebug, int kVox>
-int launch_cost_v(Engine& e, CostArgs<Real>& a, int num_problems) {
+template <typename Real, bool kDebug, int kVox, bool kCons>
+int launch_cost_c(Engine& e, CostArgs<Real>& a, int num_problems) {
   const int ntiles = (e.N + kTileSteps - 1) / kTileSteps;
   int warps = std::min(ntiles, 4);
   warps = std::max(warps, std::min(e.D, 4));  // joint-limit pass likes a few warps
   size_t smem = ((size_t(e.D) * e.N * 8 + 15) & ~size_t(15)) + size_t(e.num_nodes) * sizeof(DevNode<Real>) + size_t(e.K) * sizeof(DevSphere<Real>) +
-                256 * sizeof(Real) + size_t(warps) * 12 * 32 * sizeof(Real);
-  auto kern = k_cost<Real, kDebug, kVox>;
+                256 * sizeof(Real) + size_t(warps) * 12 * 32 * sizeof(Real) + e.constraints.size() * sizeof(DevConstraint<Real>);
+  auto kern = k_cost<Real, kDebug, kVox, kCons>;
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   if (smem > 220 * 1024) return fail("trajectory + robot tables exceed shared memory");
   a.total_rollouts = num_problems * a.n_rollouts;
@@ -258,6 +261,14 @@ int launch_cost_v(Engine& e, CostArgs<Real>& a, int num_problems) {
   begin_launch(e);
   kern<<<grid, warps * 32, smem, e.stream>>>(a);
   return check_launch(e, "k_cost");
+}
+
+// the constraint evaluators are compiled out of the common (no path constraints) instantiation; the debug tap always
+// uses the general one
+template <typename Real, bool kDebug, int kVox>
+int launch_cost_v(Engine& e, CostArgs<Real>& a, int num_problems) {
+  if (kDebug || !e.constraints.empty()) return launch_cost_c<Real, kDebug, kVox, true>(e, a, num_problems);
+  return launch_cost_c<Real, kDebug, kVox, kDebug>(e, a, num_problems);
 }
 
 template <typename Real, bool kDebug>
@@ -283,13 +294,16 @@ CostArgs<Real> base_cost_args(Engine& e) {
   a.sdf = e.sdf;
   a.inv_time = 1.0 / e.desc.discretization;
   a.obstacle_weight = e.desc.obstacle_cost_weight;
+  a.constraint_weight = e.constraint_cost_weight;
+  a.num_constraints = int(e.constraints.size());
+  a.constraints = reinterpret_cast<const DevConstraint<Real>*>(e.dconstraints.p);
   return a;
 }
 
 // cost plugin over rollouts stored as params[b*pstride + r*D*N], writing costs[b*cstride + r*N]
 int launch_cost(Engine& e, const double* params, size_t pstride, int n_rollouts, int num_problems, int include_pads,
                 double* costs, size_t cstride, int* flags, int flag_stride, int flag_offset, double* clipped,
-                stomp_sphere_debug* debug) {
+                stomp_sphere_debug* debug, int* cflags = nullptr) {
   if (!e.have_robot || !e.have_sdf) return fail("set_robot and set_sdf must be called before the cost plugin runs");
   if (!e.have_problems) return fail("set_problems must be called before the cost plugin runs");
   if (e.f32) {
@@ -298,6 +312,7 @@ int launch_cost(Engine& e, const double* params, size_t pstride, int n_rollouts,
     a.params = params; a.params_problem_stride = pstride; a.params_rollout_stride = size_t(e.D) * e.N;
     a.costs = costs; a.cost_problem_stride = cstride;
     a.collision_free = flags; a.flag_problem_stride = flag_stride; a.flag_offset = flag_offset;
+    a.constraints_satisfied = cflags;
     a.clipped = clipped; a.debug = debug;
     return debug ? launch_cost_t<float, true>(e, a, num_problems) : launch_cost_t<float, false>(e, a, num_problems);
   }
@@ -306,6 +321,7 @@ int launch_cost(Engine& e, const double* params, size_t pstride, int n_rollouts,
   a.params = params; a.params_problem_stride = pstride; a.params_rollout_stride = size_t(e.D) * e.N;
   a.costs = costs; a.cost_problem_stride = cstride;
   a.collision_free = flags; a.flag_problem_stride = flag_stride; a.flag_offset = flag_offset;
+  a.constraints_satisfied = cflags;
   a.clipped = clipped; a.debug = debug;
   return debug ? launch_cost_t<double, true>(e, a, num_problems) : launch_cost_t<double, false>(e, a, num_problems);
 }
@@ -457,7 +473,7 @@ int step_improve(Engine& e, int apply) {
 int step_extra(Engine& e, bool run_cost, int iteration_number, bool have_control = false) {
   if (run_cost) {
     if (launch_cost(e, e.theta.p, size_t(e.D) * e.N, 1, e.B, iteration_number == 1, e.extra_state.p, size_t(e.N),
-                    e.collision_free.p, e.R + 1, e.R, e.extra_clipped.p, nullptr))
+                    e.collision_free.p, e.R + 1, e.R, e.extra_clipped.p, nullptr, e.constraints_ok.p))
       return 1;
   }
   if (!have_control) {
@@ -482,7 +498,7 @@ int iterate_front(Engine& e, int iteration_number) {  // up to and including k_c
   if (step_get_rollouts(e, iteration_number, true)) return 1;
   if (gather_reused_state(e)) return 1;
   if (launch_cost(e, e.params[e.cur].p, size_t(e.R) * e.D * e.N, e.num_gen, e.B, iteration_number == 1, e.state[e.cur].p,
-                  size_t(e.R) * e.N, e.collision_free.p, e.R + 1, 0, e.clipped.p, nullptr))
+                  size_t(e.R) * e.N, e.collision_free.p, e.R + 1, 0, e.clipped.p, nullptr, e.constraints_ok.p))
     return 1;
   return launch_cumulative(e);
 }
@@ -510,6 +526,10 @@ int fill_stats(Engine& e, stomp_iter_stats* stats) {
     CUDA_TRY(cudaMemcpy2DAsync(stats->noiseless_collision_free, 4, e.collision_free.p + e.R, size_t(e.R + 1) * 4, 4, e.B,
                                cudaMemcpyDeviceToHost, e.stream));
   }
+  if (stats->noiseless_constraints_satisfied) {
+    CUDA_TRY(cudaMemcpy2DAsync(stats->noiseless_constraints_satisfied, 4, e.constraints_ok.p + e.R, size_t(e.R + 1) * 4, 4, e.B,
+                               cudaMemcpyDeviceToHost, e.stream));
+  }
   CUDA_TRY(cudaStreamSynchronize(e.stream));
   return 0;
 }
@@ -520,10 +540,41 @@ int ensure_scratch(Engine& e, size_t n_rollouts_total) {
   CUDA_TRY(e.scratch_noise.alloc(n_rollouts_total * e.D * e.N));
   CUDA_TRY(e.scratch_costs.alloc(n_rollouts_total * e.D * e.N));
   CUDA_TRY(e.scratch_flags.alloc(n_rollouts_total));
+  CUDA_TRY(e.scratch_cflags.alloc(n_rollouts_total));
   e.scratch_n = n_rollouts_total;
   return 0;
 }
 
+template <typename Real>
+int upload_constraints(Engine& e) {
+  std::vector<DevConstraint<Real>> dc(e.constraints.size());
+  for (size_t i = 0; i < dc.size(); ++i) {
+    const stomp_orientation_constraint& c = e.constraints[i];
+    std::memset(&dc[i], 0, sizeof(dc[i]));
+    const double* q = c.orientation;   // btMatrix3x3::setRotation(btQuaternion(x, y, z, w))
+    const double d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3], s2 = 2.0 / d;
+    const double xs = q[0] * s2, ys = q[1] * s2, zs = q[2] * s2, wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
+    const double xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs, yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
+    const double nom[9] = {1.0 - (yy + zz), xy - wz, xz + wy, xy + wz, 1.0 - (xx + zz), yz - wx, xz - wy, yz + wx, 1.0 - (xx + yy)};
+    for (int r = 0; r < 3; ++r)
+      for (int k = 0; k < 3; ++k) dc[i].nominal_inv[r * 3 + k] = Real(nom[k * 3 + r]);
+    for (int k = 0; k < 9; ++k) dc[i].rel[k] = Real(e.robot.seg_rel[c.segment].R[k]);
+    dc[i].node = e.robot.seg_node[c.segment];
+    dc[i].body_fixed = c.body_fixed ? 1 : 0;
+    const double tol[3] = {c.absolute_roll_tolerance, c.absolute_pitch_tolerance, c.absolute_yaw_tolerance};
+    for (int k = 0; k < 3; ++k) {
+      dc[i].tol[k] = Real(tol[k]);
+      dc[i].w[k] = Real(tol[k] >= M_PI ? 0.0 : 1.0);   // src/constraint_evaluator.cpp:68-74
+    }
+    dc[i].weight = Real(c.weight);
+  }
+  static const unsigned char zeros[16] = {0};
+  if (dc.empty() ? upload(e, e.dconstraints, zeros, sizeof(zeros))
+                 : upload(e, e.dconstraints, reinterpret_cast<const unsigned char*>(dc.data()), dc.size() * sizeof(DevConstraint<Real>)))
+    return 1;
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
 Engine* E(void* h) { return static_cast<Engine*>(h); }
 
 #define ENGINE_OR_FAIL(h)                          \
@@ -594,6 +645,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   if (desc->keep_intermediates) { ALLOC(e.noise_projected, BRDN); ALLOC(e.probabilities, BRDN); ALLOC(e.clipped, BRDN); }
   ALLOC(e.extra_state, size_t(e.B) * e.N); ALLOC(e.extra_control, BDN); ALLOC(e.updates, BDN); ALLOC(e.noiseless_sum, size_t(e.B));
   ALLOC(e.reuse_src, size_t(e.B) * std::max(1, e.Rre)); ALLOC(e.collision_free, size_t(e.B) * (e.R + 1));
+  ALLOC(e.constraints_ok, size_t(e.B) * (e.R + 1));
   ALLOC(e.noise_scale, size_t(e.D));
   ALLOC(e.extra_clipped, BDN); ALLOC(e.best_traj, BDN); ALLOC(e.best_cost, size_t(e.B));
   ALLOC(e.track_state, size_t(e.B) * sizeof(TrackState)); ALLOC(e.num_done, 1);
@@ -671,6 +723,7 @@ int stomp_engine_set_robot(void* h, const stomp_segment* segments, int32_t num_s
   if (upload(e, e.has_limits, hl.data(), size_t(e.D)) || upload(e, e.limit_min, lo.data(), size_t(e.D)) ||
       upload(e, e.limit_max, hi.data(), size_t(e.D)))
     return 1;
+  e.constraints.clear();   // segment numbering may have changed
   CUDA_TRY(e.debug.alloc(size_t(e.N + 3) * std::max(1, e.K)));
   CUDA_TRY(cudaStreamSynchronize(e.stream));
   e.have_robot = true;
@@ -803,6 +856,17 @@ int stomp_engine_get_sdf(void* h, int32_t dims[3], int32_t* voxel_dtype, void* v
     CUDA_TRY(cudaStreamSynchronize(e.stream));
   }
   return 0;
+}
+
+int stomp_engine_set_constraints(void* h, const stomp_orientation_constraint* constraints, int32_t n, double constraint_cost_weight) {
+  ENGINE_OR_FAIL(h);
+  if (!e.have_robot) return fail("set_robot must be called before set_constraints");
+  if (n < 0 || n > kMaxConstraints || (n > 0 && !constraints)) return fail("bad constraints");
+  for (int i = 0; i < n; ++i)
+    if (constraints[i].segment < 0 || constraints[i].segment >= int(e.robot.seg_node.size())) return fail("constraint segment out of range");
+  e.constraints.assign(constraints, constraints + n);
+  e.constraint_cost_weight = constraint_cost_weight;
+  return e.f32 ? upload_constraints<float>(e) : upload_constraints<double>(e);
 }
 
 int stomp_engine_set_noise(void* h, const double* noise_stddev, const double* noise_decay) {
@@ -941,10 +1005,18 @@ int stomp_engine_execute(void* h, const double* parameters, int32_t n, int32_t i
   if (ensure_scratch(e, total)) return 1;
   CUDA_TRY(cudaMemcpyAsync(e.scratch_params.p, parameters, total * e.D * e.N * 8, cudaMemcpyHostToDevice, e.stream));
   if (launch_cost(e, e.scratch_params.p, size_t(n) * e.D * e.N, n, e.B, iteration_number == 1, e.scratch_costs.p, size_t(n) * e.N,
-                  e.scratch_flags.p, n, 0, nullptr, nullptr))
+                  e.scratch_flags.p, n, 0, nullptr, nullptr, e.scratch_cflags.p))
     return 1;
   CUDA_TRY(cudaMemcpyAsync(costs, e.scratch_costs.p, total * e.N * 8, cudaMemcpyDeviceToHost, e.stream));
   if (collision_free) CUDA_TRY(cudaMemcpyAsync(collision_free, e.scratch_flags.p, total * 4, cudaMemcpyDeviceToHost, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+int stomp_engine_execute_constraints_satisfied(void* h, int32_t* satisfied, size_t count) {
+  ENGINE_OR_FAIL(h);
+  if (!satisfied || count > e.scratch_cflags.n) return fail("bad argument");
+  CUDA_TRY(cudaMemcpyAsync(satisfied, e.scratch_cflags.p, count * 4, cudaMemcpyDeviceToHost, e.stream));
   CUDA_TRY(cudaStreamSynchronize(e.stream));
   return 0;
 }
@@ -1045,7 +1117,7 @@ int stomp_engine_optimize(void* h, int32_t max_iterations, int32_t max_after_cf,
     if (iterate_once(e, it + 1)) return 1;
     begin_launch(e);
     k_track_best<<<e.B, 128, 0, e.stream>>>(it, max_after_cf, e.D * e.N, e.R + 1, e.R, e.noiseless_sum.p, e.collision_free.p,
-                                            e.extra_clipped.p, reinterpret_cast<TrackState*>(e.track_state.p), e.best_cost.p,
+                                            e.constraints_ok.p, e.extra_clipped.p, reinterpret_cast<TrackState*>(e.track_state.p), e.best_cost.p,
                                             e.best_traj.p, want_log ? e.cost_log.p : nullptr, e.B, e.num_done.p);
     if (check_launch(e, "k_track_best")) return 1;
     if ((it + 1) % check_every == 0 && it + 1 < max_iterations) {
@@ -1104,6 +1176,7 @@ int stomp_engine_get(void* h, int32_t field, void* out, size_t bytes) {
     case STOMP_FIELD_UPDATES: src = e.updates.p; need = BDN * 8; break;
     case STOMP_FIELD_NOISELESS_COSTS: src = e.extra_state.p; need = size_t(e.B) * e.N * 8; break;
     case STOMP_FIELD_COLLISION_FREE: src = e.collision_free.p; need = size_t(e.B) * (e.R + 1) * 4; break;
+    case STOMP_FIELD_CONSTRAINTS_SATISFIED: src = e.constraints_ok.p; need = size_t(e.B) * (e.R + 1) * 4; break;
     case STOMP_FIELD_ROLLOUT_TOTAL_COSTS: src = e.totals.p; need = size_t(e.B) * (e.R + 1) * 8; break;
     case STOMP_FIELD_CLIPPED_PARAMETERS: src = e.clipped.p; need = BRDN * 8; break;
     case STOMP_FIELD_BEST_TRAJECTORY: src = e.best_traj.p; need = BDN * 8; break;

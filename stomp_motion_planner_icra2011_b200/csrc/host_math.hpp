@@ -291,6 +291,10 @@ struct FoldedRobot {
   std::vector<HostNode> nodes;
   std::vector<HostSphere> spheres;
   int num_slots = 0;
+  // per input segment: the node its frame rides on (-1: static) and the frame relative to that node
+  // (static segments: the constant frame in the reference frame)
+  std::vector<int> seg_node;
+  std::vector<Frame> seg_rel;
 };
 
 inline bool fold_robot(const stomp_segment* segs, int S, int ref_seg, const stomp_sphere* sph, int K, int D,
@@ -366,6 +370,12 @@ inline bool fold_robot(const stomp_segment* segs, int S, int ref_seg, const stom
     node_of[s] = int(out.nodes.size());
     rel[s] = frame_identity();
     out.nodes.push_back(n);
+  }
+  out.seg_node.assign(S, -1);
+  out.seg_rel.assign(S, frame_identity());
+  for (int s = 0; s < S; ++s) {
+    out.seg_node[s] = dyn[s] ? node_of[s] : -1;
+    out.seg_rel[s] = dyn[s] ? rel[s] : stat[s];
   }
   // spheres on static segments get an anchor node each distinct segment (fixed type, constant frame)
   std::vector<int> static_anchor(S, -1);

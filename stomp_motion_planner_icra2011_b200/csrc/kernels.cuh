@@ -57,6 +57,15 @@ struct alignas(16) DevSphere {
   int original_index;
 };
 
+// OrientationConstraintEvaluator (src/constraint_evaluator.cpp:50-114) folded for the device: the constrained segment's
+// rotation is F(node).R * rel, the nominal orientation is pre-inverted, weights are 0 when the tolerance is >= pi.
+constexpr int kMaxConstraints = 8;
+template <typename Real>
+struct alignas(16) DevConstraint {
+  Real rel[9], nominal_inv[9], tol[3], w[3], weight;
+  int node, body_fixed;
+};
+
 struct Band {           // banded Cholesky factor of R = C C^T and the projection scaling
   const double* fw;         // [N][8]  {1/C(i,i), C(i,i-1)/C(i,i), ..., C(i,i-6)/C(i,i), 0}
   const double* bw;         // [N][8]  {1/C(i,i), C(i+1,i)/C(i,i), ..., C(i+6,i)/C(i,i), 0}
@@ -560,6 +569,10 @@ struct CostArgs {
   Sdf sdf;
   double inv_time;           // 1/discretization
   double obstacle_weight;
+  double constraint_weight;  // constraint_cost_weight
+  int num_constraints;
+  const DevConstraint<Real>* constraints;
+  int* constraints_satisfied; // same indexing as collision_free (may be NULL)
   double* costs;             // [..][N]
   int* collision_free;       // [..]
   double* clipped;           // optional tap [same layout as params]
@@ -572,13 +585,52 @@ template <> struct Math<double> {
   static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
   static __device__ __forceinline__ double round_(double x) { return round(x); }
   static __device__ __forceinline__ double fabs_(double x) { return fabs(x); }
+  static __device__ __forceinline__ double asin_(double x) { return asin(x); }
+  static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+  static __device__ __forceinline__ double cos_(double x) { return cos(x); }
 };
 template <> struct Math<float> {
   static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
   static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
   static __device__ __forceinline__ float round_(float x) { return roundf(x); }
   static __device__ __forceinline__ float fabs_(float x) { return fabsf(x); }
+  static __device__ __forceinline__ float asin_(float x) { return asinf(x); }
+  static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+  static __device__ __forceinline__ float cos_(float x) { return cosf(x); }
 };
+
+// cost of one orientation constraint for the segment rotation Rs = Fr * rel (Fr: rotation of the carrying node's frame, or
+// nullptr for a static segment); bullet's btMatrix3x3::getEulerYPR (solution 1) restated.  Returns "satisfied".
+template <typename Real>
+__device__ __forceinline__ bool constraint_cost(const DevConstraint<Real>& c, const Real* Fr, Real& cost) {
+  Real Rs[9], res[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      Rs[i * 3 + j] = Fr ? Fr[i * 3] * c.rel[j] + Fr[i * 3 + 1] * c.rel[3 + j] + Fr[i * 3 + 2] * c.rel[6 + j] : c.rel[i * 3 + j];
+  const Real* a = c.body_fixed ? c.nominal_inv : Rs;
+  const Real* b = c.body_fixed ? Rs : c.nominal_inv;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) res[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
+  const Real kHalfPi = Real(1.5707963267948966);
+  Real roll, pitch, yaw;
+  if (Math<Real>::fabs_(res[6]) >= Real(1)) {
+    yaw = Real(0);
+    roll = Math<Real>::atan2_(res[7], res[8]);
+    pitch = res[6] < Real(0) ? kHalfPi : -kHalfPi;
+  } else {
+    pitch = -Math<Real>::asin_(res[6]);
+    const Real cp = Math<Real>::cos_(pitch);
+    roll = Math<Real>::atan2_(res[7] / cp, res[8] / cp);
+    yaw = Math<Real>::atan2_(res[3] / cp, res[0] / cp);
+  }
+  roll = Math<Real>::fabs_(roll); pitch = Math<Real>::fabs_(pitch); yaw = Math<Real>::fabs_(yaw);
+  cost = c.weight * (c.w[0] * roll + c.w[1] * pitch + c.w[2] * yaw);
+  return !(roll > c.tol[0] || pitch > c.tol[1] || yaw > c.tol[2]);
+}
 
 __device__ __forceinline__ double shfl_rel(double v, int delta) {
   // value of lane (lane + delta), clamped at the warp edges (edge lanes are halo lanes, never productive)
@@ -705,7 +757,7 @@ __device__ __forceinline__ void cta_copy_async16(void* dst_smem, const void* src
 
 // Persistent CTAs: the grid is sized to the machine (SMs x resident CTAs) and every CTA walks rollouts with a
 // grid stride, so the robot tables are staged in shared memory once per CTA instead of once per rollout.
-template <typename Real, bool kDebug, int kVox>
+template <typename Real, bool kDebug, int kVox, bool kCons>
 __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<Real> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = a.D, N = a.N, K = a.K;
@@ -719,6 +771,9 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
   const unsigned vs_addr = smem_u32(sqrt_tab + 256 + size_t(warp) * 12 * 32 + lane);
   const unsigned sph_addr = smem_u32(spheres), tab_addr = smem_u32(sqrt_tab);
   constexpr unsigned kVsStride = 32 * sizeof(Real);
+  DevConstraint<Real>* cons = reinterpret_cast<DevConstraint<Real>*>(sqrt_tab + 256 + size_t(nwarps) * 12 * 32);
+  const int num_cons = kCons ? a.num_constraints : 0;
+  cta_copy_async16(cons, a.constraints, int(sizeof(DevConstraint<Real>)) * num_cons);
   // robot tables: asynchronous 16-byte copies, all in flight together (waited for with the first trajectory)
   cta_copy_async16(nodes, a.nodes, int(sizeof(DevNode<Real>)) * a.num_nodes);
   cta_copy_async16(spheres, a.spheres, int(sizeof(DevSphere<Real>)) * K);
@@ -745,7 +800,9 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     int* flag = a.collision_free ? a.collision_free + size_t(b) * a.flag_problem_stride + a.flag_offset + r : nullptr;
+    int* cflag = a.constraints_satisfied ? a.constraints_satisfied + size_t(b) * a.flag_problem_stride + a.flag_offset + r : nullptr;
     if (threadIdx.x == 0 && flag) *flag = 1;   // ordered before the warps' "= 0" stores by the barriers below
+    if (threadIdx.x == 0 && cflag) *cflag = 1;
     __syncthreads();
 
     // ---- handleJointLimits: warp per joint, <= 11 passes of (arg max violation, rank-1 correction) ----------
@@ -789,16 +846,22 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
     const double* ps = a.pad_start + size_t(b) * D;
     const double* pg = a.pad_goal + size_t(b) * D;
     double* out = a.costs + size_t(b) * a.cost_problem_stride + size_t(r) * N;
-    int collided = 0;
+    int collided = 0, violated = 0;
 
     for (int tile = warp; tile < ntiles; tile += nwarps) {
       const int t = tile * kTileSteps - 1 + lane;      // trajectory point of this lane (-1 .. N+1 are meaningful)
       const bool productive = lane >= 1 && lane <= kTileSteps && t < N;
       const bool counts = productive || (a.include_pads && (t == -1 || t == N));
-      Real cost = Real(0);
+      Real cost = Real(0), ccost = Real(0);
       Real F[12], saved[kMaxSlots][12];
 #pragma unroll
       for (int i = 0; i < 12; ++i) F[i] = Real(0);
+      for (int ci = 0; ci < num_cons; ++ci)   // constraints on segments no group joint moves
+        if (cons[ci].node < 0) {
+          Real cc;
+          if (!constraint_cost<Real>(cons[ci], nullptr, cc)) violated |= int(productive);
+          ccost += cc;
+        }
 
       for (int n = 0; n < a.num_nodes; ++n) {
         const DevNode<Real>& nd = nodes[n];
@@ -843,6 +906,12 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
 #pragma unroll
           for (int i = 0; i < 12; ++i) saved[nd.save_slot][i] = F[i];
         }
+        for (int ci = 0; ci < num_cons; ++ci)
+          if (cons[ci].node == n) {
+            Real cc;
+            if (!constraint_cost<Real>(cons[ci], F, cc)) violated |= int(productive);
+            ccost += cc;
+          }
         const int sph_begin = nd.sphere_begin, sph_end = nd.sphere_end;
         if (sph_end > sph_begin) {
           // velocity frame V = sum_k rule_k/dt * F(t+k), vel(sphere) = V.R * p + V.p (linear in the frame); built
@@ -899,9 +968,11 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
           }
         }
       }
-      if (productive) out[t] = a.obstacle_weight * double(cost);
+      if (productive) out[t] = kCons ? a.obstacle_weight * double(cost) + a.constraint_weight * double(ccost)
+                                     : a.obstacle_weight * double(cost);
     }
     if (collided && flag) *flag = 0;
+    if (violated && cflag) *cflag = 0;
   }
 }
 
@@ -1119,7 +1190,7 @@ struct TrackState {
 
 __global__ void k_track_best(int iteration, int max_after_collision_free, int DN, int flag_stride, int flag_offset,
                              const double* __restrict__ noiseless_cost, const int* __restrict__ collision_free,
-                             const double* __restrict__ trajectory, TrackState* __restrict__ state, double* __restrict__ best_cost,
+                             const int* __restrict__ constraints_satisfied, const double* __restrict__ trajectory, TrackState* __restrict__ state, double* __restrict__ best_cost,
                              double* __restrict__ best, double* __restrict__ cost_log, int B, int* __restrict__ num_done) {
   const int b = blockIdx.x;
   __shared__ int s_copy;
@@ -1129,14 +1200,15 @@ __global__ void k_track_best(int iteration, int max_after_collision_free, int DN
     if (!st.done) {
       const double cost = noiseless_cost[b];
       const bool cf = collision_free[size_t(b) * flag_stride + flag_offset] != 0;
-      st.collision_free_iteration = cf ? st.collision_free_iteration + 1 : 0;
+      const bool cs = constraints_satisfied[size_t(b) * flag_stride + flag_offset] != 0;
+      st.collision_free_iteration = (cf && cs) ? st.collision_free_iteration + 1 : 0;
       if (cf && st.collision_success_iteration == -1) st.collision_success_iteration = iteration;
-      if (cf && st.success_iteration == -1) st.success_iteration = iteration;
+      if (cf && cs && st.success_iteration == -1) st.success_iteration = iteration;
       if (cost_log) cost_log[size_t(iteration) * B + b] = cost;
       if (iteration == 0) {
         best_cost[b] = cost;
         s_copy = 1;
-      } else if (cost < best_cost[b] && cf) {
+      } else if (cost < best_cost[b] && cf && cs) {
         best_cost[b] = cost;
         st.last_improvement_iteration = iteration;
         s_copy = 1;

@@ -29,6 +29,7 @@ EXPORTS = [
     "stomp_engine_timer_stop", "stomp_engine_shard_buffers", "stomp_engine_iterate_sharded_phase",
     "stomp_engine_set_profiling", "stomp_engine_get_profile", "stomp_engine_optimize",
     "stomp_engine_build_sdf", "stomp_engine_get_sdf", "stomp_engine_inject_noise_async", "stomp_engine_last_stats",
+    "stomp_engine_set_constraints", "stomp_engine_execute_constraints_satisfied",
 ]
 
 
@@ -122,6 +123,21 @@ class Engine:
         self._ck(self.L.stomp_engine_get_sdf(self.h, dims, C.byref(dt), out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes)))
         return out, dt.value
 
+    def set_constraints(self, constraints, weight):
+        """constraints: dicts {segment, orientation (x,y,z,w), tolerances (roll,pitch,yaw), weight, body_fixed}."""
+        arr = (_abi.OrientationConstraint * max(1, len(constraints)))()
+        for i, c in enumerate(constraints):
+            arr[i].segment, arr[i].body_fixed = c["segment"], int(c.get("body_fixed", 0))
+            arr[i].orientation[:] = c["orientation"]
+            arr[i].absolute_roll_tolerance, arr[i].absolute_pitch_tolerance, arr[i].absolute_yaw_tolerance = c["tolerances"]
+            arr[i].weight = c.get("weight", 1.0)
+        self._ck(self.L.stomp_engine_set_constraints(self.h, arr, len(constraints), C.c_double(weight)))
+
+    def execute_constraints_satisfied(self, n):
+        out = np.empty((self.B, n), dtype=np.int32)
+        self._ck(self.L.stomp_engine_execute_constraints_satisfied(self.h, _ip(out), C.c_size_t(out.size)))
+        return out
+
     # ---- policy -------------------------------------------------------------------------
     def set_problems(self, start, goal):
         s, g = _f64(start), _f64(goal)
@@ -164,7 +180,7 @@ class Engine:
     def last_stats(self, cost=None, cf=None):
         cost = np.empty(self.B) if cost is None else cost
         cf = np.empty(self.B, dtype=np.int32) if cf is None else cf
-        st = _abi.IterStats(_dp(cost), _ip(cf), 0, 0)
+        st = _abi.IterStats(_dp(cost), _ip(cf), 0, 0, None)
         self._ck(self.L.stomp_engine_last_stats(self.h, C.byref(st)))
         return cost, cf
 
@@ -221,7 +237,7 @@ class Engine:
             return None
         cost = np.empty(self.B)
         cf = np.empty(self.B, dtype=np.int32)
-        st = _abi.IterStats(_dp(cost), _ip(cf), 0, 0)
+        st = _abi.IterStats(_dp(cost), _ip(cf), 0, 0, None)
         self._ck(self.L.stomp_engine_iterate(self.h, iteration_number, C.byref(st)))
         return cost, cf, st.num_generated_rollouts
 
@@ -231,7 +247,7 @@ class Engine:
             return None
         cost = np.empty(self.B)
         cf = np.empty(self.B, dtype=np.int32)
-        st = _abi.IterStats(_dp(cost), _ip(cf), 0, 0)
+        st = _abi.IterStats(_dp(cost), _ip(cf), 0, 0, None)
         self._ck(self.L.stomp_engine_run(self.h, first_iteration, count, C.byref(st)))
         return cost, cf, st.num_generated_rollouts
 
@@ -289,7 +305,7 @@ class Engine:
             _abi.FIELD_CONTROL_COST: (N, N), _abi.FIELD_CLIPPED_PARAMETERS: (B, R, D, N),
             _abi.FIELD_BEST_TRAJECTORY: (B, D, N), _abi.FIELD_NOISELESS_TRAJECTORY: (B, D, N),
         }
-        if field == _abi.FIELD_COLLISION_FREE:
+        if field in (_abi.FIELD_COLLISION_FREE, _abi.FIELD_CONSTRAINTS_SATISFIED):
             out = np.empty((B, R + 1), dtype=np.int32)
         else:
             out = np.empty(shapes[field])

@@ -538,3 +538,67 @@ def test_bad_arguments_are_rejected():
     shard = scenes.make_scenario("tiny", num_problems=2)
     with pytest.raises(RuntimeError, match="sharding"):
         _engine(shard, shard_rank=0, shard_world=2)
+
+
+def _constraint_scene():
+    sc = scenes.make_scenario("tiny", num_problems=2)
+    names = [g["name"] for g in sc.robot.segments]
+    palm, tip, base = names.index("r_gripper_palm_link"), names.index("r_gripper_l_finger_tip_frame"), names.index("torso_lift_link")
+    q = np.array([0.1, -0.2, 0.05, 0.97])
+    cons = [dict(segment=palm, orientation=(0.0, 0.0, 0.0, 1.0), tolerances=(0.3, 0.3, 4.0), weight=1.5, body_fixed=0),
+            dict(segment=tip, orientation=tuple(q), tolerances=(4.0, 0.2, 0.5), weight=0.7, body_fixed=1),
+            dict(segment=base, orientation=(0.0, 0.0, 0.1, 0.99), tolerances=(0.5, 0.5, 0.5), weight=2.0, body_fixed=0)]   # static segment
+    return sc, cons
+
+
+def test_orientation_constraints_cost_plugin():
+    """the second cost plugin (OrientationConstraintEvaluator): per-timestep costs and the satisfied flag."""
+    sc, cons = _constraint_scene()
+    eng, ors = _engine(sc), _oracles(sc)
+    eng.set_constraints(cons, 0.2)
+    for o in ors:
+        o.set_constraints(cons, 0.2)
+    params = _noisy_rollouts(sc, ors, np.random.default_rng(12), 5, sigma=0.3)
+    params[:, 0] = np.stack([o.get_parameters() for o in ors])
+    costs, cf = eng.execute(params)
+    sat = eng.execute_constraints_satisfied(5)
+    plain = _engine(sc).execute(params)[0]
+    assert np.abs(costs - plain).max() > 1e-3                     # the constraint term is really there
+    for b, o in enumerate(ors):
+        oc, ocf = o.execute(params[b])
+        assert_close(costs[b], oc, RTOL_F64, "state + constraint costs")
+        np.testing.assert_array_equal(cf[b], ocf)
+        np.testing.assert_array_equal(sat[b], o.execute_constraints_satisfied(5))
+    # a constraint with generous tolerances everywhere is satisfied; a tight one on a moving link is not
+    eng.set_constraints([dict(segment=cons[0]["segment"], orientation=(0, 0, 0, 1), tolerances=(4.0, 4.0, 4.0), weight=1.0)], 0.2)
+    eng.execute(params)
+    assert eng.execute_constraints_satisfied(5).all()
+    eng.set_constraints([dict(segment=cons[0]["segment"], orientation=(0, 0, 0, 1), tolerances=(1e-3, 1e-3, 1e-3), weight=1.0)], 0.2)
+    eng.execute(params)
+    assert not eng.execute_constraints_satisfied(5).any()
+
+
+def test_orientation_constraints_full_iterations_and_optimize():
+    sc, cons = _constraint_scene()
+    eng, ors = _engine(sc, keep_intermediates=1), _oracles(sc)
+    eng.set_constraints(cons[:2], 0.2)
+    for o in ors:
+        o.set_constraints(cons[:2], 0.2)
+    rng = np.random.default_rng(13)
+    L = ors[0].get(_abi.FIELD_NOISE_CHOLESKY)
+    for it in range(1, 5):
+        ngen = sc.num_rollouts if it == 1 else sc.num_rollouts - sc.num_reused_rollouts
+        eps = correlated_noise(L, rng, (2, ngen), sc.noise_stddev * sc.noise_decay ** (it - 1))
+        eng.inject_noise(eps)
+        cost, cf, _ = eng.iterate(it)
+        for b, o in enumerate(ors):
+            oc, ocf, _ = o.iterate(it, eps[b])
+            assert_close(cost[b], oc, RTOL_F64, "noise-less cost with constraints")
+            assert_close(eng.get(_abi.FIELD_THETA)[b], o.get(_abi.FIELD_THETA), RTOL_F64, "theta")
+            np.testing.assert_array_equal(eng.get(_abi.FIELD_CONSTRAINTS_SATISFIED)[b][[*range(ngen), sc.num_rollouts]],
+                                          o.get(_abi.FIELD_CONSTRAINTS_SATISFIED)[[*range(ngen), sc.num_rollouts]])
+    # optimize(): success needs collision free AND constraints satisfied (stomp_optimizer.cpp:301-316)
+    eng2 = _engine(sc)
+    eng2.set_constraints([dict(segment=cons[0]["segment"], orientation=(0, 0, 0, 1), tolerances=(1e-4, 1e-4, 1e-4), weight=1.0)], 0.2)
+    res = eng2.optimize(10, 3)
+    assert (res["success"] == 0).all() and (res["success_iteration"] == -1).all() and (res["iterations"] == 10).all()
