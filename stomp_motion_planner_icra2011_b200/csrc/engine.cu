@@ -63,7 +63,10 @@ struct Engine {
   stomp_engine_desc desc;
   int B = 0, D = 0, N = 0, R = 0, Rre = 0, K = 0;
   int device = 0, num_sms = 148;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, tail_stream = nullptr;
+  cudaStream_t ws = nullptr;   // stream the launch helpers currently enqueue on (stream or tail_stream)
+  cudaEvent_t ev_tail = nullptr, ev_upd = nullptr;
+  bool overlap = true, tail_dirty = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_copy_done[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   int inject_write = 0, inject_pending_buf = 0;
@@ -103,7 +106,7 @@ struct Engine {
   DevBuf<int> scratch_flags;
   DevBuf<stomp_sphere_debug> debug;
   DevBuf<double> part, minmax, sums;  // sharded / huge-R statistics
-  DevBuf<double> gen_scratch;         // time-major work buffer of k_generate
+  DevBuf<double> gen_scratch, gen_scratch2;   // time-major work buffers of k_generate (main / tail stream)
   DevBuf<double> extra_clipped, best_traj, best_cost, cost_log;   // optimize() bookkeeping
   DevBuf<unsigned char> track_state;
   DevBuf<int> num_done;
@@ -141,7 +144,7 @@ void begin_launch(Engine& e) {
     e.prof_b.push_back(b);
     e.prof_name.push_back("");
   }
-  cudaEventRecord(e.prof_a[e.prof_used], e.stream);
+  cudaEventRecord(e.prof_a[e.prof_used], e.ws);
 }
 
 int check_launch(Engine& e, const char* what) {
@@ -149,10 +152,20 @@ int check_launch(Engine& e, const char* what) {
   if (err != cudaSuccess) return fail(std::string(what) + ": " + cudaGetErrorString(err));
   e.launches++;
   if (e.prof_on) {
-    cudaEventRecord(e.prof_b[e.prof_used], e.stream);
+    cudaEventRecord(e.prof_b[e.prof_used], e.ws);
     e.prof_name[e.prof_used] = what;
     e.prof_used++;
   }
+  return 0;
+}
+
+// main stream waits for everything enqueued on the tail stream (device-side, no host sync)
+int join_streams(Engine& e) {
+  e.ws = e.stream;
+  if (!e.tail_dirty) return 0;
+  CUDA_TRY(cudaEventRecord(e.ev_tail, e.tail_stream));
+  CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_tail, 0));
+  e.tail_dirty = false;
   return 0;
 }
 
@@ -202,17 +215,20 @@ int upload_sqrt_table(Engine& e) {
 
 int launch_generate(Engine& e, GenArgs a) {
   const int N = e.N, tpb = 128;
-  const long long nvec = (long long)a.B * (a.extra ? 1 : a.R) * a.D;
+  if (a.r_count == 0 && !a.extra) { a.r_begin = 0; a.r_count = a.R; }
+  const long long nvec = (long long)a.B * (a.extra ? 1 : a.r_count) * a.D;
+  if (nvec == 0) return 0;
   const unsigned grid = unsigned((nvec + tpb - 1) / tpb);
   const size_t stride = size_t(grid) * tpb;
-  if (e.gen_scratch.n < stride * N) CUDA_TRY(e.gen_scratch.alloc(stride * N));
-  a.scratch = e.gen_scratch.p;
+  DevBuf<double>& scratch = e.ws == e.tail_stream ? e.gen_scratch2 : e.gen_scratch;
+  if (scratch.n < stride * N) CUDA_TRY(scratch.alloc(stride * N));
+  a.scratch = scratch.p;
   a.scratch_stride = stride;
   const size_t smem = ((STOMP_GEN_LDG_BAND ? 0 : size_t(N) * 17) + size_t(tpb / 32) * 2 * 32 * kTileLd) * 8;
   if (smem > 220 * 1024) return fail("num_time_steps too large for the band tables of k_generate");
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   begin_launch(e);
-  k_generate<<<grid, tpb, smem, e.stream>>>(a);
+  k_generate<<<grid, tpb, smem, e.ws>>>(a);
   return check_launch(e, "k_generate");
 }
 
@@ -259,7 +275,7 @@ int launch_cost_c(Engine& e, CostArgs<Real>& a, int num_problems) {
     grid = std::min(a.total_rollouts, std::max(1, per_sm) * e.num_sms);
   }
   begin_launch(e);
-  kern<<<grid, warps * 32, smem, e.stream>>>(a);
+  kern<<<grid, warps * 32, smem, e.ws>>>(a);
   return check_launch(e, "k_cost");
 }
 
@@ -330,7 +346,7 @@ int block_for(int N) { return std::min(1024, ((N + 31) / 32) * 32); }
 
 int launch_cumulative(Engine& e) {
   begin_launch(e);
-  k_cumulative<<<unsigned(e.B) * e.R, block_for(e.N), 0, e.stream>>>(e.R, e.D, e.N, e.desc.use_cumulative_costs,
+  k_cumulative<<<unsigned(e.B) * e.R, block_for(e.N), 0, e.ws>>>(e.R, e.D, e.N, e.desc.use_cumulative_costs,
                                                                     e.state[e.cur].p, e.control.p, e.cumulative.p, e.totals.p);
   return check_launch(e, "k_cumulative");
 }
@@ -358,7 +374,7 @@ int launch_update(Engine& e, int apply, bool fuse_extra_control) {
   CUDA_TRY(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   begin_launch(e);
   static const int tpb_max = getenv("STOMP_UPDATE_TPB") ? atoi(getenv("STOMP_UPDATE_TPB")) : 128;  // A/B on B200: 64:0.163 128:0.097 256:0.150 512:0.244 ms
-  k_update<<<unsigned(e.B) * groups, std::min(tpb_max, ((dpc * e.N + 31) / 32) * 32), smem, e.stream>>>(a);
+  k_update<<<unsigned(e.B) * groups, std::min(tpb_max, ((dpc * e.N + 31) / 32) * 32), smem, e.ws>>>(a);
   return check_launch(e, "k_update");
 }
 
@@ -368,30 +384,30 @@ int launch_minmax(Engine& e) {
   const int DN = e.D * e.N, rpc = (e.R + kChunks - 1) / kChunks, nch = (e.R + rpc - 1) / rpc;
   dim3 grid((DN + 127) / 128, nch);
   begin_launch(e);
-  k_minmax_partial<<<grid, 128, 0, e.stream>>>(e.R, DN, rpc, e.cumulative.p, e.part.p);
+  k_minmax_partial<<<grid, 128, 0, e.ws>>>(e.R, DN, rpc, e.cumulative.p, e.part.p);
   if (check_launch(e, "k_minmax_partial")) return 1;
   begin_launch(e);
-  k_pair_reduce<<<(2 * DN + 127) / 128, 128, 0, e.stream>>>(DN, nch, 1, e.part.p, e.minmax.p);
+  k_pair_reduce<<<(2 * DN + 127) / 128, 128, 0, e.ws>>>(DN, nch, 1, e.part.p, e.minmax.p);
   return check_launch(e, "k_pair_reduce");
 }
 int launch_sums(Engine& e) {
   const int DN = e.D * e.N, rpc = (e.R + kChunks - 1) / kChunks, nch = (e.R + rpc - 1) / rpc;
   dim3 grid((DN + 127) / 128, nch);
   begin_launch(e);
-  k_sums_partial<<<grid, 128, 0, e.stream>>>(e.R, DN, rpc, e.cumulative.p, e.noise.p, e.minmax.p, e.part.p);
+  k_sums_partial<<<grid, 128, 0, e.ws>>>(e.R, DN, rpc, e.cumulative.p, e.noise.p, e.minmax.p, e.part.p);
   if (check_launch(e, "k_sums_partial")) return 1;
   begin_launch(e);
-  k_pair_reduce<<<(2 * DN + 127) / 128, 128, 0, e.stream>>>(DN, nch, 0, e.part.p, e.sums.p);
+  k_pair_reduce<<<(2 * DN + 127) / 128, 128, 0, e.ws>>>(DN, nch, 0, e.part.p, e.sums.p);
   return check_launch(e, "k_pair_reduce");
 }
 int launch_finalize(Engine& e, int apply) {
   if (e.probabilities.p) {
     begin_launch(e);
-    k_probabilities<<<1184, 256, 0, e.stream>>>(e.R, e.D * e.N, e.cumulative.p, e.minmax.p, e.sums.p, e.probabilities.p);
+    k_probabilities<<<1184, 256, 0, e.ws>>>(e.R, e.D * e.N, e.cumulative.p, e.minmax.p, e.sums.p, e.probabilities.p);
     if (check_launch(e, "k_probabilities")) return 1;
   }
   begin_launch(e);
-  k_finalize<<<e.D, block_for(e.N), band_smem(e, 1), e.stream>>>(e.D, e.N, apply, e.sums.p, e.updates.p, e.theta.p, e.band_view());
+  k_finalize<<<e.D, block_for(e.N), band_smem(e, 1), e.ws>>>(e.D, e.N, apply, e.sums.p, e.updates.p, e.theta.p, e.band_view());
   return check_launch(e, "k_finalize");
 }
 
@@ -401,39 +417,60 @@ int set_noise_scale(Engine& e, const double* scale) {
   return upload(e, e.noise_scale, scale, size_t(e.D));
 }
 
-// generateRollouts bookkeeping (src/policy_improvement.cpp:166-176) + reuse selection + k_generate
-int step_get_rollouts(Engine& e, int iteration_number, bool with_control) {
+// generateRollouts bookkeeping (src/policy_improvement.cpp:166-176)
+struct RolloutPlan {
+  bool reuse = false, injected = false;
+};
+
+void plan_rollouts(Engine& e, RolloutPlan& p) {
   e.cur = 1 - e.cur;
   e.num_gen = e.R - e.Rre;
-  bool reuse = false;
+  p.reuse = false;
   if (!e.reused_next) {
     e.num_gen = e.R;
     if (e.Rre > 0) e.reused_next = true;
   } else {
-    reuse = true;
+    p.reuse = true;
   }
-  if (reuse) {
-    begin_launch(e);
-    k_select_reuse<<<e.B, 128, 0, e.stream>>>(e.totals.p, e.R, e.Rre, e.extra_added ? 1 : 0, e.reuse_src.p);
-    if (check_launch(e, "k_select_reuse")) return 1;
-    e.extra_added = false;
-    // reused rollouts keep their (stale) state costs: gather them into the current buffer with the parameters.
-    // Done by k_gather_state below (tiny).
-  }
+  p.injected = e.injected_pending;
+  e.injected_pending = false;
+  ++e.generation;   // the Philox "iteration" counter
+}
+
+int launch_select(Engine& e) {
+  begin_launch(e);
+  k_select_reuse<<<e.B, 128, 0, e.ws>>>(e.totals.p, e.R, e.Rre, e.extra_added ? 1 : 0, e.reuse_src.p);
+  if (check_launch(e, "k_select_reuse")) return 1;
+  e.extra_added = false;
+  return 0;
+}
+
+// noise / parameters / projected noise / control costs of rollout slots [r_begin, r_begin + r_count)
+int launch_generate_range(Engine& e, const RolloutPlan& p, int r_begin, int r_count, bool with_control) {
+  if (r_count <= 0) return 0;
   GenArgs a = base_gen_args(e);
   a.mode_generate = 1;
   a.mode_project = 1;
   a.mode_control = with_control ? 1 : 0;
-  a.injected = e.injected_pending ? 1 : 0;
-  (void)iteration_number;
-  a.iteration = ++e.generation;
+  a.injected = p.injected ? 1 : 0;
+  a.iteration = e.generation;
   a.control_weight = 0.5 * e.control_cost_weight;
-  const bool injected = e.injected_pending;
-  e.injected_pending = false;
-  if (injected) CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_copy_done[e.inject_pending_buf], 0));
+  a.r_begin = r_begin;
+  a.r_count = r_count;
+  const bool uses_injection = p.injected && r_begin < e.num_gen;
+  if (uses_injection) CUDA_TRY(cudaStreamWaitEvent(e.ws, e.ev_copy_done[e.inject_pending_buf], 0));
   if (launch_generate(e, a)) return 1;
-  if (injected) CUDA_TRY(cudaEventRecord(e.ev_consumed[e.inject_pending_buf], e.stream));
+  if (uses_injection) CUDA_TRY(cudaEventRecord(e.ev_consumed[e.inject_pending_buf], e.ws));
   return 0;
+}
+
+// serial form: reuse selection + all rollout slots on the current stream (step-by-step API, sharded phases)
+int step_get_rollouts(Engine& e, int iteration_number, bool with_control) {
+  (void)iteration_number;
+  RolloutPlan p;
+  plan_rollouts(e, p);
+  if (p.reuse && launch_select(e)) return 1;
+  return launch_generate_range(e, p, 0, e.R, with_control);
 }
 
 __global__ void k_gather_state(int R, int R_gen, int N, const int* __restrict__ reuse_src, const double* __restrict__ prev,
@@ -448,7 +485,7 @@ __global__ void k_gather_state(int R, int R_gen, int N, const int* __restrict__ 
 int gather_reused_state(Engine& e) {
   if (e.num_gen == e.R) return 0;
   begin_launch(e);
-  k_gather_state<<<unsigned(e.B) * (e.R - e.num_gen), 128, 0, e.stream>>>(e.R, e.num_gen, e.N, e.reuse_src.p,
+  k_gather_state<<<unsigned(e.B) * (e.R - e.num_gen), 128, 0, e.ws>>>(e.R, e.num_gen, e.N, e.reuse_src.p,
                                                                           e.state[1 - e.cur].p, e.extra_state.p, e.state[e.cur].p);
   return check_launch(e, "k_gather_state");
 }
@@ -484,7 +521,7 @@ int step_extra(Engine& e, bool run_cost, int iteration_number, bool have_control
     if (launch_generate(e, a)) return 1;
   }
   begin_launch(e);
-  k_extra_total<<<e.B, 128, 0, e.stream>>>(e.R, e.D, e.N, e.extra_state.p, e.extra_control.p, e.totals.p, e.noiseless_sum.p);
+  k_extra_total<<<e.B, 128, 0, e.ws>>>(e.R, e.D, e.N, e.extra_state.p, e.extra_control.p, e.totals.p, e.noiseless_sum.p);
   if (check_launch(e, "k_extra_total")) return 1;
   e.extra_added = true;
   return 0;
@@ -503,12 +540,10 @@ int iterate_front(Engine& e, int iteration_number) {  // up to and including k_c
   return launch_cumulative(e);
 }
 
-int iterate_once(Engine& e, int iteration_number) {
+int iterate_serial(Engine& e, int iteration_number) {
+  if (join_streams(e)) return 1;
   if (iterate_front(e, iteration_number)) return 1;
   if (e.huge_path()) {
-    if (e.B != 1) return fail("the sharded / huge-rollout statistics path supports num_problems == 1 only");
-    if (e.desc.rollout_shard_world > 1)
-      return fail("rollout-sharded engines iterate through stomp_engine_iterate_sharded_phase");
     if (launch_minmax(e) || launch_sums(e) || launch_finalize(e, 1)) return 1;
   } else {
     if (launch_update(e, 1, true)) return 1;
@@ -517,8 +552,55 @@ int iterate_once(Engine& e, int iteration_number) {
   return step_extra(e, true, iteration_number);
 }
 
+// One iteration on two streams.  The noise-less rollout of iteration i, the reuse selection it feeds and everything about the
+// REUSED rollout slots of iteration i+1 (gather, M*eps, control costs) only matter to iteration i+1's statistics, not to its
+// new rollouts: they run on the tail stream while the main stream already samples and costs the new rollouts of
+// iteration i+1.  (A caller that reads the statistics after every iteration synchronises both and sees no overlap.)
+//   main: [k_generate(new) -> k_cost(new)] -> wait(tail) -> k_cumulative -> k_update            -> record(upd)
+//   tail: [k_select_reuse -> k_generate(reused) -> k_gather_state] record(tail) ... wait(upd) -> k_cost(noise-less) -> k_extra_total
+int iterate_once(Engine& e, int iteration_number) {
+  if (e.huge_path()) {
+    if (e.B != 1) return fail("the sharded / huge-rollout statistics path supports num_problems == 1 only");
+    if (e.desc.rollout_shard_world > 1)
+      return fail("rollout-sharded engines iterate through stomp_engine_iterate_sharded_phase");
+  }
+  if (!e.overlap || e.prof_on) return iterate_serial(e, iteration_number);
+  e.ws = e.stream;
+  std::vector<double> scale(e.D);
+  for (int d = 0; d < e.D; ++d) scale[d] = e.noise_stddev[d] * std::pow(e.noise_decay[d], iteration_number - 1);
+  if (set_noise_scale(e, scale.data())) return 1;
+  e.control_cost_weight = e.desc.smoothness_cost_weight;
+  RolloutPlan p;
+  plan_rollouts(e, p);
+  if (p.reuse) {
+    e.ws = e.tail_stream;
+    if (launch_select(e) || launch_generate_range(e, p, e.num_gen, e.R - e.num_gen, true) || gather_reused_state(e)) {
+      e.ws = e.stream;
+      return 1;
+    }
+  }
+  CUDA_TRY(cudaEventRecord(e.ev_tail, e.tail_stream));   // also covers the previous iteration's noise-less rollout
+  e.ws = e.stream;
+  if (launch_generate_range(e, p, 0, e.num_gen, true)) return 1;
+  if (launch_cost(e, e.params[e.cur].p, size_t(e.R) * e.D * e.N, e.num_gen, e.B, iteration_number == 1, e.state[e.cur].p,
+                  size_t(e.R) * e.N, e.collision_free.p, e.R + 1, 0, e.clipped.p, nullptr, e.constraints_ok.p))
+    return 1;
+  CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_tail, 0));
+  if (launch_cumulative(e)) return 1;
+  const bool huge = e.huge_path();
+  if (huge ? (launch_minmax(e) || launch_sums(e) || launch_finalize(e, 1)) : launch_update(e, 1, true)) return 1;
+  CUDA_TRY(cudaEventRecord(e.ev_upd, e.stream));
+  e.ws = e.tail_stream;
+  CUDA_TRY(cudaStreamWaitEvent(e.tail_stream, e.ev_upd, 0));
+  const int rc = step_extra(e, true, iteration_number, !huge);
+  e.tail_dirty = true;
+  e.ws = e.stream;
+  return rc;
+}
+
 int fill_stats(Engine& e, stomp_iter_stats* stats) {
   if (!stats) return 0;
+  if (join_streams(e)) return 1;
   stats->num_generated_rollouts = e.num_gen;
   if (stats->noiseless_cost)
     CUDA_TRY(cudaMemcpyAsync(stats->noiseless_cost, e.noiseless_sum.p, size_t(e.B) * 8, cudaMemcpyDeviceToHost, e.stream));
@@ -577,10 +659,14 @@ int upload_constraints(Engine& e) {
 }
 Engine* E(void* h) { return static_cast<Engine*>(h); }
 
-#define ENGINE_OR_FAIL(h)                          \
+#define ENGINE_NOJOIN(h)                           \
   if (!(h)) return fail("null engine handle");     \
   Engine& e = *E(h);                               \
   CUDA_TRY(cudaSetDevice(e.device));
+
+#define ENGINE_OR_FAIL(h)                          \
+  ENGINE_NOJOIN(h)                                 \
+  if (join_streams(e)) return 1;
 
 }  // namespace
 
@@ -633,6 +719,12 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   if ((c = cudaDeviceGetAttribute(&e.num_sms, cudaDevAttrMultiProcessorCount, e.device)) != cudaSuccess) return bail(c, "cudaDeviceGetAttribute");
   if ((c = cudaEventCreate(&e.ev0)) != cudaSuccess || (c = cudaEventCreate(&e.ev1)) != cudaSuccess) return bail(c, "cudaEventCreate");
   if ((c = cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
+  if ((c = cudaStreamCreateWithFlags(&e.tail_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
+  if ((c = cudaEventCreateWithFlags(&e.ev_tail, cudaEventDisableTiming)) != cudaSuccess ||
+      (c = cudaEventCreateWithFlags(&e.ev_upd, cudaEventDisableTiming)) != cudaSuccess)
+    return bail(c, "cudaEventCreate");
+  e.ws = e.stream;
+  e.overlap = !(getenv("STOMP_NO_OVERLAP") && atoi(getenv("STOMP_NO_OVERLAP")) != 0);
   for (int i = 0; i < 2; ++i)
     if ((c = cudaEventCreateWithFlags(&e.ev_copy_done[i], cudaEventDisableTiming)) != cudaSuccess ||
         (c = cudaEventCreateWithFlags(&e.ev_consumed[i], cudaEventDisableTiming)) != cudaSuccess)
@@ -693,6 +785,9 @@ int stomp_engine_destroy(void* h) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+  if (e->tail_stream) { cudaStreamSynchronize(e->tail_stream); cudaStreamDestroy(e->tail_stream); }
+  if (e->ev_tail) cudaEventDestroy(e->ev_tail);
+  if (e->ev_upd) cudaEventDestroy(e->ev_upd);
   for (int i = 0; i < 2; ++i) {
     if (e->ev_copy_done[i]) cudaEventDestroy(e->ev_copy_done[i]);
     if (e->ev_consumed[i]) cudaEventDestroy(e->ev_consumed[i]);
@@ -816,7 +911,7 @@ int stomp_engine_build_sdf(void* h, const double size[3], const double origin[3]
       return 1;
     const unsigned grid = unsigned(std::min<long long>((total + 255) / 256, 148 * 32));
     begin_launch(e);
-    k_sdf_mark<<<std::max(1u, grid), 256, 0, e.stream>>>(int(shapes.size()), total, reinterpret_cast<const SdfShape*>(dshapes.p), dlat.p,
+    k_sdf_mark<<<std::max(1u, grid), 256, 0, e.ws>>>(int(shapes.size()), total, reinterpret_cast<const SdfShape*>(dshapes.p), dlat.p,
                                                         origin[0], origin[1], origin[2], resolution, nx, ny, nz, occ.p);
     if (check_launch(e, "k_sdf_mark")) return 1;
   }
@@ -824,14 +919,14 @@ int stomp_engine_build_sdf(void* h, const double size[3], const double origin[3]
   CUDA_TRY(e.vox.alloc(cells * (u8 ? 1 : 2)));
   const unsigned egrid = unsigned(std::min<size_t>((cells + 255) / 256, size_t(148) * 64));
   begin_launch(e);
-  k_edt_pass<0, uint16_t><<<egrid, 256, 0, e.stream>>>(nx, ny, nz, cap, occ.p, g1.p);
+  k_edt_pass<0, uint16_t><<<egrid, 256, 0, e.ws>>>(nx, ny, nz, cap, occ.p, g1.p);
   if (check_launch(e, "k_edt_pass")) return 1;
   begin_launch(e);
-  k_edt_pass<1, uint16_t><<<egrid, 256, 0, e.stream>>>(nx, ny, nz, cap, g1.p, g2.p);
+  k_edt_pass<1, uint16_t><<<egrid, 256, 0, e.ws>>>(nx, ny, nz, cap, g1.p, g2.p);
   if (check_launch(e, "k_edt_pass")) return 1;
   begin_launch(e);
-  if (u8) k_edt_pass<2, uint8_t><<<egrid, 256, 0, e.stream>>>(nx, ny, nz, cap, g2.p, reinterpret_cast<uint8_t*>(e.vox.p));
-  else k_edt_pass<2, uint16_t><<<egrid, 256, 0, e.stream>>>(nx, ny, nz, cap, g2.p, reinterpret_cast<uint16_t*>(e.vox.p));
+  if (u8) k_edt_pass<2, uint8_t><<<egrid, 256, 0, e.ws>>>(nx, ny, nz, cap, g2.p, reinterpret_cast<uint8_t*>(e.vox.p));
+  else k_edt_pass<2, uint16_t><<<egrid, 256, 0, e.ws>>>(nx, ny, nz, cap, g2.p, reinterpret_cast<uint16_t*>(e.vox.p));
   if (check_launch(e, "k_edt_pass")) return 1;
   CUDA_TRY(cudaStreamSynchronize(e.stream));
   e.sdf.vox = e.vox.p;
@@ -921,7 +1016,7 @@ int stomp_engine_update_parameters(void* h, const double* updates) {
   size_t n = size_t(e.B) * e.D * e.N;
   if (upload(e, e.updates, updates, n)) return 1;
   begin_launch(e);
-  k_axpy<<<unsigned((n + 255) / 256), 256, 0, e.stream>>>(n, e.updates.p, e.theta.p);
+  k_axpy<<<unsigned((n + 255) / 256), 256, 0, e.ws>>>(n, e.updates.p, e.theta.p);
   if (check_launch(e, "k_axpy")) return 1;
   CUDA_TRY(cudaStreamSynchronize(e.stream));
   return 0;
@@ -1086,14 +1181,14 @@ int stomp_engine_add_extra_rollouts(void* h, const double* costs) {
 }
 
 int stomp_engine_iterate(void* h, int32_t iteration_number, stomp_iter_stats* stats) {
-  ENGINE_OR_FAIL(h);
+  ENGINE_NOJOIN(h);
   if (!e.have_problems) return fail("set_problems must be called first");
   if (iterate_once(e, iteration_number)) return 1;
   return fill_stats(e, stats);
 }
 
 int stomp_engine_run(void* h, int32_t first_iteration, int32_t count, stomp_iter_stats* last_stats) {
-  ENGINE_OR_FAIL(h);
+  ENGINE_NOJOIN(h);
   if (!e.have_problems) return fail("set_problems must be called first");
   for (int i = 0; i < count; ++i)
     if (iterate_once(e, first_iteration + i)) return 1;
@@ -1115,19 +1210,23 @@ int stomp_engine_optimize(void* h, int32_t max_iterations, int32_t max_after_cf,
   int it = 0;
   for (; it < max_iterations; ++it) {
     if (iterate_once(e, it + 1)) return 1;
+    if (e.tail_dirty) e.ws = e.tail_stream;   // the bookkeeping follows the noise-less rollout on its stream
     begin_launch(e);
-    k_track_best<<<e.B, 128, 0, e.stream>>>(it, max_after_cf, e.D * e.N, e.R + 1, e.R, e.noiseless_sum.p, e.collision_free.p,
+    k_track_best<<<e.B, 128, 0, e.ws>>>(it, max_after_cf, e.D * e.N, e.R + 1, e.R, e.noiseless_sum.p, e.collision_free.p,
                                             e.constraints_ok.p, e.extra_clipped.p, reinterpret_cast<TrackState*>(e.track_state.p), e.best_cost.p,
                                             e.best_traj.p, want_log ? e.cost_log.p : nullptr, e.B, e.num_done.p);
     if (check_launch(e, "k_track_best")) return 1;
+    e.ws = e.stream;
     if ((it + 1) % check_every == 0 && it + 1 < max_iterations) {
       int done = 0;
+      if (join_streams(e)) return 1;
       CUDA_TRY(cudaMemcpyAsync(&done, e.num_done.p, sizeof(int), cudaMemcpyDeviceToHost, e.stream));
       CUDA_TRY(cudaStreamSynchronize(e.stream));
       if (done >= e.B) { ++it; break; }
     }
   }
   const int ran = std::min(it, max_iterations);
+  if (join_streams(e)) return 1;
   std::vector<TrackState> st(e.B);
   CUDA_TRY(cudaMemcpyAsync(st.data(), e.track_state.p, st.size() * sizeof(TrackState), cudaMemcpyDeviceToHost, e.stream));
   if (stats && stats->best_cost) CUDA_TRY(cudaMemcpyAsync(stats->best_cost, e.best_cost.p, size_t(e.B) * 8, cudaMemcpyDeviceToHost, e.stream));

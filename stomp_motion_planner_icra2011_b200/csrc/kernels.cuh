@@ -137,6 +137,7 @@ __global__ void k_select_reuse(const double* __restrict__ totals, int R, int R_r
 struct GenArgs {
   int B, R, D, N;
   int R_gen;                 // slots < R_gen are new, slots >= R_gen are reused (gathered)
+  int r_begin, r_count;      // rollout slots processed by this launch: [r_begin, r_begin + r_count)
   int mode_generate;         // 1: produce noise/params (new: sample or injected; reused: gather)
   int mode_project;          // 1: y = M * noise is added before the stencil; 0: stencil on params + eps_in
   int mode_control;          // 1: compute control costs
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
   __syncthreads();
 #endif
 
-  const int per_problem = (a.extra ? 1 : a.R) * a.D;
+  const int per_problem = (a.extra ? 1 : a.r_count) * a.D;
   const long long nvec = (long long)a.B * per_problem;
   const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = v < nvec;
@@ -329,8 +330,9 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
     int rem = int(v - (long long)b * per_problem);
     r = rem / a.D;
     d = rem - r * a.D;
+    r += a.extra ? 0 : a.r_begin;
   }
-  const size_t row_off = size_t(v) * N;
+  const size_t row_off = a.extra ? (size_t(b) * a.D + d) * N : ((size_t(b) * a.R + r) * a.D + d) * N;
   const double* th_row = active ? a.theta + (size_t(b) * a.D + d) * N : nullptr;
   double* wb = a.scratch + v;                 // time-major scratch: element i at wb[i * sstride]
   const size_t sstride = a.scratch_stride;

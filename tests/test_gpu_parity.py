@@ -602,3 +602,24 @@ def test_orientation_constraints_full_iterations_and_optimize():
     eng2.set_constraints([dict(segment=cons[0]["segment"], orientation=(0, 0, 0, 1), tolerances=(1e-4, 1e-4, 1e-4), weight=1.0)], 0.2)
     res = eng2.optimize(10, 3)
     assert (res["success"] == 0).all() and (res["success_iteration"] == -1).all() and (res["iterations"] == 10).all()
+
+
+def test_two_stream_overlap_is_invisible():
+    """iterations launched back to back (noise-less rollout and reused-slot work of iteration i overlapped with the new
+    rollouts of iteration i+1 on a second stream) give bit-identical results to iterations that are synchronised one by one."""
+    sc = scenes.make_scenario("C1", num_problems=5)
+    a, b, c = _engine(sc, keep_intermediates=1), _engine(sc, keep_intermediates=1), _engine(sc, keep_intermediates=1)
+    its = 9
+    for it in range(1, its + 1):
+        ca, fa, _ = a.iterate(it)                 # host sync after every iteration
+    b.run(1, its)                                 # one call, no host sync in between
+    for it in range(1, its + 1):
+        c.iterate(it, stats=False)                # async launches
+    cb, fb = b.last_stats()
+    cc, fc = c.last_stats()
+    for other, cost, cf in ((b, cb, fb), (c, cc, fc)):
+        np.testing.assert_array_equal(ca, cost)
+        np.testing.assert_array_equal(fa, cf)
+        for f in (_abi.FIELD_THETA, _abi.FIELD_PARAMETERS, _abi.FIELD_STATE_COSTS, _abi.FIELD_CONTROL_COSTS, _abi.FIELD_NOISE,
+                  _abi.FIELD_ROLLOUT_TOTAL_COSTS, _abi.FIELD_PROBABILITIES, _abi.FIELD_NOISELESS_COSTS):
+            np.testing.assert_array_equal(a.get(f), other.get(f))
