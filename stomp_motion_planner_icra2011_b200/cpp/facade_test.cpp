@@ -134,6 +134,11 @@ int main() {
   if (D != 4 || N != 60 || cc.size() != 4u || cc[0].rows() != 60 || np[0] != 60 || !(cc[0](30, 30) > 0.0)) { std::printf("FAIL policy getters\n"); return 1; }
   CovariantMovementPrimitive* alias = dynamic_cast<CovariantMovementPrimitive*>(pol.get());
   if (!alias) { std::printf("FAIL alias\n"); return 1; }
+  std::vector<VectorXd> mj;
+  fillInMinJerk(start, goal, 60, 0.05, mj);
+  const double mid = 0.5 * (start[0] + goal[0]);
+  if (mj.size() != 4u || mj[0].size() != 60u || std::fabs(0.5 * (mj[0][29] + mj[0][30]) - mid) > 1e-9 ||
+      std::fabs(mj[0][0] - start[0]) > 1e-3 || std::fabs(mj[0][59] - goal[0]) > 1e-3) { std::printf("FAIL min jerk\n"); return 1; }
   std::printf("facade ok\n");
   return 0;
 }

@@ -77,6 +77,30 @@ struct StompCollisionSpace {
   double origin[3] = {0, 0, 0}, resolution = 0.015;
 };
 
+// StompTrajectory::fillInMinJerk (src/stomp_trajectory.cpp:179-223): quintic between the fixed points before / after the
+// free block with zero start / end velocity and acceleration.  trajectory[d][t], t = 0 .. num_free_points-1.
+inline void fillInMinJerk(const VectorXd& start, const VectorXd& goal, int num_free_points, double discretization,
+                          std::vector<VectorXd>& trajectory) {
+  double T[6];
+  T[0] = 1.0;
+  T[1] = (num_free_points + 1) * discretization;
+  for (int i = 2; i <= 5; ++i) T[i] = T[i - 1] * T[1];
+  trajectory.assign(start.size(), VectorXd(num_free_points, 0.0));
+  for (size_t j = 0; j < start.size(); ++j) {
+    const double x0 = start[j], x1 = goal[j];
+    const double coeff[6] = {x0, 0, 0, (-20 * x0 + 20 * x1) / (2 * T[3]), (30 * x0 - 30 * x1) / (2 * T[4]), (-12 * x0 + 12 * x1) / (2 * T[5])};
+    for (int i = 1; i <= num_free_points; ++i) {
+      double t[6];
+      t[0] = 1.0;
+      t[1] = i * discretization;
+      for (int k = 2; k <= 5; ++k) t[k] = t[k - 1] * t[1];
+      double v = 0.0;
+      for (int k = 0; k <= 5; ++k) v += t[k] * coeff[k];
+      trajectory[j][i - 1] = v;
+    }
+  }
+}
+
 // shared RAII owner of one engine handle
 class Engine {
  public:

@@ -76,6 +76,20 @@ class Robot:
             pos = origin * (i / max(count - 1.0, 1.0))
             self.spheres.append(dict(segment=seg, radius=radius, clearance=clearance, pos=tuple(pos)))
 
+    def add_attached_object(self, seg, shape, dimensions, position, padding=0.0, clearance=0.07):
+        """StompRobotModel::generateAttachedObjectCollisionPoints (src/stomp_robot_model.cpp:377-453): one collision point per
+        attached shape = its bounding sphere (geometric_shapes bodies::computeBoundingSphere, padded) in the owner link's frame.
+        shape: 'sphere' (r), 'box' (x, y, z), 'cylinder' (r, length); position: shape centre in the link frame."""
+        if shape == "sphere":
+            radius = dimensions[0] + padding
+        elif shape == "box":
+            radius = math.sqrt(sum((d / 2.0 + padding) ** 2 for d in dimensions))
+        elif shape == "cylinder":
+            radius = math.sqrt((dimensions[0] + padding) ** 2 + (dimensions[1] / 2.0 + padding) ** 2)
+        else:
+            raise ValueError(shape)
+        self.spheres.append(dict(segment=seg, radius=radius, clearance=clearance, pos=tuple(float(v) for v in position)))
+
     # ---- ctypes views -------------------------------------------------------------------
     def c_segments(self):
         arr = (_abi.Segment * len(self.segments))()
@@ -193,6 +207,19 @@ def random_tree(rng, num_group=5, num_extra=6, spheres=12):
                                clearance=0.07, pos=tuple(rng.uniform(-0.2, 0.2, 3))))
     rb.limits = [(int(rng.integers(0, 2)), -0.8, 0.9) for _ in range(num_group)]
     return rb
+
+
+def fill_in_min_jerk(start, goal, num_free_points, discretization):
+    """StompTrajectory::fillInMinJerk (src/stomp_trajectory.cpp:179-223): quintic with zero start / end velocity and
+    acceleration between the fixed points before and after the free block.  Returns [D][num_free_points]."""
+    start, goal = np.asarray(start, float), np.asarray(goal, float)
+    T1 = (num_free_points + 1) * discretization
+    T = [T1 ** k for k in range(6)]
+    c3 = (-20 * start + 20 * goal) / (2 * T[3])
+    c4 = (30 * start - 30 * goal) / (2 * T[4])
+    c5 = (-12 * start + 12 * goal) / (2 * T[5])
+    t = (np.arange(1, num_free_points + 1) * discretization)[None, :]
+    return start[:, None] + c3[:, None] * t ** 3 + c4[:, None] * t ** 4 + c5[:, None] * t ** 5
 
 
 # ---- distance fields ---------------------------------------------------------------------

@@ -91,3 +91,28 @@ def test_urdf_rotated_axis_is_expressed_in_the_parent_frame():
       <axis xyz="1 0 0"/><limit lower="-1" upper="1"/></joint></robot>"""
     rb = robot_from_urdf(urdf, ["j"], "a")
     np.testing.assert_allclose(rb.segments[1]["axis"], (0.0, 1.0, 0.0), atol=1e-15)   # R_pj * (1,0,0)
+
+
+def test_attached_object_bounding_spheres():
+    rb = scenes.pr2_right_arm()
+    palm = [g["name"] for g in rb.segments].index("r_gripper_palm_link")
+    n0 = len(rb.spheres)
+    rb.add_attached_object(palm, "cylinder", (0.02, 0.3), (0.15, 0.0, 0.0), padding=0.01)
+    rb.add_attached_object(palm, "box", (0.1, 0.2, 0.3), (0.2, 0.0, 0.0))
+    rb.add_attached_object(palm, "sphere", (0.05,), (0.0, 0.1, 0.0))
+    assert len(rb.spheres) == n0 + 3
+    np.testing.assert_allclose([s["radius"] for s in rb.spheres[n0:]],
+                               [np.hypot(0.03, 0.16), np.sqrt(0.05 ** 2 + 0.1 ** 2 + 0.15 ** 2), 0.05])
+    assert all(s["segment"] == palm for s in rb.spheres[n0:])
+
+
+def test_min_jerk_initial_trajectory():
+    start, goal = np.array([0.3, -1.0]), np.array([1.1, 0.4])
+    N, dt = 99, 0.05
+    traj = scenes.fill_in_min_jerk(start, goal, N, dt)
+    full = np.concatenate([start[:, None], traj, goal[:, None]], axis=1)
+    s = np.arange(N + 2) / (N + 1)
+    want = start[:, None] + (goal - start)[:, None] * (10 * s ** 3 - 15 * s ** 4 + 6 * s ** 5)     # the min-jerk polynomial
+    np.testing.assert_allclose(full, want, rtol=1e-12, atol=1e-14)
+    vel = np.diff(full, axis=1) / dt
+    assert np.abs(vel[:, 0]).max() < 1e-3 and np.abs(vel[:, -1]).max() < 1e-3      # zero boundary velocity
