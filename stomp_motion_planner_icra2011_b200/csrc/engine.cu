@@ -256,23 +256,38 @@ GenArgs base_gen_args(Engine& e) {
 
 template <typename Real, bool kDebug, int kVox, bool kCons>
 int launch_cost_c(Engine& e, CostArgs<Real>& a, int num_problems) {
-  const int ntiles = (e.N + kTileSteps - 1) / kTileSteps;
-  int warps = std::min(ntiles, 4);
-  warps = std::max(warps, std::min(e.D, 4));  // joint-limit pass likes a few warps
-  size_t smem = ((size_t(e.D) * e.N * 8 + 15) & ~size_t(15)) + size_t(e.num_nodes) * sizeof(DevNode<Real>) + size_t(e.K) * sizeof(DevSphere<Real>) +
-                256 * sizeof(Real) + size_t(warps) * 12 * 32 * sizeof(Real) + e.constraints.size() * sizeof(DevConstraint<Real>);
+  a.total_rollouts = num_problems * a.n_rollouts;
+  // lane packing: concatenate the timelines of `pack` rollouts per CTA when that needs fewer 29-step warp tiles per rollout
+  const int seg = e.N + 3;
+  auto tiles_for = [&](int p) { return (p * seg - 3 + kTileSteps - 1) / kTileSteps; };
+  auto smem_for = [&](int p, int warps) {
+    return ((size_t(p) * e.D * e.N * 8 + 15) & ~size_t(15)) + size_t(e.num_nodes) * sizeof(DevNode<Real>) +
+           size_t(e.K) * sizeof(DevSphere<Real>) + 256 * sizeof(Real) + size_t(warps) * 12 * 32 * sizeof(Real) +
+           e.constraints.size() * sizeof(DevConstraint<Real>);
+  };
+  const int max_warps = kCostMaxThreads / 32;
+  int pack = 1;
+  if (!kDebug)
+    for (int p = 2; p <= 4 && p <= a.total_rollouts; ++p)
+      if (tiles_for(p) * pack < tiles_for(pack) * p && smem_for(p, std::min(tiles_for(p), max_warps)) <= 56 * 1024) pack = p;
+  const int tiles = tiles_for(pack);
+  int warps = std::min(tiles, max_warps);
+  warps = std::max(warps, std::min(pack * e.D, 4));  // joint-limit pass likes a few warps
+  const size_t smem = smem_for(pack, warps);
+  if (smem > 220 * 1024) return fail("trajectory + robot tables exceed shared memory");
   auto kern = k_cost<Real, kDebug, kVox, kCons>;
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  if (smem > 220 * 1024) return fail("trajectory + robot tables exceed shared memory");
-  a.total_rollouts = num_problems * a.n_rollouts;
-  // STOMP_PERSISTENT=1: one CTA per resident slot walking rollouts with a grid stride; default: one CTA per
-  // rollout (the hardware block scheduler balances rollouts whose joint-limit projection takes longer)
+  a.pack = pack;
+  a.tiles_per_job = tiles;
+  const int njobs = (a.total_rollouts + pack - 1) / pack;
+  // STOMP_PERSISTENT=1: one CTA per resident slot walking jobs with a grid stride; default: one CTA per job
+  // (the hardware block scheduler balances rollouts whose joint-limit projection takes longer)
   static const bool persistent = getenv("STOMP_PERSISTENT") && atoi(getenv("STOMP_PERSISTENT")) != 0;
-  int grid = a.total_rollouts;
+  int grid = njobs;
   if (persistent) {
     int per_sm = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
-    grid = std::min(a.total_rollouts, std::max(1, per_sm) * e.num_sms);
+    grid = std::min(grid, std::max(1, per_sm) * e.num_sms);
   }
   begin_launch(e);
   kern<<<grid, warps * 32, smem, e.ws>>>(a);

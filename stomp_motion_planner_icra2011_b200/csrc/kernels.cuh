@@ -553,6 +553,8 @@ template <typename Real>
 struct CostArgs {
   int n_rollouts;            // rollouts per problem processed by this launch
   int total_rollouts;        // problems * n_rollouts
+  int pack;                  // rollouts whose timelines one CTA concatenates (see k_cost)
+  int tiles_per_job;         // ceil((pack * (N + 3) - 3) / 29)
   int D, N, K, num_nodes;
   int include_pads;          // 1: start/goal padding points count towards collision_free (iteration_ == 0)
   size_t params_problem_stride, params_rollout_stride;  // in doubles
@@ -759,12 +761,20 @@ __device__ __forceinline__ void cta_copy_async16(void* dst_smem, const void* src
 
 // Persistent CTAs: the grid is sized to the machine (SMs x resident CTAs) and every CTA walks rollouts with a
 // grid stride, so the robot tables are staged in shared memory once per CTA instead of once per rollout.
+// Lane packing: a warp tile is a window of 32 consecutive points of the CTA's *concatenated* timeline
+//   [rollout 0: t = -1 .. N+1][rollout 1: t = -1 .. N+1] ...          (N + 3 points per rollout, `pack` rollouts)
+// advanced by 29 points per tile; lanes 1..29 of a window are productive when their point is a free timestep, and their
+// velocity taps (-1, +1, +2) are always points of the same rollout inside the same window.  With pack = 1 this is the
+// plain "29 timesteps per warp" tiling; packing 2 rollouts of N = 100 needs 7 warps instead of 8.
+constexpr int kCostMaxThreads = 224;   // 7 warps; 72 registers -> 4 CTAs (28 warps) per SM
+
 template <typename Real, bool kDebug, int kVox, bool kCons>
-__global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<Real> a) {
+__global__ void __launch_bounds__(kCostMaxThreads, 4) k_cost(CostArgs<Real> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int D = a.D, N = a.N, K = a.K;
-  double* q = reinterpret_cast<double*>(smem_raw);                        // [D][N] clipped trajectory
-  DevNode<Real>* nodes = reinterpret_cast<DevNode<Real>*>(smem_raw + ((size_t(D) * N * 8 + 15) & ~size_t(15)));
+  const int D = a.D, N = a.N, K = a.K, P = a.pack;
+  const int DN = D * N;
+  double* q = reinterpret_cast<double*>(smem_raw);                        // [P][D][N] clipped trajectories
+  DevNode<Real>* nodes = reinterpret_cast<DevNode<Real>*>(smem_raw + ((size_t(P) * DN * 8 + 15) & ~size_t(15)));
   DevSphere<Real>* spheres = reinterpret_cast<DevSphere<Real>*>(nodes + a.num_nodes);
   Real* sqrt_tab = reinterpret_cast<Real*>(spheres + K);                  // [256]
 
@@ -788,31 +798,38 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
   g.nx1 = a.sdf.nx - 1; g.ny1 = a.sdf.ny - 1; g.nz1 = a.sdf.nz - 1; g.sny = a.sdf.ny; g.snz = a.sdf.nz;
   const Real c_m1 = Real(a.inv_time * (-2.0 / 6.0)), c_0 = Real(a.inv_time * (-3.0 / 6.0)), c_p1 = Real(a.inv_time * (6.0 / 6.0)),
              c_p2 = Real(a.inv_time * (-1.0 / 6.0));
-  const int ntiles = (N + kTileSteps - 1) / kTileSteps;
+  const int ntiles = a.tiles_per_job;
+  const int seg = N + 3;                       // timeline points per rollout: t = -1 .. N+1
   const void* vox = a.sdf.vox;
+  const int njobs = (a.total_rollouts + P - 1) / P;
 
-  for (int job = blockIdx.x; job < a.total_rollouts; job += gridDim.x) {
-    const int b = job / a.n_rollouts, r = job - b * a.n_rollouts;
-    const double* src = a.params + size_t(b) * a.params_problem_stride + size_t(r) * a.params_rollout_stride;
-    __syncthreads();   // previous rollout fully consumed
-    for (int i = threadIdx.x; i < D * N; i += blockDim.x) {
+  for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+    const int first = job * P, count = min(P, a.total_rollouts - first);
+    __syncthreads();   // previous job fully consumed
+    for (int i = threadIdx.x; i < count * DN; i += blockDim.x) {
+      const int p = i / DN, k = i - p * DN, ro = first + p;
+      const int b = ro / a.n_rollouts, r = ro - b * a.n_rollouts;
+      const double* src = a.params + size_t(b) * a.params_problem_stride + size_t(r) * a.params_rollout_stride;
       const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(q + i));
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(src + i) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(src + k) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    int* flag = a.collision_free ? a.collision_free + size_t(b) * a.flag_problem_stride + a.flag_offset + r : nullptr;
-    int* cflag = a.constraints_satisfied ? a.constraints_satisfied + size_t(b) * a.flag_problem_stride + a.flag_offset + r : nullptr;
-    if (threadIdx.x == 0 && flag) *flag = 1;   // ordered before the warps' "= 0" stores by the barriers below
-    if (threadIdx.x == 0 && cflag) *cflag = 1;
+    if (int(threadIdx.x) < count) {   // flags start at "free / satisfied"; ordered before the "= 0" stores by the barriers below
+      const int ro = first + threadIdx.x;
+      const int b = ro / a.n_rollouts, r = ro - b * a.n_rollouts;
+      if (a.collision_free) a.collision_free[size_t(b) * a.flag_problem_stride + a.flag_offset + r] = 1;
+      if (a.constraints_satisfied) a.constraints_satisfied[size_t(b) * a.flag_problem_stride + a.flag_offset + r] = 1;
+    }
     __syncthreads();
 
-    // ---- handleJointLimits: warp per joint, <= 11 passes of (arg max violation, rank-1 correction) ----------
-    for (int d = warp; d < D; d += nwarps) {
+    // ---- handleJointLimits: warp per joint column, <= 11 passes of (arg max violation, rank-1 correction) ----------
+    for (int col = warp; col < count * D; col += nwarps) {
+      const int d = col % D;
       if (!a.has_limits[d]) continue;
       const double jmax = a.limit_max[d], jmin = a.limit_min[d];
-      double* qd = q + size_t(d) * N;
-      for (int count = 0; count < 11; ++count) {
+      double* qd = q + size_t(col) * N;
+      for (int pass = 0; pass < 11; ++pass) {
         double best_abs = 1e-6, best_amount = 0.0;
         int best_idx = -1;
         for (int i = lane; i < N; i += 32) {
@@ -832,28 +849,36 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
           if (take) { best_abs = oa; best_amount = om; best_idx = oi; }
         }
         if (best_idx < 0) break;
-        const double* col = a.qinv_t + size_t(best_idx) * N;
-        double multiplier = best_amount / col[best_idx];
-        for (int i = lane; i < N; i += 32) qd[i] += multiplier * col[i];
+        const double* colv = a.qinv_t + size_t(best_idx) * N;
+        double multiplier = best_amount / colv[best_idx];
+        for (int i = lane; i < N; i += 32) qd[i] += multiplier * colv[i];
         __syncwarp();
       }
     }
     __syncthreads();
     if (a.clipped) {
-      double* dst = a.clipped + size_t(b) * a.params_problem_stride + size_t(r) * a.params_rollout_stride;
-      for (int i = threadIdx.x; i < D * N; i += blockDim.x) dst[i] = q[i];
+      for (int i = threadIdx.x; i < count * DN; i += blockDim.x) {
+        const int p = i / DN, k = i - p * DN, ro = first + p;
+        const int b = ro / a.n_rollouts, r = ro - b * a.n_rollouts;
+        a.clipped[size_t(b) * a.params_problem_stride + size_t(r) * a.params_rollout_stride + k] = q[i];
+      }
     }
 
     // ---- FK + spheres + SDF + velocity + cost -------------------------------------------------------
-    const double* ps = a.pad_start + size_t(b) * D;
-    const double* pg = a.pad_goal + size_t(b) * D;
-    double* out = a.costs + size_t(b) * a.cost_problem_stride + size_t(r) * N;
-    int collided = 0, violated = 0;
-
     for (int tile = warp; tile < ntiles; tile += nwarps) {
-      const int t = tile * kTileSteps - 1 + lane;      // trajectory point of this lane (-1 .. N+1 are meaningful)
-      const bool productive = lane >= 1 && lane <= kTileSteps && t < N;
-      const bool counts = productive || (a.include_pads && (t == -1 || t == N));
+      // this lane's point of the concatenated timeline
+      const int gp = tile * kTileSteps + lane;
+      const int p = min(gp / seg, count - 1);                 // rollout within the pack (clamped: surplus lanes idle on the last one)
+      const int t = gp - (gp / seg) * seg - 1 + (gp / seg - p) * seg;   // -1 .. N+1 for real points, beyond for surplus lanes
+      const bool real_point = gp / seg < count;
+      const int ro = first + p;
+      const int b = ro / a.n_rollouts, r = ro - b * a.n_rollouts;
+      const double* qp = q + size_t(p) * DN;
+      const double* ps = a.pad_start + size_t(b) * D;
+      const double* pg = a.pad_goal + size_t(b) * D;
+      const bool productive = real_point && lane >= 1 && lane <= kTileSteps && t >= 0 && t < N;
+      const bool counts = productive || (a.include_pads && real_point && (t == -1 || t == N));
+      int collided = 0, violated = 0;
       Real cost = Real(0), ccost = Real(0);
       Real F[12], saved[kMaxSlots][12];
 #pragma unroll
@@ -870,7 +895,7 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
         Real Pm[12];
         {
           Real qv = Real(0);
-          if (nd.q_index >= 0) qv = Real(t < 0 ? ps[nd.q_index] : (t >= N ? pg[nd.q_index] : q[size_t(nd.q_index) * N + t]));
+          if (nd.q_index >= 0) qv = Real(t < 0 ? ps[nd.q_index] : (t >= N ? pg[nd.q_index] : qp[size_t(nd.q_index) * N + t]));
           if (nd.type == STOMP_JOINT_REVOLUTE) {
             Real sn, cs;
             Math<Real>::sincos_(qv, &sn, &cs);
@@ -970,11 +995,14 @@ __global__ void __launch_bounds__(128, STOMP_KCOST_MIN_BLOCKS) k_cost(CostArgs<R
           }
         }
       }
-      if (productive) out[t] = kCons ? a.obstacle_weight * double(cost) + a.constraint_weight * double(ccost)
-                                     : a.obstacle_weight * double(cost);
+      if (productive) {
+        double* out = a.costs + size_t(b) * a.cost_problem_stride + size_t(r) * N;
+        out[t] = kCons ? a.obstacle_weight * double(cost) + a.constraint_weight * double(ccost) : a.obstacle_weight * double(cost);
+      }
+      if (collided && a.collision_free) a.collision_free[size_t(b) * a.flag_problem_stride + a.flag_offset + r] = 0;
+      if (kCons && violated && a.constraints_satisfied)
+        a.constraints_satisfied[size_t(b) * a.flag_problem_stride + a.flag_offset + r] = 0;
     }
-    if (collided && flag) *flag = 0;
-    if (violated && cflag) *cflag = 0;
   }
 }
 
