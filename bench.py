@@ -204,10 +204,13 @@ def run_engine(args):
         raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
     dist = None
+    json_out = sys.stdout
     if world > 1:
-        # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION/INFO; stdout must carry the JSON line only
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner to fd 1 when the communicator is created; stdout must carry the JSON line only:
+        # keep a private copy of the real stdout for the JSON line and point fd 1 at stderr for everything else
+        sys.stdout.flush()
+        json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -373,7 +376,8 @@ def run_engine(args):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
