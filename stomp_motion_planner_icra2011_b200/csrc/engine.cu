@@ -224,7 +224,7 @@ int launch_generate(Engine& e, GenArgs a) {
   if (scratch.n < stride * N) CUDA_TRY(scratch.alloc(stride * N));
   a.scratch = scratch.p;
   a.scratch_stride = stride;
-  const size_t smem = ((STOMP_GEN_LDG_BAND ? 0 : size_t(N) * 17) + size_t(tpb / 32) * 2 * 32 * kTileLd) * 8;
+  const size_t smem = (size_t(N) * 17 + size_t(tpb / 32) * 2 * 32 * kTileLd) * 8;
   if (smem > 220 * 1024) return fail("num_time_steps too large for the band tables of k_generate");
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   begin_launch(e);
@@ -280,17 +280,10 @@ int launch_cost_c(Engine& e, CostArgs<Real>& a, int num_problems) {
   a.pack = pack;
   a.tiles_per_job = tiles;
   const int njobs = (a.total_rollouts + pack - 1) / pack;
-  // STOMP_PERSISTENT=1: one CTA per resident slot walking jobs with a grid stride; default: one CTA per job
-  // (the hardware block scheduler balances rollouts whose joint-limit projection takes longer)
-  static const bool persistent = getenv("STOMP_PERSISTENT") && atoi(getenv("STOMP_PERSISTENT")) != 0;
-  int grid = njobs;
-  if (persistent) {
-    int per_sm = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
-    grid = std::min(grid, std::max(1, per_sm) * e.num_sms);
-  }
+  // one CTA per job: the hardware block scheduler balances rollouts whose joint-limit projection takes longer (a persistent
+  // grid-stride schedule was 15 % slower, profiles/README.md)
   begin_launch(e);
-  kern<<<grid, warps * 32, smem, e.ws>>>(a);
+  kern<<<njobs, warps * 32, smem, e.ws>>>(a);
   return check_launch(e, "k_cost");
 }
 
@@ -359,10 +352,12 @@ int launch_cost(Engine& e, const double* params, size_t pstride, int n_rollouts,
 
 int block_for(int N) { return std::min(1024, ((N + 31) / 32) * 32); }
 
-int launch_cumulative(Engine& e) {
+int launch_cumulative(Engine& e, int r_begin = 0, int r_count = -1) {
+  if (r_count < 0) r_count = e.R - r_begin;
+  if (r_count == 0) return 0;
   begin_launch(e);
-  k_cumulative<<<unsigned(e.B) * e.R, block_for(e.N), 0, e.ws>>>(e.R, e.D, e.N, e.desc.use_cumulative_costs,
-                                                                    e.state[e.cur].p, e.control.p, e.cumulative.p, e.totals.p);
+  k_cumulative<<<unsigned(e.B) * r_count, block_for(e.N), 0, e.ws>>>(e.R, r_begin, r_count, e.D, e.N, e.desc.use_cumulative_costs,
+                                                                       e.state[e.cur].p, e.control.p, e.cumulative.p, e.totals.p);
   return check_launch(e, "k_cumulative");
 }
 
@@ -388,7 +383,7 @@ int launch_update(Engine& e, int apply, bool fuse_extra_control) {
   const int groups = (e.D + dpc - 1) / dpc;
   CUDA_TRY(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   begin_launch(e);
-  static const int tpb_max = getenv("STOMP_UPDATE_TPB") ? atoi(getenv("STOMP_UPDATE_TPB")) : 128;  // A/B on B200: 64:0.163 128:0.097 256:0.150 512:0.244 ms
+  const int tpb_max = 128;   // A/B on B200 (C2): 64 threads 0.163, 128: 0.097, 256: 0.150, 512: 0.244 ms
   k_update<<<unsigned(e.B) * groups, std::min(tpb_max, ((dpc * e.N + 31) / 32) * 32), smem, e.ws>>>(a);
   return check_launch(e, "k_update");
 }
@@ -571,8 +566,9 @@ int iterate_serial(Engine& e, int iteration_number) {
 // REUSED rollout slots of iteration i+1 (gather, M*eps, control costs) only matter to iteration i+1's statistics, not to its
 // new rollouts: they run on the tail stream while the main stream already samples and costs the new rollouts of
 // iteration i+1.  (A caller that reads the statistics after every iteration synchronises both and sees no overlap.)
-//   main: [k_generate(new) -> k_cost(new)] -> wait(tail) -> k_cumulative -> k_update            -> record(upd)
-//   tail: [k_select_reuse -> k_generate(reused) -> k_gather_state] record(tail) ... wait(upd) -> k_cost(noise-less) -> k_extra_total
+//   main: [k_generate(new) -> k_cost(new) -> k_cumulative(new)] -> wait(tail) -> k_update              -> record(upd)
+//   tail: [k_select_reuse -> k_generate(reused) -> k_gather_state -> k_cumulative(reused)] record(tail)
+//         ... wait(upd) -> k_cost(noise-less) -> k_extra_total
 int iterate_once(Engine& e, int iteration_number) {
   if (e.huge_path()) {
     if (e.B != 1) return fail("the sharded / huge-rollout statistics path supports num_problems == 1 only");
@@ -589,7 +585,8 @@ int iterate_once(Engine& e, int iteration_number) {
   plan_rollouts(e, p);
   if (p.reuse) {
     e.ws = e.tail_stream;
-    if (launch_select(e) || launch_generate_range(e, p, e.num_gen, e.R - e.num_gen, true) || gather_reused_state(e)) {
+    if (launch_select(e) || launch_generate_range(e, p, e.num_gen, e.R - e.num_gen, true) || gather_reused_state(e) ||
+        launch_cumulative(e, e.num_gen, e.R - e.num_gen)) {
       e.ws = e.stream;
       return 1;
     }
@@ -600,8 +597,8 @@ int iterate_once(Engine& e, int iteration_number) {
   if (launch_cost(e, e.params[e.cur].p, size_t(e.R) * e.D * e.N, e.num_gen, e.B, iteration_number == 1, e.state[e.cur].p,
                   size_t(e.R) * e.N, e.collision_free.p, e.R + 1, 0, e.clipped.p, nullptr, e.constraints_ok.p))
     return 1;
+  if (launch_cumulative(e, 0, e.num_gen)) return 1;       // new slots; the reused slots' were done on the tail stream
   CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_tail, 0));
-  if (launch_cumulative(e)) return 1;
   const bool huge = e.huge_path();
   if (huge ? (launch_minmax(e) || launch_sums(e) || launch_finalize(e, 1)) : launch_update(e, 1, true)) return 1;
   CUDA_TRY(cudaEventRecord(e.ev_upd, e.stream));

@@ -21,18 +21,9 @@
 
 #include "../../include/stomp_b200.h"
 
-// build-time tuning knobs of k_cost (A/B tested on B200, see profiles/)
-#ifndef STOMP_KCOST_MIN_BLOCKS
-#define STOMP_KCOST_MIN_BLOCKS 7   // resident CTAs per SM the register allocation targets
-#endif
+// build-time tuning knobs (A/B tested on B200, see profiles/README.md)
 #ifndef STOMP_GEN_MIN_BLOCKS
 #define STOMP_GEN_MIN_BLOCKS 4     // k_generate: resident CTAs per SM targeted by the register allocation
-#endif
-#ifndef STOMP_GEN_LDG_BAND
-#define STOMP_GEN_LDG_BAND 0       // k_generate: 1 = read the band tables through L1 instead of shared memory
-#endif
-#ifndef STOMP_SPHERE_BATCH
-#define STOMP_SPHERE_BATCH 1       // SDF gathers kept in flight per lane
 #endif
 
 namespace stomp_dev {
@@ -303,13 +294,6 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
   extern __shared__ double smem[];
   const int N = a.N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#if STOMP_GEN_LDG_BAND
-  const double* sfw = a.band.fw;             // [N][8]  warp-uniform addresses: one L1 transaction per row
-  const double* sbw = a.band.bw;
-  const double* sscale = a.band.proj_scale;
-  double* tE = smem + size_t(warp) * 2 * 32 * kTileLd;   // per-warp tiles
-  double* tT = tE + 32 * kTileLd;
-#else
   double* sfw = smem;                        // [N][8]
   double* sbw = sfw + N * 8;                 // [N][8]
   double* sscale = sbw + N * 8;              // [N]
@@ -318,7 +302,6 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
   for (int k = threadIdx.x; k < N * 8; k += blockDim.x) sfw[k] = a.band.fw[k], sbw[k] = a.band.bw[k];
   for (int i = threadIdx.x; i < N; i += blockDim.x) sscale[i] = a.band.proj_scale[i];
   __syncthreads();
-#endif
 
   const int per_problem = (a.extra ? 1 : a.r_count) * a.D;
   const long long nvec = (long long)a.B * per_problem;
@@ -1029,12 +1012,12 @@ __device__ __forceinline__ double block_suffix_scan(double v, double* swarp /* [
 
 // k_cumulative: CTA per (b, r).  cumulative[b][r][d][t] = S + C[d] (suffix-summed over t when enabled) and
 // totals[b][r] = sum_t S + sum_d sum_t C[d]  (Rollout::getCost).
-__global__ void k_cumulative(int R, int D, int N, int use_cumulative, const double* __restrict__ state,
-                             const double* __restrict__ control, double* __restrict__ cumulative,
-                             double* __restrict__ totals) {
+__global__ void k_cumulative(int R, int r_begin, int r_count, int D, int N, int use_cumulative,
+                             const double* __restrict__ state, const double* __restrict__ control,
+                             double* __restrict__ cumulative, double* __restrict__ totals) {
   __shared__ double swarp[32];
   __shared__ double sred[32];
-  const int b = blockIdx.x / R, r = blockIdx.x - b * R;
+  const int b = blockIdx.x / r_count, r = r_begin + (blockIdx.x - b * r_count);
   const double* S = state + (size_t(b) * R + r) * N;
   const double* C = control + (size_t(b) * R + r) * D * N;
   double* out = cumulative + (size_t(b) * R + r) * D * N;
