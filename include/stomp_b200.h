@@ -42,7 +42,7 @@ enum stomp_voxel_dtype {
 };
 enum stomp_joint_type { STOMP_JOINT_FIXED = 0, STOMP_JOINT_REVOLUTE = 1, STOMP_JOINT_PRISMATIC = 2 };
 enum stomp_noise_mode {
-  STOMP_NOISE_PHILOX = 0,  /* engine RNG: eps = sigma * chol(R^-1) * z, z ~ Philox4x32-10 + Box-Muller */
+  STOMP_NOISE_PHILOX = 0,  /* engine RNG: eps = sigma * C^-T z (R = C C^T, banded), z ~ Philox4x32-10 + fp32 Box-Muller */
   STOMP_NOISE_INJECTED = 1 /* host-injection mode: eps supplied by stomp_engine_inject_noise */
 };
 

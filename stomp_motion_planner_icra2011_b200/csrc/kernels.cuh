@@ -92,14 +92,15 @@ __device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t stream, uint
                                             double& z0, double& z1) {
   uint32_t c[4] = {pair, iteration, uint32_t(stream), uint32_t(stream >> 32)};
   philox4x32_10(c, uint32_t(seed), uint32_t(seed >> 32));
-  // 53-bit uniforms in (0,1]
-  double u1 = (double((uint64_t(c[0]) << 21) ^ (uint64_t(c[1]) >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
-  double u2 = (double((uint64_t(c[2]) << 21) ^ (uint64_t(c[3]) >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
-  double r = sqrt(-2.0 * log(u1));
-  double s, co;
-  sincospi(2.0 * u2, &s, &co);
-  z0 = r * co;
-  z1 = r * s;
+  // Box-Muller in fp32 (the exploration noise needs the distribution, not 53-bit normals): u1 in (0,1] from 32 bits
+  // (|z| <= 6.66), the angle from 32 bits; evaluating log / sincospi in fp64 was ~20 % of k_generate's instructions
+  const float u1 = (float(c[0] >> 8) + 1.0f) * (1.0f / 16777216.0f);
+  const float u2 = float(c[2] >> 8) * (1.0f / 16777216.0f);
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float sn, co;
+  sincospif(2.0f * u2, &sn, &co);
+  z0 = double(r * co);
+  z1 = double(r * sn);
 }
 
 // ---------------------------------------------------------------------------------------------
