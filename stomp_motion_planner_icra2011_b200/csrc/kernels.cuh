@@ -1120,20 +1120,39 @@ __global__ void k_update(UpdateArgs a) {
     const size_t base = (size_t(b) * R * D + d) * N + t;
     const double* c = a.cumulative + base;
     const double* e = a.noise + base;
+    // rollouts are visited in groups of kGroup with all loads of a group issued before the first use (the loop count is
+    // a run-time value, so the compiler does not software-pipeline it; ncu showed 45 % of the stalls on these loads)
+    constexpr int kGroup = 5;
     double mn = c[0], mx = c[0];
-    for (int r = 1; r < R; ++r) {
-      double v = c[r * rstride];
-      if (v < mn) mn = v;
-      if (v > mx) mx = v;
+    for (int r0 = 0; r0 < R; r0 += kGroup) {
+      double cv[kGroup];
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j) cv[j] = r0 + j < R ? c[(r0 + j) * rstride] : mn;
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j) {
+        if (cv[j] < mn) mn = cv[j];
+        if (cv[j] > mx) mx = cv[j];
+      }
     }
     double denom = mx - mn;
     if (denom < 1e-8) denom = 1e-8;
     const double h = -10.0 / denom;
     double p_sum = 0.0, acc = 0.0;
-    for (int r = 0; r < R; ++r) {
-      double w = exp(h * (c[r * rstride] - mn));
-      p_sum += w;
-      acc += e[r * rstride] * w;
+    for (int r0 = 0; r0 < R; r0 += kGroup) {
+      double cv[kGroup], ev[kGroup];
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j) {
+        const bool in = r0 + j < R;
+        cv[j] = in ? c[(r0 + j) * rstride] : 0.0;
+        ev[j] = in ? e[(r0 + j) * rstride] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j)
+        if (r0 + j < R) {
+          const double w = exp(h * (cv[j] - mn));
+          p_sum += w;
+          acc += ev[j] * w;
+        }
     }
     const double inv = 1.0 / p_sum;
     if (a.probabilities)
