@@ -294,28 +294,44 @@ def run_engine(args):
         base = np.einsum("ij,...j->...i", L, z) * 2.0
         eps_np[...] = np.resize(base, eps_np.shape)
 
-        cost_np, cf_np = np.empty(B), np.empty(B, dtype=np.int32)
+        # results of step i are requested asynchronously and collected while step i+1 already runs (two host buffer sets)
+        res = [(torch.empty((B, D, N), dtype=torch.float64).pin_memory().numpy(),
+                torch.empty(B, dtype=torch.float64).pin_memory().numpy(),
+                torch.empty(B, dtype=torch.int32).pin_memory().numpy()) for _ in range(2)]
+        pending = []
         eng.inject_noise_async(eps_np)              # noise of the first timed step
 
         def e2e_step(i):
             eng.iterate(i, stats=False)             # consumes the pending injection (device-side wait on the copy)
+            th, co, cf_ = res[i % 2]
+            pending.append(eng.request_results_async(th, co, cf_))   # D2H of theta / noise-less cost / collision flag
             eng.inject_noise_async(eps_np)          # next step's noise: H2D on the copy stream, overlaps this iteration
-            eng.last_stats(cost_np, cf_np)          # D2H of the noise-less cost / collision flag of every problem
-            eng.get_parameters(theta_np)            # D2H of the updated trajectories
-        h2d, api = int(eps_np.nbytes + 8 * D), ("stomp_engine_iterate + stomp_engine_inject_noise_async(pinned eps of the next "
-                                                "step) + stomp_engine_last_stats + stomp_engine_get_parameters(pinned)")
+            if len(pending) > 1:
+                eng.wait_results(pending.pop(0))    # step i-1's results are now in host memory
+
+        def e2e_drain():
+            while pending:
+                eng.wait_results(pending.pop(0))
+        h2d, api = int(eps_np.nbytes + 8 * D), ("per step: stomp_engine_iterate + stomp_engine_request_results_async(pinned theta, cost, flag) + "
+                                                "stomp_engine_inject_noise_async(pinned eps of the next step) + "
+                                                "stomp_engine_wait_results(previous step)")
     else:
         def e2e_step(i):
             eng_iterate(i)
             eng.get_parameters(theta_np)
+
+        def e2e_drain():
+            pass
         h2d, api = 8 * D, "sharded iterate (3 phases + 2 all-reduces) + stomp_engine_get_parameters(pinned); noise is engine Philox"
     for _ in range(2):
         e2e_step(it); it += 1
+    e2e_drain()
     barrier()
     t0 = time.perf_counter()
     for _ in range(Ke):
         e2e_step(it)
         it += 1
+    e2e_drain()                                     # every step's results are in host memory when the clock stops
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": total_evals_step * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,

@@ -287,6 +287,15 @@ int stomp_engine_synchronize(void* engine);
  * that launched the iteration with stats == NULL; waits for the iteration to finish. */
 int stomp_engine_last_stats(void* engine, stomp_iter_stats* stats);
 
+/* Asynchronous read-back of the results of the iteration launched last (stomp_engine_iterate with stats == NULL): the
+ * updated trajectories theta [B][D][N], the noise-less rollout's cost [B] and collision flag [B] (any may be NULL) are
+ * snapshotted on the device in stream order and copied to the caller's (pinned) host buffers on a dedicated stream, without
+ * blocking the host or the iterations launched afterwards.  Two requests can be in flight; *ticket receives 0 or 1 and
+ * stomp_engine_wait_results(ticket) blocks until that request's host buffers are complete. */
+int stomp_engine_request_results_async(void* engine, double* theta, double* noiseless_cost, int32_t* noiseless_collision_free,
+                                       int32_t* ticket);
+int stomp_engine_wait_results(void* engine, int32_t ticket);
+
 /* StompOptimizer::optimize, STOMP branch (src/stomp_optimizer.cpp:284-359,368-400), for every problem of the batch with
  * the bookkeeping on the device: per iteration the noise-less rollout's cost / collision flag update
  * collision_free_iteration_, the success iterations, the best (joint-limit-clipped) trajectory and

@@ -66,6 +66,11 @@ struct Engine {
   cudaStream_t stream = nullptr, copy_stream = nullptr, tail_stream = nullptr;
   cudaStream_t ws = nullptr;   // stream the launch helpers currently enqueue on (stream or tail_stream)
   cudaEvent_t ev_tail = nullptr, ev_upd = nullptr;
+  // asynchronous result read-back (two requests in flight)
+  cudaStream_t result_stream = nullptr;
+  cudaEvent_t ev_snap_main[2] = {nullptr, nullptr}, ev_snap_tail[2] = {nullptr, nullptr}, ev_results[2] = {nullptr, nullptr};
+  int next_ticket = 0;
+  bool ticket_used[2] = {false, false};
   bool overlap = true, tail_dirty = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_copy_done[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
@@ -106,6 +111,8 @@ struct Engine {
   DevBuf<int> scratch_flags;
   DevBuf<stomp_sphere_debug> debug;
   DevBuf<double> part, minmax, sums;  // sharded / huge-R statistics
+  DevBuf<double> snap_theta[2], snap_cost[2];
+  DevBuf<int> snap_flag[2];
   DevBuf<double> gen_scratch, gen_scratch2;   // time-major work buffers of k_generate (main / tail stream)
   DevBuf<double> extra_clipped, best_traj, best_cost, cost_log;   // optimize() bookkeeping
   DevBuf<unsigned char> track_state;
@@ -735,6 +742,12 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   if ((c = cudaEventCreateWithFlags(&e.ev_tail, cudaEventDisableTiming)) != cudaSuccess ||
       (c = cudaEventCreateWithFlags(&e.ev_upd, cudaEventDisableTiming)) != cudaSuccess)
     return bail(c, "cudaEventCreate");
+  if ((c = cudaStreamCreateWithFlags(&e.result_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
+  for (int i = 0; i < 2; ++i)
+    if ((c = cudaEventCreateWithFlags(&e.ev_snap_main[i], cudaEventDisableTiming)) != cudaSuccess ||
+        (c = cudaEventCreateWithFlags(&e.ev_snap_tail[i], cudaEventDisableTiming)) != cudaSuccess ||
+        (c = cudaEventCreateWithFlags(&e.ev_results[i], cudaEventDisableTiming)) != cudaSuccess)
+      return bail(c, "cudaEventCreate");
   e.ws = e.stream;
   e.overlap = !(getenv("STOMP_NO_OVERLAP") && atoi(getenv("STOMP_NO_OVERLAP")) != 0);
   for (int i = 0; i < 2; ++i)
@@ -798,6 +811,12 @@ int stomp_engine_destroy(void* h) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
   if (e->tail_stream) { cudaStreamSynchronize(e->tail_stream); cudaStreamDestroy(e->tail_stream); }
+  if (e->result_stream) { cudaStreamSynchronize(e->result_stream); cudaStreamDestroy(e->result_stream); }
+  for (int i = 0; i < 2; ++i) {
+    if (e->ev_snap_main[i]) cudaEventDestroy(e->ev_snap_main[i]);
+    if (e->ev_snap_tail[i]) cudaEventDestroy(e->ev_snap_tail[i]);
+    if (e->ev_results[i]) cudaEventDestroy(e->ev_results[i]);
+  }
   if (e->ev_tail) cudaEventDestroy(e->ev_tail);
   if (e->ev_upd) cudaEventDestroy(e->ev_upd);
   for (int i = 0; i < 2; ++i) {
@@ -1260,6 +1279,50 @@ int stomp_engine_synchronize(void* h) {
   ENGINE_OR_FAIL(h);
   CUDA_TRY(cudaStreamSynchronize(e.copy_stream));
   CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+int stomp_engine_request_results_async(void* h, double* theta, double* noiseless_cost, int32_t* noiseless_collision_free,
+                                       int32_t* ticket) {
+  ENGINE_NOJOIN(h);
+  const int k = e.next_ticket;
+  e.next_ticket ^= 1;
+  const size_t BDN = size_t(e.B) * e.D * e.N;
+  if (e.snap_theta[k].n != BDN) {
+    CUDA_TRY(e.snap_theta[k].alloc(BDN));
+    CUDA_TRY(e.snap_cost[k].alloc(size_t(e.B)));
+    CUDA_TRY(e.snap_flag[k].alloc(size_t(e.B)));
+  }
+  // the snapshot buffers of this ticket may still be read by the previous request that used it
+  if (e.ticket_used[k]) {
+    CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_results[k], 0));
+    CUDA_TRY(cudaStreamWaitEvent(e.tail_stream, e.ev_results[k], 0));
+  }
+  // theta: after this iteration's update, before the next one (main stream order)
+  if (theta) CUDA_TRY(cudaMemcpyAsync(e.snap_theta[k].p, e.theta.p, BDN * 8, cudaMemcpyDeviceToDevice, e.stream));
+  CUDA_TRY(cudaEventRecord(e.ev_snap_main[k], e.stream));
+  // noise-less cost / flag: after the noise-less rollout, which runs on the tail stream when iterations overlap
+  cudaStream_t ts = e.tail_dirty ? e.tail_stream : e.stream;
+  if (noiseless_cost) CUDA_TRY(cudaMemcpyAsync(e.snap_cost[k].p, e.noiseless_sum.p, size_t(e.B) * 8, cudaMemcpyDeviceToDevice, ts));
+  if (noiseless_collision_free)
+    CUDA_TRY(cudaMemcpy2DAsync(e.snap_flag[k].p, 4, e.collision_free.p + e.R, size_t(e.R + 1) * 4, 4, e.B, cudaMemcpyDeviceToDevice, ts));
+  CUDA_TRY(cudaEventRecord(e.ev_snap_tail[k], ts));
+  CUDA_TRY(cudaStreamWaitEvent(e.result_stream, e.ev_snap_main[k], 0));
+  CUDA_TRY(cudaStreamWaitEvent(e.result_stream, e.ev_snap_tail[k], 0));
+  if (theta) CUDA_TRY(cudaMemcpyAsync(theta, e.snap_theta[k].p, BDN * 8, cudaMemcpyDeviceToHost, e.result_stream));
+  if (noiseless_cost) CUDA_TRY(cudaMemcpyAsync(noiseless_cost, e.snap_cost[k].p, size_t(e.B) * 8, cudaMemcpyDeviceToHost, e.result_stream));
+  if (noiseless_collision_free)
+    CUDA_TRY(cudaMemcpyAsync(noiseless_collision_free, e.snap_flag[k].p, size_t(e.B) * 4, cudaMemcpyDeviceToHost, e.result_stream));
+  CUDA_TRY(cudaEventRecord(e.ev_results[k], e.result_stream));
+  e.ticket_used[k] = true;
+  if (ticket) *ticket = k;
+  return 0;
+}
+
+int stomp_engine_wait_results(void* h, int32_t ticket) {
+  ENGINE_NOJOIN(h);
+  if (ticket < 0 || ticket > 1 || !e.ticket_used[ticket]) return fail("unknown result ticket");
+  CUDA_TRY(cudaEventSynchronize(e.ev_results[ticket]));
   return 0;
 }
 

@@ -30,6 +30,7 @@ EXPORTS = [
     "stomp_engine_set_profiling", "stomp_engine_get_profile", "stomp_engine_optimize",
     "stomp_engine_build_sdf", "stomp_engine_get_sdf", "stomp_engine_inject_noise_async", "stomp_engine_last_stats",
     "stomp_engine_set_constraints", "stomp_engine_execute_constraints_satisfied",
+    "stomp_engine_request_results_async", "stomp_engine_wait_results",
 ]
 
 
@@ -183,6 +184,15 @@ class Engine:
         st = _abi.IterStats(_dp(cost), _ip(cf), 0, 0, None)
         self._ck(self.L.stomp_engine_last_stats(self.h, C.byref(st)))
         return cost, cf
+
+    def request_results_async(self, theta=None, cost=None, cf=None):
+        """asynchronous read-back of the last launched iteration into (pinned) numpy buffers; returns a ticket."""
+        t = C.c_int32()
+        self._ck(self.L.stomp_engine_request_results_async(self.h, _dp(theta), _dp(cost), _ip(cf), C.byref(t)))
+        return t.value
+
+    def wait_results(self, ticket):
+        self._ck(self.L.stomp_engine_wait_results(self.h, ticket))
 
     def sample_noise(self, iteration, n):
         out = np.empty((self.B, n, self.D, self.N))

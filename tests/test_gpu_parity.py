@@ -623,3 +623,36 @@ def test_two_stream_overlap_is_invisible():
         for f in (_abi.FIELD_THETA, _abi.FIELD_PARAMETERS, _abi.FIELD_STATE_COSTS, _abi.FIELD_CONTROL_COSTS, _abi.FIELD_NOISE,
                   _abi.FIELD_ROLLOUT_TOTAL_COSTS, _abi.FIELD_PROBABILITIES, _abi.FIELD_NOISELESS_COSTS):
             np.testing.assert_array_equal(a.get(f), other.get(f))
+
+
+def test_async_result_readback_pipeline():
+    """request_results_async / wait_results: results of iteration i collected while iteration i+1 runs equal the
+    synchronous read-back, with injected noise uploaded asynchronously as well (the bench's e2e loop)."""
+    sc = scenes.make_scenario("tiny", num_problems=4)
+    a, b = _engine(sc), _engine(sc)
+    rng = np.random.default_rng(23)
+    L = np.linalg.cholesky(a.get(_abi.FIELD_INV_CONTROL_COST))
+    D, N = sc.robot.num_dimensions, sc.num_time_steps
+    its = 7
+    eps = [np.ascontiguousarray(correlated_noise(L, rng, (4, sc.num_rollouts if it == 0 else sc.num_rollouts - sc.num_reused_rollouts),
+                                                 np.full(D, 2.0))) for it in range(its)]
+    want = []
+    for it in range(its):
+        a.inject_noise(eps[it])
+        c, f, _ = a.iterate(it + 1)
+        want.append((a.get_parameters(), c, f))
+    bufs = [(np.empty((4, D, N)), np.empty(4), np.empty(4, dtype=np.int32)) for _ in range(its)]
+    tickets = []
+    b.inject_noise_async(eps[0])
+    for it in range(its):
+        b.iterate(it + 1, stats=False)
+        tickets.append(b.request_results_async(*bufs[it]))
+        if it + 1 < its:
+            b.inject_noise_async(eps[it + 1])
+        if it >= 1:
+            b.wait_results(tickets[it - 1])
+            for got, ref in zip(bufs[it - 1], want[it - 1]):
+                np.testing.assert_array_equal(got, ref)
+    b.wait_results(tickets[-1])
+    for got, ref in zip(bufs[-1], want[-1]):
+        np.testing.assert_array_equal(got, ref)
