@@ -1,0 +1,2 @@
+// oracle/ref_shim: see ros/ros.h in this directory (test infrastructure).
+#include <ros/ros.h>
