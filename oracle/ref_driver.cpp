@@ -3,7 +3,7 @@
  * from /root/reference/stomp_motion_planner/src/{policy_improvement,policy_improvement_loop,
  * covariant_trajectory_policy,stomp_cost}.cpp against the stand-in headers in oracle/ref_shim/.
  *
- * THIS IS TEST INFRASTRUCTURE (oracle/_ref/libstomp_ref_pi2.so, built by oracle/Makefile when
+ * THIS IS TEST INFRASTRUCTURE (oracle/_ref/libstomp_ref.so, built by oracle/Makefile when
  * /root/reference is present).  It exists to pin oracle/stomp_oracle.cpp — and through it the CUDA
  * engine — to outputs of the reference itself.  Nothing under stomp_motion_planner_icra2011_b200/ may
  * load it.  tests/golden/make_ref_golden.py runs it here and commits the vectors it produces, because
@@ -33,11 +33,19 @@
 #include <boost/random/mersenne_twister.hpp>
 #define private public   /* read Rollout / PolicyImprovement internals; the reference TUs are compiled without this */
 #define protected public
+#include <kdl/tree.hpp>
+#include <ros_msgs_shim.h>
 #include <stomp_motion_planner/policy_improvement_loop.h>
 #include <stomp_motion_planner/covariant_trajectory_policy.h>
 #include <stomp_motion_planner/stomp_cost.h>
+#include <stomp_motion_planner/stomp_optimizer.h>
+#include <stomp_motion_planner/stomp_collision_space.h>
+#include <stomp_motion_planner/stomp_parameters.h>
+#include <stomp_motion_planner/STOMPStatistics.h>
 #undef private
 #undef protected
+
+#include "../include/stomp_b200.h" /* plain-C table structs shared with the engine and the oracle */
 
 #include <cstring>
 #include <string>
@@ -111,6 +119,7 @@ void* stomp_ref_create(int N, int D, int R, int R_reuse, double movement_duratio
   srand(1); /* MultivariateGaussian seeds mt19937 from rand() (multivariate_gaussian.h:84) */
   Ref* h = new Ref;
   h->N = N; h->D = D; h->R = R;
+  h->nh = ros::NodeHandle("~");
   h->nh.set("num_rollouts", XmlRpc::XmlRpcValue(R));
   h->nh.set("num_reused_rollouts", XmlRpc::XmlRpcValue(R_reuse));
   h->nh.set("num_time_steps", XmlRpc::XmlRpcValue(N));
@@ -173,11 +182,8 @@ int stomp_ref_compute_control_costs(void* p, const double* parameters, const dou
 
 /* Read-out of internal state.  Per-rollout fields are [R][D][N] (state_costs [R][N], total [R]); the
  * "extra_" prefix addresses extra_rollouts_[0]; matrices are row-major [N][N] of dimension 0. */
-int stomp_ref_get(void* p, const char* field, double* out) {
-  Ref* h = static_cast<Ref*>(p);
-  PolicyImprovement& pi = h->loop.policy_improvement_;
+static int pi_get(PolicyImprovement& pi, CovariantTrajectoryPolicy& policy, int N, int D, const char* field, double* out) {
   std::string f(field);
-  const int N = h->N, D = h->D;
   std::vector<Rollout>* rs = &pi.rollouts_;
   if (f.compare(0, 6, "extra_") == 0) { rs = &pi.extra_rollouts_; f = f.substr(6); }
   const int R = int(rs->size());
@@ -202,9 +208,9 @@ int stomp_ref_get(void* p, const char* field, double* out) {
   if (f == "inv_control_cost_matrix") { copy_mat_rowmajor(pi.inv_control_costs_[0], out); return 0; }
   if (f == "projection_matrix") { copy_mat_rowmajor(pi.projection_matrix_[0], out); return 0; }
   if (f == "covariance_cholesky") { copy_mat_rowmajor(pi.noise_generators_[0].covariance_cholesky_, out); return 0; }
-  if (f == "control_cost_matrix_all") { copy_mat_rowmajor(h->policy->control_costs_all_[0], out); return 0; }
+  if (f == "control_cost_matrix_all") { copy_mat_rowmajor(policy.control_costs_all_[0], out); return 0; }
   if (f == "parameters_all") {
-    for (int d = 0; d < D; ++d) copy_vec(h->policy->parameters_all_[d], out + size_t(d) * (N + 12));
+    for (int d = 0; d < D; ++d) copy_vec(policy.parameters_all_[d], out + size_t(d) * (N + 12));
     return 0;
   }
   if (f == "parameter_updates") {
@@ -213,15 +219,22 @@ int stomp_ref_get(void* p, const char* field, double* out) {
     return 0;
   }
   if (f == "num_rollouts_gen") { out[0] = pi.num_rollouts_gen_; return 0; }
-  if (f == "movement_dt") { out[0] = h->policy->movement_dt_; return 0; }
+  if (f == "movement_dt") { out[0] = policy.movement_dt_; return 0; }
   return 2;
+}
+
+int stomp_ref_get(void* p, const char* field, double* out) {
+  Ref* h = static_cast<Ref*>(p);
+  return pi_get(h->loop.policy_improvement_, *h->policy, h->N, h->D, field, out);
 }
 
 /* StompCost as StompOptimizer::initialize builds and scales it (src/stomp_optimizer.cpp:104-125) for
  * n_joints joints with per-joint cost multipliers joint_cost[j]; out = quad_cost_inv_ [n_joints][N][N]. */
 int stomp_ref_quad_cost_inv(int num_vars_all, double discretization, const double* smoothness_costs /*[3]*/,
                             double ridge, int n_joints, const double* joint_cost, double* out) {
-  StompTrajectory traj(num_vars_all, discretization);
+  StompRobotModel model;
+  model.num_kdl_joints_ = 1;
+  StompTrajectory traj(&model, num_vars_all, discretization);
   std::vector<StompCost> costs;
   costs.reserve(n_joints);
   double max_cost_scale = 0.0;
@@ -237,6 +250,394 @@ int stomp_ref_quad_cost_inv(int num_vars_all, double discretization, const doubl
     costs[i].scale(max_cost_scale);
     copy_mat_rowmajor(costs[i].getQuadraticCostInverse(), out + size_t(i) * n * n);
   }
+  return 0;
+}
+
+} /* extern "C" */
+
+/* =====================================================================================================
+ * The cost-plugin half: the reference's StompOptimizer (src/stomp_optimizer.cpp, all 1213 lines), StompTrajectory,
+ * StompCollisionPoint, both TreeFkSolverJointPosAxis solvers, OrientationConstraintEvaluator and StompParameters,
+ * compiled unmodified.  Not compiled: src/stomp_robot_model.cpp (URDF / planning_environment ingestion) and
+ * src/stomp_collision_space.cpp (scene rasterisation) — their OUTPUTS are what the engine's tables replace
+ * (include/stomp_b200.h: stomp_segment / stomp_sphere / stomp_joint_limit, the voxel grid), so the driver fills the
+ * reference's own data structures (KDL::Tree, StompPlanningGroup, StompCollisionPoint list, distance field) from
+ * those same tables, the way StompRobotModel::init (src/stomp_robot_model.cpp:95-190) and
+ * StompCollisionSpace::init (src/stomp_collision_space.cpp:61-84) would from a URDF and a parameter server.
+ * ===================================================================================================== */
+namespace stomp_motion_planner {
+/* constructors / destructors of the two classes whose .cpp files are not compiled */
+StompRobotModel::StompRobotModel() : monitor_(NULL), num_kdl_joints_(0), fk_solver_(NULL), max_radius_clearance_(0.0) {}
+StompRobotModel::~StompRobotModel() {}
+StompCollisionSpace::StompCollisionSpace()
+    : distance_field_(NULL), max_expansion_(0.0), resolution_(0.0), field_bias_x_(0.0), field_bias_y_(0.0),
+      field_bias_z_(0.0), monitor_(NULL), collision_models_(NULL) {}
+StompCollisionSpace::~StompCollisionSpace() {}
+}  // namespace stomp_motion_planner
+
+namespace {
+
+std::string seg_name(int i) { char b[32]; std::snprintf(b, sizeof b, "s%04d", i); return b; }
+
+/* records the parameters of every Task::execute call, then runs the reference's own execute */
+class SpyOptimizer : public StompOptimizer {
+ public:
+  SpyOptimizer(StompTrajectory* t, const StompRobotModel* m, const StompRobotModel::StompPlanningGroup* g,
+               const StompParameters* p, const ros::Publisher& a, const ros::Publisher& b, const ros::Publisher& c,
+               StompCollisionSpace* s, const motion_planning_msgs::Constraints& k)
+      : StompOptimizer(t, m, g, p, a, b, c, s, k) {}
+  bool execute(std::vector<Eigen::VectorXd>& parameters, Eigen::VectorXd& costs, const int iteration_number) {
+    bool ok = StompOptimizer::execute(parameters, costs, iteration_number);
+    std::vector<double> rec;
+    for (size_t d = 0; d < parameters.size(); ++d)
+      for (int t = 0; t < parameters[d].size(); ++t) rec.push_back(parameters[d](t));
+    exec_iteration.push_back(iteration_number);
+    exec_parameters.push_back(rec);
+    std::vector<double> c(costs.size());
+    for (int t = 0; t < costs.size(); ++t) c[t] = costs(t);
+    exec_costs.push_back(c);
+    exec_collision_free.push_back(last_trajectory_collision_free_ ? 1 : 0);
+    exec_constraints_satisfied.push_back(last_trajectory_constraints_satisfied_ ? 1 : 0);
+    return ok;
+  }
+  std::vector<int> exec_iteration, exec_collision_free, exec_constraints_satisfied;
+  std::vector<std::vector<double> > exec_parameters, exec_costs;
+};
+
+struct RefOpt {
+  int N, D, K, S;
+  StompRobotModel model;
+  StompParameters params;
+  StompCollisionSpace space;
+  distance_field::PropagationDistanceField* df;
+  StompTrajectory* full;
+  boost::shared_ptr<SpyOptimizer> opt;
+  PolicyImprovementLoop* loop;
+  ros::Publisher pub_a, pub_b, pub_stats;
+  std::vector<uint8_t> voxels;
+  RefOpt() : df(NULL), full(NULL), loop(NULL) {}
+  ~RefOpt() {
+    if (opt) opt->resetSharedPtr();
+    opt.reset();
+    delete loop;
+    delete full;
+    delete df;
+    delete model.fk_solver_;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+void* stomp_ref_opt_create(const stomp_engine_desc* desc, const stomp_segment* segs, int32_t num_segments,
+                           int32_t reference_segment, const stomp_sphere* spheres, int32_t num_spheres,
+                           const stomp_joint_limit* limits, const void* voxels, int32_t nx, int32_t ny, int32_t nz,
+                           const double* origin, double resolution, int32_t voxel_dtype, const double* noise_stddev,
+                           const double* noise_decay, const double* start, const double* goal,
+                           const stomp_orientation_constraint* constraints, int32_t num_constraints,
+                           double constraint_cost_weight, int32_t max_iterations,
+                           int32_t max_iterations_after_collision_free) {
+  srand(1);
+  RefOpt* h = new RefOpt;
+  const int D = desc->num_dimensions, N = desc->num_time_steps;
+  h->N = N; h->D = D; h->K = num_spheres; h->S = num_segments;
+
+  /* ---- KDL tree from the segment table (kdl_parser: Joint(name, origin, axis, type), Segment(name, joint, f_tip)) */
+  StompRobotModel& m = h->model;
+  m.kdl_tree_ = KDL::Tree(seg_name(0));
+  for (int i = 1; i < num_segments; ++i) {
+    const stomp_segment& g = segs[i];
+    KDL::Vector pos(g.pos[0], g.pos[1], g.pos[2]), axis(g.axis[0], g.axis[1], g.axis[2]);
+    KDL::Rotation rot(g.rot[0], g.rot[1], g.rot[2], g.rot[3], g.rot[4], g.rot[5], g.rot[6], g.rot[7], g.rot[8]);
+    KDL::Joint joint = g.joint_type == STOMP_JOINT_REVOLUTE    ? KDL::Joint("j" + seg_name(i), pos, axis, KDL::Joint::RotAxis)
+                       : g.joint_type == STOMP_JOINT_PRISMATIC ? KDL::Joint("j" + seg_name(i), pos, axis, KDL::Joint::TransAxis)
+                                                               : KDL::Joint("j" + seg_name(i), KDL::Joint::None);
+    if (!m.kdl_tree_.addSegment(KDL::Segment(seg_name(i), joint, KDL::Frame(rot, pos)), seg_name(g.parent))) {
+      delete h;
+      return 0;
+    }
+  }
+  m.num_kdl_joints_ = m.kdl_tree_.getNrOfJoints();
+  m.reference_frame_ = seg_name(reference_segment);
+  m.fk_solver_ = new KDL::TreeFkSolverJointPosAxis(m.kdl_tree_, m.reference_frame_);
+  m.kdl_number_to_urdf_name_.resize(m.num_kdl_joints_);
+  for (int i = 1; i < num_segments; ++i)
+    if (segs[i].joint_type != STOMP_JOINT_FIXED) {
+      int q = m.kdl_tree_.getSegment(seg_name(i))->second.q_nr;
+      m.kdl_number_to_urdf_name_[q] = "j" + seg_name(i);
+      m.urdf_name_to_kdl_number_["j" + seg_name(i)] = q;
+    }
+
+  /* ---- planning group (src/stomp_robot_model.cpp:131-190) */
+  StompRobotModel::StompPlanningGroup group;
+  group.name_ = "group";
+  group.num_joints_ = 0;
+  group.stomp_joints_.resize(D);
+  std::vector<bool> active_joints(m.num_kdl_joints_, false);
+  for (int i = 1; i < num_segments; ++i) {
+    int d = segs[i].group_index;
+    if (d < 0) continue;
+    StompRobotModel::StompJoint joint;
+    KDL::SegmentMap::const_iterator it = m.kdl_tree_.getSegment(seg_name(i));
+    joint.stomp_joint_index_ = d;
+    joint.kdl_joint_index_ = it->second.q_nr;
+    joint.kdl_joint_ = &(it->second.segment.getJoint());
+    joint.link_name_ = seg_name(i);
+    joint.joint_name_ = "j" + seg_name(i);
+    joint.joint_update_limit_ = 0.1;
+    joint.wrap_around_ = !limits[d].has_limits;
+    joint.has_joint_limits_ = limits[d].has_limits != 0;
+    joint.joint_limit_min_ = limits[d].min;
+    joint.joint_limit_max_ = limits[d].max;
+    group.stomp_joints_[d] = joint;
+    group.num_joints_++;
+    active_joints[joint.kdl_joint_index_] = true;
+  }
+  group.fk_solver_.reset(new KDL::TreeFkSolverJointPosAxisPartial(m.kdl_tree_, m.reference_frame_, active_joints));
+  /* inverse dynamics: interface only (torque_cost_weight is 0; optimize() still calls it once per point for its
+   * statistics message, src/stomp_optimizer.cpp:385-397) */
+  group.id_solver_.reset(new KDL::ChainIdSolver_RNE(group.kdl_chain_, KDL::Vector(0, 0, -9.8)));
+  /* collision points: parent joints by walking up the tree (StompRobotModel::getLinkInformation, :238-262) */
+  for (int j = 0; j < num_spheres; ++j) {
+    std::vector<int> parents;
+    KDL::SegmentMap::const_iterator it = m.kdl_tree_.getSegment(seg_name(spheres[j].segment));
+    while (it != m.kdl_tree_.getRootSegment()) {
+      if (it->second.segment.getJoint().getType() != KDL::Joint::None) parents.push_back(it->second.q_nr);
+      it = it->second.parent;
+    }
+    int segment_number = m.fk_solver_->segmentNameToIndex(seg_name(spheres[j].segment));
+    group.collision_points_.push_back(StompCollisionPoint(parents, spheres[j].radius, spheres[j].clearance, segment_number,
+                                                          KDL::Vector(spheres[j].pos[0], spheres[j].pos[1], spheres[j].pos[2])));
+    if (m.max_radius_clearance_ < spheres[j].radius + spheres[j].clearance)
+      m.max_radius_clearance_ = spheres[j].radius + spheres[j].clearance;
+  }
+  m.planning_groups_.insert(std::make_pair(group.name_, group));
+  const StompRobotModel::StompPlanningGroup* pg = m.getPlanningGroup("group");
+
+  /* ---- parameters (src/stomp_parameters.cpp:50-76 reads these from the parameter server) */
+  ros::NodeHandle nh("~");
+  nh.set("max_iterations", XmlRpc::XmlRpcValue(int(max_iterations)));
+  nh.set("max_iterations_after_collision_free", XmlRpc::XmlRpcValue(int(max_iterations_after_collision_free)));
+  nh.set("smoothness_cost_weight", XmlRpc::XmlRpcValue(desc->smoothness_cost_weight));
+  nh.set("obstacle_cost_weight", XmlRpc::XmlRpcValue(desc->obstacle_cost_weight));
+  nh.set("constraint_cost_weight", XmlRpc::XmlRpcValue(constraint_cost_weight));
+  nh.set("torque_cost_weight", XmlRpc::XmlRpcValue(0.0));
+  nh.set("smoothness_cost_velocity", XmlRpc::XmlRpcValue(desc->derivative_costs[0]));
+  nh.set("smoothness_cost_acceleration", XmlRpc::XmlRpcValue(desc->derivative_costs[1]));
+  nh.set("smoothness_cost_jerk", XmlRpc::XmlRpcValue(desc->derivative_costs[2]));
+  nh.set("ridge_factor", XmlRpc::XmlRpcValue(desc->ridge_factor));
+  nh.set("animate_path", XmlRpc::XmlRpcValue(false));
+  nh.set("animate_endeffector", XmlRpc::XmlRpcValue(false));
+  nh.set("animate_endeffector_segment", XmlRpc::XmlRpcValue(seg_name(num_segments - 1)));
+  nh.set("use_chomp", XmlRpc::XmlRpcValue(false));
+  nh.set("num_rollouts", XmlRpc::XmlRpcValue(int(desc->num_rollouts)));
+  nh.set("num_reused_rollouts", XmlRpc::XmlRpcValue(int(desc->num_reused_rollouts)));
+  nh.set("num_time_steps", XmlRpc::XmlRpcValue(N));
+  nh.set("noise_stddev", XmlRpc::XmlRpcValue(std::vector<double>(noise_stddev, noise_stddev + D)));
+  nh.set("noise_decay", XmlRpc::XmlRpcValue(std::vector<double>(noise_decay, noise_decay + D)));
+  nh.set("use_cumulative_costs", XmlRpc::XmlRpcValue(bool(desc->use_cumulative_costs != 0)));
+  nh.set("write_to_file", XmlRpc::XmlRpcValue(false));
+  h->params.initFromNodeHandle();
+
+  /* ---- collision space: the voxel grid the engine receives, behind the distance_field lookup */
+  size_t vb = voxel_dtype == STOMP_VOXEL_U8_SQ ? 1 : (voxel_dtype == STOMP_VOXEL_U16_SQ ? 2 : 4);
+  h->voxels.assign(static_cast<const uint8_t*>(voxels), static_cast<const uint8_t*>(voxels) + size_t(nx) * ny * nz * vb);
+  h->df = new distance_field::PropagationDistanceField(h->voxels.data(), nx, ny, nz, origin, resolution, voxel_dtype);
+  h->space.distance_field_ = h->df;
+  h->space.resolution_ = resolution;
+  h->space.reference_frame_ = m.reference_frame_;
+
+  /* ---- full trajectory as StompPlannerNode::planKinematicPath builds it (src/stomp_planner_node.cpp:188-220):
+   *      N+2 points, start state at 0 (all robot joints), goal at the last point, min-jerk in between */
+  h->full = new StompTrajectory(&m, N + 2, desc->discretization);
+  for (int i = 1; i < num_segments; ++i) {
+    if (segs[i].joint_type == STOMP_JOINT_FIXED) continue;
+    int q = m.kdl_tree_.getSegment(seg_name(i))->second.q_nr;
+    int d = segs[i].group_index;
+    (*h->full)(0, q) = d >= 0 ? start[d] : segs[i].fixed_value;
+  }
+  int goal_index = h->full->getNumPoints() - 1;
+  h->full->getTrajectoryPoint(goal_index) = h->full->getTrajectoryPoint(0);
+  for (int d = 0; d < D; ++d) (*h->full)(goal_index, pg->stomp_joints_[d].kdl_joint_index_) = goal[d];
+  h->full->fillInMinJerk();
+
+  motion_planning_msgs::Constraints cons;
+  for (int i = 0; i < num_constraints; ++i) {
+    motion_planning_msgs::OrientationConstraint oc;
+    oc.link_name = seg_name(constraints[i].segment);
+    oc.type = constraints[i].body_fixed ? int(motion_planning_msgs::OrientationConstraint::LINK_FRAME)
+                                        : int(motion_planning_msgs::OrientationConstraint::HEADER_FRAME);
+    oc.orientation.x = constraints[i].orientation[0]; oc.orientation.y = constraints[i].orientation[1];
+    oc.orientation.z = constraints[i].orientation[2]; oc.orientation.w = constraints[i].orientation[3];
+    oc.absolute_roll_tolerance = constraints[i].absolute_roll_tolerance;
+    oc.absolute_pitch_tolerance = constraints[i].absolute_pitch_tolerance;
+    oc.absolute_yaw_tolerance = constraints[i].absolute_yaw_tolerance;
+    oc.weight = constraints[i].weight;
+    cons.orientation_constraints.push_back(oc);
+  }
+
+  h->opt.reset(new SpyOptimizer(h->full, &m, pg, &h->params, h->pub_a, h->pub_b, h->pub_stats, &h->space, cons));
+  boost::shared_ptr<StompOptimizer> base = h->opt;
+  h->opt->setSharedPtr(base);
+  return h;
+}
+
+void stomp_ref_opt_destroy(void* p) { delete static_cast<RefOpt*>(p); }
+
+/* numbers the test checks before trusting anything else: [0] derived policy movement duration (int-truncated group
+ * duration, src/stomp_optimizer.cpp:185), [1] num_vars_free, [2] num_vars_all, [3] free_vars_start, [4] #segments of the FK
+ * solver, [5] 1 if the solver numbers segment i of the table as i (DFS pre-order), [6] #kdl joints */
+int stomp_ref_opt_info(void* p, double* out) {
+  RefOpt* h = static_cast<RefOpt*>(p);
+  out[0] = h->opt->group_trajectory_.getDuration();
+  out[1] = h->opt->num_vars_free_;
+  out[2] = h->opt->num_vars_all_;
+  out[3] = h->opt->free_vars_start_;
+  out[4] = h->model.fk_solver_->getSegmentNames().size();
+  bool same = true;
+  for (int i = 0; i < h->S; ++i) same = same && h->model.fk_solver_->segmentNameToIndex(seg_name(i)) == i;
+  out[5] = same ? 1 : 0;
+  out[6] = h->model.num_kdl_joints_;
+  return 0;
+}
+
+/* StompOptimizer::execute (src/stomp_optimizer.cpp:1063-1165) with iteration_ = iteration_number - 1, as inside optimize() */
+int stomp_ref_opt_execute(void* p, const double* parameters, int32_t iteration_number, double* costs,
+                          int32_t* collision_free, int32_t* constraints_satisfied) {
+  RefOpt* h = static_cast<RefOpt*>(p);
+  std::vector<Eigen::VectorXd> v(h->D, Eigen::VectorXd::Zero(h->N));
+  for (int d = 0; d < h->D; ++d)
+    for (int t = 0; t < h->N; ++t) v[d](t) = parameters[size_t(d) * h->N + t];
+  Eigen::VectorXd c = Eigen::VectorXd::Zero(h->N);
+  h->opt->iteration_ = iteration_number - 1;
+  bool ok = h->opt->StompOptimizer::execute(v, c, iteration_number);
+  for (int t = 0; t < h->N; ++t) costs[t] = c(t);
+  if (collision_free) *collision_free = h->opt->last_trajectory_collision_free_ ? 1 : 0;
+  if (constraints_satisfied) *constraints_satisfied = h->opt->last_trajectory_constraints_satisfied_ ? 1 : 0;
+  return ok ? 0 : 1;
+}
+
+/* per-sphere state after the last execute, trajectory points -1 .. N+1: debug[N+3][K]; clipped[D][N] = group trajectory
+ * after handleJointLimits.  voxel = the distance field's own cell rule applied to the reference's sphere position. */
+int stomp_ref_opt_debug(void* p, stomp_sphere_debug* debug, double* clipped) {
+  RefOpt* h = static_cast<RefOpt*>(p);
+  StompOptimizer& o = *h->opt;
+  for (int t = -1; t <= h->N + 1; ++t)
+    for (int j = 0; j < h->K; ++j) {
+      int i = o.free_vars_start_ + t;
+      stomp_sphere_debug& r = debug[size_t(t + 1) * h->K + j];
+      for (int a = 0; a < 3; ++a) {
+        r.position[a] = o.collision_point_pos_[i][j](a);
+        r.voxel[a] = h->df->getCellFromLocation(a, r.position[a]);
+      }
+      r.in_collision = o.point_is_in_collision_[i][j];
+      r.potential = o.collision_point_potential_[i][j];
+      r.vel_mag = (t >= 0 && t < h->N) ? o.collision_point_vel_mag_[i][j] : 0.0;
+    }
+  if (clipped)
+    for (int d = 0; d < h->D; ++d)
+      for (int t = 0; t < h->N; ++t) clipped[size_t(d) * h->N + t] = o.group_trajectory_(o.free_vars_start_ + t, d);
+  return 0;
+}
+
+/* segment frames of trajectory point t (0-based free index) after the last execute: out[S][12] = rot row-major, pos */
+int stomp_ref_opt_frames(void* p, int32_t t, double* out) {
+  RefOpt* h = static_cast<RefOpt*>(p);
+  const std::vector<KDL::Frame>& f = h->opt->segment_frames_[h->opt->free_vars_start_ + t];
+  for (int s = 0; s < h->S; ++s) {  /* table order; the solver's own number of table segment s may differ */
+    const KDL::Frame& fr = f[h->model.fk_solver_->segmentNameToIndex(seg_name(s))];
+    for (int k = 0; k < 9; ++k) out[s * 12 + k] = fr.M.data[k];
+    for (int k = 0; k < 3; ++k) out[s * 12 + 9 + k] = fr.p(k);
+  }
+  return 0;
+}
+
+/* The prologue of StompOptimizer::optimize (src/stomp_optimizer.cpp:261-271) with the PI loop owned by the handle, so
+ * that its internals can be read between iterations. */
+int stomp_ref_opt_begin(void* p) {
+  RefOpt* h = static_cast<RefOpt*>(p);
+  delete h->loop;
+  h->loop = new PolicyImprovementLoop;
+  ros::NodeHandle nh("~");
+  boost::shared_ptr<Task> task = h->opt;
+  if (!h->loop->initialize(nh, task)) return 1;
+  StompOptimizer& o = *h->opt;
+  o.iteration_ = 0;
+  o.copyPolicyToGroupTrajectory();
+  o.handleJointLimits();
+  o.updateFullTrajectory();
+  o.performForwardKinematics();
+  return 0;
+}
+
+/* one pass of the loop body of optimize(): iteration_ = iteration_number - 1; pi_loop.runSingleIteration(iteration_ + 1) */
+int stomp_ref_opt_iterate(void* p, int32_t iteration_number, double* noiseless_cost, int32_t* collision_free,
+                          int32_t* constraints_satisfied) {
+  RefOpt* h = static_cast<RefOpt*>(p);
+  h->opt->iteration_ = iteration_number - 1;
+  if (!h->loop->runSingleIteration(iteration_number)) return 1;
+  *noiseless_cost = h->opt->last_trajectory_cost_;
+  *collision_free = h->opt->last_trajectory_collision_free_ ? 1 : 0;
+  *constraints_satisfied = h->opt->last_trajectory_constraints_satisfied_ ? 1 : 0;
+  return 0;
+}
+
+/* same selector strings as stomp_ref_get, on the loop begun by stomp_ref_opt_begin */
+int stomp_ref_opt_get(void* p, const char* field, double* out) {
+  RefOpt* h = static_cast<RefOpt*>(p);
+  std::string f(field);
+  if (f == "exec_collision_free") {
+    for (size_t i = 0; i < h->opt->exec_collision_free.size(); ++i) out[i] = h->opt->exec_collision_free[i];
+    return 0;
+  }
+  if (f == "exec_count") { out[0] = h->opt->exec_costs.size(); return 0; }
+  if (f == "exec_clear") {
+    h->opt->exec_iteration.clear(); h->opt->exec_parameters.clear(); h->opt->exec_costs.clear();
+    h->opt->exec_collision_free.clear(); h->opt->exec_constraints_satisfied.clear();
+    return 0;
+  }
+  if (f == "exec_parameters") {
+    for (size_t i = 0; i < h->opt->exec_parameters.size(); ++i)
+      std::copy(h->opt->exec_parameters[i].begin(), h->opt->exec_parameters[i].end(), out + i * size_t(h->D) * h->N);
+    return 0;
+  }
+  if (f == "exec_costs") {
+    for (size_t i = 0; i < h->opt->exec_costs.size(); ++i)
+      std::copy(h->opt->exec_costs[i].begin(), h->opt->exec_costs[i].end(), out + i * size_t(h->N));
+    return 0;
+  }
+  if (f == "best_group_trajectory") {
+    for (int d = 0; d < h->D; ++d)
+      for (int t = 0; t < h->N; ++t) out[size_t(d) * h->N + t] = h->opt->group_trajectory_(h->opt->free_vars_start_ + t, d);
+    return 0;
+  }
+  if (f == "theta") {
+    std::vector<Eigen::VectorXd> v;
+    h->opt->policy_->getParameters(v);
+    for (int d = 0; d < h->D; ++d) copy_vec(v[d], out + size_t(d) * h->N);
+    return 0;
+  }
+  if (f == "quad_cost_inv") { copy_mat_rowmajor(h->opt->joint_costs_[0].getQuadraticCostInverse(), out); return 0; }
+  if (!h->loop) return 3;
+  return pi_get(h->loop->policy_improvement_, *h->opt->policy_, h->N, h->D, field, out);
+}
+
+/* The reference's whole StompOptimizer::optimize() (src/stomp_optimizer.cpp:248-400).  stats[0..5] = success,
+ * success_iteration, collision_success_iteration, best_cost, #iterations run (costs.size()), last_improvement_iteration;
+ * costs[] = STOMPStatistics::costs (caller sizes it to max_iterations). */
+int stomp_ref_opt_optimize(void* p, double* stats, double* costs) {
+  RefOpt* h = static_cast<RefOpt*>(p);
+  h->opt->optimize();
+  boost::shared_ptr<STOMPStatistics> s = ros::Publisher::last<boost::shared_ptr<STOMPStatistics> >();
+  if (!s) return 1;
+  stats[0] = s->success ? 1 : 0;
+  stats[1] = s->success_iteration;
+  stats[2] = s->collision_success_iteration;
+  stats[3] = s->best_cost;
+  stats[4] = s->costs.size();
+  stats[5] = h->opt->last_improvement_iteration_;
+  for (size_t i = 0; i < s->costs.size(); ++i) costs[i] = s->costs[i];
   return 0;
 }
 

@@ -17,6 +17,8 @@
 #define ROS_WARN(...) ((void)0)
 #define ROS_INFO_STREAM(x) ((void)0)
 #define ROS_DEBUG_STREAM(x) ((void)0)
+#define ROS_WARN_STREAM(x) ((void)0)
+#define ROS_ERROR_STREAM(x) ((void)0)
 #define ROS_ERROR(...) do { std::fprintf(stderr, "[ref] "); std::fprintf(stderr, __VA_ARGS__); std::fprintf(stderr, "\n"); } while (0)
 
 // The reference is built with -DNDEBUG, where ROS_ASSERT compiles to nothing and ROS_ASSERT_FUNC
@@ -62,8 +64,15 @@ namespace ros {
 class NodeHandle {
  public:
   typedef std::map<std::string, XmlRpc::XmlRpcValue> Params;
-  NodeHandle() : params_(new Params) {}
-  explicit NodeHandle(const std::string& ns) : ns_(ns), params_(new Params) {}
+  // every handle of one namespace sees the same parameters, like handles onto one parameter server
+  static std::shared_ptr<Params> server(const std::string& ns) {
+    static std::map<std::string, std::shared_ptr<Params> > servers;
+    std::shared_ptr<Params>& p = servers[ns];
+    if (!p) p.reset(new Params);
+    return p;
+  }
+  NodeHandle() : ns_("~"), params_(server("~")) {}
+  explicit NodeHandle(const std::string& ns) : ns_(ns), params_(server(ns)) {}
   const std::string& getNamespace() const { return ns_; }
 
   // test-side population
@@ -106,6 +115,45 @@ class NodeHandle {
   std::string ns_;
   std::shared_ptr<Params> params_;
 };
+
+
+class WallDuration {
+ public:
+  explicit WallDuration(double s = 0.0) : s_(s) {}
+  double toSec() const { return s_; }
+  bool sleep() const { return true; }
+ private:
+  double s_;
+};
+class WallTime {
+ public:
+  static WallTime now() { return WallTime(); }
+  WallDuration operator-(const WallTime&) const { return WallDuration(0.0); }
+};
+class Duration {
+ public:
+  explicit Duration(double s = 0.0) : s_(s) {}
+  double toSec() const { return s_; }
+  bool sleep() const { return true; }
+  Duration operator-(const Duration& o) const { return Duration(s_ - o.s_); }
+ private:
+  double s_;
+};
+class Time {
+ public:
+  Time() {}
+  static Time now() { return Time(); }
+};
+inline bool ok() { return true; }
+inline void spinOnce() {}
+
+// A publisher that keeps the last message of each type it was given (read back by oracle/ref_driver.cpp).
+class Publisher {
+ public:
+  template <typename M> void publish(const M& m) const { last<M>() = m; }
+  template <typename M> static M& last() { static M m; return m; }
+};
+class Subscriber {};
 
 }  // namespace ros
 

@@ -6,10 +6,14 @@
  * cpu_baseline / --impl reference legs may load it.  The product (the CUDA engine behind
  * include/stomp_b200.h) never links, imports or calls anything in oracle/.
  *
- * PARITY UNPINNED: the reference ships no unit tests, golden vectors or known-answer data
- * for this path and cannot be compiled here (ROS, Eigen 2, Boost, KDL and
- * distance_field are absent).  The oracle is pinned only by the invariants / KATs derivable
- * from the cited formulas (tests/test_oracle_*.py).
+ * PARITY PINNED against outputs of the reference itself: the reference ships no unit tests, golden vectors or
+ * known-answer data for this path and its rosbuild build cannot run here, but 11 of its 14
+ * translation units compile UNMODIFIED from /root/reference against stand-in headers for the third-party packages it
+ * does not vendor (oracle/ref_shim/, oracle/ref_driver.cpp -> oracle/_ref/libstomp_ref.so).  tests/golden/ref_*.npz are
+ * that library's outputs; tests/test_reference_pinning.py holds this oracle to them (every intermediate of
+ * runSingleIteration, every per-sphere quantity of StompOptimizer::execute, the statistics of optimize()): integer work
+ * exact, floating point <= 1e-8.  What stays a restatement on BOTH sides are the un-vendored third-party semantics
+ * listed below.
  *
  * The oracle keeps the reference's algorithmic shape on purpose (dense (N+12)^2
  * differentiation-matrix mat-vecs, dense L*z and M*eps, one serial execute per rollout), so

@@ -200,6 +200,15 @@ def random_tree(rng, num_group=5, num_extra=6, spheres=12):
         rb.add_segment("s%d" % n, parent, jt, rng.uniform(-0.25, 0.25, 3), rng.normal(size=3),
                        rot=_rpy(*rng.uniform(-1.0, 1.0, 3)), group=g if kind == "g" else -1,
                        fixed=float(rng.uniform(-0.5, 0.5)))
+    # renumber in DFS pre-order (children in creation order): the order kdl_parser builds a KDL::Tree in and the one
+    # TreeFkSolverJointPosAxis::assignSegmentNumber (src/treefksolverjointposaxis.cpp:128-139) assigns
+    order, stack = [], [0]
+    while stack:
+        s = stack.pop()
+        order.append(s)
+        stack.extend(reversed(rb.children(s)))
+    new_index = {old: new for new, old in enumerate(order)}
+    rb.segments = [dict(rb.segments[old], parent=new_index.get(rb.segments[old]["parent"], -1)) for old in order]
     # reference frame: a segment that no group joint moves (first segment whose ancestry is static)
     rb.reference_segment = 0
     for _ in range(spheres):

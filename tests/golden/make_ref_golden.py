@@ -1,15 +1,18 @@
-"""Generates tests/golden/ref_pi2_*.npz by RUNNING THE REFERENCE'S OWN CODE: the unmodified translation units
-src/policy_improvement.cpp, src/policy_improvement_loop.cpp, src/covariant_trajectory_policy.cpp and src/stomp_cost.cpp
-of /root/reference/stomp_motion_planner, compiled against the stand-in headers of oracle/ref_shim/ into
-oracle/_ref/libstomp_ref_pi2.so (oracle/Makefile target `ref`, oracle/ref_driver.cpp).
+"""Generates tests/golden/ref_*.npz by RUNNING THE REFERENCE'S OWN CODE: 11 of its 14 translation units
+(policy_improvement, policy_improvement_loop, covariant_trajectory_policy, stomp_cost, stomp_optimizer, stomp_trajectory,
+stomp_collision_point, treefksolverjointposaxis, treefksolverjointposaxis_partial, constraint_evaluator,
+stomp_parameters), compiled unmodified from /root/reference/stomp_motion_planner/src against the stand-in headers of
+oracle/ref_shim/ into oracle/_ref/libstomp_ref.so (oracle/Makefile target `ref`, oracle/ref_driver.cpp).
 
 Run from the repo root in a container that has /root/reference:  python tests/golden/make_ref_golden.py
 
-Everything in the files is an output of the reference's PolicyImprovementLoop::runSingleIteration — the noise its
-MultivariateGaussian drew, M eps, control costs, cumulative costs, probabilities, updates, the updated policy, getCost()
-of every rollout (which fixes the reuse order) — except `state_costs`: the reference's cost plugin
-(StompOptimizer::execute) cannot be compiled here, so Task::execute is served by the CPU restatement's cost plugin
-(oracle/stomp_oracle.cpp) and its answers are recorded next to the parameters they were asked for (`exec_*`).
+Every array is an output of the reference: the noise its MultivariateGaussian drew, the rollouts it executed, the state
+costs / collision flags / sphere positions / potentials of StompOptimizer::execute, M eps, control and cumulative costs,
+probabilities, updates, the updated policy, getCost() of every rollout, and the statistics StompOptimizer::optimize
+publishes.  Inputs are the synthetic scenes of stomp_motion_planner_icra2011_b200/scenes.py (same seeds as the tests).
+
+What the stand-in headers restate instead of the reference (third-party packages the reference does not vendor): Eigen 2
+dense primitives, KDL frame algebra, the distance_field cell lookup, Bullet's getRPY (see the headers of oracle/ref_shim/).
 """
 import os
 import sys
@@ -19,34 +22,52 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from oracle import reference_pi2 as rp  # noqa: E402
-from oracle.oracle import Oracle  # noqa: E402
+from oracle import reference as rp  # noqa: E402
 from stomp_motion_planner_icra2011_b200 import scenes  # noqa: E402
 
-CASES = (("tiny", 0, 5), ("tiny", 1, 5), ("C1", 1, 4), ("C1", 0, 2))
+HERE = os.path.dirname(os.path.abspath(__file__))
+ITERATION_CASES = (("tiny", 0, 5), ("tiny", 1, 5), ("C1", 1, 4), ("C1", 0, 2))
 PER_ROLLOUT = ("noise", "parameters", "noise_projected", "control_costs", "cumulative_costs", "probabilities")
 
 
-def run_case(name, cumulative, iterations):
-    sc = scenes.make_scenario(name, num_problems=1, use_cumulative_costs=cumulative)
+def scenario(name, cumulative=1, **kw):
+    """the test scenario, with the policy duration the reference itself derives (int-truncated group-trajectory duration,
+    src/stomp_optimizer.cpp:185 / include/stomp_motion_planner/stomp_trajectory.h:270-273)."""
+    sc = scenes.make_scenario(name, num_problems=1, use_cumulative_costs=cumulative, **kw)
+    sc.movement_duration = float(int((sc.num_time_steps + 11) * sc.discretization))
+    return sc
+
+
+def constraint_scene():
+    sc = scenario("tiny")
+    seg = [i for i, g in enumerate(sc.robot.segments) if g["name"] == "r_gripper_palm_link"][0]
+    cons = [dict(segment=seg, body_fixed=0, orientation=(0.0, 0.0, 0.0, 1.0), tolerances=(0.4, 0.3, 4.0), weight=1.5),
+            dict(segment=seg - 2, body_fixed=1, orientation=(0.1, -0.2, 0.3, 0.9), tolerances=(4.0, 0.5, 0.6), weight=0.7)]
+    return sc, cons, 2.0
+
+
+def iteration_case(name, cumulative, iterations, constraints=(), weight=0.0):
+    sc = scenario(name, cumulative)
     D, N, R = sc.robot.num_dimensions, sc.num_time_steps, sc.num_rollouts
-    plugin = Oracle(sc, 0)
-    ref = rp.ReferencePI2(N, D, R, sc.num_reused_rollouts, sc.movement_duration, sc.ridge_factor, sc.derivative_costs,
-                          sc.noise_stddev, sc.noise_decay, sc.smoothness_cost_weight, cumulative, sc.start[0], sc.goal[0],
-                          lambda p, it: plugin.execute(p, it)[0][0])
-    out = {"theta0": ref.get_parameters(), "parameters_all0": ref.get("parameters_all"),
-           "movement_dt": ref.get("movement_dt")}
+    ref = rp.ReferenceOptimizer(sc, 0, constraints=constraints, constraint_cost_weight=weight)
+    assert ref.movement_duration == sc.movement_duration
+    ref.begin()
+    out = {"movement_duration": np.array(ref.movement_duration), "theta0": ref.get("theta"),
+           "parameters_all0": ref.get("parameters_all"), "movement_dt": ref.get("movement_dt")}
     if cumulative == 1:  # setup matrices do not depend on the flag; store them once per scene
-        for f in ("control_cost_matrix", "inv_control_cost_matrix", "projection_matrix", "covariance_cholesky"):
+        for f in ("control_cost_matrix", "inv_control_cost_matrix", "projection_matrix", "covariance_cholesky", "quad_cost_inv"):
             out[f] = ref.get(f)
-        out["quad_cost_inv"] = rp.quad_cost_inv(N + 12, sc.discretization, sc.derivative_costs, sc.ridge_factor, np.ones(D))[0]
+        # Policy::computeControlCosts on arbitrary inputs, through the PI^2-only entry points of the same library
+        pi = rp.ReferencePI2(N, D, R, sc.num_reused_rollouts, sc.movement_duration, sc.ridge_factor, sc.derivative_costs,
+                             sc.noise_stddev, sc.noise_decay, sc.smoothness_cost_weight, cumulative, sc.start[0], sc.goal[0],
+                             lambda p, it: np.zeros(N))
         rng = np.random.default_rng(5)
-        p, e = rng.standard_normal((D, N)), 0.1 * rng.standard_normal((D, N))
-        out["cc_parameters"], out["cc_noise"] = p, e
-        out["cc_out"] = ref.compute_control_costs(p, e, 0.5 * sc.smoothness_cost_weight)
+        out["cc_parameters"], out["cc_noise"] = rng.standard_normal((D, N)), 0.1 * rng.standard_normal((D, N))
+        out["cc_out"] = pi.compute_control_costs(out["cc_parameters"], out["cc_noise"], 0.5 * sc.smoothness_cost_weight)
+        pi.close()
     for it in range(1, iterations + 1):
-        ref.calls.clear()
-        ref.run_single_iteration(it)
+        ref.get("exec_clear")
+        cost, cf, cs = ref.iterate(it)
         k = "it%d_" % it
         ngen = int(ref.get("num_rollouts_gen")[0])
         out[k + "num_rollouts_gen"] = np.array(ngen, dtype=np.int32)
@@ -57,20 +78,102 @@ def run_case(name, cumulative, iterations):
         out[k + "totals"] = np.concatenate([ref.get("total"), ref.get("extra_total")])
         out[k + "extra_control_costs"] = ref.get("extra_control_costs")[0]
         out[k + "updates"] = ref.get("parameter_updates")
-        out[k + "theta"] = ref.get_parameters()
-        assert len(ref.calls) == ngen + 1 and all(c[0] == it for c in ref.calls)
-        out[k + "exec_costs"] = np.stack([c[2] for c in ref.calls])  # answers of the cost plugin, last = noise-less rollout
+        out[k + "theta"] = ref.get("theta")
+        out[k + "noiseless_cost"] = np.array(cost)
+        out[k + "noiseless_flags"] = np.array([cf, cs], dtype=np.int32)
+        assert int(ref.get("exec_count")[0]) == ngen + 1
+        out[k + "exec_costs"] = ref.get("exec_costs")            # answers of StompOptimizer::execute, last = noise-less rollout
+        out[k + "exec_collision_free"] = ref.get("exec_collision_free").astype(np.int32)
     ref.close()
     return out
 
 
+def cost_plugin_case(name, rollouts, seed, constraints=(), weight=0.0, robot=None, start=None, goal=None):
+    """StompOptimizer::execute on noisy rollouts around the min-control-cost trajectory + its per-sphere internals."""
+    sc = scenario(name)
+    if robot is not None:
+        sc.robot, sc.start, sc.goal = robot, start, goal
+    D, N = sc.robot.num_dimensions, sc.num_time_steps
+    ref = rp.ReferenceOptimizer(sc, 0, constraints=constraints, constraint_cost_weight=weight)
+    ref.begin()
+    L, theta = ref.get("covariance_cholesky"), ref.get("theta")
+    rng = np.random.default_rng(seed)
+    z = rng.standard_normal((rollouts, D, N))
+    scale = 2.0 * (1.0 + 3.0 * np.arange(rollouts))             # later rollouts leave the joint limits
+    params = theta[None] + np.einsum("ij,rdj->rdi", L, z) * scale[:, None, None]
+    out = {"movement_duration": np.array(ref.movement_duration), "parameters": params}
+    costs, flags, dbg, clipped = [], [], [], []
+    for r in range(rollouts):
+        for it in (1, 2):
+            c, cf, cs = ref.execute(params[r], it)
+            costs.append(c)
+            flags.append((cf, cs))
+        d, cl = ref.execute_debug(params[r])
+        dbg.append(d)
+        clipped.append(cl)
+    out["costs"] = np.stack(costs).reshape(rollouts, 2, N)        # [r][iteration 1 | 2][N]
+    out["flags"] = np.array(flags, dtype=np.int32).reshape(rollouts, 2, 2)   # collision_free, constraints_satisfied
+    for key in ("voxel", "in_collision", "position", "potential", "vel_mag"):
+        out["dbg_" + key] = np.stack([d[key] for d in dbg])
+    out["clipped"] = np.stack(clipped)
+    ref.close()
+    return out
+
+
+def optimize_case(name, seed, max_iterations, max_cf):
+    sc = scenario(name, seed=seed)
+    D, N, R = sc.robot.num_dimensions, sc.num_time_steps, sc.num_rollouts
+    ref = rp.ReferenceOptimizer(sc, 0, max_iterations=max_iterations, max_iterations_after_collision_free=max_cf)
+    theta0 = ref.get("theta")
+    res = ref.optimize()
+    params = ref.get("exec_parameters")
+    n_it = res["iterations"]
+    out = {"movement_duration": np.array(ref.movement_duration), "seed": np.array(seed), "max_iterations": np.array(max_iterations),
+           "max_iterations_after_collision_free": np.array(max_cf), "theta0": theta0}
+    for k in ("success", "success_iteration", "collision_success_iteration", "best_cost", "iterations",
+              "last_improvement_iteration", "costs", "best_trajectory"):
+        out["stats_" + k] = np.asarray(res[k])
+    # the rollouts executed per iteration: R new ones in the first iteration, R - R_reuse afterwards, then the noise-less one
+    pos, theta = 0, theta0
+    for it in range(1, n_it + 1):
+        ngen = R if it == 1 else R - sc.num_reused_rollouts
+        out["it%d_noise" % it] = params[pos:pos + ngen] - theta[None]     # Rollout::noise_ up to one rounding of theta + eps
+        theta = params[pos + ngen]
+        pos += ngen + 1
+    assert pos == len(params)
+    out["exec_collision_free"] = ref.get("exec_collision_free").astype(np.int32)
+    ref.close()
+    return out
+
+
+def random_tree_case(seed):
+    rng = np.random.default_rng(100 + seed)
+    rb = scenes.random_tree(rng)
+    start = rng.uniform(-1, 1, (1, rb.num_dimensions))
+    goal = rng.uniform(-1, 1, (1, rb.num_dimensions))
+    out = cost_plugin_case("tiny", 1, 40 + seed, robot=rb, start=start, goal=goal)
+    out["start"], out["goal"] = start, goal
+    return out
+
+
 def main():
-    here = os.path.dirname(os.path.abspath(__file__))
-    for name, cumulative, iterations in CASES:
-        out = run_case(name, cumulative, iterations)
-        path = os.path.join(here, "ref_pi2_%s_c%d.npz" % (name.lower(), cumulative))
+    def save(stem, out):
+        path = os.path.join(HERE, stem + ".npz")
         np.savez_compressed(path, **out)
         print(path, len(out), "arrays", os.path.getsize(path) // 1024, "KiB")
+
+    for name, cumulative, iterations in ITERATION_CASES:
+        save("ref_iter_%s_c%d" % (name.lower(), cumulative), iteration_case(name, cumulative, iterations))
+    sc, cons, w = constraint_scene()
+    save("ref_iter_tiny_constraints", iteration_case("tiny", 1, 3, cons, w))
+    save("ref_cost_tiny", cost_plugin_case("tiny", 4, 21))
+    save("ref_cost_c1", cost_plugin_case("C1", 2, 22))
+    save("ref_cost_tiny_constraints", cost_plugin_case("tiny", 3, 23, cons, w))
+    for seed in (0, 1, 2):
+        save("ref_cost_tree%d" % seed, random_tree_case(seed))
+    save("ref_optimize_tiny_s8", optimize_case("tiny", 8, 60, 5))     # collision free at iteration 28, early exit after 33
+    save("ref_optimize_tiny_s7", optimize_case("tiny", 7, 20, 6))     # never collision free: runs to max_iterations
+    save("ref_optimize_c1_s8", optimize_case("C1", 8, 40, 5))        # collision free from the first iteration
 
 
 if __name__ == "__main__":

@@ -1,102 +1,172 @@
-"""Pins the CPU oracle to OUTPUTS OF THE REFERENCE ITSELF for the PI^2 half of the path.
+"""Pins the CPU oracle to OUTPUTS OF THE REFERENCE ITSELF.
 
-tests/golden/ref_pi2_*.npz were produced by the reference's own, unmodified translation units
-(src/policy_improvement.cpp, src/policy_improvement_loop.cpp, src/covariant_trajectory_policy.cpp, src/stomp_cost.cpp,
-include/.../multivariate_gaussian.h) compiled against stand-in Eigen 2 / roscpp / Boost headers (oracle/ref_shim/,
-oracle/ref_driver.cpp, tests/golden/make_ref_golden.py).  The oracle is fed the noise the reference drew
-(host-injection mode) and must reproduce every intermediate of PolicyImprovementLoop::runSingleIteration.
+tests/golden/ref_*.npz were produced by 11 of the reference's 14 translation units, compiled UNMODIFIED from
+/root/reference/stomp_motion_planner/src (PolicyImprovementLoop, PolicyImprovement, CovariantTrajectoryPolicy,
+MultivariateGaussian, StompCost, StompOptimizer incl. execute / handleJointLimits / performForwardKinematics / optimize,
+StompTrajectory, StompCollisionPoint, both TreeFkSolverJointPosAxis solvers, OrientationConstraintEvaluator,
+StompParameters) against stand-in headers for the third-party packages it does not vendor (oracle/ref_shim/: Eigen 2,
+roscpp, Boost, KDL, distance_field, Bullet).  oracle/ref_driver.cpp + tests/golden/make_ref_golden.py are the recipe.
 
-Tolerance 1e-8 relative to the array's largest magnitude: the oracle and the compiled reference sum dense products in
-different orders and invert R (cond ~ 6e6) with different eliminations; observed agreement is 1e-13 (N=20) to 3e-9 (N=100).
-Not pinned by these vectors: the cost plugin (StompOptimizer::execute cannot be compiled here) — `state_costs` in the
-fixtures are the oracle's own answers to the reference's Task::execute calls.
+The oracle is fed the noise the reference drew (host-injection mode) and must reproduce every intermediate of
+PolicyImprovementLoop::runSingleIteration, every per-sphere quantity of StompOptimizer::execute and the statistics of
+StompOptimizer::optimize.
+
+Tolerances: integer work (voxel indices, collision flags, reuse ranking, iteration counts) exact; floating point 1e-8
+relative to the array's largest magnitude — the oracle and the compiled reference sum dense products in different orders and
+invert R (cond ~ 6e6) with different eliminations; observed agreement is 1e-13 (N=20) to 3e-9 (N=100).
 """
 import os
 
 import numpy as np
 import pytest
 
-from oracle import oracle, reference_pi2
-from stomp_motion_planner_icra2011_b200 import _abi, scenes
+from oracle import oracle, reference
+from stomp_motion_planner_icra2011_b200 import _abi
+from tests import ref_golden as rg
 from tests.helpers import assert_close
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = [("tiny", 0), ("tiny", 1), ("C1", 1), ("C1", 0)]
 RTOL = 1e-8
-
-FIELDS = ((_abi.FIELD_NOISE_PROJECTED, "noise_projected"), (_abi.FIELD_PARAMETERS, "parameters"),
-          (_abi.FIELD_STATE_COSTS, "state_costs"), (_abi.FIELD_CONTROL_COSTS, "control_costs"),
-          (_abi.FIELD_CUMULATIVE_COSTS, "cumulative_costs"), (_abi.FIELD_PROBABILITIES, "probabilities"),
-          (_abi.FIELD_UPDATES, "updates"), (_abi.FIELD_THETA, "theta"), (_abi.FIELD_ROLLOUT_TOTAL_COSTS, "totals"))
-
-
-def _load(name, cumulative):
-    return np.load(os.path.join(GOLDEN, "ref_pi2_%s_c%d.npz" % (name.lower(), cumulative)))
-
-
-def _iterations(g):
-    return sorted(int(k[2:k.index("_")]) for k in g.files if k.endswith("_theta"))
 
 
 @pytest.mark.parametrize("name", ["tiny", "C1"])
 def test_setup_matrices_match_the_compiled_reference(name):
     """R, R^-1, M (column-max scaling), chol(R^-1), the joint-limit Q^-1 and the min-control-cost trajectory."""
-    g = _load(name, 1)
-    sc = scenes.make_scenario(name, num_problems=1, use_cumulative_costs=1)
+    g = rg.load("ref_iter_%s_c1" % name.lower())
+    sc = rg.scenario(name, g)
     o = oracle.Oracle(sc, 0)
-    for f, nm in ((_abi.FIELD_CONTROL_COST, "control_cost_matrix"), (_abi.FIELD_INV_CONTROL_COST, "inv_control_cost_matrix"),
-                  (_abi.FIELD_PROJECTION, "projection_matrix"), (_abi.FIELD_NOISE_CHOLESKY, "covariance_cholesky"),
-                  (_abi.FIELD_QUAD_COST_INV, "quad_cost_inv"), (_abi.FIELD_THETA, "theta0")):
+    for f, nm in rg.SETUP_FIELDS + ((_abi.FIELD_THETA, "theta0"),):
         assert_close(o.get(f), g[nm], 1e-7 if nm == "covariance_cholesky" else RTOL, nm)
     # KAT from src/policy_improvement.cpp:430-436, now checked on the reference's own M
     np.testing.assert_allclose(g["projection_matrix"].max(axis=0), 1.0 / sc.num_time_steps, rtol=1e-12)
     assert float(g["movement_dt"][0]) == sc.movement_duration / (sc.num_time_steps + 1)
-
-
-@pytest.mark.parametrize("name", ["tiny", "C1"])
-def test_control_cost_function_matches_the_compiled_reference(name):
-    g = _load(name, 1)
-    sc = scenes.make_scenario(name, num_problems=1, use_cumulative_costs=1)
-    o = oracle.Oracle(sc, 0)
     got = o.compute_control_costs(g["cc_parameters"][None], g["cc_noise"][None], 0.5 * sc.smoothness_cost_weight)[0]
     assert_close(got, g["cc_out"], RTOL, "computeControlCosts")
 
 
-@pytest.mark.parametrize("name,cumulative", CASES)
-def test_oracle_reproduces_the_reference_iterations(name, cumulative):
-    g = _load(name, cumulative)
-    sc = scenes.make_scenario(name, num_problems=1, use_cumulative_costs=cumulative)
-    o = oracle.Oracle(sc, 0)
+def _check_iterations(sc, g, o):
+    R = sc.num_rollouts
     assert_close(o.get(_abi.FIELD_THETA), g["theta0"], RTOL, "theta0")
-    for it in _iterations(g):
+    for it in rg.iterations(g):
         k = "it%d_" % it
-        _, _, ngen = o.iterate(it, g[k + "noise"])
+        cost, cf, ngen = o.iterate(it, g[k + "noise"])
         assert ngen == int(g[k + "num_rollouts_gen"])
         np.testing.assert_array_equal(o.get(_abi.FIELD_NOISE)[:ngen], g[k + "noise"])
-        for f, nm in FIELDS:
+        for f, nm in rg.ITERATION_FIELDS:
             assert_close(o.get(f), g[k + nm], RTOL, "%s it %d" % (nm, it))
-        # the reuse order is integer work: the ranking of (getCost(), index) must be the reference's
-        assert np.array_equal(np.argsort(o.get(_abi.FIELD_ROLLOUT_TOTAL_COSTS), kind="stable"),
-                              np.argsort(g[k + "totals"], kind="stable"))
+        assert_close(cost, float(g[k + "noiseless_cost"]), RTOL, "noise-less rollout cost")
+        assert cf == int(g[k + "noiseless_flags"][0])
+        assert_close(o.get(_abi.FIELD_NOISELESS_COSTS), g[k + "exec_costs"][-1], RTOL, "noise-less state costs")
+        ecf = o.get(_abi.FIELD_COLLISION_FREE)
+        np.testing.assert_array_equal(ecf[:ngen], g[k + "exec_collision_free"][:ngen])
+        assert ecf[R] == g[k + "exec_collision_free"][-1]
+        # integer work: the ranking that selects the next iteration's reused rollouts
+        assert rg.reuse_ranking(o.get(_abi.FIELD_ROLLOUT_TOTAL_COSTS), R) == rg.reuse_ranking(g[k + "totals"], R)
+        yield it, k
+
+
+@pytest.mark.parametrize("name,cumulative", [("tiny", 0), ("tiny", 1), ("C1", 1), ("C1", 0)])
+def test_oracle_reproduces_the_reference_iterations(name, cumulative):
+    g = rg.load("ref_iter_%s_c%d" % (name.lower(), cumulative))
+    sc = rg.scenario(name, g, cumulative)
+    assert len(list(_check_iterations(sc, g, oracle.Oracle(sc, 0)))) >= 2
+
+
+def test_oracle_reproduces_the_reference_iterations_with_orientation_constraints():
+    g = rg.load("ref_iter_tiny_constraints")
+    sc, cons, w = rg.constraint_scene(g)
+    o = oracle.Oracle(sc, 0)
+    o.set_constraints(cons, w)
+    for it, k in _check_iterations(sc, g, o):
+        assert o.get(_abi.FIELD_CONSTRAINTS_SATISFIED)[sc.num_rollouts] == g[k + "noiseless_flags"][1]
 
 
 def test_reused_rollouts_are_the_references_choice():
     """slots [R_gen, R) of iteration i+1 hold the R_reuse cheapest of iteration i's R rollouts + the noise-less one."""
-    g = _load("C1", 1)
+    g = rg.load("ref_iter_c1_c1")
     R, Rre = 10, 5
-    for it in _iterations(g)[:-1]:
-        tot = g["it%d_totals" % it]                      # [R] + extra
-        order = sorted(range(R + 1), key=lambda r: (tot[r], -1 if r == R else r))[:Rre]
+    for it in rg.iterations(g)[:-1]:
+        order = rg.reuse_ranking(g["it%d_totals" % it], R)[:Rre]
         prev_params = np.concatenate([g["it%d_parameters" % it], g["it%d_theta" % it][None]])
         np.testing.assert_array_equal(g["it%d_parameters" % (it + 1)][R - Rre:], prev_params[order])
 
 
-@pytest.mark.skipif(not os.path.isdir(reference_pi2.REFERENCE_ROOT), reason="/root/reference is not on this machine")
+def _check_cost_plugin(sc, g, o, constraints=False):
+    org, res = sc.sdf.origin, sc.sdf.resolution
+    n = g["parameters"].shape[0]
+    flips = 0
+    for r in range(n):
+        for i, itn in enumerate((1, 2)):
+            costs, cf = o.execute(g["parameters"][r], itn)
+            assert_close(costs[0], g["costs"][r, i], RTOL, "state costs, rollout %d iteration %d" % (r, itn))
+            assert cf[0] == g["flags"][r, i, 0]
+            if constraints:
+                assert o.execute_constraints_satisfied(1)[0] == g["flags"][r, i, 1]
+        dbg, clipped = o.execute_debug(g["parameters"][r])
+        assert_close(clipped, g["clipped"][r], RTOL, "trajectory after handleJointLimits")
+        assert_close(dbg["position"], g["dbg_position"][r], 1e-9, "collision point positions", atol_scale=1e-9)
+        safe = rg.boundary_safe(g["dbg_position"][r], org, res)
+        flips += int((~safe).sum())
+        np.testing.assert_array_equal(dbg["voxel"][safe], g["dbg_voxel"][r][safe])          # bit-exact integer work
+        np.testing.assert_array_equal(dbg["in_collision"][safe], g["dbg_in_collision"][r][safe])
+        assert_close(dbg["potential"][safe], g["dbg_potential"][r][safe], RTOL, "potential")
+        assert_close(dbg["vel_mag"], g["dbg_vel_mag"][r], RTOL, "velocity magnitude")
+    assert flips < 5
+
+
+@pytest.mark.parametrize("name", ["tiny", "C1"])
+def test_cost_plugin_matches_the_compiled_stomp_optimizer(name):
+    """StompOptimizer::execute: joint limits, FK, sphere positions, voxel indices, collision flags, potential, |v|, costs."""
+    g = rg.load("ref_cost_%s" % name.lower())
+    sc = rg.scenario(name, g)
+    _check_cost_plugin(sc, g, oracle.Oracle(sc, 0))
+    assert g["dbg_in_collision"].any() and (g["dbg_potential"] > 0).any(), "fixture exercises no obstacle"
+    assert np.abs(g["clipped"] - g["parameters"]).max() > 1e-3, "fixture exercises no joint limit"
+
+
+def test_cost_plugin_with_orientation_constraints_matches_the_compiled_reference():
+    g = rg.load("ref_cost_tiny_constraints")
+    sc, cons, w = rg.constraint_scene(g)
+    o = oracle.Oracle(sc, 0)
+    o.set_constraints(cons, w)
+    _check_cost_plugin(sc, g, o, constraints=True)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_forward_kinematics_of_random_trees_matches_the_compiled_solvers(seed):
+    """branching trees with fixed / prismatic / revolute joints through TreeFkSolverJointPosAxisPartial."""
+    g = rg.load("ref_cost_tree%d" % seed)
+    sc = rg.tree_scene(seed, g)
+    _check_cost_plugin(sc, g, oracle.Oracle(sc, 0))
+
+
+@pytest.mark.parametrize("stem,name", [("ref_optimize_tiny_s8", "tiny"), ("ref_optimize_tiny_s7", "tiny"), ("ref_optimize_c1_s8", "C1")])
+def test_optimize_bookkeeping_matches_the_compiled_reference(stem, name):
+    """StompOptimizer::optimize end to end: success iteration, early exit, cost log, best trajectory."""
+    g = rg.load(stem)
+    sc = rg.scenario(name, g, seed=int(g["seed"]))
+    o = oracle.Oracle(sc, 0)
+    assert_close(o.get(_abi.FIELD_THETA), g["theta0"], RTOL, "theta0")
+
+    def step(it):
+        cost, cf, _ = o.iterate(it, g["it%d_noise" % it])
+        return cost, cf, 1, o.get_parameters()
+
+    res = rg.host_bookkeeping(step, int(g["max_iterations"]), int(g["max_iterations_after_collision_free"]))
+    assert res["success"] == bool(g["stats_success"])
+    assert res["success_iteration"] == int(g["stats_success_iteration"]) == int(g["stats_collision_success_iteration"])
+    assert res["iterations"] == int(g["stats_iterations"])
+    assert res["last_improvement_iteration"] == int(g["stats_last_improvement_iteration"])
+    assert_close(res["costs"], g["stats_costs"], 1e-7, "STOMPStatistics.costs")
+    assert_close(res["best_cost"], float(g["stats_best_cost"]), 1e-7, "best cost")
+
+
+@pytest.mark.skipif(not os.path.isdir(reference.REFERENCE_ROOT), reason="/root/reference is not on this machine")
 def test_fixtures_are_what_the_compiled_reference_produces_today():
     """Rebuild-and-rerun check (only where the reference sources exist): the committed vectors are reproducible."""
     from tests.golden import make_ref_golden
-    fresh = make_ref_golden.run_case("tiny", 1, 5)
-    g = _load("tiny", 1)
-    assert sorted(fresh) == sorted(g.files)
-    for k in g.files:
-        np.testing.assert_allclose(fresh[k], g[k], rtol=1e-12, atol=1e-300, err_msg=k)
+    for stem, fresh in (("ref_iter_tiny_c1", make_ref_golden.iteration_case("tiny", 1, 5)),
+                        ("ref_cost_tiny", make_ref_golden.cost_plugin_case("tiny", 4, 21))):
+        g = rg.load(stem)
+        assert sorted(fresh) == sorted(g.files)
+        for k in g.files:
+            np.testing.assert_allclose(fresh[k], g[k], rtol=1e-12, atol=1e-300, err_msg=k)
