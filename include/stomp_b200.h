@@ -208,6 +208,24 @@ int stomp_engine_build_sdf(void* engine, const double size[3], const double orig
                            const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders);
 /* Copies the current voxel grid out (parity tap): dims[3], voxel dtype, and up to `bytes` of voxels (may be NULL). */
 int stomp_engine_get_sdf(void* engine, int32_t dims[3], int32_t* voxel_dtype, void* voxels, size_t bytes);
+/* Inverse-dynamics (torque) cost term of StompOptimizer::execute (src/stomp_optimizer.cpp:1117-1142, getTorques :1006-1061):
+ *   costs(t) += torque_cost_weight * sum_j |tau_j(t)|,   tau = RNE(q(t), qd(t), qdd(t)) with zero external wrenches,
+ * q = the joint-limit-projected group trajectory, qd / qdd = its 7-tap finite differences (DIFF_RULES rows 0 and 1 over the
+ * padded trajectory, include/stomp_motion_planner/stomp_trajectory.h:286-310), RNE = KDL::ChainIdSolver_RNE over the
+ * KDL::Chain of the planning group (src/stomp_robot_model.cpp:181-185) with gravity (0, 0, -9.8) in the chain root's frame.
+ * The chain is the path chain_root_segment -> chain_tip_segment of the segment table (root excluded, like
+ * KDL::Tree::getChain); its movable joints must be exactly the group joints 0..D-1 in order (the reference indexes the chain
+ * solver's joint arrays by group joint).  One stomp_link_inertia per segment of the table = the KDL::RigidBodyInertia
+ * kdl_parser attaches to that segment: mass, centre of mass and rotational inertia about the centre of mass, all in the
+ * segment's own (link) frame.  The term is evaluated only when torque_cost_weight > 1e-9 (the reference's test); weight 0
+ * (every shipped configuration, src/stomp_parameters.cpp:56) removes it. */
+typedef struct stomp_link_inertia {
+  double mass;
+  double com[3];
+  double inertia[6]; /* ixx, iyy, izz, ixy, ixz, iyz */
+} stomp_link_inertia;
+int stomp_engine_set_dynamics(void* engine, const stomp_link_inertia* inertia /* [num_segments] */, int32_t chain_root_segment,
+                              int32_t chain_tip_segment, const double gravity[3], double torque_cost_weight);
 /* Orientation path constraints of the planning request (StompOptimizer::initialize, src/stomp_optimizer.cpp:196-201) and
  * constraint_cost_weight (config/params.yaml:12).  n == 0 removes them.  Must be called after stomp_engine_set_robot. */
 int stomp_engine_set_constraints(void* engine, const stomp_orientation_constraint* constraints, int32_t n,

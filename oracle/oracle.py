@@ -95,6 +95,18 @@ class Oracle:
             arr[i].weight = c.get("weight", 1.0)
         self._ck(self.L.stomp_oracle_set_constraints(self.h, arr, len(constraints), C.c_double(weight)))
 
+    def set_dynamics(self, torque_cost_weight, gravity=(0.0, 0.0, -9.8)):
+        """torque term of StompOptimizer::execute over the robot's inverse-dynamics chain (Robot.inertias / Robot.chain)."""
+        rb = self.sc.robot
+        g = np.ascontiguousarray(gravity, dtype=np.float64)
+        self._ck(self.L.stomp_oracle_set_dynamics(self.h, rb.c_inertias(), rb.chain[0], rb.chain[1], _dp(g),
+                                                  C.c_double(torque_cost_weight)))
+
+    def last_torques(self):
+        out = np.empty((self.N, self.D))
+        self._ck(self.L.stomp_oracle_last_torques(self.h, _dp(out)))
+        return out
+
     def execute_constraints_satisfied(self, n):
         out = np.empty(n, dtype=np.int32)
         self._ck(self.L.stomp_oracle_execute_constraints_satisfied(self.h, _ip(out), C.c_size_t(n)))

@@ -315,6 +315,7 @@ struct RefOpt {
   PolicyImprovementLoop* loop;
   ros::Publisher pub_a, pub_b, pub_stats;
   std::vector<uint8_t> voxels;
+  std::vector<stomp_segment> segs;
   RefOpt() : df(NULL), full(NULL), loop(NULL) {}
   ~RefOpt() {
     if (opt) opt->resetSharedPtr();
@@ -342,6 +343,7 @@ void* stomp_ref_opt_create(const stomp_engine_desc* desc, const stomp_segment* s
   RefOpt* h = new RefOpt;
   const int D = desc->num_dimensions, N = desc->num_time_steps;
   h->N = N; h->D = D; h->K = num_spheres; h->S = num_segments;
+  h->segs.assign(segs, segs + num_segments);
 
   /* ---- KDL tree from the segment table (kdl_parser: Joint(name, origin, axis, type), Segment(name, joint, f_tip)) */
   StompRobotModel& m = h->model;
@@ -484,6 +486,37 @@ void* stomp_ref_opt_create(const stomp_engine_desc* desc, const stomp_segment* s
 }
 
 void stomp_ref_opt_destroy(void* p) { delete static_cast<RefOpt*>(p); }
+
+/* KDL::Chain + ChainIdSolver_RNE of the planning group (src/stomp_robot_model.cpp:181-185, where the chain is hard-coded to
+ * the PR2's torso_lift_link -> r_gripper_tool_frame) for the path root -> tip of the table, with the segment inertias, and
+ * the torque_cost_weight parameter. */
+int stomp_ref_opt_set_dynamics(void* p, const stomp_link_inertia* inertia, int32_t root, int32_t tip, const double* gravity,
+                               double torque_cost_weight) {
+  RefOpt* h = static_cast<RefOpt*>(p);
+  std::vector<int> path;
+  for (int s = tip; s != root; s = h->segs[s].parent) {
+    if (s < 0) return 1;
+    path.push_back(s);
+  }
+  KDL::Chain chain;
+  for (size_t k = path.size(); k-- > 0;) {
+    const int i = path[k];
+    const stomp_segment& g = h->segs[i];
+    KDL::Vector pos(g.pos[0], g.pos[1], g.pos[2]), axis(g.axis[0], g.axis[1], g.axis[2]);
+    KDL::Rotation rot(g.rot[0], g.rot[1], g.rot[2], g.rot[3], g.rot[4], g.rot[5], g.rot[6], g.rot[7], g.rot[8]);
+    KDL::Joint joint = g.joint_type == STOMP_JOINT_REVOLUTE    ? KDL::Joint("j" + seg_name(i), pos, axis, KDL::Joint::RotAxis)
+                       : g.joint_type == STOMP_JOINT_PRISMATIC ? KDL::Joint("j" + seg_name(i), pos, axis, KDL::Joint::TransAxis)
+                                                               : KDL::Joint("j" + seg_name(i), KDL::Joint::None);
+    KDL::RigidBodyInertia rbi(inertia[i].mass, KDL::Vector(inertia[i].com[0], inertia[i].com[1], inertia[i].com[2]),
+                              inertia[i].inertia);
+    chain.addSegment(KDL::Segment(seg_name(i), joint, KDL::Frame(rot, pos), rbi));
+  }
+  StompRobotModel::StompPlanningGroup& group = h->model.planning_groups_.find("group")->second;
+  group.kdl_chain_ = chain;
+  group.id_solver_.reset(new KDL::ChainIdSolver_RNE(group.kdl_chain_, KDL::Vector(gravity[0], gravity[1], gravity[2])));
+  h->params.torque_cost_weight_ = torque_cost_weight;
+  return int(chain.getNrOfJoints()) == h->D ? 0 : 2;
+}
 
 /* numbers the test checks before trusting anything else: [0] derived policy movement duration (int-truncated group
  * duration, src/stomp_optimizer.cpp:185), [1] num_vars_free, [2] num_vars_all, [3] free_vars_start, [4] #segments of the FK

@@ -44,6 +44,8 @@ inline Vector operator*(const Vector& a, const Vector& b) {  // cross product, a
 inline double dot(const Vector& a, const Vector& b) { return a.data[0] * b.data[0] + a.data[1] * b.data[1] + a.data[2] * b.data[2]; }
 inline void SetToZero(Vector& v) { v = Vector::Zero(); }
 
+class Twist;
+class Wrench;
 class Rotation {
  public:
   double data[9];  // row-major
@@ -61,6 +63,8 @@ class Rotation {
                   data[6] * v.data[0] + data[7] * v.data[1] + data[8] * v.data[2]);
   }
   Vector Inverse(const Vector& v) const { return Inverse() * v; }
+  inline Twist Inverse(const Twist& t) const;
+  inline Twist operator*(const Twist& t) const;
   // rotation of `angle` about a unit-length axis
   static Rotation Rot2(const Vector& v, double angle) {
     double ct = std::cos(angle), st = std::sin(angle), vt = 1 - ct;
@@ -123,19 +127,44 @@ class Frame {
   static Frame Identity() { return Frame(); }
   Frame Inverse() const { Rotation Mi = M.Inverse(); return Frame(Mi, -(Mi * p)); }
   Vector operator*(const Vector& v) const { return M * v + p; }
+  inline Twist operator*(const Twist& t) const;
+  inline Twist Inverse(const Twist& t) const;
+  inline Wrench operator*(const Wrench& w) const;
 };
 inline Frame operator*(const Frame& a, const Frame& b) { return Frame(a.M * b.M, a.M * b.p + a.p); }
 
 class Twist {
  public:
   Vector vel, rot;
+  Twist() {}
+  Twist(const Vector& v, const Vector& r) : vel(v), rot(r) {}
   static Twist Zero() { return Twist(); }
+  // the same motion seen at a reference point displaced by v_base_AB
+  Twist RefPoint(const Vector& v_base_AB) const { return Twist(vel + rot * v_base_AB, rot); }
 };
 class Wrench {
  public:
   Vector force, torque;
+  Wrench() {}
+  Wrench(const Vector& f, const Vector& t) : force(f), torque(t) {}
   static Wrench Zero() { return Wrench(); }  // static, as in KDL: `wrenches[i].Zero()` in the reference is a no-op on the element
 };
+inline Twist operator+(const Twist& a, const Twist& b) { return Twist(a.vel + b.vel, a.rot + b.rot); }
+inline Twist operator-(const Twist& a) { return Twist(-a.vel, -a.rot); }
+inline Twist operator*(const Twist& a, double s) { return Twist(a.vel * s, a.rot * s); }
+inline Twist operator*(double s, const Twist& a) { return Twist(a.vel * s, a.rot * s); }
+// spatial cross products (KDL frames.inl)
+inline Twist operator*(const Twist& lhs, const Twist& rhs) { return Twist(lhs.rot * rhs.vel + lhs.vel * rhs.rot, lhs.rot * rhs.rot); }
+inline Wrench operator*(const Twist& lhs, const Wrench& rhs) { return Wrench(lhs.rot * rhs.force, lhs.rot * rhs.torque + lhs.vel * rhs.force); }
+inline Wrench operator+(const Wrench& a, const Wrench& b) { return Wrench(a.force + b.force, a.torque + b.torque); }
+inline Wrench operator-(const Wrench& a, const Wrench& b) { return Wrench(a.force - b.force, a.torque - b.torque); }
+inline double dot(const Twist& t, const Wrench& w) { return dot(t.vel, w.force) + dot(t.rot, w.torque); }
+
+inline Twist Rotation::Inverse(const Twist& t) const { return Twist(Inverse(t.vel), Inverse(t.rot)); }
+inline Twist Rotation::operator*(const Twist& t) const { return Twist((*this) * t.vel, (*this) * t.rot); }
+inline Twist Frame::operator*(const Twist& t) const { Vector r = M * t.rot; return Twist(M * t.vel + p * r, r); }
+inline Twist Frame::Inverse(const Twist& t) const { return Twist(M.Inverse(t.vel - p * t.rot), M.Inverse(t.rot)); }
+inline Wrench Frame::operator*(const Wrench& w) const { Vector f = M * w.force; return Wrench(f, M * w.torque + p * f); }
 
 }  // namespace KDL
 #endif

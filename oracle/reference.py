@@ -203,6 +203,14 @@ class ReferenceOptimizer:
         except Exception:
             pass
 
+    def set_dynamics(self, torque_cost_weight, gravity=(0.0, 0.0, -9.8)):
+        rb = self.sc.robot
+        g = np.ascontiguousarray(gravity, dtype=np.float64)
+        rc = self.L.stomp_ref_opt_set_dynamics(self.h, rb.c_inertias(), rb.chain[0], rb.chain[1], _dp(g),
+                                               C.c_double(torque_cost_weight))
+        if rc != 0:
+            raise RuntimeError("stomp_ref_opt_set_dynamics failed (rc %d)" % rc)
+
     def execute(self, parameters, iteration_number=2):
         """StompOptimizer::execute -> (costs[N], collision_free, constraints_satisfied)."""
         p = np.ascontiguousarray(parameters, dtype=np.float64).reshape(self.D, self.N)

@@ -265,6 +265,13 @@ struct Oracle {
   double last_cost = 0.0;
   Vec noiseless_costs;
   std::vector<int> collision_free_slots; /* [R+1] */
+  /* inverse dynamics of the planning group's chain (src/stomp_optimizer.cpp:1006-1061; KDL::ChainIdSolver_RNE restated) */
+  struct ChainLink { int seg; double m, h[3], I[9]; };
+  std::vector<ChainLink> chain;
+  double gravity[3] = {0, 0, -9.8};
+  double torque_cost_weight = 0.0;
+  Vec last_torques; /* [N][D] of the last execute (parity tap) */
+
   /* constraint evaluators (src/constraint_evaluator.cpp) */
   std::vector<stomp_orientation_constraint> constraints;
   double constraint_cost_weight = 0.0;
@@ -541,8 +548,118 @@ bool perform_forward_kinematics(Oracle& o) {
   return is_collision_free;
 }
 
-/* StompOptimizer::execute, src/stomp_optimizer.cpp:1063-1165 (constraint and torque terms are
- * outside the path: no constraint evaluators, torque_cost_weight = 0) */
+/* ---- inverse dynamics: KDL::ChainIdSolver_RNE::CartToJnt restated (orocos KDL 1.0, Featherstone's recursive Newton-Euler in
+ * segment-tip coordinates; spatial vectors kept as (linear, angular) pairs like KDL::Twist / KDL::Wrench) ------------------ */
+inline void cross3(const double a[3], const double b[3], double o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline void rot_t(const double R[9], const double v[3], double o[3]) { /* R^T v */
+  for (int i = 0; i < 3; ++i) o[i] = R[i] * v[0] + R[3 + i] * v[1] + R[6 + i] * v[2];
+}
+inline void rot_n(const double R[9], const double v[3], double o[3]) { /* R v */
+  for (int i = 0; i < 3; ++i) o[i] = R[i * 3] * v[0] + R[i * 3 + 1] * v[1] + R[i * 3 + 2] * v[2];
+}
+struct Spatial { double lin[3], ang[3]; };
+/* Frame::Inverse(Twist): the twist seen from the child frame X */
+Spatial twist_to_child(const Frame& X, const Spatial& t) {
+  double pxw[3], d[3];
+  Spatial o;
+  cross3(X.p, t.ang, pxw);
+  for (int i = 0; i < 3; ++i) d[i] = t.lin[i] - pxw[i];
+  rot_t(X.R, d, o.lin);
+  rot_t(X.R, t.ang, o.ang);
+  return o;
+}
+/* RigidBodyInertia * Twist */
+Spatial inertia_times(const Oracle::ChainLink& L, const Spatial& t) {
+  Spatial w;
+  double hxw[3], hxv[3], Iw[3];
+  cross3(L.h, t.ang, hxw);
+  cross3(L.h, t.lin, hxv);
+  rot_n(L.I, t.ang, Iw);
+  for (int i = 0; i < 3; ++i) { w.lin[i] = L.m * t.lin[i] - hxw[i]; w.ang[i] = Iw[i] + hxv[i]; }
+  return w;
+}
+/* torques[D] of one trajectory point (group joint values q, velocities qd, accelerations qdd) */
+void chain_inverse_dynamics(const Oracle& o, const double* q, const double* qd, const double* qdd, double* torques) {
+  const int ns = int(o.chain.size());
+  std::vector<Frame> X(ns);
+  std::vector<Spatial> S(ns), f(ns);
+  Spatial v = {}, a = {};
+  for (int i = 0; i < ns; ++i) {
+    const stomp_segment& sg = o.segs[o.chain[i].seg];
+    const int j = sg.group_index;
+    const double q_ = j >= 0 ? q[j] : 0.0, qd_ = j >= 0 ? qd[j] : 0.0, qdd_ = j >= 0 ? qdd[j] : 0.0;
+    X[i] = segment_pose(sg, q_);
+    /* unit twist of the joint in the parent frame: the segment tip sits on the joint origin (kdl_parser), so no RefPoint shift */
+    Spatial unit = {};
+    if (j >= 0 && sg.joint_type == STOMP_JOINT_REVOLUTE) for (int k = 0; k < 3; ++k) unit.ang[k] = sg.axis[k];
+    if (j >= 0 && sg.joint_type == STOMP_JOINT_PRISMATIC) for (int k = 0; k < 3; ++k) unit.lin[k] = sg.axis[k];
+    rot_t(X[i].R, unit.lin, S[i].lin);
+    rot_t(X[i].R, unit.ang, S[i].ang);
+    Spatial vj;
+    for (int k = 0; k < 3; ++k) { vj.lin[k] = S[i].lin[k] * qd_; vj.ang[k] = S[i].ang[k] * qd_; }
+    Spatial vp, ap;
+    if (i == 0) {
+      vp = Spatial{};
+      Spatial ag = {};
+      for (int k = 0; k < 3; ++k) ag.lin[k] = -o.gravity[k];
+      ap = twist_to_child(X[i], ag);
+    } else {
+      vp = twist_to_child(X[i], v);
+      ap = twist_to_child(X[i], a);
+    }
+    for (int k = 0; k < 3; ++k) { v.lin[k] = vp.lin[k] + vj.lin[k]; v.ang[k] = vp.ang[k] + vj.ang[k]; }
+    /* v x vj (Twist * Twist) */
+    double c1[3], c2[3], c3[3];
+    cross3(v.ang, vj.lin, c1);
+    cross3(v.lin, vj.ang, c2);
+    cross3(v.ang, vj.ang, c3);
+    for (int k = 0; k < 3; ++k) {
+      a.lin[k] = ap.lin[k] + S[i].lin[k] * qdd_ + c1[k] + c2[k];
+      a.ang[k] = ap.ang[k] + S[i].ang[k] * qdd_ + c3[k];
+    }
+    /* f = I a + v x* (I v) */
+    Spatial Ia = inertia_times(o.chain[i], a), Iv = inertia_times(o.chain[i], v);
+    double d1[3], d2[3], d3[3];
+    cross3(v.ang, Iv.lin, d1);
+    cross3(v.ang, Iv.ang, d2);
+    cross3(v.lin, Iv.lin, d3);
+    for (int k = 0; k < 3; ++k) { f[i].lin[k] = Ia.lin[k] + d1[k]; f[i].ang[k] = Ia.ang[k] + d2[k] + d3[k]; }
+  }
+  for (int i = ns - 1; i >= 0; --i) {
+    const int j = o.segs[o.chain[i].seg].group_index;
+    if (j >= 0) {
+      double t = 0.0;
+      for (int k = 0; k < 3; ++k) t += S[i].lin[k] * f[i].lin[k] + S[i].ang[k] * f[i].ang[k];
+      torques[j] = t;
+    }
+    if (i != 0) { /* Frame * Wrench into the parent's coordinates */
+      double F[3], T[3], pxF[3];
+      rot_n(X[i].R, f[i].lin, F);
+      rot_n(X[i].R, f[i].ang, T);
+      cross3(X[i].p, F, pxF);
+      for (int k = 0; k < 3; ++k) { f[i - 1].lin[k] += F[k]; f[i - 1].ang[k] += T[k] + pxF[k]; }
+    }
+  }
+}
+
+/* StompOptimizer::getTorques, src/stomp_optimizer.cpp:1034-1060: joint velocities / accelerations by the 7-tap rules over the
+ * group trajectory (include/stomp_motion_planner/stomp_trajectory.h:286-310), then the chain's inverse dynamics */
+void get_torques(const Oracle& o, int index, double* torques) {
+  Vec q(o.D), qd(o.D, 0.0), qdd(o.D, 0.0);
+  const double invTime = 1.0 / o.desc.discretization, invTime2 = 1.0 / (o.desc.discretization * o.desc.discretization);
+  for (int d = 0; d < o.D; ++d) {
+    q[d] = o.group_traj[d][index];
+    for (int k = -DIFF_RULE_LENGTH / 2; k <= DIFF_RULE_LENGTH / 2; ++k) {
+      qd[d] += (invTime * DIFF_RULES[0][k + DIFF_RULE_LENGTH / 2]) * o.group_traj[d][index + k];
+      qdd[d] += (invTime2 * DIFF_RULES[1][k + DIFF_RULE_LENGTH / 2]) * o.group_traj[d][index + k];
+    }
+  }
+  chain_inverse_dynamics(o, q.data(), qd.data(), qdd.data(), torques);
+}
+
+/* StompOptimizer::execute, src/stomp_optimizer.cpp:1063-1165 */
 void task_execute(Oracle& o, const std::vector<Vec>& parameters, Vec& costs, int iteration_number) {
   o.iteration_ = iteration_number - 1; /* optimize() calls runSingleIteration(iteration_+1) */
   for (int d = 0; d < o.D; ++d)
@@ -552,6 +669,7 @@ void task_execute(Oracle& o, const std::vector<Vec>& parameters, Vec& costs, int
   o.last_collision_free = perform_forward_kinematics(o);
   o.last_constraints_satisfied = true;
   costs.assign(o.N, 0.0);
+  o.last_torques.assign(size_t(o.N) * o.D, 0.0);
   for (int i = o.fs; i <= o.fe; ++i) {
     double state_collision_cost = 0.0, cumulative = 0.0;
     for (int j = 0; j < o.K; ++j) {
@@ -564,7 +682,17 @@ void task_execute(Oracle& o, const std::vector<Vec>& parameters, Vec& costs, int
       if (!constraint_cost(c, o.cp_frames[size_t(i) * o.segs.size() + c.segment], cost)) o.last_constraints_satisfied = false;
       state_constraint_cost += cost;
     }
-    costs[i - o.fs] = o.desc.obstacle_cost_weight * state_collision_cost + o.constraint_cost_weight * state_constraint_cost;
+    double state_torque_cost = 0.0;
+    if (o.torque_cost_weight > 1e-9) {
+      Vec torques(o.D, 0.0);
+      get_torques(o, i, torques.data());
+      for (int j = 0; j < o.D; ++j) {
+        state_torque_cost += std::fabs(torques[j]);
+        o.last_torques[size_t(i - o.fs) * o.D + j] = torques[j];
+      }
+    }
+    costs[i - o.fs] = o.desc.obstacle_cost_weight * state_collision_cost + o.constraint_cost_weight * state_constraint_cost +
+                      o.torque_cost_weight * state_torque_cost;
   }
   double s = 0.0;
   for (double c : costs) s += c;
@@ -822,6 +950,48 @@ int stomp_oracle_set_constraints(void* h, const stomp_orientation_constraint* c,
     if (c[i].segment < 0 || c[i].segment >= int(o.segs.size())) return fail("constraint segment out of range");
   o.constraints.assign(c, c + n);
   o.constraint_cost_weight = weight;
+  return 0;
+}
+
+int stomp_oracle_set_dynamics(void* h, const stomp_link_inertia* inertia, int32_t root, int32_t tip, const double* gravity,
+                              double torque_cost_weight) {
+  Oracle& o = *static_cast<Oracle*>(h);
+  std::vector<int> path;
+  for (int s = tip; s != root; s = o.segs[s].parent) {
+    if (s < 0 || s >= int(o.segs.size())) return fail("chain tip is not below chain root");
+    path.push_back(s);
+  }
+  o.chain.clear();
+  int next_joint = 0;
+  for (size_t k = path.size(); k-- > 0;) {
+    const int i = path[k];
+    if (o.segs[i].joint_type != STOMP_JOINT_FIXED) {
+      if (o.segs[i].group_index != next_joint) return fail("the chain's movable joints must be the group joints in order");
+      ++next_joint;
+    }
+    Oracle::ChainLink L;
+    L.seg = i;
+    L.m = inertia[i].mass;
+    const double* c = inertia[i].com;
+    const double* Ic = inertia[i].inertia;
+    const double cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+    for (int a = 0; a < 3; ++a) L.h[a] = L.m * c[a];
+    /* inertia about the frame origin: Ic + m (|c|^2 1 - c c^T) */
+    const double full[9] = {Ic[0], Ic[3], Ic[4], Ic[3], Ic[1], Ic[5], Ic[4], Ic[5], Ic[2]};
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) L.I[a * 3 + b] = full[a * 3 + b] + L.m * ((a == b ? cc : 0.0) - c[a] * c[b]);
+    o.chain.push_back(L);
+  }
+  if (next_joint != o.D) return fail("the chain's movable joints must be the group joints in order");
+  for (int a = 0; a < 3; ++a) o.gravity[a] = gravity[a];
+  o.torque_cost_weight = torque_cost_weight;
+  return 0;
+}
+
+/* joint torques [N][D] of the last execute (0 when the torque term is off) */
+int stomp_oracle_last_torques(void* h, double* out) {
+  Oracle& o = *static_cast<Oracle*>(h);
+  std::copy(o.last_torques.begin(), o.last_torques.end(), out);
   return 0;
 }
 

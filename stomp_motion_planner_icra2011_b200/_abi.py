@@ -93,6 +93,10 @@ class OrientationConstraint(C.Structure):
     ]
 
 
+class LinkInertia(C.Structure):
+    _fields_ = [("mass", C.c_double), ("com", C.c_double * 3), ("inertia", C.c_double * 6)]
+
+
 class SphereDebug(C.Structure):
     _fields_ = [
         ("voxel", C.c_int32 * 3),

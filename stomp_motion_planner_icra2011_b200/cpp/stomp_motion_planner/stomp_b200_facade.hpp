@@ -53,6 +53,7 @@ struct StompParameters {
   int max_iterations = 500, max_iterations_after_collision_free = 500;
   double smoothness_cost_velocity = 0.0, smoothness_cost_acceleration = 1.0, smoothness_cost_jerk = 0.0;
   double smoothness_cost_weight = 0.1, obstacle_cost_weight = 1.0, ridge_factor = 0.0;
+  double torque_cost_weight = 0.0;   // src/stomp_parameters.cpp:56; > 1e-9 turns the inverse-dynamics term on
   // PolicyImprovementLoop::readParameters (src/policy_improvement_loop.cpp:112-123)
   int num_rollouts = 10, num_reused_rollouts = 5, num_time_steps = 99;
   std::vector<double> noise_stddev, noise_decay;
@@ -68,6 +69,10 @@ struct StompRobotModel {
   int reference_segment = 0;
   std::vector<stomp_sphere> collision_points;
   std::vector<stomp_joint_limit> joint_limits;  // one per planning-group joint
+  // StompPlanningGroup::kdl_chain_ / id_solver_ (src/stomp_robot_model.cpp:181-185): one inertia per segment and the
+  // root / tip of the inverse-dynamics chain; only read when StompParameters::torque_cost_weight > 1e-9
+  std::vector<stomp_link_inertia> link_inertias;
+  int chain_root_segment = -1, chain_tip_segment = -1;
   int getNumJoints() const { return int(joint_limits.size()); }
 };
 
@@ -387,6 +392,13 @@ class StompOptimizer : public Task, public std::enable_shared_from_this<StompOpt
     if (stomp_engine_set_sdf(h, collision_space_->voxels.data(), collision_space_->nx, collision_space_->ny, collision_space_->nz,
                              collision_space_->origin, collision_space_->resolution, collision_space_->voxel_dtype))
       return false;
+    if (parameters_->torque_cost_weight > 1e-9) {   // src/stomp_optimizer.cpp:1120
+      const double gravity[3] = {0.0, 0.0, -9.8};   // src/stomp_robot_model.cpp:184
+      if (robot_model_->link_inertias.size() != robot_model_->segments.size() ||
+          stomp_engine_set_dynamics(h, robot_model_->link_inertias.data(), robot_model_->chain_root_segment,
+                                    robot_model_->chain_tip_segment, gravity, parameters_->torque_cost_weight))
+        return false;
+    }
     std::vector<double> sd = parameters_->noise_stddev, dc = parameters_->noise_decay;
     sd.resize(d.num_dimensions, 2.0);
     dc.resize(d.num_dimensions, 0.999);

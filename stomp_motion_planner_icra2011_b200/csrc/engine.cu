@@ -81,6 +81,12 @@ struct Engine {
   sh::PolicyMatrices pm;
   sh::FoldedRobot robot;
   bool have_robot = false, have_sdf = false, have_problems = false;
+  // inverse-dynamics (torque) cost term, stomp_engine_set_dynamics
+  std::vector<stomp_segment> raw_segments;
+  DevBuf<unsigned char> chain;
+  DevBuf<double> torque_q, torque_tap;
+  int chain_len = 0;
+  double torque_weight = 0.0, gravity[3] = {0.0, 0.0, -9.8};
   std::vector<double> noise_stddev, noise_decay;
   uint64_t seed = 0x57012011ull;
 
@@ -331,10 +337,53 @@ CostArgs<Real> base_cost_args(Engine& e) {
   return a;
 }
 
+// torque term (weight > 1e-9 only): costs += w * sum_j |tau_j| from the joint-limit-projected rollouts k_cost just wrote
+int launch_torque(Engine& e, const double* clipped, size_t pstride, int n_rollouts, int num_problems, double* costs, size_t cstride) {
+  TorqueArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.D = e.D; a.N = e.N; a.n_rollouts = n_rollouts; a.total_rollouts = num_problems * n_rollouts; a.ns = e.chain_len;
+  a.q_problem_stride = pstride; a.q_rollout_stride = size_t(e.D) * e.N; a.cost_problem_stride = cstride;
+  a.q = clipped; a.pad_start = e.pad_start.p; a.pad_goal = e.pad_goal.p;
+  a.chain = reinterpret_cast<const DevChainLink*>(e.chain.p);
+  a.inv_time = 1.0 / e.desc.discretization;
+  a.inv_time2 = 1.0 / (e.desc.discretization * e.desc.discretization);
+  for (int k = 0; k < 3; ++k) a.g[k] = e.gravity[k];
+  a.weight = e.torque_weight;
+  a.costs = costs;
+  a.torques = e.torque_tap.n >= size_t(a.total_rollouts) * e.N * e.D ? e.torque_tap.p : nullptr;
+  const long long total = (long long)a.total_rollouts * e.N;
+  begin_launch(e);
+  k_torque<<<unsigned((total + 127) / 128), 128, 0, e.ws>>>(a);
+  return check_launch(e, "k_torque");
+}
+
+int launch_cost_only(Engine& e, const double* params, size_t pstride, int n_rollouts, int num_problems, int include_pads,
+                     double* costs, size_t cstride, int* flags, int flag_stride, int flag_offset, double* clipped,
+                     stomp_sphere_debug* debug, int* cflags);
+
 // cost plugin over rollouts stored as params[b*pstride + r*D*N], writing costs[b*cstride + r*N]
 int launch_cost(Engine& e, const double* params, size_t pstride, int n_rollouts, int num_problems, int include_pads,
                 double* costs, size_t cstride, int* flags, int flag_stride, int flag_offset, double* clipped,
                 stomp_sphere_debug* debug, int* cflags = nullptr) {
+  const bool torque = e.torque_weight > 1e-9 && e.chain_len > 0;   // the reference's test, src/stomp_optimizer.cpp:1120
+  if (torque && !clipped) {
+    const size_t need = pstride * size_t(num_problems);
+    if (e.torque_q.n < need) {
+      CUDA_TRY(cudaStreamSynchronize(e.stream));
+      CUDA_TRY(cudaStreamSynchronize(e.tail_stream));
+      CUDA_TRY(e.torque_q.alloc(need));
+    }
+    clipped = e.torque_q.p;
+  }
+  if (launch_cost_only(e, params, pstride, n_rollouts, num_problems, include_pads, costs, cstride, flags, flag_stride, flag_offset,
+                       clipped, debug, cflags))
+    return 1;
+  return torque ? launch_torque(e, clipped, pstride, n_rollouts, num_problems, costs, cstride) : 0;
+}
+
+int launch_cost_only(Engine& e, const double* params, size_t pstride, int n_rollouts, int num_problems, int include_pads,
+                     double* costs, size_t cstride, int* flags, int flag_stride, int flag_offset, double* clipped,
+                     stomp_sphere_debug* debug, int* cflags) {
   if (!e.have_robot || !e.have_sdf) return fail("set_robot and set_sdf must be called before the cost plugin runs");
   if (!e.have_problems) return fail("set_problems must be called before the cost plugin runs");
   if (e.f32) {
@@ -841,6 +890,9 @@ int stomp_engine_set_robot(void* h, const stomp_segment* segments, int32_t num_s
   if (e.robot.num_slots > kMaxSlots) return fail("kinematic tree branches too deeply for the FK kernel (frame slots)");
   e.K = num_spheres;
   e.num_nodes = int(e.robot.nodes.size());
+  e.raw_segments.assign(segments, segments + num_segments);
+  e.chain_len = 0;          // segment numbering may have changed: the dynamics have to be set again
+  e.torque_weight = 0.0;
   if (e.f32 ? upload_robot_tables<float>(e) : upload_robot_tables<double>(e)) return 1;
   std::vector<int> hl(e.D, 0);
   std::vector<double> lo(e.D, 0.0), hi(e.D, 0.0);
@@ -993,6 +1045,56 @@ int stomp_engine_set_constraints(void* h, const stomp_orientation_constraint* co
   e.constraints.assign(constraints, constraints + n);
   e.constraint_cost_weight = constraint_cost_weight;
   return e.f32 ? upload_constraints<float>(e) : upload_constraints<double>(e);
+}
+
+int stomp_engine_set_dynamics(void* h, const stomp_link_inertia* inertia, int32_t chain_root_segment, int32_t chain_tip_segment,
+                              const double gravity[3], double torque_cost_weight) {
+  ENGINE_OR_FAIL(h);
+  if (!e.have_robot) return fail("set_robot must be called before set_dynamics");
+  if (!inertia || !gravity) return fail("null argument");
+  const int S = int(e.raw_segments.size());
+  if (chain_root_segment < 0 || chain_root_segment >= S || chain_tip_segment < 0 || chain_tip_segment >= S)
+    return fail("chain segment out of range");
+  std::vector<int> path;
+  for (int s = chain_tip_segment; s != chain_root_segment; s = e.raw_segments[s].parent) {
+    if (s < 0) return fail("chain tip is not below chain root");
+    path.push_back(s);
+  }
+  if (path.empty() || int(path.size()) > kMaxChain) return fail("inverse-dynamics chain is empty or longer than kMaxChain segments");
+  std::vector<DevChainLink> links;
+  int next_joint = 0;
+  for (size_t k = path.size(); k-- > 0;) {
+    const stomp_segment& g = e.raw_segments[path[k]];
+    const stomp_link_inertia& in = inertia[path[k]];
+    DevChainLink L;
+    std::memset(&L, 0, sizeof(L));
+    L.type = g.joint_type;
+    L.group = g.joint_type == STOMP_JOINT_FIXED ? -1 : g.group_index;
+    if (g.joint_type != STOMP_JOINT_FIXED) {
+      // the reference hands the group's joint arrays to the chain solver: chain joint j must be group joint j
+      if (g.group_index != next_joint) return fail("the chain's movable joints must be the group joints in order");
+      ++next_joint;
+    }
+    for (int i = 0; i < 9; ++i) L.rot[i] = g.rot[i];
+    for (int i = 0; i < 3; ++i) { L.pos[i] = g.pos[i]; L.axis[i] = g.axis[i]; L.h[i] = in.mass * in.com[i]; }
+    L.m = in.mass;
+    // KDL::RigidBodyInertia(m, cog, Ic): rotational inertia about the frame origin = Ic + m (|c|^2 1 - c c^T)
+    const double* c = in.com;
+    const double cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+    const double full[9] = {in.inertia[0], in.inertia[3], in.inertia[4], in.inertia[3], in.inertia[1], in.inertia[5],
+                            in.inertia[4], in.inertia[5], in.inertia[2]};
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) L.I[a * 3 + b] = full[a * 3 + b] + in.mass * ((a == b ? cc : 0.0) - c[a] * c[b]);
+    links.push_back(L);
+  }
+  if (next_joint != e.D) return fail("the chain's movable joints must be the group joints in order");
+  if (join_streams(e)) return 1;
+  if (upload(e, e.chain, reinterpret_cast<const unsigned char*>(links.data()), links.size() * sizeof(DevChainLink))) return 1;
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  e.chain_len = int(links.size());
+  for (int k = 0; k < 3; ++k) e.gravity[k] = gravity[k];
+  e.torque_weight = torque_cost_weight;
+  return 0;
 }
 
 int stomp_engine_set_noise(void* h, const double* noise_stddev, const double* noise_decay) {

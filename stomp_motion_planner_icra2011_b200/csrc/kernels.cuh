@@ -991,6 +991,170 @@ __global__ void __launch_bounds__(kCostMaxThreads, 4) k_cost(CostArgs<Real> a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_torque: the inverse-dynamics term of StompOptimizer::execute (src/stomp_optimizer.cpp:1117-1142, getTorques :1034-1060):
+//   costs[t] += torque_cost_weight * sum_j |tau_j(t)|
+// One thread per (rollout, free timestep).  q = the joint-limit-projected group trajectory k_cost wrote (`clipped` tap), qd /
+// qdd = the 7-tap rules over the padded trajectory (stomp_trajectory.h:286-310), tau = KDL::ChainIdSolver_RNE restated:
+// recursive Newton-Euler in segment-tip coordinates, spatial vectors as (linear, angular) pairs like KDL::Twist / Wrench,
+// gravity entering as the base acceleration -g.  Off unless torque_cost_weight > 1e-9 (never in the shipped configurations), so
+// it is written for clarity, not speed: the per-segment state lives in local memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxChain = 24;
+struct DevChainLink {
+  int type, group;            // stomp_joint_type, group joint index (-1: fixed)
+  double rot[9], pos[3], axis[3];
+  double m, h[3], I[9];       // KDL::RigidBodyInertia in the segment frame: mass, m * cog, inertia about the frame origin
+};
+struct TorqueArgs {
+  int D, N, n_rollouts, total_rollouts, ns;
+  size_t q_problem_stride, q_rollout_stride, cost_problem_stride;   // in doubles
+  const double* q;           // joint-limit-projected rollouts, same layout as the rollout parameters
+  const double* pad_start;   // [B][D]
+  const double* pad_goal;    // [B][D]
+  const DevChainLink* chain; // [ns]
+  double inv_time, inv_time2, g[3], weight;
+  double* costs;             // [..][N], accumulated into
+  double* torques;           // optional tap [total_rollouts][N][D]
+};
+
+__device__ __forceinline__ void t_cross(const double* a, const double* b, double* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ void t_rot_t(const double* R, const double* v, double* o) {   // R^T v
+#pragma unroll
+  for (int i = 0; i < 3; ++i) o[i] = R[i] * v[0] + R[3 + i] * v[1] + R[6 + i] * v[2];
+}
+__device__ __forceinline__ void t_rot_n(const double* R, const double* v, double* o) {   // R v
+#pragma unroll
+  for (int i = 0; i < 3; ++i) o[i] = R[i * 3] * v[0] + R[i * 3 + 1] * v[1] + R[i * 3 + 2] * v[2];
+}
+// KDL::Frame::Inverse(Twist): lin' = R^T (lin - p x ang), ang' = R^T ang     (t = {lin[3], ang[3]})
+__device__ __forceinline__ void t_to_child(const double* R, const double* p, const double* t, double* o) {
+  double c[3], d[3];
+  t_cross(p, t + 3, c);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) d[i] = t[i] - c[i];
+  t_rot_t(R, d, o);
+  t_rot_t(R, t + 3, o + 3);
+}
+// KDL::RigidBodyInertia * Twist -> Wrench {force, torque}
+__device__ __forceinline__ void t_inertia(const DevChainLink& L, const double* t, double* w) {
+  double hw[3], hv[3], Iw[3];
+  t_cross(L.h, t + 3, hw);
+  t_cross(L.h, t, hv);
+  t_rot_n(L.I, t + 3, Iw);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { w[i] = L.m * t[i] - hw[i]; w[3 + i] = Iw[i] + hv[i]; }
+}
+
+__global__ void __launch_bounds__(128) k_torque(TorqueArgs a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.total_rollouts * a.N) return;
+  const int ro = int(idx / a.N), t = int(idx - (long long)ro * a.N);
+  const int b = ro / a.n_rollouts, r = ro - b * a.n_rollouts;
+  const double* q = a.q + size_t(b) * a.q_problem_stride + size_t(r) * a.q_rollout_stride;
+  const double* ps = a.pad_start + size_t(b) * a.D;
+  const double* pg = a.pad_goal + size_t(b) * a.D;
+  const double rule_v[7] = {0, 0, -2 / 6.0, -3 / 6.0, 6 / 6.0, -1 / 6.0, 0};
+  const double rule_a[7] = {0, -1 / 12.0, 16 / 12.0, -30 / 12.0, 16 / 12.0, -1 / 12.0, 0};
+
+  double XR[kMaxChain][9], Xp[kMaxChain][3], S[kMaxChain][6], f[kMaxChain][6];
+  double v[6] = {0, 0, 0, 0, 0, 0}, acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < a.ns; ++i) {
+    const DevChainLink& L = a.chain[i];
+    double q_ = 0.0, qd_ = 0.0, qdd_ = 0.0;
+    if (L.group >= 0) {
+      const double* qj = q + size_t(L.group) * a.N;
+      for (int k = -3; k <= 3; ++k) {
+        const int tt = t + k;
+        const double val = tt < 0 ? ps[L.group] : (tt >= a.N ? pg[L.group] : qj[tt]);
+        if (k == 0) q_ = val;
+        qd_ += (a.inv_time * rule_v[k + 3]) * val;
+        qdd_ += (a.inv_time2 * rule_a[k + 3]) * val;
+      }
+    }
+    // segment.pose(q): Frame(Rot(axis, q) * rot, pos) | Frame(rot, pos + q * axis) | Frame(rot, pos)
+    double unit[6] = {0, 0, 0, 0, 0, 0};
+    if (L.type == STOMP_JOINT_REVOLUTE) {
+      double sn, cs;
+      sincos(q_, &sn, &cs);
+      const double vt = 1.0 - cs, x = L.axis[0], y = L.axis[1], z = L.axis[2];
+      const double Rq[9] = {cs + vt * x * x, vt * x * y - sn * z, vt * x * z + sn * y,
+                            vt * x * y + sn * z, cs + vt * y * y, vt * y * z - sn * x,
+                            vt * x * z - sn * y, vt * y * z + sn * x, cs + vt * z * z};
+#pragma unroll
+      for (int m = 0; m < 3; ++m)
+#pragma unroll
+        for (int n = 0; n < 3; ++n) XR[i][m * 3 + n] = Rq[m * 3] * L.rot[n] + Rq[m * 3 + 1] * L.rot[3 + n] + Rq[m * 3 + 2] * L.rot[6 + n];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) { Xp[i][m] = L.pos[m]; unit[3 + m] = L.group >= 0 ? L.axis[m] : 0.0; }
+    } else {
+#pragma unroll
+      for (int m = 0; m < 9; ++m) XR[i][m] = L.rot[m];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        Xp[i][m] = L.pos[m] + (L.type == STOMP_JOINT_PRISMATIC ? q_ * L.axis[m] : 0.0);
+        unit[m] = (L.type == STOMP_JOINT_PRISMATIC && L.group >= 0) ? L.axis[m] : 0.0;
+      }
+    }
+    // S = X.M^-1 * unit twist (the segment tip sits on the joint origin, so no reference-point shift); vj = S * qd
+    t_rot_t(XR[i], unit, S[i]);
+    t_rot_t(XR[i], unit + 3, S[i] + 3);
+    double vj[6], vp[6], ap[6];
+#pragma unroll
+    for (int m = 0; m < 6; ++m) vj[m] = S[i][m] * qd_;
+    if (i == 0) {
+      const double ag[6] = {-a.g[0], -a.g[1], -a.g[2], 0, 0, 0};
+#pragma unroll
+      for (int m = 0; m < 6; ++m) vp[m] = 0.0;
+      t_to_child(XR[i], Xp[i], ag, ap);
+    } else {
+      t_to_child(XR[i], Xp[i], v, vp);
+      t_to_child(XR[i], Xp[i], acc, ap);
+    }
+#pragma unroll
+    for (int m = 0; m < 6; ++m) v[m] = vp[m] + vj[m];
+    double c1[3], c2[3], c3[3];
+    t_cross(v + 3, vj, c1);       // Twist * Twist: (ang x lin' + lin x ang', ang x ang')
+    t_cross(v, vj + 3, c2);
+    t_cross(v + 3, vj + 3, c3);
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      acc[m] = ap[m] + S[i][m] * qdd_ + c1[m] + c2[m];
+      acc[3 + m] = ap[3 + m] + S[i][3 + m] * qdd_ + c3[m];
+    }
+    double Ia[6], Iv[6], d1[3], d2[3], d3[3];
+    t_inertia(L, acc, Ia);
+    t_inertia(L, v, Iv);
+    t_cross(v + 3, Iv, d1);       // Twist * Wrench: (ang x force, ang x torque + lin x force)
+    t_cross(v + 3, Iv + 3, d2);
+    t_cross(v, Iv, d3);
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { f[i][m] = Ia[m] + d1[m]; f[i][3 + m] = Ia[3 + m] + d2[m] + d3[m]; }
+  }
+  double sum = 0.0;
+  for (int i = a.ns - 1; i >= 0; --i) {
+    const int j = a.chain[i].group;
+    if (j >= 0) {
+      double tau = 0.0;
+#pragma unroll
+      for (int m = 0; m < 6; ++m) tau += S[i][m] * f[i][m];
+      sum += fabs(tau);
+      if (a.torques) a.torques[(size_t(ro) * a.N + t) * a.D + j] = tau;
+    }
+    if (i != 0) {                 // Frame * Wrench into the parent's coordinates
+      double F[3], T[3], pF[3];
+      t_rot_n(XR[i], f[i], F);
+      t_rot_n(XR[i], f[i] + 3, T);
+      t_cross(Xp[i], F, pF);
+#pragma unroll
+      for (int m = 0; m < 3; ++m) { f[i - 1][m] += F[m]; f[i - 1][3 + m] += T[m] + pF[m]; }
+    }
+  }
+  a.costs[size_t(b) * a.cost_problem_stride + size_t(r) * a.N + t] += a.weight * sum;
+}
+
+// ---------------------------------------------------------------------------------------------
 // block-wide reverse inclusive scan over threads (warp shuffles + one shared array)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double block_suffix_scan(double v, double* swarp /* [32] */, double carry_in, double* carry_out) {

@@ -30,7 +30,7 @@ EXPORTS = [
     "stomp_engine_set_profiling", "stomp_engine_get_profile", "stomp_engine_optimize",
     "stomp_engine_build_sdf", "stomp_engine_get_sdf", "stomp_engine_inject_noise_async", "stomp_engine_last_stats",
     "stomp_engine_set_constraints", "stomp_engine_execute_constraints_satisfied",
-    "stomp_engine_request_results_async", "stomp_engine_wait_results",
+    "stomp_engine_request_results_async", "stomp_engine_wait_results", "stomp_engine_set_dynamics",
 ]
 
 
@@ -133,6 +133,13 @@ class Engine:
             arr[i].absolute_roll_tolerance, arr[i].absolute_pitch_tolerance, arr[i].absolute_yaw_tolerance = c["tolerances"]
             arr[i].weight = c.get("weight", 1.0)
         self._ck(self.L.stomp_engine_set_constraints(self.h, arr, len(constraints), C.c_double(weight)))
+
+    def set_dynamics(self, torque_cost_weight, gravity=(0.0, 0.0, -9.8)):
+        """torque term of StompOptimizer::execute over the robot's inverse-dynamics chain (Robot.inertias / Robot.chain)."""
+        rb = self.sc.robot
+        g = _f64(gravity)
+        self._ck(self.L.stomp_engine_set_dynamics(self.h, rb.c_inertias(), rb.chain[0], rb.chain[1], _dp(g),
+                                                  C.c_double(torque_cost_weight)))
 
     def execute_constraints_satisfied(self, n):
         out = np.empty((self.B, n), dtype=np.int32)

@@ -39,6 +39,8 @@ class Robot:
     spheres: list = field(default_factory=list)    # dicts: segment,radius,clearance,pos
     limits: list = field(default_factory=list)     # (has, lo, hi) per group joint
     reference_segment: int = 0
+    inertias: dict = field(default_factory=dict)   # segment -> (mass, com(3), (ixx, iyy, izz, ixy, ixz, iyz)); others massless
+    chain: tuple = ()                              # (root segment, tip segment) of the inverse-dynamics chain
 
     @property
     def num_dimensions(self):
@@ -108,6 +110,15 @@ class Robot:
             arr[i].pos[:] = s["pos"]
         return arr
 
+    def c_inertias(self):
+        """one stomp_link_inertia per segment (KDL::RigidBodyInertia of the segment in its own frame)."""
+        arr = (_abi.LinkInertia * len(self.segments))()
+        for i, (m, com, ic) in self.inertias.items():
+            arr[i].mass = m
+            arr[i].com[:] = com
+            arr[i].inertia[:] = ic
+        return arr
+
     def c_limits(self):
         arr = (_abi.JointLimit * len(self.limits))()
         for i, (has, lo, hi) in enumerate(self.limits):
@@ -152,6 +163,19 @@ def pr2_right_arm(clearance=0.07, spheres_per_link=None, sphere_radius=0.03):
         (1, -2.0, -0.1),
         (0, 0.0, 0.0),   # wrist roll: continuous
     ]
+    # link inertias for the torque term: synthetic, PR2-like magnitudes (mass, centre of mass, inertia about it); the chain is
+    # the one the reference hard-codes, torso_lift_link -> the end of the wrist (src/stomp_robot_model.cpp:181-183)
+    rb.inertias = {
+        pan: (25.8, (-0.001, -0.002, -0.27), (0.866, 0.874, 0.273, -0.061, -0.121, -0.059)),
+        lift: (2.75, (0.022, -0.027, -0.031), (0.021, 0.021, 0.0198, 0.005, 0.003, 0.006)),
+        uroll: (6.02, (0.21, 0.0007, -0.0003), (0.0154, 0.0775, 0.0762, 0.0002, -0.0012, -0.0001)),
+        elbow: (1.9, (0.01, 0.0, -0.012), (0.0035, 0.0044, 0.0042, -0.0001, -0.0001, 0.0)),
+        froll: (2.69, (0.18, -0.0003, -0.0003), (0.0146, 0.0164, 0.0146, 0.0, 0.0, 0.0)),
+        wflex: (0.61, (-0.0016, 0.0, -0.0007), (0.00065, 0.0002, 0.00064, 0.0, 0.0, 0.0)),
+        wroll: (0.68, (0.056, 0.0005, -0.001), (0.0012, 0.0012, 0.0004, 0.0, 0.0, 0.0)),
+        palm: (0.58, (0.07, 0.0, -0.002), (0.0004, 0.0006, 0.0008, 0.0, 0.0, 0.0)),
+    }
+    rb.chain = (torso, palm)
     if spheres_per_link is None:
         rb.add_link_spheres(upper, 0.10, clearance)
         rb.add_link_spheres(fore, 0.065, clearance)

@@ -46,11 +46,16 @@ def constraint_scene():
     return sc, cons, 2.0
 
 
-def iteration_case(name, cumulative, iterations, constraints=(), weight=0.0):
+TORQUE_WEIGHT = 0.02     # the shipped configurations use 0 (term off); this switches StompOptimizer::getTorques on
+
+
+def iteration_case(name, cumulative, iterations, constraints=(), weight=0.0, torque=0.0):
     sc = scenario(name, cumulative)
     D, N, R = sc.robot.num_dimensions, sc.num_time_steps, sc.num_rollouts
     ref = rp.ReferenceOptimizer(sc, 0, constraints=constraints, constraint_cost_weight=weight)
     assert ref.movement_duration == sc.movement_duration
+    if torque:
+        ref.set_dynamics(torque)
     ref.begin()
     out = {"movement_duration": np.array(ref.movement_duration), "theta0": ref.get("theta"),
            "parameters_all0": ref.get("parameters_all"), "movement_dt": ref.get("movement_dt")}
@@ -88,13 +93,15 @@ def iteration_case(name, cumulative, iterations, constraints=(), weight=0.0):
     return out
 
 
-def cost_plugin_case(name, rollouts, seed, constraints=(), weight=0.0, robot=None, start=None, goal=None):
+def cost_plugin_case(name, rollouts, seed, constraints=(), weight=0.0, robot=None, start=None, goal=None, torque=0.0):
     """StompOptimizer::execute on noisy rollouts around the min-control-cost trajectory + its per-sphere internals."""
     sc = scenario(name)
     if robot is not None:
         sc.robot, sc.start, sc.goal = robot, start, goal
     D, N = sc.robot.num_dimensions, sc.num_time_steps
     ref = rp.ReferenceOptimizer(sc, 0, constraints=constraints, constraint_cost_weight=weight)
+    if torque:
+        ref.set_dynamics(torque)
     ref.begin()
     L, theta = ref.get("covariance_cholesky"), ref.get("theta")
     rng = np.random.default_rng(seed)
@@ -171,6 +178,8 @@ def main():
     save("ref_cost_tiny_constraints", cost_plugin_case("tiny", 3, 23, cons, w))
     for seed in (0, 1, 2):
         save("ref_cost_tree%d" % seed, random_tree_case(seed))
+    save("ref_cost_tiny_torque", cost_plugin_case("tiny", 3, 24, torque=TORQUE_WEIGHT))
+    save("ref_iter_tiny_torque", iteration_case("tiny", 1, 3, torque=TORQUE_WEIGHT))
     save("ref_optimize_tiny_s8", optimize_case("tiny", 8, 60, 5))     # collision free at iteration 28, early exit after 33
     save("ref_optimize_tiny_s7", optimize_case("tiny", 7, 20, 6))     # never collision free: runs to max_iterations
     save("ref_optimize_c1_s8", optimize_case("C1", 8, 40, 5))        # collision free from the first iteration

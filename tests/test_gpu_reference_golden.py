@@ -110,6 +110,29 @@ def test_engine_cost_plugin_with_orientation_constraints_matches_the_compiled_re
     _check_cost_plugin(sc, g, eng, constraints=True)
 
 
+def test_engine_torque_term_matches_the_compiled_get_torques():
+    from tests.golden.make_ref_golden import TORQUE_WEIGHT
+    g = rg.load("ref_cost_tiny_torque")
+    sc = rg.scenario("tiny", g)
+    eng = _engine(sc)
+    eng.set_dynamics(TORQUE_WEIGHT)
+    _check_cost_plugin(sc, g, eng)
+    plain = _engine(sc).execute(g["parameters"][None], 2)[0][0]
+    assert (g["costs"][:, 1] - plain).min() > 1e-3, "fixture's torque term is not active"
+    gi = rg.load("ref_iter_tiny_torque")
+    sc2 = rg.scenario("tiny", gi)
+    eng2 = _engine(sc2, keep_intermediates=1)
+    eng2.set_dynamics(TORQUE_WEIGHT)
+    assert len(list(_check_iterations(sc2, gi, eng2))) == 3
+    eng3 = _engine(sc2)                                    # without the parity taps the engine keeps its own projected copy
+    eng3.set_dynamics(TORQUE_WEIGHT)
+    for it in rg.iterations(gi):
+        eng3.inject_noise(gi["it%d_noise" % it][None])
+        cost, _, _ = eng3.iterate(it)
+        assert_close(cost[0], float(gi["it%d_noiseless_cost" % it]), RTOL_F64, "noise-less cost with the torque term")
+        assert_close(eng3.get(_abi.FIELD_THETA)[0], gi["it%d_theta" % it], RTOL_F64, "theta")
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_engine_forward_kinematics_of_random_trees_matches_the_compiled_solvers(seed):
     g = rg.load("ref_cost_tree%d" % seed)

@@ -123,6 +123,22 @@ def test_cost_plugin_matches_the_compiled_stomp_optimizer(name):
     assert np.abs(g["clipped"] - g["parameters"]).max() > 1e-3, "fixture exercises no joint limit"
 
 
+def test_torque_term_matches_the_compiled_get_torques():
+    """StompOptimizer::getTorques + the sum of |tau_j| (the RNE solver itself is third-party on both sides: tests/test_torque_cpu.py)."""
+    from tests.golden.make_ref_golden import TORQUE_WEIGHT
+    g, plain = rg.load("ref_cost_tiny_torque"), None
+    sc = rg.scenario("tiny", g)
+    o = oracle.Oracle(sc, 0)
+    o.set_dynamics(TORQUE_WEIGHT)
+    _check_cost_plugin(sc, g, o)
+    plain = oracle.Oracle(sc, 0).execute(g["parameters"][0], 2)[0][0]
+    assert (g["costs"][0, 1] - plain).min() > 1e-3, "fixture's torque term is not active"
+    gi = rg.load("ref_iter_tiny_torque")
+    o2 = oracle.Oracle(rg.scenario("tiny", gi), 0)
+    o2.set_dynamics(TORQUE_WEIGHT)
+    assert len(list(_check_iterations(sc, gi, o2))) == 3
+
+
 def test_cost_plugin_with_orientation_constraints_matches_the_compiled_reference():
     g = rg.load("ref_cost_tiny_constraints")
     sc, cons, w = rg.constraint_scene(g)
