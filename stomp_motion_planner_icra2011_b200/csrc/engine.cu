@@ -270,6 +270,8 @@ GenArgs base_gen_args(Engine& e) {
 template <typename Real, bool kDebug, int kVox, bool kCons>
 int launch_cost_c(Engine& e, CostArgs<Real>& a, int num_problems) {
   a.total_rollouts = num_problems * a.n_rollouts;
+  a.params_16B = ((e.D * e.N) % 2 == 0) && (reinterpret_cast<uintptr_t>(a.params) % 16 == 0) && (a.params_problem_stride % 2 == 0) &&
+                 (a.params_rollout_stride % 2 == 0);
   // lane packing: concatenate the timelines of `pack` rollouts per CTA when that needs fewer 29-step warp tiles per rollout
   const int seg = e.N + 3;
   auto tiles_for = [&](int p) { return (p * seg - 3 + kTileSteps - 1) / kTileSteps; };

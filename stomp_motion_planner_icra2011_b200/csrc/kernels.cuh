@@ -22,6 +22,12 @@
 #include "../../include/stomp_b200.h"
 
 // build-time tuning knobs (A/B tested on B200, see profiles/README.md)
+#ifndef STOMP_COST_PARAMS_CG
+#define STOMP_COST_PARAMS_CG 1     // k_cost: stage rollouts with 16-byte cp.async.cg (L1 bypass) instead of 8-byte .ca (A/B: 0.336 -> 0.332 ms)
+#endif
+#ifndef STOMP_COST_VOX_EVICT_LAST
+#define STOMP_COST_VOX_EVICT_LAST 0   // k_cost: L1 evict_last hint on the voxel gathers (A/B: no effect)
+#endif
 #ifndef STOMP_GEN_MIN_BLOCKS
 #define STOMP_GEN_MIN_BLOCKS 4     // k_generate: resident CTAs per SM targeted by the register allocation
 #endif
@@ -565,6 +571,7 @@ struct CostArgs {
   int* collision_free;       // [..]
   double* clipped;           // optional tap [same layout as params]
   stomp_sphere_debug* debug; // optional tap [N+3][K] (rollout 0 of problem 0)
+  int params_16B;            // rollout rows are 16-byte aligned and D*N is even: staged with 16-byte copies
 };
 
 template <typename Real> struct Math;
@@ -729,8 +736,15 @@ __device__ __forceinline__ bool voxel_cells(const GridF& g, float px, float py, 
 // distance of one voxel: PropagationDistanceField::getDistance = sqrt_table[d^2] (u8 / u16 grids) or metres (f32)
 template <typename Real, int kVox>
 __device__ __forceinline__ Real voxel_distance(const void* vox, int idx, unsigned sqrt_tab_addr, Real res) {
-  if (kVox == STOMP_VOXEL_U8_SQ)
+  if (kVox == STOMP_VOXEL_U8_SQ) {
+#if STOMP_COST_VOX_EVICT_LAST
+    unsigned v;
+    asm volatile("ld.global.nc.L1::evict_last.u8 %0, [%1];" : "=r"(v) : "l"(static_cast<const uint8_t*>(vox) + idx));
+    return lds1(sqrt_tab_addr + v * unsigned(sizeof(Real)), Real(0));
+#else
     return lds1(sqrt_tab_addr + unsigned(__ldg(static_cast<const uint8_t*>(vox) + idx)) * unsigned(sizeof(Real)), Real(0));
+#endif
+  }
   if (kVox == STOMP_VOXEL_U16_SQ) return Math<Real>::sqrt_(Real(__ldg(static_cast<const uint16_t*>(vox) + idx))) * res;
   return Real(__ldg(static_cast<const float*>(vox) + idx));
 }
@@ -790,6 +804,19 @@ __global__ void __launch_bounds__(kCostMaxThreads, 4) k_cost(CostArgs<Real> a) {
   for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
     const int first = job * P, count = min(P, a.total_rollouts - first);
     __syncthreads();   // previous job fully consumed
+#if STOMP_COST_PARAMS_CG
+    // the rollout rows are a once-read stream: 16-byte copies that bypass L1 (.cg) leave it to the voxel gathers
+    if (a.params_16B) {
+      const int DN2 = DN >> 1;
+      for (int i = threadIdx.x; i < count * DN2; i += blockDim.x) {
+        const int p = i / DN2, k = i - p * DN2, ro = first + p;
+        const int b = ro / a.n_rollouts, r = ro - b * a.n_rollouts;
+        const double* src = a.params + size_t(b) * a.params_problem_stride + size_t(r) * a.params_rollout_stride;
+        const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(q + size_t(p) * DN + 2 * k));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + 2 * k) : "memory");
+      }
+    } else
+#endif
     for (int i = threadIdx.x; i < count * DN; i += blockDim.x) {
       const int p = i / DN, k = i - p * DN, ro = first + p;
       const int b = ro / a.n_rollouts, r = ro - b * a.n_rollouts;
