@@ -164,7 +164,7 @@ def compiled_reference_rate(name, iters=15):
         ref.close()
         return {"value": iters * evals_per_iteration(sc, 1, False) / t, "unit": UNIT, "cores": 1, "kind": "reference",
                 "ms_per_iteration_per_problem": 1e3 * t / iters,
-                "sample": "1 %s problem, %d iterations after 1 warm-up; 11 of the reference's 14 .cpp files compiled unmodified "
+                "sample": "1 %s problem, %d iterations after 1 warm-up; 13 of the reference's 14 .cpp files compiled unmodified "
                           "against oracle/ref_shim (eager stand-in for Eigen 2: slower than the port, hence not the baseline)"
                           % (name, iters)}
     except Exception as e:   # the library is optional evidence, never a reason to fail the bench

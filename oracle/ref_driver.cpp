@@ -42,6 +42,7 @@
 #include <stomp_motion_planner/stomp_collision_space.h>
 #include <stomp_motion_planner/stomp_parameters.h>
 #include <stomp_motion_planner/STOMPStatistics.h>
+#include <planning_environment/monitors/collision_space_monitor.h>
 #undef private
 #undef protected
 
@@ -233,6 +234,7 @@ int stomp_ref_get(void* p, const char* field, double* out) {
 int stomp_ref_quad_cost_inv(int num_vars_all, double discretization, const double* smoothness_costs /*[3]*/,
                             double ridge, int n_joints, const double* joint_cost, double* out) {
   StompRobotModel model;
+  model.fk_solver_ = NULL;
   model.num_kdl_joints_ = 1;
   StompTrajectory traj(&model, num_vars_all, discretization);
   std::vector<StompCost> costs;
@@ -258,22 +260,14 @@ int stomp_ref_quad_cost_inv(int num_vars_all, double discretization, const doubl
 /* =====================================================================================================
  * The cost-plugin half: the reference's StompOptimizer (src/stomp_optimizer.cpp, all 1213 lines), StompTrajectory,
  * StompCollisionPoint, both TreeFkSolverJointPosAxis solvers, OrientationConstraintEvaluator and StompParameters,
- * compiled unmodified.  Not compiled: src/stomp_robot_model.cpp (URDF / planning_environment ingestion) and
- * src/stomp_collision_space.cpp (scene rasterisation) — their OUTPUTS are what the engine's tables replace
- * (include/stomp_b200.h: stomp_segment / stomp_sphere / stomp_joint_limit, the voxel grid), so the driver fills the
- * reference's own data structures (KDL::Tree, StompPlanningGroup, StompCollisionPoint list, distance field) from
- * those same tables, the way StompRobotModel::init (src/stomp_robot_model.cpp:95-190) and
- * StompCollisionSpace::init (src/stomp_collision_space.cpp:61-84) would from a URDF and a parameter server.
+ * compiled unmodified.  src/stomp_robot_model.cpp and src/stomp_collision_space.cpp are compiled too, but their init()
+ * functions need a URDF, a parameter server and a live planning_environment monitor; what they PRODUCE is exactly what the
+ * engine's tables replace (include/stomp_b200.h: stomp_segment / stomp_sphere / stomp_joint_limit, the voxel grid), so the
+ * driver fills the reference's own data structures (KDL::Tree, StompPlanningGroup, StompCollisionPoint list, distance field)
+ * from those same tables, the way StompRobotModel::init (src/stomp_robot_model.cpp:95-190) and StompCollisionSpace::init
+ * (src/stomp_collision_space.cpp:61-84) would.  The two generators that do run from those files are at the end of this file:
+ * collision-point generation and collision-object rasterisation.
  * ===================================================================================================== */
-namespace stomp_motion_planner {
-/* constructors / destructors of the two classes whose .cpp files are not compiled */
-StompRobotModel::StompRobotModel() : monitor_(NULL), num_kdl_joints_(0), fk_solver_(NULL), max_radius_clearance_(0.0) {}
-StompRobotModel::~StompRobotModel() {}
-StompCollisionSpace::StompCollisionSpace()
-    : distance_field_(NULL), max_expansion_(0.0), resolution_(0.0), field_bias_x_(0.0), field_bias_y_(0.0),
-      field_bias_z_(0.0), monitor_(NULL), collision_models_(NULL) {}
-StompCollisionSpace::~StompCollisionSpace() {}
-}  // namespace stomp_motion_planner
 
 namespace {
 
@@ -322,6 +316,7 @@ struct RefOpt {
     opt.reset();
     delete loop;
     delete full;
+    space.distance_field_ = NULL;   /* ~StompCollisionSpace deletes its field; this one is ours */
     delete df;
     delete model.fk_solver_;
   }
@@ -347,6 +342,9 @@ void* stomp_ref_opt_create(const stomp_engine_desc* desc, const stomp_segment* s
 
   /* ---- KDL tree from the segment table (kdl_parser: Joint(name, origin, axis, type), Segment(name, joint, f_tip)) */
   StompRobotModel& m = h->model;
+  m.fk_solver_ = NULL;
+  m.num_kdl_joints_ = 0;
+  m.max_radius_clearance_ = 0.0;
   m.kdl_tree_ = KDL::Tree(seg_name(0));
   for (int i = 1; i < num_segments; ++i) {
     const stomp_segment& g = segs[i];
@@ -447,6 +445,7 @@ void* stomp_ref_opt_create(const stomp_engine_desc* desc, const stomp_segment* s
   h->voxels.assign(static_cast<const uint8_t*>(voxels), static_cast<const uint8_t*>(voxels) + size_t(nx) * ny * nz * vb);
   h->df = new distance_field::PropagationDistanceField(h->voxels.data(), nx, ny, nz, origin, resolution, voxel_dtype);
   h->space.distance_field_ = h->df;
+  h->space.field_bias_x_ = h->space.field_bias_y_ = h->space.field_bias_z_ = 0.0;   /* collision_space/field_bias_* default */
   h->space.resolution_ = resolution;
   h->space.reference_frame_ = m.reference_frame_;
 
@@ -672,6 +671,146 @@ int stomp_ref_opt_optimize(void* p, double* stats, double* costs) {
   stats[5] = h->opt->last_improvement_iteration_;
   for (size_t i = 0; i < s->costs.size(); ++i) costs[i] = s->costs[i];
   return 0;
+}
+
+} /* extern "C" */
+
+/* =====================================================================================================
+ * Generators from src/stomp_robot_model.cpp and src/stomp_collision_space.cpp, run unmodified on a mock
+ * planning_environment (oracle/ref_shim/planning_environment/...): they produce the tables the engine consumes.
+ * ===================================================================================================== */
+extern "C" {
+
+/* StompRobotModel::generateLinkCollisionPoints + generateAttachedObjectCollisionPoints + populatePlanningGroupCollisionPoints
+ * (src/stomp_robot_model.cpp:352-496, 265-346).  links: the collision-checking links in getGroupLinkUnion() order with their
+ * collision_links/<link>/{link_radius, link_clearance, link_extension} parameters (radius < 0: no link_radius parameter).
+ * attached objects: owner segment, shape (0 sphere r | 1 box x y z | 2 cylinder r length), centre in the owner link's frame.
+ * Writes the planning group's collision points (segment = table index) and returns their number. */
+int stomp_ref_collision_points(const stomp_segment* segs, int32_t num_segments, int32_t reference_segment, int32_t D,
+                               const int32_t* link_segment, const double* link_radius, const double* link_clearance,
+                               const double* link_extension, int32_t num_links, double default_clearance,
+                               const int32_t* att_segment, const int32_t* att_shape, const double* att_dims,
+                               const double* att_position, int32_t num_attached, double attached_padding,
+                               stomp_sphere* out, int32_t max_out) {
+  StompRobotModel m;
+  planning_environment::CollisionSpaceMonitor monitor;
+  m.monitor_ = &monitor;
+  m.kdl_tree_ = KDL::Tree(seg_name(0));
+  for (int i = 1; i < num_segments; ++i) {
+    const stomp_segment& g = segs[i];
+    KDL::Vector pos(g.pos[0], g.pos[1], g.pos[2]), axis(g.axis[0], g.axis[1], g.axis[2]);
+    KDL::Rotation rot(g.rot[0], g.rot[1], g.rot[2], g.rot[3], g.rot[4], g.rot[5], g.rot[6], g.rot[7], g.rot[8]);
+    KDL::Joint joint = g.joint_type == STOMP_JOINT_REVOLUTE    ? KDL::Joint("j" + seg_name(i), pos, axis, KDL::Joint::RotAxis)
+                       : g.joint_type == STOMP_JOINT_PRISMATIC ? KDL::Joint("j" + seg_name(i), pos, axis, KDL::Joint::TransAxis)
+                                                               : KDL::Joint("j" + seg_name(i), KDL::Joint::None);
+    if (!m.kdl_tree_.addSegment(KDL::Segment(seg_name(i), joint, KDL::Frame(rot, pos)), seg_name(g.parent))) return -1;
+  }
+  m.num_kdl_joints_ = m.kdl_tree_.getNrOfJoints();
+  m.reference_frame_ = seg_name(reference_segment);
+  m.fk_solver_ = new KDL::TreeFkSolverJointPosAxis(m.kdl_tree_, m.reference_frame_);
+  m.collision_clearance_default_ = default_clearance;
+  m.max_radius_clearance_ = 0.0;
+  StompRobotModel::StompPlanningGroup group;
+  group.name_ = "group";
+  group.num_joints_ = D;
+  group.stomp_joints_.resize(D);
+  for (int i = 1; i < num_segments; ++i)
+    if (segs[i].group_index >= 0) {
+      group.stomp_joints_[segs[i].group_index].kdl_joint_index_ = m.kdl_tree_.getSegment(seg_name(i))->second.q_nr;
+      group.stomp_joints_[segs[i].group_index].stomp_joint_index_ = segs[i].group_index;
+    }
+  m.planning_groups_.insert(std::make_pair(group.name_, group));
+
+  ros::NodeHandle nh("~");
+  std::vector<planning_models::KinematicModel::Link> owners(num_attached);
+  std::vector<planning_models::KinematicModel::AttachedBody> bodies(num_attached);
+  std::vector<shapes::Shape*> shapes;
+  for (int i = 0; i < num_links; ++i) {
+    const std::string name = seg_name(link_segment[i]);
+    monitor.models.group_link_union.push_back(name);
+    if (link_radius[i] >= 0.0) {
+      nh.set("collision_links/" + name + "/link_radius", XmlRpc::XmlRpcValue(link_radius[i]));
+      if (link_clearance[i] >= 0.0) nh.set("collision_links/" + name + "/link_clearance", XmlRpc::XmlRpcValue(link_clearance[i]));
+      nh.set("collision_links/" + name + "/link_extension", XmlRpc::XmlRpcValue(link_extension[i]));
+    }
+  }
+  m.generateLinkCollisionPoints();
+
+  monitor.env.attached_padding = attached_padding;
+  for (int i = 0; i < num_attached; ++i) {
+    const double* d = att_dims + 3 * i;
+    shapes::Shape* sh = att_shape[i] == 0   ? static_cast<shapes::Shape*>(new shapes::Sphere(d[0]))
+                        : att_shape[i] == 1 ? static_cast<shapes::Shape*>(new shapes::Box(d[0], d[1], d[2]))
+                                            : static_cast<shapes::Shape*>(new shapes::Cylinder(d[0], d[1]));
+    shapes.push_back(sh);
+    owners[i].name = seg_name(att_segment[i]);
+    bodies[i].owner = &owners[i];
+    bodies[i].shapes.push_back(sh);
+    btTransform pose(btQuaternion(0, 0, 0, 1), btVector3(att_position[3 * i], att_position[3 * i + 1], att_position[3 * i + 2]));
+    bodies[i].globalTrans.push_back(pose);   /* the mock tf listener is the identity: poses are given in the owner's frame */
+    monitor.env.attached.push_back(&bodies[i]);
+  }
+  motion_planning_msgs::RobotState robot_state;
+  m.generateAttachedObjectCollisionPoints(&robot_state);
+  m.populatePlanningGroupCollisionPoints();
+
+  const std::vector<StompCollisionPoint>& pts = m.getPlanningGroup("group")->collision_points_;
+  std::map<int, int> number_to_table;
+  for (int i = 0; i < num_segments; ++i) number_to_table[m.fk_solver_->segmentNameToIndex(seg_name(i))] = i;
+  int n = 0;
+  for (size_t i = 0; i < pts.size() && n < max_out; ++i, ++n) {
+    out[n].segment = number_to_table[pts[i].getSegmentNumber()];
+    out[n].radius = pts[i].getRadius();
+    out[n].clearance = pts[i].getClearance();
+    for (int k = 0; k < 3; ++k) out[n].pos[k] = pts[i].getPosition()(k);
+  }
+  for (size_t i = 0; i < shapes.size(); ++i) delete shapes[i];
+  for (int i = 0; i < num_links; ++i) {   /* leave the shared parameter server clean for the next call */
+    const std::string name = seg_name(link_segment[i]);
+    nh.erase("collision_links/" + name + "/link_radius");
+    nh.erase("collision_links/" + name + "/link_clearance");
+    nh.erase("collision_links/" + name + "/link_extension");
+  }
+  delete m.fk_solver_;
+  return int(pts.size());
+}
+
+/* StompCollisionSpace::addCollisionObjectsToPoints (src/stomp_collision_space.cpp:198-297) for boxes and cylinders, then the
+ * distance field's addPointsToField binning: occupancy[nx][ny][nz] (nx = int(size / resolution)) of the cells the lattice
+ * points fall into; returns the number of points generated (including those outside the grid). */
+long long stomp_ref_collision_object_cells(const double* size, const double* origin, double resolution, const stomp_box* boxes,
+                                           int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders,
+                                           uint8_t* occupancy, int32_t* dims) {
+  StompCollisionSpace space;
+  planning_environment::CollisionSpaceMonitor monitor;
+  space.monitor_ = &monitor;
+  space.resolution_ = resolution;
+  distance_field::PropagationDistanceField df(size[0], size[1], size[2], resolution, origin[0], origin[1], origin[2], 0.0);
+  space.distance_field_ = &df;
+  collision_space::EnvironmentObjects::NamespaceObjects& no = monitor.env.env_objects.objects["objects"];
+  std::vector<shapes::Shape*> shapes;
+  for (int i = 0; i < num_boxes; ++i) {
+    const stomp_box& b = boxes[i];
+    shapes.push_back(new shapes::Box(b.dimensions[0], b.dimensions[1], b.dimensions[2]));
+    no.shape.push_back(shapes.back());
+    no.shapePose.push_back(btTransform(btQuaternion(b.orientation[0], b.orientation[1], b.orientation[2], b.orientation[3]),
+                                       btVector3(b.position[0], b.position[1], b.position[2])));
+  }
+  for (int i = 0; i < num_cylinders; ++i) {
+    const stomp_cylinder& c = cylinders[i];
+    shapes.push_back(new shapes::Cylinder(c.radius, c.height));
+    no.shape.push_back(shapes.back());
+    no.shapePose.push_back(btTransform(btQuaternion(c.orientation[0], c.orientation[1], c.orientation[2], c.orientation[3]),
+                                       btVector3(c.position[0], c.position[1], c.position[2])));
+  }
+  std::vector<btVector3> points;
+  space.addCollisionObjectsToPoints(points);
+  df.addPointsToField(points);
+  for (int a = 0; a < 3; ++a) dims[a] = df.dim(a);
+  if (occupancy) std::copy(df.occupied().begin(), df.occupied().end(), occupancy);
+  for (size_t i = 0; i < shapes.size(); ++i) delete shapes[i];
+  space.distance_field_ = NULL;
+  return (long long)points.size();
 }
 
 } /* extern "C" */

@@ -12,6 +12,9 @@ class btVector3 {
   double x() const { return v_[0]; }
   double y() const { return v_[1]; }
   double z() const { return v_[2]; }
+  void setX(double v) { v_[0] = v; }
+  void setY(double v) { v_[1] = v; }
+  void setZ(double v) { v_[2] = v; }
  private:
   double v_[3];
 };
@@ -73,5 +76,17 @@ class btMatrix3x3 {
   void getRPY(double& roll, double& pitch, double& yaw) const { getEulerYPR(yaw, pitch, roll); }
  private:
   double m_[9];
+};
+class btTransform {
+ public:
+  btTransform() {}
+  btTransform(const btQuaternion& q, const btVector3& o) : q_(q), o_(o) {}
+  const btVector3& getOrigin() const { return o_; }
+  const btQuaternion& getRotation() const { return q_; }
+  void setOrigin(const btVector3& o) { o_ = o; }
+  void setRotation(const btQuaternion& q) { q_ = q; }
+ private:
+  btQuaternion q_;
+  btVector3 o_;
 };
 #endif

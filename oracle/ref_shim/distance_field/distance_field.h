@@ -8,6 +8,8 @@
 #define STOMP_REF_SHIM_DISTANCE_FIELD
 #include <cmath>
 #include <cstdint>
+#include <vector>
+#include <LinearMath/bullet_shim.h>
 namespace distance_field {
 class PropagationDistanceField {
  public:
@@ -16,6 +18,29 @@ class PropagationDistanceField {
       : vox_(voxels), nx_(nx), ny_(ny), nz_(nz), res_(resolution), type_(voxel_type) {
     for (int i = 0; i < 3; ++i) origin_[i] = origin[i];
   }
+  // the constructor StompCollisionSpace::init uses (src/stomp_collision_space.cpp:83): an empty field of
+  // int(size / resolution) cells per axis.  Only the OCCUPANCY side of the field is restated for this form (which cells
+  // addPointsToField marks); the distance propagation itself is third-party and is not run by the harness.
+  PropagationDistanceField(double size_x, double size_y, double size_z, double resolution, double origin_x, double origin_y,
+                           double origin_z, double max_distance)
+      : vox_(0), nx_(int(size_x / resolution)), ny_(int(size_y / resolution)), nz_(int(size_z / resolution)), res_(resolution),
+        type_(U8_SQ), max_distance_(max_distance) {
+    origin_[0] = origin_x; origin_[1] = origin_y; origin_[2] = origin_z;
+    reset();
+  }
+  void reset() { occupied_.assign(size_t(nx_) * ny_ * nz_, 0); points_.clear(); }
+  void addPointsToField(const std::vector<btVector3>& points) {
+    for (size_t i = 0; i < points.size(); ++i) {
+      points_.push_back(points[i]);
+      int x = getCellFromLocation(0, points[i].x()), y = getCellFromLocation(1, points[i].y()), z = getCellFromLocation(2, points[i].z());
+      if (x < 0 || y < 0 || z < 0 || x >= nx_ || y >= ny_ || z >= nz_) continue;   // VoxelGrid::isCellValid
+      occupied_[(size_t(x) * ny_ + y) * nz_ + z] = 1;
+    }
+  }
+  template <typename A, typename B> void visualize(double, double, const A&, const B&) const {}
+  const std::vector<uint8_t>& occupied() const { return occupied_; }
+  const std::vector<btVector3>& points() const { return points_; }
+  int dim(int a) const { return a == 0 ? nx_ : (a == 1 ? ny_ : nz_); }
   int getCellFromLocation(int dim, double loc) const { return int(round((loc - origin_[dim]) / res_)); }
   double getDistanceFromCell(int x, int y, int z) const {
     size_t i = (size_t(x) * ny_ + y) * nz_ + z;
@@ -44,6 +69,9 @@ class PropagationDistanceField {
   int nx_, ny_, nz_;
   double origin_[3], res_;
   int type_;
+  double max_distance_ = 0.0;
+  std::vector<uint8_t> occupied_;
+  std::vector<btVector3> points_;
 };
 }
 #endif

@@ -43,6 +43,9 @@ class XmlRpcValue {
   Type getType() const { return type_; }
   int size() const { return int(a_.size()); }
   XmlRpcValue& operator[](int i) { return a_[size_t(i)]; }
+  XmlRpcValue& operator[](const char* k) { return m_[k]; }
+  XmlRpcValue& operator[](const std::string& k) { return m_[k]; }
+  bool hasMember(const std::string& k) const { return m_.count(k) != 0; }
   operator int&() { return i_; }
   operator double&() { return d_; }
   operator std::string&() { return s_; }
@@ -56,6 +59,7 @@ class XmlRpcValue {
   double d_;
   std::string s_;
   std::vector<XmlRpcValue> a_;
+  std::map<std::string, XmlRpcValue> m_;
 };
 }  // namespace XmlRpc
 
@@ -77,6 +81,7 @@ class NodeHandle {
 
   // test-side population
   void set(const std::string& k, const XmlRpc::XmlRpcValue& v) { (*params_)[k] = v; }
+  void erase(const std::string& k) { params_->erase(k); }
 
   bool getParam(const std::string& k, XmlRpc::XmlRpcValue& v) const {
     Params::const_iterator it = params_->find(k);

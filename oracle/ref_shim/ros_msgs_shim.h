@@ -18,6 +18,15 @@ struct Point { double x, y, z; Point() : x(0), y(0), z(0) {} };
 struct Vector3 { double x, y, z; Vector3() : x(0), y(0), z(0) {} };
 struct Quaternion { double x, y, z, w; Quaternion() : x(0), y(0), z(0), w(1) {} };
 struct Pose { Point position; Quaternion orientation; };
+struct PoseStamped { std_msgs::Header header; Pose pose; };
+}
+namespace geometric_shapes_msgs {
+struct Shape {
+  enum { SPHERE = 0, BOX = 1, CYLINDER = 2, MESH = 3 };
+  int8_t type;
+  std::vector<double> dimensions;
+  Shape() : type(0) {}
+};
 }
 namespace visualization_msgs {
 struct Marker {
@@ -62,6 +71,7 @@ struct Constraints {
 }
 namespace mapping_msgs {
 struct CollisionMap {};
+struct CollisionObjectOperation { enum { ADD = 0, REMOVE = 1 }; int8_t operation; };
 struct CollisionObject {};
 struct AttachedCollisionObject {};
 typedef boost::shared_ptr<const CollisionMap> CollisionMapConstPtr;

@@ -272,3 +272,58 @@ class ReferenceOptimizer:
         return dict(success=bool(stats[0]), success_iteration=int(stats[1]), collision_success_iteration=int(stats[2]),
                     best_cost=float(stats[3]), iterations=n, last_improvement_iteration=int(stats[5]), costs=costs[:n].copy(),
                     best_trajectory=self.get("best_group_trajectory"))
+
+
+def collision_points(robot, links, default_clearance=0.07, attached=(), attached_padding=0.0):
+    """StompRobotModel::generateLinkCollisionPoints + generateAttachedObjectCollisionPoints + populatePlanningGroupCollisionPoints
+    on the robot's segment table.  links: [(segment, radius, clearance | None, extension)] in getGroupLinkUnion() order;
+    attached: [(segment, 'sphere' | 'box' | 'cylinder', dims, position in the link frame)].
+    Returns [(segment, radius, clearance, (x, y, z))] = the planning group's collision points in the reference's order."""
+    from stomp_motion_planner_icra2011_b200 import _abi
+    L = lib()
+    n = len(links)
+    seg = np.array([l[0] for l in links], dtype=np.int32)
+    rad = np.array([l[1] for l in links], dtype=np.float64)
+    clr = np.array([-1.0 if l[2] is None else l[2] for l in links], dtype=np.float64)
+    ext = np.array([l[3] for l in links], dtype=np.float64)
+    shape_id = {"sphere": 0, "box": 1, "cylinder": 2}
+    aseg = np.array([a[0] for a in attached] + [0], dtype=np.int32)
+    ash = np.array([shape_id[a[1]] for a in attached] + [0], dtype=np.int32)
+    adims = np.zeros((len(attached) + 1, 3))
+    apos = np.zeros((len(attached) + 1, 3))
+    for i, a in enumerate(attached):
+        adims[i, :len(a[2])] = a[2]
+        apos[i] = a[3]
+    out = (_abi.Sphere * 4096)()
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))  # noqa: E731
+    L.stomp_ref_collision_points.restype = C.c_int
+    cnt = L.stomp_ref_collision_points(robot.c_segments(), len(robot.segments), robot.reference_segment, robot.num_dimensions,
+                                       ip(seg), _dp(rad), _dp(clr), _dp(ext), n, C.c_double(default_clearance), ip(aseg), ip(ash),
+                                       _dp(adims), _dp(apos), len(attached), C.c_double(attached_padding), out, 4096)
+    if cnt < 0 or cnt > 4096:
+        raise RuntimeError("stomp_ref_collision_points failed (%d)" % cnt)
+    return [(out[i].segment, out[i].radius, out[i].clearance, tuple(out[i].pos)) for i in range(cnt)]
+
+
+def collision_object_cells(size, origin, resolution, boxes=(), cylinders=()):
+    """StompCollisionSpace::addCollisionObjectsToPoints + the distance field's cell binning -> (occupancy[nx][ny][nz] bool,
+    number of lattice points generated).  boxes: [(position, quaternion xyzw, dimensions)], cylinders: [(position, quaternion,
+    radius, height)]."""
+    from stomp_motion_planner_icra2011_b200 import _abi
+    L = lib()
+    barr = (_abi.Box * max(1, len(boxes)))()
+    for i, (p, q, d) in enumerate(boxes):
+        barr[i].position[:], barr[i].orientation[:], barr[i].dimensions[:] = p, q, d
+    carr = (_abi.Cylinder * max(1, len(cylinders)))()
+    for i, (p, q, r, h) in enumerate(cylinders):
+        carr[i].position[:], carr[i].orientation[:] = p, q
+        carr[i].radius, carr[i].height = r, h
+    sz, org = np.ascontiguousarray(size, dtype=np.float64), np.ascontiguousarray(origin, dtype=np.float64)
+    n = [int(size[i] / resolution) for i in range(3)]
+    occ = np.zeros(n, dtype=np.uint8)
+    dims = (C.c_int32 * 3)()
+    L.stomp_ref_collision_object_cells.restype = C.c_longlong
+    cnt = L.stomp_ref_collision_object_cells(_dp(sz), _dp(org), C.c_double(resolution), barr, len(boxes), carr, len(cylinders),
+                                             occ.ctypes.data_as(C.POINTER(C.c_uint8)), dims)
+    assert list(dims) == n, (list(dims), n)
+    return occ.astype(bool), int(cnt)

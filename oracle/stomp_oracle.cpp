@@ -7,7 +7,7 @@
  * include/stomp_b200.h) never links, imports or calls anything in oracle/.
  *
  * PARITY PINNED against outputs of the reference itself: the reference ships no unit tests, golden vectors or
- * known-answer data for this path and its rosbuild build cannot run here, but 11 of its 14
+ * known-answer data for this path and its rosbuild build cannot run here, but 13 of its 14
  * translation units compile UNMODIFIED from /root/reference against stand-in headers for the third-party packages it
  * does not vendor (oracle/ref_shim/, oracle/ref_driver.cpp -> oracle/_ref/libstomp_ref.so).  tests/golden/ref_*.npz are
  * that library's outputs; tests/test_reference_pinning.py holds this oracle to them (every intermediate of

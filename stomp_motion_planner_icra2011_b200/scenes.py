@@ -57,19 +57,33 @@ class Robot:
         return [i for i, g in enumerate(self.segments) if g["parent"] == s]
 
     def add_link_spheres(self, seg, radius, clearance, extension=0.0):
-        """StompRobotModel::addCollisionPointsFromLinkRadius (src/stomp_robot_model.cpp:265-306)."""
+        """StompRobotModel::addCollisionPointsFromLinkRadius (src/stomp_robot_model.cpp:265-306), checked against the compiled
+        reference (tests/test_reference_pinning.py).  The points run from the link origin to the child's
+        KDL JointOrigin().  kdl_parser gives a FIXED joint no origin (the offset lives in the segment's tip frame), so for a
+        fixed child JointOrigin() is zero and the reference stacks its ceil(extension / spacing) + 1 points on the link origin;
+        that is reproduced.  (With extension 0 the reference then evaluates 0 / 0; one point at the origin is emitted instead.)"""
         first_child = True
         for c in self.children(seg):
-            origin = np.asarray(self.segments[c]["pos"], float)
+            fixed = self.segments[c]["type"] == _abi.JOINT_FIXED
+            origin = np.zeros(3) if fixed else np.asarray(self.segments[c]["pos"], float)
             spacing = radius / 2.0
             distance = float(np.linalg.norm(origin)) + extension
             num_points = int(math.ceil(distance / spacing)) + 1
             for i in range(num_points):
                 if not first_child and i == 0:
                     continue
-                pos = origin * (i / (num_points - 1.0))
-                self.spheres.append(dict(segment=seg, radius=radius, clearance=clearance, pos=tuple(pos)))
+                pos = origin * (i / (num_points - 1.0)) if num_points > 1 else origin * 0.0
+                self.spheres.append(dict(segment=seg, radius=radius, clearance=clearance, pos=tuple(float(v) for v in pos)))
             first_child = False
+
+    def moved_by_group(self, seg):
+        """True when some planning-group joint is at or above `seg` (StompPlanningGroup::addCollisionPoint keeps only those
+        points, src/stomp_robot_model.cpp:308-334)."""
+        while seg >= 0:
+            if self.segments[seg]["group"] >= 0:
+                return True
+            seg = self.segments[seg]["parent"]
+        return False
 
     def add_even_spheres(self, seg, count, radius, clearance):
         c = self.children(seg)

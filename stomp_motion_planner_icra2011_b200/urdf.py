@@ -106,5 +106,9 @@ def robot_from_urdf(urdf_xml: str, group_joints, reference_frame: str, collision
     for link, cfg in (collision_links or {}).items():
         if link not in seg_of_link:
             continue                                         # links outside the model are ignored like in the reference
-        rb.add_link_spheres(seg_of_link[link], float(cfg["link_radius"]), collision_clearance, float(cfg.get("link_extension", 0.0)))
+        # collision_links/<link>/{link_radius, link_clearance, link_extension} (src/stomp_robot_model.cpp:361-373)
+        rb.add_link_spheres(seg_of_link[link], float(cfg["link_radius"]), float(cfg.get("link_clearance", collision_clearance)),
+                            float(cfg.get("link_extension", 0.0)))
+    # a planning group only keeps the points some group joint moves (StompPlanningGroup::addCollisionPoint, :308-334)
+    rb.spheres = [s for s in rb.spheres if rb.moved_by_group(s["segment"])]
     return rb

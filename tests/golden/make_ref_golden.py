@@ -1,7 +1,7 @@
-"""Generates tests/golden/ref_*.npz by RUNNING THE REFERENCE'S OWN CODE: 11 of its 14 translation units
+"""Generates tests/golden/ref_*.npz by RUNNING THE REFERENCE'S OWN CODE: 13 of its 14 translation units
 (policy_improvement, policy_improvement_loop, covariant_trajectory_policy, stomp_cost, stomp_optimizer, stomp_trajectory,
 stomp_collision_point, treefksolverjointposaxis, treefksolverjointposaxis_partial, constraint_evaluator,
-stomp_parameters), compiled unmodified from /root/reference/stomp_motion_planner/src against the stand-in headers of
+stomp_parameters, stomp_robot_model, stomp_collision_space; the 14th is the ROS node's main), compiled unmodified from /root/reference/stomp_motion_planner/src against the stand-in headers of
 oracle/ref_shim/ into oracle/_ref/libstomp_ref.so (oracle/Makefile target `ref`, oracle/ref_driver.cpp).
 
 Run from the repo root in a container that has /root/reference:  python tests/golden/make_ref_golden.py
@@ -163,6 +163,51 @@ def random_tree_case(seed):
     return out
 
 
+PR2_LINKS = (("r_upper_arm_link", 0.10, 0.0), ("r_forearm_link", 0.065, 0.0), ("r_gripper_palm_link", 0.06, 0.0),
+             ("r_gripper_l_finger_link", 0.03, 0.01), ("r_gripper_l_finger_tip_link", 0.03, 0.01),
+             ("r_gripper_r_finger_link", 0.03, 0.01), ("r_gripper_r_finger_tip_link", 0.03, 0.01))   # link, link_radius, link_extension
+ATTACHED = (("r_gripper_palm_link", "box", (0.10, 0.06, 0.20), (0.12, 0.0, 0.0)),
+            ("r_gripper_palm_link", "cylinder", (0.03, 0.25), (0.10, 0.02, -0.01)),
+            ("r_forearm_link", "sphere", (0.05,), (0.2, 0.0, 0.04)))
+SDF_SCENE = dict(size=(2.0, 3.0, 2.2), origin=(-0.5, -1.5, -0.3), resolution=0.015)
+
+
+def sdf_objects():
+    ident = (0.0, 0.0, 0.0, 1.0)
+    yaw = (0.0, 0.0, float(np.sin(0.35)), float(np.cos(0.35)))
+    tilt = (float(np.sin(0.2)) * 0.6, float(np.sin(0.2)) * 0.8, 0.0, float(np.cos(0.2)))
+    boxes = [((0.8, -0.1, 0.015), ident, (0.4, 1.2, 0.03)), ((0.8, -0.685, 0.8), ident, (0.4, 0.03, 1.6)),
+             ((0.3, 0.6, 0.9), yaw, (0.25, 0.1, 0.3)), ((-0.45, -1.45, 1.0), tilt, (0.3, 0.3, 0.3))]   # last one pokes out of the grid
+    cyls = [((0.62, -0.62, 0.6), ident, 0.1, 1.2), ((0.2, 0.2, 0.4), tilt, 0.07, 0.5)]
+    return boxes, cyls
+
+
+def collision_point_case():
+    """StompRobotModel::generateLinkCollisionPoints / generateAttachedObjectCollisionPoints / populatePlanningGroupCollisionPoints."""
+    rb = scenes.pr2_right_arm()
+    rb.spheres = []
+    names = [g["name"] for g in rb.segments]
+    links = [(names.index(n), r, None if i % 2 else 0.05 + 0.01 * i, e) for i, (n, r, e) in enumerate(PR2_LINKS)]
+    # a link no group joint moves: the planning group drops its points (src/stomp_robot_model.cpp:308-334)
+    links.append((names.index("torso_lift_link"), 0.2, None, 0.0))
+    attached = [(names.index(n), shape, dims, pos) for n, shape, dims, pos in ATTACHED]
+    pts = rp.collision_points(rb, links, default_clearance=0.07, attached=attached, attached_padding=0.01)
+    as_array = lambda p: np.array([[a[0], a[1], a[2], *a[3]] for a in p])  # noqa: E731
+    out = {"links": np.array([[l[0], l[1], -1.0 if l[2] is None else l[2], l[3]] for l in links]), "points": as_array(pts)}
+    # the plain configuration of the synthetic arm (every clearance the default, no attached objects)
+    plain = [(names.index(n), r, None, e) for n, r, e in PR2_LINKS]
+    out["plain_points"] = as_array(rp.collision_points(rb, plain, default_clearance=0.07))
+    return out
+
+
+def collision_cells_case():
+    """StompCollisionSpace::addCollisionObjectsToPoints + the distance field's cell binning."""
+    boxes, cyls = sdf_objects()
+    occ, npts = rp.collision_object_cells(boxes=boxes, cylinders=cyls, **SDF_SCENE)
+    return {"occupancy_bits": np.packbits(occ.ravel()), "shape": np.array(occ.shape), "num_points": np.array(npts),
+            "num_occupied": np.array(int(occ.sum()))}
+
+
 def main():
     def save(stem, out):
         path = os.path.join(HERE, stem + ".npz")
@@ -180,6 +225,8 @@ def main():
         save("ref_cost_tree%d" % seed, random_tree_case(seed))
     save("ref_cost_tiny_torque", cost_plugin_case("tiny", 3, 24, torque=TORQUE_WEIGHT))
     save("ref_iter_tiny_torque", iteration_case("tiny", 1, 3, torque=TORQUE_WEIGHT))
+    save("ref_collision_points", collision_point_case())
+    save("ref_collision_cells", collision_cells_case())
     save("ref_optimize_tiny_s8", optimize_case("tiny", 8, 60, 5))     # collision free at iteration 28, early exit after 33
     save("ref_optimize_tiny_s7", optimize_case("tiny", 7, 20, 6))     # never collision free: runs to max_iterations
     save("ref_optimize_c1_s8", optimize_case("C1", 8, 40, 5))        # collision free from the first iteration

@@ -1,4 +1,4 @@
-"""GPU parity against OUTPUTS OF THE REFERENCE ITSELF (tests/golden/ref_*.npz: 11 of the reference's 14 translation units
+"""GPU parity against OUTPUTS OF THE REFERENCE ITSELF (tests/golden/ref_*.npz: 13 of the reference's 14 translation units
 compiled unmodified and run on the synthetic scenes — see tests/test_reference_pinning.py and
 tests/golden/make_ref_golden.py).  No oracle is involved at run time.
 
@@ -161,3 +161,17 @@ def test_engine_optimize_matches_the_compiled_reference(stem, name):
     assert_close(res["costs"], g["stats_costs"], RTOL_F64, "STOMPStatistics.costs")
     assert_close(res["best_cost"], float(g["stats_best_cost"]), RTOL_F64, "best cost")
     assert_close(res["best_trajectory"], g["stats_best_trajectory"], RTOL_F64, "best group trajectory")
+
+
+def test_engine_distance_field_occupancy_matches_the_compiled_collision_space():
+    """stomp_engine_build_sdf's zero set = the cells StompCollisionSpace::addCollisionObjectsToPoints marks (bit-exact)."""
+    from stomp_motion_planner_icra2011_b200 import scenes
+    from tests.golden.make_ref_golden import SDF_SCENE, sdf_objects
+    g = rg.load("ref_collision_cells")
+    boxes, cyls = sdf_objects()
+    eng = _engine(scenes.make_scenario("tiny", num_problems=1))
+    eng.build_sdf(boxes=boxes, cylinders=cyls, max_distance=0.17, **SDF_SCENE)
+    got, dtype = eng.get_sdf()
+    want = np.unpackbits(g["occupancy_bits"])[:got.size].reshape(g["shape"]).astype(bool)
+    assert dtype == _abi.VOXEL_U8_SQ and got.shape == want.shape
+    np.testing.assert_array_equal(got == 0, want)

@@ -1,6 +1,6 @@
 """Pins the CPU oracle to OUTPUTS OF THE REFERENCE ITSELF.
 
-tests/golden/ref_*.npz were produced by 11 of the reference's 14 translation units, compiled UNMODIFIED from
+tests/golden/ref_*.npz were produced by 13 of the reference's 14 translation units, compiled UNMODIFIED from
 /root/reference/stomp_motion_planner/src (PolicyImprovementLoop, PolicyImprovement, CovariantTrajectoryPolicy,
 MultivariateGaussian, StompCost, StompOptimizer incl. execute / handleJointLimits / performForwardKinematics / optimize,
 StompTrajectory, StompCollisionPoint, both TreeFkSolverJointPosAxis solvers, OrientationConstraintEvaluator,
@@ -186,3 +186,45 @@ def test_fixtures_are_what_the_compiled_reference_produces_today():
         assert sorted(fresh) == sorted(g.files)
         for k in g.files:
             np.testing.assert_allclose(fresh[k], g[k], rtol=1e-12, atol=1e-300, err_msg=k)
+
+
+def test_collision_point_generation_matches_the_compiled_robot_model():
+    """StompRobotModel::generateLinkCollisionPoints / generateAttachedObjectCollisionPoints / populatePlanningGroupCollisionPoints
+    (src/stomp_robot_model.cpp:265-496) against Robot.add_link_spheres / add_attached_object, which urdf.py builds on."""
+    from stomp_motion_planner_icra2011_b200 import scenes
+    from tests.golden.make_ref_golden import ATTACHED
+    g = rg.load("ref_collision_points")
+    as_array = lambda rb: np.array([[s["segment"], s["radius"], s["clearance"], *s["pos"]] for s in rb.spheres])  # noqa: E731
+    # the synthetic arm's own table is what the reference generates from its tree: bit-identical
+    np.testing.assert_array_equal(as_array(scenes.pr2_right_arm()), g["plain_points"])
+    # per-link clearances, a link outside the group's reach (dropped), attached objects with padding
+    rb = scenes.pr2_right_arm()
+    rb.spheres = []
+    names = [s["name"] for s in rb.segments]
+    for seg, radius, clearance, extension in g["links"]:
+        # link points first, then the link's attached-object points, link by link (populatePlanningGroupCollisionPoints)
+        rb.add_link_spheres(int(seg), radius, 0.07 if clearance < 0 else clearance, extension)
+        for n, shape, dims, pos in ATTACHED:
+            if names.index(n) == int(seg):
+                rb.add_attached_object(int(seg), shape, dims, pos, padding=0.01, clearance=0.07)
+    rb.spheres = [s for s in rb.spheres if rb.moved_by_group(s["segment"])]
+    got = as_array(rb)
+    assert got.shape == g["points"].shape
+    np.testing.assert_array_equal(got[:, 0], g["points"][:, 0])
+    np.testing.assert_allclose(got, g["points"], rtol=1e-14, atol=0)
+    assert len(g["points"]) > len(g["plain_points"]) and not (g["points"][:, 0] == names.index("torso_lift_link")).any()
+
+
+def test_collision_object_rasterisation_matches_the_compiled_collision_space():
+    """StompCollisionSpace::addCollisionObjectsToPoints (src/stomp_collision_space.cpp:198-297), lattice loops with accumulated
+    `x += resolution_`, rotated boxes and cylinders: the occupied cells are integer work, bit-exact.  (The engine's
+    stomp_engine_build_sdf is held to oracle/sdf_builder.py on the same scene by tests/test_gpu_parity.py and to this fixture by
+    tests/test_gpu_reference_golden.py.)"""
+    from oracle import sdf_builder
+    from tests.golden.make_ref_golden import SDF_SCENE, sdf_objects
+    g = rg.load("ref_collision_cells")
+    boxes, cyls = sdf_objects()
+    _, occ = sdf_builder.build(boxes=boxes, cylinders=cyls, max_distance=0.17, **SDF_SCENE)
+    want = np.unpackbits(g["occupancy_bits"])[:occ.size].reshape(g["shape"]).astype(bool)
+    assert occ.shape == want.shape and int(want.sum()) == int(g["num_occupied"]) > 10000
+    np.testing.assert_array_equal(occ, want)

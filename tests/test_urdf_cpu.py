@@ -70,7 +70,7 @@ def test_urdf_reproduces_the_synthetic_arm():
             np.testing.assert_allclose(a["axis"], b["axis"], atol=1e-15)
         assert a["fixed"] == b["fixed"]
     assert got.limits == want.limits and got.reference_segment == want.reference_segment
-    assert len(got.spheres) == len(want.spheres) == 51
+    assert len(got.spheres) == len(want.spheres) == 47
     for a, b in zip(got.spheres, want.spheres):
         assert a["segment"] == b["segment"] and a["radius"] == b["radius"] and a["clearance"] == b["clearance"]
         np.testing.assert_allclose(a["pos"], b["pos"], atol=0)
