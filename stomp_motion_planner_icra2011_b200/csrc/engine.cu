@@ -65,7 +65,7 @@ struct Engine {
   int device = 0, num_sms = 148;
   cudaStream_t stream = nullptr, copy_stream = nullptr, tail_stream = nullptr;
   cudaStream_t ws = nullptr;   // stream the launch helpers currently enqueue on (stream or tail_stream)
-  cudaEvent_t ev_tail = nullptr, ev_upd = nullptr;
+  cudaEvent_t ev_tail = nullptr, ev_upd = nullptr, ev_selected = nullptr;
   // asynchronous result read-back (two requests in flight)
   cudaStream_t result_stream = nullptr;
   cudaEvent_t ev_snap_main[2] = {nullptr, nullptr}, ev_snap_tail[2] = {nullptr, nullptr}, ev_results[2] = {nullptr, nullptr};
@@ -643,7 +643,12 @@ int iterate_once(Engine& e, int iteration_number) {
   plan_rollouts(e, p);
   if (p.reuse) {
     e.ws = e.tail_stream;
-    if (launch_select(e) || launch_generate_range(e, p, e.num_gen, e.R - e.num_gen, true) || gather_reused_state(e) ||
+    if (launch_select(e)) { e.ws = e.stream; return 1; }
+    // k_select_reuse ranks the PREVIOUS iteration's Rollout::getCost() values; this iteration's k_cumulative on the main
+    // stream overwrites the new slots' entries of that array and must not overtake it.  (It never did while the main
+    // stream's path to it was ~330 us long, but nothing ordered the two: found when an experiment shortened that path.)
+    CUDA_TRY(cudaEventRecord(e.ev_selected, e.tail_stream));
+    if (launch_generate_range(e, p, e.num_gen, e.R - e.num_gen, true) || gather_reused_state(e) ||
         launch_cumulative(e, e.num_gen, e.R - e.num_gen)) {
       e.ws = e.stream;
       return 1;
@@ -655,6 +660,7 @@ int iterate_once(Engine& e, int iteration_number) {
   if (launch_cost(e, e.params[e.cur].p, size_t(e.R) * e.D * e.N, e.num_gen, e.B, iteration_number == 1, e.state[e.cur].p,
                   size_t(e.R) * e.N, e.collision_free.p, e.R + 1, 0, e.clipped.p, nullptr, e.constraints_ok.p))
     return 1;
+  if (p.reuse) CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_selected, 0));
   if (launch_cumulative(e, 0, e.num_gen)) return 1;       // new slots; the reused slots' were done on the tail stream
   CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_tail, 0));
   const bool huge = e.huge_path();
@@ -791,7 +797,8 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   if ((c = cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
   if ((c = cudaStreamCreateWithFlags(&e.tail_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
   if ((c = cudaEventCreateWithFlags(&e.ev_tail, cudaEventDisableTiming)) != cudaSuccess ||
-      (c = cudaEventCreateWithFlags(&e.ev_upd, cudaEventDisableTiming)) != cudaSuccess)
+      (c = cudaEventCreateWithFlags(&e.ev_upd, cudaEventDisableTiming)) != cudaSuccess ||
+      (c = cudaEventCreateWithFlags(&e.ev_selected, cudaEventDisableTiming)) != cudaSuccess)
     return bail(c, "cudaEventCreate");
   if ((c = cudaStreamCreateWithFlags(&e.result_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
   for (int i = 0; i < 2; ++i)
@@ -870,6 +877,7 @@ int stomp_engine_destroy(void* h) {
   }
   if (e->ev_tail) cudaEventDestroy(e->ev_tail);
   if (e->ev_upd) cudaEventDestroy(e->ev_upd);
+  if (e->ev_selected) cudaEventDestroy(e->ev_selected);
   for (int i = 0; i < 2; ++i) {
     if (e->ev_copy_done[i]) cudaEventDestroy(e->ev_copy_done[i]);
     if (e->ev_consumed[i]) cudaEventDestroy(e->ev_consumed[i]);

@@ -171,6 +171,9 @@ class Engine:
         return out
 
     # ---- noise --------------------------------------------------------------------------
+    def set_noise(self, noise_stddev, noise_decay):
+        self._ck(self.L.stomp_engine_set_noise(self.h, _dp(_f64(noise_stddev)), _dp(_f64(noise_decay))))
+
     def seed(self, seed):
         self._ck(self.L.stomp_engine_seed(self.h, C.c_uint64(seed)))
 
