@@ -270,8 +270,12 @@ def run_engine(args):
         sc = scenes.make_scenario("C3", num_problems=1, num_rollouts=total_rollouts // world, seed=7)
         eng = Engine(sc, dtype=dtype, device=local, shard_rank=rank, shard_world=world)
         if world > 1:
-            mm, sm = device_views(eng)
-            driver = ShardedIteration(eng, mm, sm, dist=dist)
+            if args.c3_exchange == "peer":   # both exchanges in-kernel over NVLink peer memory (k_peer_allreduce)
+                from stomp_motion_planner_icra2011_b200.distributed import PeerShardedIteration
+                driver = PeerShardedIteration(eng, dist)
+            else:                            # two NCCL all-reduces between host-synchronised phases
+                mm, sm = device_views(eng)
+                driver = ShardedIteration(eng, mm, sm, dist=dist)
             eng_iterate = lambda i, stats=False: driver.iterate(i)
         else:
             eng_iterate = lambda i, stats=False: eng.iterate(i, stats=stats)
@@ -414,7 +418,9 @@ def run_engine(args):
                 "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": args.dtype,
                 "data": "synthetic",
                 "config": {"workload": _workload_desc(name, sc, B),
-                           "parallelism": ("rollouts sharded over %d GPU(s), 2 NCCL all-reduces of 2*D*N doubles per iteration" % world)
+                           "parallelism": ("rollouts sharded over %d GPU(s), 2 reductions of 2*D*N doubles per iteration, %s" %
+                                           (world, "in-kernel over NVLink peer memory (k_peer_allreduce), no host sync" if args.c3_exchange == "peer"
+                                            else "NCCL all-reduces between host-synchronised phases"))
                            if sharded else ("problems sharded over %d GPU(s), no collective" % world),
                            "l2": "per-iteration working set %.2f GB of rollout arrays >> 126 MB L2 (no flush needed)"
                                  % (6 * B * R * D * N * 8 / 1e9),
@@ -444,6 +450,8 @@ def main():
     ap.add_argument("--rollouts", type=int, default=65536, help="total rollouts of the C3 workload")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c3-exchange", choices=["peer", "nccl"], default="peer",
+                    help="C3 (rollout-sharded) only: how the two per-iteration reductions cross GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

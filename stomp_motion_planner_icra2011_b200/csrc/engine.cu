@@ -117,6 +117,12 @@ struct Engine {
   DevBuf<int> scratch_flags;
   DevBuf<stomp_sphere_debug> debug;
   DevBuf<double> part, minmax, sums;  // sharded / huge-R statistics
+  // peer-memory exchange of the sharded statistics (k_peer_allreduce): this rank's buffer, the peers' mappings of theirs
+  DevBuf<unsigned char> xchg;
+  DevBuf<int> xchg_err;
+  unsigned char* peer_base[kMaxPeers] = {nullptr};
+  bool peers_open = false;
+  unsigned long long xchg_epoch = 0;
   DevBuf<double> snap_theta[2], snap_cost[2];
   DevBuf<int> snap_flag[2];
   DevBuf<double> gen_scratch, gen_scratch2;   // time-major work buffers of k_generate (main / tail stream)
@@ -876,6 +882,9 @@ int stomp_engine_destroy(void* h) {
     if (e->ev_results[i]) cudaEventDestroy(e->ev_results[i]);
   }
   if (e->ev_tail) cudaEventDestroy(e->ev_tail);
+  if (e->peers_open)
+    for (int r = 0; r < e->desc.rollout_shard_world; ++r)
+      if (r != e->desc.rollout_shard_rank && e->peer_base[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
   if (e->ev_upd) cudaEventDestroy(e->ev_upd);
   if (e->ev_selected) cudaEventDestroy(e->ev_selected);
   for (int i = 0; i < 2; ++i) {
@@ -1540,6 +1549,82 @@ int stomp_engine_shard_buffers(void* h, void** minmax_dev, void** sums_dev, size
   if (sums_dev) *sums_dev = e.sums.p;
   if (bytes_each) *bytes_each = size_t(2) * e.D * e.N * 8;
   return 0;
+}
+
+/* ---- peer-memory exchange (rollout sharding without NCCL or host synchronisation between the phases) ----------------- */
+static size_t xchg_bytes(const Engine& e) {
+  const size_t W = size_t(e.desc.rollout_shard_world), n = size_t(2) * e.D * e.N;
+  return 2 * W * n * sizeof(double) + 2 * W * sizeof(unsigned long long);
+}
+
+int stomp_engine_shard_ipc_handle(void* h, void* handle_out, size_t handle_bytes) {
+  ENGINE_OR_FAIL(h);
+  if (!handle_out || handle_bytes < sizeof(cudaIpcMemHandle_t)) return fail("handle buffer must hold 64 bytes");
+  if (e.desc.rollout_shard_world > kMaxPeers) return fail("too many ranks for the peer exchange");
+  if (e.xchg.n != xchg_bytes(e)) {
+    CUDA_TRY(e.xchg.alloc(xchg_bytes(e)));   // zero-filled: flags start below every epoch
+    CUDA_TRY(e.xchg_err.alloc(1));
+  }
+  cudaIpcMemHandle_t ipc;
+  CUDA_TRY(cudaIpcGetMemHandle(&ipc, e.xchg.p));
+  std::memcpy(handle_out, &ipc, sizeof(ipc));
+  return 0;
+}
+
+int stomp_engine_shard_open_peers(void* h, const void* handles, int32_t count) {
+  ENGINE_OR_FAIL(h);
+  const int W = e.desc.rollout_shard_world, rank = e.desc.rollout_shard_rank;
+  if (!handles || count != W) return fail("one IPC handle per rank is required");
+  if (e.xchg.n != xchg_bytes(e)) return fail("call stomp_engine_shard_ipc_handle first");
+  for (int r = 0; r < W; ++r) {
+    if (r == rank) { e.peer_base[r] = e.xchg.p; continue; }
+    cudaIpcMemHandle_t ipc;
+    std::memcpy(&ipc, static_cast<const unsigned char*>(handles) + size_t(r) * sizeof(ipc), sizeof(ipc));
+    void* p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+    e.peer_base[r] = static_cast<unsigned char*>(p);
+  }
+  e.peers_open = true;
+  e.xchg_epoch = 0;
+  return 0;
+}
+
+static int launch_peer_allreduce(Engine& e, double* local, int is_max) {
+  PeerArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.rank = e.desc.rollout_shard_rank; a.world = e.desc.rollout_shard_world; a.n = 2 * e.D * e.N; a.is_max = is_max;
+  a.epoch = ++e.xchg_epoch;
+  for (int r = 0; r < a.world; ++r) a.peers[r] = e.peer_base[r];
+  a.local = local;
+  a.err = e.xchg_err.p;
+  begin_launch(e);
+  k_peer_allreduce<<<1, 1024, 0, e.ws>>>(a);
+  return check_launch(e, "k_peer_allreduce");
+}
+
+/* One iteration of a rollout-sharded engine with both exchanges done in-kernel over peer memory: everything is enqueued on
+ * the handle's stream, no host synchronisation, no NCCL.  Every rank must call it for the same iteration. */
+int stomp_engine_iterate_sharded_fused(void* h, int32_t iteration_number) {
+  ENGINE_OR_FAIL(h);
+  if (!e.have_problems) return fail("set_problems must be called first");
+  if (e.B != 1) return fail("rollout sharding requires num_problems == 1");
+  if (e.desc.rollout_shard_world > 1 && !e.peers_open) return fail("call stomp_engine_shard_open_peers first");
+  if (iterate_front(e, iteration_number) || launch_minmax(e)) return 1;
+  if (e.desc.rollout_shard_world > 1 && launch_peer_allreduce(e, e.minmax.p, 1)) return 1;
+  if (launch_sums(e)) return 1;
+  if (e.desc.rollout_shard_world > 1 && launch_peer_allreduce(e, e.sums.p, 0)) return 1;
+  if (launch_finalize(e, 1)) return 1;
+  return step_extra(e, true, iteration_number);
+}
+
+/* 0 when no peer exchange has timed out (blocks until the stream is idle) */
+int stomp_engine_shard_status(void* h) {
+  ENGINE_OR_FAIL(h);
+  if (!e.xchg_err.p) return 0;
+  int err = 0;
+  CUDA_TRY(cudaMemcpyAsync(&err, e.xchg_err.p, sizeof(int), cudaMemcpyDeviceToHost, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return err ? fail("a peer exchange timed out: some rank did not reach the same iteration") : 0;
 }
 
 /* phase 0: rollouts, costs, local {max c, max -c}  -> caller all-reduces minmax with MAX

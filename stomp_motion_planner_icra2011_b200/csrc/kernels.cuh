@@ -1562,6 +1562,61 @@ __global__ void k_pair_reduce(int DN, int nchunks, int is_max, const double* __r
   out[i] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_peer_allreduce: the cross-GPU exchange of the rollout-sharded statistics (config C3) done by the GPUs themselves over
+// NVLink peer memory instead of an NCCL collective between host-synchronised phases.  Every rank owns one exchange buffer
+//   data[2 phases][world][n] doubles | flags[2 phases][world] u64
+// mapped into every other rank's address space (CUDA IPC).  One CTA per rank:
+//   1. store the local n-vector into slot [phase][my rank] of EVERY peer's buffer (P2P stores), fence (system scope)
+//   2. raise flag [phase][my rank] = epoch on every peer
+//   3. wait until all `world` flags of the own buffer reached the epoch, then reduce the world slots in rank order (MAX or SUM:
+//      the same order on every rank, so all ranks hold bit-identical results) into the local vector, in place.
+// Epochs increase monotonically (two exchanges per iteration, alternating phase buffers), so a rank can only overwrite its
+// slot of phase p after every peer has raised a later flag, i.e. finished reading the previous use of that slot.
+// The wait is bounded (~2 s of SM clocks); on expiry the error flag is set instead of hanging the device.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+struct PeerArgs {
+  int rank, world, n, is_max;
+  unsigned long long epoch;
+  unsigned char* peers[kMaxPeers];   // base of every rank's exchange buffer as seen from this rank
+  double* local;                     // [n] in: this rank's partial, out: the reduction over all ranks
+  int* err;
+};
+
+__global__ void __launch_bounds__(1024) k_peer_allreduce(PeerArgs a) {
+  const int n = a.n, W = a.world, ph = a.is_max ? 0 : 1;
+  const size_t data_bytes = size_t(2) * W * n * sizeof(double);
+  for (int p = 0; p < W; ++p) {
+    double* dst = reinterpret_cast<double*>(a.peers[p]) + (size_t(ph) * W + a.rank) * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = a.local[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (int(threadIdx.x) < W) {
+    volatile unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peers[threadIdx.x] + data_bytes) + ph * W + a.rank;
+    *f = a.epoch;
+  }
+  if (int(threadIdx.x) < W) {
+    volatile unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peers[a.rank] + data_bytes) + ph * W + threadIdx.x;
+    const long long t0 = clock64();
+    while (*f < a.epoch) {
+      if (clock64() - t0 > 4000000000ll) { *a.err = 1; break; }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  const volatile double* src = reinterpret_cast<const double*>(a.peers[a.rank]) + size_t(ph) * W * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double acc = src[i];
+    for (int r = 1; r < W; ++r) {
+      const double v = src[size_t(r) * n + i];
+      acc = a.is_max ? fmax(acc, v) : acc + v;
+    }
+    a.local[i] = acc;
+  }
+}
+
 __global__ void k_sums_partial(int R, int DN, int rollouts_per_chunk, const double* __restrict__ cumulative,
                                const double* __restrict__ noise, const double* __restrict__ minmax,
                                double* __restrict__ part) {

@@ -86,6 +86,24 @@ class ShardedIteration:
             torch.cuda.current_stream(t.device).synchronize()
 
 
+class PeerShardedIteration:
+    """The same iteration with the two exchanges done in-kernel over NVLink peer memory (k_peer_allreduce): no NCCL call and
+    no host synchronisation inside an iteration.  torch.distributed is only used once, to all-gather the 64-byte CUDA IPC
+    handles of the ranks' exchange buffers."""
+
+    def __init__(self, engine, dist, group=None):
+        self.engine = engine
+        world = dist.get_world_size(group)
+        mine = engine.shard_ipc_handle()
+        handles = [None] * world
+        dist.all_gather_object(handles, mine, group=group)
+        engine.shard_open_peers(handles)
+        dist.barrier(group=group)          # every rank has mapped every buffer before the first store into one
+
+    def iterate(self, iteration_number: int):
+        self.engine.iterate_sharded_fused(iteration_number)
+
+
 class NumpyShardStandIn:
     """CPU stand-in with the engine's three-phase protocol, used by the gloo tests: it holds a shard of
     per-rollout cumulative costs and noise and implements exactly the arithmetic of k_minmax_partial /

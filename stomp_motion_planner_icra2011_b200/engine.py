@@ -31,6 +31,8 @@ EXPORTS = [
     "stomp_engine_build_sdf", "stomp_engine_get_sdf", "stomp_engine_inject_noise_async", "stomp_engine_last_stats",
     "stomp_engine_set_constraints", "stomp_engine_execute_constraints_satisfied",
     "stomp_engine_request_results_async", "stomp_engine_wait_results", "stomp_engine_set_dynamics",
+    "stomp_engine_shard_ipc_handle", "stomp_engine_shard_open_peers", "stomp_engine_iterate_sharded_fused",
+    "stomp_engine_shard_status",
 ]
 
 
@@ -309,6 +311,22 @@ class Engine:
         mm, sm, nb = C.c_void_p(), C.c_void_p(), C.c_size_t()
         self._ck(self.L.stomp_engine_shard_buffers(self.h, C.byref(mm), C.byref(sm), C.byref(nb)))
         return mm.value, sm.value, nb.value
+
+    def shard_ipc_handle(self):
+        buf = (C.c_ubyte * 64)()
+        self._ck(self.L.stomp_engine_shard_ipc_handle(self.h, buf, C.c_size_t(64)))
+        return bytes(buf)
+
+    def shard_open_peers(self, handles):
+        blob = b"".join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._ck(self.L.stomp_engine_shard_open_peers(self.h, buf, len(handles)))
+
+    def iterate_sharded_fused(self, iteration_number):
+        self._ck(self.L.stomp_engine_iterate_sharded_fused(self.h, iteration_number))
+
+    def shard_status(self):
+        self._ck(self.L.stomp_engine_shard_status(self.h))
 
     def iterate_sharded_phase(self, iteration_number, phase):
         self._ck(self.L.stomp_engine_iterate_sharded_phase(self.h, iteration_number, phase))
