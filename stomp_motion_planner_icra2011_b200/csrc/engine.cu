@@ -1605,16 +1605,30 @@ static int launch_peer_allreduce(Engine& e, double* local, int is_max) {
 /* One iteration of a rollout-sharded engine with both exchanges done in-kernel over peer memory: everything is enqueued on
  * the handle's stream, no host synchronisation, no NCCL.  Every rank must call it for the same iteration. */
 int stomp_engine_iterate_sharded_fused(void* h, int32_t iteration_number) {
-  ENGINE_OR_FAIL(h);
+  ENGINE_NOJOIN(h);
   if (!e.have_problems) return fail("set_problems must be called first");
   if (e.B != 1) return fail("rollout sharding requires num_problems == 1");
   if (e.desc.rollout_shard_world > 1 && !e.peers_open) return fail("call stomp_engine_shard_open_peers first");
+  if (e.Rre != 0) {   // with reuse the next iteration's selection needs the noise-less rollout: keep everything in order
+    if (join_streams(e)) return 1;
+  }
+  e.ws = e.stream;
   if (iterate_front(e, iteration_number) || launch_minmax(e)) return 1;
   if (e.desc.rollout_shard_world > 1 && launch_peer_allreduce(e, e.minmax.p, 1)) return 1;
   if (launch_sums(e)) return 1;
   if (e.desc.rollout_shard_world > 1 && launch_peer_allreduce(e, e.sums.p, 0)) return 1;
+  // the previous iteration's noise-less rollout (tail stream) still reads theta: the update waits for it
+  if (join_streams(e)) return 1;
   if (launch_finalize(e, 1)) return 1;
-  return step_extra(e, true, iteration_number);
+  // the noise-less rollout of ONE problem is a ~80 us latency chain nothing in the next iteration depends on (no rollout
+  // reuse when rollouts are sharded): it runs on the tail stream under the next iteration's sampling and costs
+  CUDA_TRY(cudaEventRecord(e.ev_upd, e.stream));
+  e.ws = e.tail_stream;
+  CUDA_TRY(cudaStreamWaitEvent(e.tail_stream, e.ev_upd, 0));
+  const int rc = step_extra(e, true, iteration_number);
+  e.tail_dirty = true;
+  e.ws = e.stream;
+  return rc;
 }
 
 /* 0 when no peer exchange has timed out (blocks until the stream is idle) */
