@@ -656,3 +656,33 @@ def test_async_result_readback_pipeline():
     b.wait_results(tickets[-1])
     for got, ref in zip(bufs[-1], want[-1]):
         np.testing.assert_array_equal(got, ref)
+
+
+def test_torque_and_shard_argument_errors_and_single_rank_fused_iteration():
+    sc = scenes.make_scenario("tiny", num_problems=1, num_rollouts=160)
+    sc.num_reused_rollouts = 0
+    a, b = _engine(sc), _engine(sc)
+    # the fused sharded iteration on a single rank is the huge-R path of iterate(): same kernels, same results
+    for it in range(1, 4):
+        a.iterate(it, stats=False)
+        b.iterate_sharded_fused(it)
+    b.shard_status()
+    for f in (_abi.FIELD_THETA, _abi.FIELD_ROLLOUT_TOTAL_COSTS, _abi.FIELD_NOISELESS_COSTS):
+        np.testing.assert_array_equal(a.get(f), b.get(f))
+    with pytest.raises(RuntimeError):
+        b.shard_open_peers([b"\0" * 64, b"\0" * 64])            # one handle per rank, and this engine has one rank
+    # the inverse-dynamics chain must be the group joints in order
+    rb = sc.robot
+    good = rb.chain
+    rb.chain = (good[0], good[1] - 3)
+    with pytest.raises(RuntimeError):
+        a.set_dynamics(1.0)
+    rb.chain = (good[1], good[0])                                 # tip above root
+    with pytest.raises(RuntimeError):
+        a.set_dynamics(1.0)
+    rb.chain = good
+    a.set_dynamics(0.0)                                           # weight 0: accepted, term stays off
+    c0, _ = a.execute(a.get(_abi.FIELD_THETA)[:, None])
+    a.set_dynamics(0.5)
+    c1, _ = a.execute(a.get(_abi.FIELD_THETA)[:, None])
+    assert np.all(c1 > c0)
