@@ -34,6 +34,9 @@ extern "C" {
 #define STOMP_NUM_DIFF_RULES 3   /* include/stomp_motion_planner/stomp_utils.h:50 */
 
 enum stomp_dtype { STOMP_F64 = 0, STOMP_F32 = 1 };
+/* NEAREST: the reference's lookup (distance of the nearest cell, 0 on / outside the grid's outermost layer): the parity mode.
+ * TRILINEAR: engine extension, trilinear interpolation of the eight surrounding cell distances (each corner with the same
+ * boundary rule): a continuous field, no parity claim against the reference. */
 enum stomp_sdf_mode { STOMP_SDF_NEAREST = 0, STOMP_SDF_TRILINEAR = 1 };
 enum stomp_voxel_dtype {
   STOMP_VOXEL_F32 = 0,   /* distance in metres */

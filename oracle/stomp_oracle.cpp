@@ -390,7 +390,39 @@ bool build_quad_cost_inv(Oracle& o) {
 }
 
 /* ---- distance field lookup ------------------------------------- */
+static double cell_distance(const Oracle& o, int cx, int cy, int cz) { /* a cell's distance incl. the one-cell margin rule */
+  if (cx < 1 || cy < 1 || cz < 1 || cx >= o.nx - 1 || cy >= o.ny - 1 || cz >= o.nz - 1) return 0.0;
+  size_t idx = (size_t(cx) * o.ny + cy) * o.nz + cz;
+  switch (o.vox_dtype) {
+    case STOMP_VOXEL_U8_SQ: return o.sqrt_table[o.vox[idx]];
+    case STOMP_VOXEL_U16_SQ: return o.sqrt_table[reinterpret_cast<const uint16_t*>(o.vox.data())[idx]];
+    default: return double(reinterpret_cast<const float*>(o.vox.data())[idx]);
+  }
+}
+
+/* STOMP_SDF_TRILINEAR (engine extension, not a reference mode): trilinear interpolation of the eight cell distances around the
+ * point, every corner following the nearest-cell rule above (0 on / outside the outermost layer), so the field is the
+ * continuous extension of the reference's piecewise-constant one.  cell = the lower corner. */
+double sdf_distance_trilinear(const Oracle& o, const double pos[3], int cell[3]) {
+  double f[3];
+  for (int i = 0; i < 3; ++i) {
+    const double t = (pos[i] - o.origin[i]) / o.res;
+    const double fl = std::floor(t);
+    cell[i] = std::fabs(fl) < 2.0e9 ? int(fl) : -1;
+    f[i] = t - fl;
+  }
+  double acc = 0.0;
+  for (int dx = 0; dx < 2; ++dx)
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dz = 0; dz < 2; ++dz) {
+        const double w = (dx ? f[0] : 1.0 - f[0]) * (dy ? f[1] : 1.0 - f[1]) * (dz ? f[2] : 1.0 - f[2]);
+        acc += w * cell_distance(o, cell[0] + dx, cell[1] + dy, cell[2] + dz);
+      }
+  return acc;
+}
+
 double sdf_distance(const Oracle& o, const double pos[3], int cell[3]) {
+  if (o.desc.sdf_mode == STOMP_SDF_TRILINEAR) return sdf_distance_trilinear(o, pos, cell);
   const int n[3] = {o.nx, o.ny, o.nz};
   bool outside = false;
   for (int i = 0; i < 3; ++i) {

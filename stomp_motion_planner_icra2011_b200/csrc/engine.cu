@@ -273,8 +273,8 @@ GenArgs base_gen_args(Engine& e) {
   return a;
 }
 
-template <typename Real, bool kDebug, int kVox, bool kCons>
-int launch_cost_c(Engine& e, CostArgs<Real>& a, int num_problems) {
+template <typename Real, bool kDebug, int kVox, bool kCons, bool kTri>
+int launch_cost_k(Engine& e, CostArgs<Real>& a, int num_problems) {
   a.total_rollouts = num_problems * a.n_rollouts;
   a.params_16B = ((e.D * e.N) % 2 == 0) && (reinterpret_cast<uintptr_t>(a.params) % 16 == 0) && (a.params_problem_stride % 2 == 0) &&
                  (a.params_rollout_stride % 2 == 0);
@@ -296,7 +296,7 @@ int launch_cost_c(Engine& e, CostArgs<Real>& a, int num_problems) {
   warps = std::max(warps, std::min(pack * e.D, 4));  // joint-limit pass likes a few warps
   const size_t smem = smem_for(pack, warps);
   if (smem > 220 * 1024) return fail("trajectory + robot tables exceed shared memory");
-  auto kern = k_cost<Real, kDebug, kVox, kCons>;
+  auto kern = k_cost<Real, kDebug, kVox, kCons, kTri>;
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   a.pack = pack;
   a.tiles_per_job = tiles;
@@ -306,6 +306,13 @@ int launch_cost_c(Engine& e, CostArgs<Real>& a, int num_problems) {
   begin_launch(e);
   kern<<<njobs, warps * 32, smem, e.ws>>>(a);
   return check_launch(e, "k_cost");
+}
+
+// nearest-cell lookup (the reference's) or the trilinear extension, chosen at create time
+template <typename Real, bool kDebug, int kVox, bool kCons>
+int launch_cost_c(Engine& e, CostArgs<Real>& a, int num_problems) {
+  if (e.desc.sdf_mode == STOMP_SDF_TRILINEAR) return launch_cost_k<Real, kDebug, kVox, kCons, true>(e, a, num_problems);
+  return launch_cost_k<Real, kDebug, kVox, kCons, false>(e, a, num_problems);
 }
 
 // the constraint evaluators are compiled out of the common (no path constraints) instantiation; the debug tap always
@@ -766,7 +773,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   if (desc->num_reused_rollouts < 0 || desc->num_reused_rollouts >= desc->num_rollouts)
     return fail("Number of reused rollouts must be strictly less than number of rollouts.");  // policy_improvement.cpp:102-106
   if (desc->dtype != STOMP_F64 && desc->dtype != STOMP_F32) return fail("unknown dtype");
-  if (desc->sdf_mode != STOMP_SDF_NEAREST) return fail("only the nearest-cell distance-field lookup (the reference's) is implemented");
+  if (desc->sdf_mode != STOMP_SDF_NEAREST && desc->sdf_mode != STOMP_SDF_TRILINEAR) return fail("unknown sdf_mode");
   if (desc->rollout_shard_world < 1 || desc->rollout_shard_rank < 0 || desc->rollout_shard_rank >= desc->rollout_shard_world)
     return fail("bad rollout shard rank / world");
   if (desc->rollout_shard_world > 1 && (desc->num_reused_rollouts != 0 || desc->num_problems != 1))

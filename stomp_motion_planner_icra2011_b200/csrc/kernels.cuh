@@ -749,6 +749,37 @@ __device__ __forceinline__ Real voxel_distance(const void* vox, int idx, unsigne
   return Real(__ldg(static_cast<const float*>(vox) + idx));
 }
 
+// STOMP_SDF_TRILINEAR (engine extension; the reference's lookup is the nearest-cell one above): trilinear interpolation of the
+// eight cell distances around the point.  Every corner follows the nearest-cell rule (0 on / outside the outermost layer of the
+// grid), so this is the continuous extension of the reference's piecewise-constant field.  The two corners that differ only in
+// z are adjacent bytes / words, so a lane's eight gathers touch at most four sectors.  (cx, cy, cz) = the lower corner.
+template <typename Real, int kVox, typename Grid>
+__device__ __forceinline__ Real corner_distance(const Grid& g, const void* vox, int cx, int cy, int cz, unsigned sqrt_tab_addr) {
+  const bool in = (unsigned(cx - 1) < unsigned(g.nx1 - 1)) & (unsigned(cy - 1) < unsigned(g.ny1 - 1)) & (unsigned(cz - 1) < unsigned(g.nz1 - 1));
+  return in ? voxel_distance<Real, kVox>(vox, (cx * g.sny + cy) * g.snz + cz, sqrt_tab_addr, g.res) : Real(0);
+}
+template <typename Real, int kVox, typename Grid>
+__device__ __forceinline__ Real trilinear_distance(const Grid& g, const void* vox, Real px, Real py, Real pz, unsigned sqrt_tab_addr,
+                                                   int& cx, int& cy, int& cz) {
+  const Real tx = (px - g.ox) / g.res, ty = (py - g.oy) / g.res, tz = (pz - g.oz) / g.res;
+  const Real flx = floor(tx), fly = floor(ty), flz = floor(tz);
+  cx = Math<Real>::fabs_(flx) < Real(2.0e9) ? int(flx) : -1;
+  cy = Math<Real>::fabs_(fly) < Real(2.0e9) ? int(fly) : -1;
+  cz = Math<Real>::fabs_(flz) < Real(2.0e9) ? int(flz) : -1;
+  const Real fx = tx - flx, fy = ty - fly, fz = tz - flz;
+  Real acc = Real(0);
+#pragma unroll
+  for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dz = 0; dz < 2; ++dz) {
+        const Real w = (dx ? fx : Real(1) - fx) * (dy ? fy : Real(1) - fy) * (dz ? fz : Real(1) - fz);
+        acc += w * corner_distance<Real, kVox>(g, vox, cx + dx, cy + dy, cz + dz, sqrt_tab_addr);
+      }
+  return acc;
+}
+
 __device__ __forceinline__ void cta_copy_async16(void* dst_smem, const void* src, int bytes) {
   for (int off = threadIdx.x * 16; off < bytes; off += blockDim.x * 16) {
     const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(static_cast<char*>(dst_smem) + off));
@@ -766,7 +797,7 @@ __device__ __forceinline__ void cta_copy_async16(void* dst_smem, const void* src
 // plain "29 timesteps per warp" tiling; packing 2 rollouts of N = 100 needs 7 warps instead of 8.
 constexpr int kCostMaxThreads = 224;   // 7 warps; 72 registers -> 4 CTAs (28 warps) per SM
 
-template <typename Real, bool kDebug, int kVox, bool kCons>
+template <typename Real, bool kDebug, int kVox, bool kCons, bool kTri = false>
 __global__ void __launch_bounds__(kCostMaxThreads, 4) k_cost(CostArgs<Real> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = a.D, N = a.N, K = a.K, P = a.pack;
@@ -964,9 +995,14 @@ __global__ void __launch_bounds__(kCostMaxThreads, 4) k_cost(CostArgs<Real> a) {
             const Real py = F[3] * s0 + F[4] * s1 + F[5] * s2 + F[10];
             const Real pz = F[6] * s0 + F[7] * s1 + F[8] * s2 + F[11];
             int cx, cy, cz;
-            const bool inside = voxel_cells(g, px, py, pz, cx, cy, cz);
-            // outside the grid (or within one cell of its faces) the reference returns distance 0
-            const Real dist = inside ? voxel_distance<Real, kVox>(vox, (cx * g.sny + cy) * g.snz + cz, tab_addr, g.res) : Real(0);
+            Real dist;
+            if (kTri) {
+              dist = trilinear_distance<Real, kVox>(g, vox, px, py, pz, tab_addr, cx, cy, cz);
+            } else {
+              const bool inside = voxel_cells(g, px, py, pz, cx, cy, cz);
+              // outside the grid (or within one cell of its faces) the reference returns distance 0
+              dist = inside ? voxel_distance<Real, kVox>(vox, (cx * g.sny + cy) * g.snz + cz, tab_addr, g.res) : Real(0);
+            }
             // three-piece potential (stomp_collision_space.h:209-226), branch-free
             const Real radius = sp.radius, clearance = sp.clearance;
             const Real dd = dist - radius, diff = dd - clearance;

@@ -364,6 +364,7 @@ class Scenario:
     smoothness_cost_weight: float = 1e-6
     obstacle_cost_weight: float = 1.0
     use_cumulative_costs: int = 0
+    sdf_mode: int = _abi.SDF_NEAREST   # SDF_TRILINEAR: the engine's interpolated extension (not a reference mode)
 
     def desc(self, dtype=_abi.F64, device=0, keep_intermediates=0, num_problems=None,
              shard_rank=0, shard_world=1):
@@ -375,7 +376,7 @@ class Scenario:
         d.num_problems = self.num_problems if num_problems is None else num_problems
         d.dtype = dtype
         d.use_cumulative_costs = self.use_cumulative_costs
-        d.sdf_mode = _abi.SDF_NEAREST
+        d.sdf_mode = self.sdf_mode
         d.device = device
         d.rollout_shard_rank = shard_rank
         d.rollout_shard_world = shard_world

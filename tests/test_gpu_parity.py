@@ -686,3 +686,29 @@ def test_torque_and_shard_argument_errors_and_single_rank_fused_iteration():
     a.set_dynamics(0.5)
     c1, _ = a.execute(a.get(_abi.FIELD_THETA)[:, None])
     assert np.all(c1 > c0)
+
+
+@pytest.mark.parametrize("voxel_dtype", [_abi.VOXEL_U8_SQ, _abi.VOXEL_F32])
+def test_trilinear_sdf_extension_matches_the_oracle(voxel_dtype):
+    """STOMP_SDF_TRILINEAR is an engine extension (the reference looks the nearest cell up): parity is against the oracle's
+    statement of the same interpolation; full iterations run and differ from the nearest-cell mode."""
+    sc = scenes.make_scenario("tiny", num_problems=2)
+    sc.sdf_mode = _abi.SDF_TRILINEAR
+    if voxel_dtype != _abi.VOXEL_U8_SQ:
+        sc.sdf = scenes.bake_distance_field(size=(1.6, 1.6, 1.6), origin=(-0.3, -1.0, 0.0), resolution=0.04,
+                                            boxes=[((0.7, -0.3, 0.7), (0.3, 0.5, 0.06))], cylinders=[((0.5, -0.6, 0.8), 0.06, 1.0)],
+                                            max_distance=0.17, voxel_dtype=voxel_dtype)
+    eng, ors = _engine(sc), _oracles(sc)
+    params = _noisy_rollouts(sc, ors, np.random.default_rng(21), 4)
+    costs, cf = eng.execute(params, 1)
+    for b, o in enumerate(ors):
+        oc, ocf = o.execute(params[b], 1)
+        assert_close(costs[b], oc, RTOL_F64, "state costs, trilinear field")
+        np.testing.assert_array_equal(cf[b], ocf)
+    dbg = eng.execute_debug(params[0, 1])
+    odbg, _ = ors[0].execute_debug(params[0, 1])
+    np.testing.assert_array_equal(dbg["voxel"], odbg["voxel"])            # lower corner = floor: same positions to 1e-13
+    assert_close(dbg["potential"], odbg["potential"], RTOL_F64, "potential")
+    near = scenes.make_scenario("tiny", num_problems=2)
+    assert np.abs(_engine(near).execute(params, 1)[0] - costs).max() > 1e-3
+    _run_iterations(sc, 3)

@@ -283,3 +283,41 @@ def test_stomp_reduces_cost_on_the_shelf_scene():
     for it in range(2, 60):
         last = o.iterate(it)[0]
     assert last < first
+
+
+def test_trilinear_extension_is_the_continuous_version_of_the_nearest_cell_field():
+    """STOMP_SDF_TRILINEAR (engine extension): equals the reference's nearest-cell distance at cell centres, is the mean of two
+    neighbouring cells half way between them, and is continuous where the nearest-cell field jumps."""
+    from oracle.oracle import Oracle
+    sc_n = scenes.make_scenario("tiny", num_problems=1)
+    sc_t = scenes.make_scenario("tiny", num_problems=1)
+    sc_t.sdf_mode = _abi.SDF_TRILINEAR
+    rb = scenes.Robot()
+    rb.add_segment("root", -1, _abi.JOINT_FIXED, (0, 0, 0))
+    j = rb.add_segment("slide", 0, _abi.JOINT_PRISMATIC, (0.0, 0.0, 0.0), (1, 0, 0), group=0)
+    rb.spheres = [dict(segment=j, radius=0.0, clearance=10.0, pos=(0.0, 0.0, 0.0))]   # potential = 0.5 (d - c)^2 / c: monotone in d
+    rb.limits = [(0, 0.0, 0.0)]
+    res, org = sc_n.sdf.resolution, np.asarray(sc_n.sdf.origin)
+    cell = np.array([20, 12, 22])                          # inside the grid, next to the box of the tiny scene
+    base = org + cell * res
+    for sc in (sc_n, sc_t):
+        sc.robot, sc.start, sc.goal = rb, np.zeros((1, 1)), np.zeros((1, 1))
+    N = sc_n.num_time_steps
+
+    def distances(sc, xs):
+        """distance seen by a point sphere sliding along x through `base` (segment frame placed there by the prismatic joint)"""
+        rb.segments[1]["pos"] = tuple(base)
+        o = Oracle(sc, 0)
+        params = np.zeros((1, N))
+        params[0, :len(xs)] = xs
+        dbg, _ = o.execute_debug(params)
+        pot = dbg["potential"][1:1 + len(xs), 0]
+        return 10.0 - np.sqrt(2.0 * 10.0 * pot)            # invert the middle branch of the potential
+
+    xs = np.array([0.0, 0.25, 0.5, 0.75, 1.0]) * res
+    dn, dt = distances(sc_n, xs), distances(sc_t, xs)
+    np.testing.assert_allclose(dt[[0, 4]], dn[[0, 4]], rtol=0, atol=1e-12)           # cell centres: identical
+    np.testing.assert_allclose(dt[2], 0.5 * (dn[0] + dn[4]), rtol=0, atol=1e-12)     # half way: the mean
+    np.testing.assert_allclose(dt[1], 0.75 * dn[0] + 0.25 * dn[4], rtol=0, atol=1e-12)
+    assert dn[1] == dn[0] and dn[3] == dn[4]                                         # the reference field is piecewise constant
+    assert abs(dn[0] - dn[4]) > 1e-3, (dn, "pick a cell pair across which the field changes")
