@@ -388,6 +388,16 @@ def run_engine(args):
         shares[kn] = {"ms_per_iteration": m / Kp, "launches_per_iteration": n / Kp}
     eng.set_profiling(0)
     peaks, peak_kind = _peaks()
+    # algorithmic bytes per iteration of the streaming kernels: what has to cross HBM once
+    BRDN8 = B * R * D * N * 8.0
+    algo = {"k_generate": 4.0 * BRDN8,                      # per vector: read theta / previous parameters, write noise, parameters, control costs
+            "k_cumulative": BRDN8 * (2.0 + 1.0 / D),        # read control costs + state costs, write cumulative costs
+            "k_update": 2.0 * BRDN8}                        # read cumulative costs + noise
+    for kn, nbytes in algo.items():
+        ms_it = shares[kn]["ms_per_iteration"]
+        if ms_it > 0:
+            gbs = nbytes / (ms_it * 1e-3) / 1e9
+            shares[kn].update({"algorithmic_bytes_per_iteration": nbytes, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]})
     Ksph = len(sc.robot.spheres)
     vox_bytes = {0: 4, 1: 1, 2: 2}[sc.sdf.voxel_dtype]
     bytes_per_eval = D * 8 + Ksph * vox_bytes + 8 + 1

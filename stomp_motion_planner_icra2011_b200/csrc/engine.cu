@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -81,6 +82,13 @@ struct Engine {
   sh::PolicyMatrices pm;
   sh::FoldedRobot robot;
   bool have_robot = false, have_sdf = false, have_problems = false;
+  // broad phase of k_cost: sphere clusters + conservative coarse distance field (built lazily from robot + distance field)
+  struct HostCluster { int begin, end; double c[3], rho_max, need, cap_need; bool clearance_positive; };
+  std::vector<HostCluster> clusters;
+  DevBuf<unsigned char> dclusters;
+  DevBuf<float> cull_g;
+  int cull_dims[3] = {0, 0, 0};
+  bool cull_dirty = true, cull_on = false, cull_allowed = true;
   // inverse-dynamics (torque) cost term, stomp_engine_set_dynamics
   std::vector<stomp_segment> raw_segments;
   DevBuf<unsigned char> chain;
@@ -207,6 +215,47 @@ int upload_robot_tables(Engine& e) {
     n.parent = h.parent; n.type = h.type; n.q_index = h.q_index; n.save_slot = h.save_slot; n.load_slot = h.load_slot;
     n.sphere_begin = h.sphere_begin; n.sphere_end = h.sphere_end;
   }
+  // sphere clusters: runs of <= 6 consecutive spheres of a node (consecutive spheres of a link lie next to each other)
+  static const int kClusterSize = getenv("STOMP_CLUSTER_SIZE") ? std::max(1, atoi(getenv("STOMP_CLUSTER_SIZE"))) : 6;
+  e.clusters.clear();
+  for (size_t i = 0; i < nodes.size(); ++i) {
+    nodes[i].cluster_begin = int(e.clusters.size());
+    for (int b0 = e.robot.nodes[i].sphere_begin; b0 < e.robot.nodes[i].sphere_end; b0 += kClusterSize) {
+      Engine::HostCluster cl;
+      cl.begin = b0;
+      cl.end = std::min(b0 + kClusterSize, e.robot.nodes[i].sphere_end);
+      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      for (int j = cl.begin; j < cl.end; ++j)
+        for (int k = 0; k < 3; ++k) lo[k] = std::min(lo[k], e.robot.spheres[j].pos[k]), hi[k] = std::max(hi[k], e.robot.spheres[j].pos[k]);
+      for (int k = 0; k < 3; ++k) cl.c[k] = 0.5 * (lo[k] + hi[k]);
+      cl.rho_max = cl.need = cl.cap_need = 0.0;
+      cl.clearance_positive = true;
+      for (int j = cl.begin; j < cl.end; ++j) {
+        const sh::HostSphere& hs = e.robot.spheres[j];
+        const double rho = std::sqrt((hs.pos[0] - cl.c[0]) * (hs.pos[0] - cl.c[0]) + (hs.pos[1] - cl.c[1]) * (hs.pos[1] - cl.c[1]) +
+                                     (hs.pos[2] - cl.c[2]) * (hs.pos[2] - cl.c[2]));
+        cl.rho_max = std::max(cl.rho_max, rho);
+        cl.need = std::max(cl.need, rho + hs.radius + hs.clearance);
+        cl.cap_need = std::max(cl.cap_need, hs.radius + hs.clearance);
+        if (!(hs.clearance > 0.0)) cl.clearance_positive = false;
+      }
+      e.clusters.push_back(cl);
+    }
+    nodes[i].cluster_end = int(e.clusters.size());
+  }
+  e.cull_dirty = true;
+  e.cull_on = false;
+  {
+    std::vector<DevCluster<Real>> dc(std::max<size_t>(1, e.clusters.size()));
+    std::memset(dc.data(), 0, dc.size() * sizeof(DevCluster<Real>));
+    for (size_t i = 0; i < e.clusters.size(); ++i) {
+      for (int k = 0; k < 3; ++k) dc[i].c[k] = Real(e.clusters[i].c[k]);
+      dc[i].thr = std::numeric_limits<Real>::infinity();
+      dc[i].margin = Real(0);
+      dc[i].begin = e.clusters[i].begin; dc[i].end = e.clusters[i].end;
+    }
+    if (upload(e, e.dclusters, reinterpret_cast<const unsigned char*>(dc.data()), dc.size() * sizeof(DevCluster<Real>))) return 1;
+  }
   std::vector<DevSphere<Real>> sph(e.robot.spheres.size());
   for (size_t i = 0; i < sph.size(); ++i) {
     const sh::HostSphere& h = e.robot.spheres[i];
@@ -227,6 +276,95 @@ int upload_sqrt_table(Engine& e) {
   for (int i = 0; i < 256; ++i) tab[i] = Real(std::sqrt(double(i)) * e.sdf.res);  // PropagationDistanceField sqrt_table_
   if (upload(e, e.sqrt_table, reinterpret_cast<const unsigned char*>(tab.data()), tab.size() * sizeof(Real))) return 1;
   CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+// ---- broad phase of the collision cost --------------------------------------------------------------------------------
+// Valid only when the distance field IS the capped squared distance transform of its zero set (checked on the device): then
+// the uncapped transform E of that zero set bounds every lookup.  For a sphere j of a cluster with centre c:
+//   cell(x_j) is within |p_j - c| + sqrt(3) res of cell(x_c) (rigid link, two nearest-cell roundings), the coarse value
+//   looked up is the minimum of E over a 4^3 block that contains cell(x_c) or a neighbour of it (one more sqrt(3) res), and
+//   E is 1-Lipschitz between cell centres, so   E(cell(x_j)) res >= G - |p_j - c| - 2 sqrt(3) res.
+// G >= thr = max_j(|p_j - c| + r_j + clearance_j) + (2 sqrt(3) + 1) res therefore gives distance - r_j >= clearance_j for
+// every sphere: potential exactly 0, not in collision — provided the field's own cap does not bite first
+// (sqrt(cap^2) res > r_j + clearance_j, else the cluster is never culled) and all those cells are interior (margin).
+template <typename Real>
+int upload_cluster_thresholds(Engine& e, double cap_distance) {
+  std::vector<DevCluster<Real>> dc(std::max<size_t>(1, e.clusters.size()));
+  std::memset(dc.data(), 0, dc.size() * sizeof(DevCluster<Real>));
+  const double res = e.sdf.res, slack = (2.0 * std::sqrt(3.0) + 1.0) * res + 1e-9;
+  for (size_t i = 0; i < e.clusters.size(); ++i) {
+    const Engine::HostCluster& cl = e.clusters[i];
+    for (int k = 0; k < 3; ++k) dc[i].c[k] = Real(cl.c[k]);
+    const bool usable = e.cull_on && cl.clearance_positive && cap_distance - cl.cap_need > 1e-9;
+    double thr = usable ? cl.need + slack : std::numeric_limits<double>::infinity();
+    Real t = Real(thr);
+    if (double(t) < thr) t = std::nextafter(t, std::numeric_limits<Real>::infinity());
+    dc[i].thr = t;
+    dc[i].margin = Real(std::ceil(cl.rho_max / res) + 4.0);
+    dc[i].begin = cl.begin; dc[i].end = cl.end;
+  }
+  return upload(e, e.dclusters, reinterpret_cast<const unsigned char*>(dc.data()), dc.size() * sizeof(DevCluster<Real>));
+}
+
+template <typename V>
+int build_cull_field(Engine& e, int capcull, bool* ok, double* cap_distance) {
+  const int nx = e.sdf.nx, ny = e.sdf.ny, nz = e.sdf.nz;
+  const size_t cells = size_t(nx) * ny * nz;
+  DevBuf<uint8_t> occ;
+  DevBuf<uint16_t> g1, g2;
+  DevBuf<unsigned> mx;
+  DevBuf<int> mismatch;
+  CUDA_TRY(occ.alloc(cells)); CUDA_TRY(g1.alloc(cells)); CUDA_TRY(g2.alloc(cells)); CUDA_TRY(mx.alloc(1)); CUDA_TRY(mismatch.alloc(1));
+  const unsigned egrid = unsigned(std::min<size_t>((cells + 255) / 256, size_t(148) * 64));
+  const V* vox = static_cast<const V*>(e.sdf.vox);
+  k_cull_occupancy<V><<<egrid, 256, 0, e.stream>>>(cells, vox, occ.p, mx.p);
+  unsigned cap2_given = 0;
+  CUDA_TRY(cudaMemcpyAsync(&cap2_given, mx.p, sizeof(unsigned), cudaMemcpyDeviceToHost, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  capcull = std::max(capcull, int(std::ceil(std::sqrt(double(cap2_given)))) + 1);
+  if (capcull > 255) { *ok = false; return 0; }
+  k_edt_pass<0, uint16_t><<<egrid, 256, 0, e.stream>>>(nx, ny, nz, capcull, occ.p, g1.p);
+  k_edt_pass<1, uint16_t><<<egrid, 256, 0, e.stream>>>(nx, ny, nz, capcull, g1.p, g2.p);
+  k_edt_pass<2, uint16_t><<<egrid, 256, 0, e.stream>>>(nx, ny, nz, capcull, g2.p, g1.p);
+  k_cull_verify<V><<<egrid, 256, 0, e.stream>>>(cells, vox, g1.p, mx.p, mismatch.p);
+  const int cnx = (nx + 3) / 4, cny = (ny + 3) / 4, cnz = (nz + 3) / 4;
+  CUDA_TRY(e.cull_g.alloc(size_t(cnx) * cny * cnz));
+  k_cull_pool<<<unsigned((size_t(cnx) * cny * cnz + 127) / 128), 128, 0, e.stream>>>(nx, ny, nz, cnx, cny, cnz, e.sdf.res, g1.p, e.cull_g.p);
+  int bad = 0;
+  CUDA_TRY(cudaMemcpyAsync(&bad, mismatch.p, sizeof(int), cudaMemcpyDeviceToHost, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  CUDA_TRY(cudaGetLastError());
+  e.launches += 6;
+  e.cull_dims[0] = cnx; e.cull_dims[1] = cny; e.cull_dims[2] = cnz;
+  *ok = bad == 0 && cap2_given > 0;
+  *cap_distance = std::sqrt(double(cap2_given)) * e.sdf.res;
+  return 0;
+}
+
+int ensure_cull(Engine& e) {
+  if (!e.cull_dirty) return 0;
+  e.cull_dirty = false;
+  e.cull_on = false;
+  double cap_distance = 0.0;
+  const bool candidate = e.cull_allowed && e.have_robot && e.have_sdf && e.desc.sdf_mode == STOMP_SDF_NEAREST &&
+                         (e.sdf.dtype == STOMP_VOXEL_U8_SQ || e.sdf.dtype == STOMP_VOXEL_U16_SQ) && !e.clusters.empty();
+  if (candidate) {
+    CUDA_TRY(cudaStreamSynchronize(e.stream));
+    CUDA_TRY(cudaStreamSynchronize(e.tail_stream));
+    double need = 0.0;
+    for (const Engine::HostCluster& cl : e.clusters) need = std::max(need, cl.need);
+    const int capcull = int(std::ceil((need + (2.0 * std::sqrt(3.0) + 1.0) * e.sdf.res) / e.sdf.res)) + 2;
+    bool ok = false;
+    if (e.sdf.dtype == STOMP_VOXEL_U8_SQ ? build_cull_field<uint8_t>(e, capcull, &ok, &cap_distance)
+                                         : build_cull_field<uint16_t>(e, capcull, &ok, &cap_distance))
+      return 1;
+    e.cull_on = ok;
+  }
+  if (e.have_robot) {
+    if (e.f32 ? upload_cluster_thresholds<float>(e, cap_distance) : upload_cluster_thresholds<double>(e, cap_distance)) return 1;
+    CUDA_TRY(cudaStreamSynchronize(e.stream));
+  }
   return 0;
 }
 
@@ -273,7 +411,7 @@ GenArgs base_gen_args(Engine& e) {
   return a;
 }
 
-template <typename Real, bool kDebug, int kVox, bool kCons, bool kTri>
+template <typename Real, bool kDebug, int kVox, bool kCons, bool kTri, bool kCull>
 int launch_cost_k(Engine& e, CostArgs<Real>& a, int num_problems) {
   a.total_rollouts = num_problems * a.n_rollouts;
   a.params_16B = ((e.D * e.N) % 2 == 0) && (reinterpret_cast<uintptr_t>(a.params) % 16 == 0) && (a.params_problem_stride % 2 == 0) &&
@@ -284,7 +422,7 @@ int launch_cost_k(Engine& e, CostArgs<Real>& a, int num_problems) {
   auto smem_for = [&](int p, int warps) {
     return ((size_t(p) * e.D * e.N * 8 + 15) & ~size_t(15)) + size_t(e.num_nodes) * sizeof(DevNode<Real>) +
            size_t(e.K) * sizeof(DevSphere<Real>) + 256 * sizeof(Real) + size_t(warps) * 12 * 32 * sizeof(Real) +
-           e.constraints.size() * sizeof(DevConstraint<Real>);
+           e.constraints.size() * sizeof(DevConstraint<Real>) + e.clusters.size() * sizeof(DevCluster<Real>);
   };
   const int max_warps = kCostMaxThreads / 32;
   int pack = 1;
@@ -296,7 +434,7 @@ int launch_cost_k(Engine& e, CostArgs<Real>& a, int num_problems) {
   warps = std::max(warps, std::min(pack * e.D, 4));  // joint-limit pass likes a few warps
   const size_t smem = smem_for(pack, warps);
   if (smem > 220 * 1024) return fail("trajectory + robot tables exceed shared memory");
-  auto kern = k_cost<Real, kDebug, kVox, kCons, kTri>;
+  auto kern = k_cost<Real, kDebug, kVox, kCons, kTri, kCull>;
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   a.pack = pack;
   a.tiles_per_job = tiles;
@@ -311,8 +449,9 @@ int launch_cost_k(Engine& e, CostArgs<Real>& a, int num_problems) {
 // nearest-cell lookup (the reference's) or the trilinear extension, chosen at create time
 template <typename Real, bool kDebug, int kVox, bool kCons>
 int launch_cost_c(Engine& e, CostArgs<Real>& a, int num_problems) {
-  if (e.desc.sdf_mode == STOMP_SDF_TRILINEAR) return launch_cost_k<Real, kDebug, kVox, kCons, true>(e, a, num_problems);
-  return launch_cost_k<Real, kDebug, kVox, kCons, false>(e, a, num_problems);
+  if (e.desc.sdf_mode == STOMP_SDF_TRILINEAR) return launch_cost_k<Real, kDebug, kVox, kCons, true, false>(e, a, num_problems);
+  if (!kDebug && kVox != STOMP_VOXEL_F32 && e.cull_on) return launch_cost_k<Real, kDebug, kVox, kCons, false, true>(e, a, num_problems);
+  return launch_cost_k<Real, kDebug, kVox, kCons, false, false>(e, a, num_problems);
 }
 
 // the constraint evaluators are compiled out of the common (no path constraints) instantiation; the debug tap always
@@ -349,6 +488,9 @@ CostArgs<Real> base_cost_args(Engine& e) {
   a.constraint_weight = e.constraint_cost_weight;
   a.num_constraints = int(e.constraints.size());
   a.constraints = reinterpret_cast<const DevConstraint<Real>*>(e.dconstraints.p);
+  a.clusters = reinterpret_cast<const DevCluster<Real>*>(e.dclusters.p);
+  a.num_clusters = int(e.clusters.size());
+  a.cull.g = e.cull_g.p; a.cull.nx = e.cull_dims[0]; a.cull.ny = e.cull_dims[1]; a.cull.nz = e.cull_dims[2]; a.cull.enabled = e.cull_on ? 1 : 0;
   return a;
 }
 
@@ -380,6 +522,7 @@ int launch_cost_only(Engine& e, const double* params, size_t pstride, int n_roll
 int launch_cost(Engine& e, const double* params, size_t pstride, int n_rollouts, int num_problems, int include_pads,
                 double* costs, size_t cstride, int* flags, int flag_stride, int flag_offset, double* clipped,
                 stomp_sphere_debug* debug, int* cflags = nullptr) {
+  if (e.cull_dirty && ensure_cull(e)) return 1;
   const bool torque = e.torque_weight > 1e-9 && e.chain_len > 0;   // the reference's test, src/stomp_optimizer.cpp:1120
   if (torque && !clipped) {
     const size_t need = pstride * size_t(num_problems);
@@ -821,6 +964,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
       return bail(c, "cudaEventCreate");
   e.ws = e.stream;
   e.overlap = !(getenv("STOMP_NO_OVERLAP") && atoi(getenv("STOMP_NO_OVERLAP")) != 0);
+  e.cull_allowed = !(getenv("STOMP_NO_CULL") && atoi(getenv("STOMP_NO_CULL")) != 0);   // A/B switch of the k_cost broad phase
   for (int i = 0; i < 2; ++i)
     if ((c = cudaEventCreateWithFlags(&e.ev_copy_done[i], cudaEventDisableTiming)) != cudaSuccess ||
         (c = cudaEventCreateWithFlags(&e.ev_consumed[i], cudaEventDisableTiming)) != cudaSuccess)
@@ -950,6 +1094,7 @@ int stomp_engine_set_sdf(void* h, const void* voxels, int32_t nx, int32_t ny, in
   e.sdf.inv_res = 1.0 / resolution;
   if (e.f32 ? upload_sqrt_table<float>(e) : upload_sqrt_table<double>(e)) return 1;
   e.have_sdf = true;
+  e.cull_dirty = true;
   return 0;
 }
 
@@ -1046,6 +1191,7 @@ int stomp_engine_build_sdf(void* h, const double size[3], const double origin[3]
   e.sdf.inv_res = 1.0 / resolution;
   if (e.f32 ? upload_sqrt_table<float>(e) : upload_sqrt_table<double>(e)) return 1;
   e.have_sdf = true;
+  e.cull_dirty = true;
   return 0;
 }
 

@@ -46,12 +46,28 @@ template <typename Real>
 struct alignas(16) DevNode {
   Real A0[9], A1[9], A2[9], p[3], ax[3];
   int parent, type, q_index, save_slot, load_slot, sphere_begin, sphere_end, pad_;
+  int cluster_begin, cluster_end, pad2_[2];
 };
 
 template <typename Real>
 struct alignas(16) DevSphere {
   Real pos[3], radius, clearance, inv_clearance, weight;
   int original_index;
+};
+
+// Broad phase of the collision cost (exact, see k_cost): a cluster is a run of consecutive spheres of one node with a centre
+// c (node frame) and a threshold thr.  If the coarse lower bound of the distance field at the cluster centre is >= thr and the
+// centre is `margin` fine cells inside the grid, every sphere of the cluster provably has zero potential and is not in
+// collision, and a warp whose lanes all see that skips the cluster's spheres.  thr = +inf disables the test for a cluster.
+template <typename Real>
+struct alignas(16) DevCluster {
+  Real c[3], thr, margin, pad_;
+  int begin, end;       // sphere range
+};
+struct CullField {      // conservative coarse distance field: g[coarse cell] <= distance (m) of every fine cell of the 4^3 block
+  const float* g;
+  int nx, ny, nz;       // coarse dims
+  int enabled;
 };
 
 // OrientationConstraintEvaluator (src/constraint_evaluator.cpp:50-114) folded for the device: the constrained segment's
@@ -572,12 +588,16 @@ struct CostArgs {
   double* clipped;           // optional tap [same layout as params]
   stomp_sphere_debug* debug; // optional tap [N+3][K] (rollout 0 of problem 0)
   int params_16B;            // rollout rows are 16-byte aligned and D*N is even: staged with 16-byte copies
+  const DevCluster<Real>* clusters;   // sphere clusters (always a partition of the sphere table)
+  int num_clusters;
+  CullField cull;
 };
 
 template <typename Real> struct Math;
 template <> struct Math<double> {
   static __device__ __forceinline__ void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
   static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+  static __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
   static __device__ __forceinline__ double round_(double x) { return round(x); }
   static __device__ __forceinline__ double fabs_(double x) { return fabs(x); }
   static __device__ __forceinline__ double asin_(double x) { return asin(x); }
@@ -587,6 +607,7 @@ template <> struct Math<double> {
 template <> struct Math<float> {
   static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
   static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+  static __device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
   static __device__ __forceinline__ float round_(float x) { return roundf(x); }
   static __device__ __forceinline__ float fabs_(float x) { return fabsf(x); }
   static __device__ __forceinline__ float asin_(float x) { return asinf(x); }
@@ -797,7 +818,7 @@ __device__ __forceinline__ void cta_copy_async16(void* dst_smem, const void* src
 // plain "29 timesteps per warp" tiling; packing 2 rollouts of N = 100 needs 7 warps instead of 8.
 constexpr int kCostMaxThreads = 224;   // 7 warps; 72 registers -> 4 CTAs (28 warps) per SM
 
-template <typename Real, bool kDebug, int kVox, bool kCons, bool kTri = false>
+template <typename Real, bool kDebug, int kVox, bool kCons, bool kTri = false, bool kCull = false>
 __global__ void __launch_bounds__(kCostMaxThreads, 4) k_cost(CostArgs<Real> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = a.D, N = a.N, K = a.K, P = a.pack;
@@ -814,6 +835,8 @@ __global__ void __launch_bounds__(kCostMaxThreads, 4) k_cost(CostArgs<Real> a) {
   constexpr unsigned kVsStride = 32 * sizeof(Real);
   DevConstraint<Real>* cons = reinterpret_cast<DevConstraint<Real>*>(sqrt_tab + 256 + size_t(nwarps) * 12 * 32);
   const int num_cons = kCons ? a.num_constraints : 0;
+  DevCluster<Real>* clusters = reinterpret_cast<DevCluster<Real>*>(cons + num_cons);
+  cta_copy_async16(clusters, a.clusters, int(sizeof(DevCluster<Real>)) * a.num_clusters);
   cta_copy_async16(cons, a.constraints, int(sizeof(DevConstraint<Real>)) * num_cons);
   // robot tables: asynchronous 16-byte copies, all in flight together (waited for with the first trajectory)
   cta_copy_async16(nodes, a.nodes, int(sizeof(DevNode<Real>)) * a.num_nodes);
@@ -986,7 +1009,25 @@ __global__ void __launch_bounds__(kCostMaxThreads, 4) k_cost(CostArgs<Real> a) {
           // velocity frame V = sum_k rule_k/dt * F(t+k), vel(sphere) = V.R * p + V.p (linear in the frame); built
           // lazily, only when some lane of the warp has a sphere of this link inside its clearance band
           bool haveV = false;
-          for (int j = sph_begin; j < sph_end; ++j) {
+          for (int ci = nd.cluster_begin; ci < nd.cluster_end; ++ci) {
+          const DevCluster<Real>& cl = clusters[ci];
+          if (kCull) {
+            // broad phase: coarse lower bound of the distance at the cluster centre against the cluster's threshold
+            const Real qx = F[0] * cl.c[0] + F[1] * cl.c[1] + F[2] * cl.c[2] + F[9];
+            const Real qy = F[3] * cl.c[0] + F[4] * cl.c[1] + F[5] * cl.c[2] + F[10];
+            const Real qz = F[6] * cl.c[0] + F[7] * cl.c[1] + F[8] * cl.c[2] + F[11];
+            const Real ux = Math<Real>::fma_(qx, g.inv_res, g.nox) + Real(0.5);      // fine cell = floor(u)
+            const Real uy = Math<Real>::fma_(qy, g.inv_res, g.noy) + Real(0.5);
+            const Real uz = Math<Real>::fma_(qz, g.inv_res, g.noz) + Real(0.5);
+            const Real m = cl.margin;
+            const bool in = (ux >= m) & (ux <= Real(g.nx1 + 1) - m) & (uy >= m) & (uy <= Real(g.ny1 + 1) - m) & (uz >= m) &
+                            (uz <= Real(g.nz1 + 1) - m);
+            float lb = -1.0f;
+            if (in) lb = __ldg(a.cull.g + (size_t(int(ux * Real(0.25))) * a.cull.ny + int(uy * Real(0.25))) * a.cull.nz + int(uz * Real(0.25)));
+            const bool clear = Real(lb) >= cl.thr;
+            if (__all_sync(0xffffffffu, clear || !(productive || counts))) continue;
+          }
+          for (int j = cl.begin; j < cl.end; ++j) {
             const unsigned sa = sph_addr + unsigned(j) * unsigned(sizeof(DevSphere<Real>));
             typename SphereRegsOf<Real>::type sp;
             load_sphere(sa, sp);
@@ -1039,6 +1080,7 @@ __global__ void __launch_bounds__(kCostMaxThreads, 4) k_cost(CostArgs<Real> a) {
                 rec.vel_mag = (t >= 0 && t < N && lane >= 1 && lane <= kTileSteps) ? double(vm) : 0.0;
               }
             }
+          }
           }
         }
       }
@@ -1553,6 +1595,42 @@ __global__ void k_edt_pass(int nx, int ny, int nz, int cap, const void* __restri
     }
     if (kAxis == 2) out[v] = Out(min(best, cap2));
     else out[v] = Out(best > cap2 ? kInf : best);
+  }
+}
+
+// ---- broad-phase field (k_cost culling) --------------------------------------------------------------------------
+// occupancy of a squared-distance grid = its zero set
+template <typename V>
+__global__ void k_cull_occupancy(size_t cells, const V* __restrict__ vox, uint8_t* __restrict__ occ, unsigned* __restrict__ max_value) {
+  unsigned mx = 0;
+  for (size_t v = size_t(blockIdx.x) * blockDim.x + threadIdx.x; v < cells; v += size_t(gridDim.x) * blockDim.x) {
+    const unsigned val = vox[v];
+    occ[v] = val == 0 ? 1 : 0;
+    mx = max(mx, val);
+  }
+  for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(max_value, mx);
+}
+// the grid must BE the capped squared distance transform of its zero set (then the uncapped transform bounds it everywhere)
+template <typename V>
+__global__ void k_cull_verify(size_t cells, const V* __restrict__ vox, const uint16_t* __restrict__ e2, const unsigned* __restrict__ cap2_given,
+                              int* __restrict__ mismatch) {
+  const unsigned c2 = *cap2_given;
+  for (size_t v = size_t(blockIdx.x) * blockDim.x + threadIdx.x; v < cells; v += size_t(gridDim.x) * blockDim.x)
+    if (min(unsigned(e2[v]), c2) != unsigned(vox[v])) *mismatch = 1;
+}
+// g[coarse] = res * sqrt(min e2 over the 4^3 block), rounded down: a lower bound of the distance of every fine cell in the block
+__global__ void k_cull_pool(int nx, int ny, int nz, int cnx, int cny, int cnz, double res, const uint16_t* __restrict__ e2, float* __restrict__ g) {
+  const size_t total = size_t(cnx) * cny * cnz;
+  for (size_t c = size_t(blockIdx.x) * blockDim.x + threadIdx.x; c < total; c += size_t(gridDim.x) * blockDim.x) {
+    const int cz = int(c % cnz), cy = int((c / cnz) % cny), cx = int(c / (size_t(cnz) * cny));
+    unsigned best = 0xffffu;
+    for (int x = cx * 4; x < min(nx, cx * 4 + 4); ++x)
+      for (int y = cy * 4; y < min(ny, cy * 4 + 4); ++y)
+        for (int z = cz * 4; z < min(nz, cz * 4 + 4); ++z) best = min(best, unsigned(e2[(size_t(x) * ny + y) * nz + z]));
+    float d = float(res * sqrt(double(best)));
+    if (double(d) > res * sqrt(double(best))) d = nextafterf(d, 0.0f);
+    g[c] = d > 0.0f ? nextafterf(d, 0.0f) : 0.0f;
   }
 }
 

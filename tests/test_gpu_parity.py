@@ -712,3 +712,41 @@ def test_trilinear_sdf_extension_matches_the_oracle(voxel_dtype):
     near = scenes.make_scenario("tiny", num_problems=2)
     assert np.abs(_engine(near).execute(params, 1)[0] - costs).max() > 1e-3
     _run_iterations(sc, 3)
+
+
+@pytest.mark.parametrize("name", ["tiny", "C1"])
+def test_broad_phase_culling_is_exact(name, monkeypatch):
+    """k_cost skips a cluster of spheres when a conservative coarse bound of the distance field proves that all of them have
+    zero potential: costs, collision flags and whole iterations must be bit-identical to the engine without the broad phase
+    (STOMP_NO_CULL), for rollouts near obstacles, far from them, and partly outside the grid."""
+    sc = scenes.make_scenario(name, num_problems=6)
+    a = _engine(sc)
+    monkeypatch.setenv("STOMP_NO_CULL", "1")
+    b = _engine(sc)
+    monkeypatch.delenv("STOMP_NO_CULL")
+    ors = _oracles(sc)
+    rng = np.random.default_rng(31)
+    for sigma in (0.3, 2.0, 8.0):                       # 8.0 throws parts of the arm out of the grid
+        params = _noisy_rollouts(sc, ors, rng, 6, sigma=sigma)
+        for itn in (1, 2):
+            ca, fa = a.execute(params, itn)
+            cb, fb = b.execute(params, itn)
+            np.testing.assert_array_equal(ca, cb)
+            np.testing.assert_array_equal(fa, fb)
+    assert (ca == 0).any() and (ca > 0).any()
+    for it in range(1, 6):
+        a.iterate(it, stats=False)
+        b.iterate(it, stats=False)
+    for f in (_abi.FIELD_THETA, _abi.FIELD_STATE_COSTS, _abi.FIELD_ROLLOUT_TOTAL_COSTS, _abi.FIELD_COLLISION_FREE):
+        np.testing.assert_array_equal(a.get(f), b.get(f))
+    # a field that is not the distance transform of its zero set switches the broad phase off instead of trusting it
+    sc2 = scenes.make_scenario(name, num_problems=2)
+    vox = sc2.sdf.voxels.copy()
+    vox[vox.shape[0] // 2, vox.shape[1] // 2, vox.shape[2] // 2:] = 1      # a spurious "one cell from an obstacle" column
+    sc2.sdf = scenes.DistanceField(vox, sc2.sdf.origin, sc2.sdf.resolution, sc2.sdf.voxel_dtype)
+    c = _engine(sc2)
+    monkeypatch.setenv("STOMP_NO_CULL", "1")
+    d = _engine(sc2)
+    monkeypatch.delenv("STOMP_NO_CULL")
+    p2 = _noisy_rollouts(sc2, _oracles(sc2), rng, 5, sigma=2.0)
+    np.testing.assert_array_equal(c.execute(p2, 1)[0], d.execute(p2, 1)[0])
