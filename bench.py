@@ -414,7 +414,7 @@ def run_engine(args):
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
                 "algorithmic_bytes_per_eval": bytes_per_eval, "avg_launch_ms": 1e3 * avg_launch_s,
                 "kernel_share_of_step": cost_ms / all_ms if all_ms else None,
-                "binding": {"roof": "sm instruction issue", "frac": 0.60,
+                "binding": {"roof": "sm instruction issue", "frac": 0.53,
                             "source": "ncu smsp__issue_active.avg.pct_of_peak_sustained_active of the main launch, "
                                       "profiles/r1_s3_top_ncu_summary.csv"},
                 "note": "k_cost is instruction-issue bound, not HBM bound: algorithmic traffic is ~%d B/eval against ~%d fp64 flop/eval "
