@@ -280,7 +280,7 @@ def run_engine(args):
         else:
             eng_iterate = lambda i, stats=False: eng.iterate(i, stats=stats)
     else:
-        B = args.problems
+        B = args.problems or {"C1": 1, "C2": 1024, "C4": 512, "C5": 1}.get(name, 1024)
         sc = workload(name, rank, B)
         eng = Engine(sc, dtype=dtype, device=local)
         eng_iterate = lambda i, stats=False: eng.iterate(i, stats=stats)
@@ -456,7 +456,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
-    ap.add_argument("--problems", type=int, default=1024, help="planning problems per GPU")
+    ap.add_argument("--problems", type=int, default=None,
+                    help="planning problems per GPU (default: what BASELINE.json names: C1 1, C2 1024, C4 4096 / 8, C5 1)")
     ap.add_argument("--rollouts", type=int, default=65536, help="total rollouts of the C3 workload")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

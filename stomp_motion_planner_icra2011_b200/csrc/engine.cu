@@ -6,6 +6,7 @@
 // device is an error.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -89,6 +90,7 @@ struct Engine {
   DevBuf<float> cull_g;
   int cull_dims[3] = {0, 0, 0};
   bool cull_dirty = true, cull_on = false, cull_allowed = true;
+  double cull_clear_fraction = 0.0;
   // inverse-dynamics (torque) cost term, stomp_engine_set_dynamics
   std::vector<stomp_segment> raw_segments;
   DevBuf<unsigned char> chain;
@@ -360,6 +362,26 @@ int ensure_cull(Engine& e) {
                                          : build_cull_field<uint16_t>(e, capcull, &ok, &cap_distance))
       return 1;
     e.cull_on = ok;
+    if (ok) {
+      // the broad phase only pays where most of the workspace is clear of obstacles (C2: 80 % of the coarse cells clear for the
+      // median cluster, k_cost -5 %; dense clutter C4: 27 %, k_cost +6 % with it): decide from the field itself
+      std::vector<double> thr;
+      const double slack = (2.0 * std::sqrt(3.0) + 1.0) * e.sdf.res + 1e-9;
+      for (const Engine::HostCluster& cl : e.clusters)
+        if (cl.clearance_positive && cap_distance - cl.cap_need > 1e-9) thr.push_back(cl.need + slack);
+      if (thr.empty()) {
+        e.cull_on = false;
+      } else {
+        std::nth_element(thr.begin(), thr.begin() + thr.size() / 2, thr.end());
+        const double median = thr[thr.size() / 2];
+        std::vector<float> g(e.cull_g.n);
+        CUDA_TRY(cudaMemcpy(g.data(), e.cull_g.p, g.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        size_t clear = 0;
+        for (float v : g) clear += double(v) >= median;
+        e.cull_clear_fraction = g.empty() ? 0.0 : double(clear) / double(g.size());
+        e.cull_on = e.cull_clear_fraction >= 0.5;
+      }
+    }
   }
   if (e.have_robot) {
     if (e.f32 ? upload_cluster_thresholds<float>(e, cap_distance) : upload_cluster_thresholds<double>(e, cap_distance)) return 1;
