@@ -1751,6 +1751,10 @@ int stomp_engine_shard_open_peers(void* h, const void* handles, int32_t count) {
   const int W = e.desc.rollout_shard_world, rank = e.desc.rollout_shard_rank;
   if (!handles || count != W) return fail("one IPC handle per rank is required");
   if (e.xchg.n != xchg_bytes(e)) return fail("call stomp_engine_shard_ipc_handle first");
+  if (e.peers_open)   // mapping again (e.g. after a peer was re-created): drop the old mappings first
+    for (int r = 0; r < W; ++r)
+      if (r != rank && e.peer_base[r]) { cudaIpcCloseMemHandle(e.peer_base[r]); e.peer_base[r] = nullptr; }
+  e.peers_open = false;
   for (int r = 0; r < W; ++r) {
     if (r == rank) { e.peer_base[r] = e.xchg.p; continue; }
     cudaIpcMemHandle_t ipc;
