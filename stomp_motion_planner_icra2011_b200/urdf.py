@@ -38,13 +38,35 @@ _TYPES = {"revolute": _abi.JOINT_REVOLUTE, "continuous": _abi.JOINT_REVOLUTE, "p
           "fixed": _abi.JOINT_FIXED, "floating": _abi.JOINT_FIXED, "planar": _abi.JOINT_FIXED}
 
 
+def _link_inertia(link_el):
+    """<inertial> of a URDF link -> (mass, centre of mass, (ixx, iyy, izz, ixy, ixz, iyz)) in the LINK frame, the
+    KDL::RigidBodyInertia kdl_parser attaches to the link's segment: the <origin> places the inertial frame, its rotation turns
+    the inertia tensor (given about the centre of mass in the inertial frame's axes) into the link's axes."""
+    el = link_el.find("inertial")
+    if el is None or el.find("mass") is None:
+        return None
+    mass = float(el.find("mass").get("value", 0.0))
+    origin = el.find("origin")
+    xyz = _floats(origin.get("xyz") if origin is not None else None, 3, (0, 0, 0))
+    rpy = _floats(origin.get("rpy") if origin is not None else None, 3, (0, 0, 0))
+    it = el.find("inertia")
+    g = (lambda k: float(it.get(k, 0.0))) if it is not None else (lambda k: 0.0)
+    Ic = np.array([[g("ixx"), g("ixy"), g("ixz")], [g("ixy"), g("iyy"), g("iyz")], [g("ixz"), g("iyz"), g("izz")]])
+    R = np.asarray(_rpy_matrix(*rpy)).reshape(3, 3)
+    Il = R @ Ic @ R.T
+    return mass, tuple(xyz), (Il[0, 0], Il[1, 1], Il[2, 2], Il[0, 1], Il[0, 2], Il[1, 2])
+
+
 def robot_from_urdf(urdf_xml: str, group_joints, reference_frame: str, collision_links=None, collision_clearance=0.07,
-                    joint_state=None) -> Robot:
+                    joint_state=None, dynamics_chain=None) -> Robot:
     """group_joints: ordered joint names of the planning group (planning_groups.yaml);
     collision_links: {link_name: {"link_radius": r, "link_extension": e}} (config/pr2_both_arms_stomp_config.yaml:3-33);
-    joint_state: {joint_name: value} for joints outside the group (robot start state)."""
+    joint_state: {joint_name: value} for joints outside the group (robot start state);
+    dynamics_chain: (root link, tip link) of the inverse-dynamics chain (the reference hard-codes the PR2's
+    ("torso_lift_link", "r_gripper_tool_frame"), src/stomp_robot_model.cpp:183); link <inertial> blocks fill Robot.inertias."""
     root = ET.fromstring(urdf_xml)
     links = [l.get("name") for l in root.findall("link")]
+    link_inertia = {l.get("name"): _link_inertia(l) for l in root.findall("link")}
     joints = []
     for j in root.findall("joint"):
         origin = j.find("origin")
@@ -109,6 +131,12 @@ def robot_from_urdf(urdf_xml: str, group_joints, reference_frame: str, collision
         # collision_links/<link>/{link_radius, link_clearance, link_extension} (src/stomp_robot_model.cpp:361-373)
         rb.add_link_spheres(seg_of_link[link], float(cfg["link_radius"]), float(cfg.get("link_clearance", collision_clearance)),
                             float(cfg.get("link_extension", 0.0)))
+    rb.inertias = {seg_of_link[name]: val for name, val in link_inertia.items() if val is not None and name in seg_of_link}
+    if dynamics_chain is not None:
+        for name in dynamics_chain:
+            if name not in seg_of_link:
+                raise ValueError("dynamics chain link %r is not a link of the URDF" % name)
+        rb.chain = (seg_of_link[dynamics_chain[0]], seg_of_link[dynamics_chain[1]])
     # a planning group only keeps the points some group joint moves (StompPlanningGroup::addCollisionPoint, :308-334)
     rb.spheres = [s for s in rb.spheres if rb.moved_by_group(s["segment"])]
     return rb

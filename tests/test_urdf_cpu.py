@@ -116,3 +116,34 @@ def test_min_jerk_initial_trajectory():
     np.testing.assert_allclose(full, want, rtol=1e-12, atol=1e-14)
     vel = np.diff(full, axis=1) / dt
     assert np.abs(vel[:, 0]).max() < 1e-3 and np.abs(vel[:, -1]).max() < 1e-3      # zero boundary velocity
+
+
+def test_urdf_inertials_and_dynamics_chain():
+    """<inertial> blocks -> the per-segment KDL::RigidBodyInertia table of stomp_engine_set_dynamics (mass, centre of mass and
+    inertia about it in the LINK frame: the <origin> rotation turns the tensor), and the chain by link names."""
+    urdf = URDF.replace('<link name="r_upper_arm_roll_link"/>', '<link name="r_upper_arm_roll_link"><inertial><mass value="6.0"/>'
+                        '<origin xyz="0.2 0 0" rpy="0 0 1.5707963267948966"/>'
+                        '<inertia ixx="0.01" iyy="0.08" izz="0.07" ixy="0" ixz="0" iyz="0"/></inertial></link>')
+    urdf = urdf.replace('<link name="r_forearm_roll_link"/>', '<link name="r_forearm_roll_link"><inertial><mass value="2.5"/>'
+                        '<inertia ixx="0.014" iyy="0.016" izz="0.015" ixy="0.001" ixz="0" iyz="0"/></inertial></link>')
+    rb = robot_from_urdf(urdf, GROUP, "base_link", COLLISION_LINKS, 0.07, STATE, dynamics_chain=("torso_lift_link", "r_gripper_palm_link"))
+    names = [g["name"] for g in rb.segments]
+    up, fr = names.index("r_upper_arm_roll_link"), names.index("r_forearm_roll_link")
+    assert set(rb.inertias) == {up, fr}
+    m, com, ic = rb.inertias[up]
+    assert m == 6.0 and com == (0.2, 0.0, 0.0)
+    np.testing.assert_allclose(ic, (0.08, 0.01, 0.07, 0.0, 0.0, 0.0), atol=1e-15)     # a quarter turn about z swaps ixx and iyy
+    np.testing.assert_allclose(rb.inertias[fr][2], (0.014, 0.016, 0.015, 0.001, 0.0, 0.0), atol=0)
+    assert rb.chain == (names.index("torso_lift_link"), names.index("r_gripper_palm_link"))
+    arr = rb.c_inertias()
+    assert arr[up].mass == 6.0 and arr[names.index("r_elbow_flex_link")].mass == 0.0
+    with pytest.raises(ValueError):
+        robot_from_urdf(urdf, GROUP, "base_link", COLLISION_LINKS, 0.07, STATE, dynamics_chain=("torso_lift_link", "nope"))
+    # the oracle accepts the table (chain joints = the group joints in order) and gravity loads the shoulder
+    from oracle.oracle import Oracle
+    sc = scenes.make_scenario("tiny", num_problems=1)
+    sc.robot = rb
+    o = Oracle(sc, 0)
+    o.set_dynamics(1.0)
+    o.execute(o.get_parameters(), 2)
+    assert np.abs(o.last_torques()).max() > 1.0
