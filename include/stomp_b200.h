@@ -209,6 +209,11 @@ typedef struct stomp_cylinder {
 } stomp_cylinder;
 int stomp_engine_build_sdf(void* engine, const double size[3], const double origin[3], double resolution, double max_distance,
                            const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders);
+/* The same with collision-map points added: every point[num_points][3] (reference frame, metres) occupies the cell it falls
+ * into — the "points" namespace of the environment model (src/stomp_collision_space.cpp:205-213), e.g. a sensor's voxel map. */
+int stomp_engine_build_sdf_points(void* engine, const double size[3], const double origin[3], double resolution, double max_distance,
+                                  const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders,
+                                  const double* points, int64_t num_points);
 /* Copies the current voxel grid out (parity tap): dims[3], voxel dtype, and up to `bytes` of voxels (may be NULL). */
 int stomp_engine_get_sdf(void* engine, int32_t dims[3], int32_t* voxel_dtype, void* voxels, size_t bytes);
 /* Inverse-dynamics (torque) cost term of StompOptimizer::execute (src/stomp_optimizer.cpp:1117-1142, getTorques :1006-1061):

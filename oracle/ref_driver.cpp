@@ -780,7 +780,7 @@ int stomp_ref_collision_points(const stomp_segment* segs, int32_t num_segments, 
  * points fall into; returns the number of points generated (including those outside the grid). */
 long long stomp_ref_collision_object_cells(const double* size, const double* origin, double resolution, const stomp_box* boxes,
                                            int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders,
-                                           uint8_t* occupancy, int32_t* dims) {
+                                           const double* map_points, int64_t num_map_points, uint8_t* occupancy, int32_t* dims) {
   StompCollisionSpace space;
   planning_environment::CollisionSpaceMonitor monitor;
   space.monitor_ = &monitor;
@@ -802,6 +802,14 @@ long long stomp_ref_collision_object_cells(const double* size, const double* ori
     no.shape.push_back(shapes.back());
     no.shapePose.push_back(btTransform(btQuaternion(c.orientation[0], c.orientation[1], c.orientation[2], c.orientation[3]),
                                        btVector3(c.position[0], c.position[1], c.position[2])));
+  }
+  if (num_map_points > 0) {   /* the collision map arrives as the namespace "points": one (ignored) shape per point, pose = the point */
+    collision_space::EnvironmentObjects::NamespaceObjects& np = monitor.env.env_objects.objects["points"];
+    for (int64_t i = 0; i < num_map_points; ++i) {
+      shapes.push_back(new shapes::Box(resolution, resolution, resolution));
+      np.shape.push_back(shapes.back());
+      np.shapePose.push_back(btTransform(btQuaternion(0, 0, 0, 1), btVector3(map_points[3 * i], map_points[3 * i + 1], map_points[3 * i + 2])));
+    }
   }
   std::vector<btVector3> points;
   space.addCollisionObjectsToPoints(points);

@@ -305,7 +305,7 @@ def collision_points(robot, links, default_clearance=0.07, attached=(), attached
     return [(out[i].segment, out[i].radius, out[i].clearance, tuple(out[i].pos)) for i in range(cnt)]
 
 
-def collision_object_cells(size, origin, resolution, boxes=(), cylinders=()):
+def collision_object_cells(size, origin, resolution, boxes=(), cylinders=(), points=None):
     """StompCollisionSpace::addCollisionObjectsToPoints + the distance field's cell binning -> (occupancy[nx][ny][nz] bool,
     number of lattice points generated).  boxes: [(position, quaternion xyzw, dimensions)], cylinders: [(position, quaternion,
     radius, height)]."""
@@ -323,7 +323,8 @@ def collision_object_cells(size, origin, resolution, boxes=(), cylinders=()):
     occ = np.zeros(n, dtype=np.uint8)
     dims = (C.c_int32 * 3)()
     L.stomp_ref_collision_object_cells.restype = C.c_longlong
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3) if points is not None else np.zeros((0, 3))
     cnt = L.stomp_ref_collision_object_cells(_dp(sz), _dp(org), C.c_double(resolution), barr, len(boxes), carr, len(cylinders),
-                                             occ.ctypes.data_as(C.POINTER(C.c_uint8)), dims)
+                                             _dp(pts), C.c_int64(len(pts)), occ.ctypes.data_as(C.POINTER(C.c_uint8)), dims)
     assert list(dims) == n, (list(dims), n)
     return occ.astype(bool), int(cnt)

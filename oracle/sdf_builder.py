@@ -30,7 +30,7 @@ def _round_half_away(t):
     return np.where(t >= 0, np.floor(t + 0.5), np.ceil(t - 0.5))
 
 
-def build(size, origin, resolution, max_distance, boxes=(), cylinders=()):
+def build(size, origin, resolution, max_distance, boxes=(), cylinders=(), points=None):
     from scipy import ndimage
     n = [int(size[i] / resolution) for i in range(3)]
     occ = np.zeros(n, dtype=bool)
@@ -55,6 +55,10 @@ def build(size, origin, resolution, max_distance, boxes=(), cylinders=()):
     for (p, q, r, h) in cylinders:
         mark(p, q, _lattice(p[0] - r, r * 2.0, resolution), _lattice(p[1] - r, r * 2.0, resolution),
              _lattice(p[2] - h / 2.0, h, resolution), r)
+    if points is not None and len(points):       # the "points" namespace: each collision-map point occupies its cell
+        c = _round_half_away((np.asarray(points, float).reshape(-1, 3) - origin) / resolution).astype(np.int64)
+        c = c[np.all((c >= 0) & (c < np.array(n)), axis=1)]
+        occ[c[:, 0], c[:, 1], c[:, 2]] = True
     cap = int(math.ceil(max_distance / resolution))
     if occ.any():
         d = ndimage.distance_transform_edt(~occ)

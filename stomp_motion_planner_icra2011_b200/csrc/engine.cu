@@ -1138,7 +1138,14 @@ void quaternion_to_rotation(const double q[4], double R[9]) {   // KDL::Rotation
 
 int stomp_engine_build_sdf(void* h, const double size[3], const double origin[3], double resolution, double max_distance,
                            const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders) {
+  return stomp_engine_build_sdf_points(h, size, origin, resolution, max_distance, boxes, num_boxes, cylinders, num_cylinders, nullptr, 0);
+}
+
+int stomp_engine_build_sdf_points(void* h, const double size[3], const double origin[3], double resolution, double max_distance,
+                                  const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders,
+                                  const double* points, int64_t num_points) {
   ENGINE_OR_FAIL(h);
+  if (num_points < 0 || (num_points > 0 && !points)) return fail("bad collision-map points");
   if (!size || !origin || resolution <= 0.0 || max_distance <= 0.0) return fail("bad distance field specification");
   if ((num_boxes > 0 && !boxes) || (num_cylinders > 0 && !cylinders) || num_boxes < 0 || num_cylinders < 0) return fail("bad collision objects");
   const int nx = int(size[0] / resolution), ny = int(size[1] / resolution), nz = int(size[2] / resolution);
@@ -1190,6 +1197,15 @@ int stomp_engine_build_sdf(void* h, const double size[3], const double origin[3]
     k_sdf_mark<<<std::max(1u, grid), 256, 0, e.ws>>>(int(shapes.size()), total, reinterpret_cast<const SdfShape*>(dshapes.p), dlat.p,
                                                         origin[0], origin[1], origin[2], resolution, nx, ny, nz, occ.p);
     if (check_launch(e, "k_sdf_mark")) return 1;
+  }
+  if (num_points > 0) {
+    DevBuf<double> dpts;
+    if (upload(e, dpts, points, size_t(num_points) * 3)) return 1;
+    begin_launch(e);
+    k_sdf_mark_points<<<unsigned(std::min<long long>((num_points + 255) / 256, 148 * 32)), 256, 0, e.ws>>>(
+        num_points, dpts.p, origin[0], origin[1], origin[2], resolution, nx, ny, nz, occ.p);
+    if (check_launch(e, "k_sdf_mark_points")) return 1;
+    CUDA_TRY(cudaStreamSynchronize(e.stream));   // dpts goes out of scope
   }
   const bool u8 = cap * cap < 256;
   CUDA_TRY(e.vox.alloc(cells * (u8 ? 1 : 2)));

@@ -1572,6 +1572,19 @@ __global__ void k_sdf_mark(int num_shapes, long long total, const SdfShape* __re
   }
 }
 
+// collision-map points (the "points" namespace of the environment, src/stomp_collision_space.cpp:205-213): each point occupies
+// the cell it falls into
+__global__ void k_sdf_mark_points(long long total, const double* __restrict__ pts, double ox, double oy, double oz, double res, int nx,
+                                  int ny, int nz, uint8_t* __restrict__ occ) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const double tx = (pts[3 * i] - ox) / res, ty = (pts[3 * i + 1] - oy) / res, tz = (pts[3 * i + 2] - oz) / res;
+    if (!(fabs(tx) < 1e9 && fabs(ty) < 1e9 && fabs(tz) < 1e9)) continue;
+    const int cx = int(round(tx)), cy = int(round(ty)), cz = int(round(tz));
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= nx || cy >= ny || cz >= nz) continue;
+    occ[(size_t(cx) * ny + cy) * nz + cz] = 1;
+  }
+}
+
 // axis: 0 = x (input: occupancy u8 -> d^2 along x), 1 = y, 2 = z (inputs: u16 partial squared distances).
 // out[v] = min over |k| <= cap of in[v + k along axis] + k^2, saturated at cap^2 (kInf marks "nothing within cap").
 template <int kAxis, typename Out>

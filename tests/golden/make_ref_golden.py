@@ -200,10 +200,17 @@ def collision_point_case():
     return out
 
 
-def collision_cells_case():
+def map_points():
+    """a synthetic collision map: points on a tilted plane patch, some outside the grid"""
+    rng = np.random.default_rng(17)
+    uv = rng.uniform(-0.4, 0.4, (4000, 2))
+    return np.stack([0.9 + uv[:, 0], 1.2 + uv[:, 1] * 1.2, 1.0 + 0.3 * uv[:, 0] - 0.2 * uv[:, 1]], axis=1)
+
+
+def collision_cells_case(with_points=False):
     """StompCollisionSpace::addCollisionObjectsToPoints + the distance field's cell binning."""
     boxes, cyls = sdf_objects()
-    occ, npts = rp.collision_object_cells(boxes=boxes, cylinders=cyls, **SDF_SCENE)
+    occ, npts = rp.collision_object_cells(boxes=boxes, cylinders=cyls, points=map_points() if with_points else None, **SDF_SCENE)
     return {"occupancy_bits": np.packbits(occ.ravel()), "shape": np.array(occ.shape), "num_points": np.array(npts),
             "num_occupied": np.array(int(occ.sum()))}
 
@@ -227,6 +234,7 @@ def main():
     save("ref_iter_tiny_torque", iteration_case("tiny", 1, 3, torque=TORQUE_WEIGHT))
     save("ref_collision_points", collision_point_case())
     save("ref_collision_cells", collision_cells_case())
+    save("ref_collision_cells_points", collision_cells_case(with_points=True))
     save("ref_optimize_tiny_s8", optimize_case("tiny", 8, 60, 5))     # collision free at iteration 28, early exit after 33
     save("ref_optimize_tiny_s7", optimize_case("tiny", 7, 20, 6))     # never collision free: runs to max_iterations
     save("ref_optimize_c1_s8", optimize_case("C1", 8, 40, 5))        # collision free from the first iteration

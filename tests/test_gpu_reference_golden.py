@@ -166,12 +166,13 @@ def test_engine_optimize_matches_the_compiled_reference(stem, name):
 def test_engine_distance_field_occupancy_matches_the_compiled_collision_space():
     """stomp_engine_build_sdf's zero set = the cells StompCollisionSpace::addCollisionObjectsToPoints marks (bit-exact)."""
     from stomp_motion_planner_icra2011_b200 import scenes
-    from tests.golden.make_ref_golden import SDF_SCENE, sdf_objects
-    g = rg.load("ref_collision_cells")
+    from tests.golden.make_ref_golden import SDF_SCENE, map_points, sdf_objects
     boxes, cyls = sdf_objects()
     eng = _engine(scenes.make_scenario("tiny", num_problems=1))
-    eng.build_sdf(boxes=boxes, cylinders=cyls, max_distance=0.17, **SDF_SCENE)
-    got, dtype = eng.get_sdf()
-    want = np.unpackbits(g["occupancy_bits"])[:got.size].reshape(g["shape"]).astype(bool)
-    assert dtype == _abi.VOXEL_U8_SQ and got.shape == want.shape
-    np.testing.assert_array_equal(got == 0, want)
+    for stem, pts in (("ref_collision_cells", None), ("ref_collision_cells_points", map_points())):   # + a collision map
+        g = rg.load(stem)
+        eng.build_sdf(boxes=boxes, cylinders=cyls, max_distance=0.17, points=pts, **SDF_SCENE)
+        got, dtype = eng.get_sdf()
+        want = np.unpackbits(g["occupancy_bits"])[:got.size].reshape(g["shape"]).astype(bool)
+        assert dtype == _abi.VOXEL_U8_SQ and got.shape == want.shape
+        np.testing.assert_array_equal(got == 0, want)

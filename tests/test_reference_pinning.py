@@ -221,10 +221,12 @@ def test_collision_object_rasterisation_matches_the_compiled_collision_space():
     stomp_engine_build_sdf is held to oracle/sdf_builder.py on the same scene by tests/test_gpu_parity.py and to this fixture by
     tests/test_gpu_reference_golden.py.)"""
     from oracle import sdf_builder
-    from tests.golden.make_ref_golden import SDF_SCENE, sdf_objects
-    g = rg.load("ref_collision_cells")
+    from tests.golden.make_ref_golden import SDF_SCENE, map_points, sdf_objects
     boxes, cyls = sdf_objects()
-    _, occ = sdf_builder.build(boxes=boxes, cylinders=cyls, max_distance=0.17, **SDF_SCENE)
-    want = np.unpackbits(g["occupancy_bits"])[:occ.size].reshape(g["shape"]).astype(bool)
-    assert occ.shape == want.shape and int(want.sum()) == int(g["num_occupied"]) > 10000
-    np.testing.assert_array_equal(occ, want)
+    for stem, pts in (("ref_collision_cells", None), ("ref_collision_cells_points", map_points())):   # + a collision map
+        g = rg.load(stem)
+        _, occ = sdf_builder.build(boxes=boxes, cylinders=cyls, max_distance=0.17, points=pts, **SDF_SCENE)
+        want = np.unpackbits(g["occupancy_bits"])[:occ.size].reshape(g["shape"]).astype(bool)
+        assert occ.shape == want.shape and int(want.sum()) == int(g["num_occupied"]) > 10000
+        np.testing.assert_array_equal(occ, want)
+    assert int(rg.load("ref_collision_cells_points")["num_occupied"]) > int(rg.load("ref_collision_cells")["num_occupied"]) + 500
