@@ -23,6 +23,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <limits>
 #include <memory>
 #include <string>
 #include <vector>
@@ -104,6 +105,39 @@ inline void fillInMinJerk(const VectorXd& start, const VectorXd& goal, int num_f
       trajectory[j][i - 1] = v;
     }
   }
+}
+
+// ---- request pre / post-processing of StompPlannerNode::planKinematicPath (host side, either side of the path) ----------
+// angles::shortest_angular_distance(from, to): (to - from) normalised into (-pi, pi]
+inline double shortestAngularDistance(double from, double to) {
+  double a = std::fmod(std::fmod(to - from, 2.0 * M_PI) + 2.0 * M_PI, 2.0 * M_PI);   // normalize_angle_positive
+  if (a > M_PI) a -= 2.0 * M_PI;
+  return a;
+}
+// "fix the goal to move the shortest angular distance for wrap-around joints" (src/stomp_planner_node.cpp:207-217): a joint
+// without limits is a continuous one (StompJoint::wrap_around_, src/stomp_robot_model.cpp:160-162)
+inline void fixGoalForWrapAroundJoints(const VectorXd& start, VectorXd& goal, const std::vector<stomp_joint_limit>& limits) {
+  for (size_t j = 0; j < goal.size() && j < limits.size(); ++j)
+    if (!limits[j].has_limits) goal[j] = start[j] + shortestAngularDistance(start[j], goal[j]);
+}
+// time_from_start of the response trajectory (src/stomp_planner_node.cpp:257-279): points = start, the N optimised points,
+// goal; every step lasts the trajectory discretization unless a joint would exceed its velocity limit
+// (joint_velocity_limits/<joint>, default unlimited), then as long as that joint needs.  trajectory[d][t], t = 0 .. N-1.
+inline std::vector<double> timeFromStart(const VectorXd& start, const std::vector<VectorXd>& trajectory, const VectorXd& goal,
+                                         double discretization, const std::vector<double>& velocity_limits) {
+  const size_t D = trajectory.size(), N = D ? trajectory[0].size() : 0;
+  auto position = [&](size_t i, size_t j) { return i == 0 ? start[j] : (i == N + 1 ? goal[j] : trajectory[j][i - 1]); };
+  std::vector<double> t(N + 2, 0.0);
+  for (size_t i = 1; i < N + 2; ++i) {
+    double duration = discretization;
+    for (size_t j = 0; j < D; ++j) {
+      const double limit = j < velocity_limits.size() ? velocity_limits[j] : std::numeric_limits<double>::max();
+      const double d = std::fabs(position(i, j) - position(i - 1, j)) / limit;
+      if (d > duration) duration = d;
+    }
+    t[i] = t[i - 1] + duration;
+  }
+  return t;
 }
 
 // shared RAII owner of one engine handle
