@@ -120,6 +120,8 @@ struct Engine {
   std::vector<stomp_orientation_constraint> constraints;
   double constraint_cost_weight = 0.0;
   DevBuf<double> band_fw, band_bw, proj_scale, qinv_t, noise_scale;
+  DevBuf<double> dense_cinv, dense_ms;   // [N][N] C^-1 and R^-1 diag(s) for k_generate_dense (small batches)
+  bool dense_allowed = true;
   DevBuf<double> limit_min, limit_max;
   DevBuf<int> has_limits;
   DevBuf<unsigned char> nodes, spheres, sqrt_table, vox;
@@ -705,7 +707,21 @@ int launch_generate_range(Engine& e, const RolloutPlan& p, int r_begin, int r_co
   a.r_count = r_count;
   const bool uses_injection = p.injected && r_begin < e.num_gen;
   if (uses_injection) CUDA_TRY(cudaStreamWaitEvent(e.ws, e.ev_copy_done[e.inject_pending_buf], 0));
-  if (launch_generate(e, a)) return 1;
+  // small batches: the dense formulation (a few microseconds of latency) instead of the serial band solves (~N microseconds).
+  // Rough cost models of the two kernels on a B200 decide: the band kernel is one wave of ~0.95 us per timestep, the dense
+  // one streams 1.5 N^2 matrix elements per vector out of L2 (measured: C1 0.149 -> 0.097 ms per iteration with it, but
+  // C5's 15 360 vectors of N = 300 0.72 -> 2.44 ms, hence the factor of two in favour of the band kernel)
+  const double nvec = double(e.B) * r_count * e.D;
+  const double est_band = 0.95e-6 * e.N;
+  const double est_dense = 5.0e-6 + nvec * 12.0 * double(e.N) * e.N / 4.0e12;
+  if (e.dense_allowed && e.N <= 1024 && est_dense < 0.5 * est_band) {
+    const size_t smem = (size_t(3) * e.N + 2 * kPad) * 8;
+    begin_launch(e);
+    k_generate_dense<<<unsigned(nvec), 128, smem, e.ws>>>(a, e.dense_cinv.p, e.dense_ms.p);
+    if (check_launch(e, "k_generate")) return 1;
+  } else if (launch_generate(e, a)) {
+    return 1;
+  }
   if (uses_injection) CUDA_TRY(cudaEventRecord(e.ev_consumed[e.inject_pending_buf], e.ws));
   return 0;
 }
@@ -1026,6 +1042,27 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
     delete ep;
     return 1;
   }
+  {
+    // dense forms of the two solves for the small-batch kernel: C^-1 (column k = forward substitution of e_k) and R^-1 diag(s)
+    const int N = e.N, hb = e.pm.chol.hb;
+    std::vector<double> cinv(size_t(N) * N, 0.0), msd(size_t(N) * N, 0.0), x(N);
+    for (int k = 0; k < N; ++k) {
+      std::fill(x.begin(), x.end(), 0.0);
+      for (int i = k; i < N; ++i) {
+        double s = i == k ? 1.0 : 0.0;
+        for (int j = 1; j <= hb && i - j >= k; ++j) s -= e.pm.chol.band[size_t(i) * (hb + 1) + j] * x[i - j];
+        x[i] = s * e.pm.chol.inv_diag[i];
+        cinv[size_t(i) * N + k] = x[i];
+      }
+    }
+    for (int j = 0; j < N; ++j)
+      for (int t = 0; t < N; ++t) msd[size_t(j) * N + t] = e.pm.Rinv(j, t) * e.pm.proj_scale[j];
+    if (upload(e, e.dense_cinv, cinv.data(), cinv.size()) || upload(e, e.dense_ms, msd.data(), msd.size())) {
+      delete ep;
+      return 1;
+    }
+  }
+  e.dense_allowed = !(getenv("STOMP_NO_DENSE") && atoi(getenv("STOMP_NO_DENSE")) != 0);   // A/B switch of k_generate_dense
   e.noise_stddev.assign(e.D, 1.0);
   e.noise_decay.assign(e.D, 1.0);
   std::vector<int> hl(e.D, 0);

@@ -550,6 +550,110 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_generate_dense: the same noise / parameters / M*noise / control costs as k_generate for SMALL batches, where k_generate's
+// one-thread-per-vector band solves are a serial chain of ~4 N steps with nothing to hide it behind (one planning problem:
+// 35 vectors).  One CTA per vector, one thread per timestep, and the two triangular solves written as the dense products
+// they stand for — exactly the reference's formulation (MultivariateGaussian: L z; projection: M eps):
+//   eps_t = sigma * sum_{j >= t} Cinv[j][t] z_j          (eps = sigma C^-T z, the same linear map and the same Philox z
+//                                                          as the band path: realisations agree to rounding)
+//   y_t   = sum_j Ms[j][t] eps_j,  Ms[j][t] = R^-1[j][t] s_j  (R^-1 symmetric: rows read with t across the lanes)
+// followed by the control-cost stencils over [pads, parameters + y, pads].  N^2 flops per vector instead of ~20 N, but a
+// few microseconds of latency instead of ~N microseconds.  engine.cu picks the kernel from the batch size.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_generate_dense(GenArgs a, const double* __restrict__ cinv, const double* __restrict__ ms) {
+  extern __shared__ double dsm[];
+  const int N = a.N, Nall = N + 2 * kPad;
+  double* z = dsm;            // [N] standard normals, then reused for nothing else
+  double* e = z + N;          // [N] noise
+  double* xs = e + N;         // [Nall] padded x = parameters + M noise
+  const int per_problem = a.r_count * a.D;
+  const int v = blockIdx.x;
+  const int b = v / per_problem, rem = v - b * per_problem;
+  const int r = a.r_begin + rem / a.D, d = rem % a.D;
+  const size_t row_off = ((size_t(b) * a.R + r) * a.D + d) * N;
+  const double* th = a.theta + (size_t(b) * a.D + d) * N;
+  const bool is_new = r < a.R_gen;
+  const bool philox = is_new && !a.injected;
+  const double* src = nullptr;
+  if (!is_new) {
+    const int sidx = a.reuse_src[size_t(b) * (a.R - a.R_gen) + (r - a.R_gen)];
+    src = sidx >= 0 ? a.params_prev + ((size_t(b) * a.R + sidx) * a.D + d) * N : th;
+  }
+  if (philox) {
+    const uint64_t stream = (uint64_t(b) * uint64_t(a.rollouts_global) + uint64_t(a.rollout_id_offset + r)) * uint64_t(a.D) + d;
+    for (int pr = threadIdx.x; 2 * pr < N; pr += blockDim.x) {
+      double z0, z1;
+      normal_pair(a.seed, stream, a.iteration, uint32_t(pr), z0, z1);
+      z[2 * pr] = z0;
+      if (2 * pr + 1 < N) z[2 * pr + 1] = z1;
+    }
+    __syncthreads();
+    const double sg = a.noise_scale[d];
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+      double a0 = 0.0, a1 = 0.0;
+      int j = t;
+      for (; j + 1 < N; j += 2) {
+        a0 = fma(cinv[size_t(j) * N + t], z[j], a0);
+        a1 = fma(cinv[size_t(j + 1) * N + t], z[j + 1], a1);
+      }
+      if (j < N) a0 = fma(cinv[size_t(j) * N + t], z[j], a0);
+      e[t] = sg * (a0 + a1);
+    }
+  } else if (is_new) {
+    for (int t = threadIdx.x; t < N; t += blockDim.x) e[t] = a.eps_in[row_off + t];
+  } else {
+    for (int t = threadIdx.x; t < N; t += blockDim.x) e[t] = src[t] - th[t];   // policy_improvement.cpp:222
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < N; t += blockDim.x) {
+    const double ev = e[t];
+    const double pv = is_new ? th[t] + ev : src[t];
+    a.noise[row_off + t] = ev;
+    a.params[row_off + t] = pv;
+    if (!a.mode_control) continue;
+    double a0 = 0.0, a1 = 0.0;
+    int j = 0;
+    for (; j + 1 < N; j += 2) {
+      a0 = fma(ms[size_t(j) * N + t], e[j], a0);
+      a1 = fma(ms[size_t(j + 1) * N + t], e[j + 1], a1);
+    }
+    if (j < N) a0 = fma(ms[size_t(j) * N + t], e[j], a0);
+    const double y = a0 + a1;
+    if (a.noise_projected) a.noise_projected[row_off + t] = y;
+    xs[kPad + t] = pv + y;
+  }
+  for (int q = threadIdx.x; q < kPad; q += blockDim.x) {
+    xs[q] = a.pad_start[size_t(b) * a.D + d];
+    xs[kPad + N + q] = a.pad_goal[size_t(b) * a.D + d];
+  }
+  if (!a.mode_control) return;
+  __syncthreads();
+  auto row_cost = [&](int p) -> double {     // padded row p; taps outside [0, Nall) are the dropped ones
+    double cost = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (a.st.weight[k] == 0.0) continue;
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int idx = p + j - 3;
+        acc += a.st.coef[k][j] * ((idx < 0 || idx >= Nall) ? 0.0 : xs[idx]);
+      }
+      cost += a.control_weight * a.st.weight[k] * (acc * acc);
+    }
+    return cost;
+  };
+  for (int t = threadIdx.x; t < N; t += blockDim.x) {
+    double cost = row_cost(kPad + t);
+    if (t == 0)
+      for (int q = 0; q < kPad; ++q) cost += row_cost(q);
+    if (t == N - 1)
+      for (int q = 0; q < kPad; ++q) cost += row_cost(kPad + N + (kPad - 1 - q));
+    a.control[row_off + t] = cost;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_cost: the cost plugin.  One CTA per rollout; each warp owns a tile of 29 free timesteps
 // (lane l <-> timestep tile*29 - 1 + l), so the finite-difference velocity taps (-1, 0, +1, +2) of the
 // productive lanes 1..29 come from neighbouring lanes by warp shuffle and no sphere position ever leaves

@@ -1,6 +1,9 @@
 """Shared helpers of the parity tests: seeded noise drawn on the host exactly the way the reference's
 MultivariateGaussian does (eps = sigma * chol(R^-1) * z), so that the oracle and the engine receive
 identical injected noise (BASELINE.json north_star: host-injection mode)."""
+import contextlib
+import os
+
 import numpy as np
 
 from stomp_motion_planner_icra2011_b200 import _abi
@@ -28,3 +31,18 @@ def assert_close(actual, desired, rtol, what, atol_scale=1e-9):
 
 def oracle_batch(oracle_mod, sc):
     return [oracle_mod.Oracle(sc, b) for b in range(sc.start.shape[0])]
+
+
+@contextlib.contextmanager
+def band_solves_only():
+    """Engines created inside always use k_generate's band solves (STOMP_NO_DENSE is read at stomp_engine_create); small
+    batches otherwise take k_generate_dense, and the bench-size path would go untested by the small parity cases."""
+    old = os.environ.get("STOMP_NO_DENSE")
+    os.environ["STOMP_NO_DENSE"] = "1"
+    try:
+        yield
+    finally:
+        if old is None:
+            del os.environ["STOMP_NO_DENSE"]
+        else:
+            os.environ["STOMP_NO_DENSE"] = old

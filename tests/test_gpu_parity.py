@@ -7,13 +7,16 @@ import numpy as np
 import pytest
 
 from stomp_motion_planner_icra2011_b200 import _abi, scenes
-from tests.helpers import RTOL_F64, RTOL_F32, assert_close, correlated_noise, oracle_batch
+from tests.helpers import RTOL_F64, RTOL_F32, assert_close, correlated_noise, oracle_batch, band_solves_only
 
 pytestmark = pytest.mark.gpu
 
 
-def _engine(sc, **kw):
+def _engine(sc, band_only=False, **kw):
     from stomp_motion_planner_icra2011_b200.engine import Engine
+    if band_only:
+        with band_solves_only():
+            return Engine(sc, **kw)
     return Engine(sc, **kw)
 
 
@@ -103,7 +106,10 @@ def test_forward_kinematics_random_trees(seed):
 
 
 def _run_iterations(sc, iterations, dtype=_abi.F64, check=True, rtol=RTOL_F64):
-    eng, ors = _engine(sc, dtype=dtype, keep_intermediates=1), _oracles(sc)
+    # both generation kernels against the oracle: the one the batch size selects (k_generate_dense for these small cases) and
+    # the band solves the bench-size batches run
+    engines = [_engine(sc, dtype=dtype, keep_intermediates=1), _engine(sc, band_only=True, dtype=dtype, keep_intermediates=1)]
+    ors = _oracles(sc)
     rng = np.random.default_rng(11)
     L = ors[0].get(_abi.FIELD_NOISE_CHOLESKY)
     B, D = sc.start.shape
@@ -116,21 +122,25 @@ def _run_iterations(sc, iterations, dtype=_abi.F64, check=True, rtol=RTOL_F64):
         sigma = sc.noise_stddev * sc.noise_decay ** (it - 1)
         ngen = sc.num_rollouts if it == 1 else sc.num_rollouts - sc.num_reused_rollouts
         eps = correlated_noise(L, rng, (B, ngen), sigma)
-        eng.inject_noise(eps)
-        cost, cf, g = eng.iterate(it)
-        assert g == ngen
+        res = []
+        for eng in engines:
+            eng.inject_noise(eps)
+            cost, cf, g = eng.iterate(it)
+            assert g == ngen
+            res.append((cost, cf))
         for b, o in enumerate(ors):
             oc, ocf, og = o.iterate(it, eps[b])
             assert og == ngen
             if not check:
                 continue
-            for f, nm in fields:
-                assert_close(eng.get(f)[b], o.get(f), rtol, "%s, iteration %d, problem %d" % (nm, it, b))
-            assert_close(cost[b], oc, rtol, "noiseless cost")
-            assert cf[b] == ocf
-            ecf, orcf = eng.get(_abi.FIELD_COLLISION_FREE)[b], o.get(_abi.FIELD_COLLISION_FREE)
-            np.testing.assert_array_equal(ecf[:ngen], orcf[:ngen])
-    return eng, ors
+            for eng, (cost, cf) in zip(engines, res):
+                for f, nm in fields:
+                    assert_close(eng.get(f)[b], o.get(f), rtol, "%s, iteration %d, problem %d" % (nm, it, b))
+                assert_close(cost[b], oc, rtol, "noiseless cost")
+                assert cf[b] == ocf
+                ecf, orcf = eng.get(_abi.FIELD_COLLISION_FREE)[b], o.get(_abi.FIELD_COLLISION_FREE)
+                np.testing.assert_array_equal(ecf[:ngen], orcf[:ngen])
+    return engines[0], ors
 
 
 @pytest.mark.parametrize("name,cumulative", [("tiny", 0), ("tiny", 1), ("C1", 0), ("C1", 1)])
@@ -305,7 +315,7 @@ def test_c5_thirty_dof_chain_shape():
     _run_iterations(sc, 2)
 
 
-def test_full_size_batch_properties():
+def test_full_size_batch_properties(monkeypatch):
     """BASELINE configs[1] at full size (1024 problems): size-independent properties.
     (a) every problem of the batch evolves exactly as it does when planned alone (problems are independent);
     (b) probabilities sum to one over rollouts; (c) reused rollouts keep their state costs and parameters."""
@@ -313,7 +323,11 @@ def test_full_size_batch_properties():
     assert sc.start.shape[0] == 1024
     big = _engine(sc, keep_intermediates=1)
     picks = [0, 511, 1023]
+    # bit-exact comparison: both engines on the band-solve kernel (a 3-problem batch would take k_generate_dense, which agrees
+    # to rounding only — test_small_batch_dense_generation_matches_the_band_solves)
+    monkeypatch.setenv("STOMP_NO_DENSE", "1")
     small = _engine(sc, keep_intermediates=1, problems=picks)
+    monkeypatch.delenv("STOMP_NO_DENSE")
     rng = np.random.default_rng(21)
     L = np.linalg.cholesky(big.get(_abi.FIELD_INV_CONTROL_COST))
     D = sc.robot.num_dimensions
@@ -750,3 +764,33 @@ def test_broad_phase_culling_is_exact(name, monkeypatch):
     monkeypatch.delenv("STOMP_NO_CULL")
     p2 = _noisy_rollouts(sc2, _oracles(sc2), rng, 5, sigma=2.0)
     np.testing.assert_array_equal(c.execute(p2, 1)[0], d.execute(p2, 1)[0])
+
+
+@pytest.mark.parametrize("name,problems", [("tiny", 2), ("C1", 1)])
+def test_small_batch_dense_generation_matches_the_band_solves(name, problems, monkeypatch):
+    """Small batches take k_generate_dense (eps = sigma C^-T z and M eps as dense products) instead of k_generate's serial band
+    solves: the same linear maps on the same Philox normals, so noise, parameters, M*noise and control costs agree to
+    rounding — with the engine's own noise (iterations with and without reuse) and with injected noise."""
+    sc = scenes.make_scenario(name, num_problems=problems)
+    a = _engine(sc, keep_intermediates=1)
+    monkeypatch.setenv("STOMP_NO_DENSE", "1")
+    b = _engine(sc, keep_intermediates=1)
+    monkeypatch.delenv("STOMP_NO_DENSE")
+    fields = (_abi.FIELD_NOISE, _abi.FIELD_PARAMETERS, _abi.FIELD_NOISE_PROJECTED, _abi.FIELD_CONTROL_COSTS)
+    for it in (1, 2, 3):
+        a.iterate(it, stats=False)
+        b.iterate(it, stats=False)
+        for f in fields:
+            x, y = a.get(f), b.get(f)
+            scale = np.abs(y).max() + 1e-300
+            assert np.abs(x - y).max() <= 1e-9 * scale, (it, f, np.abs(x - y).max(), scale)
+        assert_close(a.get(_abi.FIELD_THETA), b.get(_abi.FIELD_THETA), 1e-7, "theta after iteration %d" % it)
+    rng = np.random.default_rng(5)
+    eps = 0.05 * rng.standard_normal(a.get(_abi.FIELD_NOISE).shape)
+    for e in (a, b):
+        e.set_problems(sc.start, sc.goal)
+        e.inject_noise(eps)
+        e.iterate(1, stats=False)
+    for f in fields:
+        x, y = a.get(f), b.get(f)
+        assert np.abs(x - y).max() <= 1e-9 * (np.abs(y).max() + 1e-300), f

@@ -11,13 +11,16 @@ import pytest
 
 from stomp_motion_planner_icra2011_b200 import _abi
 from tests import ref_golden as rg
-from tests.helpers import RTOL_F64, assert_close
+from tests.helpers import RTOL_F64, assert_close, band_solves_only
 
 pytestmark = pytest.mark.gpu
 
 
-def _engine(sc, **kw):
+def _engine(sc, band_only=False, **kw):
     from stomp_motion_planner_icra2011_b200.engine import Engine
+    if band_only:
+        with band_solves_only():
+            return Engine(sc, **kw)
     return Engine(sc, **kw)
 
 
@@ -53,11 +56,12 @@ def _check_iterations(sc, g, eng):
         yield it, k
 
 
+@pytest.mark.parametrize("band_only", [False, True], ids=["dense", "band"])   # both generation kernels (see helpers.band_solves_only)
 @pytest.mark.parametrize("name,cumulative", [("tiny", 0), ("tiny", 1), ("C1", 1), ("C1", 0)])
-def test_engine_reproduces_the_reference_iterations(name, cumulative):
+def test_engine_reproduces_the_reference_iterations(name, cumulative, band_only):
     g = rg.load("ref_iter_%s_c%d" % (name.lower(), cumulative))
     sc = rg.scenario(name, g, cumulative)
-    assert len(list(_check_iterations(sc, g, _engine(sc, keep_intermediates=1)))) >= 2
+    assert len(list(_check_iterations(sc, g, _engine(sc, band_only=band_only, keep_intermediates=1)))) >= 2
 
 
 def test_engine_reproduces_the_reference_iterations_with_orientation_constraints():
