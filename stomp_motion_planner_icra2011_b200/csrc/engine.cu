@@ -121,7 +121,7 @@ struct Engine {
   double constraint_cost_weight = 0.0;
   DevBuf<double> band_fw, band_bw, proj_scale, qinv_t, noise_scale;
   DevBuf<double> dense_cinv, dense_ms;   // [N][N] C^-1 and R^-1 diag(s) for k_generate_dense (small batches)
-  bool dense_allowed = true;
+  int gen_mode = 0;   // 0: pick k_generate / k_generate_dense by batch shape; 1, 2: always that one (A/B)
   DevBuf<double> limit_min, limit_max;
   DevBuf<int> has_limits;
   DevBuf<unsigned char> nodes, spheres, sqrt_table, vox;
@@ -707,14 +707,18 @@ int launch_generate_range(Engine& e, const RolloutPlan& p, int r_begin, int r_co
   a.r_count = r_count;
   const bool uses_injection = p.injected && r_begin < e.num_gen;
   if (uses_injection) CUDA_TRY(cudaStreamWaitEvent(e.ws, e.ev_copy_done[e.inject_pending_buf], 0));
-  // small batches: the dense formulation (a few microseconds of latency) instead of the serial band solves (~N microseconds).
-  // Rough cost models of the two kernels on a B200 decide: the band kernel is one wave of ~0.95 us per timestep, the dense
-  // one streams 1.5 N^2 matrix elements per vector out of L2 (measured: C1 0.149 -> 0.097 ms per iteration with it, but
-  // C5's 15 360 vectors of N = 300 0.72 -> 2.44 ms, hence the factor of two in favour of the band kernel)
+  // Two kernels produce the same outputs (the same linear maps on the same Philox normals; they agree to rounding):
+  //  * k_generate_dense — one CTA per vector, a few microseconds of latency: small batches (one planning problem = 35 vectors)
+  //  * k_generate       — serial band solves, ~0.95 us per timestep whatever the batch: everything else
+  // (measured on a B200: C1 0.149 -> 0.097 ms per iteration with the dense kernel, but C5's 15 360 vectors of N = 300
+  // 0.72 -> 2.44 ms, since every CTA streams 1.5 N^2 matrix elements from L2; a register-tiled variant sharing the matrices
+  // between 32 vectors was bound by shared-memory operand bandwidth and lost everywhere: profiles/README.md)
   const double nvec = double(e.B) * r_count * e.D;
   const double est_band = 0.95e-6 * e.N;
   const double est_dense = 5.0e-6 + nvec * 12.0 * double(e.N) * e.N / 4.0e12;
-  if (e.dense_allowed && e.N <= 1024 && est_dense < 0.5 * est_band) {
+  int kind = e.gen_mode;
+  if (kind == 0) kind = (e.N <= 1024 && est_dense < 0.5 * est_band) ? 2 : 1;
+  if (kind == 2) {
     const size_t smem = (size_t(3) * e.N + 2 * kPad) * 8;
     begin_launch(e);
     k_generate_dense<<<unsigned(nvec), 128, smem, e.ws>>>(a, e.dense_cinv.p, e.dense_ms.p);
@@ -1062,7 +1066,9 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
       return 1;
     }
   }
-  e.dense_allowed = !(getenv("STOMP_NO_DENSE") && atoi(getenv("STOMP_NO_DENSE")) != 0);   // A/B switch of k_generate_dense
+  // A/B switches of the generation kernels: STOMP_GENERATE=band|dense forces one, STOMP_NO_DENSE=1 is "band"
+  if (const char* g = getenv("STOMP_GENERATE")) e.gen_mode = !strcmp(g, "band") ? 1 : !strcmp(g, "dense") ? 2 : 0;
+  if (getenv("STOMP_NO_DENSE") && atoi(getenv("STOMP_NO_DENSE")) != 0) e.gen_mode = 1;
   e.noise_stddev.assign(e.D, 1.0);
   e.noise_decay.assign(e.D, 1.0);
   std::vector<int> hl(e.D, 0);

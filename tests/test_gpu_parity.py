@@ -324,7 +324,7 @@ def test_full_size_batch_properties(monkeypatch):
     big = _engine(sc, keep_intermediates=1)
     picks = [0, 511, 1023]
     # bit-exact comparison: both engines on the band-solve kernel (a 3-problem batch would take k_generate_dense, which agrees
-    # to rounding only — test_small_batch_dense_generation_matches_the_band_solves)
+    # to rounding only — test_dense_generation_kernels_match_the_band_solves)
     monkeypatch.setenv("STOMP_NO_DENSE", "1")
     small = _engine(sc, keep_intermediates=1, problems=picks)
     monkeypatch.delenv("STOMP_NO_DENSE")
@@ -766,16 +766,22 @@ def test_broad_phase_culling_is_exact(name, monkeypatch):
     np.testing.assert_array_equal(c.execute(p2, 1)[0], d.execute(p2, 1)[0])
 
 
-@pytest.mark.parametrize("name,problems", [("tiny", 2), ("C1", 1)])
-def test_small_batch_dense_generation_matches_the_band_solves(name, problems, monkeypatch):
+@pytest.mark.parametrize("name,problems,kernel", [("tiny", 2, "dense"), ("C1", 1, "dense"), ("C5", 1, "dense")])
+def test_dense_generation_kernels_match_the_band_solves(name, problems, kernel, monkeypatch):
     """Small batches take k_generate_dense (eps = sigma C^-T z and M eps as dense products) instead of k_generate's serial band
-    solves: the same linear maps on the same Philox normals, so noise, parameters, M*noise and control costs agree to
-    rounding — with the engine's own noise (iterations with and without reuse) and with injected noise."""
-    sc = scenes.make_scenario(name, num_problems=problems)
+    solves: the same linear maps on the same Philox normals, so noise, parameters, M*noise and control costs agree to rounding
+    — with the engine's own noise (iterations with and without reuse) and with injected noise.  C5 has 300 timesteps (several
+    passes of the CTA over time; R^-1 is worse conditioned, hence the looser bound)."""
+    tol = 1e-7 if name == "C5" else 1e-9
+    kw = dict(num_rollouts=12) if name == "C5" else {}
+    sc = scenes.make_scenario(name, num_problems=problems, **kw)
+    if name == "C5":
+        sc.num_reused_rollouts = 4
+    monkeypatch.setenv("STOMP_GENERATE", kernel)
     a = _engine(sc, keep_intermediates=1)
-    monkeypatch.setenv("STOMP_NO_DENSE", "1")
+    monkeypatch.setenv("STOMP_GENERATE", "band")
     b = _engine(sc, keep_intermediates=1)
-    monkeypatch.delenv("STOMP_NO_DENSE")
+    monkeypatch.delenv("STOMP_GENERATE")
     fields = (_abi.FIELD_NOISE, _abi.FIELD_PARAMETERS, _abi.FIELD_NOISE_PROJECTED, _abi.FIELD_CONTROL_COSTS)
     for it in (1, 2, 3):
         a.iterate(it, stats=False)
@@ -783,7 +789,7 @@ def test_small_batch_dense_generation_matches_the_band_solves(name, problems, mo
         for f in fields:
             x, y = a.get(f), b.get(f)
             scale = np.abs(y).max() + 1e-300
-            assert np.abs(x - y).max() <= 1e-9 * scale, (it, f, np.abs(x - y).max(), scale)
+            assert np.abs(x - y).max() <= tol * scale, (it, f, np.abs(x - y).max(), scale)
         assert_close(a.get(_abi.FIELD_THETA), b.get(_abi.FIELD_THETA), 1e-7, "theta after iteration %d" % it)
     rng = np.random.default_rng(5)
     eps = 0.05 * rng.standard_normal(a.get(_abi.FIELD_NOISE).shape)
@@ -793,4 +799,4 @@ def test_small_batch_dense_generation_matches_the_band_solves(name, problems, mo
         e.iterate(1, stats=False)
     for f in fields:
         x, y = a.get(f), b.get(f)
-        assert np.abs(x - y).max() <= 1e-9 * (np.abs(y).max() + 1e-300), f
+        assert np.abs(x - y).max() <= tol * (np.abs(y).max() + 1e-300), f
