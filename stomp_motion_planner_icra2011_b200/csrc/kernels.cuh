@@ -1459,6 +1459,7 @@ __global__ void k_extra_total(int R, int D, int N, const double* __restrict__ st
 struct UpdateArgs {
   int R, D, N, apply;
   int dims_per_cta;          // a CTA handles dims [g*dims_per_cta, ...) of one problem
+  int pre_reduced;           // 1: a.updates already holds the weighted noise (k_rollout_weights)
   const double* cumulative;  // [B][R][D][N]
   const double* noise;       // [B][R][D][N]
   double* probabilities;     // optional tap
@@ -1472,6 +1473,77 @@ struct UpdateArgs {
   double control_weight;     // 0.5 * control_cost_weight
   Stencil st;
 };
+
+// One (problem, dimension, timestep) element of the PI^2 update (policy_improvement.cpp:283-340): min / max of the cumulative
+// costs over rollouts, exp(-10 (c - min) / (max - min)) weights, probability-weighted noise.  Rollouts are visited in groups
+// of kGroup with all loads of a group issued before the first use (the loop count is a run-time value, so the compiler does
+// not software-pipeline it; ncu showed 45 % of the stalls on these loads).  kCache: R <= kGroup, every value is loaded once,
+// up front, and both passes run from registers — one memory round trip per element.  Same operations in the same order in
+// every instantiation: results do not depend on which one ran.
+template <int kGroup, bool kCache>
+__device__ __forceinline__ double weighted_noise(const double* __restrict__ c, const double* __restrict__ e, size_t rstride, int R,
+                                                 double* __restrict__ prob_out) {
+  double cc[kCache ? kGroup : 1], ec[kCache ? kGroup : 1];
+  if (kCache) {
+#pragma unroll
+    for (int j = 0; j < kGroup; ++j) {
+      const bool in = j < R;
+      cc[j] = in ? c[j * rstride] : 0.0;
+      ec[j] = in ? e[j * rstride] : 0.0;
+    }
+  }
+  double mn = kCache ? cc[0] : c[0], mx = mn;
+  for (int r0 = 0; r0 < R; r0 += kGroup) {
+    double cv[kGroup];
+#pragma unroll
+    for (int j = 0; j < kGroup; ++j) cv[j] = r0 + j < R ? (kCache ? cc[j] : c[(r0 + j) * rstride]) : mn;
+#pragma unroll
+    for (int j = 0; j < kGroup; ++j) {
+      if (cv[j] < mn) mn = cv[j];
+      if (cv[j] > mx) mx = cv[j];
+    }
+  }
+  double denom = mx - mn;
+  if (denom < 1e-8) denom = 1e-8;
+  const double h = -10.0 / denom;
+  double p_sum = 0.0, acc = 0.0;
+  for (int r0 = 0; r0 < R; r0 += kGroup) {
+    double cv[kGroup], ev[kGroup];
+#pragma unroll
+    for (int j = 0; j < kGroup; ++j) {
+      const bool in = r0 + j < R;
+      cv[j] = in ? (kCache ? cc[j] : c[(r0 + j) * rstride]) : 0.0;
+      ev[j] = in ? (kCache ? ec[j] : e[(r0 + j) * rstride]) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < kGroup; ++j)
+      if (r0 + j < R) {
+        const double w = exp(h * (cv[j] - mn));
+        p_sum += w;
+        acc += ev[j] * w;
+      }
+  }
+  const double inv = 1.0 / p_sum;
+  if (prob_out)
+    for (int r = 0; r < R; ++r) prob_out[r * rstride] = exp(h * (c[r * rstride] - mn)) * inv;
+  return acc * inv;
+}
+
+// Large batches: the reduction over rollouts as its own streaming kernel, one thread per (problem, dimension, timestep)
+// element — inside k_update a thread walks ~6 elements one after the other, four memory round trips each, at 900 threads per
+// SM.  Leaves the scaled, not yet projected update in a.updates; k_update (pre_reduced) picks it up.
+__global__ void __launch_bounds__(256) k_rollout_weights(UpdateArgs a, long long total) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= total) return;
+  const int N = a.N, R = a.R, D = a.D;
+  const long long bd = k / N;
+  const int t = int(k - bd * N), b = int(bd / D), d = int(bd - (long long)b * D);
+  const size_t base = (size_t(b) * R * D + d) * N + t, rstride = size_t(D) * N;
+  double* prob = a.probabilities ? a.probabilities + base : nullptr;
+  const double v = R <= 10 ? weighted_noise<10, true>(a.cumulative + base, a.noise + base, rstride, R, prob)
+                           : weighted_noise<5, false>(a.cumulative + base, a.noise + base, rstride, R, prob);
+  a.updates[k] = v * a.band.proj_scale[t];
+}
 
 // CTA per (problem, group of dimensions).  Phase 1 (all threads, thread per timestep): min / max over
 // rollouts, exp-normalised weights, probability-weighted noise.  Phase 2 (one lane per dimension): the
@@ -1491,46 +1563,12 @@ __global__ void k_update(UpdateArgs a) {
   for (int k = threadIdx.x; k < nd * N; k += blockDim.x) {
     const int dl = k / N, t = k - dl * N, d = d0 + dl;
     const size_t base = (size_t(b) * R * D + d) * N + t;
-    const double* c = a.cumulative + base;
-    const double* e = a.noise + base;
-    // rollouts are visited in groups of kGroup with all loads of a group issued before the first use (the loop count is
-    // a run-time value, so the compiler does not software-pipeline it; ncu showed 45 % of the stalls on these loads)
-    constexpr int kGroup = 5;
-    double mn = c[0], mx = c[0];
-    for (int r0 = 0; r0 < R; r0 += kGroup) {
-      double cv[kGroup];
-#pragma unroll
-      for (int j = 0; j < kGroup; ++j) cv[j] = r0 + j < R ? c[(r0 + j) * rstride] : mn;
-#pragma unroll
-      for (int j = 0; j < kGroup; ++j) {
-        if (cv[j] < mn) mn = cv[j];
-        if (cv[j] > mx) mx = cv[j];
-      }
+    if (a.pre_reduced) {             // k_rollout_weights already did the reduction over rollouts
+      u[dl * stride + t] = a.updates[(size_t(b) * D + d) * N + t];
+      continue;
     }
-    double denom = mx - mn;
-    if (denom < 1e-8) denom = 1e-8;
-    const double h = -10.0 / denom;
-    double p_sum = 0.0, acc = 0.0;
-    for (int r0 = 0; r0 < R; r0 += kGroup) {
-      double cv[kGroup], ev[kGroup];
-#pragma unroll
-      for (int j = 0; j < kGroup; ++j) {
-        const bool in = r0 + j < R;
-        cv[j] = in ? c[(r0 + j) * rstride] : 0.0;
-        ev[j] = in ? e[(r0 + j) * rstride] : 0.0;
-      }
-#pragma unroll
-      for (int j = 0; j < kGroup; ++j)
-        if (r0 + j < R) {
-          const double w = exp(h * (cv[j] - mn));
-          p_sum += w;
-          acc += ev[j] * w;
-        }
-    }
-    const double inv = 1.0 / p_sum;
-    if (a.probabilities)
-      for (int r = 0; r < R; ++r) a.probabilities[base + r * rstride] = exp(h * (c[r * rstride] - mn)) * inv;
-    u[dl * stride + t] = acc * inv * a.band.proj_scale[t];
+    u[dl * stride + t] = weighted_noise<5, false>(a.cumulative + base, a.noise + base, rstride, R,
+                                                  a.probabilities ? a.probabilities + base : nullptr) * a.band.proj_scale[t];
   }
   __syncthreads();
   if (threadIdx.x < nd) {
