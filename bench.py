@@ -411,7 +411,7 @@ def run_engine(args):
     cost_ms, cost_n = eng.get_profile("k_cost")
     all_ms, all_n = eng.get_profile("")
     shares = {}
-    for kn in ("k_select_reuse", "k_generate", "k_gather_state", "k_cost", "k_cumulative", "k_rollout_weights", "k_update", "k_extra_total",
+    for kn in ("k_select_reuse", "k_generate", "k_gather_state", "k_cost", "k_cumulative", "k_update", "k_extra_total",
                "k_minmax_partial", "k_sums_partial", "k_pair_reduce", "k_finalize"):
         m, n = eng.get_profile(kn)
         shares[kn] = {"ms_per_iteration": m / Kp, "launches_per_iteration": n / Kp}
@@ -422,8 +422,6 @@ def run_engine(args):
     algo = {"k_generate": 4.0 * BRDN8,                      # per vector: read theta / previous parameters, write noise, parameters, control costs
             "k_cumulative": BRDN8 * (2.0 + 1.0 / D),        # read control costs + state costs, write cumulative costs
             "k_update": 2.0 * BRDN8}                        # read cumulative costs + noise
-    if shares["k_rollout_weights"]["ms_per_iteration"] > 0:  # large batches: the reduction over rollouts is its own kernel
-        algo["k_rollout_weights"] = algo.pop("k_update")
     for kn, nbytes in algo.items():
         ms_it = shares[kn]["ms_per_iteration"]
         if ms_it > 0:

@@ -121,7 +121,7 @@ struct Engine {
   double constraint_cost_weight = 0.0;
   DevBuf<double> band_fw, band_bw, proj_scale, qinv_t, noise_scale;
   DevBuf<double> dense_cinv, dense_ms;   // [N][N] C^-1 and R^-1 diag(s) for k_generate_dense (small batches)
-  bool split_update = false;  // A/B switch (STOMP_SPLIT_UPDATE=1): reduction over rollouts as its own kernel, k_rollout_weights
+  bool dense_update = true;   // A/B switch (STOMP_NO_DENSE_UPDATE=1): k_update projects with the banded solves
   int gen_mode = 0;   // 0: pick k_generate / k_generate_dense by batch shape; 1, 2: always that one (A/B)
   DevBuf<double> limit_min, limit_max;
   DevBuf<int> has_limits;
@@ -614,20 +614,19 @@ int launch_update(Engine& e, int apply, bool fuse_extra_control) {
   }
   a.cumulative = e.cumulative.p; a.noise = e.noise.p; a.probabilities = e.probabilities.p;
   a.updates = e.updates.p; a.theta = e.theta.p; a.band = e.band_view();
+  // the projection as a dense product (kernels.cuh) while the N x N matrix is a few hundred KB of L2-resident reads per CTA
+  a.dense_ms = (e.dense_update && e.N <= 512) ? e.dense_ms.p : nullptr;
+  auto update_smem = [&](int rows) {
+    const size_t stride = size_t(e.N + 2 * kPad) | 1;
+    return (2 * rows * stride + size_t(rows) * 2 * kPad + (a.dense_ms ? 0 : size_t(e.N) * 16)) * 8;
+  };
   // enough CTAs to fill the machine twice when the batch allows it; otherwise one dimension per CTA
   int dpc = int(std::min<long long>(std::min(e.D, 32), std::max<long long>(1, (long long)e.B * e.D / 296)));
-  size_t smem = band_smem(e, dpc);
-  while (smem > 200 * 1024 && dpc > 1) smem = band_smem(e, --dpc);
+  size_t smem = update_smem(dpc);
+  while (smem > 200 * 1024 && dpc > 1) smem = update_smem(--dpc);
   a.dims_per_cta = dpc;
   const int groups = (e.D + dpc - 1) / dpc;
   CUDA_TRY(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  const long long elements = (long long)e.B * e.D * e.N;
-  if (e.split_update && elements >= 100000) {      // enough elements to fill the machine with one thread each
-    begin_launch(e);
-    k_rollout_weights<<<unsigned((elements + 255) / 256), 256, 0, e.ws>>>(a, elements);
-    if (check_launch(e, "k_rollout_weights")) return 1;
-    a.pre_reduced = 1;
-  }
   begin_launch(e);
   const int tpb_max = 128;   // A/B on B200 (C2): 64 threads 0.163, 128: 0.097, 256: 0.150, 512: 0.244 ms
   k_update<<<unsigned(e.B) * groups, std::min(tpb_max, ((dpc * e.N + 31) / 32) * 32), smem, e.ws>>>(a);
@@ -1077,7 +1076,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   // A/B switches of the generation kernels: STOMP_GENERATE=band|dense forces one, STOMP_NO_DENSE=1 is "band"
   if (const char* g = getenv("STOMP_GENERATE")) e.gen_mode = !strcmp(g, "band") ? 1 : !strcmp(g, "dense") ? 2 : 0;
   if (getenv("STOMP_NO_DENSE") && atoi(getenv("STOMP_NO_DENSE")) != 0) e.gen_mode = 1;
-  e.split_update = getenv("STOMP_SPLIT_UPDATE") && atoi(getenv("STOMP_SPLIT_UPDATE")) != 0;
+  e.dense_update = !(getenv("STOMP_NO_DENSE_UPDATE") && atoi(getenv("STOMP_NO_DENSE_UPDATE")) != 0);
   e.noise_stddev.assign(e.D, 1.0);
   e.noise_decay.assign(e.D, 1.0);
   std::vector<int> hl(e.D, 0);

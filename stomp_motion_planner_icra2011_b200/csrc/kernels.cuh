@@ -1459,7 +1459,7 @@ __global__ void k_extra_total(int R, int D, int N, const double* __restrict__ st
 struct UpdateArgs {
   int R, D, N, apply;
   int dims_per_cta;          // a CTA handles dims [g*dims_per_cta, ...) of one problem
-  int pre_reduced;           // 1: a.updates already holds the weighted noise (k_rollout_weights)
+  const double* dense_ms;    // [N][N] rows j of R^-1 diag(s) (engine.cu), or nullptr: banded solves
   const double* cumulative;  // [B][R][D][N]
   const double* noise;       // [B][R][D][N]
   double* probabilities;     // optional tap
@@ -1473,6 +1473,31 @@ struct UpdateArgs {
   double control_weight;     // 0.5 * control_cost_weight
   Stencil st;
 };
+
+// exp(x) for the PI^2 weights, x = -10 (c - min) / (max - min) in [-10, 0] (valid for |x| < 700).  The library exp is ~100
+// instructions with its range checks; ncu showed k_update issue bound on them (39 M warp instructions, 1 400 per element
+// for ten weights).  Cody-Waite reduction x = k ln2 + t, |t| <= 0.35, Taylor polynomial of degree 13 (remainder 6e-18),
+// 2^k added to the exponent field: ~22 instructions, within 2 ulp of the correctly rounded value.
+__device__ __forceinline__ double exp_weight(double x) {
+  const double kf = rint(x * 1.4426950408889634074);
+  double t = fma(kf, -6.93147180369123816490e-01, x);
+  t = fma(kf, -1.90821492927058770002e-10, t);
+  double p = 1.6059043836821613e-10;            // 1/13!
+  p = fma(p, t, 2.0876756987868100e-09);        // 1/12!
+  p = fma(p, t, 2.5052108385441720e-08);        // 1/11!
+  p = fma(p, t, 2.7557319223985893e-07);        // 1/10!
+  p = fma(p, t, 2.7557319223985888e-06);        // 1/9!
+  p = fma(p, t, 2.4801587301587302e-05);        // 1/8!
+  p = fma(p, t, 1.9841269841269841e-04);        // 1/7!
+  p = fma(p, t, 1.3888888888888889e-03);        // 1/6!
+  p = fma(p, t, 8.3333333333333332e-03);        // 1/5!
+  p = fma(p, t, 4.1666666666666664e-02);        // 1/4!
+  p = fma(p, t, 1.6666666666666666e-01);        // 1/3!
+  p = fma(p, t, 0.5);
+  p = fma(p, t, 1.0);
+  p = fma(p, t, 1.0);
+  return __longlong_as_double(__double_as_longlong(p) + (static_cast<long long>(__double2int_rn(kf)) << 52));
+}
 
 // One (problem, dimension, timestep) element of the PI^2 update (policy_improvement.cpp:283-340): min / max of the cumulative
 // costs over rollouts, exp(-10 (c - min) / (max - min)) weights, probability-weighted noise.  Rollouts are visited in groups
@@ -1518,107 +1543,128 @@ __device__ __forceinline__ double weighted_noise(const double* __restrict__ c, c
 #pragma unroll
     for (int j = 0; j < kGroup; ++j)
       if (r0 + j < R) {
-        const double w = exp(h * (cv[j] - mn));
+        const double w = exp_weight(h * (cv[j] - mn));
         p_sum += w;
         acc += ev[j] * w;
       }
   }
   const double inv = 1.0 / p_sum;
   if (prob_out)
-    for (int r = 0; r < R; ++r) prob_out[r * rstride] = exp(h * (c[r * rstride] - mn)) * inv;
+    for (int r = 0; r < R; ++r) prob_out[r * rstride] = exp_weight(h * (c[r * rstride] - mn)) * inv;
   return acc * inv;
 }
 
-// Large batches: the reduction over rollouts as its own streaming kernel, one thread per (problem, dimension, timestep)
-// element — inside k_update a thread walks ~6 elements one after the other, four memory round trips each, at 900 threads per
-// SM.  Leaves the scaled, not yet projected update in a.updates; k_update (pre_reduced) picks it up.
-__global__ void __launch_bounds__(256) k_rollout_weights(UpdateArgs a, long long total) {
-  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= total) return;
-  const int N = a.N, R = a.R, D = a.D;
-  const long long bd = k / N;
-  const int t = int(k - bd * N), b = int(bd / D), d = int(bd - (long long)b * D);
-  const size_t base = (size_t(b) * R * D + d) * N + t, rstride = size_t(D) * N;
-  double* prob = a.probabilities ? a.probabilities + base : nullptr;
-  const double v = R <= 10 ? weighted_noise<10, true>(a.cumulative + base, a.noise + base, rstride, R, prob)
-                           : weighted_noise<5, false>(a.cumulative + base, a.noise + base, rstride, R, prob);
-  a.updates[k] = v * a.band.proj_scale[t];
-}
-
 // CTA per (problem, group of dimensions).  Phase 1 (all threads, thread per timestep): min / max over
-// rollouts, exp-normalised weights, probability-weighted noise.  Phase 2 (one lane per dimension): the
-// projection through M = R^-1 diag(s) as two banded triangular solves.  Phase 3: theta += update.
-__global__ void k_update(UpdateArgs a) {
+// rollouts, exp-normalised weights, probability-weighted noise.  Phase 2: the projection through M = R^-1 diag(s) — as the
+// dense product it stands for (all threads, a.dense_ms = [j][t] rows of R^-1 diag(s); ncu: the two banded solves ran on one
+// lane per dimension for a fifth of the kernel's time while the other warps waited at the barrier), or, for long series, as
+// the two banded triangular solves.  Phase 3: theta += update, and the control cost of the updated trajectory from a padded
+// copy in shared memory.  Seven CTAs per SM keep a 1024-problem batch in one wave (at 96 registers it took two: 0.088 ms
+// instead of 0.061).
+__global__ void __launch_bounds__(128, 7) k_update(UpdateArgs a) {
   extern __shared__ double smem[];
   const int N = a.N, R = a.R, D = a.D, G = a.dims_per_cta;
-  const int stride = N | 1;
-  double* sfw = smem;               // [N][8]
-  double* sbw = sfw + N * 8;        // [N][8]
-  double* u = sbw + N * 8;          // [G][stride]
+  const int Nall = N + 2 * kPad;
+  const int stride = Nall | 1;
+  const bool dense = a.dense_ms != nullptr;
+  double* u = smem;                           // [G][stride]  weighted noise; later the padded updated trajectory
+  double* y = u + size_t(G) * stride;         // [G][stride]  dense: projected update
+  double* fold = y + size_t(G) * stride;      // [G][2 kPad]  control costs of the padded rows
+  double* sfw = fold + size_t(G) * 2 * kPad;  // [N][8]       band path only
+  double* sbw = sfw + N * 8;                  // [N][8]
   const int groups = (D + G - 1) / G;
   const int b = blockIdx.x / groups, d0 = (blockIdx.x - b * groups) * G;
   const int nd = min(G, D - d0);
-  for (int k = threadIdx.x; k < N * 8; k += blockDim.x) sfw[k] = a.band.fw[k], sbw[k] = a.band.bw[k];
+  if (!dense)
+    for (int k = threadIdx.x; k < N * 8; k += blockDim.x) sfw[k] = a.band.fw[k], sbw[k] = a.band.bw[k];
   const size_t rstride = size_t(D) * N;
   for (int k = threadIdx.x; k < nd * N; k += blockDim.x) {
     const int dl = k / N, t = k - dl * N, d = d0 + dl;
     const size_t base = (size_t(b) * R * D + d) * N + t;
-    if (a.pre_reduced) {             // k_rollout_weights already did the reduction over rollouts
-      u[dl * stride + t] = a.updates[(size_t(b) * D + d) * N + t];
-      continue;
-    }
-    u[dl * stride + t] = weighted_noise<5, false>(a.cumulative + base, a.noise + base, rstride, R,
-                                                  a.probabilities ? a.probabilities + base : nullptr) * a.band.proj_scale[t];
+    double* prob = a.probabilities ? a.probabilities + base : nullptr;
+    double v = R <= 10 ? weighted_noise<10, true>(a.cumulative + base, a.noise + base, rstride, R, prob)
+                       : weighted_noise<5, false>(a.cumulative + base, a.noise + base, rstride, R, prob);
+    if (!dense) v *= a.band.proj_scale[t];      // the dense matrix carries the scaling
+    u[dl * stride + t] = v;
   }
   __syncthreads();
-  if (threadIdx.x < nd) {
+  if (dense) {
+    constexpr int kDims = 8;         // dimensions accumulated per pass over the matrix column
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+      for (int q0 = 0; q0 < nd; q0 += kDims) {
+        double acc[kDims];
+#pragma unroll
+        for (int q = 0; q < kDims; ++q) acc[q] = 0.0;
+        const double* mp = a.dense_ms + t;
+#pragma unroll 4
+        for (int j = 0; j < N; ++j, mp += N) {
+          const double m = __ldg(mp);
+#pragma unroll
+          for (int q = 0; q < kDims; ++q)
+            if (q0 + q < nd) acc[q] = fma(m, u[(q0 + q) * stride + j], acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < kDims; ++q)
+          if (q0 + q < nd) y[(q0 + q) * stride + t] = acc[q];
+      }
+    }
+  } else if (threadIdx.x < nd) {
     double* x = u + threadIdx.x * stride;
     band_forward(x, sfw, N);
     band_backward(x, sbw, N);
   }
   __syncthreads();
+  const double* upd = dense ? y : u;
   const size_t off = (size_t(b) * D + d0) * N;
+  const bool control = a.apply && a.extra_control;
   for (int k = threadIdx.x; k < nd * N; k += blockDim.x) {
     const int dl = k / N, t = k - dl * N;
-    double v = u[dl * stride + t];
+    const double v = upd[dl * stride + t];
     a.updates[off + k] = v;
     if (a.apply) {
       const double th = a.theta[off + k] + v;
       a.theta[off + k] = th;
-      u[dl * stride + t] = th;   // keep the updated trajectory for the control-cost stencil below
+      if (control) (dense ? u : y)[dl * stride + kPad + t] = th;   // padded copy for the stencils (the array phase 2 is done with)
     }
   }
-  if (!(a.apply && a.extra_control)) return;
-  __syncthreads();
-  // control cost of the noise-less (updated) trajectory: fully parallel 7-tap stencils over [pads, theta, pads]
+  if (!control) return;
+  // control cost of the noise-less (updated) trajectory: 7-tap stencils over [pads, theta, pads]
   // (covariant_trajectory_policy.cpp:228-255 with zero noise; what addExtraRollouts computes for the extra rollout)
-  const int Nall = N + 2 * kPad;
-  for (int k = threadIdx.x; k < nd * N; k += blockDim.x) {
-    const int dl = k / N, t = k - dl * N, d = d0 + dl;
-    const double xs = a.pad_start[size_t(b) * D + d], xg = a.pad_goal[size_t(b) * D + d];
-    const double* row = u + dl * stride;
-    auto cost_at = [&](int p) -> double {
-      double cost = 0.0;
+  double* xp = dense ? u : y;
+  for (int k = threadIdx.x; k < nd * 2 * kPad; k += blockDim.x) {
+    const int dl = k / (2 * kPad), q = k - dl * 2 * kPad, d = d0 + dl;
+    xp[dl * stride + (q < kPad ? q : N + q)] = q < kPad ? a.pad_start[size_t(b) * D + d] : a.pad_goal[size_t(b) * D + d];
+  }
+  __syncthreads();
+  auto cost_at = [&](const double* row, int p, bool interior) -> double {   // padded row p; interior: every tap is in range
+    double cost = 0.0;
 #pragma unroll
-      for (int kk = 0; kk < 3; ++kk) {
-        if (a.st.weight[kk] == 0.0) continue;
-        double acc = 0.0;
+    for (int kk = 0; kk < 3; ++kk) {
+      if (a.st.weight[kk] == 0.0) continue;
+      double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {
-          const int idx = p + j - 3;
-          if (idx < 0 || idx >= Nall) continue;
-          const double xv = idx < kPad ? xs : (idx >= kPad + N ? xg : row[idx - kPad]);
-          acc += a.st.coef[kk][j] * xv;
-        }
-        cost += a.control_weight * a.st.weight[kk] * (acc * acc);
+      for (int j = 0; j < 7; ++j) {
+        const int idx = p + j - 3;
+        if (!interior && (idx < 0 || idx >= Nall)) continue;   // dropped taps of the differentiation matrices
+        acc += a.st.coef[kk][j] * row[idx];
       }
-      return cost;
-    };
-    double c = cost_at(t + kPad);
+      cost += a.control_weight * a.st.weight[kk] * (acc * acc);
+    }
+    return cost;
+  };
+  // the padded rows' costs belong to the first / last free row; one thread each instead of twelve in a row on two threads
+  for (int k = threadIdx.x; k < nd * 2 * kPad; k += blockDim.x) {
+    const int dl = k / (2 * kPad), q = k - dl * 2 * kPad;
+    fold[k] = cost_at(xp + dl * stride, q < kPad ? q : Nall - 1 - (q - kPad), false);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nd * N; k += blockDim.x) {
+    const int dl = k / N, t = k - dl * N;
+    double c = cost_at(xp + dl * stride, t + kPad, true);
     if (t == 0)
-      for (int i = 0; i < kPad; ++i) c += cost_at(i);
+      for (int i = 0; i < kPad; ++i) c += fold[dl * 2 * kPad + i];
     if (t == N - 1)
-      for (int i = 0; i < kPad; ++i) c += cost_at(Nall - 1 - i);
+      for (int i = 0; i < kPad; ++i) c += fold[dl * 2 * kPad + kPad + i];
     a.extra_control[off + k] = c;
   }
 }
@@ -1896,8 +1942,9 @@ __global__ void k_sums_partial(int R, int DN, int rollouts_per_chunk, const doub
     double denom = mx - mn;
     if (denom < 1e-8) denom = 1e-8;
     double se = 0.0, see = 0.0;
+    const double h = -10.0 / denom;
     for (int r = r0; r < r1; ++r) {
-      double e = exp(-10.0 * (cumulative[size_t(r) * DN + i] - mn) / denom);
+      double e = exp_weight(h * (cumulative[size_t(r) * DN + i] - mn));
       se += e;
       see += e * noise[size_t(r) * DN + i];
     }
@@ -1914,7 +1961,7 @@ __global__ void k_probabilities(int R, int DN, const double* __restrict__ cumula
     double mx = minmax[i], mn = -minmax[DN + i];
     double denom = mx - mn;
     if (denom < 1e-8) denom = 1e-8;
-    prob[k] = exp(-10.0 * (cumulative[k] - mn) / denom) / sums[i];
+    prob[k] = exp_weight(-10.0 / denom * (cumulative[k] - mn)) / sums[i];
   }
 }
 
