@@ -358,6 +358,9 @@ int stomp_engine_timer_stop(void* engine, float* elapsed_ms);
  * (src/policy_improvement.cpp:255-257,389-397). */
 int stomp_engine_set_profiling(void* engine, int32_t enabled);
 int stomp_engine_get_profile(void* engine, const char* kernel_substr, double* total_ms, int64_t* num_launches);
+/* enabled == 2 in stomp_engine_set_profiling keeps the two-stream schedule while recording; this writes what was recorded as
+ * CSV (index, kernel, stream 0 main / 1 tail, begin_us, end_us after the first recorded launch).  Measurement aid only. */
+int stomp_engine_dump_timeline(void* engine, const char* path);
 
 /* ---- rollout sharding over GPUs (config C3) ----------------------------------------- */
 /* Device buffers the host plumbing (torch.distributed / NCCL) all-reduces between the phases of

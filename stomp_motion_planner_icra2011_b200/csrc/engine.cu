@@ -147,7 +147,8 @@ struct Engine {
   size_t scratch_n = 0;
 
   // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
-  bool prof_on = false;
+  bool prof_on = false, prof_timeline = false;   // timeline: keep the two-stream schedule while recording
+  std::vector<int> prof_stream;                  // 0 main, 1 tail, 2 other
   std::vector<cudaEvent_t> prof_a, prof_b;
   std::vector<std::string> prof_name;
   size_t prof_used = 0;
@@ -175,6 +176,7 @@ void begin_launch(Engine& e) {
     e.prof_a.push_back(a);
     e.prof_b.push_back(b);
     e.prof_name.push_back("");
+    e.prof_stream.push_back(0);
   }
   cudaEventRecord(e.prof_a[e.prof_used], e.ws);
 }
@@ -186,6 +188,7 @@ int check_launch(Engine& e, const char* what) {
   if (e.prof_on) {
     cudaEventRecord(e.prof_b[e.prof_used], e.ws);
     e.prof_name[e.prof_used] = what;
+    e.prof_stream[e.prof_used] = e.ws == e.stream ? 0 : (e.ws == e.tail_stream ? 1 : 2);
     e.prof_used++;
   }
   return 0;
@@ -838,7 +841,7 @@ int iterate_once(Engine& e, int iteration_number) {
     if (e.desc.rollout_shard_world > 1)
       return fail("rollout-sharded engines iterate through stomp_engine_iterate_sharded_phase");
   }
-  if (!e.overlap || e.prof_on) return iterate_serial(e, iteration_number);
+  if (!e.overlap || (e.prof_on && !e.prof_timeline)) return iterate_serial(e, iteration_number);
   e.ws = e.stream;
   std::vector<double> scale(e.D);
   for (int d = 0; d < e.D; ++d) scale[d] = e.noise_stddev[d] * std::pow(e.noise_decay[d], iteration_number - 1);
@@ -1000,6 +1003,8 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   if ((c = cudaDeviceGetAttribute(&e.num_sms, cudaDevAttrMultiProcessorCount, e.device)) != cudaSuccess) return bail(c, "cudaDeviceGetAttribute");
   if ((c = cudaEventCreate(&e.ev0)) != cudaSuccess || (c = cudaEventCreate(&e.ev1)) != cudaSuccess) return bail(c, "cudaEventCreate");
   if ((c = cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
+  // equal priorities: with the tail stream at the greatest priority the timeline looks better under event recording
+  // (k_extra_total no longer waits 157 us for a CTA slot) but the unrecorded loop is slower, 0.522 vs 0.510 ms (profiles/README.md)
   if ((c = cudaStreamCreateWithFlags(&e.tail_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
   if ((c = cudaEventCreateWithFlags(&e.ev_tail, cudaEventDisableTiming)) != cudaSuccess ||
       (c = cudaEventCreateWithFlags(&e.ev_upd, cudaEventDisableTiming)) != cudaSuccess ||
@@ -1760,9 +1765,35 @@ int stomp_engine_timer_stop(void* h, float* elapsed_ms) {
 
 int stomp_engine_set_profiling(void* h, int32_t enabled) {
   ENGINE_OR_FAIL(h);
+  if (join_streams(e)) return 1;
   CUDA_TRY(cudaStreamSynchronize(e.stream));
   e.prof_on = enabled != 0;
+  e.prof_timeline = enabled == 2;
   e.prof_used = 0;
+  return 0;
+}
+
+/* Writes the launches recorded since stomp_engine_set_profiling(engine, 2) as CSV: index, kernel, stream (0 main, 1 tail),
+ * begin and end in microseconds after the first recorded launch began.  Event timestamps: "begin" is when the stream reached
+ * the launch (its dependencies resolved), "end" when the kernel finished. */
+int stomp_engine_dump_timeline(void* h, const char* path) {
+  ENGINE_OR_FAIL(h);
+  if (!path) return fail("null argument");
+  if (join_streams(e)) return 1;
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  FILE* f = std::fopen(path, "w");
+  if (!f) return fail(std::string("cannot open ") + path);
+  std::fprintf(f, "index,kernel,stream,begin_us,end_us\n");
+  for (size_t i = 0; i < e.prof_used; ++i) {
+    float t0 = 0.f, t1 = 0.f;
+    if (cudaEventElapsedTime(&t0, e.prof_a[0], e.prof_a[i]) != cudaSuccess ||
+        cudaEventElapsedTime(&t1, e.prof_a[0], e.prof_b[i]) != cudaSuccess) {
+      std::fclose(f);
+      return fail("cudaEventElapsedTime failed while writing the timeline");
+    }
+    std::fprintf(f, "%zu,%s,%d,%.3f,%.3f\n", i, e.prof_name[i].c_str(), e.prof_stream[i], 1e3 * t0, 1e3 * t1);
+  }
+  std::fclose(f);
   return 0;
 }
 

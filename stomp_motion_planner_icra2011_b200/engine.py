@@ -27,7 +27,7 @@ EXPORTS = [
     "stomp_engine_add_extra_rollouts", "stomp_engine_iterate", "stomp_engine_run", "stomp_engine_synchronize",
     "stomp_engine_get", "stomp_engine_launch_count", "stomp_engine_stream", "stomp_engine_timer_start",
     "stomp_engine_timer_stop", "stomp_engine_shard_buffers", "stomp_engine_iterate_sharded_phase",
-    "stomp_engine_set_profiling", "stomp_engine_get_profile", "stomp_engine_optimize",
+    "stomp_engine_set_profiling", "stomp_engine_get_profile", "stomp_engine_dump_timeline", "stomp_engine_optimize",
     "stomp_engine_build_sdf", "stomp_engine_get_sdf", "stomp_engine_inject_noise_async", "stomp_engine_last_stats",
     "stomp_engine_set_constraints", "stomp_engine_execute_constraints_satisfied",
     "stomp_engine_request_results_async", "stomp_engine_wait_results", "stomp_engine_set_dynamics",
@@ -306,6 +306,10 @@ class Engine:
         ms, n = C.c_double(), C.c_int64()
         self._ck(self.L.stomp_engine_get_profile(self.h, kernel_substr.encode(), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def dump_timeline(self, path):
+        """CSV of the launches recorded since set_profiling(2) (two-stream schedule kept): index, kernel, stream, begin_us, end_us."""
+        self._ck(self.L.stomp_engine_dump_timeline(self.h, str(path).encode()))
 
     def launch_count(self):
         return int(self.L.stomp_engine_launch_count(self.h))
