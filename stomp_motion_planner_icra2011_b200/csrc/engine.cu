@@ -147,6 +147,13 @@ struct Engine {
   size_t scratch_n = 0;
 
   // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
+  // STOMP_CHAIN_PROBE=1: two timing events per overlapped iteration (end of the main stream's k_cumulative, end of the tail
+  // stream's chain) and, at destroy, the mean of "tail end - main end" on stderr: which chain k_update really waits for,
+  // with far less perturbation than the per-launch events of the timeline
+  bool chain_probe = false;
+  cudaEvent_t probe_main = nullptr, probe_tail = nullptr, probe_upd = nullptr;
+  double probe_sum_us = 0.0, probe_upd_sum_us = 0.0;
+  long long probe_n = 0;
   bool prof_on = false, prof_timeline = false;   // timeline: keep the two-stream schedule while recording
   std::vector<int> prof_stream;                  // 0 main, 1 tail, 2 other
   std::vector<cudaEvent_t> prof_a, prof_b;
@@ -863,6 +870,7 @@ int iterate_once(Engine& e, int iteration_number) {
     }
   }
   CUDA_TRY(cudaEventRecord(e.ev_tail, e.tail_stream));   // also covers the previous iteration's noise-less rollout
+  if (e.chain_probe && p.reuse) CUDA_TRY(cudaEventRecord(e.probe_tail, e.tail_stream));
   e.ws = e.stream;
   if (launch_generate_range(e, p, 0, e.num_gen, true)) return 1;
   if (launch_cost(e, e.params[e.cur].p, size_t(e.R) * e.D * e.N, e.num_gen, e.B, iteration_number == 1, e.state[e.cur].p,
@@ -870,10 +878,23 @@ int iterate_once(Engine& e, int iteration_number) {
     return 1;
   if (p.reuse) CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_selected, 0));
   if (launch_cumulative(e, 0, e.num_gen)) return 1;       // new slots; the reused slots' were done on the tail stream
+  if (e.chain_probe && p.reuse) CUDA_TRY(cudaEventRecord(e.probe_main, e.stream));
   CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_tail, 0));
   const bool huge = e.huge_path();
   if (huge ? (launch_minmax(e) || launch_sums(e) || launch_finalize(e, 1)) : launch_update(e, 1, true)) return 1;
   CUDA_TRY(cudaEventRecord(e.ev_upd, e.stream));
+  if (e.chain_probe && p.reuse && (iteration_number % 16) == 0) {      // sampled: the read-back synchronises
+    CUDA_TRY(cudaEventRecord(e.probe_upd, e.stream));
+    CUDA_TRY(cudaEventSynchronize(e.probe_upd));
+    CUDA_TRY(cudaEventSynchronize(e.probe_tail));
+    float d = 0.f, u = 0.f;
+    if (cudaEventElapsedTime(&d, e.probe_main, e.probe_tail) == cudaSuccess &&
+        cudaEventElapsedTime(&u, e.probe_main, e.probe_upd) == cudaSuccess) {
+      e.probe_sum_us += 1e3 * d;
+      e.probe_upd_sum_us += 1e3 * u;
+      ++e.probe_n;
+    }
+  }
   e.ws = e.tail_stream;
   CUDA_TRY(cudaStreamWaitEvent(e.tail_stream, e.ev_upd, 0));
   const int rc = step_extra(e, true, iteration_number, !huge);
@@ -1081,6 +1102,10 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   // A/B switches of the generation kernels: STOMP_GENERATE=band|dense forces one, STOMP_NO_DENSE=1 is "band"
   if (const char* g = getenv("STOMP_GENERATE")) e.gen_mode = !strcmp(g, "band") ? 1 : !strcmp(g, "dense") ? 2 : 0;
   if (getenv("STOMP_NO_DENSE") && atoi(getenv("STOMP_NO_DENSE")) != 0) e.gen_mode = 1;
+  e.chain_probe = getenv("STOMP_CHAIN_PROBE") && atoi(getenv("STOMP_CHAIN_PROBE")) != 0;
+  if (e.chain_probe && (cudaEventCreate(&e.probe_main) != cudaSuccess || cudaEventCreate(&e.probe_tail) != cudaSuccess ||
+                        cudaEventCreate(&e.probe_upd) != cudaSuccess))
+    e.chain_probe = false;
   e.dense_update = !(getenv("STOMP_NO_DENSE_UPDATE") && atoi(getenv("STOMP_NO_DENSE_UPDATE")) != 0);
   e.noise_stddev.assign(e.D, 1.0);
   e.noise_decay.assign(e.D, 1.0);
@@ -1116,6 +1141,13 @@ int stomp_engine_destroy(void* h) {
       if (r != e->desc.rollout_shard_rank && e->peer_base[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
   if (e->ev_upd) cudaEventDestroy(e->ev_upd);
   if (e->ev_selected) cudaEventDestroy(e->ev_selected);
+  if (e->chain_probe) {
+    if (e->probe_n)
+      std::fprintf(stderr, "stomp_b200 chain probe: tail chain ends %+.1f us after the main stream's k_cumulative, k_update ends "
+                           "%.1f us after it (mean of %lld sampled iterations)\n",
+                   e->probe_sum_us / e->probe_n, e->probe_upd_sum_us / e->probe_n, e->probe_n);
+    cudaEventDestroy(e->probe_main); cudaEventDestroy(e->probe_tail); cudaEventDestroy(e->probe_upd);
+  }
   for (int i = 0; i < 2; ++i) {
     if (e->ev_copy_done[i]) cudaEventDestroy(e->ev_copy_done[i]);
     if (e->ev_consumed[i]) cudaEventDestroy(e->ev_consumed[i]);
