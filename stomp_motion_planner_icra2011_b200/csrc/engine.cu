@@ -455,9 +455,9 @@ int launch_cost_k(Engine& e, CostArgs<Real>& a, int num_problems) {
   const int seg = e.N + 3;
   auto tiles_for = [&](int p) { return (p * seg - 3 + kTileSteps - 1) / kTileSteps; };
   auto smem_for = [&](int p, int warps) {
-    return ((size_t(p) * e.D * e.N * 8 + 15) & ~size_t(15)) + size_t(e.num_nodes) * sizeof(DevNode<Real>) +
+    return ((size_t(p) * (size_t(e.D) * e.N + 2 * e.D) * 8 + 15) & ~size_t(15)) + size_t(e.num_nodes) * sizeof(DevNode<Real>) +
            size_t(e.K) * sizeof(DevSphere<Real>) + 256 * sizeof(Real) + size_t(warps) * 12 * 32 * sizeof(Real) +
-           e.constraints.size() * sizeof(DevConstraint<Real>) + e.clusters.size() * sizeof(DevCluster<Real>);
+           e.constraints.size() * sizeof(DevConstraint<Real>) + e.clusters.size() * sizeof(DevCluster<Real>) + 16 /* mbarrier */;
   };
   const int max_warps = kCostMaxThreads / 32;
   int pack = 1;
@@ -526,6 +526,13 @@ CostArgs<Real> base_cost_args(Engine& e) {
   a.clusters = reinterpret_cast<const DevCluster<Real>*>(e.dclusters.p);
   a.num_clusters = int(e.clusters.size());
   a.cull.g = e.cull_g.p; a.cull.nx = e.cull_dims[0]; a.cull.ny = e.cull_dims[1]; a.cull.nz = e.cull_dims[2]; a.cull.enabled = e.cull_on ? 1 : 0;
+  a.g_ox = Real(e.sdf.origin[0]); a.g_oy = Real(e.sdf.origin[1]); a.g_oz = Real(e.sdf.origin[2]);
+  a.g_res = Real(e.sdf.res); a.g_inv_res = Real(e.sdf.inv_res);
+  a.g_nox = Real(-e.sdf.origin[0] * e.sdf.inv_res); a.g_noy = Real(-e.sdf.origin[1] * e.sdf.inv_res);
+  a.g_noz = Real(-e.sdf.origin[2] * e.sdf.inv_res);
+  // finite-difference velocity rule {-2, -3, 6, -1} / 6 over t-1 .. t+2, divided by dt (stomp_utils.h:49-56)
+  a.c_m1 = Real(a.inv_time * (-2.0 / 6.0)); a.c_0 = Real(a.inv_time * (-3.0 / 6.0)); a.c_p1 = Real(a.inv_time * (6.0 / 6.0));
+  a.c_p2 = Real(a.inv_time * (-1.0 / 6.0));
   return a;
 }
 

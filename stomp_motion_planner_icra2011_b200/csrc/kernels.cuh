@@ -695,6 +695,10 @@ struct CostArgs {
   const DevCluster<Real>* clusters;   // sphere clusters (always a partition of the sphere table)
   int num_clusters;
   CullField cull;
+  // lookup constants in the kernel's arithmetic type, computed once on the host: they are read as constant-bank operands
+  // instead of occupying ~20 registers per thread (grid origin, resolution, -origin/res, finite-difference rule / dt)
+  Real g_ox, g_oy, g_oz, g_res, g_inv_res, g_nox, g_noy, g_noz;
+  Real c_m1, c_0, c_p1, c_p2;
 };
 
 template <typename Real> struct Math;
@@ -905,30 +909,57 @@ __device__ __forceinline__ Real trilinear_distance(const Grid& g, const void* vo
   return acc;
 }
 
-__device__ __forceinline__ void cta_copy_async16(void* dst_smem, const void* src, int bytes) {
-  for (int off = threadIdx.x * 16; off < bytes; off += blockDim.x * 16) {
-    const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(static_cast<char*>(dst_smem) + off));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(static_cast<const char*>(src) + off) : "memory");
-  }
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier completion -------------------------------------------------
+// One elected thread arms the CTA's mbarrier with the byte count and issues one bulk copy per contiguous block (robot
+// tables, rollout rows); the copy engine moves the bytes into shared memory while the threads go on, and everybody waits
+// on the barrier's phase.  Replaces per-thread 16-byte cp.async loops whose index arithmetic was 12 % of k_cost's
+// instructions (ncu source page, round 1).  Sizes and addresses are multiples of 16 bytes.
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra MBAR_WAIT_%=;\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
 }
 
-
-// Persistent CTAs: the grid is sized to the machine (SMs x resident CTAs) and every CTA walks rollouts with a
-// grid stride, so the robot tables are staged in shared memory once per CTA instead of once per rollout.
 // Lane packing: a warp tile is a window of 32 consecutive points of the CTA's *concatenated* timeline
 //   [rollout 0: t = -1 .. N+1][rollout 1: t = -1 .. N+1] ...          (N + 3 points per rollout, `pack` rollouts)
 // advanced by 29 points per tile; lanes 1..29 of a window are productive when their point is a free timestep, and their
 // velocity taps (-1, +1, +2) are always points of the same rollout inside the same window.  With pack = 1 this is the
 // plain "29 timesteps per warp" tiling; packing 2 rollouts of N = 100 needs 7 warps instead of 8.
+// One CTA per job (the hardware block scheduler balances rollouts whose joint-limit projection takes longer); the job loop
+// only matters when a caller launches fewer CTAs than jobs.
+#ifndef STOMP_COST_MIN_BLOCKS
+#define STOMP_COST_MIN_BLOCKS 4
+#endif
 constexpr int kCostMaxThreads = 224;   // 7 warps; 72 registers -> 4 CTAs (28 warps) per SM
 
 template <typename Real, bool kDebug, int kVox, bool kCons, bool kTri = false, bool kCull = false>
-__global__ void __launch_bounds__(kCostMaxThreads, 4) k_cost(CostArgs<Real> a) {
+__global__ void __launch_bounds__(kCostMaxThreads, STOMP_COST_MIN_BLOCKS) k_cost(CostArgs<Real> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = a.D, N = a.N, K = a.K, P = a.pack;
   const int DN = D * N;
-  double* q = reinterpret_cast<double*>(smem_raw);                        // [P][D][N] clipped trajectories
-  DevNode<Real>* nodes = reinterpret_cast<DevNode<Real>*>(smem_raw + ((size_t(P) * DN * 8 + 15) & ~size_t(15)));
+  // shared layout: rollouts [P][D][N] | start/goal padding [P][2][D] | nodes | spheres | sqrt table | per-warp velocity frames |
+  // constraints | clusters | mbarrier
+  double* q = reinterpret_cast<double*>(smem_raw);                        // joint-limit-projected trajectories
+  double* pads = q + size_t(P) * DN;
+  DevNode<Real>* nodes = reinterpret_cast<DevNode<Real>*>(smem_raw + ((size_t(P) * (DN + 2 * D) * 8 + 15) & ~size_t(15)));
   DevSphere<Real>* spheres = reinterpret_cast<DevSphere<Real>*>(nodes + a.num_nodes);
   Real* sqrt_tab = reinterpret_cast<Real*>(spheres + K);                  // [256]
 
@@ -940,56 +971,64 @@ __global__ void __launch_bounds__(kCostMaxThreads, 4) k_cost(CostArgs<Real> a) {
   DevConstraint<Real>* cons = reinterpret_cast<DevConstraint<Real>*>(sqrt_tab + 256 + size_t(nwarps) * 12 * 32);
   const int num_cons = kCons ? a.num_constraints : 0;
   DevCluster<Real>* clusters = reinterpret_cast<DevCluster<Real>*>(cons + num_cons);
-  cta_copy_async16(clusters, a.clusters, int(sizeof(DevCluster<Real>)) * a.num_clusters);
-  cta_copy_async16(cons, a.constraints, int(sizeof(DevConstraint<Real>)) * num_cons);
-  // robot tables: asynchronous 16-byte copies, all in flight together (waited for with the first trajectory)
-  cta_copy_async16(nodes, a.nodes, int(sizeof(DevNode<Real>)) * a.num_nodes);
-  cta_copy_async16(spheres, a.spheres, int(sizeof(DevSphere<Real>)) * K);
-  cta_copy_async16(sqrt_tab, a.sqrt_table, 256 * int(sizeof(Real)));
+  const unsigned bar = smem_u32(clusters + a.num_clusters);
+  const unsigned table_bytes = unsigned(sizeof(DevNode<Real>)) * a.num_nodes + unsigned(sizeof(DevSphere<Real>)) * K +
+                               256u * unsigned(sizeof(Real)) + unsigned(sizeof(DevConstraint<Real>)) * num_cons +
+                               unsigned(sizeof(DevCluster<Real>)) * a.num_clusters;
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
   typename GridOf<Real>::type g;
-  g.ox = Real(a.sdf.origin[0]); g.oy = Real(a.sdf.origin[1]); g.oz = Real(a.sdf.origin[2]);
-  g.res = Real(a.sdf.res); g.inv_res = Real(a.sdf.inv_res);
-  g.nox = Real(-a.sdf.origin[0] * a.sdf.inv_res); g.noy = Real(-a.sdf.origin[1] * a.sdf.inv_res);
-  g.noz = Real(-a.sdf.origin[2] * a.sdf.inv_res);
+  g.ox = a.g_ox; g.oy = a.g_oy; g.oz = a.g_oz; g.res = a.g_res; g.inv_res = a.g_inv_res;
+  g.nox = a.g_nox; g.noy = a.g_noy; g.noz = a.g_noz;
   g.nx1 = a.sdf.nx - 1; g.ny1 = a.sdf.ny - 1; g.nz1 = a.sdf.nz - 1; g.sny = a.sdf.ny; g.snz = a.sdf.nz;
-  const Real c_m1 = Real(a.inv_time * (-2.0 / 6.0)), c_0 = Real(a.inv_time * (-3.0 / 6.0)), c_p1 = Real(a.inv_time * (6.0 / 6.0)),
-             c_p2 = Real(a.inv_time * (-1.0 / 6.0));
+  const Real c_m1 = a.c_m1, c_0 = a.c_0, c_p1 = a.c_p1, c_p2 = a.c_p2;
   const int ntiles = a.tiles_per_job;
   const int seg = N + 3;                       // timeline points per rollout: t = -1 .. N+1
   const void* vox = a.sdf.vox;
   const int njobs = (a.total_rollouts + P - 1) / P;
 
-  for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+  unsigned phase = 0;
+  for (int job = blockIdx.x; job < njobs; job += gridDim.x, phase ^= 1u) {
     const int first = job * P, count = min(P, a.total_rollouts - first);
-    __syncthreads();   // previous job fully consumed
-#if STOMP_COST_PARAMS_CG
-    // the rollout rows are a once-read stream: 16-byte copies that bypass L1 (.cg) leave it to the voxel gathers
-    if (a.params_16B) {
-      const int DN2 = DN >> 1;
-      for (int i = threadIdx.x; i < count * DN2; i += blockDim.x) {
-        const int p = i / DN2, k = i - p * DN2, ro = first + p;
-        const int b = ro / a.n_rollouts, r = ro - b * a.n_rollouts;
-        const double* src = a.params + size_t(b) * a.params_problem_stride + size_t(r) * a.params_rollout_stride;
-        const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(q + size_t(p) * DN + 2 * k));
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + 2 * k) : "memory");
+    if (job != int(blockIdx.x)) __syncthreads();   // previous job fully consumed
+    if (threadIdx.x == 0) {
+      // robot tables (first job only) and the rollout rows of this job: one bulk copy each, completion on the mbarrier
+      const bool tables = job == int(blockIdx.x);
+      const unsigned row_bytes = a.params_16B ? unsigned(DN) * 8u : 0u;
+      mbar_expect_tx(bar, (tables ? table_bytes : 0u) + row_bytes * unsigned(count));
+      if (tables) {
+        bulk_g2s(smem_u32(nodes), a.nodes, unsigned(sizeof(DevNode<Real>)) * a.num_nodes, bar);
+        if (K > 0) bulk_g2s(sph_addr, a.spheres, unsigned(sizeof(DevSphere<Real>)) * K, bar);
+        bulk_g2s(tab_addr, a.sqrt_table, 256u * unsigned(sizeof(Real)), bar);
+        if (num_cons > 0) bulk_g2s(smem_u32(cons), a.constraints, unsigned(sizeof(DevConstraint<Real>)) * num_cons, bar);
+        if (a.num_clusters > 0) bulk_g2s(smem_u32(clusters), a.clusters, unsigned(sizeof(DevCluster<Real>)) * a.num_clusters, bar);
       }
-    } else
-#endif
-    for (int i = threadIdx.x; i < count * DN; i += blockDim.x) {
-      const int p = i / DN, k = i - p * DN, ro = first + p;
-      const int b = ro / a.n_rollouts, r = ro - b * a.n_rollouts;
-      const double* src = a.params + size_t(b) * a.params_problem_stride + size_t(r) * a.params_rollout_stride;
-      const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(q + i));
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(src + k) : "memory");
+      if (a.params_16B)
+        for (int p = 0; p < count; ++p) {
+          const int ro = first + p;
+          const int b = ro / a.n_rollouts, r = ro - b * a.n_rollouts;
+          bulk_g2s(smem_u32(q + size_t(p) * DN), a.params + size_t(b) * a.params_problem_stride + size_t(r) * a.params_rollout_stride,
+                   row_bytes, bar);
+        }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (!a.params_16B)   // rows that are not 16-byte aligned (odd D*N): plain loads
+      for (int i = threadIdx.x; i < count * DN; i += blockDim.x) {
+        const int p = i / DN, k = i - p * DN, ro = first + p;
+        const int b = ro / a.n_rollouts, r = ro - b * a.n_rollouts;
+        q[i] = a.params[size_t(b) * a.params_problem_stride + size_t(r) * a.params_rollout_stride + k];
+      }
+    if (int(threadIdx.x) < count * 2 * D) {   // start / goal padding values of the job's problems
+      const int p = threadIdx.x / (2 * D), k = threadIdx.x - p * 2 * D;
+      const int b = (first + p) / a.n_rollouts;
+      pads[threadIdx.x] = k < D ? a.pad_start[size_t(b) * D + k] : a.pad_goal[size_t(b) * D + k - D];
+    }
     if (int(threadIdx.x) < count) {   // flags start at "free / satisfied"; ordered before the "= 0" stores by the barriers below
       const int ro = first + threadIdx.x;
       const int b = ro / a.n_rollouts, r = ro - b * a.n_rollouts;
       if (a.collision_free) a.collision_free[size_t(b) * a.flag_problem_stride + a.flag_offset + r] = 1;
       if (a.constraints_satisfied) a.constraints_satisfied[size_t(b) * a.flag_problem_stride + a.flag_offset + r] = 1;
     }
+    mbar_wait(bar, phase);
     __syncthreads();
 
     // ---- handleJointLimits: warp per joint column, <= 11 passes of (arg max violation, rank-1 correction) ----------
@@ -998,6 +1037,15 @@ __global__ void __launch_bounds__(kCostMaxThreads, 4) k_cost(CostArgs<Real> a) {
       if (!a.has_limits[d]) continue;
       const double jmax = a.limit_max[d], jmin = a.limit_min[d];
       double* qd = q + size_t(col) * N;
+      {
+        // most columns violate nothing (C2: 80 %): find that out with compares only, before the arg-max machinery
+        bool any = false;
+        for (int i = lane; i < N; i += 32) {
+          const double v = qd[i];
+          any |= (v > jmax && jmax - v < -1e-6) || (v < jmin && jmin - v > 1e-6);
+        }
+        if (!__any_sync(0xffffffffu, any)) continue;
+      }
       for (int pass = 0; pass < 11; ++pass) {
         double best_abs = 1e-6, best_amount = 0.0;
         int best_idx = -1;
@@ -1042,9 +1090,9 @@ __global__ void __launch_bounds__(kCostMaxThreads, 4) k_cost(CostArgs<Real> a) {
       const bool real_point = gp / seg < count;
       const int ro = first + p;
       const int b = ro / a.n_rollouts, r = ro - b * a.n_rollouts;
-      const double* qp = q + size_t(p) * DN;
-      const double* ps = a.pad_start + size_t(b) * D;
-      const double* pg = a.pad_goal + size_t(b) * D;
+      const double* qp = q + size_t(p) * DN + min(max(t, 0), N - 1);   // this lane's column of the rollout
+      const double* padp = pads + size_t(p) * 2 * D + (t < 0 ? 0 : D);
+      const bool in_pad = t < 0 || t >= N;
       const bool productive = real_point && lane >= 1 && lane <= kTileSteps && t >= 0 && t < N;
       const bool counts = productive || (a.include_pads && real_point && (t == -1 || t == N));
       int collided = 0, violated = 0;
@@ -1064,7 +1112,7 @@ __global__ void __launch_bounds__(kCostMaxThreads, 4) k_cost(CostArgs<Real> a) {
         Real Pm[12];
         {
           Real qv = Real(0);
-          if (nd.q_index >= 0) qv = Real(t < 0 ? ps[nd.q_index] : (t >= N ? pg[nd.q_index] : qp[size_t(nd.q_index) * N + t]));
+          if (nd.q_index >= 0) qv = Real(in_pad ? padp[nd.q_index] : qp[size_t(nd.q_index) * N]);
           if (nd.type == STOMP_JOINT_REVOLUTE) {
             Real sn, cs;
             Math<Real>::sincos_(qv, &sn, &cs);
@@ -1083,19 +1131,17 @@ __global__ void __launch_bounds__(kCostMaxThreads, 4) k_cost(CostArgs<Real> a) {
 #pragma unroll
           for (int i = 0; i < 12; ++i) F[i] = Pm[i];
         } else {
-          Real Pf[12];
-          if (nd.load_slot >= 0) {
+          if (nd.load_slot >= 0) {   // branching trees only: the parent is not the previous node
 #pragma unroll
-            for (int i = 0; i < 12; ++i) Pf[i] = saved[nd.load_slot][i];
-          } else {
-#pragma unroll
-            for (int i = 0; i < 12; ++i) Pf[i] = F[i];
+            for (int i = 0; i < 12; ++i) F[i] = saved[nd.load_slot][i];
           }
+          // F <- F * Pm, row by row in place (row i of the product only needs row i of the parent frame)
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
+            const Real f0 = F[i * 3], f1 = F[i * 3 + 1], f2 = F[i * 3 + 2];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) F[i * 3 + j] = Pf[i * 3] * Pm[j] + Pf[i * 3 + 1] * Pm[3 + j] + Pf[i * 3 + 2] * Pm[6 + j];
-            F[9 + i] = Pf[i * 3] * Pm[9] + Pf[i * 3 + 1] * Pm[10] + Pf[i * 3 + 2] * Pm[11] + Pf[9 + i];
+            for (int j = 0; j < 3; ++j) F[i * 3 + j] = f0 * Pm[j] + f1 * Pm[3 + j] + f2 * Pm[6 + j];
+            F[9 + i] = f0 * Pm[9] + f1 * Pm[10] + f2 * Pm[11] + F[9 + i];
           }
         }
         if (nd.save_slot >= 0) {
