@@ -224,257 +224,369 @@ def _workload_desc(name, sc, B):
 # ---------------------------------------------------------------------------------------------------
 # this engine
 # ---------------------------------------------------------------------------------------------------
-def run_engine(args):
-    import torch
-    from stomp_motion_planner_icra2011_b200 import _abi
-    from stomp_motion_planner_icra2011_b200.engine import Engine
+DEFAULT_PROBLEMS = {"C1": 1, "C2": 1024, "C4": 512, "C5": 1}
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    json_out = sys.stdout
-    if world > 1:
-        # NCCL writes its version banner to fd 1 when the communicator is created; stdout must carry the JSON line only:
-        # keep a private copy of the real stdout for the JSON line and point fd 1 at stderr for everything else
-        sys.stdout.flush()
-        json_out = os.fdopen(os.dup(1), "w")
-        os.dup2(2, 1)
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+def _load_json(*parts):
+    path = os.path.join(ROOT, *parts)
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f)
 
-    def max_over_ranks(x):
-        if dist is None:
+
+class Ctx:
+    """rank / world / NCCL plumbing shared by the measurements"""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        self.json_out = sys.stdout
+        if self.world > 1:
+            # NCCL writes its version banner to fd 1 when the communicator is created; stdout must carry the JSON line only:
+            # keep a private copy of the real stdout for the JSON line and point fd 1 at stderr for everything else
+            sys.stdout.flush()
+            self.json_out = os.fdopen(os.dup(1), "w")
+            os.dup2(2, 1)
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.dist is None:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+
+def timed_run(ctx, eng, first_it, K, W):
+    """W warm-up iterations, then exactly K iterations (stomp_engine_run) between barriers; device time, max over ranks"""
+    eng.run(first_it, W)
+    eng.synchronize()
+    ctx.barrier()
+    l0 = eng.launch_count()
+    eng.timer_start()
+    eng.run(first_it + W, K)
+    ms = eng.timer_stop()
+    ctx.barrier()
+    return ctx.max_over_ranks(ms), eng.launch_count() - l0, first_it + W + K
+
+
+def bench_small(ctx, name, dtype, K, W, problems=None):
+    """short device-resident measurement of another BASELINE.json config (sub-record of the driver-run line)"""
+    from stomp_motion_planner_icra2011_b200.engine import Engine
+    B = problems or DEFAULT_PROBLEMS[name]
+    sc = workload(name, ctx.rank, B)
+    eng = Engine(sc, dtype=dtype, device=ctx.local)
+    ms, launches, _ = timed_run(ctx, eng, 1, K, W)
+    ev = evals_per_iteration(sc, B, False)
+    eng.close()
+    return {"workload": _workload_desc(name, sc, B), "ms_per_step": ms / K, "steps": K, "warmup": W, "value": ev * K / (ms * 1e-3), "unit": UNIT,
+            "evals_per_step": ev, "gpu_launches": int(launches)}
+
+
+def bench_c3(ctx, args, dtype):
+    """config C3: ONE planning problem, args.rollouts rollouts per iteration sharded over the ranks (strong scaling); per
+    iteration two reductions of 2*D*N doubles cross the GPUs — in-kernel over NVLink peer memory (k_shard_stats) and, for
+    comparison, as NCCL all-reduces between host-synchronised phases.  Includes a self-check of the sharded policy against an
+    unsharded engine (the content of tests/test_gpu_multi.py, which needs more than the one GPU of the test box)."""
+    from stomp_motion_planner_icra2011_b200 import scenes, _abi
+    from stomp_motion_planner_icra2011_b200.engine import Engine
+    from stomp_motion_planner_icra2011_b200.distributed import ShardedIteration, PeerShardedIteration, device_views
+    world, rank = ctx.world, ctx.rank
+    R_total = args.rollouts
+    if R_total % world:
+        return {"skipped": "rollouts not divisible by the number of ranks"}
+    K, W = max(3, min(args.steps, 10)), 3
+    sc = scenes.make_scenario("C3", num_problems=1, num_rollouts=R_total // world, seed=7)
+    N, D = sc.num_time_steps, sc.robot.num_dimensions
+    evals_step = R_total * N + N          # the noise-less rollout is replicated on every rank: counted once
+    out = {"workload": "C3: 1 planning problem, %d rollouts/iteration sharded over %d GPU(s) (%d per GPU), N=%d, %d-DOF, no rollout reuse"
+                       % (R_total, world, R_total // world, N, D), "evals_per_step": evals_step, "steps": K, "warmup": W, "unit": UNIT,
+           "scaling": "strong"}
+
+    def timed(iterate, first):
+        it = first
+        for _ in range(W):
+            iterate(it); it += 1
+        eng.synchronize()
+        ctx.barrier()
+        eng.timer_start()
+        for _ in range(K):
+            iterate(it); it += 1
+        ms = eng.timer_stop()
+        ctx.barrier()
+        return ctx.max_over_ranks(ms), it
+
+    eng = Engine(sc, dtype=dtype, device=ctx.local, shard_rank=rank, shard_world=world)
+    if world == 1:
+        ms, it = timed(lambda i: eng.iterate(i, stats=False), 1)
+        out["single_gpu"] = {"ms_per_step": ms / K, "value": evals_step * K / (ms * 1e-3)}
+        out["ms_per_step"], out["value"] = ms / K, evals_step * K / (ms * 1e-3)
+        out["exchange"] = "none (one GPU): chunked statistics, k_shard_stats with the update fused into the second launch"
+    else:
+        peer = PeerShardedIteration(eng, ctx.dist)
+        ms, it = timed(peer.iterate, 1)
+        out["peer"] = {"ms_per_step": ms / K, "value": evals_step * K / (ms * 1e-3),
+                       "how": "both exchanges inside k_shard_stats over NVLink peer memory (P2P stores + flags), whole iteration enqueued "
+                              "without a host sync, 2 statistics launches per iteration"}
+        eng.shard_status()
+        mm, sm = device_views(eng)
+        nccl = ShardedIteration(eng, mm, sm, dist=ctx.dist)
+        ms2, it = timed(nccl.iterate, it)
+        out["nccl"] = {"ms_per_step": ms2 / K, "value": evals_step * K / (ms2 * 1e-3),
+                       "how": "two NCCL all-reduces of 2*D*N doubles between three host-synchronised phases"}
+        out["ms_per_step"], out["value"] = ms / K, evals_step * K / (ms * 1e-3)
+        out["exchange"] = "peer"
+    eng.close()
+    # self-check: 3 sharded iterations against an unsharded engine holding all rollouts (Philox streams are keyed by the global
+    # rollout id, so the draw does not depend on the sharding); every rank must hold the same policy
+    chk = Engine(sc, dtype=dtype, device=ctx.local, shard_rank=rank, shard_world=world)
+    drv = PeerShardedIteration(chk, ctx.dist) if world > 1 else None
+    for i in (1, 2, 3):
+        drv.iterate(i) if drv else chk.iterate(i, stats=False)
+    th = chk.get_parameters()
+    chk.close()
+    diff_ranks = 0.0
+    if world > 1:
+        t = ctx.torch.tensor(th, device="cuda")
+        t0 = t.clone()
+        ctx.dist.broadcast(t0, src=0)
+        diff_ranks = ctx.max_over_ranks(float((t - t0).abs().max().item()))
+    if rank == 0:
+        sc1 = scenes.make_scenario("C3", num_problems=1, num_rollouts=R_total, seed=7)
+        one = Engine(sc1, dtype=dtype, device=ctx.local)
+        for i in (1, 2, 3):
+            one.iterate(i, stats=False)
+        th1 = one.get_parameters()
+        one.close()
+        d = float(np.abs(th - th1).max())
+        out["self_check"] = {"iterations": 3, "max_abs_theta_diff_vs_unsharded": d, "theta_matches_unsharded": bool(d <= 1e-12),
+                             "max_abs_theta_diff_between_ranks": diff_ranks, "ranks_bit_identical": bool(diff_ranks == 0.0)}
+    ctx.barrier()
+    return out
+
+
+def run_engine(args):
+    from stomp_motion_planner_icra2011_b200 import _abi
+    from stomp_motion_planner_icra2011_b200.engine import Engine
+    ctx = Ctx()
+    torch, rank, world, local = ctx.torch, ctx.rank, ctx.world, ctx.local
     name = args.workload
     dtype = _abi.F32 if args.dtype == "f32" else _abi.F64
-    sharded = name == "C3"
-    if sharded:
-        # one planning problem, rollouts sharded over the ranks (strong scaling), two NCCL all-reduces per iteration
-        from stomp_motion_planner_icra2011_b200 import scenes
-        from stomp_motion_planner_icra2011_b200.distributed import ShardedIteration, device_views
-        B = 1
-        total_rollouts = args.rollouts
-        sc = scenes.make_scenario("C3", num_problems=1, num_rollouts=total_rollouts // world, seed=7)
-        eng = Engine(sc, dtype=dtype, device=local, shard_rank=rank, shard_world=world)
-        if world > 1:
-            if args.c3_exchange == "peer":   # both exchanges in-kernel over NVLink peer memory (k_peer_allreduce)
-                from stomp_motion_planner_icra2011_b200.distributed import PeerShardedIteration
-                driver = PeerShardedIteration(eng, dist)
-            else:                            # two NCCL all-reduces between host-synchronised phases
-                mm, sm = device_views(eng)
-                driver = ShardedIteration(eng, mm, sm, dist=dist)
-            eng_iterate = lambda i, stats=False: driver.iterate(i)
-        else:
-            eng_iterate = lambda i, stats=False: eng.iterate(i, stats=stats)
-    else:
-        B = args.problems or {"C1": 1, "C2": 1024, "C4": 512, "C5": 1}.get(name, 1024)
-        sc = workload(name, rank, B)
-        eng = Engine(sc, dtype=dtype, device=local)
-        eng_iterate = lambda i, stats=False: eng.iterate(i, stats=stats)
+    if name == "C3":      # stand-alone C3 run: the sharded record is the line
+        c3 = bench_c3(ctx, args, dtype)
+        if rank == 0:
+            line = {"metric": METRIC, "value": c3["value"], "unit": UNIT, "n_gpus": world, "steps": c3["steps"], "warmup": c3["warmup"],
+                    "ms_per_step": c3["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                    "dtype": args.dtype, "data": "synthetic", "config": {"workload": c3["workload"]}, "c3": c3}
+            ctx.json_out.write(json.dumps(line) + "\n")
+            ctx.json_out.flush()
+        if ctx.dist is not None:
+            ctx.dist.destroy_process_group()
+        return 0
+
+    B = args.problems or DEFAULT_PROBLEMS.get(name, 1024)
+    sc = workload(name, rank, B)
+    eng = Engine(sc, dtype=dtype, device=local)
     D, N, R = eng.D, eng.N, eng.R
     rgen = R - sc.num_reused_rollouts
     K, W = args.steps, max(args.warmup, 3)
 
-    # ---- device-resident throughput ("value") -----------------------------------------------------
-    it = 1
-    for _ in range(W):
-        eng_iterate(it)
-        it += 1
-    eng.synchronize()
+    # ---- device-resident throughput ("value"): inputs resident in HBM, engine Philox noise --------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    barrier()
-    l0 = eng.launch_count()
-    eng.timer_start()
-    for _ in range(K):
-        eng_iterate(it)
-        it += 1
-    ms = eng.timer_stop()
-    barrier()
-    launches = eng.launch_count() - l0
-    ms = max_over_ranks(ms)
+    ms, launches, it = timed_run(ctx, eng, 1, K, W)
     clocks = sampler.stop() if rank == 0 else None
     evals_step = evals_per_iteration(sc, B, False)        # per rank
-    if sharded:   # the noise-less rollout is replicated on every rank: count it once
-        total_evals_step = world * B * rgen * N + N
-    else:
-        total_evals_step = world * evals_step
+    total_evals_step = world * evals_step
     value = total_evals_step * K / (ms * 1e-3)
 
-    # ---- end to end through the C ABI with host buffers ("e2e") ----------------------------------------
-    # host-injection mode: every step copies that step's noise from pinned host memory, runs the iteration,
-    # and reads the per-problem noise-less cost / collision flag and the updated trajectories back.
-    theta_pinned = torch.empty((B, D, N), dtype=torch.float64).pin_memory()
-    theta_np = theta_pinned.numpy()
+    # ---- end to end through the C ABI with host buffers ("e2e") ----------------------------------------------------------
+    # What PolicyImprovementLoop::runSingleIteration(iteration) takes and returns: the iteration number in (the noise scales
+    # sigma_d decay_d^(it-1), D doubles, are uploaded by stomp_engine_iterate), and every step the updated trajectories, the
+    # noise-less rollout's cost and its collision flag out to pinned host memory.  Results of step i are requested
+    # asynchronously and collected while step i+1 runs (two host buffer sets).
     Ke = max(3, min(K, 20))
-    if not sharded:
-        L = np.linalg.cholesky(eng.get(_abi.FIELD_INV_CONTROL_COST))
-        rng = np.random.default_rng(1234 + rank)
-        eps_pinned = torch.empty((B, rgen, D, N), dtype=torch.float64).pin_memory()
-        eps_np = eps_pinned.numpy()
-        z = rng.standard_normal((min(B, 16), rgen, D, N))
-        base = np.einsum("ij,...j->...i", L, z) * 2.0
-        eps_np[...] = np.resize(base, eps_np.shape)
+    res = [(torch.empty((B, D, N), dtype=torch.float64).pin_memory().numpy(),
+            torch.empty(B, dtype=torch.float64).pin_memory().numpy(),
+            torch.empty(B, dtype=torch.int32).pin_memory().numpy()) for _ in range(2)]
+    d2h = int(res[0][0].nbytes + B * 12)
+    pending = []
 
-        # results of step i are requested asynchronously and collected while step i+1 already runs (two host buffer sets)
-        res = [(torch.empty((B, D, N), dtype=torch.float64).pin_memory().numpy(),
-                torch.empty(B, dtype=torch.float64).pin_memory().numpy(),
-                torch.empty(B, dtype=torch.int32).pin_memory().numpy()) for _ in range(2)]
-        pending = []
-        eng.inject_noise_async(eps_np)              # noise of the first timed step
+    def drain():
+        while pending:
+            eng.wait_results(pending.pop(0))
 
-        def e2e_step(i):
-            eng.iterate(i, stats=False)             # consumes the pending injection (device-side wait on the copy)
-            th, co, cf_ = res[i % 2]
-            pending.append(eng.request_results_async(th, co, cf_))   # D2H of theta / noise-less cost / collision flag
-            eng.inject_noise_async(eps_np)          # next step's noise: H2D on the copy stream, overlaps this iteration
-            if len(pending) > 1:
-                eng.wait_results(pending.pop(0))    # step i-1's results are now in host memory
+    def prod_step(i):
+        eng.iterate(i, stats=False)
+        th, co, cf_ = res[i % 2]
+        pending.append(eng.request_results_async(th, co, cf_))
+        if len(pending) > 1:
+            eng.wait_results(pending.pop(0))
 
-        def e2e_drain():
-            while pending:
-                eng.wait_results(pending.pop(0))
-        h2d, api = int(eps_np.nbytes + 8 * D), ("per step: stomp_engine_iterate + stomp_engine_request_results_async(pinned theta, cost, flag) + "
-                                                "stomp_engine_inject_noise_async(pinned eps of the next step) + "
-                                                "stomp_engine_wait_results(previous step)")
-    else:
-        def e2e_step(i):
-            eng_iterate(i)
-            eng.get_parameters(theta_np)
-
-        def e2e_drain():
-            pass
-        h2d, api = 8 * D, "sharded iterate (3 phases + 2 all-reduces) + stomp_engine_get_parameters(pinned); noise is engine Philox"
-    for _ in range(2):
-        e2e_step(it); it += 1
-    e2e_drain()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(Ke):
-        e2e_step(it)
-        it += 1
-    e2e_drain()                                     # every step's results are in host memory when the clock stops
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    # the production mode for comparison: the engine draws its own noise (the reference's runSingleIteration(iteration) takes no
-    # host input either), every step's trajectories / cost / flag still come back to pinned host memory
-    rng_mode = None
-    if not sharded:
-        pend2 = []
-
-        def rng_step(i):
-            eng.iterate(i, stats=False)
-            th, co, cf_ = res[i % 2]
-            pend2.append(eng.request_results_async(th, co, cf_))
-            if len(pend2) > 1:
-                eng.wait_results(pend2.pop(0))
+    def time_steps(step, first):
+        i = first
         for _ in range(2):
-            rng_step(it); it += 1
-        while pend2:
-            eng.wait_results(pend2.pop(0))
-        barrier()
-        t1 = time.perf_counter()
+            step(i); i += 1
+        drain()
+        ctx.barrier()
+        t0 = time.perf_counter()
         for _ in range(Ke):
-            rng_step(it); it += 1
-        while pend2:
-            eng.wait_results(pend2.pop(0))
+            step(i); i += 1
+        drain()                                     # every step's results are in host memory when the clock stops
         torch.cuda.synchronize()
-        rng_s = max_over_ranks(time.perf_counter() - t1)
-        rng_mode = {"value": total_evals_step * Ke / rng_s, "unit": UNIT, "ms_per_step": 1e3 * rng_s / Ke, "h2d_bytes_per_step": 8 * D,
-                    "d2h_bytes_per_step": int(theta_np.nbytes + B * 12),
-                    "note": "engine Philox noise instead of host-injected noise; results still read back every step"}
-    e2e = {"value": total_evals_step * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": int(theta_np.nbytes + B * 12), "ms_per_step": 1e3 * e2e_s / Ke, "steps": Ke, "api": api}
-    if rng_mode is not None:
-        e2e["engine_noise_mode"] = rng_mode
+        return ctx.max_over_ranks(time.perf_counter() - t0), i
 
-    # ---- per-kernel event timing for the roofline (separate pass: events around every launch) ---------
+    prod_s, it = time_steps(prod_step, it)
+    e2e = {"value": total_evals_step * Ke / prod_s, "unit": UNIT, "h2d_bytes_per_step": 8 * D, "d2h_bytes_per_step": d2h,
+           "ms_per_step": 1e3 * prod_s / Ke, "steps": Ke,
+           "api": "per step: stomp_engine_iterate(iteration) [uploads the D noise scales; noise is the engine's Philox stream, like the "
+                  "reference's runSingleIteration(iteration) which takes no host data either] + stomp_engine_request_results_async("
+                  "pinned theta [B][D][N], noise-less cost [B], collision flag [B]) + stomp_engine_wait_results(previous step)"}
+    # the parity mode for comparison: the host ALSO supplies every step's exploration noise (B*R_gen*D*N doubles from pinned
+    # memory).  At 28.7 MB per 0.5 ms step this is a 57 GB/s stream per GPU: one PCIe Gen5 x16 link each, and 8 ranks read
+    # ~460 GB/s from one host NUMA node, which is why this mode cannot scale across the box.
+    L = np.linalg.cholesky(eng.get(_abi.FIELD_INV_CONTROL_COST))
+    rng = np.random.default_rng(1234 + rank)
+    eps_pinned = torch.empty((B, rgen, D, N), dtype=torch.float64).pin_memory()
+    eps_np = eps_pinned.numpy()
+    z = rng.standard_normal((min(B, 16), rgen, D, N))
+    eps_np[...] = np.resize(np.einsum("ij,...j->...i", L, z) * 2.0, eps_np.shape)
+    eng.inject_noise_async(eps_np)              # noise of the first step
+
+    def inj_step(i):
+        eng.iterate(i, stats=False)             # consumes the pending injection (device-side wait on the copy)
+        th, co, cf_ = res[i % 2]
+        pending.append(eng.request_results_async(th, co, cf_))
+        eng.inject_noise_async(eps_np)          # next step's noise: H2D on the copy stream, overlaps this iteration
+        if len(pending) > 1:
+            eng.wait_results(pending.pop(0))
+
+    inj_s, it = time_steps(inj_step, it)
+    eng.iterate(it, stats=False); it += 1        # consumes the last pending injection
+    eng.synchronize()
+    e2e_injected = {"value": total_evals_step * Ke / inj_s, "unit": UNIT, "h2d_bytes_per_step": int(eps_np.nbytes + 8 * D),
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * inj_s / Ke, "steps": Ke,
+                    "host_read_gbs_all_ranks": world * eps_np.nbytes / (inj_s / Ke) / 1e9,
+                    "note": "host-injection (parity) mode: + stomp_engine_inject_noise_async(pinned eps of the next step) every step; "
+                            "bound by host memory / PCIe, not by the GPUs, when several ranks share one host"}
+
+    # ---- per-kernel event timing for the roofline (separate pass: events around every launch, one stream) ------------------
     eng.set_profiling(1)
     Kp = max(3, min(K, 20))
     for _ in range(Kp):
-        eng_iterate(it)
+        eng.iterate(it, stats=False)
         it += 1
     cost_ms, cost_n = eng.get_profile("k_cost")
     all_ms, all_n = eng.get_profile("")
     shares = {}
     for kn in ("k_select_reuse", "k_generate", "k_gather_state", "k_cost", "k_cumulative", "k_update", "k_extra_total",
-               "k_minmax_partial", "k_sums_partial", "k_pair_reduce", "k_finalize"):
+               "k_shard_stats", "k_finalize"):
         m, n = eng.get_profile(kn)
-        shares[kn] = {"ms_per_iteration": m / Kp, "launches_per_iteration": n / Kp}
+        if n:
+            shares[kn] = {"ms_per_iteration": m / Kp, "launches_per_iteration": n / Kp}
     eng.set_profiling(0)
     peaks, peak_kind = _peaks()
+    mine = _load_json("profiles", "r2_peaks.json") or {}
+    counts = (_load_json("profiles", "r2_kcost_counts.json") or {}) if (name == "C2" and B == 1024 and args.dtype == "f64") else {}
     # algorithmic bytes per iteration of the streaming kernels (DESIGN.md section 4): what has to cross HBM once
     BRDN8 = B * R * D * N * 8.0
     algo = {"k_generate": 4.0 * BRDN8,                      # per vector: read theta / previous parameters, write noise, parameters, control costs
             "k_cumulative": BRDN8 * (2.0 + 1.0 / D),        # read control costs + state costs, write cumulative costs
             "k_update": 2.0 * BRDN8}                        # read cumulative costs + noise
     for kn, nbytes in algo.items():
-        ms_it = shares[kn]["ms_per_iteration"]
-        if ms_it > 0:
-            gbs = nbytes / (ms_it * 1e-3) / 1e9
+        if kn in shares and shares[kn]["ms_per_iteration"] > 0:
+            gbs = nbytes / (shares[kn]["ms_per_iteration"] * 1e-3) / 1e9
             shares[kn].update({"algorithmic_bytes_per_iteration": nbytes, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]})
     Ksph = len(sc.robot.spheres)
     vox_bytes = {0: 4, 1: 1, 2: 2}[sc.sdf.voxel_dtype]
     bytes_per_eval = D * 8 + Ksph * vox_bytes + 8 + 1
-    algo_bytes_launch = bytes_per_eval * evals_step / 2.0            # two k_cost launches per iteration
+    evals_launch = evals_step / 2.0                                   # two k_cost launches per iteration (new rollouts, noise-less)
     avg_launch_s = cost_ms * 1e-3 / max(cost_n, 1)
-    achieved = algo_bytes_launch / avg_launch_s / 1e9
-    flops_per_eval = 7 * 110 + Ksph * 54
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath) and name == "C2" and B == 1024 and args.dtype == "f64":
-        with open(tpath) as f:
-            traffic = json.load(f)["k_cost"]["avg_launch_bytes"]
+    achieved = bytes_per_eval * evals_launch / avg_launch_s / 1e9
+    # the roofs k_cost could be bound by, each = (per-eval count of the committed ncu capture of this build) x (evals per launch)
+    # / (this run's event-timed launch duration) against a peak measured on this pool (scripts/peaks.cu)
+    roofs = {"hbm": {"achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                     "per_eval": bytes_per_eval, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)"}}
+    if counts and mine:
+        def roof(per_eval, peak, unit, what):
+            rate = per_eval * evals_launch / avg_launch_s
+            return {"achieved": rate, "peak": peak, "unit": unit, "frac": rate / peak, "per_eval": per_eval, "what": what}
+        roofs["issue"] = roof(counts["warp_inst_per_eval"], mine["issue_warp_inst_per_s"], "warp instructions/s",
+                              "all warp instructions (ncu smsp__inst_executed.sum) against the measured FFMA issue rate of the chip")
+        roofs["fp64"] = roof(counts["fp64_warp_inst_per_eval"] * 64.0, mine["fp64_fma_tflops"] * 1e12, "flop/s (fp64 pipe, 1 warp instruction = 64 flop)",
+                             "fp64-pipe warp instructions (ncu smsp__inst_executed_pipe_fp64.sum) against the measured DFMA rate")
+        roofs["l2_gather"] = roof(counts["l2_tex_read_sectors_per_eval"] * 32.0, mine["l2_gather_sector_gbs"] * 1e9, "B/s of 32-byte L2 sectors",
+                                  "L2 read sectors requested by the SMs (ncu lts__t_sectors_srcunit_tex_op_read.sum) against the measured random-gather rate")
+        binding = max((k for k in roofs), key=lambda k: roofs[k]["frac"])
+    else:
+        binding = "hbm"
     roofline = {"bound": "hbm", "kernel": "k_cost", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": counts.get("dram_bytes_per_launch"),
+                "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
                 "algorithmic_bytes_per_eval": bytes_per_eval, "avg_launch_ms": 1e3 * avg_launch_s,
                 "kernel_share_of_step": cost_ms / all_ms if all_ms else None,
-                "binding": {"roof": "sm instruction issue", "frac": 0.53,
-                            "source": "ncu smsp__issue_active.avg.pct_of_peak_sustained_active of the main launch, "
-                                      "profiles/r1_s3_top_ncu_summary.csv"},
-                "note": "k_cost is instruction-issue bound, not HBM bound: algorithmic traffic is ~%d B/eval against ~%d fp64 flop/eval "
-                        "(est. %.2f TFLOP/s fp64); traffic = ncu DRAM bytes per launch, mostly L2 hits on the u8 grid"
-                        % (bytes_per_eval, flops_per_eval, flops_per_eval * evals_step / 2.0 / avg_launch_s / 1e12),
+                "roofs": roofs, "nearest_roof": binding,
+                "counts_source": counts.get("source"), "peaks_source": mine.get("how"),
+                "note": "k_cost is a latency-bound fp64 / integer kernel over an L2-resident u8 grid: no roof is near (the nearest is "
+                        "instruction issue); HBM is the contract's `bound`, `roofs` holds the measured alternatives",
                 "kernels": shares}
 
+    extras = {}
+    if name == "C2" and not args.no_extras:
+        # the other BASELINE.json configurations, briefly, so that their numbers are driver-run too
+        if world == 1:
+            for other, (k_, w_) in (("C1", (48, 8)), ("C5", (10, 3)), ("C4", (5, 3))):
+                try:
+                    extras[other] = bench_small(ctx, other, dtype, k_, w_)
+                except Exception as ex:      # a sub-record never fails the headline
+                    extras[other] = {"error": repr(ex)}
+        try:
+            extras["C3"] = bench_c3(ctx, args, dtype)
+        except Exception as ex:
+            extras["C3"] = {"error": repr(ex)}
+            ctx.barrier()
+
     if rank == 0:
-        cpu = cpu_baseline(name) if world == 1 and not args.no_cpu_baseline and not sharded else None
+        cpu = cpu_baseline(name) if world == 1 and not args.no_cpu_baseline else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-                "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": args.dtype,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
                 "data": "synthetic",
                 "config": {"workload": _workload_desc(name, sc, B),
-                           "parallelism": ("rollouts sharded over %d GPU(s), 2 reductions of 2*D*N doubles per iteration, %s" %
-                                           (world, "in-kernel over NVLink peer memory (k_peer_allreduce), no host sync" if args.c3_exchange == "peer"
-                                            else "NCCL all-reduces between host-synchronised phases"))
-                           if sharded else ("problems sharded over %d GPU(s), no collective" % world),
+                           "parallelism": "problems sharded over %d GPU(s), no collective" % world,
                            "l2": "per-iteration working set %.2f GB of rollout arrays >> 126 MB L2 (no flush needed)"
                                  % (6 * B * R * D * N * 8 / 1e9),
                            "noise": "engine Philox RNG", "evals_per_step_per_gpu": evals_step,
                            "iterations_per_sec": 1e3 * K / ms,
-                           "problem_iterations_per_sec": (1 if sharded else world * B) * 1e3 * K / ms,
+                           "problem_iterations_per_sec": world * B * 1e3 * K / ms,
                            "rollouts_per_sec": total_evals_step / N * 1e3 * K / ms},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+                "clocks": clocks, "e2e": e2e, "e2e_injected": e2e_injected, "gpu_launches": int(launches), "roofline": roofline}
+        if "C3" in extras:
+            line["c3"] = extras.pop("C3")
+        if extras:
+            line["other_workloads"] = extras
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        json_out.write(json.dumps(line) + "\n")
-        json_out.flush()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+        ctx.json_out.write(json.dumps(line) + "\n")
+        ctx.json_out.flush()
+    if ctx.dist is not None:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
     return 0
 
 
@@ -490,8 +602,7 @@ def main():
     ap.add_argument("--rollouts", type=int, default=65536, help="total rollouts of the C3 workload")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--c3-exchange", choices=["peer", "nccl"], default="peer",
-                    help="C3 (rollout-sharded) only: how the two per-iteration reductions cross GPUs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C1 / C4 / C5 / C3 sub-records of the C2 line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -306,8 +306,16 @@ int stomp_engine_add_extra_rollouts(void* engine, const double* costs);
 /* PolicyImprovementLoop::runSingleIteration(iteration_number) with the built-in GPU Task
  * (src/policy_improvement_loop.cpp:143-202).  stats may be NULL (no host sync then). */
 int stomp_engine_iterate(void* engine, int32_t iteration_number, stomp_iter_stats* stats);
-/* iterations first..first+count-1 back to back on the device, no host round trip in between. */
+/* iterations first..first+count-1 back to back on the device, no host round trip in between.  With graph mode 1, steady-state
+ * iterations (rollout reuse primed, engine noise, no profiling) are replayed from a CUDA graph of 8 captured iterations of the
+ * two-stream schedule: one graph launch instead of ~90 kernel launches, with the Philox generation counter and the
+ * per-iteration noise scales advanced on the device; results are bit-identical to stomp_engine_iterate called count times. */
 int stomp_engine_run(void* engine, int32_t first_iteration, int32_t count, stomp_iter_stats* last_stats);
+/* 0 (default): stomp_engine_run launches every kernel from the host; 1: it replays CUDA graphs when it can.  Off by default
+ * because the loop is bound by kernel-to-kernel dependency latency, not by host launch rate, and graph nodes resolve their
+ * cross-branch dependencies more slowly than stream launches do (measured on B200: C1 0.140 vs 0.093 ms per iteration, C2 0.570
+ * vs 0.505; profiles/README.md).  env STOMP_GRAPH sets the default. */
+int stomp_engine_set_graph_mode(void* engine, int32_t mode);
 int stomp_engine_synchronize(void* engine);
 /* Results of the last iteration's noise-less rollout (what stomp_engine_iterate returns through `stats`), for callers
  * that launched the iteration with stats == NULL; waits for the iteration to finish. */

@@ -1,5 +1,5 @@
 """torchrun --nproc-per-node W scripts/check_peer_exchange.py : config C3's rollout-sharded iteration with the exchanges done
-(a) by NCCL all-reduces between host-synchronised phases and (b) in-kernel over NVLink peer memory (k_peer_allreduce), on the
+(a) by NCCL all-reduces between host-synchronised phases and (b) in-kernel over NVLink peer memory (k_shard_stats), on the
 same seeds.  Checks: every rank holds the same theta; (a) and (b) agree to rounding (NCCL's summation order is its own); both
 agree with an unsharded engine holding all rollouts on rank 0's GPU.  Prints timing of both."""
 import os
@@ -53,6 +53,25 @@ def main():
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         assert torch.equal(lo, hi), "ranks disagree on theta"
+    # mapping the peers a second time on the same engines (the epoch restarted while the flags kept the old
+    # session's values, so the first waits passed at once): the session restarts cleanly and the result is the same
+    def run_reopened():
+        eng = Engine(sc, device=local, shard_rank=rank, shard_world=world)
+        drv = PeerShardedIteration(eng, dist)
+        for it in range(1, 3):
+            drv.iterate(it)
+        eng.synchronize()
+        dist.barrier()
+        drv = PeerShardedIteration(eng, dist)      # re-open: flags cleared, epoch 0 again, barrier inside
+        for it in range(3, 2 + iters):
+            drv.iterate(it)
+        eng.synchronize()
+        eng.shard_status()
+        theta = eng.get(_abi.FIELD_THETA)[0].copy()
+        eng.close()
+        return theta
+    th_re = run_reopened()
+    assert np.array_equal(th_re, th_peer), "re-opened peer session differs: %g" % np.abs(th_re - th_peer).max()
     scale = np.abs(th_nccl).max()
     err = np.abs(th_nccl - th_peer).max() / scale
     assert err < 1e-9, err

@@ -45,10 +45,11 @@ struct DevBuf {
   size_t n = 0;
   cudaError_t alloc(size_t count) {
     release();
-    n = count;
     if (count == 0) return cudaSuccess;
     cudaError_t e = cudaMalloc(&p, count * sizeof(T));
-    if (e == cudaSuccess) e = cudaMemset(p, 0, count * sizeof(T));
+    if (e != cudaSuccess) { p = nullptr; return e; }
+    n = count;   // only a successful allocation has a size: `buf.n >= need` checks never pass on a null buffer
+    e = cudaMemset(p, 0, count * sizeof(T));
     // the handle's stream is non-blocking: make sure the legacy-stream memset cannot overtake later copies
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     return e;
@@ -76,7 +77,7 @@ struct Engine {
   bool overlap = true, tail_dirty = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_copy_done[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
-  int inject_write = 0, inject_pending_buf = 0;
+  int inject_write = 0, inject_pending_buf = 0, inject_pending_n = 0;
   int64_t launches = 0;
   bool f32 = false;
 
@@ -130,9 +131,9 @@ struct Engine {
   DevBuf<int> scratch_flags;
   DevBuf<stomp_sphere_debug> debug;
   DevBuf<double> part, minmax, sums;  // sharded / huge-R statistics
-  // peer-memory exchange of the sharded statistics (k_peer_allreduce): this rank's buffer, the peers' mappings of theirs
+  // peer-memory exchange of the sharded statistics (k_shard_stats): this rank's buffer, the peers' mappings of theirs
   DevBuf<unsigned char> xchg;
-  DevBuf<int> xchg_err;
+  DevBuf<int> xchg_err, shard_counters;
   unsigned char* peer_base[kMaxPeers] = {nullptr};
   bool peers_open = false;
   unsigned long long xchg_epoch = 0;
@@ -146,6 +147,17 @@ struct Engine {
   Sdf sdf;
   size_t scratch_n = 0;
 
+  // CUDA-graph replay of stomp_engine_run (steady-state iterations, engine noise): kGraphIters iterations of the two-stream
+  // schedule captured once; the per-iteration host work (Philox generation counter, noise scales) moves to k_advance_iteration
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // one per parity of the params / state-cost ping-pong at entry
+  uint64_t graph_key[2] = {0, 0}, config_epoch = 1;   // config_epoch: bumped by every setter that changes what the launches carry
+  int64_t graph_launches = 0;                  // kernel launches inside one replay
+  int graph_mode = 0;                          // 0 off (default: replay measured slower, profiles/README.md), 1 on (STOMP_GRAPH=1 / stomp_engine_set_graph_mode)
+  bool capturing = false;
+  int64_t steady_iterations = 0;               // iterations run in the steady state since set_problems (buffers are sized)
+  DevBuf<uint32_t> dev_generation;
+  DevBuf<int> dev_table_index;
+  DevBuf<double> scale_table;
   // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
   // STOMP_CHAIN_PROBE=1: two timing events per overlapped iteration (end of the main stream's k_cumulative, end of the tail
   // stream's chain) and, at destroy, the mean of "tail end - main end" on stderr: which chain k_update really waits for,
@@ -443,6 +455,7 @@ GenArgs base_gen_args(Engine& e) {
   a.control = e.control.p;
   a.band = e.band_view();
   a.st = e.stencil();
+  a.iteration_ptr = e.capturing ? e.dev_generation.p : nullptr;
   return a;
 }
 
@@ -650,27 +663,44 @@ int launch_update(Engine& e, int apply, bool fuse_extra_control) {
   return check_launch(e, "k_update");
 }
 
-// huge-R / sharded statistics, phase by phase (B == 1)
+// huge-R / sharded statistics (B == 1): one k_shard_stats launch per phase (partials, reduction over the chunks, optional
+// peer-memory exchange, optional fused projection + update)
 constexpr int kChunks = 128;
-int launch_minmax(Engine& e) {
-  const int DN = e.D * e.N, rpc = (e.R + kChunks - 1) / kChunks, nch = (e.R + rpc - 1) / rpc;
-  dim3 grid((DN + 127) / 128, nch);
+int launch_finalize(Engine& e, int apply);
+
+int launch_shard_stats(Engine& e, bool is_max, bool exchange, bool finalize, int apply) {
+  // at least 32 rollouts per chunk: a chunk-CTA should have more to do than its share of the cross-chunk reduction
+  const int DN = e.D * e.N, rpc = std::max((e.R + kChunks - 1) / kChunks, std::min(e.R, 32)), nch = (e.R + rpc - 1) / rpc;
+  const int colblocks = (DN + 127) / 128;
+  // the fused finalize keeps the band tables and all D rows in the last CTA's shared memory — which every CTA of the launch then
+  // reserves: only worth it while that is small (C3: 18 KB; C5's 110 KB cut the partial reductions to 2 CTAs / SM, 0.70 -> 0.88 ms
+  // per iteration).  The probability tap needs the global sums before the update.  Both fall back to a separate k_finalize launch.
+  size_t smem = (size_t(e.N) * 16 + size_t(e.D) * (e.N | 1)) * 8;
+  const bool fuse = finalize && !e.probabilities.p && smem <= 24 * 1024;
+  if (!fuse) smem = 0;
+  ShardStatsArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.R = e.R; a.D = e.D; a.N = e.N; a.rollouts_per_chunk = rpc;
+  a.is_max = is_max ? 1 : 0;
+  a.do_exchange = exchange ? 1 : 0;
+  a.do_finalize = fuse ? 1 : 0;
+  a.apply = apply;
+  a.cumulative = e.cumulative.p; a.noise = e.noise.p; a.minmax = e.minmax.p; a.part = e.part.p;
+  a.out = is_max ? e.minmax.p : e.sums.p;
+  a.counters = e.shard_counters.p;
+  a.rank = e.desc.rollout_shard_rank; a.world = e.desc.rollout_shard_world;
+  if (exchange) {
+    a.epoch = ++e.xchg_epoch;
+    for (int r = 0; r < a.world; ++r) a.peers[r] = e.peer_base[r];
+  }
+  a.err = e.xchg_err.p;
+  a.updates = e.updates.p; a.theta = e.theta.p; a.band = e.band_view();
+  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_shard_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   begin_launch(e);
-  k_minmax_partial<<<grid, 128, 0, e.ws>>>(e.R, DN, rpc, e.cumulative.p, e.part.p);
-  if (check_launch(e, "k_minmax_partial")) return 1;
-  begin_launch(e);
-  k_pair_reduce<<<(2 * DN + 127) / 128, 128, 0, e.ws>>>(DN, nch, 1, e.part.p, e.minmax.p);
-  return check_launch(e, "k_pair_reduce");
-}
-int launch_sums(Engine& e) {
-  const int DN = e.D * e.N, rpc = (e.R + kChunks - 1) / kChunks, nch = (e.R + rpc - 1) / rpc;
-  dim3 grid((DN + 127) / 128, nch);
-  begin_launch(e);
-  k_sums_partial<<<grid, 128, 0, e.ws>>>(e.R, DN, rpc, e.cumulative.p, e.noise.p, e.minmax.p, e.part.p);
-  if (check_launch(e, "k_sums_partial")) return 1;
-  begin_launch(e);
-  k_pair_reduce<<<(2 * DN + 127) / 128, 128, 0, e.ws>>>(DN, nch, 0, e.part.p, e.sums.p);
-  return check_launch(e, "k_pair_reduce");
+  k_shard_stats<<<dim3(colblocks, nch), 128, smem, e.ws>>>(a);
+  if (check_launch(e, is_max ? "k_shard_stats_max" : "k_shard_stats_sum")) return 1;
+  if (finalize && !fuse) return launch_finalize(e, apply);
+  return 0;
 }
 int launch_finalize(Engine& e, int apply) {
   if (e.probabilities.p) {
@@ -679,7 +709,7 @@ int launch_finalize(Engine& e, int apply) {
     if (check_launch(e, "k_probabilities")) return 1;
   }
   begin_launch(e);
-  k_finalize<<<e.D, block_for(e.N), band_smem(e, 1), e.ws>>>(e.D, e.N, apply, e.sums.p, e.updates.p, e.theta.p, e.band_view());
+  k_finalize<<<e.D, block_for(e.N), band_smem(e, 1), e.ws>>>(e.D, e.N, apply, e.sums.p, e.updates.p, e.theta.p, e.band_view(), e.xchg_err.p);
   return check_launch(e, "k_finalize");
 }
 
@@ -730,6 +760,9 @@ int launch_generate_range(Engine& e, const RolloutPlan& p, int r_begin, int r_co
   a.r_begin = r_begin;
   a.r_count = r_count;
   const bool uses_injection = p.injected && r_begin < e.num_gen;
+  if (uses_injection && e.inject_pending_n < e.num_gen)
+    return fail("injected noise holds " + std::to_string(e.inject_pending_n) + " rollouts per problem but this iteration generates " +
+                std::to_string(e.num_gen));
   if (uses_injection) CUDA_TRY(cudaStreamWaitEvent(e.ws, e.ev_copy_done[e.inject_pending_buf], 0));
   // Two kernels produce the same outputs (the same linear maps on the same Philox normals; they agree to rounding):
   //  * k_generate_dense — one CTA per vector, a few microseconds of latency: small batches (one planning problem = 35 vectors)
@@ -791,8 +824,7 @@ int step_improve(Engine& e, int apply) {
   if (launch_cumulative(e)) return 1;
   if (e.huge_path()) {
     if (e.B != 1) return fail("the sharded / huge-rollout statistics path supports num_problems == 1 only");
-    if (launch_minmax(e) || launch_sums(e)) return 1;
-    return launch_finalize(e, apply);
+    return launch_shard_stats(e, true, false, false, 0) || launch_shard_stats(e, false, false, true, apply);
   }
   return launch_update(e, apply, false);
 }
@@ -834,7 +866,7 @@ int iterate_serial(Engine& e, int iteration_number) {
   if (join_streams(e)) return 1;
   if (iterate_front(e, iteration_number)) return 1;
   if (e.huge_path()) {
-    if (launch_minmax(e) || launch_sums(e) || launch_finalize(e, 1)) return 1;
+    if (launch_shard_stats(e, true, false, false, 0) || launch_shard_stats(e, false, false, true, 1)) return 1;
   } else {
     if (launch_update(e, 1, true)) return 1;
     return step_extra(e, true, iteration_number, true);
@@ -857,9 +889,15 @@ int iterate_once(Engine& e, int iteration_number) {
   }
   if (!e.overlap || (e.prof_on && !e.prof_timeline)) return iterate_serial(e, iteration_number);
   e.ws = e.stream;
-  std::vector<double> scale(e.D);
-  for (int d = 0; d < e.D; ++d) scale[d] = e.noise_stddev[d] * std::pow(e.noise_decay[d], iteration_number - 1);
-  if (set_noise_scale(e, scale.data())) return 1;
+  if (e.capturing) {
+    begin_launch(e);
+    k_advance_iteration<<<1, 32, 0, e.stream>>>(e.dev_generation.p, e.dev_table_index.p, e.scale_table.p, e.D, e.noise_scale.p);
+    if (check_launch(e, "k_advance_iteration")) return 1;
+  } else {
+    std::vector<double> scale(e.D);
+    for (int d = 0; d < e.D; ++d) scale[d] = e.noise_stddev[d] * std::pow(e.noise_decay[d], iteration_number - 1);
+    if (set_noise_scale(e, scale.data())) return 1;
+  }
   e.control_cost_weight = e.desc.smoothness_cost_weight;
   RolloutPlan p;
   plan_rollouts(e, p);
@@ -888,7 +926,7 @@ int iterate_once(Engine& e, int iteration_number) {
   if (e.chain_probe && p.reuse) CUDA_TRY(cudaEventRecord(e.probe_main, e.stream));
   CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_tail, 0));
   const bool huge = e.huge_path();
-  if (huge ? (launch_minmax(e) || launch_sums(e) || launch_finalize(e, 1)) : launch_update(e, 1, true)) return 1;
+  if (huge ? (launch_shard_stats(e, true, false, false, 0) || launch_shard_stats(e, false, false, true, 1)) : launch_update(e, 1, true)) return 1;
   CUDA_TRY(cudaEventRecord(e.ev_upd, e.stream));
   if (e.chain_probe && p.reuse && (iteration_number % 16) == 0) {      // sampled: the read-back synchronises
     CUDA_TRY(cudaEventRecord(e.probe_upd, e.stream));
@@ -907,12 +945,109 @@ int iterate_once(Engine& e, int iteration_number) {
   const int rc = step_extra(e, true, iteration_number, !huge);
   e.tail_dirty = true;
   e.ws = e.stream;
+  if (p.reuse || e.Rre == 0) ++e.steady_iterations;
   return rc;
+}
+
+// ---- CUDA-graph replay ------------------------------------------------------------------------------------------------------
+constexpr int kGraphIters = 8;   // even: the params / state-cost ping-pong returns to where it started
+
+bool graph_eligible(const Engine& e, int iteration_number) {
+  return e.graph_mode != 0 && e.overlap && !e.prof_on && !e.chain_probe && !e.injected_pending && !e.huge_path() &&
+         e.desc.rollout_shard_world == 1 && iteration_number > 1 && (e.reused_next || e.Rre == 0) && e.steady_iterations >= 2 &&
+         !e.cull_dirty && e.have_robot && e.have_sdf && e.have_problems;
+}
+
+// captures kGraphIters steady-state iterations (main + tail stream) into e.graph_exec; host bookkeeping is restored afterwards
+int capture_iterations(Engine& e) {
+  cudaGraphExec_t& exec = e.graph_exec[e.cur];
+  if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; }
+  if (join_streams(e)) return 1;
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  const int cur0 = e.cur, num_gen0 = e.num_gen;
+  const uint32_t gen0 = e.generation;
+  const bool extra0 = e.extra_added, reused0 = e.reused_next;
+  const int64_t launches0 = e.launches, steady0 = e.steady_iterations;
+  CUDA_TRY(cudaStreamBeginCapture(e.stream, cudaStreamCaptureModeThreadLocal));
+  e.capturing = true;
+  int rc = 0;
+  // fork: the tail stream joins the capture
+  if (cudaEventRecord(e.ev_upd, e.stream) != cudaSuccess || cudaStreamWaitEvent(e.tail_stream, e.ev_upd, 0) != cudaSuccess) rc = 1;
+  e.tail_dirty = false;
+  for (int k = 0; k < kGraphIters && !rc; ++k) rc = iterate_once(e, 2);   // iteration_number only matters through "== 1"
+  // join: everything on the tail stream is part of the graph
+  if (!rc && (cudaEventRecord(e.ev_tail, e.tail_stream) != cudaSuccess || cudaStreamWaitEvent(e.stream, e.ev_tail, 0) != cudaSuccess)) rc = 1;
+  e.capturing = false;
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(e.stream, &graph);
+  e.graph_launches = e.launches - launches0;
+  e.cur = cur0; e.num_gen = num_gen0; e.generation = gen0; e.extra_added = extra0; e.reused_next = reused0;
+  e.launches = launches0; e.steady_iterations = steady0;
+  e.tail_dirty = false;
+  e.ws = e.stream;
+  if (rc || ce != cudaSuccess || !graph) {
+    (void)cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    return rc ? 1 : fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+  }
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) { exec = nullptr; (void)cudaGetLastError(); return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
+  e.graph_key[e.cur] = e.config_epoch;
+  return 0;
+}
+
+// runs `groups` x kGraphIters iterations starting at first_iteration by replaying the captured graph
+int replay_iterations(Engine& e, int first_iteration, int groups) {
+  if (!e.graph_exec[e.cur] || e.graph_key[e.cur] != e.config_epoch) {
+    if (capture_iterations(e)) return 1;
+  }
+  const int total = groups * kGraphIters;
+  std::vector<double> table(size_t(total) * e.D);
+  for (int i = 0; i < total; ++i)
+    for (int d = 0; d < e.D; ++d)
+      table[size_t(i) * e.D + d] = e.noise_stddev[d] * std::pow(e.noise_decay[d], first_iteration + i - 1);
+  if (join_streams(e)) return 1;
+  if (e.scale_table.n < table.size()) {
+    CUDA_TRY(cudaStreamSynchronize(e.stream));
+    CUDA_TRY(e.scale_table.alloc(std::max<size_t>(table.size(), size_t(1024) * e.D)));
+    // the graphs hold the table's address: a new allocation needs new captures
+    e.graph_key[0] = e.graph_key[1] = 0;
+    if (capture_iterations(e)) return 1;
+  }
+  const int zero = 0;
+  CUDA_TRY(cudaMemcpyAsync(e.scale_table.p, table.data(), table.size() * 8, cudaMemcpyHostToDevice, e.stream));
+  CUDA_TRY(cudaMemcpyAsync(e.dev_generation.p, &e.generation, sizeof(uint32_t), cudaMemcpyHostToDevice, e.stream));
+  CUDA_TRY(cudaMemcpyAsync(e.dev_table_index.p, &zero, sizeof(int), cudaMemcpyHostToDevice, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));   // the uploads read host stack memory
+  for (int g = 0; g < groups; ++g) CUDA_TRY(cudaGraphLaunch(e.graph_exec[e.cur], e.stream));
+  // the graphs run on the main stream only: whatever the tail stream is given next (the reuse selection of a following plain
+  // iteration) must wait for them
+  CUDA_TRY(cudaEventRecord(e.ev_upd, e.stream));
+  CUDA_TRY(cudaStreamWaitEvent(e.tail_stream, e.ev_upd, 0));
+  // the host mirror of what the replayed iterations did (PolicyImprovement bookkeeping of iterate_once)
+  e.generation += uint32_t(total);
+  e.num_gen = e.R - e.Rre;
+  e.extra_added = true;
+  e.steady_iterations += total;
+  e.launches += int64_t(groups) * e.graph_launches;
+  e.tail_dirty = false;   // the graph ends with the tail stream joined
+  return 0;
+}
+
+// sticky flag of the peer-memory exchange (k_shard_stats): a rank that never arrived leaves theta without the update
+int check_shard_error(Engine& e) {
+  if (e.desc.rollout_shard_world <= 1 || !e.peers_open || !e.xchg_err.p) return 0;
+  int err = 0;
+  CUDA_TRY(cudaMemcpyAsync(&err, e.xchg_err.p, sizeof(int), cudaMemcpyDeviceToHost, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return err ? fail("a peer exchange timed out: some rank did not reach the same iteration; the policy was not updated") : 0;
 }
 
 int fill_stats(Engine& e, stomp_iter_stats* stats) {
   if (!stats) return 0;
   if (join_streams(e)) return 1;
+  if (check_shard_error(e)) return 1;
   stats->num_generated_rollouts = e.num_gen;
   if (stats->noiseless_cost)
     CUDA_TRY(cudaMemcpyAsync(stats->noiseless_cost, e.noiseless_sum.p, size_t(e.B) * 8, cudaMemcpyDeviceToHost, e.stream));
@@ -1017,12 +1152,12 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   e.device = desc->device;
   e.f32 = desc->dtype == STOMP_F32;
   std::string err;
-  if (!sh::build_policy_matrices(*desc, e.pm, err)) { delete ep; return fail(err); }
-  if (e.pm.chol.hb > kMaxHb) { delete ep; return fail("control cost bandwidth too large"); }
+  if (!sh::build_policy_matrices(*desc, e.pm, err)) { stomp_engine_destroy(ep); return fail(err); }
+  if (e.pm.chol.hb > kMaxHb) { stomp_engine_destroy(ep); return fail("control cost bandwidth too large"); }
   auto bail = [&](cudaError_t c, const char* what) {
     std::string m = std::string(what) + ": " + cudaGetErrorString(c);
     (void)cudaGetLastError();
-    delete ep;
+    stomp_engine_destroy(ep);
     return fail(m);
   };
   cudaError_t c;
@@ -1060,10 +1195,11 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   ALLOC(e.extra_state, size_t(e.B) * e.N); ALLOC(e.extra_control, BDN); ALLOC(e.updates, BDN); ALLOC(e.noiseless_sum, size_t(e.B));
   ALLOC(e.reuse_src, size_t(e.B) * std::max(1, e.Rre)); ALLOC(e.collision_free, size_t(e.B) * (e.R + 1));
   ALLOC(e.constraints_ok, size_t(e.B) * (e.R + 1));
-  ALLOC(e.noise_scale, size_t(e.D));
+  ALLOC(e.noise_scale, size_t(e.D)); ALLOC(e.dev_generation, 1); ALLOC(e.dev_table_index, 1);
   ALLOC(e.extra_clipped, BDN); ALLOC(e.best_traj, BDN); ALLOC(e.best_cost, size_t(e.B));
   ALLOC(e.track_state, size_t(e.B) * sizeof(TrackState)); ALLOC(e.num_done, 1);
   ALLOC(e.part, size_t(kChunks) * 2 * e.D * e.N); ALLOC(e.minmax, size_t(2) * e.D * e.N); ALLOC(e.sums, size_t(2) * e.D * e.N);
+  ALLOC(e.shard_counters, size_t(2) + size_t(e.D) * e.N / 128 + 1); ALLOC(e.xchg_err, 1);
 #undef ALLOC
   // matrices
   std::vector<double> qt(size_t(e.N) * e.N);
@@ -1083,7 +1219,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   }
   if (upload(e, e.band_fw, fw.data(), fw.size()) || upload(e, e.band_bw, bw.data(), bw.size()) ||
       upload(e, e.proj_scale, e.pm.proj_scale.data(), size_t(e.N)) || upload(e, e.qinv_t, qt.data(), qt.size())) {
-    delete ep;
+    stomp_engine_destroy(ep);
     return 1;
   }
   {
@@ -1102,13 +1238,14 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
     for (int j = 0; j < N; ++j)
       for (int t = 0; t < N; ++t) msd[size_t(j) * N + t] = e.pm.Rinv(j, t) * e.pm.proj_scale[j];
     if (upload(e, e.dense_cinv, cinv.data(), cinv.size()) || upload(e, e.dense_ms, msd.data(), msd.size())) {
-      delete ep;
+      stomp_engine_destroy(ep);
       return 1;
     }
   }
   // A/B switches of the generation kernels: STOMP_GENERATE=band|dense forces one, STOMP_NO_DENSE=1 is "band"
   if (const char* g = getenv("STOMP_GENERATE")) e.gen_mode = !strcmp(g, "band") ? 1 : !strcmp(g, "dense") ? 2 : 0;
   if (getenv("STOMP_NO_DENSE") && atoi(getenv("STOMP_NO_DENSE")) != 0) e.gen_mode = 1;
+  if (getenv("STOMP_GRAPH")) e.graph_mode = atoi(getenv("STOMP_GRAPH")) != 0 ? 1 : 0;
   e.chain_probe = getenv("STOMP_CHAIN_PROBE") && atoi(getenv("STOMP_CHAIN_PROBE")) != 0;
   if (e.chain_probe && (cudaEventCreate(&e.probe_main) != cudaSuccess || cudaEventCreate(&e.probe_tail) != cudaSuccess ||
                         cudaEventCreate(&e.probe_upd) != cudaSuccess))
@@ -1120,7 +1257,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   std::vector<double> zeros(e.D, 0.0);
   if (upload(e, e.has_limits, hl.data(), size_t(e.D)) || upload(e, e.limit_min, zeros.data(), size_t(e.D)) ||
       upload(e, e.limit_max, zeros.data(), size_t(e.D))) {
-    delete ep;
+    stomp_engine_destroy(ep);
     return 1;
   }
   if ((c = cudaStreamSynchronize(e.stream)) != cudaSuccess) return bail(c, "cudaStreamSynchronize");
@@ -1142,6 +1279,8 @@ int stomp_engine_destroy(void* h) {
     if (e->ev_snap_tail[i]) cudaEventDestroy(e->ev_snap_tail[i]);
     if (e->ev_results[i]) cudaEventDestroy(e->ev_results[i]);
   }
+  for (int i = 0; i < 2; ++i)
+    if (e->graph_exec[i]) cudaGraphExecDestroy(e->graph_exec[i]);
   if (e->ev_tail) cudaEventDestroy(e->ev_tail);
   if (e->peers_open)
     for (int r = 0; r < e->desc.rollout_shard_world; ++r)
@@ -1192,6 +1331,7 @@ int stomp_engine_set_robot(void* h, const stomp_segment* segments, int32_t num_s
   CUDA_TRY(e.debug.alloc(size_t(e.N + 3) * std::max(1, e.K)));
   CUDA_TRY(cudaStreamSynchronize(e.stream));
   e.have_robot = true;
+  ++e.config_epoch;
   return 0;
 }
 
@@ -1212,6 +1352,7 @@ int stomp_engine_set_sdf(void* h, const void* voxels, int32_t nx, int32_t ny, in
   if (e.f32 ? upload_sqrt_table<float>(e) : upload_sqrt_table<double>(e)) return 1;
   e.have_sdf = true;
   e.cull_dirty = true;
+  ++e.config_epoch;
   return 0;
 }
 
@@ -1325,6 +1466,7 @@ int stomp_engine_build_sdf_points(void* h, const double size[3], const double or
   if (e.f32 ? upload_sqrt_table<float>(e) : upload_sqrt_table<double>(e)) return 1;
   e.have_sdf = true;
   e.cull_dirty = true;
+  ++e.config_epoch;
   return 0;
 }
 
@@ -1349,6 +1491,7 @@ int stomp_engine_set_constraints(void* h, const stomp_orientation_constraint* co
     if (constraints[i].segment < 0 || constraints[i].segment >= int(e.robot.seg_node.size())) return fail("constraint segment out of range");
   e.constraints.assign(constraints, constraints + n);
   e.constraint_cost_weight = constraint_cost_weight;
+  ++e.config_epoch;
   return e.f32 ? upload_constraints<float>(e) : upload_constraints<double>(e);
 }
 
@@ -1399,6 +1542,7 @@ int stomp_engine_set_dynamics(void* h, const stomp_link_inertia* inertia, int32_
   e.chain_len = int(links.size());
   for (int k = 0; k < 3; ++k) e.gravity[k] = gravity[k];
   e.torque_weight = torque_cost_weight;
+  ++e.config_epoch;
   return 0;
 }
 
@@ -1429,6 +1573,7 @@ int stomp_engine_set_problems(void* h, const double* start, const double* goal) 
   e.cur = 0;
   e.injected_pending = false;
   e.have_problems = true;
+  e.steady_iterations = 0;
   return 0;
 }
 
@@ -1445,7 +1590,7 @@ int stomp_engine_get_parameters(void* h, double* theta) {
   if (!theta) return fail("null argument");
   CUDA_TRY(cudaMemcpyAsync(theta, e.theta.p, size_t(e.B) * e.D * e.N * 8, cudaMemcpyDeviceToHost, e.stream));
   CUDA_TRY(cudaStreamSynchronize(e.stream));
-  return 0;
+  return check_shard_error(e);
 }
 
 int stomp_engine_update_parameters(void* h, const double* updates) {
@@ -1484,6 +1629,7 @@ int stomp_engine_compute_control_costs(void* h, const double* parameters, const 
 int stomp_engine_seed(void* h, uint64_t seed) {
   ENGINE_OR_FAIL(h);
   e.seed = seed;
+  ++e.config_epoch;
   return 0;
 }
 
@@ -1500,6 +1646,7 @@ int stomp_engine_inject_noise_async(void* h, const double* eps, int32_t n) {
   CUDA_TRY(cudaMemcpy2DAsync(e.eps_in2[buf].p, size_t(e.R) * e.D * e.N * 8, eps, row, row, e.B, cudaMemcpyHostToDevice, e.copy_stream));
   CUDA_TRY(cudaEventRecord(e.ev_copy_done[buf], e.copy_stream));
   e.inject_pending_buf = buf;
+  e.inject_pending_n = n;
   e.injected_pending = true;
   return 0;
 }
@@ -1628,9 +1775,26 @@ int stomp_engine_iterate(void* h, int32_t iteration_number, stomp_iter_stats* st
 int stomp_engine_run(void* h, int32_t first_iteration, int32_t count, stomp_iter_stats* last_stats) {
   ENGINE_NOJOIN(h);
   if (!e.have_problems) return fail("set_problems must be called first");
-  for (int i = 0; i < count; ++i)
-    if (iterate_once(e, first_iteration + i)) return 1;
+  int i = 0;
+  while (i < count) {
+    const int it = first_iteration + i;
+    if (count - i >= kGraphIters && graph_eligible(e, it)) {
+      const int groups = (count - i) / kGraphIters;
+      if (replay_iterations(e, it, groups)) return 1;
+      i += groups * kGraphIters;
+      continue;
+    }
+    if (iterate_once(e, it)) return 1;
+    ++i;
+  }
   return fill_stats(e, last_stats);
+}
+
+int stomp_engine_set_graph_mode(void* h, int32_t mode) {
+  ENGINE_OR_FAIL(h);
+  if (mode != 0 && mode != 1) return fail("graph mode must be 0 or 1");
+  e.graph_mode = mode;
+  return 0;
 }
 
 int stomp_engine_optimize(void* h, int32_t max_iterations, int32_t max_after_cf, stomp_optimize_stats* stats) {
@@ -1638,12 +1802,19 @@ int stomp_engine_optimize(void* h, int32_t max_iterations, int32_t max_after_cf,
   if (!e.have_problems) return fail("set_problems must be called first");
   if (max_iterations < 1) return fail("max_iterations must be >= 1");
   if (e.desc.rollout_shard_world > 1) return fail("optimize is not available on a rollout-sharded engine");
+  // the reference builds a fresh PolicyImprovementLoop for every optimize() (src/stomp_optimizer.cpp:262-263): no rollouts of an
+  // earlier run are reused and no extra rollout is pending.  The Philox generation counter is kept, so a second run draws new noise.
+  e.reused_next = false;
+  e.extra_added = false;
+  e.injected_pending = false;
+  e.num_gen = 0;
   std::vector<TrackState> init(e.B, TrackState{0, -1, -1, -1, 0, 0});
   if (upload(e, e.track_state, reinterpret_cast<const unsigned char*>(init.data()), init.size() * sizeof(TrackState))) return 1;
   CUDA_TRY(cudaMemsetAsync(e.num_done.p, 0, sizeof(int), e.stream));
   CUDA_TRY(cudaStreamSynchronize(e.stream));
   const bool want_log = stats && stats->costs;
   if (want_log && e.cost_log.n < size_t(max_iterations) * e.B) CUDA_TRY(e.cost_log.alloc(size_t(max_iterations) * e.B));
+  if (want_log) CUDA_TRY(cudaMemsetAsync(e.cost_log.p, 0, e.cost_log.n * sizeof(double), e.stream));   // entries past a problem's last iteration read 0
   const int check_every = 16;   // host looks at the "all problems done" counter this often; results do not depend on it
   int it = 0;
   for (; it < max_iterations; ++it) {
@@ -1875,7 +2046,6 @@ int stomp_engine_shard_ipc_handle(void* h, void* handle_out, size_t handle_bytes
   if (e.desc.rollout_shard_world > kMaxPeers) return fail("too many ranks for the peer exchange");
   if (e.xchg.n != xchg_bytes(e)) {
     CUDA_TRY(e.xchg.alloc(xchg_bytes(e)));   // zero-filled: flags start below every epoch
-    CUDA_TRY(e.xchg_err.alloc(1));
   }
   cudaIpcMemHandle_t ipc;
   CUDA_TRY(cudaIpcGetMemHandle(&ipc, e.xchg.p));
@@ -1900,22 +2070,16 @@ int stomp_engine_shard_open_peers(void* h, const void* handles, int32_t count) {
     CUDA_TRY(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
     e.peer_base[r] = static_cast<unsigned char*>(p);
   }
+  // A (re-)opened session starts at epoch 0 on every rank: the flag area of the own buffer still holds the epochs of the
+  // previous session and must not satisfy the first waits.  Every rank clears its own flags here; the caller must barrier
+  // between this call and the first exchange (a peer's first flag store must not be overtaken by the clear).
+  const size_t n = size_t(2) * e.D * e.N;
+  CUDA_TRY(cudaMemsetAsync(e.xchg.p + 2 * size_t(W) * n * sizeof(double), 0, 2 * size_t(W) * sizeof(unsigned long long), e.stream));
+  CUDA_TRY(cudaMemsetAsync(e.xchg_err.p, 0, sizeof(int), e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
   e.peers_open = true;
   e.xchg_epoch = 0;
   return 0;
-}
-
-static int launch_peer_allreduce(Engine& e, double* local, int is_max) {
-  PeerArgs a;
-  std::memset(&a, 0, sizeof(a));
-  a.rank = e.desc.rollout_shard_rank; a.world = e.desc.rollout_shard_world; a.n = 2 * e.D * e.N; a.is_max = is_max;
-  a.epoch = ++e.xchg_epoch;
-  for (int r = 0; r < a.world; ++r) a.peers[r] = e.peer_base[r];
-  a.local = local;
-  a.err = e.xchg_err.p;
-  begin_launch(e);
-  k_peer_allreduce<<<1, 1024, 0, e.ws>>>(a);
-  return check_launch(e, "k_peer_allreduce");
 }
 
 /* One iteration of a rollout-sharded engine with both exchanges done in-kernel over peer memory: everything is enqueued on
@@ -1929,13 +2093,11 @@ int stomp_engine_iterate_sharded_fused(void* h, int32_t iteration_number) {
     if (join_streams(e)) return 1;
   }
   e.ws = e.stream;
-  if (iterate_front(e, iteration_number) || launch_minmax(e)) return 1;
-  if (e.desc.rollout_shard_world > 1 && launch_peer_allreduce(e, e.minmax.p, 1)) return 1;
-  if (launch_sums(e)) return 1;
-  if (e.desc.rollout_shard_world > 1 && launch_peer_allreduce(e, e.sums.p, 0)) return 1;
-  // the previous iteration's noise-less rollout (tail stream) still reads theta: the update waits for it
+  const bool exchange = e.desc.rollout_shard_world > 1;
+  if (iterate_front(e, iteration_number) || launch_shard_stats(e, true, exchange, false, 0)) return 1;
+  // the previous iteration's noise-less rollout (tail stream) still reads theta: the launch that ends in the update waits for it
   if (join_streams(e)) return 1;
-  if (launch_finalize(e, 1)) return 1;
+  if (launch_shard_stats(e, false, exchange, true, 1)) return 1;
   // the noise-less rollout of ONE problem is a ~80 us latency chain nothing in the next iteration depends on (no rollout
   // reuse when rollouts are sharded): it runs on the tail stream under the next iteration's sampling and costs
   CUDA_TRY(cudaEventRecord(e.ev_upd, e.stream));
@@ -1950,11 +2112,7 @@ int stomp_engine_iterate_sharded_fused(void* h, int32_t iteration_number) {
 /* 0 when no peer exchange has timed out (blocks until the stream is idle) */
 int stomp_engine_shard_status(void* h) {
   ENGINE_OR_FAIL(h);
-  if (!e.xchg_err.p) return 0;
-  int err = 0;
-  CUDA_TRY(cudaMemcpyAsync(&err, e.xchg_err.p, sizeof(int), cudaMemcpyDeviceToHost, e.stream));
-  CUDA_TRY(cudaStreamSynchronize(e.stream));
-  return err ? fail("a peer exchange timed out: some rank did not reach the same iteration") : 0;
+  return check_shard_error(e);
 }
 
 /* phase 0: rollouts, costs, local {max c, max -c}  -> caller all-reduces minmax with MAX
@@ -1965,8 +2123,8 @@ int stomp_engine_iterate_sharded_phase(void* h, int32_t iteration_number, int32_
   if (!e.have_problems) return fail("set_problems must be called first");
   if (e.B != 1) return fail("rollout sharding requires num_problems == 1");
   switch (phase) {
-    case 0: if (iterate_front(e, iteration_number)) return 1; return launch_minmax(e);
-    case 1: return launch_sums(e);
+    case 0: if (iterate_front(e, iteration_number)) return 1; return launch_shard_stats(e, true, false, false, 0);
+    case 1: return launch_shard_stats(e, false, false, false, 0);
     case 2: if (launch_finalize(e, 1)) return 1; return step_extra(e, true, iteration_number);
     default: return fail("phase must be 0, 1 or 2");
   }

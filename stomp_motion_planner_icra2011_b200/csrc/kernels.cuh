@@ -148,6 +148,20 @@ __global__ void k_select_reuse(const double* __restrict__ totals, int R, int R_r
   }
 }
 
+// k_advance_iteration (CUDA-graph replay of stomp_engine_run): what the host does between two iterations, on the device —
+// the Philox generation counter advances and the noise scales sigma_d decay_d^(it-1) of the next iteration are taken from a
+// table the host computed for the whole run (so they are bit-identical to the values the per-iteration upload would carry).
+__global__ void k_advance_iteration(uint32_t* __restrict__ generation, int* __restrict__ table_index, const double* __restrict__ table,
+                                    int D, double* __restrict__ noise_scale) {
+  const int idx = *table_index;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) noise_scale[d] = table[size_t(idx) * D + d];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *generation += 1u;
+    *table_index = idx + 1;
+  }
+}
+
 struct GenArgs {
   int B, R, D, N;
   int R_gen;                 // slots < R_gen are new, slots >= R_gen are reused (gathered)
@@ -160,6 +174,7 @@ struct GenArgs {
   double control_weight;     // 0.5 * control_cost_weight
   uint64_t seed;
   uint32_t iteration;
+  const uint32_t* iteration_ptr;   // non-null (CUDA-graph replay): the Philox generation counter lives on the device
   int64_t rollout_id_offset; // global rollout id of local slot 0 (rollout sharding)
   int64_t rollouts_global;   // global number of rollouts per problem (stream id stride)
   const double* theta;       // [B][D][N]
@@ -363,6 +378,7 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
     double* out_params = active ? a.params + row_off : nullptr;
     const double sg = active ? a.noise_scale[d] : 0.0;
     const uint64_t stream = (uint64_t(b) * uint64_t(a.rollouts_global) + uint64_t(a.rollout_id_offset + r)) * uint64_t(a.D) + d;
+    const uint32_t gen_iteration = a.iteration_ptr ? *a.iteration_ptr : a.iteration;
     BandWindow bw;
     for (int c0 = last_c0; c0 >= 0; c0 -= kChunk) {
       const int len = min(kChunk, N - c0);
@@ -374,7 +390,7 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
           const int p_lo = c0 >> 1, p_hi = (c0 + len - 1) >> 1;
           for (int pr = p_lo; pr <= p_hi; ++pr) {
             double z0, z1;
-            normal_pair(a.seed, stream, a.iteration, uint32_t(pr), z0, z1);
+            normal_pair(a.seed, stream, gen_iteration, uint32_t(pr), z0, z1);
             const int i0 = 2 * pr - c0, i1 = i0 + 1;
             if (i0 >= 0 && i0 < len) my_tE[i0] = z0;
             if (i1 >= 0 && i1 < len) my_tE[i1] = z1;
@@ -581,9 +597,10 @@ __global__ void __launch_bounds__(128) k_generate_dense(GenArgs a, const double*
   }
   if (philox) {
     const uint64_t stream = (uint64_t(b) * uint64_t(a.rollouts_global) + uint64_t(a.rollout_id_offset + r)) * uint64_t(a.D) + d;
+    const uint32_t gen_iteration = a.iteration_ptr ? *a.iteration_ptr : a.iteration;
     for (int pr = threadIdx.x; 2 * pr < N; pr += blockDim.x) {
       double z0, z1;
-      normal_pair(a.seed, stream, a.iteration, uint32_t(pr), z0, z1);
+      normal_pair(a.seed, stream, gen_iteration, uint32_t(pr), z0, z1);
       z[2 * pr] = z0;
       if (2 * pr + 1 < N) z[2 * pr + 1] = z1;
     }
@@ -1888,85 +1905,72 @@ __global__ void k_axpy(size_t n, const double* __restrict__ x, double* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// Rollout-sharded / huge-R statistics (config C3): partial reductions over rollout chunks.
-//   k_minmax_partial : part[chunk][2][D*N] = {max c, max -c}
-//   k_minmax_reduce  : minmax[2][D*N]
-//   k_sums_partial   : part[chunk][2][D*N] = {sum e, sum e*eps}
-//   k_sums_reduce    : sums[2][D*N]
-//   k_finalize       : u = (sum e*eps / sum e) -> projection -> theta
-// ---------------------------------------------------------------------------------------------
-__global__ void k_minmax_partial(int R, int DN, int rollouts_per_chunk, const double* __restrict__ cumulative,
-                                 double* __restrict__ part) {
-  const int chunk = blockIdx.y;
-  const int r0 = chunk * rollouts_per_chunk, r1 = min(R, r0 + rollouts_per_chunk);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < DN; i += gridDim.x * blockDim.x) {
-    double mx = -1.0e300, mn = 1.0e300;
-    for (int r = r0; r < r1; ++r) {
-      double v = cumulative[size_t(r) * DN + i];
-      mx = fmax(mx, v);
-      mn = fmin(mn, v);
-    }
-    part[(size_t(chunk) * 2 + 0) * DN + i] = mx;
-    part[(size_t(chunk) * 2 + 1) * DN + i] = -mn;
-  }
-}
-
-__global__ void k_pair_reduce(int DN, int nchunks, int is_max, const double* __restrict__ part, double* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * DN) return;
-  int which = i / DN, j = i - which * DN;
-  double acc = is_max ? -1.0e300 : 0.0;
-  for (int c = 0; c < nchunks; ++c) {
-    double v = part[(size_t(c) * 2 + which) * DN + j];
-    acc = is_max ? fmax(acc, v) : acc + v;
-  }
-  out[i] = acc;
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_peer_allreduce: the cross-GPU exchange of the rollout-sharded statistics (config C3) done by the GPUs themselves over
-// NVLink peer memory instead of an NCCL collective between host-synchronised phases.  Every rank owns one exchange buffer
-//   data[2 phases][world][n] doubles | flags[2 phases][world] u64
-// mapped into every other rank's address space (CUDA IPC).  One CTA per rank:
-//   1. store the local n-vector into slot [phase][my rank] of EVERY peer's buffer (P2P stores), fence (system scope)
-//   2. raise flag [phase][my rank] = epoch on every peer
-//   3. wait until all `world` flags of the own buffer reached the epoch, then reduce the world slots in rank order (MAX or SUM:
-//      the same order on every rank, so all ranks hold bit-identical results) into the local vector, in place.
-// Epochs increase monotonically (two exchanges per iteration, alternating phase buffers), so a rank can only overwrite its
-// slot of phase p after every peer has raised a later flag, i.e. finished reading the previous use of that slot.
-// The wait is bounded (~2 s of SM clocks); on expiry the error flag is set instead of hanging the device.
+// k_shard_stats: one launch per statistics phase of the rollout-sharded / huge-R path (config C3), grid = (column blocks of
+// 128 (d,t) elements) x (rollout chunks):
+//   1. every CTA reduces its chunk of rollouts for its 128 columns: phase MAX {max c, max -c}, phase SUM {sum e, sum e*eps}
+//   2. the LAST chunk-CTA of a column block (atomic ticket) reduces that block over the chunks, in chunk order
+//   3. the LAST column block to finish does the cross-GPU exchange over NVLink peer memory, in place:
+//        store the local 2*D*N vector into slot [phase][my rank] of EVERY peer's exchange buffer (P2P stores), fence at
+//        system scope, raise flag [phase][my rank] = epoch on every peer, wait for the `world` flags of the own buffer, reduce
+//        the world slots in rank order (the same order on every rank: all ranks hold bit-identical statistics)
+//   4. (phase SUM, fused finalize) u = (sum e*eps / sum e) .* s, the projection M u as two banded triangular solves (one lane
+//      per dimension), theta += update.
+// Exchange buffer of a rank: data[2 phases][world][n] doubles | flags[2 phases][world] u64, mapped into every peer (CUDA IPC).
+// Epochs increase monotonically (two exchanges per iteration, alternating phase buffers), so a rank can only overwrite its slot
+// of phase p after every peer has raised a later flag, i.e. finished reading the previous use of that slot.  The wait is
+// bounded (~2 s of SM clocks); on expiry the sticky error flag is set, the reduction is skipped, and no later finalize applies
+// an update (the host sees the flag in stomp_engine_shard_status / get_parameters / the iteration statistics).
+// Round 1 ran k_*_partial, k_pair_reduce, k_peer_allreduce and k_finalize as separate launches (7 per iteration).
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 16;
-struct PeerArgs {
-  int rank, world, n, is_max;
+struct ShardStatsArgs {
+  int R, D, N, rollouts_per_chunk;
+  int is_max;                 // 1: phase MAX, 0: phase SUM
+  int do_exchange;            // peer-memory all-reduce of the result (world > 1, peers mapped)
+  int do_finalize, apply;     // phase SUM: projection + update in the same launch
+  const double* cumulative;   // [R][D*N]
+  const double* noise;        // [R][D*N]
+  const double* minmax;       // [2][D*N] (phase SUM input)
+  double* part;               // [chunks][2][D*N]
+  double* out;                // [2][D*N]: minmax (phase MAX) or sums (phase SUM)
+  int* counters;              // [column blocks + 1], zero between launches
+  // exchange
+  int rank, world;
   unsigned long long epoch;
-  unsigned char* peers[kMaxPeers];   // base of every rank's exchange buffer as seen from this rank
-  double* local;                     // [n] in: this rank's partial, out: the reduction over all ranks
+  unsigned char* peers[kMaxPeers];
   int* err;
+  // finalize
+  double* updates;            // [D*N]
+  double* theta;              // [D*N]
+  Band band;
 };
 
-__global__ void __launch_bounds__(1024) k_peer_allreduce(PeerArgs a) {
-  const int n = a.n, W = a.world, ph = a.is_max ? 0 : 1;
+__device__ __forceinline__ void peer_exchange(const ShardStatsArgs& a, double* local, int n) {
+  const int W = a.world, ph = a.is_max ? 0 : 1;
   const size_t data_bytes = size_t(2) * W * n * sizeof(double);
   for (int p = 0; p < W; ++p) {
     double* dst = reinterpret_cast<double*>(a.peers[p]) + (size_t(ph) * W + a.rank) * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = a.local[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldcg(local + i);
   }
   __threadfence_system();
   __syncthreads();
-  if (int(threadIdx.x) < W) {
-    volatile unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peers[threadIdx.x] + data_bytes) + ph * W + a.rank;
+  __shared__ int s_timeout;
+  if (threadIdx.x == 0) s_timeout = 0;
+  __syncthreads();
+  for (int p = threadIdx.x; p < W; p += blockDim.x) {
+    volatile unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peers[p] + data_bytes) + ph * W + a.rank;
     *f = a.epoch;
   }
-  if (int(threadIdx.x) < W) {
-    volatile unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peers[a.rank] + data_bytes) + ph * W + threadIdx.x;
+  for (int p = threadIdx.x; p < W; p += blockDim.x) {
+    volatile unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peers[a.rank] + data_bytes) + ph * W + p;
     const long long t0 = clock64();
     while (*f < a.epoch) {
-      if (clock64() - t0 > 4000000000ll) { *a.err = 1; break; }
+      if (clock64() - t0 > 4000000000ll) { *a.err = 1; s_timeout = 1; break; }
     }
   }
   __syncthreads();
   __threadfence_system();
+  if (s_timeout) return;        // some rank never arrived: leave the local partial, the sticky flag stops the update
   const volatile double* src = reinterpret_cast<const double*>(a.peers[a.rank]) + size_t(ph) * W * n;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double acc = src[i];
@@ -1974,28 +1978,95 @@ __global__ void __launch_bounds__(1024) k_peer_allreduce(PeerArgs a) {
       const double v = src[size_t(r) * n + i];
       acc = a.is_max ? fmax(acc, v) : acc + v;
     }
-    a.local[i] = acc;
+    local[i] = acc;
   }
+  __threadfence();
+  __syncthreads();
 }
 
-__global__ void k_sums_partial(int R, int DN, int rollouts_per_chunk, const double* __restrict__ cumulative,
-                               const double* __restrict__ noise, const double* __restrict__ minmax,
-                               double* __restrict__ part) {
-  const int chunk = blockIdx.y;
-  const int r0 = chunk * rollouts_per_chunk, r1 = min(R, r0 + rollouts_per_chunk);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < DN; i += gridDim.x * blockDim.x) {
-    double mx = minmax[i], mn = -minmax[DN + i];
-    double denom = mx - mn;
-    if (denom < 1e-8) denom = 1e-8;
-    double se = 0.0, see = 0.0;
-    const double h = -10.0 / denom;
-    for (int r = r0; r < r1; ++r) {
-      double e = exp_weight(h * (cumulative[size_t(r) * DN + i] - mn));
-      se += e;
-      see += e * noise[size_t(r) * DN + i];
+__global__ void __launch_bounds__(128) k_shard_stats(ShardStatsArgs a) {
+  extern __shared__ double sm_fin[];   // finalize only: band tables [N][16] + u [D][N|1]
+  __shared__ int s_last;
+  const int DN = a.D * a.N, chunk = blockIdx.y, nchunks = gridDim.y;
+  const int r0 = chunk * a.rollouts_per_chunk, r1 = min(a.R, r0 + a.rollouts_per_chunk);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < DN) {
+    if (a.is_max) {
+      double mx = -1.0e300, mn = 1.0e300;
+      for (int r = r0; r < r1; ++r) {
+        const double v = a.cumulative[size_t(r) * DN + i];
+        mx = fmax(mx, v);
+        mn = fmin(mn, v);
+      }
+      a.part[(size_t(chunk) * 2 + 0) * DN + i] = mx;
+      a.part[(size_t(chunk) * 2 + 1) * DN + i] = -mn;
+    } else {
+      const double mx = a.minmax[i], mn = -a.minmax[DN + i];
+      double denom = mx - mn;
+      if (denom < 1e-8) denom = 1e-8;
+      const double h = -10.0 / denom;
+      double se = 0.0, see = 0.0;
+      for (int r = r0; r < r1; ++r) {
+        const double e = exp_weight(h * (a.cumulative[size_t(r) * DN + i] - mn));
+        se += e;
+        see += e * a.noise[size_t(r) * DN + i];
+      }
+      a.part[(size_t(chunk) * 2 + 0) * DN + i] = se;
+      a.part[(size_t(chunk) * 2 + 1) * DN + i] = see;
     }
-    part[(size_t(chunk) * 2 + 0) * DN + i] = se;
-    part[(size_t(chunk) * 2 + 1) * DN + i] = see;
+  }
+  // ---- last chunk-CTA of this column block: reduce over the chunks (chunk order) --------------------------------------
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(a.counters + 1 + blockIdx.x, 1) == nchunks - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (i < DN) {
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      double acc = a.is_max ? -1.0e300 : 0.0;
+      for (int c = 0; c < nchunks; ++c) {
+        const double v = __ldcg(a.part + (size_t(c) * 2 + which) * DN + i);
+        acc = a.is_max ? fmax(acc, v) : acc + v;
+      }
+      a.out[size_t(which) * DN + i] = acc;
+    }
+  }
+  // ---- last column block: exchange across the GPUs, then (phase SUM) the update -----------------------------------------
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a.counters[1 + blockIdx.x] = 0;
+    s_last = atomicAdd(a.counters, 1) == int(gridDim.x) - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) a.counters[0] = 0;
+  __threadfence();
+  if (a.do_exchange) peer_exchange(a, a.out, 2 * DN);
+  if (!a.do_finalize) return;
+  if (a.err != nullptr && *reinterpret_cast<volatile int*>(a.err) != 0) return;   // a timed-out exchange never updates theta
+  const int N = a.N, D = a.D, stride = N | 1;
+  double* sfw = sm_fin;
+  double* sbw = sfw + N * 8;
+  double* u = sbw + N * 8;
+  for (int k = threadIdx.x; k < N * 8; k += blockDim.x) sfw[k] = a.band.fw[k], sbw[k] = a.band.bw[k];
+  for (int k = threadIdx.x; k < DN; k += blockDim.x) {
+    const int d = k / N, t = k - d * N;
+    u[d * stride + t] = (__ldcg(a.out + DN + k) / __ldcg(a.out + k)) * a.band.proj_scale[t];
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    band_forward(u + d * stride, sfw, N);
+    band_backward(u + d * stride, sbw, N);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < DN; k += blockDim.x) {
+    const int d = k / N, t = k - d * N;
+    const double v = u[d * stride + t];
+    a.updates[k] = v;
+    if (a.apply) a.theta[k] += v;
   }
 }
 
@@ -2012,8 +2083,9 @@ __global__ void k_probabilities(int R, int DN, const double* __restrict__ cumula
 }
 
 __global__ void k_finalize(int D, int N, int apply, const double* __restrict__ sums, double* __restrict__ updates,
-                           double* __restrict__ theta, Band band) {
+                           double* __restrict__ theta, Band band, const int* __restrict__ err) {
   extern __shared__ double smem[];
+  if (err != nullptr && *err != 0) return;   // a timed-out peer exchange never updates theta
   const int d = blockIdx.x, DN = D * N;
   double* sfw = smem;
   double* sbw = sfw + N * 8;

@@ -32,7 +32,7 @@ EXPORTS = [
     "stomp_engine_set_constraints", "stomp_engine_execute_constraints_satisfied",
     "stomp_engine_request_results_async", "stomp_engine_wait_results", "stomp_engine_set_dynamics",
     "stomp_engine_shard_ipc_handle", "stomp_engine_shard_open_peers", "stomp_engine_iterate_sharded_fused",
-    "stomp_engine_shard_status", "stomp_engine_build_sdf_points",
+    "stomp_engine_shard_status", "stomp_engine_build_sdf_points", "stomp_engine_set_graph_mode",
 ]
 
 
@@ -275,6 +275,10 @@ class Engine:
         st = _abi.IterStats(_dp(cost), _ip(cf), 0, 0, None)
         self._ck(self.L.stomp_engine_run(self.h, first_iteration, count, C.byref(st)))
         return cost, cf, st.num_generated_rollouts
+
+    def set_graph_mode(self, mode):
+        """0: run() launches every kernel itself; 1 (default): steady-state iterations are replayed from a CUDA graph."""
+        self._ck(self.L.stomp_engine_set_graph_mode(self.h, int(mode)))
 
     def optimize(self, max_iterations, max_iterations_after_collision_free):
         """StompOptimizer::optimize for the whole batch; returns a dict of per-problem statistics."""

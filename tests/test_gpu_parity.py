@@ -639,6 +639,31 @@ def test_two_stream_overlap_is_invisible():
             np.testing.assert_array_equal(a.get(f), other.get(f))
 
 
+@pytest.mark.parametrize("name,problems", [("C1", 1), ("C1", 5), ("tiny", 3)])
+def test_graph_replay_is_invisible(name, problems):
+    """stomp_engine_run replays steady-state iterations from a CUDA graph (8 iterations per launch, Philox counter and noise
+    scales advanced on the device): bit-identical to launching every kernel from the host, including the iterations around
+    the replayed block and a second run() that starts on the other ping-pong parity."""
+    sc = scenes.make_scenario(name, num_problems=problems)
+    sc.noise_decay = np.full(sc.robot.num_dimensions, 0.97)       # the per-iteration noise scale must follow the table
+    a, b = _engine(sc, keep_intermediates=1), _engine(sc, keep_intermediates=1)
+    a.set_graph_mode(1)
+    b.set_graph_mode(0)
+    for eng in (a, b):
+        eng.run(1, 3)             # not steady yet: plain launches
+        eng.run(4, 29)            # 24 replayed + 5 plain
+        eng.run(33, 9)            # odd parity at entry: the second graph
+    assert a.launch_count() == b.launch_count() + 4 * 8            # one k_advance_iteration per replayed iteration
+    ca, fa = a.last_stats()
+    cb, fb = b.last_stats()
+    np.testing.assert_array_equal(ca, cb)
+    np.testing.assert_array_equal(fa, fb)
+    for f in (_abi.FIELD_THETA, _abi.FIELD_PARAMETERS, _abi.FIELD_STATE_COSTS, _abi.FIELD_CONTROL_COSTS, _abi.FIELD_NOISE,
+              _abi.FIELD_ROLLOUT_TOTAL_COSTS, _abi.FIELD_PROBABILITIES, _abi.FIELD_NOISELESS_COSTS):
+        np.testing.assert_array_equal(a.get(f), b.get(f))
+    assert np.abs(a.get(_abi.FIELD_NOISE)).max() > 0
+
+
 def test_async_result_readback_pipeline():
     """request_results_async / wait_results: results of iteration i collected while iteration i+1 runs equal the
     synchronous read-back, with injected noise uploaded asynchronously as well (the bench's e2e loop)."""
