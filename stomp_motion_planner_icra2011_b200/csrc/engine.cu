@@ -123,7 +123,8 @@ struct Engine {
   DevBuf<double> band_fw, band_bw, proj_scale, qinv_t, noise_scale;
   DevBuf<double> dense_cinv, dense_ms;   // [N][N] C^-1 and R^-1 diag(s) for k_generate_dense (small batches)
   bool dense_update = true;   // A/B switch (STOMP_NO_DENSE_UPDATE=1): k_update projects with the banded solves
-  int gen_mode = 0;   // 0: pick k_generate / k_generate_dense by batch shape; 1, 2: always that one (A/B)
+  bool dmma_update = true;    // A/B switch (STOMP_NO_DMMA=1): the dense projection runs as scalar DFMAs instead of DMMA tiles
+  int gen_mode = 0;   // 0: pick k_generate / k_generate_dense / k_generate_mma by batch shape; 1, 2, 3: always that one (A/B)
   DevBuf<double> limit_min, limit_max;
   DevBuf<int> has_limits;
   DevBuf<unsigned char> nodes, spheres, sqrt_table, vox;
@@ -646,6 +647,7 @@ int launch_update(Engine& e, int apply, bool fuse_extra_control) {
   a.updates = e.updates.p; a.theta = e.theta.p; a.band = e.band_view();
   // the projection as a dense product (kernels.cuh) while the N x N matrix is a few hundred KB of L2-resident reads per CTA
   a.dense_ms = (e.dense_update && e.N <= 512) ? e.dense_ms.p : nullptr;
+  a.use_dmma = e.dmma_update ? 1 : 0;
   auto update_smem = [&](int rows) {
     const size_t stride = size_t(e.N + 2 * kPad) | 1;
     return (2 * rows * stride + size_t(rows) * 2 * kPad + (a.dense_ms ? 0 : size_t(e.N) * 16)) * 8;
@@ -774,8 +776,20 @@ int launch_generate_range(Engine& e, const RolloutPlan& p, int r_begin, int r_co
   const double est_band = 0.95e-6 * e.N;
   const double est_dense = 5.0e-6 + nvec * 12.0 * double(e.N) * e.N / 4.0e12;
   int kind = e.gen_mode;
+  // k_generate_mma — both linear maps as DMMA GEMMs over tiles of 16 vectors: large batches whose three shared tiles fit
+  const size_t mma_smem = (size_t(2) * ((e.N + 7) & ~7) + size_t(e.N) + 2 * kPad) * kMmaS * 8;
+  const bool mma_ok = mma_smem <= 200 * 1024 && e.N <= 1024;
+  // measured on B200 (profiles/README.md, round 2): the DMMA kernel loses to the band solves at N = 100 (C2: 0.230 vs 0.108 ms
+  // per launch under ncu; 13 % of the fp64 tensor peak, its A-fragment loads and stencils cost as many instructions as the
+  // band kernel's whole sweep), so it is only taken on request (STOMP_GENERATE=mma)
   if (kind == 0) kind = (e.N <= 1024 && est_dense < 0.5 * est_band) ? 2 : 1;
-  if (kind == 2) {
+  if (kind == 3 && !mma_ok) kind = 1;
+  if (kind == 3) {
+    if (mma_smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_generate_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, int(mma_smem)));
+    begin_launch(e);
+    k_generate_mma<<<unsigned((nvec + kMmaV - 1) / kMmaV), 128, mma_smem, e.ws>>>(a, e.dense_cinv.p, e.dense_ms.p);
+    if (check_launch(e, "k_generate")) return 1;
+  } else if (kind == 2) {
     const size_t smem = (size_t(3) * e.N + 2 * kPad) * 8;
     begin_launch(e);
     k_generate_dense<<<unsigned(nvec), 128, smem, e.ws>>>(a, e.dense_cinv.p, e.dense_ms.p);
@@ -1243,7 +1257,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
     }
   }
   // A/B switches of the generation kernels: STOMP_GENERATE=band|dense forces one, STOMP_NO_DENSE=1 is "band"
-  if (const char* g = getenv("STOMP_GENERATE")) e.gen_mode = !strcmp(g, "band") ? 1 : !strcmp(g, "dense") ? 2 : 0;
+  if (const char* g = getenv("STOMP_GENERATE")) e.gen_mode = !strcmp(g, "band") ? 1 : !strcmp(g, "dense") ? 2 : !strcmp(g, "mma") ? 3 : 0;
   if (getenv("STOMP_NO_DENSE") && atoi(getenv("STOMP_NO_DENSE")) != 0) e.gen_mode = 1;
   if (getenv("STOMP_GRAPH")) e.graph_mode = atoi(getenv("STOMP_GRAPH")) != 0 ? 1 : 0;
   e.chain_probe = getenv("STOMP_CHAIN_PROBE") && atoi(getenv("STOMP_CHAIN_PROBE")) != 0;
@@ -1251,6 +1265,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
                         cudaEventCreate(&e.probe_upd) != cudaSuccess))
     e.chain_probe = false;
   e.dense_update = !(getenv("STOMP_NO_DENSE_UPDATE") && atoi(getenv("STOMP_NO_DENSE_UPDATE")) != 0);
+  e.dmma_update = !(getenv("STOMP_NO_DMMA") && atoi(getenv("STOMP_NO_DMMA")) != 0);
   e.noise_stddev.assign(e.D, 1.0);
   e.noise_decay.assign(e.D, 1.0);
   std::vector<int> hl(e.D, 0);

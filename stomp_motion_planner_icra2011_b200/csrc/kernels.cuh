@@ -671,6 +671,214 @@ __global__ void __launch_bounds__(128) k_generate_dense(GenArgs a, const double*
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_generate_mma: the same four outputs (noise, parameters, M*noise, control costs) for LARGE batches with both linear maps
+// evaluated as fp64 tensor-core GEMMs (mma.sync.aligned.m8n8k4.f64, SASS DMMA) over a tile of kMmaV vectors per CTA:
+//   E[t][v] = sigma_v * sum_{j >= t} A1[t][j] Z[j][v],   A1[t][j] = C^-1[j][t]          (eps = sigma C^-T z, upper triangular)
+//   Y[t][v] = sum_j A2[t][j] E[j][v],                    A2[t][j] = R^-1[j][t] s_j       (y = M eps)
+// M = timesteps (8-row tiles spread over the 4 warps), N = the tile's vectors (two 8-column tiles), K = j in steps of 4.  The
+// matrices (A operands) stream from L1 / L2 — for one k, the eight lanes of a fragment column read eight consecutive t — and
+// the vectors (B operands) sit in shared memory with a row stride of 20 doubles, which makes the fragment loads conflict
+// free.  Z is filled from the same Philox streams as the other generation kernels, so the three agree to rounding
+// (test_dense_generation_kernels_match_the_band_solves).  k_generate's serial band solves need ~330 instructions per
+// vector-timestep at 12 % occupancy (one thread per vector); here one DMMA does 256 multiply-adds.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMmaV = 16;        // vectors per CTA
+constexpr int kMmaS = 20;        // row stride of the shared tiles in doubles (= 4 mod 16: conflict-free fragment loads)
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// C[t][v] (+)= sum_{j in [4 ks0(mt), Np)} M[j][t] * Bs[j][v] for the m-tiles mt = warp, warp + 4, ... ; acc[i][nt][2]
+template <bool kTriangular>
+__device__ __forceinline__ void mma_tiles(const double* __restrict__ M, const double* __restrict__ Bs, int N, int mtiles, int warp,
+                                          int frow, int fk, double (&acc)[4][2][2]) {
+  // `warp` = index of the warp's first m-tile (group base + warp id); its tiles are warp, warp + 4, warp + 8, warp + 12
+  const int ksteps = (N + 3) >> 2;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) acc[i][nt][0] = acc[i][nt][1] = 0.0;
+  const int ks_begin = kTriangular ? 2 * warp : 0;    // rows t0 = 8 mt only see j >= t0
+#pragma unroll 2
+  for (int ks = ks_begin; ks < ksteps; ++ks) {
+    const int j = ks * 4 + fk;
+    const bool jv = j < N;
+    const double b0 = Bs[j * kMmaS + frow], b1 = Bs[j * kMmaS + 8 + frow];
+    const double* mrow = M + size_t(min(j, N - 1)) * N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int mt = warp + 4 * i;
+      if (mt < mtiles && (!kTriangular || ks >= 2 * mt)) {
+        const int t = mt * 8 + frow;
+        const double av = (jv && t < N) ? __ldg(mrow + t) : 0.0;
+        dmma(acc[i][0][0], acc[i][0][1], av, b0);
+        dmma(acc[i][1][0], acc[i][1][1], av, b1);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_generate_mma(GenArgs a, const double* __restrict__ cinv, const double* __restrict__ ms) {
+  extern __shared__ double msm[];
+  const int N = a.N, Np = (N + 7) & ~7, Nall = N + 2 * kPad;
+  double* Zs = msm;                              // [Np][kMmaS]  standard normals; later the control costs
+  double* Es = Zs + size_t(Np) * kMmaS;          // [Np][kMmaS]  noise
+  double* Xs = Es + size_t(Np) * kMmaS;          // [Nall][kMmaS] padded x = parameters + M noise
+  __shared__ size_t s_row[kMmaV], s_th[kMmaV];
+  __shared__ const double* s_src[kMmaV];
+  __shared__ double s_sg[kMmaV], s_ps[kMmaV], s_pg[kMmaV];
+  __shared__ int s_flags[kMmaV];                 // bit 0 valid, bit 1 new rollout, bit 2 Philox noise
+  __shared__ uint64_t s_stream[kMmaV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, frow = lane >> 2, fk = lane & 3;
+  const int per_problem = a.r_count * a.D;
+  const long long nvec = (long long)a.B * per_problem;
+  if (threadIdx.x < kMmaV) {
+    const int vl = threadIdx.x;
+    const long long v = (long long)blockIdx.x * kMmaV + vl;
+    int flags = 0;
+    if (v < nvec) {
+      const int b = int(v / per_problem), rem = int(v - (long long)b * per_problem);
+      const int r = a.r_begin + rem / a.D, d = rem % a.D;
+      const bool is_new = r < a.R_gen;
+      flags = 1 | (is_new ? 2 : 0) | ((is_new && !a.injected) ? 4 : 0);
+      s_row[vl] = ((size_t(b) * a.R + r) * a.D + d) * N;
+      s_th[vl] = (size_t(b) * a.D + d) * N;
+      const double* src = nullptr;
+      if (!is_new) {
+        const int sidx = a.reuse_src[size_t(b) * (a.R - a.R_gen) + (r - a.R_gen)];
+        src = sidx >= 0 ? a.params_prev + ((size_t(b) * a.R + sidx) * a.D + d) * N : a.theta + (size_t(b) * a.D + d) * N;
+      }
+      s_src[vl] = src;
+      s_sg[vl] = a.noise_scale[d];
+      s_ps[vl] = a.pad_start[size_t(b) * a.D + d];
+      s_pg[vl] = a.pad_goal[size_t(b) * a.D + d];
+      s_stream[vl] = (uint64_t(b) * uint64_t(a.rollouts_global) + uint64_t(a.rollout_id_offset + r)) * uint64_t(a.D) + d;
+    }
+    s_flags[vl] = flags;
+  }
+  __syncthreads();
+  int any_philox = 0;
+#pragma unroll
+  for (int vl = 0; vl < kMmaV; ++vl) any_philox |= s_flags[vl] & 4;
+  // ---- Z: standard normals of the Philox vectors (zeros elsewhere and in the padded rows) -------------------------------
+  if (any_philox) {
+    const uint32_t gen_iteration = a.iteration_ptr ? *a.iteration_ptr : a.iteration;
+    const int npairs = (Np + 1) >> 1;
+    for (int idx = threadIdx.x; idx < kMmaV * npairs; idx += blockDim.x) {
+      const int vl = idx % kMmaV, pr = idx / kMmaV;
+      double z0 = 0.0, z1 = 0.0;
+      if ((s_flags[vl] & 4) && 2 * pr < N) {
+        normal_pair(a.seed, s_stream[vl], gen_iteration, uint32_t(pr), z0, z1);
+        if (2 * pr + 1 >= N) z1 = 0.0;
+      }
+      Zs[(2 * pr) * kMmaS + vl] = z0;
+      if (2 * pr + 1 < Np) Zs[(2 * pr + 1) * kMmaS + vl] = z1;
+    }
+    __syncthreads();
+  }
+  const int mtiles = Np >> 3;
+  double acc[4][2][2];
+  // ---- GEMM 1 + epilogue: noise, parameters ---------------------------------------------------------------------------------
+  for (int mt0 = 0; mt0 < mtiles; mt0 += 16) {   // groups of 16 m-tiles (128 timesteps): four per warp
+  if (any_philox) {
+    mma_tiles<true>(cinv, Zs, N, mtiles, mt0 + warp, frow, fk, acc);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) acc[i][nt][0] = acc[i][nt][1] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int mt = mt0 + warp + 4 * i;
+    if (mt >= mtiles) continue;
+    const int t = mt * 8 + frow;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int vl = nt * 8 + 2 * fk + h;
+        const int fl = s_flags[vl];
+        double e = 0.0;
+        if ((fl & 1) && t < N) {
+          const double th = a.theta[s_th[vl] + t];
+          double pv;
+          if (fl & 4) { e = s_sg[vl] * acc[i][nt][h]; pv = th + e; }
+          else if (fl & 2) { e = a.eps_in[s_row[vl] + t]; pv = th + e; }
+          else { pv = s_src[vl][t]; e = pv - th; }                     // policy_improvement.cpp:222
+          a.noise[s_row[vl] + t] = e;
+          a.params[s_row[vl] + t] = pv;
+          Xs[(kPad + t) * kMmaS + vl] = pv;
+        }
+        Es[t * kMmaS + vl] = e;
+      }
+  }
+  }
+  if (!a.mode_control) return;
+  __syncthreads();
+  // ---- GEMM 2 + epilogue: y = M eps, x = parameters + y ------------------------------------------------------------------
+  for (int mt0 = 0; mt0 < mtiles; mt0 += 16) {
+  mma_tiles<false>(ms, Es, N, mtiles, mt0 + warp, frow, fk, acc);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int mt = mt0 + warp + 4 * i;
+    if (mt >= mtiles) continue;
+    const int t = mt * 8 + frow;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int vl = nt * 8 + 2 * fk + h;
+        if ((s_flags[vl] & 1) && t < N) {
+          const double y = acc[i][nt][h];
+          if (a.noise_projected) a.noise_projected[s_row[vl] + t] = y;
+          Xs[(kPad + t) * kMmaS + vl] += y;
+        }
+      }
+  }
+  }
+  for (int idx = threadIdx.x; idx < kMmaV * kPad; idx += blockDim.x) {
+    const int vl = idx % kMmaV, q = idx / kMmaV;
+    Xs[q * kMmaS + vl] = s_ps[vl];
+    Xs[(kPad + N + q) * kMmaS + vl] = s_pg[vl];
+  }
+  __syncthreads();
+  // ---- control-cost stencils over [pads, x, pads] (covariant_trajectory_policy.cpp:228-255) -----------------------------------
+  double* Cs = Zs;
+  auto row_cost = [&](int vl, int p) -> double {     // padded row p; taps outside [0, Nall) are the dropped ones
+    double cost = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (a.st.weight[k] == 0.0) continue;
+      double s_ = 0.0;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int idx = p + j - 3;
+        s_ += a.st.coef[k][j] * ((idx < 0 || idx >= Nall) ? 0.0 : Xs[idx * kMmaS + vl]);
+      }
+      cost += a.control_weight * a.st.weight[k] * (s_ * s_);
+    }
+    return cost;
+  };
+  for (int idx = threadIdx.x; idx < kMmaV * N; idx += blockDim.x) {
+    const int vl = idx % kMmaV, t = idx / kMmaV;
+    if (!(s_flags[vl] & 1)) continue;
+    double cost = row_cost(vl, kPad + t);
+    if (t == 0)
+      for (int q = 0; q < kPad; ++q) cost += row_cost(vl, q);
+    if (t == N - 1)
+      for (int q = 0; q < kPad; ++q) cost += row_cost(vl, kPad + N + (kPad - 1 - q));
+    Cs[t * kMmaS + vl] = cost;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < kMmaV * N; idx += blockDim.x) {
+    const int vl = idx / N, t = idx - vl * N;
+    if (s_flags[vl] & 1) a.control[s_row[vl] + t] = Cs[t * kMmaS + vl];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_cost: the cost plugin.  One CTA per rollout; each warp owns a tile of 29 free timesteps
 // (lane l <-> timestep tile*29 - 1 + l), so the finite-difference velocity taps (-1, 0, +1, +2) of the
 // productive lanes 1..29 come from neighbouring lanes by warp shuffle and no sphere position ever leaves
@@ -1523,6 +1731,7 @@ struct UpdateArgs {
   int R, D, N, apply;
   int dims_per_cta;          // a CTA handles dims [g*dims_per_cta, ...) of one problem
   const double* dense_ms;    // [N][N] rows j of R^-1 diag(s) (engine.cu), or nullptr: banded solves
+  int use_dmma;              // dense projection on the tensor pipe (mma.sync m8n8k4 f64) instead of the scalar DFMA loop
   const double* cumulative;  // [B][R][D][N]
   const double* noise;       // [B][R][D][N]
   double* probabilities;     // optional tap
@@ -1651,7 +1860,39 @@ __global__ void __launch_bounds__(128, 7) k_update(UpdateArgs a) {
     u[dl * stride + t] = v;
   }
   __syncthreads();
-  if (dense) {
+  if (dense && a.use_dmma) {
+    // The batched projection as a tensor-core GEMM (north_star: "on tensor cores when batched across many problems"):
+    //   Y[t][q] = sum_j A[t][j] U[j][q],  A[t][j] = R^-1[j][t] s_j (dense_ms[j][t]),  U[j][q] = weighted noise of dimension q
+    // with mma.sync.aligned.m8n8k4.f64 (SASS DMMA): M = timesteps (8-row tiles over the warps), N = the CTA's dimensions
+    // (8-column tiles), K = j in steps of 4.  One DMMA replaces 8 x 8 x 4 scalar DFMAs of the loop below; A fragments come
+    // from the L1/L2-resident matrix (for one k, lanes with consecutive rows read consecutive t), B fragments from `u`.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int frow = lane >> 2, fk = lane & 3;           // fragment coordinates of this lane
+    const int mtiles = (N + 7) >> 3, ksteps = (N + 3) >> 2;
+    for (int q0 = 0; q0 < nd; q0 += 8) {
+      const int qb = q0 + frow;                            // B fragment column (dimension) of this lane
+      const double* ub = u + size_t(min(qb, nd - 1)) * stride;
+      const bool qv = qb < nd;
+      for (int mt = warp; mt < mtiles; mt += nwarps) {
+        const int t = mt * 8 + frow;                       // A fragment row (timestep) of this lane
+        const bool tv = t < N;
+        const double* ap = a.dense_ms + min(t, N - 1);
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll 4
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int j = ks * 4 + fk;
+          const bool jv = j < N;
+          const double av = (tv && jv) ? __ldg(ap + size_t(j) * N) : 0.0;
+          const double bv = (qv && jv) ? ub[j] : 0.0;
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
+        }
+        // accumulator fragment: row = lane >> 2, columns 2 * (lane & 3) + {0, 1}
+        const int qc = q0 + 2 * fk;
+        if (tv && qc < nd) y[qc * stride + t] = c0;
+        if (tv && qc + 1 < nd) y[(qc + 1) * stride + t] = c1;
+      }
+    }
+  } else if (dense) {
     constexpr int kDims = 8;         // dimensions accumulated per pass over the matrix column
     for (int t = threadIdx.x; t < N; t += blockDim.x) {
       for (int q0 = 0; q0 < nd; q0 += kDims) {

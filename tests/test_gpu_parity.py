@@ -791,9 +791,11 @@ def test_broad_phase_culling_is_exact(name, monkeypatch):
     np.testing.assert_array_equal(c.execute(p2, 1)[0], d.execute(p2, 1)[0])
 
 
-@pytest.mark.parametrize("name,problems,kernel", [("tiny", 2, "dense"), ("C1", 1, "dense"), ("C5", 1, "dense")])
+@pytest.mark.parametrize("name,problems,kernel", [("tiny", 2, "dense"), ("C1", 1, "dense"), ("C5", 1, "dense"),
+                                                  ("tiny", 2, "mma"), ("C1", 5, "mma"), ("C5", 1, "mma")])
 def test_dense_generation_kernels_match_the_band_solves(name, problems, kernel, monkeypatch):
-    """Small batches take k_generate_dense (eps = sigma C^-T z and M eps as dense products) instead of k_generate's serial band
+    """Large batches take k_generate_mma (both maps as fp64 tensor-core GEMMs over tiles of 16 vectors; the tiny / 5-problem
+    cases here leave the last tile partly empty).  Small batches take k_generate_dense (eps = sigma C^-T z and M eps as dense products) instead of k_generate's serial band
     solves: the same linear maps on the same Philox normals, so noise, parameters, M*noise and control costs agree to rounding
     — with the engine's own noise (iterations with and without reuse) and with injected noise.  C5 has 300 timesteps (several
     passes of the CTA over time; R^-1 is worse conditioned, hence the looser bound)."""
