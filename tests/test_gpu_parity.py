@@ -199,28 +199,60 @@ def test_compute_control_costs_matches_policy():
         assert_close(got[b], o.compute_control_costs(p[b], e[b], 0.7), RTOL_F64, "control costs")
 
 
-def test_fp32_mode_within_1e3():
-    """fp32 instantiation of the cost plugin: costs within 1e-3 relative wherever no voxel index flipped
-    (a position that differs by 1e-7 m can land in the neighbouring 15 mm cell; such rollouts are counted)."""
-    sc = scenes.make_scenario("C1", num_problems=2)
-    eng, ors = _engine(sc, dtype=_abi.F32), _oracles(sc)
+def _voxel_flips(eng, oracle, params):
+    """(timestep, sphere) pairs whose voxel index differs between the engine's and the oracle's evaluation of one rollout"""
+    dbg = eng.execute_debug(params)
+    odbg, _ = oracle.execute_debug(params)
+    return int((dbg["voxel"] != odbg["voxel"]).any(axis=-1).sum())
+
+
+@pytest.mark.parametrize("name,picks", [("C1", [0, 1]), ("C2", [0, 517, 1023])])
+def test_fp32_mode_within_1e3(name, picks):
+    """dtype = STOMP_F32 (the cost plugin — FK, sphere transforms, potential, velocity — in fp32; the PI^2 statistics stay fp64,
+    DESIGN.md): ten iterations on the oracle's noise.  Per iteration every new rollout's state costs are within 1e-3 of the
+    oracle's unless one of its sphere centres landed in a neighbouring 15 mm voxel (fp32 positions are good to ~1e-7 m);
+    every such rollout is re-evaluated through the debug tap and must show a counted voxel flip.  The policy after ten
+    iterations agrees to 1e-3."""
+    nprob = 2 if name == "C1" else 1024
+    sc = scenes.make_scenario(name, num_problems=nprob)
+    from oracle.oracle import Oracle
+    ors = [Oracle(sc, b) for b in picks]
+    eng = _engine(sc, dtype=_abi.F32, keep_intermediates=1, problems=picks)
+    dbg_eng = _engine(sc, dtype=_abi.F32, problems=[picks[0]])      # debug tap evaluates rollout 0 of its problem 0
     rng = np.random.default_rng(3)
-    params = _noisy_rollouts(sc, ors, rng, 8)
-    costs, cf = eng.execute(params, iteration_number=2)
-    bad = 0
-    for b, o in enumerate(ors):
-        oc, ocf = o.execute(params[b], iteration_number=2)
-        scale = np.abs(oc).max()
-        err = np.abs(costs[b] - oc).max(axis=-1) / scale
-        bad += int((err > RTOL_F32).sum())
-    assert bad <= 2, "more than 2 of 16 rollouts differ by > 1e-3 (voxel flips expected to be rare)"
+    L = ors[0].get(_abi.FIELD_NOISE_CHOLESKY)
+    D, N = sc.robot.num_dimensions, sc.num_time_steps
+    flipped = checked = 0
+    for it in range(1, 11):
+        ngen = sc.num_rollouts if it == 1 else sc.num_rollouts - sc.num_reused_rollouts
+        eps = correlated_noise(L, rng, (len(picks), ngen), np.full(D, 2.0 * 0.999 ** (it - 1)))
+        eng.inject_noise(eps)
+        eng.iterate(it)
+        st, par = eng.get(_abi.FIELD_STATE_COSTS), eng.get(_abi.FIELD_PARAMETERS)
+        for k, o in enumerate(ors):
+            o.iterate(it, eps[k])
+            ost = o.get(_abi.FIELD_STATE_COSTS)
+            scale = max(np.abs(ost[:ngen]).max(), 1e-300)
+            err = np.abs(st[k, :ngen] - ost[:ngen]).max(axis=-1) / scale
+            for r in np.nonzero(err > RTOL_F32)[0]:
+                # the start / goal padding of the debug engine must be this problem's: re-point it
+                dbg_eng.set_problems(sc.start[[picks[k]]], sc.goal[[picks[k]]])
+                flips = _voxel_flips(dbg_eng, o, par[k, r])
+                assert flips >= 1, "rollout %d of problem %d, iteration %d: %.2e off without a voxel flip" % (r, picks[k], it, err[r])
+                flipped += 1
+            checked += ngen
+    assert flipped <= 0.05 * checked, "voxel flips should be rare: %d of %d rollouts" % (flipped, checked)
+    for k, o in enumerate(ors):
+        assert_close(eng.get(_abi.FIELD_THETA)[k], o.get(_abi.FIELD_THETA), RTOL_F32, "theta after 10 fp32 iterations")
 
 
-def test_philox_noise_statistics():
-    """The engine's own RNG: sample covariance of eps against R^-1 and stream independence."""
-    sc = scenes.make_scenario("tiny", num_problems=1, num_time_steps=24)
+@pytest.mark.parametrize("N,n,tol", [(24, 20000, 0.02), (100, 30000, 0.03), (300, 20000, 0.06)])
+def test_philox_noise_statistics(N, n, tol):
+    """The engine's own RNG: sample covariance of eps against R^-1 and stream independence — at the unit-test size, at the
+    benchmark's N = 100 (cond(R) ~ 6e6) and at C5's N = 300 (cond ~ N^4).  The Frobenius error of a sample covariance from m
+    draws is ~ sqrt(N / m) in the whitened basis; `tol` leaves a factor ~3 over that."""
+    sc = scenes.make_scenario("tiny", num_problems=1, num_time_steps=N)
     eng, ors = _engine(sc), _oracles(sc)
-    n = 20000
     x = eng.sample_noise(1, n)[0]                  # [n][D][N], unit sigma
     D, N = x.shape[1:]
     Rinv = ors[0].get(_abi.FIELD_INV_CONTROL_COST)
@@ -228,7 +260,7 @@ def test_philox_noise_statistics():
     cov = flat.T @ flat / flat.shape[0]
     assert np.abs(flat.mean(axis=0)).max() < 4 * np.sqrt(Rinv.diagonal().max() / flat.shape[0])
     rel = np.linalg.norm(cov - Rinv) / np.linalg.norm(Rinv)
-    assert rel < 0.02, rel
+    assert rel < tol, rel
     # whitened samples are i.i.d. N(0,1): kurtosis ~ 3, and different (rollout, dimension) streams are uncorrelated
     C = np.linalg.cholesky(ors[0].get(_abi.FIELD_CONTROL_COST))
     z = flat @ C                                   # cov = C^T R^-1 C = I
@@ -315,6 +347,37 @@ def test_c5_thirty_dof_chain_shape():
     _run_iterations(sc, 2)
 
 
+@pytest.mark.parametrize("name", ["C4", "C5"])
+def test_c4_c5_at_baseline_sizes(name):
+    """BASELINE configs[3] / configs[4] at their stated shapes against the oracle on picked problems: C4 with K = 420 spheres,
+    N = 200, a 256^3 grid and a 64-problem batch (the per-GPU batch of the config is 512; 64 already fills the machine with
+    k_cost CTAs), C5 with all 512 rollouts of the 30-DOF, N = 300 chain (the chunked-statistics path)."""
+    from oracle.oracle import Oracle
+    if name == "C4":
+        sc, picks = scenes.make_scenario("C4", num_problems=64), [0, 63]
+    else:
+        sc, picks = scenes.make_scenario("C5"), [0]
+        assert sc.num_rollouts == 512 and sc.num_time_steps == 300 and sc.robot.num_dimensions == 30
+    eng = _engine(sc, keep_intermediates=1)
+    ors = {b: Oracle(sc, b) for b in picks}
+    rng = np.random.default_rng(17)
+    L = ors[picks[0]].get(_abi.FIELD_NOISE_CHOLESKY)
+    B, D = sc.start.shape
+    for it in (1, 2):
+        ngen = sc.num_rollouts if it == 1 else sc.num_rollouts - sc.num_reused_rollouts
+        eps = correlated_noise(L, rng, (B, ngen), sc.noise_stddev * sc.noise_decay ** (it - 1))
+        eng.inject_noise(eps)
+        cost, cf, g = eng.iterate(it)
+        assert g == ngen
+        th, st = eng.get(_abi.FIELD_THETA), eng.get(_abi.FIELD_STATE_COSTS)
+        for b in picks:
+            oc, ocf, og = ors[b].iterate(it, eps[b])
+            assert og == ngen and ocf == cf[b]
+            np.testing.assert_allclose(cost[b], oc, rtol=RTOL_F64)
+            assert_close(st[b, :ngen], ors[b].get(_abi.FIELD_STATE_COSTS)[:ngen], RTOL_F64, "state costs, iteration %d" % it)
+            assert_close(th[b], ors[b].get(_abi.FIELD_THETA), RTOL_F64, "theta, iteration %d" % it)
+
+
 def test_full_size_batch_properties(monkeypatch):
     """BASELINE configs[1] at full size (1024 problems): size-independent properties.
     (a) every problem of the batch evolves exactly as it does when planned alone (problems are independent);
@@ -328,6 +391,8 @@ def test_full_size_batch_properties(monkeypatch):
     monkeypatch.setenv("STOMP_NO_DENSE", "1")
     small = _engine(sc, keep_intermediates=1, problems=picks)
     monkeypatch.delenv("STOMP_NO_DENSE")
+    from oracle.oracle import Oracle
+    ors = {b: Oracle(sc, b) for b in picks}
     rng = np.random.default_rng(21)
     L = np.linalg.cholesky(big.get(_abi.FIELD_INV_CONTROL_COST))
     D = sc.robot.num_dimensions
@@ -343,6 +408,17 @@ def test_full_size_batch_properties(monkeypatch):
         np.testing.assert_array_equal(cb[picks], cs)
         np.testing.assert_array_equal(fb[picks], fs)
         np.testing.assert_array_equal(big.get(_abi.FIELD_THETA)[picks], small.get(_abi.FIELD_THETA))
+        # (d) the bench-size path itself (band k_generate over 35 840 vectors, 7-CTA/SM k_update, lane-packed k_cost) against the
+        # oracle on the same noise, problem by problem
+        th_big = big.get(_abi.FIELD_THETA)
+        st_big, cc_big = big.get(_abi.FIELD_STATE_COSTS), big.get(_abi.FIELD_CONTROL_COSTS)
+        for b in picks:
+            oc, ocf, og = ors[b].iterate(it, eps[b])
+            assert og == ngen and ocf == fb[b]
+            np.testing.assert_allclose(cb[b], oc, rtol=RTOL_F64)
+            assert_close(th_big[b], ors[b].get(_abi.FIELD_THETA), RTOL_F64, "theta of problem %d, iteration %d" % (b, it))
+            assert_close(st_big[b, :ngen], ors[b].get(_abi.FIELD_STATE_COSTS)[:ngen], RTOL_F64, "state costs")
+            assert_close(cc_big[b], ors[b].get(_abi.FIELD_CONTROL_COSTS), RTOL_F64, "control costs")
         P = big.get(_abi.FIELD_PROBABILITIES)
         np.testing.assert_allclose(P.sum(axis=1), 1.0, rtol=1e-12)
         state, params = big.get(_abi.FIELD_STATE_COSTS), big.get(_abi.FIELD_PARAMETERS)
