@@ -214,6 +214,28 @@ int stomp_engine_build_sdf(void* engine, const double size[3], const double orig
 int stomp_engine_build_sdf_points(void* engine, const double size[3], const double origin[3], double resolution, double max_distance,
                                   const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders,
                                   const double* points, int64_t num_points);
+/* The same with robot bodies added: StompCollisionSpace::setStartState also voxelises the robot's own links that are not in the
+ * planning group (torso, head, the other arm ...) at the start state, and MESH-free collision objects handed over as bodies
+ * (src/stomp_collision_space.cpp:167-188, addAllBodiesButExcludeLinksToPoints :567-588, getVoxelsInBody :590-650).
+ * getVoxelsInBody walks the lattice  centre + k * resolution,  |k| <= int(bounding radius / resolution)  per axis around the
+ * body's bounding-sphere centre and keeps the points from which a +z ray crosses the body's surface an odd number of times;
+ * for the convex primitives here that is "strictly inside the scaled + padded shape" (geometric_shapes' bodies::Sphere / Box /
+ * Cylinder are not vendored: their scale-then-pad convention and bounding spheres are restated).  Every
+ * kept point occupies the cell int(round((p - origin) / resolution)) like every other point.  `bodies` carry WORLD poses (the
+ * caller evaluates the links' transforms at the start state; the facade's StompCollisionSpace::setStartState does). */
+enum stomp_body_type { STOMP_BODY_SPHERE = 0, STOMP_BODY_BOX = 1, STOMP_BODY_CYLINDER = 2 };
+typedef struct stomp_body {
+  int32_t type;
+  int32_t reserved;
+  double dimensions[3];  /* sphere: radius; box: x, y, z extents; cylinder: radius, length (axis z) */
+  double position[3];
+  double orientation[4]; /* quaternion x, y, z, w */
+  double scale;          /* bodies::Body::setScale, 1.0 = unscaled */
+  double padding;        /* bodies::Body::setPadding, metres */
+} stomp_body;
+int stomp_engine_build_sdf_bodies(void* engine, const double size[3], const double origin[3], double resolution, double max_distance,
+                                  const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders,
+                                  const double* points, int64_t num_points, const stomp_body* bodies, int32_t num_bodies);
 /* Copies the current voxel grid out (parity tap): dims[3], voxel dtype, and up to `bytes` of voxels (may be NULL). */
 int stomp_engine_get_sdf(void* engine, int32_t dims[3], int32_t* voxel_dtype, void* voxels, size_t bytes);
 /* Inverse-dynamics (torque) cost term of StompOptimizer::execute (src/stomp_optimizer.cpp:1117-1142, getTorques :1006-1061):

@@ -30,7 +30,7 @@ def _round_half_away(t):
     return np.where(t >= 0, np.floor(t + 0.5), np.ceil(t - 0.5))
 
 
-def build(size, origin, resolution, max_distance, boxes=(), cylinders=(), points=None):
+def build(size, origin, resolution, max_distance, boxes=(), cylinders=(), points=None, bodies=()):
     from scipy import ndimage
     n = [int(size[i] / resolution) for i in range(3)]
     occ = np.zeros(n, dtype=bool)
@@ -59,6 +59,41 @@ def build(size, origin, resolution, max_distance, boxes=(), cylinders=(), points
         c = _round_half_away((np.asarray(points, float).reshape(-1, 3) - origin) / resolution).astype(np.int64)
         c = c[np.all((c >= 0) & (c < np.array(n)), axis=1)]
         occ[c[:, 0], c[:, 1], c[:, 2]] = True
+    # robot / primitive bodies: StompCollisionSpace::getVoxelsInBody (src/stomp_collision_space.cpp:590-650) — the lattice
+    # centre + k * res, |k| <= int(bounding radius / res) per axis; a point is kept when a +z ray from it crosses the surface
+    # an odd number of times = strictly inside the convex scaled-then-padded primitive
+    for (btype, dims, pos, quat, scale, padding) in bodies:
+        c = np.asarray(pos, float)
+        Rm = _rotation(quat)
+        if btype == 0:
+            par = [dims[0] * scale + padding]
+            bound = par[0]
+        elif btype == 1:
+            par = [dims[k] / 2.0 * scale + padding for k in range(3)]
+            bound = math.sqrt(sum(v * v for v in par))
+        else:
+            par = [dims[0] * scale + padding, dims[1] / 2.0 * scale + padding]
+            bound = math.sqrt(par[0] ** 2 + par[1] ** 2)
+        axes = []
+        for k in range(3):
+            gmin = int(((c[k] - bound) - c[k]) * (1.0 / resolution))
+            gmax = int(((c[k] + bound) - c[k]) * (1.0 / resolution))
+            axes.append(np.arange(gmin, gmax + 1) * resolution + c[k])
+        X, Y, Z = np.meshgrid(*axes, indexing="ij")
+        W = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=-1)
+        d = W - c
+        lx = Rm[0, 0] * d[:, 0] + Rm[1, 0] * d[:, 1] + Rm[2, 0] * d[:, 2]
+        ly = Rm[0, 1] * d[:, 0] + Rm[1, 1] * d[:, 1] + Rm[2, 1] * d[:, 2]
+        lz = Rm[0, 2] * d[:, 0] + Rm[1, 2] * d[:, 1] + Rm[2, 2] * d[:, 2]
+        if btype == 0:
+            inside = lx * lx + ly * ly + lz * lz < par[0] * par[0]
+        elif btype == 1:
+            inside = (np.abs(lx) < par[0]) & (np.abs(ly) < par[1]) & (np.abs(lz) < par[2])
+        else:
+            inside = (np.abs(lz) < par[1]) & (lx * lx + ly * ly < par[0] * par[0])
+        cc = _round_half_away((W[inside] - origin) / resolution).astype(np.int64)
+        cc = cc[np.all((cc >= 0) & (cc < np.array(n)), axis=1)]
+        occ[cc[:, 0], cc[:, 1], cc[:, 2]] = True
     cap = int(math.ceil(max_distance / resolution))
     if occ.any():
         d = ndimage.distance_transform_edt(~occ)

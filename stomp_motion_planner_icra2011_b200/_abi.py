@@ -125,3 +125,11 @@ class Box(C.Structure):
 
 class Cylinder(C.Structure):
     _fields_ = [("position", C.c_double * 3), ("orientation", C.c_double * 4), ("radius", C.c_double), ("height", C.c_double)]
+
+
+BODY_SPHERE, BODY_BOX, BODY_CYLINDER = 0, 1, 2
+
+
+class Body(C.Structure):
+    _fields_ = [("type", C.c_int32), ("reserved", C.c_int32), ("dimensions", C.c_double * 3), ("position", C.c_double * 3),
+                ("orientation", C.c_double * 4), ("scale", C.c_double), ("padding", C.c_double)]

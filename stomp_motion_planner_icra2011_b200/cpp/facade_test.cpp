@@ -33,10 +33,22 @@ class ForwardingTask : public Task {
   bool getPolicy(std::shared_ptr<Policy>& policy) override { return inner_->getPolicy(policy); }
   bool setPolicy(const std::shared_ptr<Policy> policy) override { return inner_->setPolicy(policy); }
   bool getControlCostWeight(double& w) override { return inner_->getControlCostWeight(w); }
-  std::shared_ptr<Engine> getEngine() override { return inner_->getEngine(); }
+  // no getEngine(): only the reference's five Task methods, like an existing cost plugin; the loop finds the engine through
+  // the policy
   int calls = 0;
- private:
+ protected:
   std::shared_ptr<StompOptimizer> inner_;
+};
+
+// the optional batched hook: all rollouts of an iteration in one call
+class BatchedTask : public ForwardingTask {
+ public:
+  using ForwardingTask::ForwardingTask;
+  bool executeBatch(std::vector<std::vector<VectorXd> >& rollouts, MatrixXd& costs, const int it) override {
+    ++batch_calls;
+    return inner_->executeBatch(rollouts, costs, it);
+  }
+  int batch_calls = 0;
 };
 
 int main() {
@@ -104,17 +116,22 @@ int main() {
   auto a = std::make_shared<StompOptimizer>(start, goal, &robot, &params, &space);
   auto b_inner = std::make_shared<StompOptimizer>(start, goal, &robot, &params, &space);
   auto b = std::make_shared<ForwardingTask>(b_inner);
-  PolicyImprovementLoop loop_a, loop_b;
-  if (!loop_a.initialize(params, a) || !loop_b.initialize(params, b)) { std::printf("FAIL loop init: %s\n", lastError()); return 1; }
+  auto c_inner = std::make_shared<StompOptimizer>(start, goal, &robot, &params, &space);
+  auto c = std::make_shared<BatchedTask>(c_inner);
+  PolicyImprovementLoop loop_a, loop_b, loop_c;
+  if (!loop_a.initialize(params, a) || !loop_b.initialize(params, b) || !loop_c.initialize(params, c)) { std::printf("FAIL loop init: %s\n", lastError()); return 1; }
   double max_diff = 0.0;
   for (int it = 1; it <= 6; ++it) {
-    if (!loop_a.runSingleIteration(it) || !loop_b.runSingleIteration(it)) { std::printf("FAIL iteration: %s\n", lastError()); return 1; }
-    std::shared_ptr<Policy> pa, pb;
-    a->getPolicy(pa); b->getPolicy(pb);
-    std::vector<VectorXd> ta, tb;
-    pa->getParameters(ta); pb->getParameters(tb);
+    if (!loop_a.runSingleIteration(it) || !loop_b.runSingleIteration(it) || !loop_c.runSingleIteration(it)) { std::printf("FAIL iteration: %s\n", lastError()); return 1; }
+    std::shared_ptr<Policy> pa, pb, pc;
+    a->getPolicy(pa); b->getPolicy(pb); c->getPolicy(pc);
+    std::vector<VectorXd> ta, tb, tc;
+    pa->getParameters(ta); pb->getParameters(tb); pc->getParameters(tc);
     for (size_t d = 0; d < ta.size(); ++d)
-      for (size_t t = 0; t < ta[d].size(); ++t) max_diff = std::fmax(max_diff, std::fabs(ta[d][t] - tb[d][t]));
+      for (size_t t = 0; t < ta[d].size(); ++t) {
+        max_diff = std::fmax(max_diff, std::fabs(ta[d][t] - tb[d][t]));
+        if (tb[d][t] != tc[d][t]) { std::printf("FAIL batched plugin hook differs from the per-rollout one\n"); return 1; }
+      }
     if (std::fabs(loop_a.lastNoiselessCost() - loop_b.lastNoiselessCost()) > 1e-9 * (1.0 + std::fabs(loop_a.lastNoiselessCost()))) {
       std::printf("FAIL noise-less cost differs at iteration %d: %.12g vs %.12g\n", it, loop_a.lastNoiselessCost(), loop_b.lastNoiselessCost());
       return 1;
@@ -123,6 +140,8 @@ int main() {
   // 10 rollouts at iteration 1, 5 afterwards, +1 noise-less each: 6*1 + 10 + 5*5 = 41 plugin calls
   std::printf("fused vs host-Task path: max |theta diff| = %.3e, host Task::execute calls = %d\n", max_diff, b->calls);
   if (max_diff > 1e-9 || b->calls != 41) { std::printf("FAIL paths disagree\n"); return 1; }
+  // the batched hook: one executeBatch per iteration + one execute for the noise-less rollout
+  if (c->batch_calls != 6 || c->calls != 6) { std::printf("FAIL batched hook call counts %d %d\n", c->batch_calls, c->calls); return 1; }
 
   // ---- 3. Policy interface bits ---------------------------------------------------------------------------------
   std::shared_ptr<Policy> pol;

@@ -180,14 +180,30 @@ class Task {
   virtual bool getPolicy(std::shared_ptr<Policy>& policy) = 0;
   virtual bool setPolicy(const std::shared_ptr<Policy> policy) = 0;
   virtual bool getControlCostWeight(double& control_cost_weight) = 0;
-  // engine the task's policy lives on (the PI^2 state is kept there)
-  virtual std::shared_ptr<Engine> getEngine() = 0;
+  // ---- optional extensions (defaults keep an existing cost plugin source compatible: the five methods above are the
+  //      reference's whole Task interface, include/stomp_motion_planner/task.h:52-93) -------------------------------------
+  // All rollouts of an iteration at once: rollouts[r][d][t] -> costs(r, t).  The default calls execute() rollout by rollout
+  // like PolicyImprovementLoop::runSingleIteration does (src/policy_improvement_loop.cpp:160-166); a plugin that evaluates on
+  // the GPU overrides it and saves R - 1 host round trips per iteration.
+  virtual bool executeBatch(std::vector<std::vector<VectorXd> >& rollouts, MatrixXd& costs, const int iteration_number) {
+    VectorXd tmp;
+    for (size_t r = 0; r < rollouts.size(); ++r) {
+      if (!execute(rollouts[r], tmp, iteration_number)) return false;
+      if (costs.rows() != int(rollouts.size()) || costs.cols() != int(tmp.size())) costs = MatrixXd(int(rollouts.size()), int(tmp.size()));
+      for (size_t t = 0; t < tmp.size(); ++t) costs(int(r), int(t)) = tmp[t];
+    }
+    return true;
+  }
+  // Engine the PI^2 state lives on.  The loop asks the task's policy (CovariantTrajectoryPolicy::getEngine) when this returns
+  // null, so a custom Task does not need to know about engines at all.
+  virtual std::shared_ptr<Engine> getEngine() { return nullptr; }
 };
 
 // ---- CovariantTrajectoryPolicy ---------------------------------------------------------------------------------
 class CovariantTrajectoryPolicy : public Policy {
  public:
   explicit CovariantTrajectoryPolicy(std::shared_ptr<Engine> engine) : e_(engine) {}
+  std::shared_ptr<Engine> getEngine() const { return e_; }
   // setToMinControlCost (src/covariant_trajectory_policy.cpp:102-112): also resets the rollout-reuse state
   bool setToMinControlCost(const VectorXd& start, const VectorXd& goal) {
     return stomp_engine_set_problems(e_->get(), start.data(), goal.data()) == 0;
@@ -350,6 +366,20 @@ class StompOptimizer : public Task, public std::enable_shared_from_this<StompOpt
     for (double c : costs) last_trajectory_cost_ += c;
     return true;
   }
+  // all rollouts in one stomp_engine_execute call (one upload, one k_cost launch, one read-back)
+  bool executeBatch(std::vector<std::vector<VectorXd> >& rollouts, MatrixXd& costs, const int iteration_number) override {
+    const size_t DN = size_t(engine_->D) * engine_->N;
+    std::vector<double> p;
+    p.reserve(rollouts.size() * DN);
+    for (const std::vector<VectorXd>& ro : rollouts)
+      for (const VectorXd& v : ro) p.insert(p.end(), v.begin(), v.end());
+    if (rollouts.empty() || p.size() != rollouts.size() * DN) return false;
+    costs = MatrixXd(int(rollouts.size()), engine_->N);
+    std::vector<int32_t> cf(rollouts.size(), 0);
+    if (stomp_engine_execute(engine_->get(), p.data(), int32_t(rollouts.size()), iteration_number, costs.data.data(), cf.data())) return false;
+    last_trajectory_collision_free_ = cf.back() != 0;
+    return true;
+  }
   bool getPolicy(std::shared_ptr<Policy>& policy) override { policy = policy_; return true; }
   bool setPolicy(const std::shared_ptr<Policy>) override { return true; }
   bool getControlCostWeight(double& w) override { w = parameters_->smoothness_cost_weight; return true; }
@@ -459,6 +489,8 @@ inline bool PolicyImprovementLoop::initialize(const StompParameters& params, std
   if (!task_->initialize(params_, params_.num_time_steps)) return false;
   if (!task_->getPolicy(policy_) || !task_->getControlCostWeight(control_cost_weight_)) return false;
   e_ = task_->getEngine();
+  if (!e_)
+    if (CovariantTrajectoryPolicy* ctp = dynamic_cast<CovariantTrajectoryPolicy*>(policy_.get())) e_ = ctp->getEngine();
   if (!e_) return false;
   params_.noise_stddev.resize(e_->D, 2.0);
   params_.noise_decay.resize(e_->D, 0.999);
@@ -487,10 +519,8 @@ inline bool PolicyImprovementLoop::runSingleIteration(const int iteration_number
   if (!policy_improvement_.getRollouts(rollouts, noise)) return false;
   MatrixXd rollout_costs(int(rollouts.size()), e_->N);
   VectorXd tmp;
-  for (size_t r = 0; r < rollouts.size(); ++r) {
-    if (!task_->execute(rollouts[r], tmp, iteration_number)) return false;
-    for (int t = 0; t < e_->N; ++t) rollout_costs(int(r), t) = tmp[t];
-  }
+  if (!task_->executeBatch(rollouts, rollout_costs, iteration_number)) return false;
+  if (rollout_costs.rows() != int(rollouts.size()) || rollout_costs.cols() != e_->N) return false;
   std::vector<double> all_costs;
   if (!policy_improvement_.setRolloutCosts(rollout_costs, control_cost_weight_, all_costs)) return false;
   std::vector<MatrixXd> parameter_updates;

@@ -1,0 +1,72 @@
+// Host-only driver of stomp_robot_model_urdf.hpp (no GPU needed): tests/test_urdf_cpp_cpu.py builds it, feeds it a URDF and a
+// small spec file and compares the dumped tables with stomp_motion_planner_icra2011_b200/urdf.py.
+// usage: urdf_model_test robot.urdf spec.txt
+//   spec lines:  group j1 j2 ... | reference link | clearance c | collision link radius extension | state joint value |
+//                chain root tip | exclude link ... | start q1 q2 ... | padding scale pad
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <stomp_motion_planner/stomp_robot_model_urdf.hpp>
+using namespace stomp_motion_planner;
+
+int main(int argc, char** argv) {
+  if (argc < 3) return 2;
+  std::ifstream uf(argv[1]);
+  std::stringstream ub;
+  ub << uf.rdbuf();
+  std::vector<std::string> group, exclude;
+  std::string reference, chain_root, chain_tip;
+  std::vector<CollisionLinkConfig> col;
+  std::map<std::string, double> state;
+  std::vector<double> start;
+  double clearance = 0.07, scale = 1.0, padding = 0.0;
+  std::ifstream sf(argv[2]);
+  std::string line;
+  while (std::getline(sf, line)) {
+    std::istringstream is(line);
+    std::string key, w;
+    is >> key;
+    if (key == "group") while (is >> w) group.push_back(w);
+    else if (key == "reference") is >> reference;
+    else if (key == "clearance") is >> clearance;
+    else if (key == "collision") { CollisionLinkConfig c; is >> c.link >> c.link_radius >> c.link_extension; col.push_back(c); }
+    else if (key == "state") { double v; is >> w >> v; state[w] = v; }
+    else if (key == "chain") is >> chain_root >> chain_tip;
+    else if (key == "exclude") while (is >> w) exclude.push_back(w);
+    else if (key == "start") { double v; while (is >> v) start.push_back(v); }
+    else if (key == "padding") is >> scale >> padding;
+  }
+  StompRobotModelUrdf m;
+  std::string err;
+  if (!loadRobotModelFromUrdf(ub.str(), group, reference, col, clearance, state, chain_root, chain_tip, m, err)) {
+    std::printf("error %s\n", err.c_str());
+    return 1;
+  }
+  std::printf("reference %d chain %d %d\n", m.reference_segment, m.chain_root_segment, m.chain_tip_segment);
+  for (size_t s = 0; s < m.segments.size(); ++s) {
+    const stomp_segment& g = m.segments[s];
+    std::printf("segment %s %d %d %d", m.segment_names[s].c_str(), g.parent, g.joint_type, g.group_index);
+    for (double v : g.rot) std::printf(" %.17g", v);
+    for (double v : g.pos) std::printf(" %.17g", v);
+    for (double v : g.axis) std::printf(" %.17g", v);
+    std::printf(" %.17g\n", g.fixed_value);
+  }
+  for (const stomp_joint_limit& l : m.joint_limits) std::printf("limit %d %.17g %.17g\n", l.has_limits, l.min, l.max);
+  for (const stomp_sphere& sp : m.collision_points)
+    std::printf("sphere %d %.17g %.17g %.17g %.17g %.17g\n", sp.segment, sp.radius, sp.clearance, sp.pos[0], sp.pos[1], sp.pos[2]);
+  for (size_t s = 0; s < m.link_inertias.size(); ++s) {
+    const stomp_link_inertia& li = m.link_inertias[s];
+    if (li.mass == 0.0) continue;
+    std::printf("inertia %zu %.17g %.17g %.17g %.17g", s, li.mass, li.com[0], li.com[1], li.com[2]);
+    for (double v : li.inertia) std::printf(" %.17g", v);
+    std::printf("\n");
+  }
+  for (const stomp_body& b : bodiesAtState(m, start, exclude, scale, padding)) {
+    std::printf("body %d %.17g %.17g %.17g", b.type, b.dimensions[0], b.dimensions[1], b.dimensions[2]);
+    for (double v : b.position) std::printf(" %.17g", v);
+    for (double v : b.orientation) std::printf(" %.17g", v);
+    std::printf(" %.17g %.17g\n", b.scale, b.padding);
+  }
+  return 0;
+}

@@ -1395,7 +1395,15 @@ int stomp_engine_build_sdf(void* h, const double size[3], const double origin[3]
 int stomp_engine_build_sdf_points(void* h, const double size[3], const double origin[3], double resolution, double max_distance,
                                   const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders,
                                   const double* points, int64_t num_points) {
+  return stomp_engine_build_sdf_bodies(h, size, origin, resolution, max_distance, boxes, num_boxes, cylinders, num_cylinders, points,
+                                       num_points, nullptr, 0);
+}
+
+int stomp_engine_build_sdf_bodies(void* h, const double size[3], const double origin[3], double resolution, double max_distance,
+                                  const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders,
+                                  const double* points, int64_t num_points, const stomp_body* bodies, int32_t num_bodies) {
   ENGINE_OR_FAIL(h);
+  if (num_bodies < 0 || (num_bodies > 0 && !bodies)) return fail("bad bodies");
   if (num_points < 0 || (num_points > 0 && !points)) return fail("bad collision-map points");
   if (!size || !origin || resolution <= 0.0 || max_distance <= 0.0) return fail("bad distance field specification");
   if ((num_boxes > 0 && !boxes) || (num_cylinders > 0 && !cylinders) || num_boxes < 0 || num_cylinders < 0) return fail("bad collision objects");
@@ -1457,6 +1465,53 @@ int stomp_engine_build_sdf_points(void* h, const double size[3], const double or
         num_points, dpts.p, origin[0], origin[1], origin[2], resolution, nx, ny, nz, occ.p);
     if (check_launch(e, "k_sdf_mark_points")) return 1;
     CUDA_TRY(cudaStreamSynchronize(e.stream));   // dpts goes out of scope
+  }
+  if (num_bodies > 0) {
+    std::vector<SdfBody> hb;
+    long long btotal = 0;
+    for (int i = 0; i < num_bodies; ++i) {
+      const stomp_body& sb = bodies[i];
+      SdfBody b;
+      std::memset(&b, 0, sizeof(b));
+      double R[9];
+      quaternion_to_rotation(sb.orientation, R);
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) b.Rt[r * 3 + c] = R[c * 3 + r];
+      double bound = 0.0;   // bodies::*::computeBoundingSphere of the scaled + padded shape
+      if (sb.type == STOMP_BODY_SPHERE) {
+        b.p[0] = sb.dimensions[0] * sb.scale + sb.padding;
+        bound = b.p[0];
+      } else if (sb.type == STOMP_BODY_BOX) {
+        for (int k = 0; k < 3; ++k) b.p[k] = sb.dimensions[k] / 2.0 * sb.scale + sb.padding;
+        bound = std::sqrt(b.p[0] * b.p[0] + b.p[1] * b.p[1] + b.p[2] * b.p[2]);
+      } else if (sb.type == STOMP_BODY_CYLINDER) {
+        b.p[0] = sb.dimensions[0] * sb.scale + sb.padding;
+        b.p[1] = sb.dimensions[1] / 2.0 * sb.scale + sb.padding;
+        bound = std::sqrt(b.p[0] * b.p[0] + b.p[1] * b.p[1]);
+      } else {
+        return fail("unknown body type (meshes are not supported: geometric_shapes' convex-hull containment is not restated)");
+      }
+      if (!(bound > 0.0)) return fail("body with a non-positive size");
+      b.type = sb.type;
+      b.first = btotal;
+      for (int k = 0; k < 3; ++k) {
+        b.c[k] = sb.position[k];
+        // worldToGrid(centre, centre -/+ radius): (int)((w - centre) * (1.0 / resolution)), stomp_collision_space.h:230-234
+        const int gmin = int(((b.c[k] - bound) - b.c[k]) * (1.0 / resolution));
+        const int gmax = int(((b.c[k] + bound) - b.c[k]) * (1.0 / resolution));
+        b.gmin[k] = gmin;
+        b.gn[k] = gmax - gmin + 1;
+      }
+      btotal += (long long)b.gn[0] * b.gn[1] * b.gn[2];
+      hb.push_back(b);
+    }
+    DevBuf<unsigned char> dbodies;
+    if (upload(e, dbodies, reinterpret_cast<const unsigned char*>(hb.data()), hb.size() * sizeof(SdfBody))) return 1;
+    begin_launch(e);
+    k_sdf_mark_bodies<<<unsigned(std::max<long long>(1, std::min<long long>((btotal + 255) / 256, 148 * 32))), 256, 0, e.ws>>>(
+        num_bodies, btotal, reinterpret_cast<const SdfBody*>(dbodies.p), origin[0], origin[1], origin[2], resolution, nx, ny, nz, occ.p);
+    if (check_launch(e, "k_sdf_mark_bodies")) return 1;
+    CUDA_TRY(cudaStreamSynchronize(e.stream));   // dbodies goes out of scope
   }
   const bool u8 = cap * cap < 256;
   CUDA_TRY(e.vox.alloc(cells * (u8 ? 1 : 2)));

@@ -2077,6 +2077,48 @@ __global__ void k_sdf_mark_points(long long total, const double* __restrict__ pt
   }
 }
 
+// robot bodies / primitive collision bodies (StompCollisionSpace::getVoxelsInBody, src/stomp_collision_space.cpp:590-650): one
+// thread per lattice point  centre + k * res  of the body's bounding cube; kept when strictly inside the scaled + padded shape
+struct SdfBody {
+  double c[3];         // bounding-sphere centre = body origin (world)
+  double Rt[9];        // world -> body rotation
+  double p[3];         // sphere: {r, -, -}; box: half extents; cylinder: {r, half length, -}  (scaled, then padded)
+  int type;
+  int gmin[3], gn[3];  // first lattice index and count per axis
+  long long first;
+};
+
+__global__ void k_sdf_mark_bodies(int num_bodies, long long total, const SdfBody* __restrict__ bodies, double ox, double oy, double oz,
+                                  double res, int nx, int ny, int nz, uint8_t* __restrict__ occ) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = num_bodies - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (bodies[mid].first <= i) lo = mid; else hi = mid - 1;
+    }
+    const SdfBody& b = bodies[lo];
+    long long k = i - b.first;
+    const int iz = int(k % b.gn[2]); k /= b.gn[2];
+    const int iy = int(k % b.gn[1]);
+    const int ix = int(k / b.gn[1]);
+    // gridToWorld(centre, g): g * resolution + centre (include/stomp_motion_planner/stomp_collision_space.h:237-241)
+    const double xw = (b.gmin[0] + ix) * res + b.c[0], yw = (b.gmin[1] + iy) * res + b.c[1], zw = (b.gmin[2] + iz) * res + b.c[2];
+    const double dx = xw - b.c[0], dy = yw - b.c[1], dz = zw - b.c[2];
+    const double lx = b.Rt[0] * dx + b.Rt[1] * dy + b.Rt[2] * dz, ly = b.Rt[3] * dx + b.Rt[4] * dy + b.Rt[5] * dz,
+                 lz = b.Rt[6] * dx + b.Rt[7] * dy + b.Rt[8] * dz;
+    bool inside;
+    if (b.type == STOMP_BODY_SPHERE) inside = lx * lx + ly * ly + lz * lz < b.p[0] * b.p[0];
+    else if (b.type == STOMP_BODY_BOX) inside = fabs(lx) < b.p[0] && fabs(ly) < b.p[1] && fabs(lz) < b.p[2];
+    else inside = fabs(lz) < b.p[1] && lx * lx + ly * ly < b.p[0] * b.p[0];
+    if (!inside) continue;
+    const double tx = (xw - ox) / res, ty = (yw - oy) / res, tz = (zw - oz) / res;
+    if (!(fabs(tx) < 1e9 && fabs(ty) < 1e9 && fabs(tz) < 1e9)) continue;
+    const int cx = int(round(tx)), cy = int(round(ty)), cz = int(round(tz));
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= nx || cy >= ny || cz >= nz) continue;
+    occ[(size_t(cx) * ny + cy) * nz + cz] = 1;
+  }
+}
+
 // axis: 0 = x (input: occupancy u8 -> d^2 along x), 1 = y, 2 = z (inputs: u16 partial squared distances).
 // out[v] = min over |k| <= cap of in[v + k along axis] + k^2, saturated at cap^2 (kInf marks "nothing within cap").
 template <int kAxis, typename Out>

@@ -32,7 +32,7 @@ EXPORTS = [
     "stomp_engine_set_constraints", "stomp_engine_execute_constraints_satisfied",
     "stomp_engine_request_results_async", "stomp_engine_wait_results", "stomp_engine_set_dynamics",
     "stomp_engine_shard_ipc_handle", "stomp_engine_shard_open_peers", "stomp_engine_iterate_sharded_fused",
-    "stomp_engine_shard_status", "stomp_engine_build_sdf_points", "stomp_engine_set_graph_mode",
+    "stomp_engine_shard_status", "stomp_engine_build_sdf_points", "stomp_engine_set_graph_mode", "stomp_engine_build_sdf_bodies",
 ]
 
 
@@ -106,9 +106,10 @@ class Engine:
             pass
 
     # ---- distance field construction -----------------------------------------------------
-    def build_sdf(self, size, origin, resolution, max_distance, boxes=(), cylinders=(), points=None):
+    def build_sdf(self, size, origin, resolution, max_distance, boxes=(), cylinders=(), points=None, bodies=()):
         """boxes: (position, quaternion xyzw, dimensions); cylinders: (position, quaternion, radius, height); points: [n][3]
-        collision-map points."""
+        collision-map points; bodies: (type, dimensions, position, quaternion, scale, padding) robot / primitive bodies in
+        world poses (getVoxelsInBody)."""
         cb = (_abi.Box * max(1, len(boxes)))()
         for i, (p, q, d) in enumerate(boxes):
             cb[i].position[:], cb[i].orientation[:], cb[i].dimensions[:] = p, q, d
@@ -116,10 +117,16 @@ class Engine:
         for i, (p, q, r, hgt) in enumerate(cylinders):
             cc[i].position[:], cc[i].orientation[:] = p, q
             cc[i].radius, cc[i].height = r, hgt
+        bb = (_abi.Body * max(1, len(bodies)))()
+        for i, (t, d, p, q, sc, pad) in enumerate(bodies):
+            bb[i].type = t
+            bb[i].dimensions[:] = tuple(d) + (0.0,) * (3 - len(d))
+            bb[i].position[:], bb[i].orientation[:] = p, q
+            bb[i].scale, bb[i].padding = sc, pad
         pts = _f64(points).reshape(-1, 3) if points is not None else None
-        self._ck(self.L.stomp_engine_build_sdf_points(self.h, (C.c_double * 3)(*size), (C.c_double * 3)(*origin), C.c_double(resolution),
+        self._ck(self.L.stomp_engine_build_sdf_bodies(self.h, (C.c_double * 3)(*size), (C.c_double * 3)(*origin), C.c_double(resolution),
                                                       C.c_double(max_distance), cb, len(boxes), cc, len(cylinders),
-                                                      _dp(pts), C.c_int64(0 if pts is None else len(pts))))
+                                                      _dp(pts), C.c_int64(0 if pts is None else len(pts)), bb, len(bodies)))
 
     def get_sdf(self):
         dims = (C.c_int32 * 3)()

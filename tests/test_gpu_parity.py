@@ -483,6 +483,33 @@ def test_optimize_outer_loop_matches_host_bookkeeping():
             assert np.all(res["best_trajectory"][ok, d] <= hi + 1e-4) and np.all(res["best_trajectory"][ok, d] >= lo - 1e-4)
 
 
+def test_robot_bodies_in_the_distance_field_bit_exact():
+    """stomp_engine_build_sdf_bodies: the robot's links outside the planning group (and primitive collision bodies) voxelised
+    like StompCollisionSpace::getVoxelsInBody — bounding-sphere-centred lattice, strictly-inside test of the scaled + padded
+    sphere / box / cylinder — together with boxes, cylinders and points; occupancy and distances bit-exact against the
+    NumPy restatement (oracle/sdf_builder.py)."""
+    from oracle import sdf_builder
+    sc = scenes.make_scenario("tiny", num_problems=2)
+    eng = _engine(sc)
+    ident = (0.0, 0.0, 0.0, 1.0)
+    tilt = (np.sin(0.3) * 0.6, np.sin(0.3) * 0.8, 0.0, np.cos(0.3))
+    yaw = (0.0, 0.0, np.sin(0.5), np.cos(0.5))
+    bodies = [(_abi.BODY_BOX, (0.35, 0.45, 0.8), (-0.1, 0.0, 0.75), ident, 1.0, 0.01),          # torso
+              (_abi.BODY_SPHERE, (0.12,), (0.02, 0.0, 1.35), ident, 1.0, 0.02),                  # head
+              (_abi.BODY_CYLINDER, (0.06, 0.42), (0.25, 0.35, 0.9), tilt, 1.0, 0.01),            # the other arm's upper arm
+              (_abi.BODY_BOX, (0.2, 0.1, 0.05), (0.55, 0.4, 0.7), yaw, 1.1, 0.0),                # a scaled gripper
+              (_abi.BODY_SPHERE, (0.2,), (-0.45, -1.4, 0.0), ident, 1.0, 0.0)]                   # pokes out of the grid
+    boxes = [((0.8, -0.1, 0.643), ident, (0.4, 1.2, 0.03))]
+    pts = np.random.default_rng(4).uniform((-0.4, -1.4, -0.2), (1.4, 1.4, 1.8), (300, 3))
+    spec = dict(size=(2.0, 3.0, 2.2), origin=(-0.5, -1.5, -0.3), resolution=0.015, max_distance=0.17)
+    eng.build_sdf(boxes=boxes, points=pts, bodies=bodies, **spec)
+    got, dtype = eng.get_sdf()
+    want, occ = sdf_builder.build(boxes=boxes, points=pts, bodies=bodies, **spec)
+    _, occ_without = sdf_builder.build(boxes=boxes, points=pts, **spec)
+    assert occ.sum() - occ_without.sum() > 40000          # the bodies really are in the field
+    np.testing.assert_array_equal(got, want)
+
+
 def test_distance_field_construction_bit_exact():
     """stomp_engine_build_sdf (lattice rasterisation + exact EDT on the GPU) against the NumPy/SciPy restatement of
     StompCollisionSpace::addCollisionObjectsToPoints + the capped squared distance transform: integer work, bit-exact."""

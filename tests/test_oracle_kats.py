@@ -1,5 +1,6 @@
 """CPU tests of the oracle: known answers and invariants derivable from the reference's formulas
  plus the committed golden vectors.  The reference has no unit tests of its own."""
+import math
 import os
 
 import numpy as np
@@ -321,3 +322,24 @@ def test_trilinear_extension_is_the_continuous_version_of_the_nearest_cell_field
     np.testing.assert_allclose(dt[1], 0.75 * dn[0] + 0.25 * dn[4], rtol=0, atol=1e-12)
     assert dn[1] == dn[0] and dn[3] == dn[4]                                         # the reference field is piecewise constant
     assert abs(dn[0] - dn[4]) > 1e-3, (dn, "pick a cell pair across which the field changes")
+
+
+def test_body_voxelisation_restatement_is_strict_containment():
+    """oracle/sdf_builder.py, bodies: the marked cells of a sphere / box / cylinder body are exactly the cells of the
+    bounding-sphere-centred lattice points inside the scaled-then-padded primitive (StompCollisionSpace::getVoxelsInBody,
+    src/stomp_collision_space.cpp:590-650): volume and extent checks against the analytic shapes."""
+    from oracle import sdf_builder
+    res = 0.02
+    spec = dict(size=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), resolution=res, max_distance=0.1)
+    ident = (0.0, 0.0, 0.0, 1.0)
+    cases = [((0, (0.2,), (0.5, 0.5, 0.5), ident, 1.0, 0.01), 4.0 / 3.0 * math.pi * 0.21 ** 3),
+             ((1, (0.3, 0.2, 0.4), (0.5, 0.5, 0.5), ident, 1.0, 0.0), 0.3 * 0.2 * 0.4),
+             ((2, (0.1, 0.5), (0.5, 0.5, 0.5), ident, 1.2, 0.0), math.pi * 0.12 ** 2 * 0.6)]
+    for body, volume in cases:
+        _, occ = sdf_builder.build(bodies=[body], **spec)
+        assert abs(occ.sum() * res ** 3 - volume) < 0.12 * volume
+    # a box rotated by 90 degrees about z swaps its x / y extents
+    q90 = (0.0, 0.0, math.sin(math.pi / 4), math.cos(math.pi / 4))
+    _, occ = sdf_builder.build(bodies=[(1, (0.4, 0.1, 0.1), (0.5, 0.5, 0.5), q90, 1.0, 0.0)], **spec)
+    ext = [np.ptp(np.nonzero(occ.any(axis=tuple(a for a in range(3) if a != k)))[0]) for k in range(3)]
+    assert ext[1] > 3 * ext[0] and abs(ext[1] * res - 0.4) < 3 * res
