@@ -556,6 +556,12 @@ def run_engine(args):
                     extras[other] = bench_small(ctx, other, dtype, k_, w_)
                 except Exception as ex:      # a sub-record never fails the headline
                     extras[other] = {"error": repr(ex)}
+            if args.dtype == "f64":
+                try:      # the fp32 instantiation of the cost plugin on the headline workload (north_star's 1e-3 mode)
+                    extras["C2_f32"] = bench_small(ctx, "C2", _abi.F32, 10, 3)
+                    extras["C2_f32"]["note"] = "dtype = STOMP_F32: FK, sphere transforms, potentials and velocities in fp32; PI^2 statistics stay fp64"
+                except Exception as ex:
+                    extras["C2_f32"] = {"error": repr(ex)}
         try:
             extras["C3"] = bench_c3(ctx, args, dtype)
         except Exception as ex:

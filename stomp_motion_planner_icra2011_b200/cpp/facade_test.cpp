@@ -158,6 +158,36 @@ int main() {
   const double mid = 0.5 * (start[0] + goal[0]);
   if (mj.size() != 4u || mj[0].size() != 60u || std::fabs(0.5 * (mj[0][29] + mj[0][30]) - mid) > 1e-9 ||
       std::fabs(mj[0][0] - start[0]) > 1e-3 || std::fabs(mj[0][59] - goal[0]) > 1e-3) { std::printf("FAIL min jerk\n"); return 1; }
+  // ---- 4. setStartState: the field rebuilt on the device from a collision object + a robot body outside the group ----------
+  {
+    StompCollisionSpace built;
+    built.size[0] = built.size[1] = built.size[2] = 1.8; built.max_distance = 0.36; built.resolution = 0.03;
+    built.origin[0] = -0.9; built.origin[1] = -0.9; built.origin[2] = -0.2;
+    stomp_box bx;
+    std::memset(&bx, 0, sizeof(bx));
+    bx.position[0] = 0.55; bx.position[2] = 0.55; bx.orientation[3] = 1.0;
+    bx.dimensions[0] = 0.16; bx.dimensions[1] = 0.5; bx.dimensions[2] = 0.24;
+    built.boxes.push_back(bx);
+    stomp_body torso;                      // a "torso" column behind the arm: never touched, but present in the field
+    std::memset(&torso, 0, sizeof(torso));
+    torso.type = STOMP_BODY_CYLINDER; torso.dimensions[0] = 0.1; torso.dimensions[1] = 0.6;
+    torso.position[0] = -0.5; torso.position[2] = 0.3; torso.orientation[3] = 1.0; torso.scale = 1.0; torso.padding = 0.01;
+    built.bodies.push_back(torso);
+    auto dev = std::make_shared<StompOptimizer>(start, goal, &robot, &params, &built);
+    if (!dev->ok()) { std::printf("FAIL device-built field: %s\n", lastError()); return 1; }
+    int32_t dims[3] = {0, 0, 0}, vt = -1;
+    std::vector<uint8_t> vox(size_t(60) * 60 * 60);
+    if (stomp_engine_get_sdf(dev->getEngine()->get(), dims, &vt, vox.data(), vox.size()) || dims[0] != 60 || vt != STOMP_VOXEL_U8_SQ) {
+      std::printf("FAIL get_sdf: %s\n", lastError());
+      return 1;
+    }
+    auto cell = [&](double x, double y, double z) {
+      return vox[(size_t(std::lround((x + 0.9) / 0.03)) * 60 + size_t(std::lround((y + 0.9) / 0.03))) * 60 + size_t(std::lround((z + 0.2) / 0.03))];
+    };
+    if (cell(0.55, 0.0, 0.55) != 0 || cell(-0.5, 0.0, 0.3) != 0 || cell(0.0, 0.6, 1.2) != 144) { std::printf("FAIL field contents\n"); return 1; }
+    STOMPStatistics st2;
+    if (!dev->optimize(&st2) || !(st2.best_cost <= st2.costs.front())) { std::printf("FAIL optimize on the device-built field\n"); return 1; }
+  }
   std::printf("facade ok\n");
   return 0;
 }

@@ -81,6 +81,16 @@ struct StompCollisionSpace {
   std::vector<uint8_t> voxels;  // squared cell distances, x-major
   int nx = 0, ny = 0, nz = 0, voxel_dtype = STOMP_VOXEL_U8_SQ;
   double origin[3] = {0, 0, 0}, resolution = 0.015;
+  // what StompCollisionSpace::setStartState rebuilds the field from (src/stomp_collision_space.cpp:154-197): the environment's
+  // collision objects and collision-map points, and the robot's own bodies outside the planning group at the start state
+  // (StompRobotModelUrdf::bodiesAtState).  When `size` is set, StompOptimizer builds the field on the GPU
+  // (stomp_engine_build_sdf_bodies) instead of uploading `voxels`.
+  double size[3] = {0, 0, 0}, max_distance = 0.0;   // collision_space/size_*, max_propagation_distance
+  std::vector<stomp_box> boxes;
+  std::vector<stomp_cylinder> cylinders;
+  std::vector<double> points;                       // [n][3]
+  std::vector<stomp_body> bodies;
+  bool built_on_device() const { return size[0] > 0.0 && size[1] > 0.0 && size[2] > 0.0 && max_distance > 0.0; }
 };
 
 // StompTrajectory::fillInMinJerk (src/stomp_trajectory.cpp:179-223): quintic between the fixed points before / after the
@@ -453,9 +463,16 @@ class StompOptimizer : public Task, public std::enable_shared_from_this<StompOpt
                                robot_model_->collision_points.data(), int(robot_model_->collision_points.size()),
                                robot_model_->joint_limits.data()))
       return false;
-    if (stomp_engine_set_sdf(h, collision_space_->voxels.data(), collision_space_->nx, collision_space_->ny, collision_space_->nz,
-                             collision_space_->origin, collision_space_->resolution, collision_space_->voxel_dtype))
+    if (collision_space_->built_on_device()) {
+      const StompCollisionSpace& cs = *collision_space_;
+      if (stomp_engine_build_sdf_bodies(h, cs.size, cs.origin, cs.resolution, cs.max_distance, cs.boxes.data(), int(cs.boxes.size()),
+                                        cs.cylinders.data(), int(cs.cylinders.size()), cs.points.data(), int64_t(cs.points.size() / 3),
+                                        cs.bodies.data(), int(cs.bodies.size())))
+        return false;
+    } else if (stomp_engine_set_sdf(h, collision_space_->voxels.data(), collision_space_->nx, collision_space_->ny, collision_space_->nz,
+                                    collision_space_->origin, collision_space_->resolution, collision_space_->voxel_dtype)) {
       return false;
+    }
     if (parameters_->torque_cost_weight > 1e-9) {   // src/stomp_optimizer.cpp:1120
       const double gravity[3] = {0.0, 0.0, -9.8};   // src/stomp_robot_model.cpp:184
       if (robot_model_->link_inertias.size() != robot_model_->segments.size() ||
