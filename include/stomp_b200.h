@@ -397,13 +397,17 @@ int stomp_engine_dump_timeline(void* engine, const char* path);
  * a sharded iteration: minmax = [2][D][N] (MAX of {c, -c}), sums = [2][D][N] (SUM of {e, e*eps}). */
 int stomp_engine_shard_buffers(void* engine, void** minmax_dev, void** sums_dev, size_t* bytes_each);
 int stomp_engine_iterate_sharded_phase(void* engine, int32_t iteration_number, int32_t phase /* 0,1,2 */);
-/* The same iteration with both exchanges done by the GPUs themselves over NVLink peer memory (k_peer_allreduce: P2P stores of
- * the 2*D*N partials into every peer's exchange buffer, system-scope flags, reduction in rank order) instead of NCCL calls
- * between host-synchronised phases.  Setup, once: every rank exports its exchange buffer with stomp_engine_shard_ipc_handle
- * (64-byte cudaIpcMemHandle_t), the host side all-gathers the handles (any transport), every rank maps its peers with
- * stomp_engine_shard_open_peers(handles[world][64]).  stomp_engine_iterate_sharded_fused then enqueues the whole iteration
- * on the handle's stream without a host synchronisation; every rank must call it for the same iteration.
- * stomp_engine_shard_status reports an exchange that timed out (a rank that never arrived). */
+/* The same iteration with both exchanges done by the GPUs themselves over NVLink peer memory, as the epilogue of the statistics
+ * kernel (k_shard_stats: P2P stores of the 2*D*N partials into every peer's exchange buffer, system-scope flags, reduction in
+ * rank order, then — SUM phase — the projection and theta += update in the same launch) instead of NCCL calls between
+ * host-synchronised phases.  Setup, once: every rank exports its exchange buffer with stomp_engine_shard_ipc_handle (64-byte
+ * cudaIpcMemHandle_t), the host side all-gathers the handles (any transport), every rank maps its peers with
+ * stomp_engine_shard_open_peers(handles[world][64]) and the ranks barrier once before the first iteration (open_peers clears
+ * this rank's flags and restarts the epochs, also when called again on a live engine).  stomp_engine_iterate_sharded_fused
+ * then enqueues the whole iteration on the handle's stream without a host synchronisation; every rank must call it for the
+ * same iteration.  An exchange that times out (a rank that never arrived) sets a sticky flag: the reduction is skipped, no
+ * update is applied from then on, and stomp_engine_shard_status / stomp_engine_get_parameters / the iteration statistics
+ * return the error. */
 int stomp_engine_shard_ipc_handle(void* engine, void* handle_out, size_t handle_bytes);
 int stomp_engine_shard_open_peers(void* engine, const void* handles, int32_t count);
 int stomp_engine_iterate_sharded_fused(void* engine, int32_t iteration_number);

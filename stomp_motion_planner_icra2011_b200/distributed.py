@@ -87,7 +87,7 @@ class ShardedIteration:
 
 
 class PeerShardedIteration:
-    """The same iteration with the two exchanges done in-kernel over NVLink peer memory (k_peer_allreduce): no NCCL call and
+    """The same iteration with the two exchanges done in-kernel over NVLink peer memory (k_shard_stats): no NCCL call and
     no host synchronisation inside an iteration.  torch.distributed is only used once, to all-gather the 64-byte CUDA IPC
     handles of the ranks' exchange buffers."""
 
@@ -106,8 +106,8 @@ class PeerShardedIteration:
 
 class NumpyShardStandIn:
     """CPU stand-in with the engine's three-phase protocol, used by the gloo tests: it holds a shard of
-    per-rollout cumulative costs and noise and implements exactly the arithmetic of k_minmax_partial /
-    k_sums_partial / k_finalize (kernels.cuh) in NumPy."""
+    per-rollout cumulative costs and noise and implements exactly the arithmetic of k_shard_stats' two
+    phases and its finalize (kernels.cuh) in NumPy."""
 
     def __init__(self, cumulative, noise, proj, theta):
         import torch
