@@ -122,6 +122,7 @@ struct Engine {
   double constraint_cost_weight = 0.0;
   DevBuf<double> band_fw, band_bw, proj_scale, qinv_t, noise_scale;
   DevBuf<double> dense_cinv, dense_ms;   // [N][N] C^-1 and R^-1 diag(s) for k_generate_dense (small batches)
+  DevBuf<double> mma_a1, mma_a2;         // the same two, zero-padded to [Np][Np] (Np = N rounded up to 8): k_generate_mma's A operands
   bool dense_update = true;   // A/B switch (STOMP_NO_DENSE_UPDATE=1): k_update projects with the banded solves
   bool dmma_update = true;    // A/B switch (STOMP_NO_DMMA=1): the dense projection runs as scalar DFMAs instead of DMMA tiles
   int gen_mode = 0;   // 0: pick k_generate / k_generate_dense / k_generate_mma by batch shape; 1, 2, 3: always that one (A/B)
@@ -777,17 +778,18 @@ int launch_generate_range(Engine& e, const RolloutPlan& p, int r_begin, int r_co
   const double est_dense = 5.0e-6 + nvec * 12.0 * double(e.N) * e.N / 4.0e12;
   int kind = e.gen_mode;
   // k_generate_mma — both linear maps as DMMA GEMMs over tiles of 16 vectors: large batches whose three shared tiles fit
-  const size_t mma_smem = (size_t(2) * ((e.N + 7) & ~7) + size_t(e.N) + 2 * kPad) * kMmaS * 8;
-  const bool mma_ok = mma_smem <= 200 * 1024 && e.N <= 1024;
-  // measured on B200 (profiles/README.md, round 2): the DMMA kernel loses to the band solves at N = 100 (C2: 0.230 vs 0.108 ms
-  // per launch under ncu; 13 % of the fp64 tensor peak, its A-fragment loads and stencils cost as many instructions as the
-  // band kernel's whole sweep), so it is only taken on request (STOMP_GENERATE=mma)
+  const size_t mma_smem = mma_smem_bytes(e.N);
+  const bool mma_ok = mma_smem <= 200 * 1024 && e.N <= 1024 && e.mma_a1.p != nullptr;
+  // measured on B200 (profiles/README.md, round 2): the DMMA kernel loses to the band solves (k_generate per iteration, both
+  // launches: C2 0.266 vs 0.158 ms, C5 0.66 vs 0.37 ms; new-slot launch under ncu 149 vs 107 us with the fp64 tensor path at
+  // 35 % of its peak).  The dense formulation does 1.5 N^2 flops per vector where the band solves do ~20 N, and B200's fp64
+  // tensor rate equals its DFMA rate, so it is only taken on request (STOMP_GENERATE=mma)
   if (kind == 0) kind = (e.N <= 1024 && est_dense < 0.5 * est_band) ? 2 : 1;
   if (kind == 3 && !mma_ok) kind = 1;
   if (kind == 3) {
     if (mma_smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_generate_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, int(mma_smem)));
     begin_launch(e);
-    k_generate_mma<<<unsigned((nvec + kMmaV - 1) / kMmaV), 128, mma_smem, e.ws>>>(a, e.dense_cinv.p, e.dense_ms.p);
+    k_generate_mma<<<unsigned((nvec + kMmaV - 1) / kMmaV), 128, mma_smem, e.ws>>>(a, e.mma_a1.p, e.mma_a2.p);
     if (check_launch(e, "k_generate")) return 1;
   } else if (kind == 2) {
     const size_t smem = (size_t(3) * e.N + 2 * kPad) * 8;
@@ -1251,6 +1253,21 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
     }
     for (int j = 0; j < N; ++j)
       for (int t = 0; t < N; ++t) msd[size_t(j) * N + t] = e.pm.Rinv(j, t) * e.pm.proj_scale[j];
+    if (N <= 1024) {
+      // [pass][Np][strideA]: pass = t / 128, rows j, columns t % 128 with the staged row stride (kernels.cuh, mma_gemm)
+      const int Np = (N + 7) & ~7, strideA = mma_a_stride(std::min(Np, kMmaGroup)), passes = (Np + kMmaGroup - 1) / kMmaGroup;
+      std::vector<double> p1(size_t(passes) * Np * strideA, 0.0), p2(size_t(passes) * Np * strideA, 0.0);
+      for (int j = 0; j < N; ++j)
+        for (int t = 0; t < N; ++t) {
+          const size_t at = (size_t(t / kMmaGroup) * Np + j) * strideA + (t % kMmaGroup);
+          p1[at] = cinv[size_t(j) * N + t];   // zero above the diagonal of C^-1: j < t
+          p2[at] = msd[size_t(j) * N + t];
+        }
+      if (upload(e, e.mma_a1, p1.data(), p1.size()) || upload(e, e.mma_a2, p2.data(), p2.size())) {
+        stomp_engine_destroy(ep);
+        return 1;
+      }
+    }
     if (upload(e, e.dense_cinv, cinv.data(), cinv.size()) || upload(e, e.dense_ms, msd.data(), msd.size())) {
       stomp_engine_destroy(ep);
       return 1;

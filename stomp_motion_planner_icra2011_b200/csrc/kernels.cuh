@@ -125,6 +125,37 @@ __device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t stream, uint
   z1 = double(r * sn);
 }
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier completion -------------------------------------------------
+// One elected thread arms the CTA's mbarrier with the byte count and issues one bulk copy per contiguous block (robot
+// tables, rollout rows); the copy engine moves the bytes into shared memory while the threads go on, and everybody waits
+// on the barrier's phase.  Used by k_cost (tables, rollout rows: replaces per-thread 16-byte cp.async loops) and by
+// k_generate_mma (matrix rows).  Sizes and addresses are multiples of 16 bytes.
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra MBAR_WAIT_%=;\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_select_reuse: per problem, rank (cost, index) pairs ascending like std::sort on std::pair<double,int>;
 // the extra (noise-less) rollout has index -1 and therefore wins ties.  out: src[b][j] for j < R_reuse
@@ -671,60 +702,105 @@ __global__ void __launch_bounds__(128) k_generate_dense(GenArgs a, const double*
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_generate_mma: the same four outputs (noise, parameters, M*noise, control costs) for LARGE batches with both linear maps
-// evaluated as fp64 tensor-core GEMMs (mma.sync.aligned.m8n8k4.f64, SASS DMMA) over a tile of kMmaV vectors per CTA:
+// k_generate_mma: the same four outputs (noise, parameters, M*noise, control costs) with both linear maps evaluated as fp64
+// tensor-core GEMMs (mma.sync.aligned.m8n8k4.f64, SASS DMMA) over a tile of kMmaV vectors per CTA:
 //   E[t][v] = sigma_v * sum_{j >= t} A1[t][j] Z[j][v],   A1[t][j] = C^-1[j][t]          (eps = sigma C^-T z, upper triangular)
 //   Y[t][v] = sum_j A2[t][j] E[j][v],                    A2[t][j] = R^-1[j][t] s_j       (y = M eps)
-// M = timesteps (8-row tiles spread over the 4 warps), N = the tile's vectors (two 8-column tiles), K = j in steps of 4.  The
-// matrices (A operands) stream from L1 / L2 — for one k, the eight lanes of a fragment column read eight consecutive t — and
-// the vectors (B operands) sit in shared memory with a row stride of 20 doubles, which makes the fragment loads conflict
-// free.  Z is filled from the same Philox streams as the other generation kernels, so the three agree to rounding
-// (test_dense_generation_kernels_match_the_band_solves).  k_generate's serial band solves need ~330 instructions per
-// vector-timestep at 12 % occupancy (one thread per vector); here one DMMA does 256 multiply-adds.
+// M = timesteps (8-row tiles, four per warp), N = the tile's vectors (two 8-column tiles), K = j in steps of 4.
+// The matrices are stored zero-padded as Mp[pass][j][t] (Np = N rounded up to 8 rows of `strideA` doubles per 128-timestep pass)
+// and streamed through shared memory in chunks of kMmaChunk rows by TMA bulk copies (one cp.async.bulk per chunk, two buffers,
+// one mbarrier each): the copy of chunk
+// c + 1 is in flight while the warps issue the DMMAs of chunk c, and no thread computes an address or a predicate for an A
+// operand (the first version loaded fragments with __ldg: 24 instructions per load, 21 % of the kernel, 230 us).  Staged rows
+// have a stride of 4 (mod 16) doubles and the vector tiles a stride of 20, which makes every fragment load conflict free.
+// Z is filled from the same Philox streams as the other generation kernels, so the three agree to rounding
+// (test_dense_generation_kernels_match_the_band_solves).
 // ---------------------------------------------------------------------------------------------
 constexpr int kMmaV = 16;        // vectors per CTA
-constexpr int kMmaS = 20;        // row stride of the shared tiles in doubles (= 4 mod 16: conflict-free fragment loads)
+constexpr int kMmaS = 20;        // row stride of the vector tiles in doubles (= 4 mod 16: conflict-free fragment loads)
+#ifndef STOMP_MMA_CHUNK
+#define STOMP_MMA_CHUNK 8
+#endif
+constexpr int kMmaChunk = STOMP_MMA_CHUNK;     // matrix rows (j) per staged chunk (8 = two k-steps)
+constexpr int kMmaGroup = 128;   // timesteps per pass (16 m-tiles: four per warp)
 
-__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+__host__ __device__ inline int mma_a_stride(int cols) {   // >= cols, = 4 (mod 16)
+  int st = cols;
+  while ((st & 15) != 4) ++st;
+  return st;
+}
+__host__ __device__ inline size_t mma_smem_bytes(int N) {
+  const int Np = (N + 7) & ~7, rows = Np > N + 2 * kPad ? Np : N + 2 * kPad;
+  return (size_t(2) * rows * kMmaS + size_t(2) * kMmaChunk * mma_a_stride(Np < kMmaGroup ? Np : kMmaGroup)) * 8 + 16;
 }
 
-// C[t][v] (+)= sum_{j in [4 ks0(mt), Np)} M[j][t] * Bs[j][v] for the m-tiles mt = warp, warp + 4, ... ; acc[i][nt][2]
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// acc[i][nt][:] = sum_j Mp[j][t] * Bs[j][v] for the m-tiles mt = tc0 / 8 + warp + 4 i of the pass starting at timestep tc0.
+// kTriangular: Mp[j][t] = 0 for j < t, so chunks below the pass and k-steps below an m-tile are skipped, and only the columns
+// t <= j of a row are copied.  All threads of the CTA call this together; `phase` = the parities of the two mbarriers.
 template <bool kTriangular>
-__device__ __forceinline__ void mma_tiles(const double* __restrict__ M, const double* __restrict__ Bs, int N, int mtiles, int warp,
-                                          int frow, int fk, double (&acc)[4][2][2]) {
-  // `warp` = index of the warp's first m-tile (group base + warp id); its tiles are warp, warp + 4, warp + 8, warp + 12
-  const int ksteps = (N + 3) >> 2;
+__device__ __forceinline__ void mma_gemm(const double* __restrict__ Mp, const double* __restrict__ Bs, double* __restrict__ As,
+                                         unsigned bar0, unsigned (&phase)[2], int Np, int tc0, int tcols, double (&acc)[4][2][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, frow = lane >> 2, fk = lane & 3;
+  const int strideA = mma_a_stride(Np < kMmaGroup ? Np : kMmaGroup);
+  const int mtiles_here = tcols >> 3;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) acc[i][nt][0] = acc[i][nt][1] = 0.0;
-  const int ks_begin = kTriangular ? 2 * warp : 0;    // rows t0 = 8 mt only see j >= t0
-#pragma unroll 2
-  for (int ks = ks_begin; ks < ksteps; ++ks) {
-    const int j = ks * 4 + fk;
-    const bool jv = j < N;
-    const double b0 = Bs[j * kMmaS + frow], b1 = Bs[j * kMmaS + 8 + frow];
-    const double* mrow = M + size_t(min(j, N - 1)) * N;
+  const int nchunks = Np / kMmaChunk;
+  const int c_begin = kTriangular ? tc0 / kMmaChunk : 0;
+  // the matrix is stored pass by pass with the staged row stride ([pass][Np][strideA], engine.cu), so a chunk of rows is ONE
+  // contiguous bulk copy (per-row copies of 832 bytes made the TMA request rate the bottleneck: 0.33 ms instead of 0.16)
+  const double* Mpass = Mp + size_t(tc0 / kMmaGroup) * Np * strideA;
+  auto issue = [&](int c, int buf) {     // one thread: arm the barrier, one bulk copy for the chunk's rows
+    const unsigned bytes = unsigned(kMmaChunk * strideA * 8);
+    mbar_expect_tx(bar0 + 8u * buf, bytes);
+    bulk_g2s(smem_u32(As + size_t(buf) * kMmaChunk * strideA), Mpass + size_t(c) * kMmaChunk * strideA, bytes, bar0 + 8u * buf);
+  };
+  if (threadIdx.x == 0) issue(c_begin, 0);
+  for (int c = c_begin; c < nchunks; ++c) {
+    const int buf = (c - c_begin) & 1;
+    if (threadIdx.x == 0 && c + 1 < nchunks) issue(c + 1, buf ^ 1);   // the other buffer was released by the barrier below
+    mbar_wait(bar0 + 8u * buf, phase[buf]);
+    phase[buf] ^= 1u;
+    const double* Ab = As + size_t(buf) * kMmaChunk * strideA + fk * strideA + frow;
+    // all fragment loads of the chunk first (independent LDS: one shared-memory latency per chunk), then the DMMAs; an m-tile
+    // that does not exist or lies above the diagonal (warp-uniform conditions) is skipped
+    double bf[kMmaChunk / 4][2], af[kMmaChunk / 4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int mt = warp + 4 * i;
-      if (mt < mtiles && (!kTriangular || ks >= 2 * mt)) {
-        const int t = mt * 8 + frow;
-        const double av = (jv && t < N) ? __ldg(mrow + t) : 0.0;
-        dmma(acc[i][0][0], acc[i][0][1], av, b0);
-        dmma(acc[i][1][0], acc[i][1][1], av, b1);
-      }
+    for (int ks = 0; ks < kMmaChunk / 4; ++ks) {
+      const int j = c * kMmaChunk + ks * 4 + fk;
+      bf[ks][0] = Bs[j * kMmaS + frow];
+      bf[ks][1] = Bs[j * kMmaS + 8 + frow];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[ks][i] = Ab[ks * 4 * strideA + min(warp + 4 * i, mtiles_here - 1) * 8];
     }
+#pragma unroll
+    for (int ks = 0; ks < kMmaChunk / 4; ++ks)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ml = warp + 4 * i;                                  // m-tile within the pass
+        if (ml < mtiles_here && (!kTriangular || c * (kMmaChunk / 4) + ks >= 2 * (tc0 / 8 + ml))) {
+          dmma(acc[i][0][0], acc[i][0][1], af[ks][i], bf[ks][0]);
+          dmma(acc[i][1][0], acc[i][1][1], af[ks][i], bf[ks][1]);
+        }
+      }
+    __syncthreads();      // everyone is done with `buf` before it is refilled two chunks later
   }
 }
 
-__global__ void __launch_bounds__(128) k_generate_mma(GenArgs a, const double* __restrict__ cinv, const double* __restrict__ ms) {
-  extern __shared__ double msm[];
+__global__ void __launch_bounds__(128) k_generate_mma(GenArgs a, const double* __restrict__ a1p, const double* __restrict__ a2p) {
+  extern __shared__ __align__(16) double msm[];
   const int N = a.N, Np = (N + 7) & ~7, Nall = N + 2 * kPad;
-  double* Zs = msm;                              // [Np][kMmaS]  standard normals; later the control costs
-  double* Es = Zs + size_t(Np) * kMmaS;          // [Np][kMmaS]  noise
-  double* Xs = Es + size_t(Np) * kMmaS;          // [Nall][kMmaS] padded x = parameters + M noise
+  const int rows = Np > Nall ? Np : Nall;
+  double* T0 = msm;                              // [rows][kMmaS]  standard normals Z, later the padded x = parameters + M noise
+  double* T1 = T0 + size_t(rows) * kMmaS;        // [rows][kMmaS]  noise E, later the control costs
+  double* As = T1 + size_t(rows) * kMmaS;        // [2][kMmaChunk][strideA] staged matrix rows
+  const unsigned bar0 = smem_u32(As + size_t(2) * kMmaChunk * mma_a_stride(Np < kMmaGroup ? Np : kMmaGroup));
   __shared__ size_t s_row[kMmaV], s_th[kMmaV];
   __shared__ const double* s_src[kMmaV];
   __shared__ double s_sg[kMmaV], s_ps[kMmaV], s_pg[kMmaV];
@@ -733,6 +809,7 @@ __global__ void __launch_bounds__(128) k_generate_mma(GenArgs a, const double* _
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, frow = lane >> 2, fk = lane & 3;
   const int per_problem = a.r_count * a.D;
   const long long nvec = (long long)a.B * per_problem;
+  if (threadIdx.x == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8u, 1); }
   if (threadIdx.x < kMmaV) {
     const int vl = threadIdx.x;
     const long long v = (long long)blockIdx.x * kMmaV + vl;
@@ -761,6 +838,7 @@ __global__ void __launch_bounds__(128) k_generate_mma(GenArgs a, const double* _
   int any_philox = 0;
 #pragma unroll
   for (int vl = 0; vl < kMmaV; ++vl) any_philox |= s_flags[vl] & 4;
+  unsigned phase[2] = {0u, 0u};
   // ---- Z: standard normals of the Philox vectors (zeros elsewhere and in the padded rows) -------------------------------
   if (any_philox) {
     const uint32_t gen_iteration = a.iteration_ptr ? *a.iteration_ptr : a.iteration;
@@ -772,81 +850,88 @@ __global__ void __launch_bounds__(128) k_generate_mma(GenArgs a, const double* _
         normal_pair(a.seed, s_stream[vl], gen_iteration, uint32_t(pr), z0, z1);
         if (2 * pr + 1 >= N) z1 = 0.0;
       }
-      Zs[(2 * pr) * kMmaS + vl] = z0;
-      if (2 * pr + 1 < Np) Zs[(2 * pr + 1) * kMmaS + vl] = z1;
+      T0[(2 * pr) * kMmaS + vl] = z0;
+      if (2 * pr + 1 < Np) T0[(2 * pr + 1) * kMmaS + vl] = z1;
     }
     __syncthreads();
   }
-  const int mtiles = Np >> 3;
   double acc[4][2][2];
-  // ---- GEMM 1 + epilogue: noise, parameters ---------------------------------------------------------------------------------
-  for (int mt0 = 0; mt0 < mtiles; mt0 += 16) {   // groups of 16 m-tiles (128 timesteps): four per warp
-  if (any_philox) {
-    mma_tiles<true>(cinv, Zs, N, mtiles, mt0 + warp, frow, fk, acc);
-  } else {
+  // ---- GEMM 1 + epilogue: noise and parameters, one pass per 128 timesteps ------------------------------------------------------
+  for (int tc0 = 0; tc0 < Np; tc0 += kMmaGroup) {
+    const int tcols = min(kMmaGroup, Np - tc0);
+    if (any_philox) {
+      mma_gemm<true>(a1p, T0, As, bar0, phase, Np, tc0, tcols, acc);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) acc[i][nt][0] = acc[i][nt][1] = 0.0;
-  }
+        for (int nt = 0; nt < 2; ++nt) acc[i][nt][0] = acc[i][nt][1] = 0.0;
+    }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int mt = mt0 + warp + 4 * i;
-    if (mt >= mtiles) continue;
-    const int t = mt * 8 + frow;
+    for (int i = 0; i < 4; ++i) {
+      const int ml = warp + 4 * i;
+      if (ml * 8 >= tcols) continue;
+      const int t = tc0 + ml * 8 + frow;
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
+      for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int vl = nt * 8 + 2 * fk + h;
-        const int fl = s_flags[vl];
-        double e = 0.0;
-        if ((fl & 1) && t < N) {
-          const double th = a.theta[s_th[vl] + t];
-          double pv;
-          if (fl & 4) { e = s_sg[vl] * acc[i][nt][h]; pv = th + e; }
-          else if (fl & 2) { e = a.eps_in[s_row[vl] + t]; pv = th + e; }
-          else { pv = s_src[vl][t]; e = pv - th; }                     // policy_improvement.cpp:222
-          a.noise[s_row[vl] + t] = e;
-          a.params[s_row[vl] + t] = pv;
-          Xs[(kPad + t) * kMmaS + vl] = pv;
+        for (int h = 0; h < 2; ++h) {
+          const int vl = nt * 8 + 2 * fk + h;
+          T1[t * kMmaS + vl] = (s_flags[vl] & 4) ? s_sg[vl] * acc[i][nt][h] : 0.0;     // eps of a Philox vector
         }
-        Es[t * kMmaS + vl] = e;
-      }
+    }
   }
+  __syncthreads();          // Philox eps complete; Z is dead: T0 becomes the padded x
+  // ---- noise and parameters out, coalesced along time (32 consecutive t of one vector per warp); parameters into T0 ----------
+  for (int idx = threadIdx.x; idx < kMmaV * Np; idx += blockDim.x) {
+    const int vl = idx / Np, t = idx - vl * Np;
+    const int fl = s_flags[vl];
+    if (!(fl & 1) || t >= N) continue;
+    const double th = a.theta[s_th[vl] + t];
+    double e, pv;
+    if (fl & 4) { e = T1[t * kMmaS + vl]; pv = th + e; }
+    else if (fl & 2) { e = a.eps_in[s_row[vl] + t]; pv = th + e; }
+    else { pv = s_src[vl][t]; e = pv - th; }                     // policy_improvement.cpp:222
+    a.noise[s_row[vl] + t] = e;
+    a.params[s_row[vl] + t] = pv;
+    T1[t * kMmaS + vl] = e;
+    T0[(kPad + t) * kMmaS + vl] = pv;
   }
   if (!a.mode_control) return;
-  __syncthreads();
+  __syncthreads();          // E and the parameters complete
   // ---- GEMM 2 + epilogue: y = M eps, x = parameters + y ------------------------------------------------------------------
-  for (int mt0 = 0; mt0 < mtiles; mt0 += 16) {
-  mma_tiles<false>(ms, Es, N, mtiles, mt0 + warp, frow, fk, acc);
+  for (int tc0 = 0; tc0 < Np; tc0 += kMmaGroup) {
+    const int tcols = min(kMmaGroup, Np - tc0);
+    mma_gemm<false>(a2p, T1, As, bar0, phase, Np, tc0, tcols, acc);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int mt = mt0 + warp + 4 * i;
-    if (mt >= mtiles) continue;
-    const int t = mt * 8 + frow;
+    for (int i = 0; i < 4; ++i) {
+      const int ml = warp + 4 * i;
+      if (ml * 8 >= tcols) continue;
+      const int t = tc0 + ml * 8 + frow;
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
+      for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int vl = nt * 8 + 2 * fk + h;
-        if ((s_flags[vl] & 1) && t < N) {
-          const double y = acc[i][nt][h];
-          if (a.noise_projected) a.noise_projected[s_row[vl] + t] = y;
-          Xs[(kPad + t) * kMmaS + vl] += y;
+        for (int h = 0; h < 2; ++h) {
+          const int vl = nt * 8 + 2 * fk + h;
+          const int fl = s_flags[vl];
+          if ((fl & 1) && t < N) {
+            const double y = acc[i][nt][h];
+            if (a.noise_projected) a.noise_projected[s_row[vl] + t] = y;
+            T0[(kPad + t) * kMmaS + vl] += y;          // x = parameters + M eps
+          }
         }
-      }
-  }
+    }
   }
   for (int idx = threadIdx.x; idx < kMmaV * kPad; idx += blockDim.x) {
     const int vl = idx % kMmaV, q = idx / kMmaV;
-    Xs[q * kMmaS + vl] = s_ps[vl];
-    Xs[(kPad + N + q) * kMmaS + vl] = s_pg[vl];
+    T0[q * kMmaS + vl] = s_ps[vl];
+    T0[(kPad + N + q) * kMmaS + vl] = s_pg[vl];
   }
-  __syncthreads();
+  __syncthreads();          // x complete; E is dead: T1 becomes the control costs
   // ---- control-cost stencils over [pads, x, pads] (covariant_trajectory_policy.cpp:228-255) -----------------------------------
-  double* Cs = Zs;
-  auto row_cost = [&](int vl, int p) -> double {     // padded row p; taps outside [0, Nall) are the dropped ones
+  const double* Xs = T0;
+  double* Cs = T1;
+  auto row_cost = [&](int vl, int p, bool interior) -> double {     // padded row p; taps outside [0, Nall) are the dropped ones
     double cost = 0.0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -855,7 +940,8 @@ __global__ void __launch_bounds__(128) k_generate_mma(GenArgs a, const double* _
 #pragma unroll
       for (int j = 0; j < 7; ++j) {
         const int idx = p + j - 3;
-        s_ += a.st.coef[k][j] * ((idx < 0 || idx >= Nall) ? 0.0 : Xs[idx * kMmaS + vl]);
+        if (!interior && (idx < 0 || idx >= Nall)) continue;
+        s_ += a.st.coef[k][j] * Xs[idx * kMmaS + vl];
       }
       cost += a.control_weight * a.st.weight[k] * (s_ * s_);
     }
@@ -864,11 +950,11 @@ __global__ void __launch_bounds__(128) k_generate_mma(GenArgs a, const double* _
   for (int idx = threadIdx.x; idx < kMmaV * N; idx += blockDim.x) {
     const int vl = idx % kMmaV, t = idx / kMmaV;
     if (!(s_flags[vl] & 1)) continue;
-    double cost = row_cost(vl, kPad + t);
+    double cost = row_cost(vl, kPad + t, true);
     if (t == 0)
-      for (int q = 0; q < kPad; ++q) cost += row_cost(vl, q);
+      for (int q = 0; q < kPad; ++q) cost += row_cost(vl, q, false);
     if (t == N - 1)
-      for (int q = 0; q < kPad; ++q) cost += row_cost(vl, kPad + N + (kPad - 1 - q));
+      for (int q = 0; q < kPad; ++q) cost += row_cost(vl, kPad + N + (kPad - 1 - q), false);
     Cs[t * kMmaS + vl] = cost;
   }
   __syncthreads();
@@ -992,7 +1078,6 @@ __device__ __forceinline__ float shfl_rel(float v, int delta) {
 // Explicit 32-bit shared-memory addressing for the per-sphere hot loop: the tables live at run-time offsets of the
 // dynamic shared segment, and with generic pointers ptxas re-derived the shared window base (S2UR/ULEA) at almost every
 // access (14 % of k_cost's issued instructions, ncu source page); a 32-bit .shared address needs none of that.
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void lds2(unsigned addr, double& x, double& y) {
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
 }
@@ -1132,35 +1217,6 @@ __device__ __forceinline__ Real trilinear_distance(const Grid& g, const void* vo
         acc += w * corner_distance<Real, kVox>(g, vox, cx + dx, cy + dy, cz + dz, sqrt_tab_addr);
       }
   return acc;
-}
-
-// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier completion -------------------------------------------------
-// One elected thread arms the CTA's mbarrier with the byte count and issues one bulk copy per contiguous block (robot
-// tables, rollout rows); the copy engine moves the bytes into shared memory while the threads go on, and everybody waits
-// on the barrier's phase.  Replaces per-thread 16-byte cp.async loops whose index arithmetic was 12 % of k_cost's
-// instructions (ncu source page, round 1).  Sizes and addresses are multiples of 16 bytes.
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "MBAR_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@!p bra MBAR_WAIT_%=;\n"
-      "}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
 }
 
 // Lane packing: a warp tile is a window of 32 consecutive points of the CTA's *concatenated* timeline
