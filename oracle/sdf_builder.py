@@ -101,3 +101,20 @@ def build(size, origin, resolution, max_distance, boxes=(), cylinders=(), points
     else:
         d2 = np.full(n, cap * cap, dtype=np.int64)
     return d2.astype(np.uint8 if cap * cap < 256 else np.uint16), occ
+
+
+def propagation_field(occ, cap):
+    """distance_field::PropagationDistanceField::addPointsToField restated (oracle/stomp_oracle.cpp,
+    stomp_oracle_propagate_distance_field): squared cell distances [nx][ny][nz], capped at cap^2.  The upstream package is not in
+    the reference repository; this follows its published algorithm (bucket queue over squared distances, closest-point
+    propagation through direction-restricted neighbourhoods)."""
+    import ctypes as C
+    from oracle import oracle
+    occ = np.ascontiguousarray(occ, dtype=np.uint8)
+    out = np.empty(occ.shape, dtype=np.int32)
+    L = oracle.lib()
+    rc = L.stomp_oracle_propagate_distance_field(occ.shape[0], occ.shape[1], occ.shape[2], occ.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                 int(cap), out.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc:
+        raise RuntimeError(L.stomp_oracle_last_error().decode())
+    return out

@@ -29,6 +29,7 @@
 #include "../include/stomp_b200.h"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 #include <random>
@@ -1234,6 +1235,70 @@ int stomp_oracle_get(void* h, int32_t field, void* out_, size_t bytes) {
     case STOMP_FIELD_CONTROL_COST: if (!need(NN * 8)) return fail("buffer too small"); std::copy(o.Rfree.a.begin(), o.Rfree.a.end(), out); return 0;
     default: return fail("unknown field");
   }
+}
+
+/* ---- distance_field::PropagationDistanceField::addPointsToField, restated --------------------------------------------------
+ * The reference rebuilds its field with this class (src/stomp_collision_space.cpp:187, distance_field_->addPointsToField); the
+ * package is NOT in /root/reference (ROS `distance_field`, C-Turtle / Diamondback era, un-vendored), so this follows the
+ * algorithm as that package publishes it: every voxel keeps {distance_square, closest obstacle cell, update direction};
+ * obstacle cells enter bucket 0 with update direction (0,0,0); buckets are processed in order of squared distance; a voxel of
+ * bucket 0 offers its closest point to all 26 neighbours, a voxel of a later bucket only to the 6-connected neighbours that do
+ * not point against the direction it was itself updated from (dx*tdx >= 0, ...); a neighbour takes the offer when
+ * |neighbour - closest|^2 is smaller than what it holds and at most max_distance_sq, and is queued in that bucket.  The
+ * restricted neighbourhoods make this a propagation, not an exact transform: tests/test_oracle_kats.py counts where it
+ * differs from the exact capped EDT the engine (and oracle/sdf_builder.py) compute.  occ / out are [nx][ny][nz]. */
+int stomp_oracle_propagate_distance_field(int32_t nx, int32_t ny, int32_t nz, const uint8_t* occ, int32_t cap, int32_t* out_d2) {
+  if (!occ || !out_d2 || nx < 1 || ny < 1 || nz < 1 || cap < 1) return fail("bad argument");
+  const int max_sq = cap * cap;
+  const size_t cells = size_t(nx) * ny * nz;
+  struct Vox { int d2; int cp[3]; int dir; };
+  std::vector<Vox> v(cells);
+  for (size_t i = 0; i < cells; ++i) { v[i].d2 = max_sq; v[i].cp[0] = v[i].cp[1] = v[i].cp[2] = -1; v[i].dir = -1; }
+  auto dirnum = [](int dx, int dy, int dz) { return (dx + 1) * 9 + (dy + 1) * 3 + dz + 1; };
+  // neighbourhoods_[0][dir]: all 26 targets; neighbourhoods_[1][dir]: 6-connected targets not against dir
+  std::vector<std::array<int, 3> > nb[2][27];
+  for (int n = 0; n < 2; ++n)
+    for (int dx = -1; dx <= 1; ++dx) for (int dy = -1; dy <= 1; ++dy) for (int dz = -1; dz <= 1; ++dz)
+      for (int tx = -1; tx <= 1; ++tx) for (int ty = -1; ty <= 1; ++ty) for (int tz = -1; tz <= 1; ++tz) {
+        if (tx == 0 && ty == 0 && tz == 0) continue;
+        if (n >= 1) {
+          if (std::abs(tx) + std::abs(ty) + std::abs(tz) != 1) continue;
+          if (dx * tx < 0 || dy * ty < 0 || dz * tz < 0) continue;
+        }
+        nb[n][dirnum(dx, dy, dz)].push_back({tx, ty, tz});
+      }
+  std::vector<std::vector<size_t> > buckets(size_t(max_sq) + 1);
+  for (int x = 0; x < nx; ++x) for (int y = 0; y < ny; ++y) for (int z = 0; z < nz; ++z) {
+    const size_t i = (size_t(x) * ny + y) * nz + z;
+    if (!occ[i]) continue;
+    v[i].d2 = 0; v[i].cp[0] = x; v[i].cp[1] = y; v[i].cp[2] = z; v[i].dir = dirnum(0, 0, 0);
+    buckets[0].push_back(i);
+  }
+  for (int b = 0; b <= max_sq; ++b) {
+    for (size_t q = 0; q < buckets[b].size(); ++q) {     // the bucket may grow while it is processed (offers at equal distance never win)
+      const size_t i = buckets[b][q];
+      const Vox cur = v[i];
+      if (cur.dir < 0 || cur.dir > 26) continue;
+      const int z = int(i % nz), y = int((i / nz) % ny), x = int(i / (size_t(nz) * ny));
+      for (const auto& t : nb[b > 1 ? 1 : b][cur.dir]) {
+        const int X = x + t[0], Y = y + t[1], Z = z + t[2];
+        if (X < 0 || Y < 0 || Z < 0 || X >= nx || Y >= ny || Z >= nz) continue;
+        const int ddx = X - cur.cp[0], ddy = Y - cur.cp[1], ddz = Z - cur.cp[2];
+        const int nd = ddx * ddx + ddy * ddy + ddz * ddz;
+        if (nd > max_sq) continue;
+        Vox& nv = v[(size_t(X) * ny + Y) * nz + Z];
+        if (nd < nv.d2) {
+          nv.d2 = nd;
+          nv.cp[0] = cur.cp[0]; nv.cp[1] = cur.cp[1]; nv.cp[2] = cur.cp[2];
+          nv.dir = dirnum(t[0], t[1], t[2]);
+          buckets[nd].push_back((size_t(X) * ny + Y) * nz + Z);
+        }
+      }
+    }
+    std::vector<size_t>().swap(buckets[b]);
+  }
+  for (size_t i = 0; i < cells; ++i) out_d2[i] = v[i].d2;
+  return 0;
 }
 
 } /* extern "C" */
