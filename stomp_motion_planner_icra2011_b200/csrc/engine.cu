@@ -128,7 +128,7 @@ struct Engine {
   int gen_mode = 0;   // 0: pick k_generate / k_generate_dense / k_generate_mma by batch shape; 1, 2, 3: always that one (A/B)
   DevBuf<double> limit_min, limit_max;
   DevBuf<int> has_limits;
-  DevBuf<unsigned char> nodes, spheres, sqrt_table, vox;
+  DevBuf<unsigned char> nodes, spheres, sqrt_table, vox, vox_brick;
   DevBuf<double> scratch_params, scratch_noise, scratch_costs;  // execute / compute_control_costs staging
   DevBuf<int> scratch_flags;
   DevBuf<stomp_sphere_debug> debug;
@@ -1122,6 +1122,31 @@ int upload_constraints(Engine& e) {
 }
 Engine* E(void* h) { return static_cast<Engine*>(h); }
 
+// the bricked copy of the distance field k_cost gathers from (kernels.cuh, struct Sdf)
+int build_bricks(Engine& e) {
+  e.sdf.brick = nullptr;
+  e.sdf.nby = (e.sdf.ny + 3) / 4;
+  e.sdf.nbz = (e.sdf.nz + 1) / 2;
+  if (getenv("STOMP_NO_BRICKS") && atoi(getenv("STOMP_NO_BRICKS")) != 0) return 0;
+  const size_t esz = e.sdf.dtype == STOMP_VOXEL_U8_SQ ? 1 : e.sdf.dtype == STOMP_VOXEL_U16_SQ ? 2 : 4;
+  const size_t cells = size_t((e.sdf.nx + 3) / 4) * e.sdf.nby * e.sdf.nbz * 32;
+  if (cells >= (size_t(1) << 31)) return 0;   // 32-bit brick indices: keep the plain layout
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.tail_stream));
+  if (e.vox_brick.n != cells * esz) CUDA_TRY(e.vox_brick.alloc(cells * esz));
+  const size_t n = size_t(e.sdf.nx) * e.sdf.ny * e.sdf.nz;
+  const unsigned grid = unsigned(std::min<size_t>((n + 255) / 256, size_t(148) * 64));
+  begin_launch(e);
+  if (esz == 1) k_brick_relayout<uint8_t><<<grid, 256, 0, e.ws>>>(e.sdf.nx, e.sdf.ny, e.sdf.nz, e.sdf.nby, e.sdf.nbz, static_cast<const uint8_t*>(e.sdf.vox), reinterpret_cast<uint8_t*>(e.vox_brick.p));
+  else if (esz == 2) k_brick_relayout<uint16_t><<<grid, 256, 0, e.ws>>>(e.sdf.nx, e.sdf.ny, e.sdf.nz, e.sdf.nby, e.sdf.nbz, static_cast<const uint16_t*>(e.sdf.vox), reinterpret_cast<uint16_t*>(e.vox_brick.p));
+  else k_brick_relayout<float><<<grid, 256, 0, e.ws>>>(e.sdf.nx, e.sdf.ny, e.sdf.nz, e.sdf.nby, e.sdf.nbz, static_cast<const float*>(e.sdf.vox), reinterpret_cast<float*>(e.vox_brick.p));
+  if (check_launch(e, "k_brick_relayout")) return 1;
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  e.sdf.brick = e.vox_brick.p;
+  return 0;
+}
+
+
 #define ENGINE_NOJOIN(h)                           \
   if (!(h)) return fail("null engine handle");     \
   Engine& e = *E(h);                               \
@@ -1382,6 +1407,7 @@ int stomp_engine_set_sdf(void* h, const void* voxels, int32_t nx, int32_t ny, in
   e.sdf.res = resolution;
   e.sdf.inv_res = 1.0 / resolution;
   if (e.f32 ? upload_sqrt_table<float>(e) : upload_sqrt_table<double>(e)) return 1;
+  if (build_bricks(e)) return 1;
   e.have_sdf = true;
   e.cull_dirty = true;
   ++e.config_epoch;
@@ -1551,6 +1577,7 @@ int stomp_engine_build_sdf_bodies(void* h, const double size[3], const double or
   e.sdf.res = resolution;
   e.sdf.inv_res = 1.0 / resolution;
   if (e.f32 ? upload_sqrt_table<float>(e) : upload_sqrt_table<double>(e)) return 1;
+  if (build_bricks(e)) return 1;
   e.have_sdf = true;
   e.cull_dirty = true;
   ++e.config_epoch;

@@ -91,10 +91,29 @@ struct Stencil {        // control-cost stencils of CovariantTrajectoryPolicy
 };
 
 struct Sdf {
-  const void* vox;
+  const void* vox;       // [nx][ny][nz], z fastest: the layout of the C ABI (set_sdf / get_sdf), of the rebuild and of the trilinear mode
   int nx, ny, nz, dtype;
   double origin[3], res, inv_res;
+  // the same cells in bricks of 4 x 4 x 2 (one 32-byte sector of u8 cells per brick): what k_cost's nearest-cell lookup gathers
+  // from.  A warp's lanes are consecutive timesteps of one sphere, i.e. positions a cell or two apart in an arbitrary
+  // direction; in the z-fastest layout a sector is a 32-cell column, so motion across x or y costs one sector per lane.
+  const void* brick;     // nullptr: gather from `vox`
+  int nby, nbz;          // bricks along y and z
 };
+#ifndef STOMP_SDF_BRICKS
+#define STOMP_SDF_BRICKS 1
+#endif
+__host__ __device__ __forceinline__ int brick_index(int cx, int cy, int cz, int nby, int nbz) {
+  return ((((cx >> 2) * nby + (cy >> 2)) * nbz + (cz >> 1)) << 5) | ((cx & 3) << 3) | ((cy & 3) << 1) | (cz & 1);
+}
+template <typename V>
+__global__ void k_brick_relayout(int nx, int ny, int nz, int nby, int nbz, const V* __restrict__ src, V* __restrict__ dst) {
+  const size_t cells = size_t(nx) * ny * nz;
+  for (size_t v = size_t(blockIdx.x) * blockDim.x + threadIdx.x; v < cells; v += size_t(gridDim.x) * blockDim.x) {
+    const int z = int(v % nz), y = int((v / nz) % ny), x = int(v / (size_t(nz) * ny));
+    dst[brick_index(x, y, z, nby, nbz)] = src[v];
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 + Box-Muller: one stream per (problem, global rollout, dimension), counter = sample pair
@@ -1119,11 +1138,11 @@ template <> struct SphereRegsOf<float> { typedef SphereRegsF type; };
 // reference form for every input.
 struct GridD {   // per-kernel constants of the lookup
   double ox, oy, oz, res, inv_res, nox, noy, noz;   // no* = -origin/res
-  int nx1, ny1, nz1, sny, snz;
+  int nx1, ny1, nz1, sny, snz, nby, nbz;
 };
 struct GridF {
   float ox, oy, oz, res, inv_res, nox, noy, noz;
-  int nx1, ny1, nz1, sny, snz;
+  int nx1, ny1, nz1, sny, snz, nby, nbz;
 };
 template <typename Real> struct GridOf;
 template <> struct GridOf<double> { typedef GridD type; };
@@ -1262,10 +1281,12 @@ __global__ void __launch_bounds__(kCostMaxThreads, STOMP_COST_MIN_BLOCKS) k_cost
   g.ox = a.g_ox; g.oy = a.g_oy; g.oz = a.g_oz; g.res = a.g_res; g.inv_res = a.g_inv_res;
   g.nox = a.g_nox; g.noy = a.g_noy; g.noz = a.g_noz;
   g.nx1 = a.sdf.nx - 1; g.ny1 = a.sdf.ny - 1; g.nz1 = a.sdf.nz - 1; g.sny = a.sdf.ny; g.snz = a.sdf.nz;
+  g.nby = a.sdf.nby; g.nbz = a.sdf.nbz;
   const Real c_m1 = a.c_m1, c_0 = a.c_0, c_p1 = a.c_p1, c_p2 = a.c_p2;
   const int ntiles = a.tiles_per_job;
   const int seg = N + 3;                       // timeline points per rollout: t = -1 .. N+1
-  const void* vox = a.sdf.vox;
+  const bool bricks = STOMP_SDF_BRICKS && !kTri && a.sdf.brick != nullptr;
+  const void* vox = bricks ? a.sdf.brick : a.sdf.vox;
   const int njobs = (a.total_rollouts + P - 1) / P;
 
   unsigned phase = 0;
@@ -1473,7 +1494,9 @@ __global__ void __launch_bounds__(kCostMaxThreads, STOMP_COST_MIN_BLOCKS) k_cost
             } else {
               const bool inside = voxel_cells(g, px, py, pz, cx, cy, cz);
               // outside the grid (or within one cell of its faces) the reference returns distance 0
-              dist = inside ? voxel_distance<Real, kVox>(vox, (cx * g.sny + cy) * g.snz + cz, tab_addr, g.res) : Real(0);
+              dist = inside ? voxel_distance<Real, kVox>(vox, bricks ? brick_index(cx, cy, cz, g.nby, g.nbz) : (cx * g.sny + cy) * g.snz + cz,
+                                                         tab_addr, g.res)
+                            : Real(0);
             }
             // three-piece potential (stomp_collision_space.h:209-226), branch-free
             const Real radius = sp.radius, clearance = sp.clearance;
