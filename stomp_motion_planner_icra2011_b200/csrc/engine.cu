@@ -471,7 +471,7 @@ int launch_cost_k(Engine& e, CostArgs<Real>& a, int num_problems) {
   auto tiles_for = [&](int p) { return (p * seg - 3 + kTileSteps - 1) / kTileSteps; };
   auto smem_for = [&](int p, int warps) {
     return ((size_t(p) * (size_t(e.D) * e.N + 2 * e.D) * 8 + 15) & ~size_t(15)) + size_t(e.num_nodes) * sizeof(DevNode<Real>) +
-           size_t(e.K) * sizeof(DevSphere<Real>) + 256 * sizeof(Real) + size_t(warps) * 12 * 32 * sizeof(Real) +
+           size_t(e.K) * sizeof(DevSphere<Real>) + 256 * sizeof(Real) +
            e.constraints.size() * sizeof(DevConstraint<Real>) + e.clusters.size() * sizeof(DevCluster<Real>) + 16 /* mbarrier */;
   };
   const int max_warps = kCostMaxThreads / 32;

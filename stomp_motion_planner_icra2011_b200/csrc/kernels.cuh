@@ -1255,8 +1255,8 @@ __global__ void __launch_bounds__(kCostMaxThreads, STOMP_COST_MIN_BLOCKS) k_cost
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = a.D, N = a.N, K = a.K, P = a.pack;
   const int DN = D * N;
-  // shared layout: rollouts [P][D][N] | start/goal padding [P][2][D] | nodes | spheres | sqrt table | per-warp velocity frames |
-  // constraints | clusters | mbarrier
+  // shared layout: rollouts [P][D][N] | start/goal padding [P][2][D] | nodes | spheres | sqrt table | constraints | clusters |
+  // mbarrier
   double* q = reinterpret_cast<double*>(smem_raw);                        // joint-limit-projected trajectories
   double* pads = q + size_t(P) * DN;
   DevNode<Real>* nodes = reinterpret_cast<DevNode<Real>*>(smem_raw + ((size_t(P) * (DN + 2 * D) * 8 + 15) & ~size_t(15)));
@@ -1264,11 +1264,8 @@ __global__ void __launch_bounds__(kCostMaxThreads, STOMP_COST_MIN_BLOCKS) k_cost
   Real* sqrt_tab = reinterpret_cast<Real*>(spheres + K);                  // [256]
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  // per-warp velocity frame [12][32]: kept in shared memory so that the register file holds only one frame
-  const unsigned vs_addr = smem_u32(sqrt_tab + 256 + size_t(warp) * 12 * 32 + lane);
   const unsigned sph_addr = smem_u32(spheres), tab_addr = smem_u32(sqrt_tab);
-  constexpr unsigned kVsStride = 32 * sizeof(Real);
-  DevConstraint<Real>* cons = reinterpret_cast<DevConstraint<Real>*>(sqrt_tab + 256 + size_t(nwarps) * 12 * 32);
+  DevConstraint<Real>* cons = reinterpret_cast<DevConstraint<Real>*>(sqrt_tab + 256);
   const int num_cons = kCons ? a.num_constraints : 0;
   DevCluster<Real>* clusters = reinterpret_cast<DevCluster<Real>*>(cons + num_cons);
   const unsigned bar = smem_u32(clusters + a.num_clusters);
@@ -1458,9 +1455,6 @@ __global__ void __launch_bounds__(kCostMaxThreads, STOMP_COST_MIN_BLOCKS) k_cost
           }
         const int sph_begin = nd.sphere_begin, sph_end = nd.sphere_end;
         if (sph_end > sph_begin) {
-          // velocity frame V = sum_k rule_k/dt * F(t+k), vel(sphere) = V.R * p + V.p (linear in the frame); built
-          // lazily, only when some lane of the warp has a sphere of this link inside its clearance band
-          bool haveV = false;
           for (int ci = nd.cluster_begin; ci < nd.cluster_end; ++ci) {
           const DevCluster<Real>& cl = clusters[ci];
           if (kCull) {
@@ -1508,18 +1502,11 @@ __global__ void __launch_bounds__(kCostMaxThreads, STOMP_COST_MIN_BLOCKS) k_cost
             collided |= int(hit & counts);
             Real vm = Real(0);
             if (__any_sync(0xffffffffu, kDebug || pot != Real(0))) {
-              if (!haveV) {
-#pragma unroll
-                for (int i = 0; i < 12; ++i)
-                  sts1(vs_addr + i * kVsStride, c_m1 * shfl_rel(F[i], -1) + c_0 * F[i] + c_p1 * shfl_rel(F[i], 1) + c_p2 * shfl_rel(F[i], 2));
-                haveV = true;
-              }
-              Real V[12];
-#pragma unroll
-              for (int i = 0; i < 12; ++i) V[i] = lds1(vs_addr + i * kVsStride, Real(0));
-              const Real vx = V[0] * s0 + V[1] * s1 + V[2] * s2 + V[9];
-              const Real vy = V[3] * s0 + V[4] * s1 + V[5] * s2 + V[10];
-              const Real vz = V[6] * s0 + V[7] * s1 + V[8] * s2 + V[11];
+              // finite-difference velocity of the sphere centre from the neighbouring lanes' positions (t-1, t+1, t+2): exactly
+              // the reference's formulation (positions differentiated, src/stomp_optimizer.cpp:672-690); no velocity frame
+              const Real vx = c_m1 * shfl_rel(px, -1) + c_0 * px + c_p1 * shfl_rel(px, 1) + c_p2 * shfl_rel(px, 2);
+              const Real vy = c_m1 * shfl_rel(py, -1) + c_0 * py + c_p1 * shfl_rel(py, 1) + c_p2 * shfl_rel(py, 2);
+              const Real vz = c_m1 * shfl_rel(pz, -1) + c_0 * pz + c_p1 * shfl_rel(pz, 1) + c_p2 * shfl_rel(pz, 2);
               vm = Math<Real>::sqrt_(vx * vx + vy * vy + vz * vz);
               cost += lds1(sa + 6 * unsigned(sizeof(Real)), Real(0)) * (pot * vm);   // DevSphere::weight
             }
