@@ -548,6 +548,7 @@ CostArgs<Real> base_cost_args(Engine& e) {
   // finite-difference velocity rule {-2, -3, 6, -1} / 6 over t-1 .. t+2, divided by dt (stomp_utils.h:49-56)
   a.c_m1 = Real(a.inv_time * (-2.0 / 6.0)); a.c_0 = Real(a.inv_time * (-3.0 / 6.0)); a.c_p1 = Real(a.inv_time * (6.0 / 6.0));
   a.c_p2 = Real(a.inv_time * (-1.0 / 6.0));
+  a.lim_x = unsigned(e.sdf.nx - 2); a.lim_y = unsigned(e.sdf.ny - 2); a.lim_z = unsigned(e.sdf.nz - 2);
   return a;
 }
 
@@ -1127,10 +1128,9 @@ int build_bricks(Engine& e) {
   e.sdf.brick = nullptr;
   e.sdf.nby = (e.sdf.ny + 3) / 4;
   e.sdf.nbz = (e.sdf.nz + 1) / 2;
-  if (getenv("STOMP_NO_BRICKS") && atoi(getenv("STOMP_NO_BRICKS")) != 0) return 0;
   const size_t esz = e.sdf.dtype == STOMP_VOXEL_U8_SQ ? 1 : e.sdf.dtype == STOMP_VOXEL_U16_SQ ? 2 : 4;
   const size_t cells = size_t((e.sdf.nx + 3) / 4) * e.sdf.nby * e.sdf.nbz * 32;
-  if (cells >= (size_t(1) << 31)) return 0;   // 32-bit brick indices: keep the plain layout
+  if (cells >= (size_t(1) << 31)) return fail("distance field too large (padded to bricks of 4 x 4 x 2, cells must fit a 32-bit index)");
   CUDA_TRY(cudaStreamSynchronize(e.stream));
   CUDA_TRY(cudaStreamSynchronize(e.tail_stream));
   if (e.vox_brick.n != cells * esz) CUDA_TRY(e.vox_brick.alloc(cells * esz));

@@ -1029,6 +1029,7 @@ struct CostArgs {
   // instead of occupying ~20 registers per thread (grid origin, resolution, -origin/res, finite-difference rule / dt)
   Real g_ox, g_oy, g_oz, g_res, g_inv_res, g_nox, g_noy, g_noz;
   Real c_m1, c_0, c_p1, c_p2;
+  unsigned lim_x, lim_y, lim_z;     // n - 2 per axis
 };
 
 template <typename Real> struct Math;
@@ -1139,10 +1140,12 @@ template <> struct SphereRegsOf<float> { typedef SphereRegsF type; };
 struct GridD {   // per-kernel constants of the lookup
   double ox, oy, oz, res, inv_res, nox, noy, noz;   // no* = -origin/res
   int nx1, ny1, nz1, sny, snz, nby, nbz;
+  unsigned lx, ly, lz;                              // n - 2: a cell is interior when unsigned(c - 1) < l
 };
 struct GridF {
   float ox, oy, oz, res, inv_res, nox, noy, noz;
   int nx1, ny1, nz1, sny, snz, nby, nbz;
+  unsigned lx, ly, lz;
 };
 template <typename Real> struct GridOf;
 template <> struct GridOf<double> { typedef GridD type; };
@@ -1176,7 +1179,7 @@ __device__ __forceinline__ bool voxel_cells(const GridD& g, double px, double py
     cy = exact_cell(py, g.oy, g.res);
     cz = exact_cell(pz, g.oz, g.res);
   }
-  return (unsigned(cx - 1) < unsigned(g.nx1 - 1)) & (unsigned(cy - 1) < unsigned(g.ny1 - 1)) & (unsigned(cz - 1) < unsigned(g.nz1 - 1));
+  return (unsigned(cx - 1) < g.lx) & (unsigned(cy - 1) < g.ly) & (unsigned(cz - 1) < g.lz);
 }
 __device__ __forceinline__ bool voxel_cells(const GridF& g, float px, float py, float pz, int& cx, int& cy, int& cz) {
   const float tx = fmaf(px, g.inv_res, g.nox), ty = fmaf(py, g.inv_res, g.noy), tz = fmaf(pz, g.inv_res, g.noz);
@@ -1188,7 +1191,7 @@ __device__ __forceinline__ bool voxel_cells(const GridF& g, float px, float py, 
     cy = exact_cell(py, g.oy, g.res);
     cz = exact_cell(pz, g.oz, g.res);
   }
-  return (unsigned(cx - 1) < unsigned(g.nx1 - 1)) & (unsigned(cy - 1) < unsigned(g.ny1 - 1)) & (unsigned(cz - 1) < unsigned(g.nz1 - 1));
+  return (unsigned(cx - 1) < g.lx) & (unsigned(cy - 1) < g.ly) & (unsigned(cz - 1) < g.lz);
 }
 
 // distance of one voxel: PropagationDistanceField::getDistance = sqrt_table[d^2] (u8 / u16 grids) or metres (f32)
@@ -1279,10 +1282,11 @@ __global__ void __launch_bounds__(kCostMaxThreads, STOMP_COST_MIN_BLOCKS) k_cost
   g.nox = a.g_nox; g.noy = a.g_noy; g.noz = a.g_noz;
   g.nx1 = a.sdf.nx - 1; g.ny1 = a.sdf.ny - 1; g.nz1 = a.sdf.nz - 1; g.sny = a.sdf.ny; g.snz = a.sdf.nz;
   g.nby = a.sdf.nby; g.nbz = a.sdf.nbz;
+  g.lx = a.lim_x; g.ly = a.lim_y; g.lz = a.lim_z;
   const Real c_m1 = a.c_m1, c_0 = a.c_0, c_p1 = a.c_p1, c_p2 = a.c_p2;
   const int ntiles = a.tiles_per_job;
   const int seg = N + 3;                       // timeline points per rollout: t = -1 .. N+1
-  const bool bricks = STOMP_SDF_BRICKS && !kTri && a.sdf.brick != nullptr;
+  constexpr bool bricks = STOMP_SDF_BRICKS && !kTri;      // the engine always builds the bricked copy
   const void* vox = bricks ? a.sdf.brick : a.sdf.vox;
   const int njobs = (a.total_rollouts + P - 1) / P;
 
@@ -1473,7 +1477,8 @@ __global__ void __launch_bounds__(kCostMaxThreads, STOMP_COST_MIN_BLOCKS) k_cost
             const bool clear = Real(lb) >= cl.thr;
             if (__all_sync(0xffffffffu, clear || !(productive || counts))) continue;
           }
-          for (int j = cl.begin; j < cl.end; ++j) {
+          const int jb = cl.begin, je = cl.end;     // locals: the loop must not re-read the bounds from shared memory
+          for (int j = jb; j < je; ++j) {
             const unsigned sa = sph_addr + unsigned(j) * unsigned(sizeof(DevSphere<Real>));
             typename SphereRegsOf<Real>::type sp;
             load_sphere(sa, sp);
