@@ -1466,14 +1466,17 @@ __global__ void __launch_bounds__(kCostMaxThreads, STOMP_COST_MIN_BLOCKS) k_cost
             const Real qx = F[0] * cl.c[0] + F[1] * cl.c[1] + F[2] * cl.c[2] + F[9];
             const Real qy = F[3] * cl.c[0] + F[4] * cl.c[1] + F[5] * cl.c[2] + F[10];
             const Real qz = F[6] * cl.c[0] + F[7] * cl.c[1] + F[8] * cl.c[2] + F[11];
-            const Real ux = Math<Real>::fma_(qx, g.inv_res, g.nox) + Real(0.5);      // fine cell = floor(u)
-            const Real uy = Math<Real>::fma_(qy, g.inv_res, g.noy) + Real(0.5);
-            const Real uz = Math<Real>::fma_(qz, g.inv_res, g.noz) + Real(0.5);
-            const Real m = cl.margin;
-            const bool in = (ux >= m) & (ux <= Real(g.nx1 + 1) - m) & (uy >= m) & (uy <= Real(g.ny1 + 1) - m) & (uz >= m) &
-                            (uz <= Real(g.nz1 + 1) - m);
+            // the coarse lookup in fp32: a centre that lands in a neighbouring coarse cell through rounding is covered by the
+            // one-cell slack the threshold already carries (engine.cu, upload_cluster_thresholds), and the margin test keeps
+            // every fine cell concerned interior
+            const float ux = fmaf(float(qx), float(g.inv_res), float(g.nox)) + 0.5f;      // fine cell = floor(u)
+            const float uy = fmaf(float(qy), float(g.inv_res), float(g.noy)) + 0.5f;
+            const float uz = fmaf(float(qz), float(g.inv_res), float(g.noz)) + 0.5f;
+            const float m = float(cl.margin);
+            const bool in = (ux >= m) & (ux <= float(g.nx1 + 1) - m) & (uy >= m) & (uy <= float(g.ny1 + 1) - m) & (uz >= m) &
+                            (uz <= float(g.nz1 + 1) - m);
             float lb = -1.0f;
-            if (in) lb = __ldg(a.cull.g + (size_t(int(ux * Real(0.25))) * a.cull.ny + int(uy * Real(0.25))) * a.cull.nz + int(uz * Real(0.25)));
+            if (in) lb = __ldg(a.cull.g + (int(ux * 0.25f) * a.cull.ny + int(uy * 0.25f)) * a.cull.nz + int(uz * 0.25f));
             const bool clear = Real(lb) >= cl.thr;
             if (__all_sync(0xffffffffu, clear || !(productive || counts))) continue;
           }
