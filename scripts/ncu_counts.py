@@ -32,19 +32,25 @@ for r in csv.reader(io.StringIO(src)):
         kern.append(cur)
     elif cur is not None and len(r) == len(cur["hdr"]):
         cur["rows"].append(r)
-k = kern[main_pos]
-iS, iI = k["hdr"].index("Source"), k["hdr"].index("Instructions Executed")
-fp64 = tot = 0
-for r in k["rows"]:
-    try:
-        n = int(r[iI])
-    except ValueError:
-        continue
-    tot += n
-    op = r[iS].strip().split()
-    op = op[1] if op and op[0].startswith("@") else (op[0] if op else "")
-    if op.startswith(("DFMA", "DMUL", "DADD", "DSETP", "DMNMX")):
-        fp64 += n
+def tally(k):
+    iS, iI = k["hdr"].index("Source"), k["hdr"].index("Instructions Executed")
+    fp64 = tot = 0
+    for r in k["rows"]:
+        try:
+            n = int(r[iI])
+        except ValueError:
+            continue
+        tot += n
+        op = r[iS].strip().split()
+        op = op[1] if op and op[0].startswith("@") else (op[0] if op else "")
+        if op.startswith(("DFMA", "DMUL", "DADD", "DSETP", "DMNMX")):
+            fp64 += n
+    return tot, fp64
+
+
+# the report lists one or more SASS sections per launch: take the one whose instruction total is the launch's own
+want = val("smsp__inst_executed.sum")
+tot, fp64 = min((tally(k) for k in kern), key=lambda tf: abs(tf[0] - want))
 res = {"kernel": main[h.index("Kernel Name")], "grid": int(float(main[gi])), "evals_of_launch": evals,
        "duration_us_under_ncu": val("gpu__time_duration.sum") / 1e3 if units[h.index("gpu__time_duration.sum")] in ("nsecond", "ns") else val("gpu__time_duration.sum"),
        "warp_inst": val("smsp__inst_executed.sum"), "warp_inst_per_eval": val("smsp__inst_executed.sum") / evals,

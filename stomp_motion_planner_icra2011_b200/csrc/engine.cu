@@ -656,6 +656,7 @@ int launch_update(Engine& e, int apply, bool fuse_extra_control) {
   };
   // enough CTAs to fill the machine twice when the batch allows it; otherwise one dimension per CTA
   int dpc = int(std::min<long long>(std::min(e.D, 32), std::max<long long>(1, (long long)e.B * e.D / 296)));
+  if (const char* ov = getenv("STOMP_UPDATE_DPC")) dpc = std::max(1, std::min(e.D, atoi(ov)));   // A/B: dimensions per CTA
   size_t smem = update_smem(dpc);
   while (smem > 200 * 1024 && dpc > 1) smem = update_smem(--dpc);
   a.dims_per_cta = dpc;
