@@ -124,6 +124,7 @@ struct Engine {
   DevBuf<double> dense_cinv, dense_ms;   // [N][N] C^-1 and R^-1 diag(s) for k_generate_dense (small batches)
   DevBuf<double> mma_a1, mma_a2;         // the same two, zero-padded to [Np][Np] (Np = N rounded up to 8): k_generate_mma's A operands
   bool dense_update = true;   // A/B switch (STOMP_NO_DENSE_UPDATE=1): k_update projects with the banded solves
+  bool split_cost = true;     // A/B switch (STOMP_NO_SPLIT_COST=1): small batches take the one-warp-per-tile k_cost like large ones
   bool dmma_update = true;    // A/B switch (STOMP_NO_DMMA=1): the dense projection runs as scalar DFMAs instead of DMMA tiles
   int gen_mode = 0;   // 0: pick k_generate / k_generate_dense / k_generate_mma by batch shape; 1, 2, 3: always that one (A/B)
   DevBuf<double> limit_min, limit_max;
@@ -479,6 +480,20 @@ int launch_cost_k(Engine& e, CostArgs<Real>& a, int num_problems) {
   if (!kDebug)
     for (int p = 2; p <= 4 && p <= a.total_rollouts; ++p)
       if (tiles_for(p) * pack < tiles_for(pack) * p && smem_for(p, std::min(tiles_for(p), max_warps)) <= 56 * 1024) pack = p;
+  // small batches: kSplitGroups warps per tile (kernels.cuh, kSplit) when a few rollouts cannot fill the machine anyway
+  if (!kDebug && !kCons && !kTri && e.split_cost && a.total_rollouts <= 2 * e.num_sms && e.K >= 2 * kSplitGroups) {
+    const int t1 = tiles_for(1);
+    const size_t smem1 = smem_for(1, t1) + size_t(t1) * e.K * 32 * sizeof(Real);
+    if (t1 * kSplitGroups * 32 <= kSplitMaxThreads && smem1 <= 200 * 1024) {
+      auto ks = k_cost<Real, false, kVox, false, false, kCull, true>;
+      if (smem1 > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
+      a.pack = 1;
+      a.tiles_per_job = t1;
+      begin_launch(e);
+      ks<<<a.total_rollouts, t1 * kSplitGroups * 32, smem1, e.ws>>>(a);
+      return check_launch(e, "k_cost");
+    }
+  }
   const int tiles = tiles_for(pack);
   int warps = std::min(tiles, max_warps);
   warps = std::max(warps, std::min(pack * e.D, 4));  // joint-limit pass likes a few warps
@@ -1309,6 +1324,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
     e.chain_probe = false;
   e.dense_update = !(getenv("STOMP_NO_DENSE_UPDATE") && atoi(getenv("STOMP_NO_DENSE_UPDATE")) != 0);
   e.dmma_update = !(getenv("STOMP_NO_DMMA") && atoi(getenv("STOMP_NO_DMMA")) != 0);
+  e.split_cost = !(getenv("STOMP_NO_SPLIT_COST") && atoi(getenv("STOMP_NO_SPLIT_COST")) != 0);
   e.noise_stddev.assign(e.D, 1.0);
   e.noise_decay.assign(e.D, 1.0);
   std::vector<int> hl(e.D, 0);

@@ -1042,6 +1042,8 @@ template <> struct Math<double> {
   static __device__ __forceinline__ double asin_(double x) { return asin(x); }
   static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
   static __device__ __forceinline__ double cos_(double x) { return cos(x); }
+  static __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 };
 template <> struct Math<float> {
   static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
@@ -1052,6 +1054,8 @@ template <> struct Math<float> {
   static __device__ __forceinline__ float asin_(float x) { return asinf(x); }
   static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
   static __device__ __forceinline__ float cos_(float x) { return cosf(x); }
+  static __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
 };
 
 // cost of one orientation constraint for the segment rotation Rs = Fr * rel (Fr: rotation of the carrying node's frame, or
@@ -1253,10 +1257,19 @@ __device__ __forceinline__ Real trilinear_distance(const Grid& g, const void* vo
 #endif
 constexpr int kCostMaxThreads = 224;   // 7 warps; 72 registers -> 4 CTAs (28 warps) per SM
 
-template <typename Real, bool kDebug, int kVox, bool kCons, bool kTri = false, bool kCull = false>
-__global__ void __launch_bounds__(kCostMaxThreads, STOMP_COST_MIN_BLOCKS) k_cost(CostArgs<Real> a) {
+// kSplit (small batches: a handful of rollouts cannot fill the machine, so k_cost's time is ONE warp's latency — C1: 36 us for
+// five rollouts): kSplitGroups warps share a 29-timestep tile.  Each runs the whole FK (redundant, but off nobody's critical
+// path) and evaluates every kSplitGroups-th sphere cluster, parking each sphere's weighted contribution in shared memory;
+// after a barrier one warp per tile adds the K contributions in sphere order — the same additions in the same order as the
+// sequential loop (a sphere that contributed nothing adds +0), so the costs are bit-identical to the unsplit kernel.
+constexpr int kSplitGroups = 4;
+constexpr int kSplitMaxThreads = 512;
+
+template <typename Real, bool kDebug, int kVox, bool kCons, bool kTri = false, bool kCull = false, bool kSplit = false>
+__global__ void __launch_bounds__(kSplit ? kSplitMaxThreads : kCostMaxThreads, kSplit ? 1 : STOMP_COST_MIN_BLOCKS) k_cost(CostArgs<Real> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = a.D, N = a.N, K = a.K, P = a.pack;
+  constexpr int S = kSplit ? kSplitGroups : 1;
   const int DN = D * N;
   // shared layout: rollouts [P][D][N] | start/goal padding [P][2][D] | nodes | spheres | sqrt table | constraints | clusters |
   // mbarrier
@@ -1272,6 +1285,7 @@ __global__ void __launch_bounds__(kCostMaxThreads, STOMP_COST_MIN_BLOCKS) k_cost
   const int num_cons = kCons ? a.num_constraints : 0;
   DevCluster<Real>* clusters = reinterpret_cast<DevCluster<Real>*>(cons + num_cons);
   const unsigned bar = smem_u32(clusters + a.num_clusters);
+  Real* contrib = reinterpret_cast<Real*>(reinterpret_cast<unsigned char*>(clusters + a.num_clusters) + 16);   // kSplit: [tiles][K][32]
   const unsigned table_bytes = unsigned(sizeof(DevNode<Real>)) * a.num_nodes + unsigned(sizeof(DevSphere<Real>)) * K +
                                256u * unsigned(sizeof(Real)) + unsigned(sizeof(DevConstraint<Real>)) * num_cons +
                                unsigned(sizeof(DevCluster<Real>)) * a.num_clusters;
@@ -1385,7 +1399,12 @@ __global__ void __launch_bounds__(kCostMaxThreads, STOMP_COST_MIN_BLOCKS) k_cost
     }
 
     // ---- FK + spheres + SDF + velocity + cost -------------------------------------------------------
-    for (int tile = warp; tile < ntiles; tile += nwarps) {
+    if (kSplit) {
+      for (int i = threadIdx.x; i < ntiles * K * 32; i += blockDim.x) contrib[i] = Real(0);
+      __syncthreads();
+    }
+    for (int tw = warp; tw < ntiles * S; tw += nwarps) {
+      const int tile = tw / S, sgroup = tw - tile * S;      // kSplit: this warp's share of the tile's sphere clusters
       // this lane's point of the concatenated timeline
       const int gp = tile * kTileSteps + lane;
       const int p = min(gp / seg, count - 1);                 // rollout within the pack (clamped: surplus lanes idle on the last one)
@@ -1460,6 +1479,7 @@ __global__ void __launch_bounds__(kCostMaxThreads, STOMP_COST_MIN_BLOCKS) k_cost
         const int sph_begin = nd.sphere_begin, sph_end = nd.sphere_end;
         if (sph_end > sph_begin) {
           for (int ci = nd.cluster_begin; ci < nd.cluster_end; ++ci) {
+          if (kSplit && (ci % S) != sgroup) continue;
           const DevCluster<Real>& cl = clusters[ci];
           if (kCull) {
             // broad phase: coarse lower bound of the distance at the cluster centre against the cluster's threshold
@@ -1516,7 +1536,11 @@ __global__ void __launch_bounds__(kCostMaxThreads, STOMP_COST_MIN_BLOCKS) k_cost
               const Real vy = c_m1 * shfl_rel(py, -1) + c_0 * py + c_p1 * shfl_rel(py, 1) + c_p2 * shfl_rel(py, 2);
               const Real vz = c_m1 * shfl_rel(pz, -1) + c_0 * pz + c_p1 * shfl_rel(pz, 1) + c_p2 * shfl_rel(pz, 2);
               vm = Math<Real>::sqrt_(vx * vx + vy * vy + vz * vz);
-              cost += lds1(sa + 6 * unsigned(sizeof(Real)), Real(0)) * (pot * vm);   // DevSphere::weight
+              // product and sum rounded separately (no FMA contraction): the split kernel parks the product in shared memory
+              // before it is added, and both kernels must produce the same bits; it is also how the reference's SSE2 build rounds
+              const Real contribution = Math<Real>::mul_rn(lds1(sa + 6 * unsigned(sizeof(Real)), Real(0)), pot * vm);   // DevSphere::weight
+              if (kSplit) contrib[(tile * K + j) * 32 + lane] = contribution;
+              else cost = Math<Real>::add_rn(cost, contribution);
             }
             if (kDebug) {
               if (t >= -1 && t <= N + 1 && (lane >= 1 && lane <= kTileSteps || (tile == 0 && lane == 0) ||
@@ -1533,13 +1557,28 @@ __global__ void __launch_bounds__(kCostMaxThreads, STOMP_COST_MIN_BLOCKS) k_cost
           }
         }
       }
-      if (productive) {
+      if (productive && !kSplit) {
         double* out = a.costs + size_t(b) * a.cost_problem_stride + size_t(r) * N;
         out[t] = kCons ? a.obstacle_weight * double(cost) + a.constraint_weight * double(ccost) : a.obstacle_weight * double(cost);
       }
       if (collided && a.collision_free) a.collision_free[size_t(b) * a.flag_problem_stride + a.flag_offset + r] = 0;
       if (kCons && violated && a.constraints_satisfied)
         a.constraints_satisfied[size_t(b) * a.flag_problem_stride + a.flag_offset + r] = 0;
+    }
+    if (kSplit) {      // the contributions of a timestep, added in sphere order (kCons is never split)
+      __syncthreads();
+      for (int tile = warp; tile < ntiles; tile += nwarps) {
+        const int gp = tile * kTileSteps + lane;
+        const int p = min(gp / seg, count - 1);
+        const int t = gp - (gp / seg) * seg - 1 + (gp / seg - p) * seg;
+        const int ro = first + p;
+        const int b = ro / a.n_rollouts, r = ro - b * a.n_rollouts;
+        if (gp / seg < count && lane >= 1 && lane <= kTileSteps && t >= 0 && t < N) {
+          Real cost = Real(0);
+          for (int j = 0; j < K; ++j) cost = Math<Real>::add_rn(cost, contrib[(tile * K + j) * 32 + lane]);
+          a.costs[size_t(b) * a.cost_problem_stride + size_t(r) * N + t] = a.obstacle_weight * double(cost);
+        }
+      }
     }
   }
 }

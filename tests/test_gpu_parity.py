@@ -767,6 +767,32 @@ def test_graph_replay_is_invisible(name, problems):
     assert np.abs(a.get(_abi.FIELD_NOISE)).max() > 0
 
 
+@pytest.mark.parametrize("name,problems,cumulative", [("C1", 1, 0), ("C1", 5, 1), ("tiny", 2, 0)])
+def test_split_cost_kernel_is_bit_identical(name, problems, cumulative, monkeypatch):
+    """Small batches evaluate the cost plugin with four warps per 29-timestep tile (each takes every fourth sphere cluster; the
+    per-sphere contributions are added in sphere order afterwards): state costs, flags and everything downstream are
+    bit-identical to the one-warp-per-tile kernel the large batches run."""
+    sc = scenes.make_scenario(name, num_problems=problems, use_cumulative_costs=cumulative)
+    a = _engine(sc, keep_intermediates=1)
+    monkeypatch.setenv("STOMP_NO_SPLIT_COST", "1")
+    b = _engine(sc, keep_intermediates=1)
+    monkeypatch.delenv("STOMP_NO_SPLIT_COST")
+    for it in range(1, 6):
+        ca, fa, _ = a.iterate(it)
+        cb, fb, _ = b.iterate(it)
+        np.testing.assert_array_equal(ca, cb)
+        np.testing.assert_array_equal(fa, fb)
+        for f in (_abi.FIELD_STATE_COSTS, _abi.FIELD_NOISELESS_COSTS, _abi.FIELD_COLLISION_FREE, _abi.FIELD_THETA,
+                  _abi.FIELD_CLIPPED_PARAMETERS):
+            np.testing.assert_array_equal(a.get(f), b.get(f))
+    ors = _oracles(sc)
+    params = _noisy_rollouts(sc, ors, np.random.default_rng(9), 3)
+    (c1, f1), (c2, f2) = a.execute(params, 1), b.execute(params, 1)
+    np.testing.assert_array_equal(c1, c2)
+    np.testing.assert_array_equal(f1, f2)
+    assert np.abs(c1).max() > 0
+
+
 def test_async_result_readback_pipeline():
     """request_results_async / wait_results: results of iteration i collected while iteration i+1 runs equal the
     synchronous read-back, with injected noise uploaded asynchronously as well (the bench's e2e loop)."""
