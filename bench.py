@@ -578,6 +578,8 @@ def run_engine(args):
                            "l2": "per-iteration working set %.2f GB of rollout arrays >> 126 MB L2 (no flush needed)"
                                  % (6 * B * R * D * N * 8 / 1e9),
                            "noise": "engine Philox RNG", "evals_per_step_per_gpu": evals_step,
+                           "evals_per_step_per_gpu_without_noiseless_rollout": B * rgen * N,
+                           "value_without_noiseless_rollout": world * B * rgen * N * K / (ms * 1e-3),
                            "iterations_per_sec": 1e3 * K / ms,
                            "problem_iterations_per_sec": world * B * 1e3 * K / ms,
                            "rollouts_per_sec": total_evals_step / N * 1e3 * K / ms},

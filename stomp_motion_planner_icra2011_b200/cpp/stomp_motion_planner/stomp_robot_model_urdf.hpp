@@ -10,6 +10,7 @@
 //   * generateLinkCollisionPoints / addCollisionPointsFromLinkRadius (:228-306): one sphere every radius / 2 from the link
 //     origin to each child's KDL JointOrigin() (zero for a fixed child joint), ceil(distance / spacing) + 1 points, the first
 //     point of every child after the first skipped; StompPlanningGroup::addCollisionPoint keeps the points a group joint moves
+//   * generateAttachedObjectCollisionPoints (:377-453): the bounding sphere of every attached shape as one more collision point
 //   * the links' <collision> primitives, for StompCollisionSpace::setStartState's voxelisation of the robot bodies outside
 //     the planning group (src/stomp_collision_space.cpp:167-188,567-588): bodiesAtState() places them at a joint state
 // Pinned by tests/test_urdf_cpp_cpu.py against stomp_motion_planner_icra2011_b200/urdf.py (which tests/test_urdf_cpu.py and
@@ -375,6 +376,38 @@ inline bool loadRobotModelFromUrdf(const std::string& urdf_xml, const std::vecto
     out.chain_tip_segment = out.segmentOfLink(chain_tip_link);
     if (out.chain_root_segment < 0 || out.chain_tip_segment < 0) { err = "dynamics chain link is not a link of the URDF"; return false; }
   }
+  return true;
+}
+
+// StompRobotModel::generateAttachedObjectCollisionPoints (src/stomp_robot_model.cpp:377-453): every shape attached to a link
+// becomes ONE collision point of that link = the bounding sphere of the padded shape (geometric_shapes'
+// bodies::computeBoundingSphere, restated: sphere r; box sqrt(sum (d/2 + pad)^2); cylinder sqrt((r + pad)^2 + (l/2 + pad)^2)),
+// centred at the shape's position in the link frame, with the default clearance.  Kept only if a group joint moves the link
+// (StompPlanningGroup::addCollisionPoint).  Returns false for an unknown link or shape type.
+inline bool addAttachedObjectCollisionPoint(StompRobotModelUrdf& m, const std::string& link, int body_type, const double dimensions[3],
+                                            const double position[3], double padding, double clearance) {
+  const int seg = m.segmentOfLink(link);
+  if (seg < 0) return false;
+  double radius;
+  if (body_type == STOMP_BODY_SPHERE) {
+    radius = dimensions[0] + padding;
+  } else if (body_type == STOMP_BODY_BOX) {
+    double sum = 0.0;
+    for (int k = 0; k < 3; ++k) sum += (dimensions[k] / 2.0 + padding) * (dimensions[k] / 2.0 + padding);
+    radius = std::sqrt(sum);
+  } else if (body_type == STOMP_BODY_CYLINDER) {
+    radius = std::sqrt((dimensions[0] + padding) * (dimensions[0] + padding) + (dimensions[1] / 2.0 + padding) * (dimensions[1] / 2.0 + padding));
+  } else {
+    return false;
+  }
+  bool moved = false;
+  for (int sg = seg; sg >= 0; sg = m.segments[sg].parent) moved = moved || m.segments[sg].group_index >= 0;
+  if (!moved) return true;
+  stomp_sphere sp;
+  std::memset(&sp, 0, sizeof(sp));
+  sp.segment = seg; sp.radius = radius; sp.clearance = clearance;
+  for (int k = 0; k < 3; ++k) sp.pos[k] = position[k];
+  m.collision_points.push_back(sp);
   return true;
 }
 

@@ -2,7 +2,8 @@
 // small spec file and compares the dumped tables with stomp_motion_planner_icra2011_b200/urdf.py.
 // usage: urdf_model_test robot.urdf spec.txt
 //   spec lines:  group j1 j2 ... | reference link | clearance c | collision link radius extension | state joint value |
-//                chain root tip | exclude link ... | start q1 q2 ... | padding scale pad
+//                chain root tip | exclude link ... | start q1 q2 ... | padding scale pad |
+//                attach link type d0 d1 d2 x y z padding
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -21,6 +22,8 @@ int main(int argc, char** argv) {
   std::map<std::string, double> state;
   std::vector<double> start;
   double clearance = 0.07, scale = 1.0, padding = 0.0;
+  struct Attach { std::string link; int type; double dims[3], pos[3], padding; };
+  std::vector<Attach> attach;
   std::ifstream sf(argv[2]);
   std::string line;
   while (std::getline(sf, line)) {
@@ -36,6 +39,7 @@ int main(int argc, char** argv) {
     else if (key == "exclude") while (is >> w) exclude.push_back(w);
     else if (key == "start") { double v; while (is >> v) start.push_back(v); }
     else if (key == "padding") is >> scale >> padding;
+    else if (key == "attach") { Attach at; is >> at.link >> at.type >> at.dims[0] >> at.dims[1] >> at.dims[2] >> at.pos[0] >> at.pos[1] >> at.pos[2] >> at.padding; attach.push_back(at); }
   }
   StompRobotModelUrdf m;
   std::string err;
@@ -43,6 +47,8 @@ int main(int argc, char** argv) {
     std::printf("error %s\n", err.c_str());
     return 1;
   }
+  for (const Attach& at : attach)
+    if (!addAttachedObjectCollisionPoint(m, at.link, at.type, at.dims, at.pos, at.padding, clearance)) { std::printf("error attach %s\n", at.link.c_str()); return 1; }
   std::printf("reference %d chain %d %d\n", m.reference_segment, m.chain_root_segment, m.chain_tip_segment);
   for (size_t s = 0; s < m.segments.size(); ++s) {
     const stomp_segment& g = m.segments[s];

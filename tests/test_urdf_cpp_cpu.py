@@ -122,6 +122,26 @@ def test_cpp_robot_bodies_at_the_start_state(tmp_path):
     assert len(want.segments) == 18
 
 
+def test_cpp_attached_object_collision_points(tmp_path):
+    """generateAttachedObjectCollisionPoints: one bounding-sphere collision point per attached shape, like scenes.Robot.add_attached_object
+    (pinned to the compiled reference by tests/test_reference_pinning.py); an object on a link no group joint moves adds nothing."""
+    want = robot_from_urdf(URDF, GROUP, "base_link", COLLISION_LINKS, 0.07, STATE)
+    seg = [g["name"] for g in want.segments].index("r_gripper_palm_link")
+    want.add_attached_object(seg, "box", (0.1, 0.06, 0.2), (0.12, 0.0, 0.01), padding=0.01, clearance=0.07)
+    want.add_attached_object(seg, "cylinder", (0.03, 0.25), (0.15, 0.02, 0.0), padding=0.0, clearance=0.07)
+    want.add_attached_object(seg, "sphere", (0.04,), (0.2, 0.0, 0.0), padding=0.005, clearance=0.07)
+    lines = _spec() + ["attach r_gripper_palm_link 1 0.1 0.06 0.2 0.12 0.0 0.01 0.01", "attach r_gripper_palm_link 2 0.03 0.25 0 0.15 0.02 0.0 0.0",
+                       "attach r_gripper_palm_link 0 0.04 0 0 0.2 0.0 0.0 0.005", "attach torso_lift_link 0 0.1 0 0 0 0 0 0"]
+    rc, rows = _run(tmp_path, URDF, lines)
+    assert rc == 0, rows
+    sph = [r for r in rows if r[0] == "sphere"]
+    assert len(sph) == len(want.spheres) == 50
+    for r, s_ in zip(sph[47:], want.spheres[47:]):
+        assert int(r[1]) == s_["segment"] and float(r[3]) == s_["clearance"]
+        np.testing.assert_allclose(float(r[2]), s_["radius"], rtol=1e-15)
+        np.testing.assert_array_equal([float(x) for x in r[4:7]], s_["pos"])
+
+
 def test_cpp_urdf_errors(tmp_path):
     rc, rows = _run(tmp_path, URDF.replace("</robot>", ""), _spec())
     assert rc == 1 and rows[0][0] == "error"
