@@ -68,7 +68,8 @@ struct Engine {
   int device = 0, num_sms = 148;
   cudaStream_t stream = nullptr, copy_stream = nullptr, tail_stream = nullptr;
   cudaStream_t ws = nullptr;   // stream the launch helpers currently enqueue on (stream or tail_stream)
-  cudaEvent_t ev_tail = nullptr, ev_upd = nullptr, ev_selected = nullptr;
+  cudaEvent_t ev_tail = nullptr, ev_upd = nullptr, ev_selected = nullptr, ev_cost = nullptr, ev_cum = nullptr;
+  bool cum_pending = false;        // ev_cum was recorded: the tail stream's k_cumulative still reads the control costs
   // asynchronous result read-back (two requests in flight)
   cudaStream_t result_stream = nullptr;
   cudaEvent_t ev_snap_main[2] = {nullptr, nullptr}, ev_snap_tail[2] = {nullptr, nullptr}, ev_results[2] = {nullptr, nullptr};
@@ -125,6 +126,24 @@ struct Engine {
   DevBuf<double> mma_a1, mma_a2;         // the same two, zero-padded to [Np][Np] (Np = N rounded up to 8): k_generate_mma's A operands
   bool dense_update = true;   // A/B switch (STOMP_NO_DENSE_UPDATE=1): k_update projects with the banded solves
   bool split_cost = true;     // A/B switch (STOMP_NO_SPLIT_COST=1): small batches take the one-warp-per-tile k_cost like large ones
+  // look-ahead generation: the next iteration's noise and M * noise are produced on pre_stream while this iteration runs
+  bool lookahead = true;      // A/B switch (STOMP_NO_LOOKAHEAD=1)
+  cudaStream_t pre_stream = nullptr;
+  cudaEvent_t ev_pre = nullptr, ev_fin = nullptr;
+  DevBuf<double> pre_noise, pre_y, pre_scale, gen_scratch3;
+  bool pre_valid = false, pre_dirty = false;
+  uint32_t pre_generation = 0;
+  int pre_iteration = 0, pre_num_gen = 0;
+  uint64_t pre_epoch = 0;
+  // candidate pass (small batches): every previous rollout prepared as a reused slot on cand_stream, then k_select_gather
+  cudaStream_t cand_stream = nullptr;
+  cudaEvent_t ev_cand = nullptr;
+  DevBuf<double> cand_noise, cand_control, cand_params, cand_y, gen_scratch4;
+  DevBuf<int> cand_map;
+  bool cand_valid = false, cand_dirty = false;
+  uint32_t cand_generation = 0;
+  uint64_t cand_epoch = 0;
+  bool direct_update = true;  // A/B switch (STOMP_NO_DIRECT_UPDATE=1): k_update always reads k_cumulative's output
   bool dmma_update = true;    // A/B switch (STOMP_NO_DMMA=1): the dense projection runs as scalar DFMAs instead of DMMA tiles
   int gen_mode = 0;   // 0: pick k_generate / k_generate_dense / k_generate_mma by batch shape; 1, 2, 3: always that one (A/B)
   DevBuf<double> limit_min, limit_max;
@@ -186,6 +205,15 @@ struct Engine {
   }
   // statistics over rollouts: one CTA per (problem, dims) looping over R (small R, many problems), or the
   // two-stage partial reductions over rollout chunks (rollout sharding, or one problem with many rollouts)
+  // k_update forms S + C itself and k_cumulative moves off the critical path: pays while the iteration is a chain of short
+  // launches (C1 0.071 -> 0.065 ms); with a machine-filling batch the concurrent k_cumulative slows k_update by more than
+  // the chain saves (C2 0.476 -> 0.512 ms)
+  bool direct_now() const { return direct_update && !desc.use_cumulative_costs && small_batch(); }
+  // Small batches run a latency schedule (direct k_update, look-ahead generation, candidate pass + k_select_gather): their
+  // iteration is a chain of short launches and the machine is mostly idle.  With a machine-filling batch the same work only
+  // competes for the SMs (C2: look-ahead 0.476 -> 0.577 ms), so the throughput schedule stays.
+  bool small_batch() const { return (long long)B * R * D * N <= small_max; }
+  long long small_max = 1 << 20;
   bool huge_path() const { return desc.rollout_shard_world > 1 || R > 4096 || (B == 1 && R >= 128); }
 };
 
@@ -219,10 +247,19 @@ int check_launch(Engine& e, const char* what) {
 // main stream waits for everything enqueued on the tail stream (device-side, no host sync)
 int join_streams(Engine& e) {
   e.ws = e.stream;
+  if (e.pre_dirty) {
+    CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_pre, 0));
+    e.pre_dirty = false;
+  }
+  if (e.cand_dirty) {
+    CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_cand, 0));
+    e.cand_dirty = false;
+  }
   if (!e.tail_dirty) return 0;
   CUDA_TRY(cudaEventRecord(e.ev_tail, e.tail_stream));
   CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_tail, 0));
   e.tail_dirty = false;
+  e.cum_pending = false;   // the late k_cumulative precedes ev_tail on the tail stream
   return 0;
 }
 
@@ -427,16 +464,21 @@ int launch_generate(Engine& e, GenArgs a) {
   if (nvec == 0) return 0;
   const unsigned grid = unsigned((nvec + tpb - 1) / tpb);
   const size_t stride = size_t(grid) * tpb;
-  DevBuf<double>& scratch = e.ws == e.tail_stream ? e.gen_scratch2 : e.gen_scratch;
+  DevBuf<double>& scratch = e.ws == e.tail_stream ? e.gen_scratch2
+                            : (e.ws == e.pre_stream ? e.gen_scratch3 : (e.ws == e.cand_stream ? e.gen_scratch4 : e.gen_scratch));
   if (scratch.n < stride * N) CUDA_TRY(scratch.alloc(stride * N));
   a.scratch = scratch.p;
   a.scratch_stride = stride;
   const size_t smem = (size_t(N) * 17 + size_t(tpb / 32) * 2 * 32 * kTileLd) * 8;
   if (smem > 220 * 1024) return fail("num_time_steps too large for the band tables of k_generate");
-  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  if (smem > 48 * 1024) {
+    CUDA_TRY(cudaFuncSetAttribute(k_generate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    CUDA_TRY(cudaFuncSetAttribute(k_generate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  }
   begin_launch(e);
-  k_generate<<<grid, tpb, smem, e.ws>>>(a);
-  return check_launch(e, "k_generate");
+  if (a.pre) k_generate<true><<<grid, tpb, smem, e.ws>>>(a);
+  else k_generate<false><<<grid, tpb, smem, e.ws>>>(a);
+  return check_launch(e, a.pre ? "k_generate_ahead" : "k_generate");
 }
 
 GenArgs base_gen_args(Engine& e) {
@@ -451,6 +493,7 @@ GenArgs base_gen_args(Engine& e) {
   a.noise_scale = e.noise_scale.p;
   a.eps_in = e.eps_in2[e.inject_pending_buf].p;
   a.params_prev = e.params[1 - e.cur].p;
+  a.prev_stride = e.R;
   a.reuse_src = e.reuse_src.p;
   a.noise = e.noise.p;
   a.params = e.params[e.cur].p;
@@ -661,6 +704,9 @@ int launch_update(Engine& e, int apply, bool fuse_extra_control) {
     a.st = e.stencil();
   }
   a.cumulative = e.cumulative.p; a.noise = e.noise.p; a.probabilities = e.probabilities.p;
+  // without the suffix sums a cumulative cost is just S + C[d]: k_update forms it itself (same addition, same bits) and does
+  // not depend on k_cumulative, which the two-stream schedule then takes off the critical path
+  if (e.direct_now()) { a.state = e.state[e.cur].p; a.cumulative = e.control.p; }
   a.updates = e.updates.p; a.theta = e.theta.p; a.band = e.band_view();
   // the projection as a dense product (kernels.cuh) while the N x N matrix is a few hundred KB of L2-resident reads per CTA
   a.dense_ms = (e.dense_update && e.N <= 512) ? e.dense_ms.p : nullptr;
@@ -768,7 +814,20 @@ int launch_select(Engine& e) {
 }
 
 // noise / parameters / projected noise / control costs of rollout slots [r_begin, r_begin + r_count)
-int launch_generate_range(Engine& e, const RolloutPlan& p, int r_begin, int r_count, bool with_control) {
+// which generation kernel a launch over r_count slots takes: 1 band solves, 2 dense (one CTA per vector), 3 DMMA
+int generate_kind(const Engine& e, int r_count) {
+  const double nvec = double(e.B) * r_count * e.D;
+  const double est_band = 0.95e-6 * e.N;
+  const double est_dense = 5.0e-6 + nvec * 12.0 * double(e.N) * e.N / 4.0e12;
+  int kind = e.gen_mode;
+  const bool mma_ok = mma_smem_bytes(e.N) <= 200 * 1024 && e.N <= 1024 && e.mma_a1.p != nullptr;
+  if (kind == 0) kind = (e.N <= 1024 && est_dense < 0.5 * est_band) ? 2 : 1;
+  if (kind == 3 && !mma_ok) kind = 1;
+  return kind;
+}
+
+int launch_generate_range(Engine& e, const RolloutPlan& p, int r_begin, int r_count, bool with_control, bool pre = false,
+                          bool candidates = false) {
   if (r_count <= 0) return 0;
   GenArgs a = base_gen_args(e);
   a.mode_generate = 1;
@@ -779,7 +838,29 @@ int launch_generate_range(Engine& e, const RolloutPlan& p, int r_begin, int r_co
   a.control_weight = 0.5 * e.control_cost_weight;
   a.r_begin = r_begin;
   a.r_count = r_count;
-  const bool uses_injection = p.injected && r_begin < e.num_gen;
+  if (pre) {
+    // look-ahead pass for the next iteration's new slots [0, r_count): compact outputs, the next Philox generation, no theta
+    a.pre = 1;
+    a.R = r_count; a.R_gen = r_count;
+    a.iteration = e.generation + 1;
+    a.theta = nullptr; a.params = nullptr; a.control = nullptr; a.params_prev = nullptr; a.reuse_src = nullptr; a.eps_in = nullptr;
+    a.noise = e.pre_noise.p; a.noise_projected = e.pre_y.p;
+    a.noise_scale = e.pre_scale.p;
+    a.iteration_ptr = nullptr;
+  }
+  if (candidates) {
+    // candidate pass for the NEXT iteration's reused slots: every rollout of the current iteration and the noise-less one
+    // (candidate R) treated as reused — noise = parameters - theta, M noise, control costs — into [B][R + 1][D][N] buffers
+    a.R = e.R + 1; a.R_gen = 0; a.r_begin = 0; a.r_count = e.R + 1;
+    a.params_prev = e.params[e.cur].p; a.prev_stride = e.R;
+    a.reuse_src = e.cand_map.p;
+    a.noise = e.cand_noise.p; a.params = e.cand_params.p; a.control = e.cand_control.p;
+    a.noise_projected = e.noise_projected.p ? e.cand_y.p : nullptr;
+    a.injected = 0;
+    a.iteration_ptr = nullptr;
+    r_begin = 0; r_count = e.R + 1;
+  }
+  const bool uses_injection = !candidates && p.injected && r_begin < e.num_gen;
   if (uses_injection && e.inject_pending_n < e.num_gen)
     return fail("injected noise holds " + std::to_string(e.inject_pending_n) + " rollouts per problem but this iteration generates " +
                 std::to_string(e.num_gen));
@@ -791,18 +872,14 @@ int launch_generate_range(Engine& e, const RolloutPlan& p, int r_begin, int r_co
   // 0.72 -> 2.44 ms, since every CTA streams 1.5 N^2 matrix elements from L2; a register-tiled variant sharing the matrices
   // between 32 vectors was bound by shared-memory operand bandwidth and lost everywhere: profiles/README.md)
   const double nvec = double(e.B) * r_count * e.D;
-  const double est_band = 0.95e-6 * e.N;
-  const double est_dense = 5.0e-6 + nvec * 12.0 * double(e.N) * e.N / 4.0e12;
-  int kind = e.gen_mode;
   // k_generate_mma — both linear maps as DMMA GEMMs over tiles of 16 vectors: large batches whose three shared tiles fit
   const size_t mma_smem = mma_smem_bytes(e.N);
-  const bool mma_ok = mma_smem <= 200 * 1024 && e.N <= 1024 && e.mma_a1.p != nullptr;
   // measured on B200 (profiles/README.md, round 2): the DMMA kernel loses to the band solves (k_generate per iteration, both
   // launches: C2 0.266 vs 0.158 ms, C5 0.66 vs 0.37 ms; new-slot launch under ncu 149 vs 107 us with the fp64 tensor path at
   // 35 % of its peak).  The dense formulation does 1.5 N^2 flops per vector where the band solves do ~20 N, and B200's fp64
   // tensor rate equals its DFMA rate, so it is only taken on request (STOMP_GENERATE=mma)
-  if (kind == 0) kind = (e.N <= 1024 && est_dense < 0.5 * est_band) ? 2 : 1;
-  if (kind == 3 && !mma_ok) kind = 1;
+  // (the candidate pass takes the kernel the reused slots themselves would: the same bits whichever schedule ran)
+  const int kind = generate_kind(e, candidates ? e.Rre : r_count);
   if (kind == 3) {
     if (mma_smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_generate_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, int(mma_smem)));
     begin_launch(e);
@@ -812,11 +889,117 @@ int launch_generate_range(Engine& e, const RolloutPlan& p, int r_begin, int r_co
     const size_t smem = (size_t(3) * e.N + 2 * kPad) * 8;
     begin_launch(e);
     k_generate_dense<<<unsigned(nvec), 128, smem, e.ws>>>(a, e.dense_cinv.p, e.dense_ms.p);
-    if (check_launch(e, "k_generate")) return 1;
+    if (check_launch(e, pre ? "k_generate_ahead" : "k_generate")) return 1;
   } else if (launch_generate(e, a)) {
     return 1;
   }
   if (uses_injection) CUDA_TRY(cudaEventRecord(e.ev_consumed[e.inject_pending_buf], e.ws));
+  return 0;
+}
+
+// candidate pass for the next iteration's reused slots, on cand_stream after this iteration's update (ev_upd)
+bool candidates_possible(const Engine& e) {
+  return e.lookahead && e.small_batch() && e.direct_now() && e.overlap && !e.capturing && !e.huge_path() && e.Rre > 0 &&
+         e.reused_next && e.R <= 64 && e.desc.rollout_shard_world == 1 && generate_kind(e, e.Rre) != 3;
+}
+
+int launch_candidates(Engine& e) {
+  const size_t n = size_t(e.B) * (e.R + 1) * e.D * e.N;
+  if (e.cand_noise.n < n) {
+    CUDA_TRY(cudaStreamSynchronize(e.cand_stream));
+    CUDA_TRY(e.cand_noise.alloc(n));
+    CUDA_TRY(e.cand_control.alloc(n));
+    CUDA_TRY(e.cand_params.alloc(n));
+    if (e.noise_projected.p) CUDA_TRY(e.cand_y.alloc(n));
+    std::vector<int> map(size_t(e.B) * (e.R + 1));
+    for (int b = 0; b < e.B; ++b)
+      for (int r = 0; r <= e.R; ++r) map[size_t(b) * (e.R + 1) + r] = r < e.R ? r : -1;
+    CUDA_TRY(e.cand_map.alloc(map.size()));
+    CUDA_TRY(cudaMemcpy(e.cand_map.p, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  CUDA_TRY(cudaStreamWaitEvent(e.cand_stream, e.ev_upd, 0));
+  RolloutPlan np;
+  e.ws = e.cand_stream;
+  const int rc = launch_generate_range(e, np, 0, e.R + 1, true, false, true);
+  e.ws = e.stream;
+  if (rc) return 1;
+  CUDA_TRY(cudaEventRecord(e.ev_cand, e.cand_stream));
+  e.cand_valid = true;
+  e.cand_dirty = true;
+  e.cand_generation = e.generation;
+  e.cand_epoch = e.config_epoch;
+  return 0;
+}
+
+int launch_select_gather(Engine& e) {
+  SelectGatherArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.R = e.R; a.R_reuse = e.Rre; a.D = e.D; a.N = e.N; a.use_extra = e.extra_added ? 1 : 0;
+  a.totals = e.totals.p; a.reuse_src = e.reuse_src.p;
+  a.cand_noise = e.cand_noise.p; a.cand_control = e.cand_control.p; a.cand_y = e.noise_projected.p ? e.cand_y.p : nullptr;
+  a.params_prev = e.params[1 - e.cur].p; a.theta = e.theta.p;
+  a.state_prev = e.state[1 - e.cur].p; a.extra_state = e.extra_state.p;
+  a.noise = e.noise.p; a.control = e.control.p; a.params = e.params[e.cur].p; a.noise_projected = e.noise_projected.p;
+  a.state = e.state[e.cur].p;
+  begin_launch(e);
+  k_select_gather<<<unsigned(e.B) * e.Rre, 128, 0, e.ws>>>(a);
+  if (check_launch(e, "k_select_gather")) return 1;
+  e.extra_added = false;
+  return 0;
+}
+
+// second half of the pipelined generation (k_finish_rollouts): parameters, noise, control costs of the new slots from the
+// look-ahead buffers and the updated theta
+int launch_finish_rollouts(Engine& e) {
+  FinishArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.B = e.B; a.R = e.R; a.G = e.num_gen; a.D = e.D; a.N = e.N;
+  a.theta = e.theta.p; a.pre_noise = e.pre_noise.p; a.pre_y = e.pre_y.p;
+  a.pad_start = e.pad_start.p; a.pad_goal = e.pad_goal.p;
+  a.noise = e.noise.p; a.params = e.params[e.cur].p; a.control = e.control.p; a.noise_projected = e.noise_projected.p;
+  a.control_weight = 0.5 * e.control_cost_weight;
+  a.st = e.stencil();
+  const long long total = (long long)e.B * e.num_gen * e.D * e.N;
+  begin_launch(e);
+  k_finish_rollouts<<<unsigned((total + 255) / 256), 256, 0, e.ws>>>(a);
+  return check_launch(e, "k_finish_rollouts");
+}
+
+// May the noise of iteration `next_iteration` be generated now, before the current iteration's update?  Only what cannot
+// change in between is assumed: engine noise (not injected), the steady-state slot layout, the band / dense kernels.
+bool lookahead_possible(const Engine& e, const RolloutPlan& p) {
+  return e.lookahead && e.small_batch() && e.overlap && !e.capturing && !e.huge_path() && !p.injected &&
+         e.desc.rollout_shard_world == 1 && (e.reused_next || e.Rre == 0) && e.R - e.Rre > 0 &&
+         generate_kind(e, e.R - e.Rre) != 3;
+}
+
+// enqueue the look-ahead pass of iteration next_iteration on pre_stream; it starts once k_finish_rollouts / k_generate of the
+// current iteration (ev_fin) no longer read the look-ahead buffers
+int launch_lookahead(Engine& e, int next_iteration) {
+  const int G = e.R - e.Rre;
+  const size_t n = size_t(e.B) * G * e.D * e.N;
+  if (e.pre_noise.n < n) {
+    CUDA_TRY(cudaStreamSynchronize(e.pre_stream));
+    CUDA_TRY(e.pre_noise.alloc(n));
+    CUDA_TRY(e.pre_y.alloc(n));
+  }
+  if (e.pre_scale.n < size_t(e.D)) CUDA_TRY(e.pre_scale.alloc(size_t(e.D)));
+  std::vector<double> scale(e.D);
+  for (int d = 0; d < e.D; ++d) scale[d] = e.noise_stddev[d] * std::pow(e.noise_decay[d], next_iteration - 1);
+  CUDA_TRY(cudaStreamWaitEvent(e.pre_stream, e.ev_fin, 0));
+  CUDA_TRY(cudaMemcpyAsync(e.pre_scale.p, scale.data(), size_t(e.D) * 8, cudaMemcpyHostToDevice, e.pre_stream));
+  RolloutPlan np;
+  e.ws = e.pre_stream;
+  const int rc = launch_generate_range(e, np, 0, G, true, true);
+  e.ws = e.stream;
+  if (rc) return 1;
+  CUDA_TRY(cudaEventRecord(e.ev_pre, e.pre_stream));
+  e.pre_valid = true;
+  e.pre_dirty = true;
+  e.pre_generation = e.generation + 1;
+  e.pre_iteration = next_iteration;
+  e.pre_num_gen = G;
+  e.pre_epoch = e.config_epoch;
   return 0;
 }
 
@@ -934,15 +1117,27 @@ int iterate_once(Engine& e, int iteration_number) {
   e.control_cost_weight = e.desc.smoothness_cost_weight;
   RolloutPlan p;
   plan_rollouts(e, p);
-  if (p.reuse) {
+  // k_update reads S and C itself (launch_update): k_cumulative leaves the main stream's chain
+  const bool late_cumulative = !e.huge_path() && e.direct_now();
+  const bool use_cand = p.reuse && late_cumulative && e.cand_valid && !e.capturing && e.cand_generation + 1 == e.generation &&
+                        e.cand_epoch == e.config_epoch;
+  e.cand_valid = false;
+  if (use_cand) {
+    // the reused slots were prepared by the candidate pass: rank and copy
     e.ws = e.tail_stream;
+    CUDA_TRY(cudaStreamWaitEvent(e.tail_stream, e.ev_cand, 0));
+    e.cand_dirty = false;
+    if (launch_select_gather(e)) { e.ws = e.stream; return 1; }
+  } else if (p.reuse) {
+    e.ws = e.tail_stream;
+    if (e.cand_dirty) { CUDA_TRY(cudaStreamWaitEvent(e.tail_stream, e.ev_cand, 0)); e.cand_dirty = false; }   // a discarded pass
     if (launch_select(e)) { e.ws = e.stream; return 1; }
     // k_select_reuse ranks the PREVIOUS iteration's Rollout::getCost() values; this iteration's k_cumulative on the main
     // stream overwrites the new slots' entries of that array and must not overtake it.  (It never did while the main
     // stream's path to it was ~330 us long, but nothing ordered the two: found when an experiment shortened that path.)
     CUDA_TRY(cudaEventRecord(e.ev_selected, e.tail_stream));
     if (launch_generate_range(e, p, e.num_gen, e.R - e.num_gen, true) || gather_reused_state(e) ||
-        launch_cumulative(e, e.num_gen, e.R - e.num_gen)) {
+        (!late_cumulative && launch_cumulative(e, e.num_gen, e.R - e.num_gen))) {
       e.ws = e.stream;
       return 1;
     }
@@ -950,17 +1145,47 @@ int iterate_once(Engine& e, int iteration_number) {
   CUDA_TRY(cudaEventRecord(e.ev_tail, e.tail_stream));   // also covers the previous iteration's noise-less rollout
   if (e.chain_probe && p.reuse) CUDA_TRY(cudaEventRecord(e.probe_tail, e.tail_stream));
   e.ws = e.stream;
-  if (launch_generate_range(e, p, 0, e.num_gen, true)) return 1;
+  // the previous iteration's late k_cumulative (tail stream) reads the control costs this k_generate overwrites
+  if (e.cum_pending) { CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_cum, 0)); e.cum_pending = false; }
+  // new rollouts: finish what the look-ahead pass prepared during the previous iteration, or generate them in one pass
+  const bool use_pre = e.pre_valid && !p.injected && !e.capturing && e.pre_generation == e.generation &&
+                       e.pre_iteration == iteration_number && e.pre_num_gen == e.num_gen && e.pre_epoch == e.config_epoch;
+  e.pre_valid = false;
+  if (use_pre) {
+    CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_pre, 0));
+    e.pre_dirty = false;
+    if (launch_finish_rollouts(e)) return 1;
+  } else {
+    if (e.pre_dirty) { CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_pre, 0)); e.pre_dirty = false; }   // a discarded pass
+    if (launch_generate_range(e, p, 0, e.num_gen, true)) return 1;
+  }
+  const bool ahead = lookahead_possible(e, p);
+  if (ahead) CUDA_TRY(cudaEventRecord(e.ev_fin, e.stream));
   if (launch_cost(e, e.params[e.cur].p, size_t(e.R) * e.D * e.N, e.num_gen, e.B, iteration_number == 1, e.state[e.cur].p,
                   size_t(e.R) * e.N, e.collision_free.p, e.R + 1, 0, e.clipped.p, nullptr, e.constraints_ok.p))
     return 1;
-  if (p.reuse) CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_selected, 0));
-  if (launch_cumulative(e, 0, e.num_gen)) return 1;       // new slots; the reused slots' were done on the tail stream
+  if (ahead && launch_lookahead(e, iteration_number + 1)) return 1;
+  if (late_cumulative) {
+    CUDA_TRY(cudaEventRecord(e.ev_cost, e.stream));
+  } else {
+    if (p.reuse) CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_selected, 0));
+    if (launch_cumulative(e, 0, e.num_gen)) return 1;       // new slots; the reused slots' were done on the tail stream
+  }
   if (e.chain_probe && p.reuse) CUDA_TRY(cudaEventRecord(e.probe_main, e.stream));
   CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_tail, 0));
   const bool huge = e.huge_path();
   if (huge ? (launch_shard_stats(e, true, false, false, 0) || launch_shard_stats(e, false, false, true, 1)) : launch_update(e, 1, true)) return 1;
   CUDA_TRY(cudaEventRecord(e.ev_upd, e.stream));
+  if (late_cumulative && candidates_possible(e) && launch_candidates(e)) return 1;
+  if (late_cumulative) {
+    // Rollout::getCost() of every slot for the next reuse selection (and the cumulative-cost tap), beside k_update
+    e.ws = e.tail_stream;
+    CUDA_TRY(cudaStreamWaitEvent(e.tail_stream, e.ev_cost, 0));
+    if (launch_cumulative(e)) { e.ws = e.stream; return 1; }
+    CUDA_TRY(cudaEventRecord(e.ev_cum, e.tail_stream));
+    e.cum_pending = true;
+    e.ws = e.stream;
+  }
   if (e.chain_probe && p.reuse && (iteration_number % 16) == 0) {      // sampled: the read-back synchronises
     CUDA_TRY(cudaEventRecord(e.probe_upd, e.stream));
     CUDA_TRY(cudaEventSynchronize(e.probe_upd));
@@ -1017,6 +1242,7 @@ int capture_iterations(Engine& e) {
   e.cur = cur0; e.num_gen = num_gen0; e.generation = gen0; e.extra_added = extra0; e.reused_next = reused0;
   e.launches = launches0; e.steady_iterations = steady0;
   e.tail_dirty = false;
+  e.cum_pending = false;
   e.ws = e.stream;
   if (rc || ce != cudaSuccess || !graph) {
     (void)cudaGetLastError();
@@ -1226,7 +1452,14 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   // equal priorities: with the tail stream at the greatest priority the timeline looks better under event recording
   // (k_extra_total no longer waits 157 us for a CTA slot) but the unrecorded loop is slower, 0.522 vs 0.510 ms (profiles/README.md)
   if ((c = cudaStreamCreateWithFlags(&e.tail_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
-  if ((c = cudaEventCreateWithFlags(&e.ev_tail, cudaEventDisableTiming)) != cudaSuccess ||
+  if ((c = cudaStreamCreateWithFlags(&e.pre_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
+  if ((c = cudaStreamCreateWithFlags(&e.cand_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
+  if ((c = cudaEventCreateWithFlags(&e.ev_cand, cudaEventDisableTiming)) != cudaSuccess) return bail(c, "cudaEventCreate");
+  if ((c = cudaEventCreateWithFlags(&e.ev_pre, cudaEventDisableTiming)) != cudaSuccess ||
+      (c = cudaEventCreateWithFlags(&e.ev_fin, cudaEventDisableTiming)) != cudaSuccess ||
+      (c = cudaEventCreateWithFlags(&e.ev_cost, cudaEventDisableTiming)) != cudaSuccess ||
+      (c = cudaEventCreateWithFlags(&e.ev_cum, cudaEventDisableTiming)) != cudaSuccess ||
+      (c = cudaEventCreateWithFlags(&e.ev_tail, cudaEventDisableTiming)) != cudaSuccess ||
       (c = cudaEventCreateWithFlags(&e.ev_upd, cudaEventDisableTiming)) != cudaSuccess ||
       (c = cudaEventCreateWithFlags(&e.ev_selected, cudaEventDisableTiming)) != cudaSuccess)
     return bail(c, "cudaEventCreate");
@@ -1324,6 +1557,9 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
     e.chain_probe = false;
   e.dense_update = !(getenv("STOMP_NO_DENSE_UPDATE") && atoi(getenv("STOMP_NO_DENSE_UPDATE")) != 0);
   e.dmma_update = !(getenv("STOMP_NO_DMMA") && atoi(getenv("STOMP_NO_DMMA")) != 0);
+  e.direct_update = !(getenv("STOMP_NO_DIRECT_UPDATE") && atoi(getenv("STOMP_NO_DIRECT_UPDATE")) != 0);
+  e.lookahead = !(getenv("STOMP_NO_LOOKAHEAD") && atoi(getenv("STOMP_NO_LOOKAHEAD")) != 0);
+  if (const char* dm = getenv("STOMP_SMALL_BATCH_MAX")) e.small_max = atoll(dm);   // elements B R D N; 0: throughput schedule always
   e.split_cost = !(getenv("STOMP_NO_SPLIT_COST") && atoi(getenv("STOMP_NO_SPLIT_COST")) != 0);
   e.noise_stddev.assign(e.D, 1.0);
   e.noise_decay.assign(e.D, 1.0);
@@ -1347,6 +1583,11 @@ int stomp_engine_destroy(void* h) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
   if (e->tail_stream) { cudaStreamSynchronize(e->tail_stream); cudaStreamDestroy(e->tail_stream); }
+  if (e->pre_stream) { cudaStreamSynchronize(e->pre_stream); cudaStreamDestroy(e->pre_stream); }
+  if (e->cand_stream) { cudaStreamSynchronize(e->cand_stream); cudaStreamDestroy(e->cand_stream); }
+  if (e->ev_cand) cudaEventDestroy(e->ev_cand);
+  if (e->ev_pre) cudaEventDestroy(e->ev_pre);
+  if (e->ev_fin) cudaEventDestroy(e->ev_fin);
   if (e->result_stream) { cudaStreamSynchronize(e->result_stream); cudaStreamDestroy(e->result_stream); }
   for (int i = 0; i < 2; ++i) {
     if (e->ev_snap_main[i]) cudaEventDestroy(e->ev_snap_main[i]);
@@ -1356,6 +1597,8 @@ int stomp_engine_destroy(void* h) {
   for (int i = 0; i < 2; ++i)
     if (e->graph_exec[i]) cudaGraphExecDestroy(e->graph_exec[i]);
   if (e->ev_tail) cudaEventDestroy(e->ev_tail);
+  if (e->ev_cost) cudaEventDestroy(e->ev_cost);
+  if (e->ev_cum) cudaEventDestroy(e->ev_cum);
   if (e->peers_open)
     for (int r = 0; r < e->desc.rollout_shard_world; ++r)
       if (r != e->desc.rollout_shard_rank && e->peer_base[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
@@ -1682,6 +1925,7 @@ int stomp_engine_set_noise(void* h, const double* noise_stddev, const double* no
   if (!noise_stddev || !noise_decay) return fail("null argument");
   e.noise_stddev.assign(noise_stddev, noise_stddev + e.D);
   e.noise_decay.assign(noise_decay, noise_decay + e.D);
+  e.pre_valid = false;   // a look-ahead pass used the old scales
   return 0;
 }
 
@@ -1701,6 +1945,8 @@ int stomp_engine_set_problems(void* h, const double* start, const double* goal) 
   e.extra_added = false;
   e.num_gen = 0;
   e.generation = 0;
+  e.pre_valid = false;
+  e.cand_valid = false;
   e.cur = 0;
   e.injected_pending = false;
   e.have_problems = true;
@@ -1713,6 +1959,7 @@ int stomp_engine_set_parameters(void* h, const double* theta) {
   if (!theta) return fail("null argument");
   if (upload(e, e.theta, theta, size_t(e.B) * e.D * e.N)) return 1;
   CUDA_TRY(cudaStreamSynchronize(e.stream));
+  e.cand_valid = false;   // the candidate pass subtracted the old theta
   return 0;
 }
 
@@ -1733,6 +1980,7 @@ int stomp_engine_update_parameters(void* h, const double* updates) {
   k_axpy<<<unsigned((n + 255) / 256), 256, 0, e.ws>>>(n, e.updates.p, e.theta.p);
   if (check_launch(e, "k_axpy")) return 1;
   CUDA_TRY(cudaStreamSynchronize(e.stream));
+  e.cand_valid = false;
   return 0;
 }
 
@@ -1939,6 +2187,8 @@ int stomp_engine_optimize(void* h, int32_t max_iterations, int32_t max_after_cf,
   e.extra_added = false;
   e.injected_pending = false;
   e.num_gen = 0;
+  e.pre_valid = false;
+  e.cand_valid = false;
   std::vector<TrackState> init(e.B, TrackState{0, -1, -1, -1, 0, 0});
   if (upload(e, e.track_state, reinterpret_cast<const unsigned char*>(init.data()), init.size() * sizeof(TrackState))) return 1;
   CUDA_TRY(cudaMemsetAsync(e.num_done.p, 0, sizeof(int), e.stream));

@@ -198,6 +198,63 @@ __global__ void k_select_reuse(const double* __restrict__ totals, int R, int R_r
   }
 }
 
+// k_select_gather (small batches): the reuse selection of k_select_reuse and, in the same launch, the reused slots filled from
+// the candidate pass — k_generate ran over ALL previous rollouts (+ the noise-less one) as if each were reused while the
+// noise-less rollout was still being costed, so nothing but this copy is left between that cost and the update.
+// Grid (B, R_reuse): CTA (b, j) finds the candidate of rank j and copies its noise / M noise / control costs / parameters /
+// state costs into slot R_gen + j.
+struct SelectGatherArgs {
+  int R, R_reuse, D, N, use_extra;
+  const double* totals;        // [B][R + 1]
+  int* reuse_src;              // [B][R_reuse]
+  const double* cand_noise;    // [B][R + 1][D][N]   candidate R = the noise-less rollout
+  const double* cand_control;  // [B][R + 1][D][N]
+  const double* cand_y;        // [B][R + 1][D][N] or nullptr
+  const double* params_prev;   // [B][R][D][N]
+  const double* theta;         // [B][D][N]
+  const double* state_prev;    // [B][R][N]
+  const double* extra_state;   // [B][N]
+  double* noise;               // [B][R][D][N]
+  double* control;
+  double* params;
+  double* noise_projected;     // optional tap
+  double* state;               // [B][R][N]
+};
+
+__global__ void __launch_bounds__(128) k_select_gather(SelectGatherArgs a) {
+  __shared__ int s_src;
+  const int R = a.R, b = blockIdx.x / a.R_reuse, j = blockIdx.x - b * a.R_reuse;
+  const double* tot = a.totals + size_t(b) * (R + 1);
+  const int n = R + (a.use_extra ? 1 : 0);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {     // the ranking of k_select_reuse
+    const double ci = tot[i];
+    const int ii = (i == R) ? -1 : i;
+    int rank = 0;
+    for (int k = 0; k < n; ++k) {
+      const double ck = tot[k];
+      const int kk = (k == R) ? -1 : k;
+      rank += (ck < ci) || (ck == ci && kk < ii);
+    }
+    if (rank == j) s_src = ii;
+  }
+  __syncthreads();
+  const int src = s_src;
+  if (threadIdx.x == 0) a.reuse_src[size_t(b) * a.R_reuse + j] = src;
+  const int DN = a.D * a.N, slot = R - a.R_reuse + j;
+  const size_t cand = (size_t(b) * (R + 1) + (src >= 0 ? src : R)) * DN;
+  const size_t dst = (size_t(b) * R + slot) * DN;
+  const double* psrc = src >= 0 ? a.params_prev + (size_t(b) * R + src) * DN : a.theta + size_t(b) * DN;
+  for (int k = threadIdx.x; k < DN; k += blockDim.x) {
+    a.noise[dst + k] = a.cand_noise[cand + k];
+    a.control[dst + k] = a.cand_control[cand + k];
+    a.params[dst + k] = psrc[k];
+    if (a.noise_projected) a.noise_projected[dst + k] = a.cand_y[cand + k];
+  }
+  const double* ssrc = src >= 0 ? a.state_prev + (size_t(b) * R + src) * a.N : a.extra_state + size_t(b) * a.N;
+  double* sdst = a.state + (size_t(b) * R + slot) * a.N;
+  for (int t = threadIdx.x; t < a.N; t += blockDim.x) sdst[t] = ssrc[t];
+}
+
 // k_advance_iteration (CUDA-graph replay of stomp_engine_run): what the host does between two iterations, on the device —
 // the Philox generation counter advances and the noise scales sigma_d decay_d^(it-1) of the next iteration are taken from a
 // table the host computed for the whole run (so they are bit-identical to the values the per-iteration upload would carry).
@@ -221,6 +278,9 @@ struct GenArgs {
   int mode_control;          // 1: compute control costs
   int injected;              // 1: noise for new rollouts comes from eps_in
   int extra;                 // 1: vectors are (b, d) of the extra rollout: params = theta, noise = 0
+  int pre;                   // 1: look-ahead pass for the NEXT iteration's new rollouts: only what does not depend on theta —
+                             // noise (Philox) and noise_projected = M * noise — is produced, into compact [B][r_count][D][N]
+                             // buffers (R = r_count here); k_finish_rollouts adds theta and the control costs later
   double control_weight;     // 0.5 * control_cost_weight
   uint64_t seed;
   uint32_t iteration;
@@ -232,7 +292,8 @@ struct GenArgs {
   const double* pad_goal;    // [B][D]
   const double* noise_scale; // [D] sigma_d * decay_d^(it-1)
   const double* eps_in;      // [B][R][D][N] injected noise (or caller noise when !mode_project)
-  const double* params_prev; // [B][R][D][N] previous-iteration parameters (reuse gather)
+  const double* params_prev; // [B][prev_stride][D][N] previous-iteration parameters (reuse gather)
+  int prev_stride;           // rollouts per problem in params_prev (= R except in the candidate pass, where R counts candidates)
   const int* reuse_src;      // [B][R_reuse]
   double* noise;             // [B][R][D][N]
   double* params;            // [B][R][D][N]  (extra: unused)
@@ -285,6 +346,23 @@ __device__ __forceinline__ void band_backward(double* x, const double* bw, int N
     x[i] = s;
     w6 = w5; w5 = w4; w4 = w3; w3 = w2; w2 = w1; w1 = s;
   }
+}
+
+// Control cost of one padded row from its seven taps w[j] = x_all[p - 3 + j] (dropped taps = 0):
+// sum_k 0.5 w_control w_k (sum_j rule_k[j] x_all[p - 3 + j])^2   (covariant_trajectory_policy.cpp:228-255).
+// One definition with explicit fused multiply-adds, shared by the generation kernels and k_finish_rollouts: whichever of them
+// produced a rollout's control costs, the bits are the same.
+__device__ __forceinline__ double stencil_row_cost(const Stencil& st, double control_weight, const double* w) {
+  double cost = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (st.weight[k] == 0.0) continue;
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) acc = fma(st.coef[k][j], w[j], acc);
+    cost = fma(control_weight * st.weight[k], acc * acc, cost);
+  }
+  return cost;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -378,6 +456,7 @@ struct BandWindow {
   }
 };
 
+template <bool kPre>
 __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs a) {
   extern __shared__ double smem[];
   const int N = a.N;
@@ -404,7 +483,7 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
     r += a.extra ? 0 : a.r_begin;
   }
   const size_t row_off = a.extra ? (size_t(b) * a.D + d) * N : ((size_t(b) * a.R + r) * a.D + d) * N;
-  const double* th_row = active ? a.theta + (size_t(b) * a.D + d) * N : nullptr;
+  const double* th_row = (active && !kPre) ? a.theta + (size_t(b) * a.D + d) * N : nullptr;
   double* wb = a.scratch + v;                 // time-major scratch: element i at wb[i * sstride]
   const size_t sstride = a.scratch_stride;
   const int last_c0 = ((N - 1) / kChunk) * kChunk;
@@ -419,7 +498,7 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
     if (active) {
       if (!is_new) {
         int sidx = a.reuse_src[size_t(b) * (a.R - a.R_gen) + (r - a.R_gen)];
-        src = sidx >= 0 ? a.params_prev + ((size_t(b) * a.R + sidx) * a.D + d) * N : th_row;
+        src = sidx >= 0 ? a.params_prev + ((size_t(b) * a.prev_stride + sidx) * a.D + d) * N : th_row;
       } else if (a.injected) {
         src = a.eps_in + row_off;
       }
@@ -466,7 +545,7 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
         }
       }
       warp_tile_store(tE, out_noise, c0, len, lane);
-      warp_tile_store(tT, out_params, c0, len, lane);
+      if (!kPre) warp_tile_store(tT, out_params, c0, len, lane);
     }
   }
   if (!a.mode_control) return;
@@ -491,12 +570,12 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
       }
     }
     {
-      const double* prow = active ? a.params + row_off : nullptr;
+      const double* prow = (active && !kPre) ? a.params + row_off : nullptr;
       double* ytap = (active && a.noise_projected) ? a.noise_projected + row_off : nullptr;
       BandWindow bwd;
       for (int c0 = last_c0; c0 >= 0; c0 -= kChunk) {
         const int len = min(kChunk, N - c0);
-        warp_tile_load(tT, prow, c0, len, lane);
+        if (!kPre) warp_tile_load(tT, prow, c0, len, lane);
         if (active) {
           double* wp = wb + size_t(c0) * sstride;
           double wv[kChunk];
@@ -509,16 +588,19 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
             if (k < len) {
               const double y = bwd.step(sbw + (c0 + k) * 8, wv[k]);
               my_tE[k] = y;
-              wv[k] = my_tT[k] + y;
+              if (!kPre) wv[k] = my_tT[k] + y;
             }
           }
+          if (!kPre) {
 #pragma unroll
-          for (int k = 0; k < kChunk; ++k)
-            if (k < len) wp[size_t(k) * sstride] = wv[k];
+            for (int k = 0; k < kChunk; ++k)
+              if (k < len) wp[size_t(k) * sstride] = wv[k];
+          }
         }
         if (a.noise_projected) warp_tile_store(tE, ytap, c0, len, lane);
       }
     }
+    if (kPre) return;
   } else {
     // no projection: x = theta (extra rollout) or x = parameters + caller noise (Policy::computeControlCosts)
     const double* prow = active ? (a.extra ? th_row : a.params + row_off) : nullptr;
@@ -544,18 +626,7 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
       if (idx < 0 || idx >= Nall) return 0.0;   // dropped taps of the differentiation matrices
       return idx < kPad ? xs : (idx >= kPad + N ? xg : wb[size_t(idx - kPad) * sstride]);
     };
-    auto stencil_cost = [&](const double* w) -> double {
-      double cost = 0.0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (a.st.weight[k] == 0.0) continue;
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < 7; ++j) acc += a.st.coef[k][j] * w[j];
-        cost += a.control_weight * a.st.weight[k] * (acc * acc);
-      }
-      return cost;
-    };
+    auto stencil_cost = [&](const double* w) -> double { return stencil_row_cost(a.st, a.control_weight, w); };
     double hc[kPad], tc[kPad], w[7];
     if (active) {
       // the six trailing padded rows only see the last three free values and the goal padding
@@ -643,7 +714,7 @@ __global__ void __launch_bounds__(128) k_generate_dense(GenArgs a, const double*
   const double* src = nullptr;
   if (!is_new) {
     const int sidx = a.reuse_src[size_t(b) * (a.R - a.R_gen) + (r - a.R_gen)];
-    src = sidx >= 0 ? a.params_prev + ((size_t(b) * a.R + sidx) * a.D + d) * N : th;
+    src = sidx >= 0 ? a.params_prev + ((size_t(b) * a.prev_stride + sidx) * a.D + d) * N : th;
   }
   if (philox) {
     const uint64_t stream = (uint64_t(b) * uint64_t(a.rollouts_global) + uint64_t(a.rollout_id_offset + r)) * uint64_t(a.D) + d;
@@ -674,8 +745,19 @@ __global__ void __launch_bounds__(128) k_generate_dense(GenArgs a, const double*
   __syncthreads();
   for (int t = threadIdx.x; t < N; t += blockDim.x) {
     const double ev = e[t];
-    const double pv = is_new ? th[t] + ev : src[t];
     a.noise[row_off + t] = ev;
+    if (a.pre) {            // look-ahead pass: M * noise only (theta is not known yet)
+      double a0 = 0.0, a1 = 0.0;
+      int j = 0;
+      for (; j + 1 < N; j += 2) {
+        a0 = fma(ms[size_t(j) * N + t], e[j], a0);
+        a1 = fma(ms[size_t(j + 1) * N + t], e[j + 1], a1);
+      }
+      if (j < N) a0 = fma(ms[size_t(j) * N + t], e[j], a0);
+      a.noise_projected[row_off + t] = a0 + a1;
+      continue;
+    }
+    const double pv = is_new ? th[t] + ev : src[t];
     a.params[row_off + t] = pv;
     if (!a.mode_control) continue;
     double a0 = 0.0, a1 = 0.0;
@@ -689,6 +771,7 @@ __global__ void __launch_bounds__(128) k_generate_dense(GenArgs a, const double*
     if (a.noise_projected) a.noise_projected[row_off + t] = y;
     xs[kPad + t] = pv + y;
   }
+  if (a.pre) return;
   for (int q = threadIdx.x; q < kPad; q += blockDim.x) {
     xs[q] = a.pad_start[size_t(b) * a.D + d];
     xs[kPad + N + q] = a.pad_goal[size_t(b) * a.D + d];
@@ -696,19 +779,13 @@ __global__ void __launch_bounds__(128) k_generate_dense(GenArgs a, const double*
   if (!a.mode_control) return;
   __syncthreads();
   auto row_cost = [&](int p) -> double {     // padded row p; taps outside [0, Nall) are the dropped ones
-    double cost = 0.0;
+    double w[7];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      if (a.st.weight[k] == 0.0) continue;
-      double acc = 0.0;
-#pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        const int idx = p + j - 3;
-        acc += a.st.coef[k][j] * ((idx < 0 || idx >= Nall) ? 0.0 : xs[idx]);
-      }
-      cost += a.control_weight * a.st.weight[k] * (acc * acc);
+    for (int j = 0; j < 7; ++j) {
+      const int idx = p + j - 3;
+      w[j] = (idx < 0 || idx >= Nall) ? 0.0 : xs[idx];
     }
-    return cost;
+    return stencil_row_cost(a.st, a.control_weight, w);
   };
   for (int t = threadIdx.x; t < N; t += blockDim.x) {
     double cost = row_cost(kPad + t);
@@ -718,6 +795,68 @@ __global__ void __launch_bounds__(128) k_generate_dense(GenArgs a, const double*
       for (int q = 0; q < kPad; ++q) cost += row_cost(kPad + N + (kPad - 1 - q));
     a.control[row_off + t] = cost;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_finish_rollouts: second half of the pipelined generation.  The look-ahead pass (GenArgs::pre) left the new rollouts'
+// noise and M * noise in compact buffers while the previous iteration was still running; once theta is updated this kernel
+// does what is left, one thread per (problem, new rollout, dimension, timestep):
+//   parameters = theta + noise;  x = parameters + M noise;  control cost = stencils over [pads, x, pads]
+// — the same additions in the same order and the same stencil_row_cost as the one-pass kernels: bit-identical outputs.
+// ---------------------------------------------------------------------------------------------
+struct FinishArgs {
+  int B, R, G, D, N;            // G new rollout slots [0, G) of R
+  const double* theta;          // [B][D][N]
+  const double* pre_noise;      // [B][G][D][N]
+  const double* pre_y;          // [B][G][D][N]
+  const double* pad_start;      // [B][D]
+  const double* pad_goal;       // [B][D]
+  double* noise;                // [B][R][D][N]
+  double* params;               // [B][R][D][N]
+  double* control;              // [B][R][D][N]
+  double* noise_projected;      // optional tap
+  double control_weight;
+  Stencil st;
+};
+
+__global__ void __launch_bounds__(256) k_finish_rollouts(FinishArgs a) {
+  const int N = a.N, Nall = N + 2 * kPad;
+  const long long total = (long long)a.B * a.G * a.D * N;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long vec = idx / N;
+  const int t = int(idx - vec * N);
+  const int d = int(vec % a.D);
+  const long long br = vec / a.D;
+  const int r = int(br % a.G), b = int(br / a.G);
+  const double* th = a.theta + (size_t(b) * a.D + d) * N;
+  const double* en = a.pre_noise + size_t(vec) * N;
+  const double* yn = a.pre_y + size_t(vec) * N;
+  const size_t dst = ((size_t(b) * a.R + r) * a.D + d) * N + t;
+  const double xs = a.pad_start[size_t(b) * a.D + d], xg = a.pad_goal[size_t(b) * a.D + d];
+  auto xall = [&](int p) -> double {          // padded series; taps outside [0, Nall) are the dropped ones
+    if (p < 0 || p >= Nall) return 0.0;
+    if (p < kPad) return xs;
+    if (p >= kPad + N) return xg;
+    const int f = p - kPad;
+    return (th[f] + en[f]) + yn[f];
+  };
+  auto row_cost = [&](int p) -> double {
+    double w[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) w[j] = xall(p + j - 3);
+    return stencil_row_cost(a.st, a.control_weight, w);
+  };
+  const double ev = en[t];
+  a.noise[dst] = ev;
+  a.params[dst] = th[t] + ev;
+  if (a.noise_projected) a.noise_projected[dst] = yn[t];
+  double cost = row_cost(kPad + t);
+  if (t == 0)
+    for (int q = 0; q < kPad; ++q) cost += row_cost(q);
+  if (t == N - 1)
+    for (int q = 0; q < kPad; ++q) cost += row_cost(kPad + N + (kPad - 1 - q));
+  a.control[dst] = cost;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -843,7 +982,7 @@ __global__ void __launch_bounds__(128) k_generate_mma(GenArgs a, const double* _
       const double* src = nullptr;
       if (!is_new) {
         const int sidx = a.reuse_src[size_t(b) * (a.R - a.R_gen) + (r - a.R_gen)];
-        src = sidx >= 0 ? a.params_prev + ((size_t(b) * a.R + sidx) * a.D + d) * N : a.theta + (size_t(b) * a.D + d) * N;
+        src = sidx >= 0 ? a.params_prev + ((size_t(b) * a.prev_stride + sidx) * a.D + d) * N : a.theta + (size_t(b) * a.D + d) * N;
       }
       s_src[vl] = src;
       s_sg[vl] = a.noise_scale[d];
@@ -1846,6 +1985,9 @@ struct UpdateArgs {
   const double* dense_ms;    // [N][N] rows j of R^-1 diag(s) (engine.cu), or nullptr: banded solves
   int use_dmma;              // dense projection on the tensor pipe (mma.sync m8n8k4 f64) instead of the scalar DFMA loop
   const double* cumulative;  // [B][R][D][N]
+  const double* state;       // [B][R][N] or nullptr.  Given (use_cumulative_costs == 0): the cost of (r, d, t) is formed here
+                             // as state[r][t] + cumulative[r][d][t] with `cumulative` pointing at the CONTROL costs — the very
+                             // addition k_cumulative does, so k_update need not wait for that kernel
   const double* noise;       // [B][R][D][N]
   double* probabilities;     // optional tap
   double* updates;           // [B][D][N]
@@ -1890,23 +2032,31 @@ __device__ __forceinline__ double exp_weight(double x) {
 // not software-pipeline it; ncu showed 45 % of the stalls on these loads).  kCache: R <= kGroup, every value is loaded once,
 // up front, and both passes run from registers — one memory round trip per element.  Same operations in the same order in
 // every instantiation: results do not depend on which one ran.
-template <int kGroup, bool kCache>
-__device__ __forceinline__ double weighted_noise(const double* __restrict__ c, const double* __restrict__ e, size_t rstride, int R,
-                                                 double* __restrict__ prob_out) {
+template <int kGroup, bool kCache, bool kSum>
+__device__ __forceinline__ double weighted_noise(const double* __restrict__ c, const double* __restrict__ s, const double* __restrict__ e,
+                                                 size_t rstride, size_t sstride, int R, double* __restrict__ prob_out) {
+  // cost of rollout r: the cumulative cost, or (kSum) state cost + control cost = what k_cumulative stores without the scan
+  auto cost = [&](int r) -> double { return kSum ? s[r * sstride] + c[r * rstride] : c[r * rstride]; };
   double cc[kCache ? kGroup : 1], ec[kCache ? kGroup : 1];
   if (kCache) {
+    double sv[kSum ? kGroup : 1];
 #pragma unroll
     for (int j = 0; j < kGroup; ++j) {
       const bool in = j < R;
       cc[j] = in ? c[j * rstride] : 0.0;
+      if (kSum) sv[j] = in ? s[j * sstride] : 0.0;
       ec[j] = in ? e[j * rstride] : 0.0;
     }
+    if (kSum) {
+#pragma unroll
+      for (int j = 0; j < kGroup; ++j) cc[j] = sv[j] + cc[j];
+    }
   }
-  double mn = kCache ? cc[0] : c[0], mx = mn;
+  double mn = kCache ? cc[0] : cost(0), mx = mn;
   for (int r0 = 0; r0 < R; r0 += kGroup) {
     double cv[kGroup];
 #pragma unroll
-    for (int j = 0; j < kGroup; ++j) cv[j] = r0 + j < R ? (kCache ? cc[j] : c[(r0 + j) * rstride]) : mn;
+    for (int j = 0; j < kGroup; ++j) cv[j] = r0 + j < R ? (kCache ? cc[j] : cost(r0 + j)) : mn;
 #pragma unroll
     for (int j = 0; j < kGroup; ++j) {
       if (cv[j] < mn) mn = cv[j];
@@ -1922,7 +2072,7 @@ __device__ __forceinline__ double weighted_noise(const double* __restrict__ c, c
 #pragma unroll
     for (int j = 0; j < kGroup; ++j) {
       const bool in = r0 + j < R;
-      cv[j] = in ? (kCache ? cc[j] : c[(r0 + j) * rstride]) : 0.0;
+      cv[j] = in ? (kCache ? cc[j] : cost(r0 + j)) : 0.0;
       ev[j] = in ? (kCache ? ec[j] : e[(r0 + j) * rstride]) : 0.0;
     }
 #pragma unroll
@@ -1935,7 +2085,7 @@ __device__ __forceinline__ double weighted_noise(const double* __restrict__ c, c
   }
   const double inv = 1.0 / p_sum;
   if (prob_out)
-    for (int r = 0; r < R; ++r) prob_out[r * rstride] = exp_weight(h * (c[r * rstride] - mn)) * inv;
+    for (int r = 0; r < R; ++r) prob_out[r * rstride] = exp_weight(h * (cost(r) - mn)) * inv;
   return acc * inv;
 }
 
@@ -1967,8 +2117,14 @@ __global__ void __launch_bounds__(128, 7) k_update(UpdateArgs a) {
     const int dl = k / N, t = k - dl * N, d = d0 + dl;
     const size_t base = (size_t(b) * R * D + d) * N + t;
     double* prob = a.probabilities ? a.probabilities + base : nullptr;
-    double v = R <= 10 ? weighted_noise<10, true>(a.cumulative + base, a.noise + base, rstride, R, prob)
-                       : weighted_noise<5, false>(a.cumulative + base, a.noise + base, rstride, R, prob);
+    const double* sp = a.state ? a.state + size_t(b) * R * N + t : nullptr;
+    double v;
+    if (sp)
+      v = R <= 10 ? weighted_noise<10, true, true>(a.cumulative + base, sp, a.noise + base, rstride, size_t(N), R, prob)
+                  : weighted_noise<5, false, true>(a.cumulative + base, sp, a.noise + base, rstride, size_t(N), R, prob);
+    else
+      v = R <= 10 ? weighted_noise<10, true, false>(a.cumulative + base, nullptr, a.noise + base, rstride, 0, R, prob)
+                  : weighted_noise<5, false, false>(a.cumulative + base, nullptr, a.noise + base, rstride, 0, R, prob);
     if (!dense) v *= a.band.proj_scale[t];      // the dense matrix carries the scaling
     u[dl * stride + t] = v;
   }

@@ -743,13 +743,15 @@ def test_two_stream_overlap_is_invisible():
 
 
 @pytest.mark.parametrize("name,problems", [("C1", 1), ("C1", 5), ("tiny", 3)])
-def test_graph_replay_is_invisible(name, problems):
+def test_graph_replay_is_invisible(name, problems, monkeypatch):
     """stomp_engine_run replays steady-state iterations from a CUDA graph (8 iterations per launch, Philox counter and noise
     scales advanced on the device): bit-identical to launching every kernel from the host, including the iterations around
     the replayed block and a second run() that starts on the other ping-pong parity."""
     sc = scenes.make_scenario(name, num_problems=problems)
     sc.noise_decay = np.full(sc.robot.num_dimensions, 0.97)       # the per-iteration noise scale must follow the table
+    monkeypatch.setenv("STOMP_NO_LOOKAHEAD", "1")                 # captured iterations generate in one pass: same launch counts
     a, b = _engine(sc, keep_intermediates=1), _engine(sc, keep_intermediates=1)
+    monkeypatch.delenv("STOMP_NO_LOOKAHEAD")
     a.set_graph_mode(1)
     b.set_graph_mode(0)
     for eng in (a, b):
@@ -791,6 +793,63 @@ def test_split_cost_kernel_is_bit_identical(name, problems, cumulative, monkeypa
     np.testing.assert_array_equal(c1, c2)
     np.testing.assert_array_equal(f1, f2)
     assert np.abs(c1).max() > 0
+
+
+@pytest.mark.parametrize("name,problems,cumulative,keep", [("C1", 1, 0, 1), ("C1", 1, 0, 0), ("C1", 48, 0, 1), ("C1", 48, 1, 1),
+                                                          ("C1", 8, 0, 0), ("tiny", 2, 0, 1)])
+def test_pipelined_generation_is_bit_identical(name, problems, cumulative, keep, monkeypatch):
+    """The default schedule generates the next iteration's noise and M * noise on a third stream while the current iteration
+    runs (k_generate_ahead), finishes the new rollouts after the update (k_finish_rollouts), prepares every previous rollout
+    as a reuse candidate beside the noise-less rollout's cost (candidate pass + k_select_gather) and - without cumulative
+    costs - lets k_update add S + C itself so that k_cumulative leaves the critical path (small batches only; large ones
+    keep the throughput schedule).  Every field equals the one-pass schedule bit for bit, also when the look-ahead pass has to be thrown away: injected noise, new noise settings,
+    an iteration number out of sequence, a step-by-step call in between."""
+    sc = scenes.make_scenario(name, num_problems=problems, use_cumulative_costs=cumulative)
+    sc.noise_decay = np.full(sc.robot.num_dimensions, 0.95)
+    a = _engine(sc, keep_intermediates=keep)
+    monkeypatch.setenv("STOMP_NO_LOOKAHEAD", "1")
+    monkeypatch.setenv("STOMP_NO_DIRECT_UPDATE", "1")
+    b = _engine(sc, keep_intermediates=keep)
+    monkeypatch.delenv("STOMP_NO_LOOKAHEAD")
+    monkeypatch.delenv("STOMP_NO_DIRECT_UPDATE")
+    fields = (_abi.FIELD_THETA, _abi.FIELD_NOISE, _abi.FIELD_PARAMETERS, _abi.FIELD_STATE_COSTS,
+              _abi.FIELD_CONTROL_COSTS, _abi.FIELD_CUMULATIVE_COSTS, _abi.FIELD_UPDATES,
+              _abi.FIELD_ROLLOUT_TOTAL_COSTS, _abi.FIELD_NOISELESS_COSTS, _abi.FIELD_COLLISION_FREE)
+    if keep:
+        fields += (_abi.FIELD_NOISE_PROJECTED, _abi.FIELD_PROBABILITIES)
+
+    def same(what):
+        for f in fields:
+            np.testing.assert_array_equal(a.get(f), b.get(f), err_msg="%s: field %d" % (what, f))
+
+    D, N, R = sc.robot.num_dimensions, sc.num_time_steps, sc.num_rollouts
+    G = R - sc.num_reused_rollouts
+    eps = 0.05 * np.random.default_rng(3).standard_normal((problems, G, D, N))
+    for eng in (a, b):
+        eng.run(1, 5)
+    same("five iterations in one run")
+    launches = a.launch_count()
+    for eng in (a, b):
+        for it in (6, 7):
+            c, f, _ = eng.iterate(it)                       # host reads the statistics after every iteration
+    same("iterate with statistics")
+    assert a.launch_count() != b.launch_count()             # another set of kernels ran
+    for eng in (a, b):
+        eng.inject_noise(eps)                               # iteration 8 takes the caller's noise: the look-ahead is dropped
+        eng.iterate(8, stats=False)
+        eng.run(9, 2)
+    same("injected noise in between")
+    for eng in (a, b):
+        eng.set_noise(np.full(D, 0.7), np.full(D, 0.9))     # the pending look-ahead pass used the old scales
+        eng.run(11, 3)
+        eng.iterate(40, stats=False)                        # out of sequence: another noise scale than the one prepared
+        eng.run(41, 2)
+    same("new noise settings, iteration number out of sequence")
+    for eng in (a, b):
+        eng.get_rollouts(np.full(D, 0.3))                   # step-by-step API advances the generation counter
+        eng.run(43, 3)
+    same("after a step-by-step call")
+    assert np.abs(a.get(_abi.FIELD_NOISE)).max() > 0
 
 
 def test_async_result_readback_pipeline():
