@@ -143,6 +143,7 @@ struct Engine {
   bool cand_valid = false, cand_dirty = false;
   uint32_t cand_generation = 0;
   uint64_t cand_epoch = 0;
+  bool wide_update = true;    // A/B switch (STOMP_NO_WIDE_UPDATE=1): k_update with 512-thread CTAs when there are few of them
   bool direct_update = true;  // A/B switch (STOMP_NO_DIRECT_UPDATE=1): k_update always reads k_cumulative's output
   bool dmma_update = true;    // A/B switch (STOMP_NO_DMMA=1): the dense projection runs as scalar DFMAs instead of DMMA tiles
   int gen_mode = 0;   // 0: pick k_generate / k_generate_dense / k_generate_mma by batch shape; 1, 2, 3: always that one (A/B)
@@ -722,10 +723,18 @@ int launch_update(Engine& e, int apply, bool fuse_extra_control) {
   while (smem > 200 * 1024 && dpc > 1) smem = update_smem(--dpc);
   a.dims_per_cta = dpc;
   const int groups = (e.D + dpc - 1) / dpc;
-  CUDA_TRY(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  // few CTAs (less than one per SM): wide CTAs, the latency of one CTA is the latency of the kernel
+  const bool wide = e.wide_update && (long long)e.B * groups <= e.num_sms && a.dense_ms != nullptr;
+  if (wide) {
+    CUDA_TRY(cudaFuncSetAttribute(k_update<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    begin_launch(e);
+    k_update<512, 1><<<unsigned(e.B) * groups, 512, smem, e.ws>>>(a);
+    return check_launch(e, "k_update");
+  }
+  CUDA_TRY(cudaFuncSetAttribute(k_update<128, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   begin_launch(e);
   const int tpb_max = 128;   // A/B on B200 (C2): 64 threads 0.163, 128: 0.097, 256: 0.150, 512: 0.244 ms
-  k_update<<<unsigned(e.B) * groups, std::min(tpb_max, ((dpc * e.N + 31) / 32) * 32), smem, e.ws>>>(a);
+  k_update<128, 7><<<unsigned(e.B) * groups, std::min(tpb_max, ((dpc * e.N + 31) / 32) * 32), smem, e.ws>>>(a);
   return check_launch(e, "k_update");
 }
 
@@ -1559,6 +1568,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   e.dmma_update = !(getenv("STOMP_NO_DMMA") && atoi(getenv("STOMP_NO_DMMA")) != 0);
   e.direct_update = !(getenv("STOMP_NO_DIRECT_UPDATE") && atoi(getenv("STOMP_NO_DIRECT_UPDATE")) != 0);
   e.lookahead = !(getenv("STOMP_NO_LOOKAHEAD") && atoi(getenv("STOMP_NO_LOOKAHEAD")) != 0);
+  e.wide_update = !(getenv("STOMP_NO_WIDE_UPDATE") && atoi(getenv("STOMP_NO_WIDE_UPDATE")) != 0);
   if (const char* dm = getenv("STOMP_SMALL_BATCH_MAX")) e.small_max = atoll(dm);   // elements B R D N; 0: throughput schedule always
   e.split_cost = !(getenv("STOMP_NO_SPLIT_COST") && atoi(getenv("STOMP_NO_SPLIT_COST")) != 0);
   e.noise_stddev.assign(e.D, 1.0);

@@ -2096,7 +2096,10 @@ __device__ __forceinline__ double weighted_noise(const double* __restrict__ c, c
 // the two banded triangular solves.  Phase 3: theta += update, and the control cost of the updated trajectory from a padded
 // copy in shared memory.  Seven CTAs per SM keep a 1024-problem batch in one wave (at 96 registers it took two: 0.088 ms
 // instead of 0.061).
-__global__ void __launch_bounds__(128, 7) k_update(UpdateArgs a) {
+// kThreads / kMinBlocks: 128 x 7 for batches that fill the machine; 512 x 1 for small batches, where a CTA is alone on its SM and
+// the projection's 8-row tiles (13 for N = 99) each get a warp of their own instead of queueing four deep on four warps.
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_update(UpdateArgs a) {
   extern __shared__ double smem[];
   const int N = a.N, R = a.R, D = a.D, G = a.dims_per_cta;
   const int Nall = N + 2 * kPad;
