@@ -213,8 +213,10 @@ struct Engine {
   // Small batches run a latency schedule (direct k_update, look-ahead generation, candidate pass + k_select_gather): their
   // iteration is a chain of short launches and the machine is mostly idle.  With a machine-filling batch the same work only
   // competes for the SMs (C2: look-ahead 0.476 -> 0.577 ms), so the throughput schedule stays.
+  // (C1-shaped problems on a B200, us per iteration, throughput -> latency schedule: B = 1: 65.5 -> 52.2, 4: 67.1 -> 50.5,
+  //  16: 70.6 -> 68.2, 48: 148 -> 109, 128: 179 -> 198, 512: 305 -> 352; the limit sits between 48 and 128 problems)
   bool small_batch() const { return (long long)B * R * D * N <= small_max; }
-  long long small_max = 1 << 20;
+  long long small_max = 1 << 19;
   bool huge_path() const { return desc.rollout_shard_world > 1 || R > 4096 || (B == 1 && R >= 128); }
 };
 
