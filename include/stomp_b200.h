@@ -217,7 +217,7 @@ int stomp_engine_build_sdf_points(void* engine, const double size[3], const doub
                                   const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders,
                                   const double* points, int64_t num_points);
 /* The same with robot bodies added: StompCollisionSpace::setStartState also voxelises the robot's own links that are not in the
- * planning group (torso, head, the other arm ...) at the start state, and MESH-free collision objects handed over as bodies
+ * planning group (torso, head, the other arm ...) at the start state, and primitive collision objects handed over as bodies
  * (src/stomp_collision_space.cpp:167-188, addAllBodiesButExcludeLinksToPoints :567-588, getVoxelsInBody :590-650).
  * getVoxelsInBody walks the lattice  centre + k * resolution,  |k| <= int(bounding radius / resolution)  per axis around the
  * body's bounding-sphere centre and keeps the points from which a +z ray crosses the body's surface an odd number of times;
@@ -238,6 +238,28 @@ typedef struct stomp_body {
 int stomp_engine_build_sdf_bodies(void* engine, const double size[3], const double origin[3], double resolution, double max_distance,
                                   const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders,
                                   const double* points, int64_t num_points, const stomp_body* bodies, int32_t num_bodies);
+/* The same with MESH bodies added (shapes::MESH collision objects, src/stomp_collision_space.cpp:217-223, and robot links whose
+ * collision geometry is a mesh).  bodies::createBodyFromShape turns a mesh into a bodies::ConvexMesh = the convex hull of its
+ * vertices (geometric_shapes, not vendored; restated from its published source): the hull's vertices give the
+ * mesh centre (their mean) and the bounding radius (largest distance from it); scale and padding move every hull vertex along
+ * its ray from the centre, v' = centre + (v - centre) * (scale + padding / |v - centre|); the bounding sphere is
+ * (pose * centre, radius * scale + padding).  getVoxelsInBody then keeps the lattice points of that sphere's box from which a
+ * +z ray crosses the hull's triangles an odd number of times (:625-646).  The engine computes the hull on the host, the ray
+ * parity on the device (k_sdf_mark_meshes; shared edges are assigned to exactly one triangle, so a ray through an edge or a
+ * vertex still counts once).  `vertices` are in the body frame; triangles of the input mesh are not needed. */
+typedef struct stomp_mesh_body {
+  const double* vertices; /* [num_vertices][3] */
+  int32_t num_vertices;
+  int32_t reserved;
+  double position[3];
+  double orientation[4];  /* quaternion x, y, z, w */
+  double scale;           /* 1.0 = unscaled */
+  double padding;         /* metres */
+} stomp_mesh_body;
+int stomp_engine_build_sdf_meshes(void* engine, const double size[3], const double origin[3], double resolution, double max_distance,
+                                  const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders,
+                                  const double* points, int64_t num_points, const stomp_body* bodies, int32_t num_bodies,
+                                  const stomp_mesh_body* meshes, int32_t num_meshes);
 /* Copies the current voxel grid out (parity tap): dims[3], voxel dtype, and up to `bytes` of voxels (may be NULL). */
 int stomp_engine_get_sdf(void* engine, int32_t dims[3], int32_t* voxel_dtype, void* voxels, size_t bytes);
 /* Inverse-dynamics (torque) cost term of StompOptimizer::execute (src/stomp_optimizer.cpp:1117-1142, getTorques :1006-1061):

@@ -30,7 +30,61 @@ def _round_half_away(t):
     return np.where(t >= 0, np.floor(t + 0.5), np.ceil(t - 0.5))
 
 
-def build(size, origin, resolution, max_distance, boxes=(), cylinders=(), points=None, bodies=()):
+def mesh_body_geometry(vertices, pos, quat, scale, padding):
+    """bodies::ConvexMesh restated (geometric_shapes is not vendored; include/stomp_b200.h states the contract): convex hull of
+    the vertices (qhull through SciPy, where the engine has its own incremental hull), mesh centre = mean of the hull's
+    vertices, bounding radius = largest distance from it, every hull vertex moved along its ray from the centre by
+    scale + padding / distance, then posed.  Returns (world-frame triangles [T][3][3], bounding-sphere centre, radius)."""
+    from scipy.spatial import ConvexHull
+    V = np.asarray(vertices, float).reshape(-1, 3)
+    hull = ConvexHull(V)
+    on = np.zeros(len(V), bool)
+    on[hull.simplices.ravel()] = True
+    mc = np.zeros(3)
+    for v in V[on]:                 # summed in vertex order, like the engine
+        mc = mc + v
+    mc = mc / float(on.sum())
+    d = V - mc
+    l = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])
+    radius = float(l[on].max())
+    fact = scale + np.where(l > 0.0, padding / np.where(l > 0.0, l, 1.0), 0.0)
+    sv = mc + d * fact[:, None]
+    Rm = _rotation(quat)
+    pos = np.asarray(pos, float)
+
+    def world(b):
+        return np.stack([(Rm[r, 0] * b[..., 0] + Rm[r, 1] * b[..., 1] + Rm[r, 2] * b[..., 2]) + pos[r] for r in range(3)], axis=-1)
+
+    return world(sv)[hull.simplices], world(mc), radius * scale + padding
+
+
+def _ray_parity_inside(W, tris):
+    """+z ray crossings of the triangles, per point of W [M][3] (src/stomp_collision_space.cpp:625-646): xy projection with the
+    half-open edge rule, then the sign of the height above the point.  Same individually rounded operations as
+    k_sdf_mark_meshes."""
+    def owns(dx, dy):
+        return (dy > 0.0) | ((dy == 0.0) & (dx < 0.0))
+
+    count = np.zeros(len(W), np.int64)
+    for T in tris:
+        a, b, c = T[0] - W, T[1] - W, T[2] - W
+        area = (b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0])
+        flip = area < 0.0
+        b2 = np.where(flip[:, None], c, b)
+        c2 = np.where(flip[:, None], b, c)
+        b, c = b2, c2
+        wa = b[:, 0] * c[:, 1] - b[:, 1] * c[:, 0]
+        wb = c[:, 0] * a[:, 1] - c[:, 1] * a[:, 0]
+        wc = a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]
+        inside = ((wa > 0.0) | ((wa == 0.0) & owns(c[:, 0] - b[:, 0], c[:, 1] - b[:, 1]))) & \
+                 ((wb > 0.0) | ((wb == 0.0) & owns(a[:, 0] - c[:, 0], a[:, 1] - c[:, 1]))) & \
+                 ((wc > 0.0) | ((wc == 0.0) & owns(b[:, 0] - a[:, 0], b[:, 1] - a[:, 1])))
+        h = (wa * a[:, 2] + wb * b[:, 2]) + wc * c[:, 2]
+        count += (area != 0.0) & inside & (h > 0.0)
+    return (count & 1) == 1
+
+
+def build(size, origin, resolution, max_distance, boxes=(), cylinders=(), points=None, bodies=(), meshes=()):
     from scipy import ndimage
     n = [int(size[i] / resolution) for i in range(3)]
     occ = np.zeros(n, dtype=bool)
@@ -91,6 +145,20 @@ def build(size, origin, resolution, max_distance, boxes=(), cylinders=(), points
             inside = (np.abs(lx) < par[0]) & (np.abs(ly) < par[1]) & (np.abs(lz) < par[2])
         else:
             inside = (np.abs(lz) < par[1]) & (lx * lx + ly * ly < par[0] * par[0])
+        cc = _round_half_away((W[inside] - origin) / resolution).astype(np.int64)
+        cc = cc[np.all((cc >= 0) & (cc < np.array(n)), axis=1)]
+        occ[cc[:, 0], cc[:, 1], cc[:, 2]] = True
+    # mesh bodies: the same lattice walk, ray parity against the convex hull's triangles
+    for (vertices, pos, quat, scale, padding) in meshes:
+        tris, c, bound = mesh_body_geometry(vertices, pos, quat, scale, padding)
+        axes = []
+        for k in range(3):
+            gmin = int(((c[k] - bound) - c[k]) * (1.0 / resolution))
+            gmax = int(((c[k] + bound) - c[k]) * (1.0 / resolution))
+            axes.append(np.arange(gmin, gmax + 1) * resolution + c[k])
+        X, Y, Z = np.meshgrid(*axes, indexing="ij")
+        W = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=-1)
+        inside = _ray_parity_inside(W, tris)
         cc = _round_half_away((W[inside] - origin) / resolution).astype(np.int64)
         cc = cc[np.all((cc >= 0) & (cc < np.array(n)), axis=1)]
         occ[cc[:, 0], cc[:, 1], cc[:, 2]] = True

@@ -130,6 +130,11 @@ class Cylinder(C.Structure):
 BODY_SPHERE, BODY_BOX, BODY_CYLINDER = 0, 1, 2
 
 
+class MeshBody(C.Structure):
+    _fields_ = [("vertices", C.POINTER(C.c_double)), ("num_vertices", C.c_int32), ("reserved", C.c_int32),
+                ("position", C.c_double * 3), ("orientation", C.c_double * 4), ("scale", C.c_double), ("padding", C.c_double)]
+
+
 class Body(C.Structure):
     _fields_ = [("type", C.c_int32), ("reserved", C.c_int32), ("dimensions", C.c_double * 3), ("position", C.c_double * 3),
                 ("orientation", C.c_double * 4), ("scale", C.c_double), ("padding", C.c_double)]

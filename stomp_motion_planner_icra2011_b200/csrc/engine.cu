@@ -1700,6 +1700,91 @@ void quaternion_to_rotation(const double q[4], double R[9]) {   // KDL::Rotation
   R[3] = 2 * x * y + 2 * w * z; R[4] = w2 - x2 + y2 - z2; R[5] = 2 * y * z - 2 * w * x;
   R[6] = 2 * x * z - 2 * w * y; R[7] = 2 * y * z + 2 * w * x; R[8] = w2 - x2 - y2 + z2;
 }
+// Convex hull of n points (incremental, O(n x faces)): triangles with outward normals as vertex index triples.  What
+// bodies::ConvexMesh gets from qhull; coplanar input points may be triangulated differently, which changes no interior.
+struct HullTri { int a, b, c; };
+bool convex_hull_3d(const double* v, int n, std::vector<HullTri>& out) {
+  auto P = [&](int i) { return v + size_t(i) * 3; };
+  auto sub = [](const double* p, const double* q, double r[3]) { r[0] = p[0] - q[0]; r[1] = p[1] - q[1]; r[2] = p[2] - q[2]; };
+  auto cross = [](const double* p, const double* q, double r[3]) {
+    r[0] = p[1] * q[2] - p[2] * q[1]; r[1] = p[2] * q[0] - p[0] * q[2]; r[2] = p[0] * q[1] - p[1] * q[0];
+  };
+  auto dot = [](const double* p, const double* q) { return p[0] * q[0] + p[1] * q[1] + p[2] * q[2]; };
+  if (n < 4) return false;
+  double lo[3] = {P(0)[0], P(0)[1], P(0)[2]}, hi[3] = {lo[0], lo[1], lo[2]};
+  for (int i = 1; i < n; ++i)
+    for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], P(i)[k]); hi[k] = std::max(hi[k], P(i)[k]); }
+  const double extent = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
+  if (!(extent > 0.0)) return false;
+  const double eps = 1e-10 * extent;
+  // starting tetrahedron: extreme point, farthest from it, farthest from that line, farthest from that plane
+  int i0 = 0;
+  for (int i = 1; i < n; ++i) if (P(i)[0] < P(i0)[0]) i0 = i;
+  int i1 = -1; double best = 0.0;
+  for (int i = 0; i < n; ++i) { double d[3]; sub(P(i), P(i0), d); const double l = dot(d, d); if (l > best) { best = l; i1 = i; } }
+  if (i1 < 0) return false;
+  double e01[3]; sub(P(i1), P(i0), e01);
+  int i2 = -1; best = 0.0;
+  for (int i = 0; i < n; ++i) { double d[3], c[3]; sub(P(i), P(i0), d); cross(e01, d, c); const double l = dot(c, c); if (l > best) { best = l; i2 = i; } }
+  if (i2 < 0 || std::sqrt(best) <= eps * std::sqrt(dot(e01, e01))) return false;
+  double e02[3], nrm[3]; sub(P(i2), P(i0), e02); cross(e01, e02, nrm);
+  const double nl = std::sqrt(dot(nrm, nrm));
+  int i3 = -1; best = 0.0;
+  for (int i = 0; i < n; ++i) { double d[3]; sub(P(i), P(i0), d); const double l = std::fabs(dot(nrm, d)) / nl; if (l > best) { best = l; i3 = i; } }
+  if (i3 < 0 || best <= eps) return false;   // flat mesh: no volume to voxelise
+  double inner[3];
+  for (int k = 0; k < 3; ++k) inner[k] = 0.25 * (P(i0)[k] + P(i1)[k] + P(i2)[k] + P(i3)[k]);
+  struct Face { int a, b, c; double n[3]; double off; bool alive; };
+  std::vector<Face> faces;
+  auto add_face = [&](int a, int b, int c) {
+    Face f; f.a = a; f.b = b; f.c = c; f.alive = true;
+    double u[3], w[3]; sub(P(b), P(a), u); sub(P(c), P(a), w); cross(u, w, f.n);
+    const double l = std::sqrt(dot(f.n, f.n));
+    if (l > 0.0) { f.n[0] /= l; f.n[1] /= l; f.n[2] /= l; }
+    f.off = dot(f.n, P(a));
+    if (dot(f.n, inner) - f.off > 0.0) {   // orient outward
+      std::swap(f.b, f.c);
+      f.n[0] = -f.n[0]; f.n[1] = -f.n[1]; f.n[2] = -f.n[2]; f.off = -f.off;
+    }
+    faces.push_back(f);
+  };
+  add_face(i0, i1, i2); add_face(i0, i1, i3); add_face(i0, i2, i3); add_face(i1, i2, i3);
+  std::vector<char> visible;
+  std::vector<std::pair<int, int>> horizon;
+  for (int p = 0; p < n; ++p) {
+    if (p == i0 || p == i1 || p == i2 || p == i3) continue;
+    visible.assign(faces.size(), 0);
+    bool any = false;
+    for (size_t f = 0; f < faces.size(); ++f)
+      if (faces[f].alive && dot(faces[f].n, P(p)) - faces[f].off > eps) { visible[f] = 1; any = true; }
+    if (!any) continue;   // inside the current hull
+    horizon.clear();
+    for (size_t f = 0; f < faces.size(); ++f) {
+      if (!visible[f]) continue;
+      const int ed[3][2] = {{faces[f].a, faces[f].b}, {faces[f].b, faces[f].c}, {faces[f].c, faces[f].a}};
+      for (int k = 0; k < 3; ++k) {
+        bool shared = false;   // is the reversed edge part of another visible face?
+        for (size_t g = 0; g < faces.size() && !shared; ++g) {
+          if (!visible[g] || g == f) continue;
+          const int eg[3][2] = {{faces[g].a, faces[g].b}, {faces[g].b, faces[g].c}, {faces[g].c, faces[g].a}};
+          for (int m = 0; m < 3; ++m) shared |= eg[m][0] == ed[k][1] && eg[m][1] == ed[k][0];
+        }
+        if (!shared) horizon.emplace_back(ed[k][0], ed[k][1]);
+      }
+    }
+    for (size_t f = 0; f < visible.size(); ++f) if (visible[f]) faces[f].alive = false;
+    for (const auto& ed : horizon) add_face(ed.first, ed.second, p);
+    // compact now and then: the visibility scans are linear in the face list
+    if (faces.size() > 4096) {
+      std::vector<Face> keep;
+      for (const Face& f : faces) if (f.alive) keep.push_back(f);
+      faces.swap(keep);
+    }
+  }
+  out.clear();
+  for (const Face& f : faces) if (f.alive) out.push_back(HullTri{f.a, f.b, f.c});
+  return out.size() >= 4;
+}
 }  // namespace
 
 int stomp_engine_build_sdf(void* h, const double size[3], const double origin[3], double resolution, double max_distance,
@@ -1717,7 +1802,16 @@ int stomp_engine_build_sdf_points(void* h, const double size[3], const double or
 int stomp_engine_build_sdf_bodies(void* h, const double size[3], const double origin[3], double resolution, double max_distance,
                                   const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders,
                                   const double* points, int64_t num_points, const stomp_body* bodies, int32_t num_bodies) {
+  return stomp_engine_build_sdf_meshes(h, size, origin, resolution, max_distance, boxes, num_boxes, cylinders, num_cylinders, points,
+                                       num_points, bodies, num_bodies, nullptr, 0);
+}
+
+int stomp_engine_build_sdf_meshes(void* h, const double size[3], const double origin[3], double resolution, double max_distance,
+                                  const stomp_box* boxes, int32_t num_boxes, const stomp_cylinder* cylinders, int32_t num_cylinders,
+                                  const double* points, int64_t num_points, const stomp_body* bodies, int32_t num_bodies,
+                                  const stomp_mesh_body* meshes, int32_t num_meshes) {
   ENGINE_OR_FAIL(h);
+  if (num_meshes < 0 || (num_meshes > 0 && !meshes)) return fail("bad mesh bodies");
   if (num_bodies < 0 || (num_bodies > 0 && !bodies)) return fail("bad bodies");
   if (num_points < 0 || (num_points > 0 && !points)) return fail("bad collision-map points");
   if (!size || !origin || resolution <= 0.0 || max_distance <= 0.0) return fail("bad distance field specification");
@@ -1804,7 +1898,7 @@ int stomp_engine_build_sdf_bodies(void* h, const double size[3], const double or
         b.p[1] = sb.dimensions[1] / 2.0 * sb.scale + sb.padding;
         bound = std::sqrt(b.p[0] * b.p[0] + b.p[1] * b.p[1]);
       } else {
-        return fail("unknown body type (meshes are not supported: geometric_shapes' convex-hull containment is not restated)");
+        return fail("unknown body type (mesh bodies go through stomp_engine_build_sdf_meshes)");
       }
       if (!(bound > 0.0)) return fail("body with a non-positive size");
       b.type = sb.type;
@@ -1827,6 +1921,75 @@ int stomp_engine_build_sdf_bodies(void* h, const double size[3], const double or
         num_bodies, btotal, reinterpret_cast<const SdfBody*>(dbodies.p), origin[0], origin[1], origin[2], resolution, nx, ny, nz, occ.p);
     if (check_launch(e, "k_sdf_mark_bodies")) return 1;
     CUDA_TRY(cudaStreamSynchronize(e.stream));   // dbodies goes out of scope
+  }
+  if (num_meshes > 0) {
+    // bodies::ConvexMesh restated (include/stomp_b200.h): hull, centre, bounding radius, scaled + padded + posed vertices
+    std::vector<SdfMesh> hm;
+    std::vector<double> tris;
+    std::vector<HullTri> hull;
+    long long mtotal = 0;
+    for (int i = 0; i < num_meshes; ++i) {
+      const stomp_mesh_body& mb = meshes[i];
+      if (!mb.vertices || mb.num_vertices < 4) return fail("mesh body needs at least 4 vertices");
+      if (!(mb.scale > 0.0) || !(mb.padding >= 0.0)) return fail("mesh body scale must be positive and padding non-negative");
+      if (!convex_hull_3d(mb.vertices, mb.num_vertices, hull)) return fail("mesh body has no volume (flat or degenerate vertex set)");
+      std::vector<char> on_hull(size_t(mb.num_vertices), 0);
+      for (const HullTri& t : hull) on_hull[t.a] = on_hull[t.b] = on_hull[t.c] = 1;
+      double mc[3] = {0.0, 0.0, 0.0};
+      int nh = 0;
+      for (int v = 0; v < mb.num_vertices; ++v)      // summed in vertex order (part of the contract: the lattice hangs on these bits)
+        if (on_hull[v]) { for (int k = 0; k < 3; ++k) mc[k] += mb.vertices[size_t(v) * 3 + k]; ++nh; }
+      for (int k = 0; k < 3; ++k) mc[k] /= double(nh);
+      double radius = 0.0;
+      for (int v = 0; v < mb.num_vertices; ++v)
+        if (on_hull[v]) {
+          const double dx = mb.vertices[size_t(v) * 3] - mc[0], dy = mb.vertices[size_t(v) * 3 + 1] - mc[1], dz = mb.vertices[size_t(v) * 3 + 2] - mc[2];
+          radius = std::max(radius, std::sqrt(dx * dx + dy * dy + dz * dz));
+        }
+      double R[9];
+      quaternion_to_rotation(mb.orientation, R);
+      auto world = [&](const double* b, double* w) {
+        for (int r = 0; r < 3; ++r) w[r] = (R[r * 3] * b[0] + R[r * 3 + 1] * b[1] + R[r * 3 + 2] * b[2]) + mb.position[r];
+      };
+      auto scaled_world = [&](int v, double* w) {
+        double d[3] = {mb.vertices[size_t(v) * 3] - mc[0], mb.vertices[size_t(v) * 3 + 1] - mc[1], mb.vertices[size_t(v) * 3 + 2] - mc[2]};
+        const double l = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        const double fact = mb.scale + (l > 0.0 ? mb.padding / l : 0.0);
+        const double sv[3] = {mc[0] + d[0] * fact, mc[1] + d[1] * fact, mc[2] + d[2] * fact};
+        world(sv, w);
+      };
+      SdfMesh m;
+      std::memset(&m, 0, sizeof(m));
+      world(mc, m.c);
+      const double bound = radius * mb.scale + mb.padding;
+      if (!(bound > 0.0)) return fail("mesh body with a non-positive size");
+      m.first = mtotal;
+      for (int k = 0; k < 3; ++k) {
+        m.gmin[k] = int(((m.c[k] - bound) - m.c[k]) * (1.0 / resolution));
+        const int gmax = int(((m.c[k] + bound) - m.c[k]) * (1.0 / resolution));
+        m.gn[k] = gmax - m.gmin[k] + 1;
+      }
+      mtotal += (long long)m.gn[0] * m.gn[1] * m.gn[2];
+      m.tri_first = int(tris.size() / 9);
+      m.tri_count = int(hull.size());
+      for (const HullTri& t : hull) {
+        double w[9];
+        scaled_world(t.a, w); scaled_world(t.b, w + 3); scaled_world(t.c, w + 6);
+        tris.insert(tris.end(), w, w + 9);
+      }
+      hm.push_back(m);
+    }
+    DevBuf<unsigned char> dmeshes;
+    DevBuf<double> dtris;
+    if (upload(e, dmeshes, reinterpret_cast<const unsigned char*>(hm.data()), hm.size() * sizeof(SdfMesh)) ||
+        upload(e, dtris, tris.data(), tris.size()))
+      return 1;
+    begin_launch(e);
+    k_sdf_mark_meshes<<<unsigned(std::max<long long>(1, std::min<long long>((mtotal + 255) / 256, 148 * 32))), 256, 0, e.ws>>>(
+        num_meshes, mtotal, reinterpret_cast<const SdfMesh*>(dmeshes.p), dtris.p, origin[0], origin[1], origin[2], resolution, nx, ny, nz,
+        occ.p);
+    if (check_launch(e, "k_sdf_mark_meshes")) return 1;
+    CUDA_TRY(cudaStreamSynchronize(e.stream));   // dmeshes / dtris go out of scope
   }
   const bool u8 = cap * cap < 256;
   CUDA_TRY(e.vox.alloc(cells * (u8 ? 1 : 2)));

@@ -2391,6 +2391,68 @@ __global__ void k_sdf_mark_bodies(int num_bodies, long long total, const SdfBody
   }
 }
 
+// k_sdf_mark_meshes: getVoxelsInBody for convex-hull mesh bodies (src/stomp_collision_space.cpp:625-646): a lattice point is
+// kept when the +z ray from it crosses the (scaled, padded, posed) hull's triangles an odd number of times.  A crossing is
+// decided in the xy projection with the rasteriser's half-open edge rule (a point exactly on a shared edge belongs to one of
+// the two triangles), then by the sign of the barycentric height above the point.  Every product and sum is individually
+// rounded (no FMA contraction): the NumPy restatement the tests hold this to does the same arithmetic, and the cells agree exactly.
+struct SdfMesh {
+  double c[3];         // bounding-sphere centre (world)
+  int gmin[3], gn[3];  // first lattice index and count per axis
+  long long first;     // first lattice point of this mesh in the launch
+  int tri_first, tri_count;   // its triangles in the [*][9] world-frame vertex array
+};
+
+__device__ __forceinline__ bool edge_owns(double dx, double dy) { return dy > 0.0 || (dy == 0.0 && dx < 0.0); }
+
+__global__ void k_sdf_mark_meshes(int num_meshes, long long total, const SdfMesh* __restrict__ meshes, const double* __restrict__ tris,
+                                  double ox, double oy, double oz, double res, int nx, int ny, int nz, uint8_t* __restrict__ occ) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = num_meshes - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (meshes[mid].first <= i) lo = mid; else hi = mid - 1;
+    }
+    const SdfMesh& m = meshes[lo];
+    long long k = i - m.first;
+    const int iz = int(k % m.gn[2]); k /= m.gn[2];
+    const int iy = int(k % m.gn[1]);
+    const int ix = int(k / m.gn[1]);
+    const double xw = __dadd_rn(__dmul_rn(double(m.gmin[0] + ix), res), m.c[0]), yw = __dadd_rn(__dmul_rn(double(m.gmin[1] + iy), res), m.c[1]),
+                 zw = __dadd_rn(__dmul_rn(double(m.gmin[2] + iz), res), m.c[2]);
+    int crossings = 0;
+    for (int t = 0; t < m.tri_count; ++t) {
+      const double* T = tris + size_t(m.tri_first + t) * 9;
+      double ax = __dsub_rn(T[0], xw), ay = __dsub_rn(T[1], yw), az = __dsub_rn(T[2], zw);
+      double bx = __dsub_rn(T[3], xw), by = __dsub_rn(T[4], yw), bz = __dsub_rn(T[5], zw);
+      double cx = __dsub_rn(T[6], xw), cy = __dsub_rn(T[7], yw), cz = __dsub_rn(T[8], zw);
+      const double area = __dsub_rn(__dmul_rn(__dsub_rn(bx, ax), __dsub_rn(cy, ay)), __dmul_rn(__dsub_rn(by, ay), __dsub_rn(cx, ax)));
+      if (area == 0.0) continue;             // seen edge-on from above: the ray runs inside the triangle's plane
+      if (area < 0.0) {                      // counter-clockwise in the xy projection
+        double s;
+        s = bx; bx = cx; cx = s;
+        s = by; by = cy; cy = s;
+        s = bz; bz = cz; cz = s;
+      }
+      const double wa = __dsub_rn(__dmul_rn(bx, cy), __dmul_rn(by, cx));   // edge b -> c
+      const double wb = __dsub_rn(__dmul_rn(cx, ay), __dmul_rn(cy, ax));   // edge c -> a
+      const double wc = __dsub_rn(__dmul_rn(ax, by), __dmul_rn(ay, bx));   // edge a -> b
+      const bool in = (wa > 0.0 || (wa == 0.0 && edge_owns(__dsub_rn(cx, bx), __dsub_rn(cy, by)))) &&
+                      (wb > 0.0 || (wb == 0.0 && edge_owns(__dsub_rn(ax, cx), __dsub_rn(ay, cy)))) &&
+                      (wc > 0.0 || (wc == 0.0 && edge_owns(__dsub_rn(bx, ax), __dsub_rn(by, ay))));
+      if (!in) continue;
+      const double h = __dadd_rn(__dadd_rn(__dmul_rn(wa, az), __dmul_rn(wb, bz)), __dmul_rn(wc, cz));   // height above the point x area
+      crossings += h > 0.0;
+    }
+    if (!(crossings & 1)) continue;
+    const double tx = (xw - ox) / res, ty = (yw - oy) / res, tz = (zw - oz) / res;
+    if (!(fabs(tx) < 1e9 && fabs(ty) < 1e9 && fabs(tz) < 1e9)) continue;
+    const int cx = int(round(tx)), cy = int(round(ty)), cz = int(round(tz));
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= nx || cy >= ny || cz >= nz) continue;
+    occ[(size_t(cx) * ny + cy) * nz + cz] = 1;
+  }
+}
+
 // axis: 0 = x (input: occupancy u8 -> d^2 along x), 1 = y, 2 = z (inputs: u16 partial squared distances).
 // out[v] = min over |k| <= cap of in[v + k along axis] + k^2, saturated at cap^2 (kInf marks "nothing within cap").
 template <int kAxis, typename Out>

@@ -32,7 +32,7 @@ EXPORTS = [
     "stomp_engine_set_constraints", "stomp_engine_execute_constraints_satisfied",
     "stomp_engine_request_results_async", "stomp_engine_wait_results", "stomp_engine_set_dynamics",
     "stomp_engine_shard_ipc_handle", "stomp_engine_shard_open_peers", "stomp_engine_iterate_sharded_fused",
-    "stomp_engine_shard_status", "stomp_engine_build_sdf_points", "stomp_engine_set_graph_mode", "stomp_engine_build_sdf_bodies",
+    "stomp_engine_shard_status", "stomp_engine_build_sdf_points", "stomp_engine_set_graph_mode", "stomp_engine_build_sdf_bodies", "stomp_engine_build_sdf_meshes",
 ]
 
 
@@ -106,10 +106,11 @@ class Engine:
             pass
 
     # ---- distance field construction -----------------------------------------------------
-    def build_sdf(self, size, origin, resolution, max_distance, boxes=(), cylinders=(), points=None, bodies=()):
+    def build_sdf(self, size, origin, resolution, max_distance, boxes=(), cylinders=(), points=None, bodies=(), meshes=()):
         """boxes: (position, quaternion xyzw, dimensions); cylinders: (position, quaternion, radius, height); points: [n][3]
         collision-map points; bodies: (type, dimensions, position, quaternion, scale, padding) robot / primitive bodies in
-        world poses (getVoxelsInBody)."""
+        world poses (getVoxelsInBody); meshes: (vertices [n][3], position, quaternion, scale, padding) convex-hull mesh
+        bodies (bodies::ConvexMesh)."""
         cb = (_abi.Box * max(1, len(boxes)))()
         for i, (p, q, d) in enumerate(boxes):
             cb[i].position[:], cb[i].orientation[:], cb[i].dimensions[:] = p, q, d
@@ -124,9 +125,18 @@ class Engine:
             bb[i].position[:], bb[i].orientation[:] = p, q
             bb[i].scale, bb[i].padding = sc, pad
         pts = _f64(points).reshape(-1, 3) if points is not None else None
-        self._ck(self.L.stomp_engine_build_sdf_bodies(self.h, (C.c_double * 3)(*size), (C.c_double * 3)(*origin), C.c_double(resolution),
+        mm = (_abi.MeshBody * max(1, len(meshes)))()
+        keep = []
+        for i, (v, p, q, sc, pad) in enumerate(meshes):
+            va = np.ascontiguousarray(_f64(v).reshape(-1, 3))
+            keep.append(va)
+            mm[i].vertices, mm[i].num_vertices = _dp(va), len(va)
+            mm[i].position[:], mm[i].orientation[:] = p, q
+            mm[i].scale, mm[i].padding = sc, pad
+        self._ck(self.L.stomp_engine_build_sdf_meshes(self.h, (C.c_double * 3)(*size), (C.c_double * 3)(*origin), C.c_double(resolution),
                                                       C.c_double(max_distance), cb, len(boxes), cc, len(cylinders),
-                                                      _dp(pts), C.c_int64(0 if pts is None else len(pts)), bb, len(bodies)))
+                                                      _dp(pts), C.c_int64(0 if pts is None else len(pts)), bb, len(bodies),
+                                                      mm, len(meshes)))
 
     def get_sdf(self):
         dims = (C.c_int32 * 3)()

@@ -483,6 +483,47 @@ def test_optimize_outer_loop_matches_host_bookkeeping():
             assert np.all(res["best_trajectory"][ok, d] <= hi + 1e-4) and np.all(res["best_trajectory"][ok, d] >= lo - 1e-4)
 
 
+def test_mesh_bodies_in_the_distance_field_bit_exact():
+    """stomp_engine_build_sdf_meshes: mesh collision objects / mesh link geometry voxelised like bodies::ConvexMesh under
+    StompCollisionSpace::getVoxelsInBody — convex hull (the engine's own incremental hull against qhull in the oracle), centre,
+    scale + padding along the rays from the centre, +z ray parity with each shared edge owned by one triangle — occupancy and
+    distances bit-exact against the NumPy restatement, together with the other object kinds; degenerate meshes are refused."""
+    from oracle import sdf_builder
+    sc = scenes.make_scenario("tiny", num_problems=2)
+    eng = _engine(sc)
+    rng = np.random.default_rng(12)
+    ident = (0.0, 0.0, 0.0, 1.0)
+    tilt = (np.sin(0.3) * 0.6, np.sin(0.3) * 0.8, 0.0, np.cos(0.3))
+    yaw = (0.0, 0.0, np.sin(0.5), np.cos(0.5))
+    blob = rng.standard_normal((400, 3)) * (0.12, 0.08, 0.2)             # most points are interior: the hull keeps ~60
+    shell = rng.standard_normal((150, 3))
+    shell = shell / np.linalg.norm(shell, axis=1, keepdims=True) * 0.15   # every point on the hull
+    wedge = np.array([(0, 0, 0), (0.3, 0, 0), (0, 0.2, 0), (0, 0, 0.25), (0.3, 0.2, 0.0), (0.1, 0.05, 0.3)], float)
+    meshes = [(blob, (0.3, 0.1, 0.9), tilt, 1.0, 0.01), (shell, (0.9, -0.6, 0.4), yaw, 1.15, 0.0),
+              (wedge, (0.2, 0.8, 1.2), tilt, 1.0, 0.02), (shell * 2.0, (-0.45, 1.4, 1.8), ident, 1.0, 0.0)]   # the last pokes out
+    bodies = [(_abi.BODY_BOX, (0.35, 0.45, 0.8), (-0.1, 0.0, 0.75), ident, 1.0, 0.01)]
+    boxes = [((0.8, -0.1, 0.643), ident, (0.4, 1.2, 0.03))]
+    spec = dict(size=(2.0, 3.0, 2.2), origin=(-0.5, -1.5, -0.3), resolution=0.015, max_distance=0.17)
+    eng.build_sdf(boxes=boxes, bodies=bodies, meshes=meshes, **spec)
+    got, dtype = eng.get_sdf()
+    want, occ = sdf_builder.build(boxes=boxes, bodies=bodies, meshes=meshes, **spec)
+    _, occ_without = sdf_builder.build(boxes=boxes, bodies=bodies, **spec)
+    assert occ.sum() - occ_without.sum() > 8000
+    np.testing.assert_array_equal(got, want)
+    # a box given by its corners = the box primitive (coplanar faces: any triangulation of them encloses the same cells)
+    half = np.array([0.15, 0.1, 0.2])
+    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], float) * half
+    eng.build_sdf(meshes=[(corners, (0.503, 0.497, 0.901), tilt, 1.0, 0.0)], **spec)
+    got, _ = eng.get_sdf()
+    want, _ = sdf_builder.build(bodies=[(_abi.BODY_BOX, tuple(2 * half), (0.503, 0.497, 0.901), tilt, 1.0, 0.0)], **spec)
+    np.testing.assert_array_equal(got, want)
+    flat = np.array([(0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 0), (0.3, 0.4, 0)], float)
+    with pytest.raises(RuntimeError, match="no volume"):
+        eng.build_sdf(meshes=[(flat, (0.5, 0.5, 0.5), ident, 1.0, 0.0)], **spec)
+    with pytest.raises(RuntimeError, match="4 vertices"):
+        eng.build_sdf(meshes=[(flat[:3], (0.5, 0.5, 0.5), ident, 1.0, 0.0)], **spec)
+
+
 def test_robot_bodies_in_the_distance_field_bit_exact():
     """stomp_engine_build_sdf_bodies: the robot's links outside the planning group (and primitive collision bodies) voxelised
     like StompCollisionSpace::getVoxelsInBody — bounding-sphere-centred lattice, strictly-inside test of the scaled + padded

@@ -345,6 +345,49 @@ def test_body_voxelisation_restatement_is_strict_containment():
     assert ext[1] > 3 * ext[0] and abs(ext[1] * res - 0.4) < 3 * res
 
 
+def test_mesh_body_voxelisation_restatement():
+    """oracle/sdf_builder.py, meshes (bodies::ConvexMesh + getVoxelsInBody's +z ray parity): a box given as a mesh of its
+    eight corners (plus interior points the hull must drop) marks exactly the cells of the box primitive, posed and padded
+    alike; an icosahedron's volume; a ray through a shared edge or a vertex is counted once (lattice-aligned octahedron)."""
+    from oracle import sdf_builder
+    res = 0.02
+    spec = dict(size=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), resolution=res, max_distance=0.1)
+    tilt = (math.sin(0.35) * 0.6, math.sin(0.35) * 0.8, 0.0, math.cos(0.35))
+    half = np.array([0.15, 0.1, 0.2])
+    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], float) * half
+    inner = np.random.default_rng(2).uniform(-0.9, 0.9, (20, 3)) * half
+    pos = (0.503, 0.497, 0.501)           # off the lattice: no point lies exactly on a face
+    _, occ_mesh = sdf_builder.build(meshes=[(np.vstack([corners, inner]), pos, tilt, 1.0, 0.0)], **spec)
+    _, occ_box = sdf_builder.build(bodies=[(1, tuple(2 * half), pos, tilt, 1.0, 0.0)], **spec)
+    assert occ_box.sum() > 1000
+    np.testing.assert_array_equal(occ_mesh, occ_box)
+    # scale + padding move the corners along their rays from the centre: a cube stays a cube, half edge h * scale + padding / sqrt(3)
+    h, scale, pad = 0.12, 1.2, 0.02
+    cube = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], float) * h
+    _, occ_mesh = sdf_builder.build(meshes=[(cube, pos, tilt, scale, pad)], **spec)
+    he = h * scale + pad / math.sqrt(3.0)
+    _, occ_box = sdf_builder.build(bodies=[(1, (2 * he,) * 3, pos, tilt, 1.0, 0.0)], **spec)
+    assert np.count_nonzero(occ_mesh != occ_box) <= 0.002 * occ_box.sum()      # the two lattices coincide; faces differ in rounding
+    # icosahedron: volume 5 (3 + sqrt 5) / 12 a^3 with edge a = 2 (vertices (0, +-1, +-phi) ...), scaled to circumradius 0.2
+    phi = (1 + math.sqrt(5)) / 2
+    ico = np.array([(0, s1, s2 * phi) for s1 in (-1, 1) for s2 in (-1, 1)] + [(s1, s2 * phi, 0) for s1 in (-1, 1) for s2 in (-1, 1)] +
+                   [(s2 * phi, 0, s1) for s1 in (-1, 1) for s2 in (-1, 1)], float)
+    k = 0.2 / math.sqrt(1 + phi * phi)
+    _, occ = sdf_builder.build(meshes=[(ico * k, pos, tilt, 1.0, 0.0)], **spec)
+    volume = 5 * (3 + math.sqrt(5)) / 12 * (2 * k) ** 3
+    assert abs(occ.sum() * res ** 3 - volume) < 0.05 * volume
+    # octahedron centred ON a lattice point with lattice-aligned axes: rays pass through vertices and edges; every interior
+    # lattice point |x| + |y| + |z| < r is marked exactly once, none outside
+    r = 5 * res
+    octa = np.array([(r, 0, 0), (-r, 0, 0), (0, r, 0), (0, -r, 0), (0, 0, r), (0, 0, -r)], float)
+    c = (0.5, 0.5, 0.5)
+    _, occ = sdf_builder.build(meshes=[(octa, c, (0.0, 0.0, 0.0, 1.0), 1.0, 0.0)], **spec)
+    g = np.arange(50)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    l1 = np.abs(X - 25) + np.abs(Y - 25) + np.abs(Z - 25)
+    assert occ[l1 < 5].all() and not occ[l1 > 5].any()
+
+
 def test_upstream_propagation_differs_from_the_exact_transform_only_marginally():
     """The engine's distance-field rebuild computes the exact capped squared Euclidean transform; the reference propagates with
     distance_field::PropagationDistanceField (un-vendored), whose direction-restricted neighbourhoods make it a propagation, not
