@@ -84,12 +84,13 @@ struct StompCollisionSpace {
   // what StompCollisionSpace::setStartState rebuilds the field from (src/stomp_collision_space.cpp:154-197): the environment's
   // collision objects and collision-map points, and the robot's own bodies outside the planning group at the start state
   // (StompRobotModelUrdf::bodiesAtState).  When `size` is set, StompOptimizer builds the field on the GPU
-  // (stomp_engine_build_sdf_bodies) instead of uploading `voxels`.
+  // (stomp_engine_build_sdf_meshes) instead of uploading `voxels`.
   double size[3] = {0, 0, 0}, max_distance = 0.0;   // collision_space/size_*, max_propagation_distance
   std::vector<stomp_box> boxes;
   std::vector<stomp_cylinder> cylinders;
   std::vector<double> points;                       // [n][3]
   std::vector<stomp_body> bodies;
+  std::vector<stomp_mesh_body> meshes;              // mesh collision objects / mesh link geometry (meshBodiesAtState)
   bool built_on_device() const { return size[0] > 0.0 && size[1] > 0.0 && size[2] > 0.0 && max_distance > 0.0; }
 };
 
@@ -465,9 +466,9 @@ class StompOptimizer : public Task, public std::enable_shared_from_this<StompOpt
       return false;
     if (collision_space_->built_on_device()) {
       const StompCollisionSpace& cs = *collision_space_;
-      if (stomp_engine_build_sdf_bodies(h, cs.size, cs.origin, cs.resolution, cs.max_distance, cs.boxes.data(), int(cs.boxes.size()),
+      if (stomp_engine_build_sdf_meshes(h, cs.size, cs.origin, cs.resolution, cs.max_distance, cs.boxes.data(), int(cs.boxes.size()),
                                         cs.cylinders.data(), int(cs.cylinders.size()), cs.points.data(), int64_t(cs.points.size() / 3),
-                                        cs.bodies.data(), int(cs.bodies.size())))
+                                        cs.bodies.data(), int(cs.bodies.size()), cs.meshes.data(), int(cs.meshes.size())))
         return false;
     } else if (stomp_engine_set_sdf(h, collision_space_->voxels.data(), collision_space_->nx, collision_space_->ny, collision_space_->nz,
                                     collision_space_->origin, collision_space_->resolution, collision_space_->voxel_dtype)) {

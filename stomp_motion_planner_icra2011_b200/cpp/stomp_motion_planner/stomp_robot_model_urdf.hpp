@@ -19,6 +19,8 @@
 #include <cmath>
 #include <cctype>
 #include <cstdlib>
+#include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -126,11 +128,17 @@ struct CollisionLinkConfig {      // collision_links/<link>/{link_radius, link_c
   double link_clearance = -1.0;   // < 0: the model-wide collision_clearance
 };
 
-struct LinkBody {                 // one <collision> primitive of a link, in the link (segment) frame
+constexpr int kLinkBodyMesh = 3;  // LinkBody::type of a <mesh> geometry (the primitives use stomp_body_type)
+struct LinkBody {                 // one <collision> geometry of a link, in the link (segment) frame
   int segment = -1;
   int type = STOMP_BODY_BOX;
   double dimensions[3] = {0, 0, 0};
   double rot[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pos[3] = {0, 0, 0};
+  // <mesh filename="..." scale="sx sy sz"/>: the file is read by loadLinkMeshes; vertices [n][3] in the link body's frame,
+  // already multiplied by the URDF scale (what the reference receives from planning_models as a shapes::Mesh)
+  std::string mesh_filename;
+  double mesh_scale[3] = {1, 1, 1};
+  std::vector<double> mesh_vertices;
 };
 
 struct StompRobotModelUrdf : StompRobotModel {
@@ -346,7 +354,7 @@ inline bool loadRobotModelFromUrdf(const std::string& urdf_xml, const std::vecto
       for (int k = 0; k < 3; ++k) li.com[k] = xyz[k];
       li.inertia[0] = Il[0]; li.inertia[1] = Il[4]; li.inertia[2] = Il[8]; li.inertia[3] = Il[1]; li.inertia[4] = Il[2]; li.inertia[5] = Il[5];
     }
-    // <collision> primitives (meshes are skipped: geometric_shapes' convex-hull containment is not restated)
+    // <collision> geometries (a mesh keeps its file name; loadLinkMeshes reads the vertices)
     for (const auto& c : l->children) {
       if (c->name != "collision") continue;
       const XmlElement* geo = c->child("geometry");
@@ -365,6 +373,11 @@ inline bool loadRobotModelFromUrdf(const std::string& urdf_xml, const std::vecto
       } else if (const XmlElement* sph = geo->child("sphere")) {
         b.type = STOMP_BODY_SPHERE;
         b.dimensions[0] = number(sph->attr("radius"), 0.0);
+      } else if (const XmlElement* mesh = geo->child("mesh")) {
+        static const double one3[3] = {1, 1, 1};
+        b.type = kLinkBodyMesh;
+        if (const std::string* fn = mesh->attr("filename")) b.mesh_filename = *fn;
+        if (!numbers(mesh->attr("scale"), 3, one3, b.mesh_scale, err)) return false;
       } else {
         continue;
       }
@@ -415,9 +428,65 @@ inline bool addAttachedObjectCollisionPoint(StompRobotModelUrdf& m, const std::s
 // + addAllBodiesButExcludeLinksToPoints hand to getVoxelsInBody (src/stomp_collision_space.cpp:522-588).  group_values: the
 // planning group's joints (the start state); the other joints take their fixed_value.  exclude_links: the group's
 // distance_exclude_links (its own links).  Quaternions are x, y, z, w.
-inline std::vector<stomp_body> bodiesAtState(const StompRobotModelUrdf& m, const std::vector<double>& group_values,
-                                             const std::vector<std::string>& exclude_links, double scale = 1.0, double padding = 0.0) {
-  using urdf_detail::matmul3;
+// STL reader for <mesh> collision geometry (binary: 80-byte header, uint32 count, 50 bytes per facet; ASCII: "vertex x y z"
+// lines).  Only the vertices matter: the reference turns a mesh into the convex hull of its vertices (bodies::ConvexMesh).
+inline bool readStlVertices(const std::string& path, std::vector<double>& vertices, std::string& err) {
+  std::FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) { err = "cannot open mesh file " + path; return false; }
+  std::vector<unsigned char> buf;
+  unsigned char chunk[65536];
+  size_t got;
+  while ((got = std::fread(chunk, 1, sizeof(chunk), f)) > 0) buf.insert(buf.end(), chunk, chunk + got);
+  std::fclose(f);
+  vertices.clear();
+  uint32_t count = 0;
+  if (buf.size() >= 84) std::memcpy(&count, &buf[80], 4);
+  if (buf.size() >= 84 && buf.size() == 84 + size_t(count) * 50) {
+    for (uint32_t t = 0; t < count; ++t)
+      for (int v = 0; v < 3; ++v)
+        for (int k = 0; k < 3; ++k) {
+          float x;
+          std::memcpy(&x, &buf[84 + size_t(t) * 50 + 12 + size_t(v) * 12 + size_t(k) * 4], 4);
+          vertices.push_back(double(x));
+        }
+  } else {
+    const std::string text(buf.begin(), buf.end());
+    size_t at = 0;
+    while ((at = text.find("vertex", at)) != std::string::npos) {
+      at += 6;
+      const char* c = text.c_str() + at;
+      char* end = nullptr;
+      double xyz[3];
+      bool ok = true;
+      for (int k = 0; k < 3 && ok; ++k) { xyz[k] = std::strtod(c, &end); ok = end != c; c = end; }
+      if (ok) vertices.insert(vertices.end(), xyz, xyz + 3);
+    }
+  }
+  if (vertices.size() < 12) { err = "mesh file " + path + " holds fewer than 4 vertices"; return false; }
+  return true;
+}
+
+// Reads the vertices of every <mesh> collision geometry (URDF scale applied).  `resolve` maps the URDF's file name
+// ("package://pr2_description/meshes/...") to a path on disk; the default takes it literally.
+template <typename Resolve>
+inline bool loadLinkMeshes(StompRobotModelUrdf& m, Resolve resolve, std::string& err) {
+  for (LinkBody& lb : m.link_bodies) {
+    if (lb.type != kLinkBodyMesh || !lb.mesh_vertices.empty()) continue;
+    if (!readStlVertices(resolve(lb.mesh_filename), lb.mesh_vertices, err)) return false;
+    for (size_t v = 0; v < lb.mesh_vertices.size(); ++v) lb.mesh_vertices[v] *= lb.mesh_scale[v % 3];
+  }
+  return true;
+}
+inline bool loadLinkMeshes(StompRobotModelUrdf& m, std::string& err) {
+  return loadLinkMeshes(m, [](const std::string& name) { return name; }, err);
+}
+
+namespace urdf_detail {
+// pose of every collision geometry of the links (not excluded) at a joint state, in the reference segment's frame:
+// visit(link_body, position[3], quaternion_xyzw[4])
+template <typename Visit>
+inline void linkBodyPoses(const StompRobotModelUrdf& m, const std::vector<double>& group_values,
+                          const std::vector<std::string>& exclude_links, Visit visit) {
   const size_t S = m.segments.size();
   std::vector<double> R(S * 9), p(S * 3);
   for (size_t s = 0; s < S; ++s) {          // DFS pre-order: parents come first
@@ -446,7 +515,6 @@ inline std::vector<stomp_body> bodiesAtState(const StompRobotModelUrdf& m, const
   // express everything in the reference segment's frame
   const double* Rr = &R[size_t(m.reference_segment) * 9];
   const double* pr = &p[size_t(m.reference_segment) * 3];
-  std::vector<stomp_body> out;
   for (const LinkBody& lb : m.link_bodies) {
     bool excluded = false;
     for (const std::string& e : exclude_links) excluded = excluded || m.segment_names[lb.segment] == e;
@@ -461,10 +529,6 @@ inline std::vector<stomp_body> bodiesAtState(const StompRobotModelUrdf& m, const
       for (int c = 0; c < 3; ++c) Rrt[r * 3 + c] = Rr[c * 3 + r];
     matmul3(Rrt, Rw, Rb);
     for (int k = 0; k < 3; ++k) pb[k] = Rrt[k * 3] * (pw[0] - pr[0]) + Rrt[k * 3 + 1] * (pw[1] - pr[1]) + Rrt[k * 3 + 2] * (pw[2] - pr[2]);
-    stomp_body b;
-    std::memset(&b, 0, sizeof(b));
-    b.type = lb.type;
-    for (int k = 0; k < 3; ++k) { b.dimensions[k] = lb.dimensions[k]; b.position[k] = pb[k]; }
     // rotation matrix -> quaternion (x, y, z, w)
     const double tr = Rb[0] + Rb[4] + Rb[8];
     double qx, qy, qz, qw;
@@ -481,11 +545,49 @@ inline std::vector<stomp_body> bodiesAtState(const StompRobotModelUrdf& m, const
       const double s4 = std::sqrt(1.0 + Rb[8] - Rb[0] - Rb[4]) * 2.0;
       qw = (Rb[3] - Rb[1]) / s4; qx = (Rb[2] + Rb[6]) / s4; qy = (Rb[5] + Rb[7]) / s4; qz = 0.25 * s4;
     }
-    b.orientation[0] = qx; b.orientation[1] = qy; b.orientation[2] = qz; b.orientation[3] = qw;
+    const double quat[4] = {qx, qy, qz, qw};
+    visit(lb, pb, quat);
+  }
+}
+}  // namespace urdf_detail
+
+// StompCollisionSpace::addAllBodiesButExcludeLinksToPoints' input (src/stomp_collision_space.cpp:564-586): the primitive
+// collision bodies of the robot's links at a joint state, in the reference frame; meshBodiesAtState gives the mesh ones.
+inline std::vector<stomp_body> bodiesAtState(const StompRobotModelUrdf& m, const std::vector<double>& group_values,
+                                             const std::vector<std::string>& exclude_links, double scale = 1.0, double padding = 0.0) {
+  std::vector<stomp_body> out;
+  urdf_detail::linkBodyPoses(m, group_values, exclude_links, [&](const LinkBody& lb, const double* pb, const double* quat) {
+    if (lb.type == kLinkBodyMesh) return;
+    stomp_body b;
+    std::memset(&b, 0, sizeof(b));
+    b.type = lb.type;
+    for (int k = 0; k < 3; ++k) { b.dimensions[k] = lb.dimensions[k]; b.position[k] = pb[k]; }
+    for (int k = 0; k < 4; ++k) b.orientation[k] = quat[k];
     b.scale = scale;
     b.padding = padding;
     out.push_back(b);
-  }
+  });
+  return out;
+}
+
+// The mesh collision geometries (after loadLinkMeshes) as stomp_mesh_body records for stomp_engine_build_sdf_meshes.  The
+// records point into the model's vertex arrays: keep the model alive and unchanged while they are in use.
+inline std::vector<stomp_mesh_body> meshBodiesAtState(const StompRobotModelUrdf& m, const std::vector<double>& group_values,
+                                                      const std::vector<std::string>& exclude_links, double scale = 1.0,
+                                                      double padding = 0.0) {
+  std::vector<stomp_mesh_body> out;
+  urdf_detail::linkBodyPoses(m, group_values, exclude_links, [&](const LinkBody& lb, const double* pb, const double* quat) {
+    if (lb.type != kLinkBodyMesh || lb.mesh_vertices.size() < 12) return;
+    stomp_mesh_body b;
+    std::memset(&b, 0, sizeof(b));
+    b.vertices = lb.mesh_vertices.data();
+    b.num_vertices = int32_t(lb.mesh_vertices.size() / 3);
+    for (int k = 0; k < 3; ++k) b.position[k] = pb[k];
+    for (int k = 0; k < 4; ++k) b.orientation[k] = quat[k];
+    b.scale = scale;
+    b.padding = padding;
+    out.push_back(b);
+  });
   return out;
 }
 

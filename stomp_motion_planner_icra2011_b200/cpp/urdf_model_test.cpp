@@ -3,7 +3,8 @@
 // usage: urdf_model_test robot.urdf spec.txt
 //   spec lines:  group j1 j2 ... | reference link | clearance c | collision link radius extension | state joint value |
 //                chain root tip | exclude link ... | start q1 q2 ... | padding scale pad |
-//                attach link type d0 d1 d2 x y z padding
+//                attach link type d0 d1 d2 x y z padding | meshdir directory (package:// names are looked up there)
+#include <algorithm>
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -17,7 +18,7 @@ int main(int argc, char** argv) {
   std::stringstream ub;
   ub << uf.rdbuf();
   std::vector<std::string> group, exclude;
-  std::string reference, chain_root, chain_tip;
+  std::string reference, chain_root, chain_tip, meshdir;
   std::vector<CollisionLinkConfig> col;
   std::map<std::string, double> state;
   std::vector<double> start;
@@ -39,6 +40,7 @@ int main(int argc, char** argv) {
     else if (key == "exclude") while (is >> w) exclude.push_back(w);
     else if (key == "start") { double v; while (is >> v) start.push_back(v); }
     else if (key == "padding") is >> scale >> padding;
+    else if (key == "meshdir") is >> meshdir;
     else if (key == "attach") { Attach at; is >> at.link >> at.type >> at.dims[0] >> at.dims[1] >> at.dims[2] >> at.pos[0] >> at.pos[1] >> at.pos[2] >> at.padding; attach.push_back(at); }
   }
   StompRobotModelUrdf m;
@@ -67,6 +69,23 @@ int main(int argc, char** argv) {
     std::printf("inertia %zu %.17g %.17g %.17g %.17g", s, li.mass, li.com[0], li.com[1], li.com[2]);
     for (double v : li.inertia) std::printf(" %.17g", v);
     std::printf("\n");
+  }
+  if (!meshdir.empty()) {
+    auto resolve = [&](const std::string& name) {
+      const std::string tag = "package://";
+      return meshdir + "/" + (name.compare(0, tag.size(), tag) == 0 ? name.substr(tag.size()) : name);
+    };
+    if (!loadLinkMeshes(m, resolve, err)) { std::printf("error %s\n", err.c_str()); return 1; }
+    for (const stomp_mesh_body& b : meshBodiesAtState(m, start, exclude, scale, padding)) {
+      std::printf("mesh %d", b.num_vertices);
+      for (double v : b.position) std::printf(" %.17g", v);
+      for (double v : b.orientation) std::printf(" %.17g", v);
+      std::printf(" %.17g %.17g", b.scale, b.padding);
+      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      for (int v = 0; v < b.num_vertices; ++v)
+        for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], b.vertices[v * 3 + k]); hi[k] = std::max(hi[k], b.vertices[v * 3 + k]); }
+      std::printf(" %.17g %.17g %.17g %.17g %.17g %.17g\n", lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
+    }
   }
   for (const stomp_body& b : bodiesAtState(m, start, exclude, scale, padding)) {
     std::printf("body %d %.17g %.17g %.17g", b.type, b.dimensions[0], b.dimensions[1], b.dimensions[2]);

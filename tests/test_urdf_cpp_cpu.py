@@ -144,8 +144,63 @@ def test_cpp_attached_object_collision_points(tmp_path):
 
 def test_cpp_urdf_errors(tmp_path):
     rc, rows = _run(tmp_path, URDF.replace("</robot>", ""), _spec())
-    assert rc == 1 and rows[0][0] == "error"
+    assert rc == 1 and any(r[0] == "error" for r in rows)
     rc, rows = _run(tmp_path, URDF, ["group nope_joint", "reference base_link"])
     assert rc == 1 and "not in the URDF" in " ".join(rows[0])
     rc, rows = _run(tmp_path, URDF, ["group " + " ".join(GROUP), "reference nowhere"])
     assert rc == 1 and "reference frame" in " ".join(rows[0])
+
+
+def _box_triangles(half):
+    hx, hy, hz = half
+    c = np.array([[sx * hx, sy * hy, sz * hz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)])
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+    return np.array([[c[q[0]], c[q[1]], c[q[2]]] for q in quads] + [[c[q[0]], c[q[2]], c[q[3]]] for q in quads])
+
+
+def test_cpp_mesh_link_geometry(tmp_path):
+    """<mesh> collision geometry: file name and scale from the URDF, vertices from a binary or an ASCII STL file
+    (loadLinkMeshes), placed at the joint state like the primitives (meshBodiesAtState) - the input of
+    stomp_engine_build_sdf_meshes, which voxelises the vertices' convex hull like bodies::ConvexMesh."""
+    import struct
+    tris = _box_triangles((0.2, 0.05, 0.06))
+    meshes = tmp_path / "meshes"
+    meshes.mkdir()
+    with open(meshes / "upper_arm.stl", "wb") as f:             # binary STL
+        f.write(b"binary stl".ljust(80, b" ") + struct.pack("<I", len(tris)))
+        for t in tris:
+            f.write(struct.pack("<12fH", 0.0, 0.0, 0.0, *t.ravel(), 0))
+    with open(meshes / "upper_arm_ascii.stl", "w") as f:        # ASCII STL
+        f.write("solid arm\n")
+        for t in tris:
+            f.write(" facet normal 0 0 0\n  outer loop\n" + "".join("   vertex %r %r %r\n" % tuple(float(x) for x in v) for v in t) + "  endloop\n endfacet\n")
+        f.write("endsolid arm\n")
+    urdf = _urdf_with_geometry()
+    start = [0.3, 0.2, -0.4, -1.0, 0.5, -0.6, 0.1]
+    rc, rows = _run(tmp_path, urdf, _spec(start=start) + ["meshdir " + str(meshes)])
+    assert rc == 0, rows
+    mesh = [[float(x) for x in r[1:]] for r in rows if r[0] == "mesh"]
+    assert len(mesh) == 1 and mesh[0][0] == 36
+    np.testing.assert_allclose(mesh[0][10:16], [-0.2, -0.05, -0.06, 0.2, 0.05, 0.06], rtol=1e-7)     # float32 file
+    assert mesh[0][8:10] == [1.0, 0.01]
+    # same link as the upper-arm cylinder (4th primitive): same orientation up to the cylinder's own rpy, origin 0.2 m behind it
+    arm = [[float(x) for x in b[1:]] for b in rows if b[0] == "body"][3]
+    def quat_to_rot(q):
+        x, y, z, w = q
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                         [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    Rlink = quat_to_rot(mesh[0][4:8])
+    np.testing.assert_allclose(np.array(mesh[0][1:4]) + Rlink @ np.array([0.2, 0.0, 0.0]), arm[4:7], atol=1e-14)
+    # the links of the excluded list carry no mesh either
+    rc, rows = _run(tmp_path, urdf, _spec(start=start, exclude=["r_upper_arm_link"]) + ["meshdir " + str(meshes)])
+    assert rc == 0 and not [r for r in rows if r[0] == "mesh"]
+    # ASCII file + URDF scale
+    scaled = urdf.replace('<mesh filename="package://upper_arm.stl"/>', '<mesh filename="package://upper_arm_ascii.stl" scale="2 1 0.5"/>')
+    rc, rows = _run(tmp_path, scaled, _spec(start=start) + ["meshdir " + str(meshes)])
+    assert rc == 0, rows
+    mesh = [[float(x) for x in r[1:]] for r in rows if r[0] == "mesh"]
+    np.testing.assert_allclose(mesh[0][10:16], [-0.4, -0.05, -0.03, 0.4, 0.05, 0.03], rtol=1e-15)
+    # a missing file is an error, not a silently empty body
+    rc, rows = _run(tmp_path, urdf, _spec(start=start) + ["meshdir " + str(tmp_path / "nowhere")])
+    assert rc == 1 and any(r[0] == "error" for r in rows)
