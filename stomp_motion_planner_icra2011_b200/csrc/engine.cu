@@ -727,17 +727,17 @@ int launch_update(Engine& e, int apply, bool fuse_extra_control) {
   const int groups = (e.D + dpc - 1) / dpc;
   // few CTAs (less than one per SM): wide CTAs, the latency of one CTA is the latency of the kernel
   const bool wide = e.wide_update && (long long)e.B * groups <= e.num_sms && a.dense_ms != nullptr;
-  if (wide) {
-    CUDA_TRY(cudaFuncSetAttribute(k_update<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  const bool direct = a.state != nullptr;
+  auto launch = [&](auto kernel, int threads) -> int {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     begin_launch(e);
-    k_update<512, 1><<<unsigned(e.B) * groups, 512, smem, e.ws>>>(a);
+    kernel<<<unsigned(e.B) * groups, threads, smem, e.ws>>>(a);
     return check_launch(e, "k_update");
-  }
-  CUDA_TRY(cudaFuncSetAttribute(k_update<128, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  begin_launch(e);
+  };
+  if (wide) return direct ? launch(k_update<512, 1, true>, 512) : launch(k_update<512, 1, false>, 512);
   const int tpb_max = 128;   // A/B on B200 (C2): 64 threads 0.163, 128: 0.097, 256: 0.150, 512: 0.244 ms
-  k_update<128, 7><<<unsigned(e.B) * groups, std::min(tpb_max, ((dpc * e.N + 31) / 32) * 32), smem, e.ws>>>(a);
-  return check_launch(e, "k_update");
+  const int threads = std::min(tpb_max, ((dpc * e.N + 31) / 32) * 32);
+  return direct ? launch(k_update<128, 7, true>, threads) : launch(k_update<128, 7, false>, threads);
 }
 
 // huge-R / sharded statistics (B == 1): one k_shard_stats launch per phase (partials, reduction over the chunks, optional

@@ -2098,7 +2098,9 @@ __device__ __forceinline__ double weighted_noise(const double* __restrict__ c, c
 // instead of 0.061).
 // kThreads / kMinBlocks: 128 x 7 for batches that fill the machine; 512 x 1 for small batches, where a CTA is alone on its SM and
 // the projection's 8-row tiles (13 for N = 99) each get a warp of their own instead of queueing four deep on four warps.
-template <int kThreads, int kMinBlocks>
+// kDirect: the costs are formed here as S + C[d] (UpdateArgs::state); a separate instantiation so that the other one keeps its
+// registers (as a run-time branch it cost the 7-CTA kernel 32 bytes of spills and 8 us at C2).
+template <int kThreads, int kMinBlocks, bool kDirect>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_update(UpdateArgs a) {
   extern __shared__ double smem[];
   const int N = a.N, R = a.R, D = a.D, G = a.dims_per_cta;
@@ -2120,14 +2122,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_update(UpdateArgs a) {
     const int dl = k / N, t = k - dl * N, d = d0 + dl;
     const size_t base = (size_t(b) * R * D + d) * N + t;
     double* prob = a.probabilities ? a.probabilities + base : nullptr;
-    const double* sp = a.state ? a.state + size_t(b) * R * N + t : nullptr;
     double v;
-    if (sp)
+    if (kDirect) {
+      const double* sp = a.state + size_t(b) * R * N + t;
       v = R <= 10 ? weighted_noise<10, true, true>(a.cumulative + base, sp, a.noise + base, rstride, size_t(N), R, prob)
                   : weighted_noise<5, false, true>(a.cumulative + base, sp, a.noise + base, rstride, size_t(N), R, prob);
-    else
+    } else {
       v = R <= 10 ? weighted_noise<10, true, false>(a.cumulative + base, nullptr, a.noise + base, rstride, 0, R, prob)
                   : weighted_noise<5, false, false>(a.cumulative + base, nullptr, a.noise + base, rstride, 0, R, prob);
+    }
     if (!dense) v *= a.band.proj_scale[t];      // the dense matrix carries the scaling
     u[dl * stride + t] = v;
   }
