@@ -143,10 +143,12 @@ struct Engine {
   bool cand_valid = false, cand_dirty = false;
   uint32_t cand_generation = 0;
   uint64_t cand_epoch = 0;
+  DevBuf<double> seg_hf, seg_hb;   // spike tables of k_generate_seg for seg_P segments
+  int seg_P = 0;
   bool wide_update = true;    // A/B switch (STOMP_NO_WIDE_UPDATE=1): k_update with 512-thread CTAs when there are few of them
   bool direct_update = true;  // A/B switch (STOMP_NO_DIRECT_UPDATE=1): k_update always reads k_cumulative's output
   bool dmma_update = true;    // A/B switch (STOMP_NO_DMMA=1): the dense projection runs as scalar DFMAs instead of DMMA tiles
-  int gen_mode = 0;   // 0: pick k_generate / k_generate_dense / k_generate_mma by batch shape; 1, 2, 3: always that one (A/B)
+  int gen_mode = 0;   // 0: pick by batch shape; 1 k_generate, 2 k_generate_dense, 3 k_generate_mma, 4 k_generate_seg: always that one (A/B)
   DevBuf<double> limit_min, limit_max;
   DevBuf<int> has_limits;
   DevBuf<unsigned char> nodes, spheres, sqrt_table, vox, vox_brick;
@@ -830,7 +832,7 @@ int generate_kind(const Engine& e, int r_count) {
   const double nvec = double(e.B) * r_count * e.D;
   const double est_band = 0.95e-6 * e.N;
   const double est_dense = 5.0e-6 + nvec * 12.0 * double(e.N) * e.N / 4.0e12;
-  int kind = e.gen_mode;
+  int kind = e.gen_mode == 4 ? 1 : e.gen_mode;   // 4 (seg) = the band formulation, always through k_generate_seg
   const bool mma_ok = mma_smem_bytes(e.N) <= 200 * 1024 && e.N <= 1024 && e.mma_a1.p != nullptr;
   if (kind == 0) kind = (e.N <= 1024 && est_dense < 0.5 * est_band) ? 2 : 1;
   if (kind == 3 && !mma_ok) kind = 1;
@@ -901,6 +903,31 @@ int launch_generate_range(Engine& e, const RolloutPlan& p, int r_begin, int r_co
     begin_launch(e);
     k_generate_dense<<<unsigned(nvec), 128, smem, e.ws>>>(a, e.dense_cinv.p, e.dense_ms.p);
     if (check_launch(e, pre ? "k_generate_ahead" : "k_generate")) return 1;
+  } else if (e.gen_mode == 4 && e.seg_P > 0 && !pre) {
+    // band solves split over seg_P time segments per vector: P x G warps per CTA, G groups of 32 vectors.  Measured on B200
+    // (C2, k_generate per iteration, both launches): 0.213 ms (P = 2, G = 2; 0.227 at P = 4) against 0.158 ms for one thread per
+    // vector.  ncu of the new-slot launch: 118.6 vs 107.2 us — the spike corrections, the extra scratch passes and the boundary
+    // chains cost 52 % more warp instructions (55.7 M vs 36.7 M) and the kernel is more issue- than latency-bound (issue slots
+    // 45 % busy at 16 warps / SM); at 80 registers / 3 CTAs per SM it spills (0.38 ms).  Only taken on request
+    // (STOMP_GENERATE=seg)
+    int G = std::max(1, 8 / e.seg_P);
+    if (const char* sg = getenv("STOMP_SEG_G")) G = std::max(1, std::min(8 / e.seg_P, atoi(sg)));
+    const int P = e.seg_P;
+    const long long nv = (long long)nvec;
+    const unsigned grid = unsigned((nv + 32 * G - 1) / (32 * G));
+    const size_t stride = size_t(grid) * 32 * G;
+    DevBuf<double>& scratch = e.ws == e.tail_stream ? e.gen_scratch2
+                              : (e.ws == e.pre_stream ? e.gen_scratch3 : (e.ws == e.cand_stream ? e.gen_scratch4 : e.gen_scratch));
+    if (scratch.n < stride * e.N) CUDA_TRY(scratch.alloc(stride * e.N));
+    a.scratch = scratch.p;
+    a.scratch_stride = stride;
+    a.segs = P; a.seg_hf = e.seg_hf.p; a.seg_hb = e.seg_hb.p;
+    const size_t smem = (size_t(e.N) * (16 + 12 + 1) + size_t(G) * P * 6 * 32 + size_t(P) * G * 2 * 32 * kTileLd) * 8;
+    if (smem > 220 * 1024) return fail("num_time_steps too large for the band tables of k_generate_seg");
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_generate_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    begin_launch(e);
+    k_generate_seg<<<grid, 32 * P * G, smem, e.ws>>>(a);
+    if (check_launch(e, "k_generate")) return 1;
   } else if (launch_generate(e, a)) {
     return 1;
   }
@@ -1524,6 +1551,50 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
     return 1;
   }
   {
+    // spike tables of k_generate_seg (kernels.cuh): response of a segment's rows to unit values of the neighbouring segment's
+    // six boundary entries, by the solves' own recurrences
+    const int N = e.N;
+    e.seg_P = std::max(2, std::min(8, N / 24));
+    if (const char* sp = getenv("STOMP_SEG_P")) e.seg_P = std::max(2, std::min(8, atoi(sp)));
+    if (N / e.seg_P >= 16) {
+      const int P = e.seg_P;
+      std::vector<double> hf(size_t(N) * 6, 0.0), hbk(size_t(N) * 6, 0.0);
+      for (int p = 0; p < P; ++p) {
+        const int s0 = seg_start(p, N, P), s1 = seg_start(p + 1, N, P);
+        if (p > 0)
+          for (int i = s0; i < s1; ++i)
+            for (int j = 0; j < 6; ++j) {
+              double acc = 0.0;
+              for (int k = 1; k <= 6; ++k) {
+                const int rr = i - k;
+                if (rr < 0) continue;
+                const double tv = rr >= s0 ? hf[size_t(rr) * 6 + j] : (s0 - 1 - rr == j ? 1.0 : 0.0);
+                acc -= fw[size_t(i) * 8 + k] * tv;
+              }
+              hf[size_t(i) * 6 + j] = acc;
+            }
+        if (p < P - 1)
+          for (int i = s1 - 1; i >= s0; --i)
+            for (int j = 0; j < 6; ++j) {
+              double acc = 0.0;
+              for (int k = 1; k <= 6; ++k) {
+                const int rr = i + k;
+                if (rr >= N) continue;
+                const double tv = rr < s1 ? hbk[size_t(rr) * 6 + j] : (rr - s1 == j ? 1.0 : 0.0);
+                acc -= bw[size_t(i) * 8 + k] * tv;
+              }
+              hbk[size_t(i) * 6 + j] = acc;
+            }
+      }
+      if (upload(e, e.seg_hf, hf.data(), hf.size()) || upload(e, e.seg_hb, hbk.data(), hbk.size())) {
+        stomp_engine_destroy(ep);
+        return 1;
+      }
+    } else {
+      e.seg_P = 0;
+    }
+  }
+  {
     // dense forms of the two solves for the small-batch kernel: C^-1 (column k = forward substitution of e_k) and R^-1 diag(s)
     const int N = e.N, hb = e.pm.chol.hb;
     std::vector<double> cinv(size_t(N) * N, 0.0), msd(size_t(N) * N, 0.0), x(N);
@@ -1559,7 +1630,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
     }
   }
   // A/B switches of the generation kernels: STOMP_GENERATE=band|dense forces one, STOMP_NO_DENSE=1 is "band"
-  if (const char* g = getenv("STOMP_GENERATE")) e.gen_mode = !strcmp(g, "band") ? 1 : !strcmp(g, "dense") ? 2 : !strcmp(g, "mma") ? 3 : 0;
+  if (const char* g = getenv("STOMP_GENERATE")) e.gen_mode = !strcmp(g, "band") ? 1 : !strcmp(g, "dense") ? 2 : !strcmp(g, "mma") ? 3 : !strcmp(g, "seg") ? 4 : 0;
   if (getenv("STOMP_NO_DENSE") && atoi(getenv("STOMP_NO_DENSE")) != 0) e.gen_mode = 1;
   if (getenv("STOMP_GRAPH")) e.graph_mode = atoi(getenv("STOMP_GRAPH")) != 0 ? 1 : 0;
   e.chain_probe = getenv("STOMP_CHAIN_PROBE") && atoi(getenv("STOMP_CHAIN_PROBE")) != 0;

@@ -293,6 +293,10 @@ struct GenArgs {
   const double* noise_scale; // [D] sigma_d * decay_d^(it-1)
   const double* eps_in;      // [B][R][D][N] injected noise (or caller noise when !mode_project)
   const double* params_prev; // [B][prev_stride][D][N] previous-iteration parameters (reuse gather)
+  // k_generate_seg: the band solves split over `segs` time segments per vector (spike tables, engine.cu)
+  int segs;
+  const double* seg_hf;      // [N][6] forward solve:  x_i = local_i + sum_j hf[i][j] x_{start-1-j}
+  const double* seg_hb;      // [N][6] backward solve: x_i = local_i + sum_j hb[i][j] x_{end+j}
   int prev_stride;           // rollouts per problem in params_prev (= R except in the candidate pass, where R counts candidates)
   const int* reuse_src;      // [B][R_reuse]
   double* noise;             // [B][R][D][N]
@@ -674,6 +678,368 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
             if (t == N - 1) {
 #pragma unroll
               for (int q = 0; q < kPad; ++q) cost += tc[kPad - 1 - q];
+            }
+            my_tE[k] = cost;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) w[j] = w[j + 1];
+            w[6] = nx[k];
+          }
+      }
+      warp_tile_store(tE, crow, c0, len, lane);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_generate_seg: k_generate with every band solve split over P time segments (P warps of the CTA; lane = vector, warp =
+// segment): an experiment against k_generate's one-thread-per-vector chains of ~4 N dependent steps (C2: 8 warps per SM, 11 %
+// of the warp slots).
+//
+// A banded triangular solve restricted to a segment needs only the six values next to the segment from its neighbour.  Each
+// segment first solves with those taken as zero (the LOCAL solution), the true first / last six values of the segments are
+// then fixed in a chain of P - 1 steps of 36 FMAs, and every row is corrected independently:
+//   x_i = local_i + sum_j H[i][j] X_j,   X = the neighbour's six final boundary values,
+// where H (the "spikes", host-computed in fp64 from the same band tables) is the response of the segment's rows to unit
+// boundary values.  The correction of one solve is folded into the pass that runs the next one:
+//   A1  backward local solve of C^T e = z (Philox)                                -> scratch (time-major)
+//   A2  boundary chain (backward)
+//   A3+B1  forward over the segment: e final, noise = sigma e, parameters; local forward solve of C w = s .* noise -> scratch
+//   B2  boundary chain (forward)
+//   B3+C1  backward: w final; local backward solve of C^T y = w                   -> scratch
+//   C2  boundary chain (backward)
+//   C3  y final, x = parameters + y                                              -> scratch;  CTA barrier
+//   D   control-cost stencils over [pads, x, pads] (neighbouring segments' x from the scratch)
+// Five passes over N / P steps instead of four over N.  Same linear maps as k_generate, evaluated in another order: the
+// results agree to rounding (test_dense_generation_kernels_match_the_band_solves), not bit for bit.
+// Measured slower than k_generate at every batch shape tried (engine.cu, launch_generate_range): opt-in, STOMP_GENERATE=seg.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSegBand = 6;
+#ifndef STOMP_SEG_MIN_BLOCKS
+#define STOMP_SEG_MIN_BLOCKS 2
+#endif
+// segment boundaries on multiples of the transposition chunk (aligned tiles, Philox pairs never split); the last one ends at N
+__host__ __device__ inline int seg_start(int seg, int N, int P) {
+  if (seg >= P) return N;
+  return int(((long long)seg * N / P + kChunk / 2) / kChunk) * kChunk;
+}
+
+template <bool kBackward>
+__device__ __forceinline__ void seg_chain(double* bnd, int seg, int P, int lane, const double* loc, const double* H, int row0, int row_step,
+                                          double* neighbour) {
+  // loc[m]: this segment's local boundary values (m = 0 nearest its own interior end ... see callers); bnd[seg][m][lane]
+  // receives the final ones.  kBackward: segment seg depends on seg + 1; else on seg - 1.  H row of boundary value m:
+  // H + (row0 + m * row_step) * 6.
+  for (int step = 0; step < P; ++step) {
+    const int turn = kBackward ? P - 1 - step : step;
+    if (seg == turn) {
+      const bool has = kBackward ? seg < P - 1 : seg > 0;
+      double fin[kSegBand];
+#pragma unroll
+      for (int m = 0; m < kSegBand; ++m) fin[m] = loc[m];
+      if (has) {
+        const double* nb = bnd + size_t(kBackward ? seg + 1 : seg - 1) * kSegBand * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < kSegBand; ++j) neighbour[j] = nb[j * 32];
+#pragma unroll
+        for (int m = 0; m < kSegBand; ++m) {
+          const double* h = H + size_t(row0 + m * row_step) * kSegBand;
+#pragma unroll
+          for (int j = 0; j < kSegBand; ++j) fin[m] = fma(h[j], neighbour[j], fin[m]);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < kSegBand; ++m) bnd[(size_t(seg) * kSegBand + m) * 32 + lane] = fin[m];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256, STOMP_SEG_MIN_BLOCKS) k_generate_seg(GenArgs a) {
+  extern __shared__ double smem[];
+  const int N = a.N;
+  const int lane = threadIdx.x & 31, P = a.segs, nwarps = blockDim.x >> 5, G = nwarps / P;   // G groups of 32 vectors per CTA
+  const int seg = (threadIdx.x >> 5) % P, grp = (threadIdx.x >> 5) / P;
+  double* sfw = smem;                        // [N][8]
+  double* sbw = sfw + N * 8;                 // [N][8]
+  double* shf = sbw + N * 8;                 // [N][6]
+  double* shb = shf + N * kSegBand;          // [N][6]
+  double* sscale = shb + N * kSegBand;       // [N]
+  double* bnd = sscale + N + size_t(grp) * P * kSegBand * 32;   // [G][P][6][32]: the boundary exchange of this vector group
+  double* tE = sscale + N + size_t(G) * P * kSegBand * 32 + size_t(threadIdx.x >> 5) * 2 * 32 * kTileLd;   // per-warp tiles
+  double* tT = tE + 32 * kTileLd;
+  for (int k = threadIdx.x; k < N * 8; k += blockDim.x) sfw[k] = a.band.fw[k], sbw[k] = a.band.bw[k];
+  for (int k = threadIdx.x; k < N * kSegBand; k += blockDim.x) shf[k] = a.seg_hf[k], shb[k] = a.seg_hb[k];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sscale[i] = a.band.proj_scale[i];
+  __syncthreads();
+
+  const int per_problem = a.r_count * a.D;
+  const long long nvec = (long long)a.B * per_problem;
+  const long long v = ((long long)blockIdx.x * G + grp) * 32 + lane;
+  const bool active = v < nvec;
+  int b = 0, r = 0, d = 0;
+  if (active) {
+    b = int(v / per_problem);
+    const int rem = int(v - (long long)b * per_problem);
+    r = rem / a.D;
+    d = rem - r * a.D;
+    r += a.r_begin;
+  }
+  const size_t row_off = ((size_t(b) * a.R + r) * a.D + d) * N;
+  const double* th_row = active ? a.theta + (size_t(b) * a.D + d) * N : nullptr;
+  double* wb = a.scratch + v;                 // time-major scratch: element i at wb[i * sstride]
+  const size_t sstride = a.scratch_stride;
+  const int s0 = seg_start(seg, N, P), s1 = seg_start(seg + 1, N, P);   // this warp's time segment [s0, s1)
+  const int seg_last_c0 = s0 + ((s1 - s0 - 1) / kChunk) * kChunk;
+  double* my_tE = tE + lane * kTileLd;
+  double* my_tT = tT + lane * kTileLd;
+  const bool is_new = r < a.R_gen;
+  const bool philox = active && is_new && !a.injected;
+  const bool has_next = seg < P - 1, has_prev = seg > 0;
+  double nxt[kSegBand], prv[kSegBand], loc[kSegBand];
+#pragma unroll
+  for (int j = 0; j < kSegBand; ++j) nxt[j] = prv[j] = 0.0;
+
+  // ---- A1: local backward solve of C^T e = z over the segment ------------------------------------------------------------
+  {
+    const uint64_t stream = (uint64_t(b) * uint64_t(a.rollouts_global) + uint64_t(a.rollout_id_offset + r)) * uint64_t(a.D) + d;
+    const uint32_t gen_iteration = a.iteration_ptr ? *a.iteration_ptr : a.iteration;
+    BandWindow bw;
+    if (philox) {
+      for (int c0 = seg_last_c0; c0 >= s0; c0 -= kChunk) {
+        const int len = min(kChunk, s1 - c0);
+        double z[kChunk];
+        {
+          const int p_lo = c0 >> 1, p_hi = (c0 + len - 1) >> 1;
+          for (int pr = p_lo; pr <= p_hi; ++pr) {
+            double z0, z1;
+            normal_pair(a.seed, stream, gen_iteration, uint32_t(pr), z0, z1);
+            const int i0 = 2 * pr - c0, i1 = i0 + 1;
+#pragma unroll
+            for (int k = 0; k < kChunk; ++k) {
+              if (k == i0) z[k] = z0;
+              if (k == i1) z[k] = z1;
+            }
+          }
+        }
+        double* wp = wb + size_t(c0) * sstride;
+#pragma unroll
+        for (int kk = 0; kk < kChunk; ++kk) {
+          const int k = kChunk - 1 - kk;
+          if (k < len) wp[size_t(k) * sstride] = bw.step(sbw + (c0 + k) * 8, z[k]);
+        }
+      }
+    }
+    loc[0] = bw.w1; loc[1] = bw.w2; loc[2] = bw.w3; loc[3] = bw.w4; loc[4] = bw.w5; loc[5] = bw.w6;   // e_local[s0 + m]
+  }
+  // ---- A2: the segments' true first six values, last segment first ---------------------------------------------------------
+  seg_chain<true>(bnd, seg, P, lane, loc, shb, s0, 1, nxt);
+  if (has_next) {
+#pragma unroll
+    for (int j = 0; j < kSegBand; ++j) nxt[j] = bnd[(size_t(seg + 1) * kSegBand + j) * 32 + lane];
+  }
+  __syncthreads();   // the exchange array is reused by the next chain
+
+  // ---- A3 + B1: noise and parameters; local forward solve of C w = s .* noise ------------------------------------------------
+  {
+    const double* src = nullptr;
+    if (active) {
+      if (!is_new) {
+        const int sidx = a.reuse_src[size_t(b) * (a.R - a.R_gen) + (r - a.R_gen)];
+        src = sidx >= 0 ? a.params_prev + ((size_t(b) * a.prev_stride + sidx) * a.D + d) * N : th_row;
+      } else if (a.injected) {
+        src = a.eps_in + row_off;
+      }
+    }
+    double* out_noise = active ? a.noise + row_off : nullptr;
+    double* out_params = active ? a.params + row_off : nullptr;
+    const double sg = active ? a.noise_scale[d] : 0.0;
+    BandWindow fwd;
+    for (int c0 = s0; c0 < s1; c0 += kChunk) {
+      const int len = min(kChunk, s1 - c0);
+      warp_tile_load2(tE, src, tT, th_row, c0, len, lane);
+      double* wp = wb + size_t(c0) * sstride;
+      double ev[kChunk];
+      if (philox) {
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k)
+          if (k < len) ev[k] = wp[size_t(k) * sstride];
+      }
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k)
+          if (k < len) {
+            const int t = c0 + k;
+            double eps, par;
+            if (philox) {
+              double e = ev[k];
+              if (has_next) {
+                const double* h = shb + t * kSegBand;
+#pragma unroll
+                for (int j = 0; j < kSegBand; ++j) e = fma(h[j], nxt[j], e);
+              }
+              eps = sg * e;
+              par = my_tT[k] + eps;
+            } else if (is_new) {      // injected noise
+              eps = my_tE[k];
+              par = my_tT[k] + eps;
+            } else {                  // reused rollout: noise = parameters - theta (policy_improvement.cpp:222)
+              par = my_tE[k];
+              eps = par - my_tT[k];
+            }
+            my_tE[k] = eps;
+            my_tT[k] = par;
+            if (a.mode_control) ev[k] = fwd.step(sfw + t * 8, sscale[t] * eps);
+          }
+        if (a.mode_control) {
+#pragma unroll
+          for (int k = 0; k < kChunk; ++k)
+            if (k < len) wp[size_t(k) * sstride] = ev[k];
+        }
+      }
+      warp_tile_store(tE, out_noise, c0, len, lane);
+      warp_tile_store(tT, out_params, c0, len, lane);
+    }
+    loc[0] = fwd.w1; loc[1] = fwd.w2; loc[2] = fwd.w3; loc[3] = fwd.w4; loc[4] = fwd.w5; loc[5] = fwd.w6;     // w_local[s1 - 1 - m]
+  }
+  if (!a.mode_control) return;
+  // ---- B2: the segments' true last six values, first segment first --------------------------------------------------------
+  seg_chain<false>(bnd, seg, P, lane, loc, shf, s1 - 1, -1, prv);
+  if (has_prev) {
+#pragma unroll
+    for (int j = 0; j < kSegBand; ++j) prv[j] = bnd[(size_t(seg - 1) * kSegBand + j) * 32 + lane];
+  }
+  __syncthreads();
+
+  // ---- B3 + C1: w final; local backward solve of C^T y = w --------------------------------------------------------------
+  {
+    BandWindow bwd;
+    if (active) {
+      for (int c0 = seg_last_c0; c0 >= s0; c0 -= kChunk) {
+        const int len = min(kChunk, s1 - c0);
+        double* wp = wb + size_t(c0) * sstride;
+        double wv[kChunk];
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k)
+          if (k < len) wv[k] = wp[size_t(k) * sstride];
+#pragma unroll
+        for (int kk = 0; kk < kChunk; ++kk) {
+          const int k = kChunk - 1 - kk;
+          if (k < len) {
+            const int t = c0 + k;
+            double w = wv[k];
+            if (has_prev) {
+              const double* h = shf + t * kSegBand;
+#pragma unroll
+              for (int j = 0; j < kSegBand; ++j) w = fma(h[j], prv[j], w);
+            }
+            wv[k] = bwd.step(sbw + t * 8, w);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k)
+          if (k < len) wp[size_t(k) * sstride] = wv[k];
+      }
+    }
+    loc[0] = bwd.w1; loc[1] = bwd.w2; loc[2] = bwd.w3; loc[3] = bwd.w4; loc[4] = bwd.w5; loc[5] = bwd.w6;     // y_local[s0 + m]
+  }
+  // ---- C2 ------------------------------------------------------------------------------------------------------------------
+  seg_chain<true>(bnd, seg, P, lane, loc, shb, s0, 1, nxt);
+  if (has_next) {
+#pragma unroll
+    for (int j = 0; j < kSegBand; ++j) nxt[j] = bnd[(size_t(seg + 1) * kSegBand + j) * 32 + lane];
+  }
+
+  // ---- C3: y final, x = parameters + y into the scratch ----------------------------------------------------------------------
+  {
+    const double* prow = active ? a.params + row_off : nullptr;
+    double* ytap = (active && a.noise_projected) ? a.noise_projected + row_off : nullptr;
+    for (int c0 = s0; c0 < s1; c0 += kChunk) {
+      const int len = min(kChunk, s1 - c0);
+      warp_tile_load(tT, prow, c0, len, lane);
+      if (active) {
+        double* wp = wb + size_t(c0) * sstride;
+        double yv[kChunk];
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k)
+          if (k < len) yv[k] = wp[size_t(k) * sstride];
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k)
+          if (k < len) {
+            double y = yv[k];
+            if (has_next) {
+              const double* h = shb + (c0 + k) * kSegBand;
+#pragma unroll
+              for (int j = 0; j < kSegBand; ++j) y = fma(h[j], nxt[j], y);
+            }
+            my_tE[k] = y;
+            wp[size_t(k) * sstride] = my_tT[k] + y;
+          }
+      }
+      if (a.noise_projected) warp_tile_store(tE, ytap, c0, len, lane);
+    }
+  }
+  __syncthreads();   // the stencils read the neighbouring segments' x
+
+  // ---- D: control-cost stencils over the padded series (covariant_trajectory_policy.cpp:228-255) -----------------------------
+  {
+    const int Nall = N + 2 * kPad;
+    double xs = 0.0, xg = 0.0;
+    if (active) { xs = a.pad_start[size_t(b) * a.D + d]; xg = a.pad_goal[size_t(b) * a.D + d]; }
+    auto xall = [&](int idx) -> double {
+      if (idx < 0 || idx >= Nall) return 0.0;   // dropped taps of the differentiation matrices
+      return idx < kPad ? xs : (idx >= kPad + N ? xg : wb[size_t(idx - kPad) * sstride]);
+    };
+    auto stencil_cost = [&](const double* w) -> double { return stencil_row_cost(a.st, a.control_weight, w); };
+    double w[7];
+    if (active) {
+      if (seg == P - 1) {       // the six trailing padded rows, added to the last free row in the order k_generate adds them
+        double tc[kPad];
+#pragma unroll
+        for (int q = 0; q < kPad; ++q) {
+          double ww[7];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) ww[j] = xall(kPad + N + q + j - 3);
+          tc[q] = stencil_cost(ww);
+        }
+#pragma unroll
+        for (int q = 0; q < kPad; ++q) loc[q] = tc[q];      // (loc / prv are free again: tail / head row costs)
+      }
+      if (seg == 0) {           // the six leading padded rows
+#pragma unroll
+        for (int q = 0; q < kPad; ++q) {
+          double ww[7];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) ww[j] = xall(q + j - 3);
+          prv[q] = stencil_cost(ww);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 7; ++j) w[j] = xall(s0 + kPad + j - 3);
+    }
+    double* crow = active ? a.control + row_off : nullptr;
+    for (int c0 = s0; c0 < s1; c0 += kChunk) {
+      const int len = min(kChunk, s1 - c0);
+      __syncwarp();
+      if (active) {
+        double nx[kChunk];
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k) {
+          const int f = c0 + k + 4;           // free index of the look-ahead element
+          nx[k] = 0.0;
+          if (k < len) nx[k] = f < N ? wb[size_t(f) * sstride] : (f < N + kPad ? xg : 0.0);
+        }
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k)
+          if (k < len) {
+            const int t = c0 + k;
+            double cost = stencil_cost(w);
+            if (t == 0) {
+#pragma unroll
+              for (int q = 0; q < kPad; ++q) cost += prv[q];
+            }
+            if (t == N - 1) {
+#pragma unroll
+              for (int q = 0; q < kPad; ++q) cost += loc[kPad - 1 - q];
             }
             my_tE[k] = cost;
 #pragma unroll

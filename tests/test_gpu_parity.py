@@ -1021,13 +1021,15 @@ def test_broad_phase_culling_is_exact(name, monkeypatch):
 
 
 @pytest.mark.parametrize("name,problems,kernel", [("tiny", 2, "dense"), ("C1", 1, "dense"), ("C5", 1, "dense"),
-                                                  ("tiny", 2, "mma"), ("C1", 5, "mma"), ("C5", 1, "mma")])
+                                                  ("tiny", 2, "mma"), ("C1", 5, "mma"), ("C5", 1, "mma"),
+                                                  ("tiny", 2, "seg"), ("C1", 5, "seg"), ("C1", 48, "seg"), ("C5", 1, "seg")])
 def test_dense_generation_kernels_match_the_band_solves(name, problems, kernel, monkeypatch):
     """Large batches take k_generate_mma (both maps as fp64 tensor-core GEMMs over tiles of 16 vectors; the tiny / 5-problem
     cases here leave the last tile partly empty).  Small batches take k_generate_dense (eps = sigma C^-T z and M eps as dense products) instead of k_generate's serial band
     solves: the same linear maps on the same Philox normals, so noise, parameters, M*noise and control costs agree to rounding
     — with the engine's own noise (iterations with and without reuse) and with injected noise.  C5 has 300 timesteps (several
-    passes of the CTA over time; R^-1 is worse conditioned, hence the looser bound)."""
+    passes of the CTA over time; R^-1 is worse conditioned, hence the looser bound).  "seg": k_generate_seg, the band solves split
+    over time segments per vector (local solves + boundary chain + spike corrections), what large batches run by default."""
     tol = 1e-7 if name == "C5" else 1e-9
     kw = dict(num_rollouts=12) if name == "C5" else {}
     sc = scenes.make_scenario(name, num_problems=problems, **kw)
