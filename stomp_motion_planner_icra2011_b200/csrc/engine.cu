@@ -68,8 +68,7 @@ struct Engine {
   int device = 0, num_sms = 148;
   cudaStream_t stream = nullptr, copy_stream = nullptr, tail_stream = nullptr;
   cudaStream_t ws = nullptr;   // stream the launch helpers currently enqueue on (stream or tail_stream)
-  cudaEvent_t ev_tail = nullptr, ev_upd = nullptr, ev_selected = nullptr, ev_cost = nullptr, ev_cum = nullptr;
-  bool cum_pending = false;        // ev_cum was recorded: the tail stream's k_cumulative still reads the control costs
+  cudaEvent_t ev_tail = nullptr, ev_upd = nullptr, ev_selected = nullptr, ev_cost = nullptr;
   // asynchronous result read-back (two requests in flight)
   cudaStream_t result_stream = nullptr;
   cudaEvent_t ev_snap_main[2] = {nullptr, nullptr}, ev_snap_tail[2] = {nullptr, nullptr}, ev_results[2] = {nullptr, nullptr};
@@ -113,7 +112,8 @@ struct Engine {
   // device buffers
   DevBuf<double> theta, pad_start, pad_goal;
   DevBuf<double> params[2], state[2];
-  DevBuf<double> noise, control, cumulative, totals;
+  DevBuf<double> noise, control[2], cumulative, totals;   // control[cur]: ping-pong like params / state (k_cumulative of iteration i
+                                                          // reads its control costs while iteration i + 1 already writes new ones)
   DevBuf<double> noise_projected, probabilities, clipped;      // taps (keep_intermediates)
   DevBuf<double> extra_state, extra_control, updates, noiseless_sum;
   DevBuf<double> eps_in2[2];   // injected noise, double buffered (async uploads overlap the previous iteration)
@@ -146,6 +146,8 @@ struct Engine {
   DevBuf<double> seg_hf, seg_hb;   // spike tables of k_generate_seg for seg_P segments
   int seg_P = 0;
   bool wide_update = true;    // A/B switch (STOMP_NO_WIDE_UPDATE=1): k_update with 512-thread CTAs when there are few of them
+  bool cumulative_stale = false;   // the last k_cumulative skipped the cumulative-cost array
+  int cum_placement = 0;      // A/B (STOMP_CUM_PLACEMENT=chain|late): where a large batch's k_cumulative runs when k_update is direct
   bool direct_update = true;  // A/B switch (STOMP_NO_DIRECT_UPDATE=1): k_update always reads k_cumulative's output
   bool dmma_update = true;    // A/B switch (STOMP_NO_DMMA=1): the dense projection runs as scalar DFMAs instead of DMMA tiles
   int gen_mode = 0;   // 0: pick by batch shape; 1 k_generate, 2 k_generate_dense, 3 k_generate_mma, 4 k_generate_seg: always that one (A/B)
@@ -208,10 +210,11 @@ struct Engine {
   }
   // statistics over rollouts: one CTA per (problem, dims) looping over R (small R, many problems), or the
   // two-stage partial reductions over rollout chunks (rollout sharding, or one problem with many rollouts)
-  // k_update forms S + C itself and k_cumulative moves off the critical path: pays while the iteration is a chain of short
-  // launches (C1 0.071 -> 0.065 ms); with a machine-filling batch the concurrent k_cumulative slows k_update by more than
-  // the chain saves (C2 0.476 -> 0.512 ms)
-  bool direct_now() const { return direct_update && !desc.use_cumulative_costs && small_batch(); }
+  // k_update forms S + C itself and k_cumulative (the totals of the next reuse selection, the cumulative-cost tap) leaves the
+  // critical path: C1 0.071 -> 0.065 ms.  Where it runs instead depends on the batch: beside k_update for small batches; for a
+  // machine-filling batch that costs more than it saves (C2 0.465 -> 0.500 ms: 10 240 small CTAs crowd k_update's single wave),
+  // so there it follows k_update on the tail stream, under the next iteration's k_generate (8 warps / SM)
+  bool direct_now() const { return direct_update && !desc.use_cumulative_costs; }
   // Small batches run a latency schedule (direct k_update, look-ahead generation, candidate pass + k_select_gather): their
   // iteration is a chain of short launches and the machine is mostly idle.  With a machine-filling batch the same work only
   // competes for the SMs (C2: look-ahead 0.476 -> 0.577 ms), so the throughput schedule stays.
@@ -264,7 +267,6 @@ int join_streams(Engine& e) {
   CUDA_TRY(cudaEventRecord(e.ev_tail, e.tail_stream));
   CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_tail, 0));
   e.tail_dirty = false;
-  e.cum_pending = false;   // the late k_cumulative precedes ev_tail on the tail stream
   return 0;
 }
 
@@ -503,7 +505,7 @@ GenArgs base_gen_args(Engine& e) {
   a.noise = e.noise.p;
   a.params = e.params[e.cur].p;
   a.noise_projected = e.noise_projected.p;
-  a.control = e.control.p;
+  a.control = e.control[e.cur].p;
   a.band = e.band_view();
   a.st = e.stencil();
   a.iteration_ptr = e.capturing ? e.dev_generation.p : nullptr;
@@ -687,12 +689,16 @@ int launch_cost_only(Engine& e, const double* params, size_t pstride, int n_roll
 
 int block_for(int N) { return std::min(1024, ((N + 31) / 32) * 32); }
 
-int launch_cumulative(Engine& e, int r_begin = 0, int r_count = -1) {
+// totals_only: k_update reads S and C itself (direct_now) and nobody asked for the cumulative-cost tap — the D N doubles per
+// rollout are not written (stomp_engine_get computes them on demand)
+int launch_cumulative(Engine& e, int r_begin = 0, int r_count = -1, bool totals_only = false) {
   if (r_count < 0) r_count = e.R - r_begin;
   if (r_count == 0) return 0;
   begin_launch(e);
   k_cumulative<<<unsigned(e.B) * r_count, block_for(e.N), 0, e.ws>>>(e.R, r_begin, r_count, e.D, e.N, e.desc.use_cumulative_costs,
-                                                                       e.state[e.cur].p, e.control.p, e.cumulative.p, e.totals.p);
+                                                                       e.state[e.cur].p, e.control[e.cur].p,
+                                                                       totals_only ? nullptr : e.cumulative.p, e.totals.p);
+  e.cumulative_stale = totals_only;
   return check_launch(e, "k_cumulative");
 }
 
@@ -711,7 +717,7 @@ int launch_update(Engine& e, int apply, bool fuse_extra_control) {
   a.cumulative = e.cumulative.p; a.noise = e.noise.p; a.probabilities = e.probabilities.p;
   // without the suffix sums a cumulative cost is just S + C[d]: k_update forms it itself (same addition, same bits) and does
   // not depend on k_cumulative, which the two-stream schedule then takes off the critical path
-  if (e.direct_now()) { a.state = e.state[e.cur].p; a.cumulative = e.control.p; }
+  if (e.direct_now()) { a.state = e.state[e.cur].p; a.cumulative = e.control[e.cur].p; }
   a.updates = e.updates.p; a.theta = e.theta.p; a.band = e.band_view();
   // the projection as a dense product (kernels.cuh) while the N x N matrix is a few hundred KB of L2-resident reads per CTA
   a.dense_ms = (e.dense_update && e.N <= 512) ? e.dense_ms.p : nullptr;
@@ -977,7 +983,7 @@ int launch_select_gather(Engine& e) {
   a.cand_noise = e.cand_noise.p; a.cand_control = e.cand_control.p; a.cand_y = e.noise_projected.p ? e.cand_y.p : nullptr;
   a.params_prev = e.params[1 - e.cur].p; a.theta = e.theta.p;
   a.state_prev = e.state[1 - e.cur].p; a.extra_state = e.extra_state.p;
-  a.noise = e.noise.p; a.control = e.control.p; a.params = e.params[e.cur].p; a.noise_projected = e.noise_projected.p;
+  a.noise = e.noise.p; a.control = e.control[e.cur].p; a.params = e.params[e.cur].p; a.noise_projected = e.noise_projected.p;
   a.state = e.state[e.cur].p;
   begin_launch(e);
   k_select_gather<<<unsigned(e.B) * e.Rre, 128, 0, e.ws>>>(a);
@@ -994,7 +1000,7 @@ int launch_finish_rollouts(Engine& e) {
   a.B = e.B; a.R = e.R; a.G = e.num_gen; a.D = e.D; a.N = e.N;
   a.theta = e.theta.p; a.pre_noise = e.pre_noise.p; a.pre_y = e.pre_y.p;
   a.pad_start = e.pad_start.p; a.pad_goal = e.pad_goal.p;
-  a.noise = e.noise.p; a.params = e.params[e.cur].p; a.control = e.control.p; a.noise_projected = e.noise_projected.p;
+  a.noise = e.noise.p; a.params = e.params[e.cur].p; a.control = e.control[e.cur].p; a.noise_projected = e.noise_projected.p;
   a.control_weight = 0.5 * e.control_cost_weight;
   a.st = e.stencil();
   const long long total = (long long)e.B * e.num_gen * e.D * e.N;
@@ -1156,7 +1162,13 @@ int iterate_once(Engine& e, int iteration_number) {
   RolloutPlan p;
   plan_rollouts(e, p);
   // k_update reads S and C itself (launch_update): k_cumulative leaves the main stream's chain
-  const bool late_cumulative = !e.huge_path() && e.direct_now();
+  // direct k_update, large batch: k_cumulative either stays where it was (lean: totals only) or follows k_update on the tail
+  const bool direct = !e.huge_path() && e.direct_now();
+  // (measured, same box: C2 old schedule 0.4652 ms, lean k_cumulative on the chain 0.4611, after the update 0.4672; C4 2.107 /
+  //  2.093 / 2.007 — with 420 spheres and 200 timesteps per rollout the cost kernels dwarf the generation it then overlaps)
+  const bool heavy_cost = (long long)e.K * e.N >= 20000;
+  const bool late_cumulative = direct && (e.small_batch() || e.cum_placement == 2 || (e.cum_placement == 0 && heavy_cost));
+  const bool totals_only = direct && !e.desc.keep_intermediates;
   const bool use_cand = p.reuse && late_cumulative && e.cand_valid && !e.capturing && e.cand_generation + 1 == e.generation &&
                         e.cand_epoch == e.config_epoch;
   e.cand_valid = false;
@@ -1175,7 +1187,7 @@ int iterate_once(Engine& e, int iteration_number) {
     // stream's path to it was ~330 us long, but nothing ordered the two: found when an experiment shortened that path.)
     CUDA_TRY(cudaEventRecord(e.ev_selected, e.tail_stream));
     if (launch_generate_range(e, p, e.num_gen, e.R - e.num_gen, true) || gather_reused_state(e) ||
-        (!late_cumulative && launch_cumulative(e, e.num_gen, e.R - e.num_gen))) {
+        (!late_cumulative && launch_cumulative(e, e.num_gen, e.R - e.num_gen, totals_only))) {
       e.ws = e.stream;
       return 1;
     }
@@ -1183,8 +1195,6 @@ int iterate_once(Engine& e, int iteration_number) {
   CUDA_TRY(cudaEventRecord(e.ev_tail, e.tail_stream));   // also covers the previous iteration's noise-less rollout
   if (e.chain_probe && p.reuse) CUDA_TRY(cudaEventRecord(e.probe_tail, e.tail_stream));
   e.ws = e.stream;
-  // the previous iteration's late k_cumulative (tail stream) reads the control costs this k_generate overwrites
-  if (e.cum_pending) { CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_cum, 0)); e.cum_pending = false; }
   // new rollouts: finish what the look-ahead pass prepared during the previous iteration, or generate them in one pass
   const bool use_pre = e.pre_valid && !p.injected && !e.capturing && e.pre_generation == e.generation &&
                        e.pre_iteration == iteration_number && e.pre_num_gen == e.num_gen && e.pre_epoch == e.config_epoch;
@@ -1207,7 +1217,7 @@ int iterate_once(Engine& e, int iteration_number) {
     CUDA_TRY(cudaEventRecord(e.ev_cost, e.stream));
   } else {
     if (p.reuse) CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_selected, 0));
-    if (launch_cumulative(e, 0, e.num_gen)) return 1;       // new slots; the reused slots' were done on the tail stream
+    if (launch_cumulative(e, 0, e.num_gen, totals_only)) return 1;       // new slots; the reused slots' were done on the tail stream
   }
   if (e.chain_probe && p.reuse) CUDA_TRY(cudaEventRecord(e.probe_main, e.stream));
   CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_tail, 0));
@@ -1216,12 +1226,11 @@ int iterate_once(Engine& e, int iteration_number) {
   CUDA_TRY(cudaEventRecord(e.ev_upd, e.stream));
   if (late_cumulative && candidates_possible(e) && launch_candidates(e)) return 1;
   if (late_cumulative) {
-    // Rollout::getCost() of every slot for the next reuse selection (and the cumulative-cost tap), beside k_update
+    // Rollout::getCost() of every slot for the next reuse selection (and the cumulative-cost tap): beside k_update (small
+    // batches) or after it (the control costs are double-buffered, so the next iteration's k_generate need not wait for it)
     e.ws = e.tail_stream;
-    CUDA_TRY(cudaStreamWaitEvent(e.tail_stream, e.ev_cost, 0));
-    if (launch_cumulative(e)) { e.ws = e.stream; return 1; }
-    CUDA_TRY(cudaEventRecord(e.ev_cum, e.tail_stream));
-    e.cum_pending = true;
+    CUDA_TRY(cudaStreamWaitEvent(e.tail_stream, e.small_batch() ? e.ev_cost : e.ev_upd, 0));
+    if (launch_cumulative(e, 0, -1, totals_only)) { e.ws = e.stream; return 1; }
     e.ws = e.stream;
   }
   if (e.chain_probe && p.reuse && (iteration_number % 16) == 0) {      // sampled: the read-back synchronises
@@ -1280,7 +1289,6 @@ int capture_iterations(Engine& e) {
   e.cur = cur0; e.num_gen = num_gen0; e.generation = gen0; e.extra_added = extra0; e.reused_next = reused0;
   e.launches = launches0; e.steady_iterations = steady0;
   e.tail_dirty = false;
-  e.cum_pending = false;
   e.ws = e.stream;
   if (rc || ce != cudaSuccess || !graph) {
     (void)cudaGetLastError();
@@ -1496,7 +1504,6 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   if ((c = cudaEventCreateWithFlags(&e.ev_pre, cudaEventDisableTiming)) != cudaSuccess ||
       (c = cudaEventCreateWithFlags(&e.ev_fin, cudaEventDisableTiming)) != cudaSuccess ||
       (c = cudaEventCreateWithFlags(&e.ev_cost, cudaEventDisableTiming)) != cudaSuccess ||
-      (c = cudaEventCreateWithFlags(&e.ev_cum, cudaEventDisableTiming)) != cudaSuccess ||
       (c = cudaEventCreateWithFlags(&e.ev_tail, cudaEventDisableTiming)) != cudaSuccess ||
       (c = cudaEventCreateWithFlags(&e.ev_upd, cudaEventDisableTiming)) != cudaSuccess ||
       (c = cudaEventCreateWithFlags(&e.ev_selected, cudaEventDisableTiming)) != cudaSuccess)
@@ -1518,7 +1525,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
 #define ALLOC(buf, n) if ((c = (buf).alloc(n)) != cudaSuccess) return bail(c, "cudaMalloc " #buf)
   ALLOC(e.theta, BDN); ALLOC(e.pad_start, size_t(e.B) * e.D); ALLOC(e.pad_goal, size_t(e.B) * e.D);
   ALLOC(e.params[0], BRDN); ALLOC(e.params[1], BRDN); ALLOC(e.state[0], BRN); ALLOC(e.state[1], BRN);
-  ALLOC(e.noise, BRDN); ALLOC(e.control, BRDN); ALLOC(e.cumulative, BRDN); ALLOC(e.totals, size_t(e.B) * (e.R + 1));
+  ALLOC(e.noise, BRDN); ALLOC(e.control[0], BRDN); ALLOC(e.control[1], BRDN); ALLOC(e.cumulative, BRDN); ALLOC(e.totals, size_t(e.B) * (e.R + 1));
   if (desc->keep_intermediates) { ALLOC(e.noise_projected, BRDN); ALLOC(e.probabilities, BRDN); ALLOC(e.clipped, BRDN); }
   ALLOC(e.extra_state, size_t(e.B) * e.N); ALLOC(e.extra_control, BDN); ALLOC(e.updates, BDN); ALLOC(e.noiseless_sum, size_t(e.B));
   ALLOC(e.reuse_src, size_t(e.B) * std::max(1, e.Rre)); ALLOC(e.collision_free, size_t(e.B) * (e.R + 1));
@@ -1641,6 +1648,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   e.dmma_update = !(getenv("STOMP_NO_DMMA") && atoi(getenv("STOMP_NO_DMMA")) != 0);
   e.direct_update = !(getenv("STOMP_NO_DIRECT_UPDATE") && atoi(getenv("STOMP_NO_DIRECT_UPDATE")) != 0);
   e.lookahead = !(getenv("STOMP_NO_LOOKAHEAD") && atoi(getenv("STOMP_NO_LOOKAHEAD")) != 0);
+  if (const char* cp = getenv("STOMP_CUM_PLACEMENT")) e.cum_placement = !strcmp(cp, "chain") ? 1 : !strcmp(cp, "late") ? 2 : 0;
   e.wide_update = !(getenv("STOMP_NO_WIDE_UPDATE") && atoi(getenv("STOMP_NO_WIDE_UPDATE")) != 0);
   if (const char* dm = getenv("STOMP_SMALL_BATCH_MAX")) e.small_max = atoll(dm);   // elements B R D N; 0: throughput schedule always
   e.split_cost = !(getenv("STOMP_NO_SPLIT_COST") && atoi(getenv("STOMP_NO_SPLIT_COST")) != 0);
@@ -1681,7 +1689,6 @@ int stomp_engine_destroy(void* h) {
     if (e->graph_exec[i]) cudaGraphExecDestroy(e->graph_exec[i]);
   if (e->ev_tail) cudaEventDestroy(e->ev_tail);
   if (e->ev_cost) cudaEventDestroy(e->ev_cost);
-  if (e->ev_cum) cudaEventDestroy(e->ev_cum);
   if (e->peers_open)
     for (int r = 0; r < e->desc.rollout_shard_world; ++r)
       if (r != e->desc.rollout_shard_rank && e->peer_base[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
@@ -2549,8 +2556,10 @@ int stomp_engine_get(void* h, int32_t field, void* out, size_t bytes) {
     case STOMP_FIELD_PARAMETERS: src = e.params[e.cur].p; need = BRDN * 8; break;
     case STOMP_FIELD_NOISE_PROJECTED: src = e.noise_projected.p; need = BRDN * 8; break;
     case STOMP_FIELD_STATE_COSTS: src = e.state[e.cur].p; need = size_t(e.B) * e.R * e.N * 8; break;
-    case STOMP_FIELD_CONTROL_COSTS: src = e.control.p; need = BRDN * 8; break;
-    case STOMP_FIELD_CUMULATIVE_COSTS: src = e.cumulative.p; need = BRDN * 8; break;
+    case STOMP_FIELD_CONTROL_COSTS: src = e.control[e.cur].p; need = BRDN * 8; break;
+    case STOMP_FIELD_CUMULATIVE_COSTS:
+      if (e.cumulative_stale && launch_cumulative(e)) return 1;   // the iteration only needed the totals: fill the array now
+      src = e.cumulative.p; need = BRDN * 8; break;
     case STOMP_FIELD_PROBABILITIES: src = e.probabilities.p; need = BRDN * 8; break;
     case STOMP_FIELD_UPDATES: src = e.updates.p; need = BDN * 8; break;
     case STOMP_FIELD_NOISELESS_COSTS: src = e.extra_state.p; need = size_t(e.B) * e.N * 8; break;

@@ -2299,7 +2299,7 @@ __global__ void k_cumulative(int R, int r_begin, int r_count, int D, int N, int 
         v = block_suffix_scan(t < N ? v : 0.0, swarp, carry, &next);
         carry = next;
       }
-      if (t < N) out[size_t(d) * N + t] = v;
+      if (t < N && cumulative) out[size_t(d) * N + t] = v;   // nullptr: only the totals are wanted
     }
   }
   // block reduce acc
