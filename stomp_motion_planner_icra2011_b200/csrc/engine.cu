@@ -147,6 +147,9 @@ struct Engine {
   int seg_P = 0;
   bool wide_update = true;    // A/B switch (STOMP_NO_WIDE_UPDATE=1): k_update with 512-thread CTAs when there are few of them
   bool cumulative_stale = false;   // the last k_cumulative skipped the cumulative-cost array
+  DevBuf<double> csum;             // [B][R][D] per-vector control-cost sums from k_generate (GenArgs::csum)
+  bool csum_new = false, csum_reused = false;   // ... valid for this iteration's new / reused slots
+  bool use_totals_kernel = true;   // A/B switch (STOMP_NO_TOTALS_KERNEL=1)
   int cum_placement = 0;      // A/B (STOMP_CUM_PLACEMENT=chain|late): where a large batch's k_cumulative runs when k_update is direct
   bool direct_update = true;  // A/B switch (STOMP_NO_DIRECT_UPDATE=1): k_update always reads k_cumulative's output
   bool dmma_update = true;    // A/B switch (STOMP_NO_DMMA=1): the dense projection runs as scalar DFMAs instead of DMMA tiles
@@ -691,13 +694,23 @@ int block_for(int N) { return std::min(1024, ((N + 31) / 32) * 32); }
 
 // totals_only: k_update reads S and C itself (direct_now) and nobody asked for the cumulative-cost tap — the D N doubles per
 // rollout are not written (stomp_engine_get computes them on demand)
-int launch_cumulative(Engine& e, int r_begin = 0, int r_count = -1, bool totals_only = false) {
+int launch_cumulative(Engine& e, int r_begin = 0, int r_count = -1, bool totals_only = false, bool keep_totals = false) {
   if (r_count < 0) r_count = e.R - r_begin;
   if (r_count == 0) return 0;
+  // the control costs of every slot in the range were summed by k_generate: only the state costs are left to add
+  const bool have_csum = (r_begin >= e.num_gen || e.csum_new) && (r_begin + r_count <= e.num_gen || e.csum_reused);
+  if (totals_only && e.use_totals_kernel && have_csum && !keep_totals) {
+    const long long num = (long long)e.B * r_count;
+    begin_launch(e);
+    k_totals<<<unsigned((num * 32 + 127) / 128), 128, 0, e.ws>>>(e.R, r_begin, r_count, e.D, e.N, num, e.state[e.cur].p, e.csum.p, e.totals.p);
+    e.cumulative_stale = true;
+    return check_launch(e, "k_totals");
+  }
   begin_launch(e);
   k_cumulative<<<unsigned(e.B) * r_count, block_for(e.N), 0, e.ws>>>(e.R, r_begin, r_count, e.D, e.N, e.desc.use_cumulative_costs,
                                                                        e.state[e.cur].p, e.control[e.cur].p,
-                                                                       totals_only ? nullptr : e.cumulative.p, e.totals.p);
+                                                                       totals_only ? nullptr : e.cumulative.p,
+                                                                       keep_totals ? nullptr : e.totals.p);
   e.cumulative_stale = totals_only;
   return check_launch(e, "k_cumulative");
 }
@@ -821,6 +834,7 @@ void plan_rollouts(Engine& e, RolloutPlan& p) {
   }
   p.injected = e.injected_pending;
   e.injected_pending = false;
+  e.csum_new = e.csum_reused = false;
   ++e.generation;   // the Philox "iteration" counter
 }
 
@@ -934,8 +948,14 @@ int launch_generate_range(Engine& e, const RolloutPlan& p, int r_begin, int r_co
     begin_launch(e);
     k_generate_seg<<<grid, 32 * P * G, smem, e.ws>>>(a);
     if (check_launch(e, "k_generate")) return 1;
-  } else if (launch_generate(e, a)) {
-    return 1;
+  } else {
+    const bool sums = !pre && !candidates && with_control && e.csum.p != nullptr;
+    if (sums) a.csum = e.csum.p;
+    if (launch_generate(e, a)) return 1;
+    if (sums) {      // which slots' control-cost sums this launch left behind (launch_cumulative)
+      if (r_begin < e.num_gen && r_begin == 0 && r_begin + r_count >= e.num_gen) e.csum_new = true;
+      if (r_begin + r_count == e.R && r_begin <= e.num_gen && e.num_gen < e.R) e.csum_reused = true;
+    }
   }
   if (uses_injection) CUDA_TRY(cudaEventRecord(e.ev_consumed[e.inject_pending_buf], e.ws));
   return 0;
@@ -1525,6 +1545,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
 #define ALLOC(buf, n) if ((c = (buf).alloc(n)) != cudaSuccess) return bail(c, "cudaMalloc " #buf)
   ALLOC(e.theta, BDN); ALLOC(e.pad_start, size_t(e.B) * e.D); ALLOC(e.pad_goal, size_t(e.B) * e.D);
   ALLOC(e.params[0], BRDN); ALLOC(e.params[1], BRDN); ALLOC(e.state[0], BRN); ALLOC(e.state[1], BRN);
+  ALLOC(e.csum, size_t(e.B) * e.R * e.D);
   ALLOC(e.noise, BRDN); ALLOC(e.control[0], BRDN); ALLOC(e.control[1], BRDN); ALLOC(e.cumulative, BRDN); ALLOC(e.totals, size_t(e.B) * (e.R + 1));
   if (desc->keep_intermediates) { ALLOC(e.noise_projected, BRDN); ALLOC(e.probabilities, BRDN); ALLOC(e.clipped, BRDN); }
   ALLOC(e.extra_state, size_t(e.B) * e.N); ALLOC(e.extra_control, BDN); ALLOC(e.updates, BDN); ALLOC(e.noiseless_sum, size_t(e.B));
@@ -1648,6 +1669,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   e.dmma_update = !(getenv("STOMP_NO_DMMA") && atoi(getenv("STOMP_NO_DMMA")) != 0);
   e.direct_update = !(getenv("STOMP_NO_DIRECT_UPDATE") && atoi(getenv("STOMP_NO_DIRECT_UPDATE")) != 0);
   e.lookahead = !(getenv("STOMP_NO_LOOKAHEAD") && atoi(getenv("STOMP_NO_LOOKAHEAD")) != 0);
+  e.use_totals_kernel = !(getenv("STOMP_NO_TOTALS_KERNEL") && atoi(getenv("STOMP_NO_TOTALS_KERNEL")) != 0);
   if (const char* cp = getenv("STOMP_CUM_PLACEMENT")) e.cum_placement = !strcmp(cp, "chain") ? 1 : !strcmp(cp, "late") ? 2 : 0;
   e.wide_update = !(getenv("STOMP_NO_WIDE_UPDATE") && atoi(getenv("STOMP_NO_WIDE_UPDATE")) != 0);
   if (const char* dm = getenv("STOMP_SMALL_BATCH_MAX")) e.small_max = atoll(dm);   // elements B R D N; 0: throughput schedule always
@@ -2558,7 +2580,7 @@ int stomp_engine_get(void* h, int32_t field, void* out, size_t bytes) {
     case STOMP_FIELD_STATE_COSTS: src = e.state[e.cur].p; need = size_t(e.B) * e.R * e.N * 8; break;
     case STOMP_FIELD_CONTROL_COSTS: src = e.control[e.cur].p; need = BRDN * 8; break;
     case STOMP_FIELD_CUMULATIVE_COSTS:
-      if (e.cumulative_stale && launch_cumulative(e)) return 1;   // the iteration only needed the totals: fill the array now
+      if (e.cumulative_stale && launch_cumulative(e, 0, -1, false, true)) return 1;   // the iteration only needed the totals: fill the array now
       src = e.cumulative.p; need = BRDN * 8; break;
     case STOMP_FIELD_PROBABILITIES: src = e.probabilities.p; need = BRDN * 8; break;
     case STOMP_FIELD_UPDATES: src = e.updates.p; need = BDN * 8; break;

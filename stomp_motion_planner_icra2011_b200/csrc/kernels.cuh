@@ -303,6 +303,8 @@ struct GenArgs {
   double* params;            // [B][R][D][N]  (extra: unused)
   double* noise_projected;   // optional tap
   double* control;           // [B][R][D][N]  (extra: [B][D][N])
+  double* csum;              // optional [B][R][D]: sum over t of the vector's control costs, in t order (k_generate only; feeds
+                             // k_totals, which then replaces k_cumulative's pass over the control costs)
   double* scratch;           // time-major [N][scratch_stride] work buffer
   size_t scratch_stride;     // >= number of vectors, multiple of the CTA size
   Band band;
@@ -654,6 +656,7 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
       }
     }
     double* crow = active ? a.control + row_off : nullptr;
+    double csum = 0.0;
     for (int c0 = 0; c0 < N; c0 += kChunk) {
       const int len = min(kChunk, N - c0);
       __syncwarp();
@@ -680,6 +683,7 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
               for (int q = 0; q < kPad; ++q) cost += tc[kPad - 1 - q];
             }
             my_tE[k] = cost;
+            csum += cost;
 #pragma unroll
             for (int j = 0; j < 6; ++j) w[j] = w[j + 1];
             w[6] = nx[k];
@@ -687,6 +691,7 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
       }
       warp_tile_store(tE, crow, c0, len, lane);
     }
+    if (active && a.csum && !a.extra) a.csum[(size_t(b) * a.R + r) * a.D + d] = csum;
   }
 }
 
@@ -2308,10 +2313,30 @@ __global__ void k_cumulative(int R, int r_begin, int r_count, int D, int N, int 
   for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
   if (lane == 0) sred[warp] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && totals) {
     double s = 0.0;
     for (int w = 0; w < nwarps; ++w) s += sred[w];
     totals[size_t(b) * (R + 1) + r] = s;
+  }
+}
+
+// k_totals: Rollout::getCost() when k_generate has already summed the control costs per vector (GenArgs::csum) and k_update
+// adds S + C itself: totals[b][r] = sum_t S[t] + sum_d csum[d], one warp per rollout — 1/8 of the bytes k_cumulative reads.
+__global__ void __launch_bounds__(128) k_totals(int R, int r_begin, int r_count, int D, int N, long long num, const double* __restrict__ state,
+                                                const double* __restrict__ csum, double* __restrict__ totals) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= num) return;
+  const int b = int(w / r_count), r = r_begin + int(w - (long long)b * r_count);
+  const double* S = state + (size_t(b) * R + r) * N;
+  double acc = 0.0;
+  for (int t = lane; t < N; t += 32) acc += S[t];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) {
+    const double* c = csum + (size_t(b) * R + r) * D;
+    for (int d = 0; d < D; ++d) acc += c[d];
+    totals[size_t(b) * (R + 1) + r] = acc;
   }
 }
 

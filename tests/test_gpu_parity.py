@@ -893,6 +893,35 @@ def test_pipelined_generation_is_bit_identical(name, problems, cumulative, keep,
     assert np.abs(a.get(_abi.FIELD_NOISE)).max() > 0
 
 
+def test_totals_from_partial_sums_match_k_cumulative(monkeypatch):
+    """Large batches without cumulative costs: k_generate leaves the sum of each vector's control costs behind and k_totals adds
+    the state costs (Rollout::getCost for the reuse ranking) instead of k_cumulative's pass over all control costs; k_update adds
+    S + C itself.  Same totals to rounding, the same ranking, hence bit-identical policies; the cumulative-cost tap is filled on
+    demand and leaves the totals alone."""
+    sc = scenes.make_scenario("C1", num_problems=160)
+    a = _engine(sc)
+    monkeypatch.setenv("STOMP_NO_TOTALS_KERNEL", "1")
+    b = _engine(sc)
+    monkeypatch.delenv("STOMP_NO_TOTALS_KERNEL")
+    monkeypatch.setenv("STOMP_NO_DIRECT_UPDATE", "1")
+    c = _engine(sc)
+    monkeypatch.delenv("STOMP_NO_DIRECT_UPDATE")
+    for eng in (a, b, c):
+        eng.run(1, 6)
+    ta, tb, tc = (e.get(_abi.FIELD_ROLLOUT_TOTAL_COSTS) for e in (a, b, c))
+    np.testing.assert_array_equal(tb, tc)
+    np.testing.assert_allclose(ta, tb, rtol=1e-13)
+    assert a.launch_count() == b.launch_count()                      # k_totals in place of k_cumulative, launch for launch
+    for f in (_abi.FIELD_THETA, _abi.FIELD_PARAMETERS, _abi.FIELD_STATE_COSTS, _abi.FIELD_CONTROL_COSTS, _abi.FIELD_NOISE):
+        np.testing.assert_array_equal(a.get(f), c.get(f))
+    cum_a, cum_c = a.get(_abi.FIELD_CUMULATIVE_COSTS), c.get(_abi.FIELD_CUMULATIVE_COSTS)     # filled on demand in `a`
+    np.testing.assert_array_equal(cum_a, cum_c)
+    np.testing.assert_array_equal(a.get(_abi.FIELD_ROLLOUT_TOTAL_COSTS), ta)                   # ... without touching the totals
+    for eng in (a, c):
+        eng.run(7, 3)
+    np.testing.assert_array_equal(a.get(_abi.FIELD_THETA), c.get(_abi.FIELD_THETA))
+
+
 def test_async_result_readback_pipeline():
     """request_results_async / wait_results: results of iteration i collected while iteration i+1 runs equal the
     synchronous read-back, with injected noise uploaded asynchronously as well (the bench's e2e loop)."""
