@@ -495,7 +495,7 @@ def run_engine(args):
     cost_ms, cost_n = eng.get_profile("k_cost")
     all_ms, all_n = eng.get_profile("")
     shares = {}
-    for kn in ("k_select_reuse", "k_generate", "k_gather_state", "k_cost", "k_cumulative", "k_update", "k_extra_total",
+    for kn in ("k_select_reuse", "k_generate", "k_gather_state", "k_cost", "k_cumulative", "k_totals", "k_update", "k_extra_total",
                "k_shard_stats", "k_finalize"):
         m, n = eng.get_profile(kn)
         if n:
@@ -508,7 +508,8 @@ def run_engine(args):
     BRDN8 = B * R * D * N * 8.0
     algo = {"k_generate": 4.0 * BRDN8,                      # per vector: read theta / previous parameters, write noise, parameters, control costs
             "k_cumulative": BRDN8 * (2.0 + 1.0 / D),        # read control costs + state costs, write cumulative costs
-            "k_update": 2.0 * BRDN8}                        # read cumulative costs + noise
+            "k_totals": B * R * (N + D) * 8.0,              # read state costs + per-vector control-cost sums
+            "k_update": 2.0 * BRDN8}                        # read cumulative (or control + state) costs + noise
     for kn, nbytes in algo.items():
         if kn in shares and shares[kn]["ms_per_iteration"] > 0:
             gbs = nbytes / (shares[kn]["ms_per_iteration"] * 1e-3) / 1e9

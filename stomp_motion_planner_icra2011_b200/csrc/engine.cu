@@ -1139,7 +1139,8 @@ int iterate_front(Engine& e, int iteration_number) {  // up to and including k_c
   if (launch_cost(e, e.params[e.cur].p, size_t(e.R) * e.D * e.N, e.num_gen, e.B, iteration_number == 1, e.state[e.cur].p,
                   size_t(e.R) * e.N, e.collision_free.p, e.R + 1, 0, e.clipped.p, nullptr, e.constraints_ok.p))
     return 1;
-  return launch_cumulative(e);
+  // like the two-stream schedule: only the totals when k_update adds S + C itself and nobody taps the cumulative costs
+  return launch_cumulative(e, 0, -1, !e.huge_path() && e.direct_now() && !e.desc.keep_intermediates);
 }
 
 int iterate_serial(Engine& e, int iteration_number) {
