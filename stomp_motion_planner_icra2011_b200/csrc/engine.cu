@@ -147,6 +147,7 @@ struct Engine {
   int seg_P = 0;
   bool wide_update = true;    // A/B switch (STOMP_NO_WIDE_UPDATE=1): k_update with 512-thread CTAs when there are few of them
   bool cumulative_stale = false;   // the last k_cumulative skipped the cumulative-cost array
+  bool totals_stale = false;       // ... or was not launched at all (huge path without reuse): Rollout::getCost() on demand
   DevBuf<double> csum;             // [B][R][D] per-vector control-cost sums from k_generate (GenArgs::csum)
   bool csum_new = false, csum_reused = false;   // ... valid for this iteration's new / reused slots
   bool use_totals_kernel = true;   // A/B switch (STOMP_NO_TOTALS_KERNEL=1)
@@ -692,11 +693,25 @@ int launch_cost_only(Engine& e, const double* params, size_t pstride, int n_roll
 
 int block_for(int N) { return std::min(1024, ((N + 31) / 32) * 32); }
 
+int launch_cumulative(Engine& e, int r_begin, int r_count, bool totals_only, bool keep_totals);
+// Huge / sharded path when the statistics kernels add S + C themselves and no tap wants the cumulative costs: without rollout
+// reuse nothing ranks the totals either, so nothing is launched (stomp_engine_get fills both on demand); with reuse only the
+// totals are produced.
+int launch_cumulative_huge(Engine& e, int r_begin, int r_count) {
+  const bool lean = e.direct_now() && !e.desc.keep_intermediates;
+  if (lean && e.Rre == 0) {
+    e.cumulative_stale = e.totals_stale = true;
+    return 0;
+  }
+  return launch_cumulative(e, r_begin, r_count, lean, false);
+}
+
 // totals_only: k_update reads S and C itself (direct_now) and nobody asked for the cumulative-cost tap — the D N doubles per
 // rollout are not written (stomp_engine_get computes them on demand)
 int launch_cumulative(Engine& e, int r_begin = 0, int r_count = -1, bool totals_only = false, bool keep_totals = false) {
   if (r_count < 0) r_count = e.R - r_begin;
   if (r_count == 0) return 0;
+  if (!keep_totals && r_begin == 0 && r_count == e.R) e.totals_stale = false;
   // the control costs of every slot in the range were summed by k_generate: only the state costs are left to add
   const bool have_csum = (r_begin >= e.num_gen || e.csum_new) && (r_begin + r_count <= e.num_gen || e.csum_reused);
   if (totals_only && e.use_totals_kernel && have_csum && !keep_totals) {
@@ -784,6 +799,7 @@ int launch_shard_stats(Engine& e, bool is_max, bool exchange, bool finalize, int
   a.do_finalize = fuse ? 1 : 0;
   a.apply = apply;
   a.cumulative = e.cumulative.p; a.noise = e.noise.p; a.minmax = e.minmax.p; a.part = e.part.p;
+  if (e.direct_now() && !e.probabilities.p) { a.state = e.state[e.cur].p; a.cumulative = e.control[e.cur].p; }   // S + C formed in the kernel
   a.out = is_max ? e.minmax.p : e.sums.p;
   a.counters = e.shard_counters.p;
   a.rank = e.desc.rollout_shard_rank; a.world = e.desc.rollout_shard_world;
@@ -1140,7 +1156,8 @@ int iterate_front(Engine& e, int iteration_number) {  // up to and including k_c
                   size_t(e.R) * e.N, e.collision_free.p, e.R + 1, 0, e.clipped.p, nullptr, e.constraints_ok.p))
     return 1;
   // like the two-stream schedule: only the totals when k_update adds S + C itself and nobody taps the cumulative costs
-  return launch_cumulative(e, 0, -1, !e.huge_path() && e.direct_now() && !e.desc.keep_intermediates);
+  if (e.huge_path()) return launch_cumulative_huge(e, 0, e.R);
+  return launch_cumulative(e, 0, -1, e.direct_now() && !e.desc.keep_intermediates);
 }
 
 int iterate_serial(Engine& e, int iteration_number) {
@@ -1208,7 +1225,8 @@ int iterate_once(Engine& e, int iteration_number) {
     // stream's path to it was ~330 us long, but nothing ordered the two: found when an experiment shortened that path.)
     CUDA_TRY(cudaEventRecord(e.ev_selected, e.tail_stream));
     if (launch_generate_range(e, p, e.num_gen, e.R - e.num_gen, true) || gather_reused_state(e) ||
-        (!late_cumulative && launch_cumulative(e, e.num_gen, e.R - e.num_gen, totals_only))) {
+        (!late_cumulative && (e.huge_path() ? launch_cumulative_huge(e, e.num_gen, e.R - e.num_gen)
+                                            : launch_cumulative(e, e.num_gen, e.R - e.num_gen, totals_only)))) {
       e.ws = e.stream;
       return 1;
     }
@@ -1238,7 +1256,8 @@ int iterate_once(Engine& e, int iteration_number) {
     CUDA_TRY(cudaEventRecord(e.ev_cost, e.stream));
   } else {
     if (p.reuse) CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_selected, 0));
-    if (launch_cumulative(e, 0, e.num_gen, totals_only)) return 1;       // new slots; the reused slots' were done on the tail stream
+    // new slots; the reused slots' were done on the tail stream
+    if (e.huge_path() ? launch_cumulative_huge(e, 0, e.num_gen) : launch_cumulative(e, 0, e.num_gen, totals_only)) return 1;
   }
   if (e.chain_probe && p.reuse) CUDA_TRY(cudaEventRecord(e.probe_main, e.stream));
   CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_tail, 0));
@@ -2588,7 +2607,9 @@ int stomp_engine_get(void* h, int32_t field, void* out, size_t bytes) {
     case STOMP_FIELD_NOISELESS_COSTS: src = e.extra_state.p; need = size_t(e.B) * e.N * 8; break;
     case STOMP_FIELD_COLLISION_FREE: src = e.collision_free.p; need = size_t(e.B) * (e.R + 1) * 4; break;
     case STOMP_FIELD_CONSTRAINTS_SATISFIED: src = e.constraints_ok.p; need = size_t(e.B) * (e.R + 1) * 4; break;
-    case STOMP_FIELD_ROLLOUT_TOTAL_COSTS: src = e.totals.p; need = size_t(e.B) * (e.R + 1) * 8; break;
+    case STOMP_FIELD_ROLLOUT_TOTAL_COSTS:
+      if (e.totals_stale && launch_cumulative(e, 0, -1, true)) return 1;   // nothing ranked them during the iteration: compute now
+      src = e.totals.p; need = size_t(e.B) * (e.R + 1) * 8; break;
     case STOMP_FIELD_CLIPPED_PARAMETERS: src = e.clipped.p; need = BRDN * 8; break;
     case STOMP_FIELD_BEST_TRAJECTORY: src = e.best_traj.p; need = BDN * 8; break;
     case STOMP_FIELD_NOISELESS_TRAJECTORY: src = e.extra_clipped.p; need = BDN * 8; break;

@@ -2940,6 +2940,8 @@ struct ShardStatsArgs {
   int do_exchange;            // peer-memory all-reduce of the result (world > 1, peers mapped)
   int do_finalize, apply;     // phase SUM: projection + update in the same launch
   const double* cumulative;   // [R][D*N]
+  const double* state;        // [R][N] or nullptr.  Given (no cumulative costs): cost = state[r][t] + cumulative[r][d][t] with
+                              // `cumulative` pointing at the CONTROL costs — k_cumulative's own addition, so that kernel is not needed
   const double* noise;        // [R][D*N]
   const double* minmax;       // [2][D*N] (phase SUM input)
   double* part;               // [chunks][2][D*N]
@@ -3001,11 +3003,16 @@ __global__ void __launch_bounds__(128) k_shard_stats(ShardStatsArgs a) {
   const int DN = a.D * a.N, chunk = blockIdx.y, nchunks = gridDim.y;
   const int r0 = chunk * a.rollouts_per_chunk, r1 = min(a.R, r0 + a.rollouts_per_chunk);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double* srow = a.state ? a.state + (i < DN ? i % a.N : 0) : nullptr;
+  auto cost_of = [&](int r) -> double {
+    const double c = a.cumulative[size_t(r) * DN + i];
+    return srow ? srow[size_t(r) * a.N] + c : c;
+  };
   if (i < DN) {
     if (a.is_max) {
       double mx = -1.0e300, mn = 1.0e300;
       for (int r = r0; r < r1; ++r) {
-        const double v = a.cumulative[size_t(r) * DN + i];
+        const double v = cost_of(r);
         mx = fmax(mx, v);
         mn = fmin(mn, v);
       }
@@ -3018,7 +3025,7 @@ __global__ void __launch_bounds__(128) k_shard_stats(ShardStatsArgs a) {
       const double h = -10.0 / denom;
       double se = 0.0, see = 0.0;
       for (int r = r0; r < r1; ++r) {
-        const double e = exp_weight(h * (a.cumulative[size_t(r) * DN + i] - mn));
+        const double e = exp_weight(h * (cost_of(r) - mn));
         se += e;
         see += e * a.noise[size_t(r) * DN + i];
       }
