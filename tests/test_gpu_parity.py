@@ -922,6 +922,26 @@ def test_totals_from_partial_sums_match_k_cumulative(monkeypatch):
     np.testing.assert_array_equal(a.get(_abi.FIELD_THETA), c.get(_abi.FIELD_THETA))
 
 
+def test_huge_path_fills_totals_and_cumulative_costs_on_demand():
+    """One problem with many rollouts and no reuse (C5 / C3 shape): the chunked statistics add S + C themselves and nothing ranks
+    Rollout::getCost(), so k_cumulative is not launched; stomp_engine_get computes the totals and the cumulative costs when asked.
+    Same policy bit for bit as the engine that keeps every intermediate, same cumulative costs, totals to rounding."""
+    sc = scenes.make_scenario("tiny", num_problems=1, num_rollouts=160)
+    sc.num_reused_rollouts = 0
+    a, b = _engine(sc, keep_intermediates=0), _engine(sc, keep_intermediates=1)
+    for eng in (a, b):
+        eng.run(1, 4)
+    assert a.launch_count() < b.launch_count()                      # no k_cumulative (and no k_probabilities) in `a`
+    np.testing.assert_array_equal(a.get(_abi.FIELD_THETA), b.get(_abi.FIELD_THETA))
+    np.testing.assert_allclose(a.get(_abi.FIELD_ROLLOUT_TOTAL_COSTS)[:, :160], b.get(_abi.FIELD_ROLLOUT_TOTAL_COSTS)[:, :160], rtol=1e-13)
+    np.testing.assert_array_equal(a.get(_abi.FIELD_CUMULATIVE_COSTS), b.get(_abi.FIELD_CUMULATIVE_COSTS))
+    for eng in (a, b):
+        eng.run(5, 2)
+    np.testing.assert_array_equal(a.get(_abi.FIELD_THETA), b.get(_abi.FIELD_THETA))
+    ors = _oracles(sc)
+    assert np.isfinite(a.get(_abi.FIELD_ROLLOUT_TOTAL_COSTS)[:, :160]).all() and len(ors) == 1
+
+
 def test_async_result_readback_pipeline():
     """request_results_async / wait_results: results of iteration i collected while iteration i+1 runs equal the
     synchronous read-back, with injected noise uploaded asynchronously as well (the bench's e2e loop)."""
