@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -140,7 +141,15 @@ struct Engine {
   cudaEvent_t ev_cand = nullptr;
   DevBuf<double> cand_noise, cand_control, cand_params, cand_y, gen_scratch4;
   DevBuf<int> cand_map;
+  std::vector<double> scale_host, pre_scale_host;      // noise scales of this / the look-ahead iteration (launch arguments)
+  std::map<const void*, size_t> smem_optin;
+  bool scales_in_args = false;     // A/B switch (STOMP_SCALES_IN_ARGS=1): measured slower, see set_noise_scale
   bool cand_valid = false, cand_dirty = false;
+  // small batches: k_extra_total (and optimize's k_track_best) run on cand_stream beside the tail stream's chain
+  cudaEvent_t ev_nl = nullptr, ev_extra = nullptr;
+  bool extra_dirty = false;        // ev_extra was recorded: the noise-less rollout's totals / bookkeeping may still be in flight
+  bool extra_offchain = false;     // ... in the iteration just enqueued
+  bool offchain_extra = true;      // A/B switch (STOMP_NO_OFFCHAIN_EXTRA=1)
   uint32_t cand_generation = 0;
   uint64_t cand_epoch = 0;
   DevBuf<double> seg_hf, seg_hb;   // spike tables of k_generate_seg for seg_P segments
@@ -266,6 +275,10 @@ int join_streams(Engine& e) {
   if (e.cand_dirty) {
     CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_cand, 0));
     e.cand_dirty = false;
+  }
+  if (e.extra_dirty) {
+    CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_extra, 0));
+    e.extra_dirty = false;
   }
   if (!e.tail_dirty) return 0;
   CUDA_TRY(cudaEventRecord(e.ev_tail, e.tail_stream));
@@ -468,6 +481,18 @@ int ensure_cull(Engine& e) {
 
 // ---- kernel launch helpers ----------------------------------------------------------------------
 
+// dynamic shared memory opt-in of a kernel, once per size (cudaFuncSetAttribute costs a microsecond per call)
+template <typename K>
+int ensure_smem(Engine& e, K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return 0;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  auto it = e.smem_optin.find(key);
+  if (it != e.smem_optin.end() && it->second >= bytes) return 0;
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+  e.smem_optin[key] = bytes;
+  return 0;
+}
+
 int launch_generate(Engine& e, GenArgs a) {
   const int N = e.N, tpb = 128;
   if (a.r_count == 0 && !a.extra) { a.r_begin = 0; a.r_count = a.R; }
@@ -502,6 +527,10 @@ GenArgs base_gen_args(Engine& e) {
   a.rollouts_global = int64_t(e.desc.rollout_shard_world) * e.R;
   a.theta = e.theta.p; a.pad_start = e.pad_start.p; a.pad_goal = e.pad_goal.p;
   a.noise_scale = e.noise_scale.p;
+  if (e.scales_in_args && e.D <= kMaxScaleArgs && !e.capturing && int(e.scale_host.size()) == e.D) {
+    a.scale_by_value = 1;
+    for (int d = 0; d < e.D; ++d) a.scale_v[d] = e.scale_host[d];
+  }
   a.eps_in = e.eps_in2[e.inject_pending_buf].p;
   a.params_prev = e.params[1 - e.cur].p;
   a.prev_stride = e.R;
@@ -540,7 +569,7 @@ int launch_cost_k(Engine& e, CostArgs<Real>& a, int num_problems) {
     const size_t smem1 = smem_for(1, t1) + size_t(t1) * e.K * 32 * sizeof(Real);
     if (t1 * kSplitGroups * 32 <= kSplitMaxThreads && smem1 <= 200 * 1024) {
       auto ks = k_cost<Real, false, kVox, false, false, kCull, true>;
-      if (smem1 > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
+      if (ensure_smem(e, ks, smem1)) return 1;
       a.pack = 1;
       a.tiles_per_job = t1;
       begin_launch(e);
@@ -554,7 +583,7 @@ int launch_cost_k(Engine& e, CostArgs<Real>& a, int num_problems) {
   const size_t smem = smem_for(pack, warps);
   if (smem > 220 * 1024) return fail("trajectory + robot tables exceed shared memory");
   auto kern = k_cost<Real, kDebug, kVox, kCons, kTri, kCull>;
-  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  if (ensure_smem(e, kern, smem)) return 1;
   a.pack = pack;
   a.tiles_per_job = tiles;
   const int njobs = (a.total_rollouts + pack - 1) / pack;
@@ -765,7 +794,7 @@ int launch_update(Engine& e, int apply, bool fuse_extra_control) {
   const bool wide = e.wide_update && (long long)e.B * groups <= e.num_sms && a.dense_ms != nullptr;
   const bool direct = a.state != nullptr;
   auto launch = [&](auto kernel, int threads) -> int {
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    if (ensure_smem(e, kernel, 220 * 1024)) return 1;
     begin_launch(e);
     kernel<<<unsigned(e.B) * groups, threads, smem, e.ws>>>(a);
     return check_launch(e, "k_update");
@@ -829,7 +858,12 @@ int launch_finalize(Engine& e, int apply) {
 
 // ---- PolicyImprovement steps ----------------------------------------------------------------------
 
+// the iteration's noise scales: uploaded on the launching stream.  Handing them to the kernels in the launch arguments instead
+// (STOMP_SCALES_IN_ARGS=1: no copy-engine hop on the chain) is SLOWER — C2 0.450 -> 0.481 ms, C1 47 -> 54 us per iteration, as in
+// round 1: the hop after k_update happens to pace the main stream against the tail stream favourably
 int set_noise_scale(Engine& e, const double* scale) {
+  e.scale_host.assign(scale, scale + e.D);
+  if (e.scales_in_args && e.D <= kMaxScaleArgs && !e.capturing) return 0;
   return upload(e, e.noise_scale, scale, size_t(e.D));
 }
 
@@ -895,6 +929,12 @@ int launch_generate_range(Engine& e, const RolloutPlan& p, int r_begin, int r_co
     a.theta = nullptr; a.params = nullptr; a.control = nullptr; a.params_prev = nullptr; a.reuse_src = nullptr; a.eps_in = nullptr;
     a.noise = e.pre_noise.p; a.noise_projected = e.pre_y.p;
     a.noise_scale = e.pre_scale.p;
+    if (e.scales_in_args && e.D <= kMaxScaleArgs && int(e.pre_scale_host.size()) == e.D) {
+      a.scale_by_value = 1;
+      for (int d = 0; d < e.D; ++d) a.scale_v[d] = e.pre_scale_host[d];
+    } else {
+      a.scale_by_value = 0;
+    }
     a.iteration_ptr = nullptr;
   }
   if (candidates) {
@@ -1019,6 +1059,7 @@ int launch_select_gather(Engine& e) {
   a.cand_noise = e.cand_noise.p; a.cand_control = e.cand_control.p; a.cand_y = e.noise_projected.p ? e.cand_y.p : nullptr;
   a.params_prev = e.params[1 - e.cur].p; a.theta = e.theta.p;
   a.state_prev = e.state[1 - e.cur].p; a.extra_state = e.extra_state.p;
+  a.extra_control = e.extra_control.p;
   a.noise = e.noise.p; a.control = e.control[e.cur].p; a.params = e.params[e.cur].p; a.noise_projected = e.noise_projected.p;
   a.state = e.state[e.cur].p;
   begin_launch(e);
@@ -1067,7 +1108,9 @@ int launch_lookahead(Engine& e, int next_iteration) {
   std::vector<double> scale(e.D);
   for (int d = 0; d < e.D; ++d) scale[d] = e.noise_stddev[d] * std::pow(e.noise_decay[d], next_iteration - 1);
   CUDA_TRY(cudaStreamWaitEvent(e.pre_stream, e.ev_fin, 0));
-  CUDA_TRY(cudaMemcpyAsync(e.pre_scale.p, scale.data(), size_t(e.D) * 8, cudaMemcpyHostToDevice, e.pre_stream));
+  e.pre_scale_host = scale;
+  if (!e.scales_in_args || e.D > kMaxScaleArgs)
+    CUDA_TRY(cudaMemcpyAsync(e.pre_scale.p, scale.data(), size_t(e.D) * 8, cudaMemcpyHostToDevice, e.pre_stream));
   RolloutPlan np;
   e.ws = e.pre_stream;
   const int rc = launch_generate_range(e, np, 0, G, true, true);
@@ -1125,8 +1168,11 @@ int step_improve(Engine& e, int apply) {
   return launch_update(e, apply, false);
 }
 
-int step_extra(Engine& e, bool run_cost, int iteration_number, bool have_control = false) {
+int step_extra(Engine& e, bool run_cost, int iteration_number, bool have_control = false, bool offchain = false) {
+  e.extra_offchain = false;
   if (run_cost) {
+    // the previous noise-less rollout's k_extra_total / k_track_best (cand_stream) read what this one overwrites
+    if (e.extra_dirty) CUDA_TRY(cudaStreamWaitEvent(e.ws, e.ev_extra, 0));
     if (launch_cost(e, e.theta.p, size_t(e.D) * e.N, 1, e.B, iteration_number == 1, e.extra_state.p, size_t(e.N),
                     e.collision_free.p, e.R + 1, e.R, e.extra_clipped.p, nullptr, e.constraints_ok.p))
       return 1;
@@ -1138,9 +1184,21 @@ int step_extra(Engine& e, bool run_cost, int iteration_number, bool have_control
     a.control_weight = 0.5 * e.control_cost_weight;
     if (launch_generate(e, a)) return 1;
   }
+  cudaStream_t back = e.ws;
+  if (offchain) {      // the next k_select_gather sums the noise-less rollout's total itself: nothing on this stream waits for it
+    CUDA_TRY(cudaEventRecord(e.ev_nl, e.ws));
+    CUDA_TRY(cudaStreamWaitEvent(e.cand_stream, e.ev_nl, 0));
+    e.ws = e.cand_stream;
+  }
   begin_launch(e);
   k_extra_total<<<e.B, 128, 0, e.ws>>>(e.R, e.D, e.N, e.extra_state.p, e.extra_control.p, e.totals.p, e.noiseless_sum.p);
-  if (check_launch(e, "k_extra_total")) return 1;
+  const int rc = check_launch(e, "k_extra_total");
+  if (offchain && !rc) {
+    CUDA_TRY(cudaEventRecord(e.ev_extra, e.cand_stream));
+    e.extra_dirty = e.extra_offchain = true;
+  }
+  e.ws = back;
+  if (rc) return 1;
   e.extra_added = true;
   return 0;
 }
@@ -1219,6 +1277,7 @@ int iterate_once(Engine& e, int iteration_number) {
   } else if (p.reuse) {
     e.ws = e.tail_stream;
     if (e.cand_dirty) { CUDA_TRY(cudaStreamWaitEvent(e.tail_stream, e.ev_cand, 0)); e.cand_dirty = false; }   // a discarded pass
+    if (e.extra_dirty) CUDA_TRY(cudaStreamWaitEvent(e.tail_stream, e.ev_extra, 0));   // k_select_reuse reads totals[R]
     if (launch_select(e)) { e.ws = e.stream; return 1; }
     // k_select_reuse ranks the PREVIOUS iteration's Rollout::getCost() values; this iteration's k_cumulative on the main
     // stream overwrites the new slots' entries of that array and must not overtake it.  (It never did while the main
@@ -1287,7 +1346,7 @@ int iterate_once(Engine& e, int iteration_number) {
   }
   e.ws = e.tail_stream;
   CUDA_TRY(cudaStreamWaitEvent(e.tail_stream, e.ev_upd, 0));
-  const int rc = step_extra(e, true, iteration_number, !huge);
+  const int rc = step_extra(e, true, iteration_number, !huge, e.offchain_extra && late_cumulative && candidates_possible(e));
   e.tail_dirty = true;
   e.ws = e.stream;
   if (p.reuse || e.Rre == 0) ++e.steady_iterations;
@@ -1540,7 +1599,10 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   if ((c = cudaStreamCreateWithFlags(&e.tail_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
   if ((c = cudaStreamCreateWithFlags(&e.pre_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
   if ((c = cudaStreamCreateWithFlags(&e.cand_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(c, "cudaStreamCreate");
-  if ((c = cudaEventCreateWithFlags(&e.ev_cand, cudaEventDisableTiming)) != cudaSuccess) return bail(c, "cudaEventCreate");
+  if ((c = cudaEventCreateWithFlags(&e.ev_cand, cudaEventDisableTiming)) != cudaSuccess ||
+      (c = cudaEventCreateWithFlags(&e.ev_nl, cudaEventDisableTiming)) != cudaSuccess ||
+      (c = cudaEventCreateWithFlags(&e.ev_extra, cudaEventDisableTiming)) != cudaSuccess)
+    return bail(c, "cudaEventCreate");
   if ((c = cudaEventCreateWithFlags(&e.ev_pre, cudaEventDisableTiming)) != cudaSuccess ||
       (c = cudaEventCreateWithFlags(&e.ev_fin, cudaEventDisableTiming)) != cudaSuccess ||
       (c = cudaEventCreateWithFlags(&e.ev_cost, cudaEventDisableTiming)) != cudaSuccess ||
@@ -1689,6 +1751,8 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   e.dmma_update = !(getenv("STOMP_NO_DMMA") && atoi(getenv("STOMP_NO_DMMA")) != 0);
   e.direct_update = !(getenv("STOMP_NO_DIRECT_UPDATE") && atoi(getenv("STOMP_NO_DIRECT_UPDATE")) != 0);
   e.lookahead = !(getenv("STOMP_NO_LOOKAHEAD") && atoi(getenv("STOMP_NO_LOOKAHEAD")) != 0);
+  e.scales_in_args = getenv("STOMP_SCALES_IN_ARGS") && atoi(getenv("STOMP_SCALES_IN_ARGS")) != 0;
+  e.offchain_extra = !(getenv("STOMP_NO_OFFCHAIN_EXTRA") && atoi(getenv("STOMP_NO_OFFCHAIN_EXTRA")) != 0);
   e.use_totals_kernel = !(getenv("STOMP_NO_TOTALS_KERNEL") && atoi(getenv("STOMP_NO_TOTALS_KERNEL")) != 0);
   if (const char* cp = getenv("STOMP_CUM_PLACEMENT")) e.cum_placement = !strcmp(cp, "chain") ? 1 : !strcmp(cp, "late") ? 2 : 0;
   e.wide_update = !(getenv("STOMP_NO_WIDE_UPDATE") && atoi(getenv("STOMP_NO_WIDE_UPDATE")) != 0);
@@ -1719,6 +1783,8 @@ int stomp_engine_destroy(void* h) {
   if (e->pre_stream) { cudaStreamSynchronize(e->pre_stream); cudaStreamDestroy(e->pre_stream); }
   if (e->cand_stream) { cudaStreamSynchronize(e->cand_stream); cudaStreamDestroy(e->cand_stream); }
   if (e->ev_cand) cudaEventDestroy(e->ev_cand);
+  if (e->ev_nl) cudaEventDestroy(e->ev_nl);
+  if (e->ev_extra) cudaEventDestroy(e->ev_extra);
   if (e->ev_pre) cudaEventDestroy(e->ev_pre);
   if (e->ev_fin) cudaEventDestroy(e->ev_fin);
   if (e->result_stream) { cudaStreamSynchronize(e->result_stream); cudaStreamDestroy(e->result_stream); }
@@ -2496,11 +2562,13 @@ int stomp_engine_optimize(void* h, int32_t max_iterations, int32_t max_after_cf,
   for (; it < max_iterations; ++it) {
     if (iterate_once(e, it + 1)) return 1;
     if (e.tail_dirty) e.ws = e.tail_stream;   // the bookkeeping follows the noise-less rollout on its stream
+    if (e.extra_offchain) e.ws = e.cand_stream;   // ... or k_extra_total, where that runs beside the chain
     begin_launch(e);
     k_track_best<<<e.B, 128, 0, e.ws>>>(it, max_after_cf, e.D * e.N, e.R + 1, e.R, e.noiseless_sum.p, e.collision_free.p,
                                             e.constraints_ok.p, e.extra_clipped.p, reinterpret_cast<TrackState*>(e.track_state.p), e.best_cost.p,
                                             e.best_traj.p, want_log ? e.cost_log.p : nullptr, e.B, e.num_done.p);
     if (check_launch(e, "k_track_best")) return 1;
+    if (e.extra_offchain) CUDA_TRY(cudaEventRecord(e.ev_extra, e.cand_stream));
     e.ws = e.stream;
     if ((it + 1) % check_every == 0 && it + 1 < max_iterations) {
       int done = 0;
@@ -2557,6 +2625,7 @@ int stomp_engine_request_results_async(void* h, double* theta, double* noiseless
   CUDA_TRY(cudaEventRecord(e.ev_snap_main[k], e.stream));
   // noise-less cost / flag: after the noise-less rollout, which runs on the tail stream when iterations overlap
   cudaStream_t ts = e.tail_dirty ? e.tail_stream : e.stream;
+  if (e.extra_dirty) CUDA_TRY(cudaStreamWaitEvent(ts, e.ev_extra, 0));   // k_extra_total ran beside the tail stream
   if (noiseless_cost) CUDA_TRY(cudaMemcpyAsync(e.snap_cost[k].p, e.noiseless_sum.p, size_t(e.B) * 8, cudaMemcpyDeviceToDevice, ts));
   if (noiseless_collision_free)
     CUDA_TRY(cudaMemcpy2DAsync(e.snap_flag[k].p, 4, e.collision_free.p + e.R, size_t(e.R + 1) * 4, 4, e.B, cudaMemcpyDeviceToDevice, ts));

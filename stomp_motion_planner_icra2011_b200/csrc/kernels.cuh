@@ -214,6 +214,8 @@ struct SelectGatherArgs {
   const double* theta;         // [B][D][N]
   const double* state_prev;    // [B][R][N]
   const double* extra_state;   // [B][N]
+  const double* extra_control; // [B][D][N] or nullptr.  Given: the noise-less rollout's total (candidate R) is summed here, exactly
+                               // as k_extra_total sums it, and totals[R] is not read — k_extra_total then runs beside this kernel
   double* noise;               // [B][R][D][N]
   double* control;
   double* params;
@@ -223,15 +225,36 @@ struct SelectGatherArgs {
 
 __global__ void __launch_bounds__(128) k_select_gather(SelectGatherArgs a) {
   __shared__ int s_src;
+  __shared__ double s_extra, sred[4], sred2[4];
   const int R = a.R, b = blockIdx.x / a.R_reuse, j = blockIdx.x - b * a.R_reuse;
   const double* tot = a.totals + size_t(b) * (R + 1);
   const int n = R + (a.use_extra ? 1 : 0);
+  const bool own_extra = a.use_extra && a.extra_control != nullptr;
+  if (own_extra) {     // k_extra_total's sum, operation for operation (128 threads): same bits as totals[R] will hold
+    double acc = 0.0, accs = 0.0;
+    for (int t = threadIdx.x; t < a.N; t += blockDim.x) accs += a.extra_state[size_t(b) * a.N + t];
+    for (int i = threadIdx.x; i < a.D * a.N; i += blockDim.x) acc += a.extra_control[size_t(b) * a.D * a.N + i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      accs += __shfl_xor_sync(0xffffffffu, accs, off);
+    }
+    if ((threadIdx.x & 31) == 0) { sred[threadIdx.x >> 5] = acc; sred2[threadIdx.x >> 5] = accs; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int w = 0; w < int(blockDim.x >> 5); ++w) s1 += sred[w], s2 += sred2[w];
+      s_extra = s2 + s1;
+    }
+    __syncthreads();
+  }
+  auto total_of = [&](int i) -> double { return (own_extra && i == R) ? s_extra : tot[i]; };
   for (int i = threadIdx.x; i < n; i += blockDim.x) {     // the ranking of k_select_reuse
-    const double ci = tot[i];
+    const double ci = total_of(i);
     const int ii = (i == R) ? -1 : i;
     int rank = 0;
     for (int k = 0; k < n; ++k) {
-      const double ck = tot[k];
+      const double ck = total_of(k);
       const int kk = (k == R) ? -1 : k;
       rank += (ck < ci) || (ck == ci && kk < ii);
     }
@@ -269,6 +292,7 @@ __global__ void k_advance_iteration(uint32_t* __restrict__ generation, int* __re
   }
 }
 
+constexpr int kMaxScaleArgs = 32;
 struct GenArgs {
   int B, R, D, N;
   int R_gen;                 // slots < R_gen are new, slots >= R_gen are reused (gathered)
@@ -291,6 +315,8 @@ struct GenArgs {
   const double* pad_start;   // [B][D]
   const double* pad_goal;    // [B][D]
   const double* noise_scale; // [D] sigma_d * decay_d^(it-1)
+  int scale_by_value;        // 1: the scales travel in scale_v (D <= kMaxScaleArgs) — no upload on the launching stream
+  double scale_v[32];
   const double* eps_in;      // [B][R][D][N] injected noise (or caller noise when !mode_project)
   const double* params_prev; // [B][prev_stride][D][N] previous-iteration parameters (reuse gather)
   // k_generate_seg: the band solves split over `segs` time segments per vector (spike tables, engine.cu)
@@ -310,6 +336,10 @@ struct GenArgs {
   Band band;
   Stencil st;
 };
+
+// the noise scale of dimension d: from the launch arguments (constant bank) or from the device array
+__device__ __forceinline__ double gen_noise_scale(const GenArgs& a, int d) { return a.scale_by_value ? a.scale_v[d] : a.noise_scale[d]; }
+
 
 // Banded triangular solves with R = C C^T.  The tables hold, per row, the inverse diagonal and the six
 // sub-diagonal coefficients already multiplied by it (zero beyond the bandwidth), so one step is
@@ -511,7 +541,7 @@ __global__ void __launch_bounds__(128, STOMP_GEN_MIN_BLOCKS) k_generate(GenArgs 
     }
     double* out_noise = active ? a.noise + row_off : nullptr;
     double* out_params = active ? a.params + row_off : nullptr;
-    const double sg = active ? a.noise_scale[d] : 0.0;
+    const double sg = active ? gen_noise_scale(a, d) : 0.0;
     const uint64_t stream = (uint64_t(b) * uint64_t(a.rollouts_global) + uint64_t(a.rollout_id_offset + r)) * uint64_t(a.D) + d;
     const uint32_t gen_iteration = a.iteration_ptr ? *a.iteration_ptr : a.iteration;
     BandWindow bw;
@@ -857,7 +887,7 @@ __global__ void __launch_bounds__(256, STOMP_SEG_MIN_BLOCKS) k_generate_seg(GenA
     }
     double* out_noise = active ? a.noise + row_off : nullptr;
     double* out_params = active ? a.params + row_off : nullptr;
-    const double sg = active ? a.noise_scale[d] : 0.0;
+    const double sg = active ? gen_noise_scale(a, d) : 0.0;
     BandWindow fwd;
     for (int c0 = s0; c0 < s1; c0 += kChunk) {
       const int len = min(kChunk, s1 - c0);
@@ -1097,7 +1127,7 @@ __global__ void __launch_bounds__(128) k_generate_dense(GenArgs a, const double*
       if (2 * pr + 1 < N) z[2 * pr + 1] = z1;
     }
     __syncthreads();
-    const double sg = a.noise_scale[d];
+    const double sg = gen_noise_scale(a, d);
     for (int t = threadIdx.x; t < N; t += blockDim.x) {
       double a0 = 0.0, a1 = 0.0;
       int j = t;
@@ -1356,7 +1386,7 @@ __global__ void __launch_bounds__(128) k_generate_mma(GenArgs a, const double* _
         src = sidx >= 0 ? a.params_prev + ((size_t(b) * a.prev_stride + sidx) * a.D + d) * N : a.theta + (size_t(b) * a.D + d) * N;
       }
       s_src[vl] = src;
-      s_sg[vl] = a.noise_scale[d];
+      s_sg[vl] = gen_noise_scale(a, d);
       s_ps[vl] = a.pad_start[size_t(b) * a.D + d];
       s_pg[vl] = a.pad_goal[size_t(b) * a.D + d];
       s_stream[vl] = (uint64_t(b) * uint64_t(a.rollouts_global) + uint64_t(a.rollout_id_offset + r)) * uint64_t(a.D) + d;
