@@ -143,6 +143,7 @@ struct Engine {
   DevBuf<int> cand_map;
   std::vector<double> scale_host, pre_scale_host;      // noise scales of this / the look-ahead iteration (launch arguments)
   std::map<const void*, size_t> smem_optin;
+  int update_dpc = 0;              // A/B (STOMP_UPDATE_DPC)
   bool scales_in_args = false;     // A/B switch (STOMP_SCALES_IN_ARGS=1): measured slower, see set_noise_scale
   bool cand_valid = false, cand_dirty = false;
   // small batches: k_extra_total (and optimize's k_track_best) run on cand_stream beside the tail stream's chain
@@ -785,7 +786,7 @@ int launch_update(Engine& e, int apply, bool fuse_extra_control) {
   };
   // enough CTAs to fill the machine twice when the batch allows it; otherwise one dimension per CTA
   int dpc = int(std::min<long long>(std::min(e.D, 32), std::max<long long>(1, (long long)e.B * e.D / 296)));
-  if (const char* ov = getenv("STOMP_UPDATE_DPC")) dpc = std::max(1, std::min(e.D, atoi(ov)));   // A/B: dimensions per CTA
+  if (e.update_dpc > 0) dpc = std::max(1, std::min(e.D, e.update_dpc));   // A/B (STOMP_UPDATE_DPC): dimensions per CTA
   size_t smem = update_smem(dpc);
   while (smem > 200 * 1024 && dpc > 1) smem = update_smem(--dpc);
   a.dims_per_cta = dpc;
@@ -929,7 +930,7 @@ int launch_generate_range(Engine& e, const RolloutPlan& p, int r_begin, int r_co
     a.theta = nullptr; a.params = nullptr; a.control = nullptr; a.params_prev = nullptr; a.reuse_src = nullptr; a.eps_in = nullptr;
     a.noise = e.pre_noise.p; a.noise_projected = e.pre_y.p;
     a.noise_scale = e.pre_scale.p;
-    if (e.scales_in_args && e.D <= kMaxScaleArgs && int(e.pre_scale_host.size()) == e.D) {
+    if (e.D <= kMaxScaleArgs && int(e.pre_scale_host.size()) == e.D) {     // (off the chain: no pacing effect, one API call less)
       a.scale_by_value = 1;
       for (int d = 0; d < e.D; ++d) a.scale_v[d] = e.pre_scale_host[d];
     } else {
@@ -1109,7 +1110,7 @@ int launch_lookahead(Engine& e, int next_iteration) {
   for (int d = 0; d < e.D; ++d) scale[d] = e.noise_stddev[d] * std::pow(e.noise_decay[d], next_iteration - 1);
   CUDA_TRY(cudaStreamWaitEvent(e.pre_stream, e.ev_fin, 0));
   e.pre_scale_host = scale;
-  if (!e.scales_in_args || e.D > kMaxScaleArgs)
+  if (e.D > kMaxScaleArgs)
     CUDA_TRY(cudaMemcpyAsync(e.pre_scale.p, scale.data(), size_t(e.D) * 8, cudaMemcpyHostToDevice, e.pre_stream));
   RolloutPlan np;
   e.ws = e.pre_stream;
@@ -1752,6 +1753,7 @@ int stomp_engine_create(const stomp_engine_desc* desc, void** out_engine) {
   e.direct_update = !(getenv("STOMP_NO_DIRECT_UPDATE") && atoi(getenv("STOMP_NO_DIRECT_UPDATE")) != 0);
   e.lookahead = !(getenv("STOMP_NO_LOOKAHEAD") && atoi(getenv("STOMP_NO_LOOKAHEAD")) != 0);
   e.scales_in_args = getenv("STOMP_SCALES_IN_ARGS") && atoi(getenv("STOMP_SCALES_IN_ARGS")) != 0;
+  if (const char* ov = getenv("STOMP_UPDATE_DPC")) e.update_dpc = atoi(ov);
   e.offchain_extra = !(getenv("STOMP_NO_OFFCHAIN_EXTRA") && atoi(getenv("STOMP_NO_OFFCHAIN_EXTRA")) != 0);
   e.use_totals_kernel = !(getenv("STOMP_NO_TOTALS_KERNEL") && atoi(getenv("STOMP_NO_TOTALS_KERNEL")) != 0);
   if (const char* cp = getenv("STOMP_CUM_PLACEMENT")) e.cum_placement = !strcmp(cp, "chain") ? 1 : !strcmp(cp, "late") ? 2 : 0;
