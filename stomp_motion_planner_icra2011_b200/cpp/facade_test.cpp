@@ -173,6 +173,18 @@ int main() {
     torso.type = STOMP_BODY_CYLINDER; torso.dimensions[0] = 0.1; torso.dimensions[1] = 0.6;
     torso.position[0] = -0.5; torso.position[2] = 0.3; torso.orientation[3] = 1.0; torso.scale = 1.0; torso.padding = 0.01;
     built.bodies.push_back(torso);
+    // a mesh collision object (bodies::ConvexMesh = the hull of its vertices): a cube given by its corners and one interior vertex
+    std::vector<double> cube;
+    for (int sx = -1; sx <= 1; sx += 2)
+      for (int sy = -1; sy <= 1; sy += 2)
+        for (int sz = -1; sz <= 1; sz += 2) { cube.push_back(0.1 * sx); cube.push_back(0.1 * sy); cube.push_back(0.1 * sz); }
+    cube.push_back(0.01); cube.push_back(0.02); cube.push_back(-0.03);
+    stomp_mesh_body mesh;
+    std::memset(&mesh, 0, sizeof(mesh));
+    mesh.vertices = cube.data(); mesh.num_vertices = int32_t(cube.size() / 3);
+    mesh.position[0] = -0.452; mesh.position[1] = 0.601; mesh.position[2] = 1.003; mesh.orientation[3] = 1.0;
+    mesh.scale = 1.0; mesh.padding = 0.0;
+    built.meshes.push_back(mesh);
     auto dev = std::make_shared<StompOptimizer>(start, goal, &robot, &params, &built);
     if (!dev->ok()) { std::printf("FAIL device-built field: %s\n", lastError()); return 1; }
     int32_t dims[3] = {0, 0, 0}, vt = -1;
@@ -185,6 +197,8 @@ int main() {
       return vox[(size_t(std::lround((x + 0.9) / 0.03)) * 60 + size_t(std::lround((y + 0.9) / 0.03))) * 60 + size_t(std::lround((z + 0.2) / 0.03))];
     };
     if (cell(0.55, 0.0, 0.55) != 0 || cell(-0.5, 0.0, 0.3) != 0 || cell(0.0, 0.6, 1.2) != 144) { std::printf("FAIL field contents\n"); return 1; }
+    // inside the mesh cube, and one cell beyond its +x face (the face is at x = -0.352: the next lattice cell is 1 away)
+    if (cell(-0.45, 0.6, 1.0) != 0 || cell(-0.45 + 0.15, 0.6, 1.0) == 0) { std::printf("FAIL mesh body in the field\n"); return 1; }
     STOMPStatistics st2;
     if (!dev->optimize(&st2) || !(st2.best_cost <= st2.costs.front())) { std::printf("FAIL optimize on the device-built field\n"); return 1; }
   }
