@@ -1235,9 +1235,17 @@ int iterate_serial(Engine& e, int iteration_number) {
 // REUSED rollout slots of iteration i+1 (gather, M*eps, control costs) only matter to iteration i+1's statistics, not to its
 // new rollouts: they run on the tail stream while the main stream already samples and costs the new rollouts of
 // iteration i+1.  (A caller that reads the statistics after every iteration synchronises both and sees no overlap.)
-//   main: [k_generate(new) -> k_cost(new) -> k_cumulative(new)] -> wait(tail) -> k_update              -> record(upd)
-//   tail: [k_select_reuse -> k_generate(reused) -> k_gather_state -> k_cumulative(reused)] record(tail)
+//   main: [k_generate(new) -> k_cost(new) -> k_totals(new)] -> wait(tail) -> k_update                  -> record(upd)
+//   tail: [k_select_reuse -> k_generate(reused) -> k_gather_state -> k_totals(reused)] record(tail)
 //         ... wait(upd) -> k_cost(noise-less) -> k_extra_total
+// (k_cumulative in place of k_totals with cumulative costs, taps, or a generation kernel that leaves no per-vector sums.)
+// Small batches run the latency schedule on four streams instead:
+//   main: wait(pre) -> k_finish_rollouts(new) -> k_cost(new) -> wait(tail) -> k_update                 -> record(upd)
+//   tail: wait(upd) -> k_cost(noise-less) -> wait(cand) -> k_select_gather -> record(tail); wait(cost) -> k_cumulative
+//   pre : wait(finish) -> k_generate_ahead(new slots of the next iteration)                           -> record(pre)
+//   cand: wait(upd) -> k_generate(candidates) -> record(cand); wait(noise-less cost) -> k_extra_total [-> k_track_best]
+// Every speculative piece (look-ahead pass, candidate pass) is keyed by generation / iteration number / configuration epoch
+// and falls back to the one-pass kernels when the next call is not the one it was prepared for.
 int iterate_once(Engine& e, int iteration_number) {
   if (e.huge_path()) {
     if (e.B != 1) return fail("the sharded / huge-rollout statistics path supports num_problems == 1 only");
@@ -1258,8 +1266,7 @@ int iterate_once(Engine& e, int iteration_number) {
   e.control_cost_weight = e.desc.smoothness_cost_weight;
   RolloutPlan p;
   plan_rollouts(e, p);
-  // k_update reads S and C itself (launch_update): k_cumulative leaves the main stream's chain
-  // direct k_update, large batch: k_cumulative either stays where it was (lean: totals only) or follows k_update on the tail
+  // direct k_update (it adds S + C itself): the totals either stay where k_cumulative was (lean) or follow k_update on the tail
   const bool direct = !e.huge_path() && e.direct_now();
   // (measured, same box: C2 old schedule 0.4652 ms, lean k_cumulative on the chain 0.4611, after the update 0.4672; C4 2.107 /
   //  2.093 / 2.007 — with 420 spheres and 200 timesteps per rollout the cost kernels dwarf the generation it then overlaps)
