@@ -1064,7 +1064,7 @@ int launch_select_gather(Engine& e) {
   a.noise = e.noise.p; a.control = e.control[e.cur].p; a.params = e.params[e.cur].p; a.noise_projected = e.noise_projected.p;
   a.state = e.state[e.cur].p;
   begin_launch(e);
-  k_select_gather<<<unsigned(e.B) * e.Rre, 128, 0, e.ws>>>(a);
+  k_select_gather<<<unsigned(e.B) * e.Rre, kSelectGatherThreads, 0, e.ws>>>(a);
   if (check_launch(e, "k_select_gather")) return 1;
   e.extra_added = false;
   return 0;

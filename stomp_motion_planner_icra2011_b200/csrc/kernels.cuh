@@ -223,7 +223,11 @@ struct SelectGatherArgs {
   double* state;               // [B][R][N]
 };
 
-__global__ void __launch_bounds__(128) k_select_gather(SelectGatherArgs a) {
+// (512 threads: the copies are a chain of dependent round trips per thread, so more threads = fewer trips; the sum of the
+// noise-less rollout's total keeps k_extra_total's shape — 128 threads, stride 128, warp trees, four warps in order — with the
+// loads of a thread issued together)
+constexpr int kSelectGatherThreads = 512;
+__global__ void __launch_bounds__(kSelectGatherThreads) k_select_gather(SelectGatherArgs a) {
   __shared__ int s_src;
   __shared__ double s_extra, sred[4], sred2[4];
   const int R = a.R, b = blockIdx.x / a.R_reuse, j = blockIdx.x - b * a.R_reuse;
@@ -231,19 +235,40 @@ __global__ void __launch_bounds__(128) k_select_gather(SelectGatherArgs a) {
   const int n = R + (a.use_extra ? 1 : 0);
   const bool own_extra = a.use_extra && a.extra_control != nullptr;
   if (own_extra) {     // k_extra_total's sum, operation for operation (128 threads): same bits as totals[R] will hold
-    double acc = 0.0, accs = 0.0;
-    for (int t = threadIdx.x; t < a.N; t += blockDim.x) accs += a.extra_state[size_t(b) * a.N + t];
-    for (int i = threadIdx.x; i < a.D * a.N; i += blockDim.x) acc += a.extra_control[size_t(b) * a.D * a.N + i];
+    if (threadIdx.x < 128) {
+      double acc = 0.0, accs = 0.0;
+      const double* xs = a.extra_state + size_t(b) * a.N;
+      const double* xc = a.extra_control + size_t(b) * a.D * a.N;
+      const int DNx = a.D * a.N;
+      if (DNx <= 8 * 128 && a.N <= 8 * 128) {
+        double v[8], w[8];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      acc += __shfl_xor_sync(0xffffffffu, acc, off);
-      accs += __shfl_xor_sync(0xffffffffu, accs, off);
+        for (int q = 0; q < 8; ++q) {
+          const int i = threadIdx.x + q * 128;
+          v[q] = i < DNx ? xc[i] : 0.0;
+          w[q] = i < a.N ? xs[i] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int i = threadIdx.x + q * 128;
+          if (i < a.N) accs += w[q];
+          if (i < DNx) acc += v[q];
+        }
+      } else {
+        for (int t = threadIdx.x; t < a.N; t += 128) accs += xs[t];
+        for (int i = threadIdx.x; i < DNx; i += 128) acc += xc[i];
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        accs += __shfl_xor_sync(0xffffffffu, accs, off);
+      }
+      if ((threadIdx.x & 31) == 0) { sred[threadIdx.x >> 5] = acc; sred2[threadIdx.x >> 5] = accs; }
     }
-    if ((threadIdx.x & 31) == 0) { sred[threadIdx.x >> 5] = acc; sred2[threadIdx.x >> 5] = accs; }
     __syncthreads();
     if (threadIdx.x == 0) {
       double s1 = 0.0, s2 = 0.0;
-      for (int w = 0; w < int(blockDim.x >> 5); ++w) s1 += sred[w], s2 += sred2[w];
+      for (int w = 0; w < 4; ++w) s1 += sred[w], s2 += sred2[w];
       s_extra = s2 + s1;
     }
     __syncthreads();
